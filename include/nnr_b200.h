@@ -1,0 +1,213 @@
+/* nnr_b200 -- C ABI of the B200-native CNE+SUE hot path.
+ *
+ * Every entry point is a plain `extern "C"` function over raw DEVICE pointers, sizes and a
+ * `cudaStream_t` (passed as void*).  No torch types cross this boundary.  The reference
+ * (Veason-silverbullet/NNR) is pure PyTorch, so what each function replaces is a span of
+ * library calls in the reference's Python; the span is cited as file:line next to each entry.
+ *
+ * Conventions
+ *   - return 0 on success, a negative NNR_ERR_* on argument / alignment / workspace errors, a
+ *     positive cudaError_t when a launch fails; `nnr_last_error()` returns a thread-local message.
+ *   - the caller owns every buffer (inputs, outputs, stashes, workspaces); the library never
+ *     allocates, frees or retains a pointer beyond the call; outputs are fully overwritten
+ *     unless the argument is called `accumulate`.
+ *   - launches go only to the passed stream; entry points are re-entrant.
+ *   - fp32 everywhere unless the name says otherwise; token ids int32; masks uint8 (torch.bool).
+ *
+ * Token layout.  A CNE call sees N news rows with up to L tokens each.  `nnr_seq_prepare` turns
+ * the [N,L] prefix mask into len[N], off[N+1] (exclusive prefix sum) and tok_row[N*L]; every
+ * per-token tensor is then PACKED: the token t of row r lives at row off[r]+t of a
+ * [N*L (capacity), dim] matrix, and off[N] is the number of valid tokens (read on the device, so
+ * no host synchronisation is needed).
+ */
+#ifndef NNR_B200_H
+#define NNR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNR_ABI_VERSION 1
+
+const char* nnr_last_error(void);
+int nnr_abi_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t nnr_launch_count(void);
+
+/* ---- sequence bookkeeping: newsEncoders.py:106-111 (mask[:,0]=1 in place, lengths) ---------- */
+int nnr_seq_prepare(uint8_t* mask, int N, int L, int32_t* len, int32_t* off, int32_t* tok_row,
+                    void* stream);
+
+/* ---- word-embedding gather + dropout: newsEncoders.py:117-118 (nn.Embedding + nn.Dropout) ---
+ * out[off[r]+t, :] = table[ids[r,t], :] * keep(seed, (r*L+t)*E+e) / (1-p)                       */
+int nnr_embed_gather_fwd(const float* table, const int32_t* ids, const int32_t* len,
+                         const int32_t* off, int N, int L, int E, int V, float* out, float p_drop,
+                         uint64_t seed, void* stream);
+/* autograd of the above (ATen embedding_dense_backward): deterministic sort-by-id + segment
+ * reduce into the dense [V,E] table gradient.  `dout` is packed [tokens,E].                      */
+size_t nnr_embed_gather_bwd_workspace_bytes(int N, int L);
+int nnr_embed_gather_bwd(const float* dout, const int32_t* ids, const int32_t* len,
+                         const int32_t* off, int N, int L, int E, int V, float p_drop,
+                         uint64_t seed, float* dtable, int accumulate, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ---- GEMM with fused epilogues: every nn.Linear on the path (newsEncoders.py:122-129,
+ *      layers.py:168,197,286; userEncoders.py:85-86,91) and their autograd ----------------------
+ * C[M,N] = epi( op(A)[M,K] * op(B)[K,N] ),  op(A)[m,k] = transA ? A[k*lda+m] : A[m*lda+k],
+ *                                           op(B)[k,n] = transB ? B[n*ldb+k] : B[k*ldb+n].       */
+enum {
+  NNR_EPI_NONE = 0,          /* C = acc                                                         */
+  NNR_EPI_BIAS = 1,          /* C = acc + bias[n]                                               */
+  NNR_EPI_BIAS_TANH = 2,     /* C = tanh(acc + bias[n])                                         */
+  NNR_EPI_BIAS_RELU_RES = 3, /* r = relu(acc+bias[n]); aux_out = r; C = (r + aux[m,n]) * drop   */
+  NNR_EPI_GATE = 4,          /* g = sigmoid(acc + rowbias[rowmap[m], n]); aux_out = g; C = aux*g */
+  NNR_EPI_ADD_AUX = 5        /* C = acc + aux[m,n]                                              */
+};
+enum {
+  NNR_GEMM_AUTO = 0,
+  NNR_GEMM_SIMT_FP32 = 1,    /* exact fp32 FFMA tiles                                           */
+  NNR_GEMM_TC_TF32X3 = 2,    /* tcgen05 kind::tf32, hi/lo split (3 MMAs), fp32-grade accuracy   */
+  NNR_GEMM_TC_BF16 = 3       /* tcgen05 kind::f16 bf16 operands, fp32 accumulate                */
+};
+typedef struct {
+  const float* A; int64_t lda; int32_t transA;
+  const float* B; int64_t ldb; int32_t transB;
+  float* C; int64_t ldc;
+  int32_t M, N, K;
+  const int32_t* m_dev;      /* optional device scalar: rows >= *m_dev are skipped             */
+  const int32_t* k_dev;      /* optional device scalar: contraction stops at *k_dev            */
+  int32_t epilogue;
+  int32_t accumulate;        /* C += epi(...) instead of C = epi(...)                          */
+  const float* bias;
+  const float* aux; int64_t ldaux;
+  float* aux_out; int64_t ldaux_out;
+  const float* rowbias; int64_t ldrowbias; const int32_t* rowmap;
+  float p_drop; uint64_t seed;
+  int32_t algo;
+  void* workspace; size_t workspace_bytes;   /* split-K partials (see nnr_gemm_workspace_bytes) */
+} nnr_gemm_args;
+size_t nnr_gemm_workspace_bytes(const nnr_gemm_args* args);
+int nnr_gemm(const nnr_gemm_args* args, void* stream);
+
+/* column sums: out[n] (+)= sum_m X[m,n]   (bias gradients; deterministic two-stage)            */
+size_t nnr_colsum_workspace_bytes(int M, int N);
+int nnr_colsum(const float* X, int64_t ldx, int M, int N, const int32_t* m_dev, float* out,
+               int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+/* per-row (segment) column sums over packed tokens: out[r,:] = sum_t X[off[r]+t,:]              */
+int nnr_segment_colsum(const float* X, int64_t ldx, const int32_t* off, int N, int D, float* out,
+                       int64_t ldo, void* stream);
+
+/* ---- bidirectional LSTM recurrence: nn.LSTM at newsEncoders.py:66-67,122-127 ----------------
+ * Persistent thread-block-cluster kernel; W_hh stays in shared memory for all time steps.
+ *   gx      [tokens, 2, 4H]  in: x_t W_ih^T + b_ih + b_hh (gate order i,f,g,o per direction)
+ *                            out: the activated gates (stash for the backward pass)
+ *   w_hh    [2, 4H, H]       forward / reverse recurrent weights
+ *   order   [N]              rows sorted by length, longest first (tile homogeneity only)
+ *   h_out   [tokens, 2H]     h_t, forward | reverse
+ *   c_stash [tokens, 2, H]   c_t for the backward pass
+ *   c_n     [N, 2H]          final cell state per row (forward | reverse)  (newsEncoders.py:124) */
+int nnr_lstm_fwd(float* gx, const float* w_hh, const int32_t* len, const int32_t* off,
+                 const int32_t* order, int N, int L, int H, float* h_out, float* c_stash,
+                 float* c_n, void* stream);
+/* BPTT.  gates (the stash written by nnr_lstm_fwd) is overwritten IN PLACE with dL/d(pre-
+ * activation) = dL/d(gx).  dh [tokens,2H] and dcn [N,2H] are the upstream gradients.            */
+int nnr_lstm_bwd(float* gates, const float* c_stash, const float* w_hh, const int32_t* len,
+                 const int32_t* off, const int32_t* order, int N, int L, int H, const float* dh,
+                 const float* dcn, void* stream);
+/* hprev[p, 0:H] = h[p-1, 0:H] (0 at t=0); hprev[p, H:2H] = h[p+1, H:2H] (0 at t=len-1): the
+ * recurrent input of every step, needed for dW_hh = dgates^T hprev.                             */
+int nnr_lstm_shift_h(const float* h, const int32_t* len, const int32_t* off,
+                     const int32_t* tok_row, int N, int L, int H, float* hprev, void* stream);
+/* dz = dhg*h*g*(1-g), dh0 = dhg*g : elementwise part of the selective-gate backward
+ * (newsEncoders.py:128-131)                                                                     */
+int nnr_gate_bwd_pre(const float* dhg, const float* h, const float* g, int64_t n_max,
+                     const int32_t* n_dev, int D, float* dz, float* dh0, void* stream);
+
+/* ---- fused masked attention pooling over segments: layers.py:167-175 and :196-203 -----------
+ * Segment s covers rows [seg_off[s], seg_off[s+1]) of X (or s*fixed_len.. when seg_off == NULL).
+ *   mode 0 (additive):    score[p] = dot(U[p,:A], w2)            U = tanh(W1 x + b1) precomputed
+ *   mode 1 (scaled dot):  score[p] = scale * dot(X[p,:], qvec[s,:])   qvec = K^T (Q q + b) folded
+ * mask (optional, per row of X): 0 -> score = -1e9.  Outputs pooled[S,D], alpha[rows].          */
+typedef struct {
+  const float* X; int64_t ldx; int32_t D;
+  const int32_t* seg_off; int32_t S; int32_t fixed_len; int32_t max_len;
+  int32_t mode;
+  const float* U; int64_t ldu; int32_t A; const float* w2;
+  const float* qvec; int64_t ldq; float scale;
+  const uint8_t* mask;
+  float* pooled; int64_t ldp;
+  float* alpha;
+  /* backward only */
+  const float* dpooled; int64_t lddp;
+  float* dX; int64_t lddx; int32_t accumulate_dx;
+  float* dU; int64_t lddu;        /* mode 0: dL/d(pre-tanh) = da * w2 * (1 - U^2)               */
+  float* dw2_partial;             /* mode 0: [S, A] per-segment partials (reduce with colsum)   */
+  float* dqvec; int64_t lddq;     /* mode 1: [S, D]                                              */
+} nnr_pool_args;
+int nnr_attn_pool_fwd(const nnr_pool_args* args, void* stream);
+int nnr_attn_pool_bwd(const nnr_pool_args* args, void* stream);
+
+/* ---- news vector assembly: newsEncoders.py:50-54,138 ----------------------------------------
+ * out[r] = [ts+tc | cs+cc | drop(cat_table[cat[r]]) | drop(sub_table[sub[r]])]                  */
+int nnr_news_fuse_fwd(const float* t_self, const float* t_cross, const float* c_self,
+                      const float* c_cross, const float* cat_table, const float* sub_table,
+                      const int32_t* cat, const int32_t* sub, int N, int D2, int Ec, int Es,
+                      float p_drop, uint64_t seed, float* out, void* stream);
+/* backward: d_a[N,D2] = dout[:, :D2], d_b[N,D2] = dout[:, D2:2*D2]; dense table grads
+ * (deterministic: one block per table row scanning the N rows in order).                        */
+int nnr_news_fuse_bwd(const float* dout, const int32_t* cat, const int32_t* sub, int N, int D2,
+                      int Ec, int Es, int n_cat, int n_sub, float p_drop, uint64_t seed,
+                      float* d_a, float* d_b, float* dcat_table, float* dsub_table,
+                      int accumulate, void* stream);
+
+/* ---- SUE graph: MIND_corpus.py:162-216 (structure), layers.py:286 (aggregation) --------------
+ * Build graph / mask / cluster indices on the device from per-slot categories (bit-exact with
+ * the reference's numpy: fp32 1/deg, sqrt, two roundings).  Any output pointer may be NULL.     */
+int nnr_sue_graph_build(const int32_t* categories, const int32_t* history_len, int B, int H,
+                        int C, float* graph, uint8_t* category_mask, int64_t* category_indices,
+                        void* stream);
+/* Dense (caller-supplied) graph -> per-row compressed neighbour lists (row-compressed with a fixed
+ * row capacity of G entries).  transpose=1 emits the lists of A^T (for the backward pass).
+ * nnz [B*G], col/val [B*G, G]; entries of a row are in ascending column order.                  */
+int nnr_graph_to_csr(const float* graph, int B, int G, int transpose, int32_t* nnz, int32_t* col,
+                     float* val, void* stream);
+/* out[b,i,:] = sum_{e < nnz[b,i]} val[b,i,e] * x[b,col[b,i,e],:]   (fixed order: deterministic) */
+int nnr_gcn_aggregate(const int32_t* nnz, const int32_t* col, const float* val, const float* x,
+                      int B, int G, int D, float* out, void* stream);
+
+/* ---- intra-cluster attention: userEncoders.py:85-89 (torch_scatter softmax + sum) -----------
+ *   Kp [B,H,Au], Qp [B,n,Au], g [B,H,D], idx [B,H] int64 in [0,C1)
+ *   alpha[b,k,h] = segment_softmax_h( Kp[b,h].Qp[b,k] * scale ; idx[b,h] )
+ *   intra[b,k,c,:] = sum_{h: idx=c} alpha[b,k,h] g[b,h,:]   (ascending h: deterministic)        */
+int nnr_cluster_intra_fwd(const float* Kp, const float* Qp, const float* g, const int64_t* idx,
+                          int B, int n, int H, int Au, int D, int C1, float scale, float* alpha,
+                          float* intra, void* stream);
+int nnr_cluster_intra_bwd(const float* dintra, const float* Kp, const float* Qp, const float* g,
+                          const int64_t* idx, const float* alpha, int B, int n, int H, int Au,
+                          int D, int C1, float scale, float* da_ws /* [B,n,H] scratch */,
+                          float* dKp, float* dQp, float* dg, int accumulate_dg, void* stream);
+
+/* ---- click predictor: model.py:127 ---------------------------------------------------------- */
+int nnr_rowdot_fwd(const float* a, const float* b, int R, int D, float* out, void* stream);
+/* da = dout[r]*b (+= if accumulate_a), db likewise */
+int nnr_rowdot_bwd(const float* dout, const float* a, const float* b, int R, int D, float* da,
+                   int accumulate_a, float* db, int accumulate_b, void* stream);
+
+/* elementwise dropout with the library's counter RNG (proxy nodes / cluster features /
+ * GCN inter-layer dropout): y = x * keep(seed, i)/(1-p); the same call applies the backward.   */
+int nnr_dropout(const float* x, int64_t n, float p_drop, uint64_t seed, float* y, void* stream);
+
+/* ---- optimizer: trainer.py:118-120 (clip_grad_norm_(4) + Adam) over one flat buffer ---------
+ * norm_out[0] receives the pre-clip global L2 norm.  step is 1-based.                           */
+size_t nnr_flat_clip_adam_workspace_bytes(int64_t n);
+int nnr_flat_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                       int64_t n, float lr, float beta1, float beta2, float eps, float max_norm,
+                       float grad_scale, int32_t step, float* norm_out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNR_B200_H */

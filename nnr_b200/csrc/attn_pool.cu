@@ -1,0 +1,161 @@
+// Fused masked attention pooling over segments (scores -> masked softmax -> weighted sum in one
+// kernel), forward and backward.  Replaces the chain of Linear/tanh/masked_fill/softmax/bmm calls of
+// layers.py:167-175 (Attention) and layers.py:196-203 (ScaledDotProduct_CandidateAttention).
+//
+// One CTA per segment (a news item's tokens, or the 19 clusters of one (user, candidate) pair).
+// The feature rows of the segment are read once for the scores and once for the weighted sum
+// (second read is an L2 hit: a segment is <= 128 x 1.6 KB); HBM-bound by design.
+//   mode 0: score = w2 . U[p]                 (U = tanh(W1 x + b1) produced by nnr_gemm's epilogue)
+//   mode 1: score = scale * X[p] . qvec[s]    (K folded onto the query: (K x).(q) == x.(K^T q))
+#include "common.cuh"
+#include "../../include/nnr_b200.h"
+
+#define POOL_THREADS 128
+
+__global__ void __launch_bounds__(POOL_THREADS) attn_pool_fwd_kernel(nnr_pool_args a) {
+  extern __shared__ float sc[];  // [max_len]
+  __shared__ float red[POOL_THREADS / 32];
+  const int s = blockIdx.x;
+  const int beg = a.seg_off ? a.seg_off[s] : s * a.fixed_len;
+  const int n = a.seg_off ? (a.seg_off[s + 1] - beg) : a.fixed_len;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = POOL_THREADS / 32;
+  for (int t = w; t < n; t += nw) {
+    const size_t p = (size_t)beg + t;
+    float v = 0.f;
+    if (a.mode == 0) {
+      const float* u = a.U + p * a.ldu;
+      for (int k = lane; k < a.A; k += 32) v += u[k] * a.w2[k];
+    } else {
+      const float* x = a.X + p * a.ldx;
+      const float* q = a.qvec + (size_t)s * a.ldq;
+      for (int d = lane; d < a.D; d += 32) v += x[d] * q[d];
+    }
+    v = warp_sum(v);
+    if (a.mode == 1) v *= a.scale;
+    if (a.mask && a.mask[p] == 0) v = -1e9f;
+    if (lane == 0) sc[t] = v;
+  }
+  __syncthreads();
+  // softmax over the segment
+  float m = -INFINITY;
+  for (int t = tid; t < n; t += POOL_THREADS) m = fmaxf(m, sc[t]);
+  m = warp_max(m);
+  if (lane == 0) red[w] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < nw; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int t = tid; t < n; t += POOL_THREADS) { float e = expf(sc[t] - m); sc[t] = e; sum += e; }
+  sum = warp_sum(sum);
+  if (lane == 0) red[w] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < nw; ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  for (int t = tid; t < n; t += POOL_THREADS) {
+    float al = sc[t] * inv;
+    sc[t] = al;
+    if (a.alpha) a.alpha[(size_t)beg + t] = al;
+  }
+  __syncthreads();
+  for (int d = tid; d < a.D; d += POOL_THREADS) {
+    float acc = 0.f;
+    const float* x = a.X + (size_t)beg * a.ldx + d;
+    for (int t = 0; t < n; ++t) acc += sc[t] * x[(size_t)t * a.ldx];
+    a.pooled[(size_t)s * a.ldp + d] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(POOL_THREADS) attn_pool_bwd_kernel(nnr_pool_args a) {
+  extern __shared__ float sm[];  // [2*max_len]: alpha, da
+  __shared__ float red[POOL_THREADS / 32];
+  const int s = blockIdx.x;
+  const int beg = a.seg_off ? a.seg_off[s] : s * a.fixed_len;
+  const int n = a.seg_off ? (a.seg_off[s + 1] - beg) : a.fixed_len;
+  float* al = sm;
+  float* da = sm + a.max_len;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = POOL_THREADS / 32;
+  const float* dp = a.dpooled + (size_t)s * a.lddp;
+  // dalpha[t] = dpooled . X[p]
+  for (int t = w; t < n; t += nw) {
+    const float* x = a.X + ((size_t)beg + t) * a.ldx;
+    float v = 0.f;
+    for (int d = lane; d < a.D; d += 32) v += dp[d] * x[d];
+    v = warp_sum(v);
+    if (lane == 0) { da[t] = v; al[t] = a.alpha[(size_t)beg + t]; }
+  }
+  __syncthreads();
+  float dot = 0.f;
+  for (int t = tid; t < n; t += POOL_THREADS) dot += al[t] * da[t];
+  dot = warp_sum(dot);
+  if (lane == 0) red[w] = dot;
+  __syncthreads();
+  dot = 0.f;
+  for (int i = 0; i < nw; ++i) dot += red[i];
+  __syncthreads();
+  for (int t = tid; t < n; t += POOL_THREADS) {
+    float v = al[t] * (da[t] - dot);           // dL/dscore (masked rows have alpha == 0 -> 0)
+    if (a.mode == 1) v *= a.scale;
+    da[t] = v;
+  }
+  __syncthreads();
+  // dX and (mode 1) dqvec
+  for (int d = tid; d < a.D; d += POOL_THREADS) {
+    const float g = dp[d];
+    const float q = (a.mode == 1) ? a.qvec[(size_t)s * a.ldq + d] : 0.f;
+    float accq = 0.f;
+    for (int t = 0; t < n; ++t) {
+      const size_t p = (size_t)beg + t;
+      float v = al[t] * g;
+      if (a.mode == 1) { v += da[t] * q; accq += da[t] * a.X[p * a.ldx + d]; }
+      float* o = a.dX + p * a.lddx + d;
+      *o = a.accumulate_dx ? (*o + v) : v;
+    }
+    if (a.mode == 1 && a.dqvec) a.dqvec[(size_t)s * a.lddq + d] = accq;
+  }
+  if (a.mode == 0) {
+    for (int k = tid; k < a.A; k += POOL_THREADS) {
+      const float wk = a.w2[k];
+      float accw = 0.f;
+      for (int t = 0; t < n; ++t) {
+        const size_t p = (size_t)beg + t;
+        float u = a.U[p * a.ldu + k];
+        a.dU[p * a.lddu + k] = da[t] * wk * (1.f - u * u);
+        accw += da[t] * u;
+      }
+      a.dw2_partial[(size_t)s * a.A + k] = accw;
+    }
+  }
+}
+
+static int pool_validate(const nnr_pool_args* a, bool bwd) {
+  NNR_REQUIRE(a && a->X && a->S > 0 && a->D > 0 && a->max_len > 0, NNR_ERR_ARG, "nnr_attn_pool: bad arguments");
+  NNR_REQUIRE(a->seg_off || a->fixed_len > 0, NNR_ERR_ARG, "nnr_attn_pool: need seg_off or fixed_len");
+  NNR_REQUIRE(!(a->seg_off == nullptr && a->fixed_len > a->max_len), NNR_ERR_ARG, "nnr_attn_pool: fixed_len > max_len");
+  NNR_REQUIRE(a->mode == 0 || a->mode == 1, NNR_ERR_ARG, "nnr_attn_pool: bad mode");
+  if (a->mode == 0) NNR_REQUIRE(a->U && a->w2 && a->A > 0, NNR_ERR_ARG, "nnr_attn_pool: mode 0 needs U, w2");
+  else NNR_REQUIRE(a->qvec, NNR_ERR_ARG, "nnr_attn_pool: mode 1 needs qvec");
+  NNR_REQUIRE(a->max_len <= 4096, NNR_ERR_UNSUPPORTED, "nnr_attn_pool: max_len > 4096");
+  if (!bwd) NNR_REQUIRE(a->pooled, NNR_ERR_ARG, "nnr_attn_pool_fwd: pooled is null");
+  else {
+    NNR_REQUIRE(a->dpooled && a->dX && a->alpha, NNR_ERR_ARG, "nnr_attn_pool_bwd: dpooled/dX/alpha null");
+    if (a->mode == 0) NNR_REQUIRE(a->dU && a->dw2_partial, NNR_ERR_ARG, "nnr_attn_pool_bwd: mode 0 needs dU, dw2_partial");
+  }
+  return 0;
+}
+
+extern "C" int nnr_attn_pool_fwd(const nnr_pool_args* a, void* stream) {
+  int rc = pool_validate(a, false);
+  if (rc) return rc;
+  attn_pool_fwd_kernel<<<a->S, POOL_THREADS, a->max_len * sizeof(float), (cudaStream_t)stream>>>(*a);
+  NNR_LAUNCH_CHECK("attn_pool_fwd_kernel");
+  return 0;
+}
+extern "C" int nnr_attn_pool_bwd(const nnr_pool_args* a, void* stream) {
+  int rc = pool_validate(a, true);
+  if (rc) return rc;
+  attn_pool_bwd_kernel<<<a->S, POOL_THREADS, 2 * a->max_len * sizeof(float), (cudaStream_t)stream>>>(*a);
+  NNR_LAUNCH_CHECK("attn_pool_bwd_kernel");
+  return 0;
+}

@@ -1,0 +1,72 @@
+// Shared helpers for the nnr_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#define NNR_ERR_ARG (-1)
+#define NNR_ERR_ALIGN (-2)
+#define NNR_ERR_WORKSPACE (-3)
+#define NNR_ERR_UNSUPPORTED (-4)
+
+void nnr_set_error(const char* fmt, ...);
+void nnr_count_launch(int n);
+
+#define NNR_REQUIRE(cond, code, ...)              \
+  do {                                            \
+    if (!(cond)) {                                \
+      nnr_set_error(__VA_ARGS__);                 \
+      return (code);                              \
+    }                                             \
+  } while (0)
+
+// Launch check: returns the (positive) cudaError_t of the launch, if any.
+#define NNR_LAUNCH_CHECK(name)                                                   \
+  do {                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                        \
+    nnr_count_launch(1);                                                         \
+    if (e__ != cudaSuccess) {                                                    \
+      nnr_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));     \
+      return (int)e__;                                                           \
+    }                                                                            \
+  } while (0)
+
+#define NNR_CUDA(call)                                                           \
+  do {                                                                           \
+    cudaError_t e__ = (call);                                                    \
+    if (e__ != cudaSuccess) {                                                    \
+      nnr_set_error("%s failed: %s", #call, cudaGetErrorString(e__));            \
+      return (int)e__;                                                           \
+    }                                                                            \
+  } while (0)
+
+static inline bool nnr_aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Counter-based RNG for dropout masks: one 32-bit hash per element, reproducible from
+// (seed, element index) so the backward pass regenerates the forward mask instead of storing it.
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return (uint32_t)x;
+}
+// keep-scale: 0 if dropped, 1/(1-p) if kept.  p == 0 -> always 1.
+__device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, float p, float inv_keep) {
+  if (p <= 0.0f) return 1.0f;
+  uint32_t r = mix32(seed * 0x9E3779B97F4A7C15ULL + idx);
+  float u = (float)(r >> 8) * (1.0f / 16777216.0f);
+  return u < p ? 0.0f : inv_keep;
+}
+#endif

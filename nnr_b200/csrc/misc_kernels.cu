@@ -1,0 +1,330 @@
+// Small HBM-bound kernels: column sums, segment sums, LSTM hidden-state shift, gate backward
+// prologue, news-vector assembly, row dot products, dropout, fused clip+Adam.
+#include "common.cuh"
+#include "../../include/nnr_b200.h"
+
+// ------------------------------------------------------------------------------------------
+// column sums (bias gradients): two-stage, fixed partition -> deterministic
+// ------------------------------------------------------------------------------------------
+#define CS_ROWS 256
+__global__ void colsum_stage1(const float* __restrict__ X, int64_t ldx, int M, int N, const int32_t* __restrict__ m_dev,
+                              float* __restrict__ part) {
+  int Me = m_dev ? min(M, *m_dev) : M;
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int r0 = blockIdx.y * CS_ROWS;
+  if (n >= N) return;
+  float acc = 0.f;
+  int r1 = min(r0 + CS_ROWS, Me);
+  for (int r = r0; r < r1; ++r) acc += X[(size_t)r * ldx + n];
+  part[(size_t)blockIdx.y * N + n] = acc;
+}
+__global__ void colsum_stage2(const float* __restrict__ part, int nparts, int N, float* __restrict__ out, int accumulate) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int p = 0; p < nparts; ++p) acc += part[(size_t)p * N + n];
+  out[n] = accumulate ? out[n] + acc : acc;
+}
+extern "C" size_t nnr_colsum_workspace_bytes(int M, int N) {
+  if (M <= 0 || N <= 0) return 0;
+  return (size_t)((M + CS_ROWS - 1) / CS_ROWS) * N * sizeof(float);
+}
+extern "C" int nnr_colsum(const float* X, int64_t ldx, int M, int N, const int32_t* m_dev, float* out, int accumulate,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  NNR_REQUIRE(X && out && workspace && M > 0 && N > 0, NNR_ERR_ARG, "nnr_colsum: bad arguments");
+  NNR_REQUIRE(workspace_bytes >= nnr_colsum_workspace_bytes(M, N), NNR_ERR_WORKSPACE, "nnr_colsum: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int nparts = (M + CS_ROWS - 1) / CS_ROWS;
+  dim3 g1((N + 127) / 128, nparts);
+  colsum_stage1<<<g1, 128, 0, st>>>(X, ldx, M, N, m_dev, (float*)workspace);
+  NNR_LAUNCH_CHECK("colsum_stage1");
+  colsum_stage2<<<(N + 127) / 128, 128, 0, st>>>((const float*)workspace, nparts, N, out, accumulate);
+  NNR_LAUNCH_CHECK("colsum_stage2");
+  return 0;
+}
+
+// out[r,:] = sum_t X[off[r]+t,:]
+__global__ void segment_colsum_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict__ off, int D,
+                                      float* __restrict__ out, int64_t ldo) {
+  int r = blockIdx.x;
+  int a = off[r], b = off[r + 1];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int p = a; p < b; ++p) acc += X[(size_t)p * ldx + d];
+    out[(size_t)r * ldo + d] = acc;
+  }
+}
+extern "C" int nnr_segment_colsum(const float* X, int64_t ldx, const int32_t* off, int N, int D, float* out, int64_t ldo,
+                                  void* stream) {
+  NNR_REQUIRE(X && off && out && N > 0 && D > 0, NNR_ERR_ARG, "nnr_segment_colsum: bad arguments");
+  segment_colsum_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(X, ldx, off, D, out, ldo);
+  NNR_LAUNCH_CHECK("segment_colsum_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// hprev for dW_hh
+// ------------------------------------------------------------------------------------------
+__global__ void lstm_shift_h_kernel(const float* __restrict__ h, const int32_t* __restrict__ len,
+                                    const int32_t* __restrict__ off, const int32_t* __restrict__ tok_row, int N, int H,
+                                    float* __restrict__ hprev) {
+  int ntok = off[N];
+  int p = blockIdx.x;
+  if (p >= ntok) return;
+  int r = tok_row[p];
+  int t = p - off[r];
+  int l = len[r];
+  int H2 = 2 * H;
+  for (int k = threadIdx.x; k < H2; k += blockDim.x) {
+    float v;
+    if (k < H) v = (t > 0) ? h[(size_t)(p - 1) * H2 + k] : 0.f;
+    else v = (t < l - 1) ? h[(size_t)(p + 1) * H2 + k] : 0.f;
+    hprev[(size_t)p * H2 + k] = v;
+  }
+}
+extern "C" int nnr_lstm_shift_h(const float* h, const int32_t* len, const int32_t* off, const int32_t* tok_row, int N,
+                                int L, int H, float* hprev, void* stream) {
+  NNR_REQUIRE(h && len && off && tok_row && hprev && N > 0 && L > 0 && H > 0, NNR_ERR_ARG, "nnr_lstm_shift_h: bad arguments");
+  lstm_shift_h_kernel<<<N * L, 128, 0, (cudaStream_t)stream>>>(h, len, off, tok_row, N, H, hprev);
+  NNR_LAUNCH_CHECK("lstm_shift_h_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// selective gate backward prologue
+// ------------------------------------------------------------------------------------------
+__global__ void gate_bwd_pre_kernel(const float* __restrict__ dhg, const float* __restrict__ h, const float* __restrict__ g,
+                                    int64_t n_max, const int32_t* __restrict__ n_dev, int D, float* __restrict__ dz,
+                                    float* __restrict__ dh0) {
+  int64_t n = n_dev ? min(n_max, (int64_t)(*n_dev) * D) : n_max;
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float4 a = *reinterpret_cast<const float4*>(dhg + i);
+  float4 hh = *reinterpret_cast<const float4*>(h + i);
+  float4 gg = *reinterpret_cast<const float4*>(g + i);
+  float4 z, d0;
+  z.x = a.x * hh.x * gg.x * (1.f - gg.x); d0.x = a.x * gg.x;
+  z.y = a.y * hh.y * gg.y * (1.f - gg.y); d0.y = a.y * gg.y;
+  z.z = a.z * hh.z * gg.z * (1.f - gg.z); d0.z = a.z * gg.z;
+  z.w = a.w * hh.w * gg.w * (1.f - gg.w); d0.w = a.w * gg.w;
+  *reinterpret_cast<float4*>(dz + i) = z;
+  *reinterpret_cast<float4*>(dh0 + i) = d0;
+}
+extern "C" int nnr_gate_bwd_pre(const float* dhg, const float* h, const float* g, int64_t n_max, const int32_t* n_dev,
+                                int D, float* dz, float* dh0, void* stream) {
+  NNR_REQUIRE(dhg && h && g && dz && dh0 && n_max > 0 && D > 0, NNR_ERR_ARG, "nnr_gate_bwd_pre: bad arguments");
+  NNR_REQUIRE(n_max % 4 == 0 && D % 4 == 0 && nnr_aligned16(dhg) && nnr_aligned16(h) && nnr_aligned16(g) &&
+                  nnr_aligned16(dz) && nnr_aligned16(dh0),
+              NNR_ERR_ALIGN, "nnr_gate_bwd_pre: needs 16B alignment and D %% 4 == 0");
+  int64_t n4 = n_max / 4;
+  gate_bwd_pre_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dhg, h, g, n_max, n_dev, D, dz, dh0);
+  NNR_LAUNCH_CHECK("gate_bwd_pre_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// news vector assembly (newsEncoders.py:50-54,138)
+// ------------------------------------------------------------------------------------------
+__global__ void news_fuse_fwd_kernel(const float* __restrict__ ts, const float* __restrict__ tc, const float* __restrict__ cs,
+                                     const float* __restrict__ cc, const float* __restrict__ cat_table,
+                                     const float* __restrict__ sub_table, const int32_t* __restrict__ cat,
+                                     const int32_t* __restrict__ sub, int D2, int Ec, int Es, float p, float inv_keep,
+                                     uint64_t seed, float* __restrict__ out) {
+  int r = blockIdx.x;
+  int Dout = 2 * D2 + Ec + Es;
+  float* o = out + (size_t)r * Dout;
+  for (int d = threadIdx.x; d < Dout; d += blockDim.x) {
+    float v;
+    if (d < D2) v = ts[(size_t)r * D2 + d] + (tc ? tc[(size_t)r * D2 + d] : 0.f);
+    else if (d < 2 * D2) v = cs[(size_t)r * D2 + d - D2] + (cc ? cc[(size_t)r * D2 + d - D2] : 0.f);
+    else if (d < 2 * D2 + Ec) {
+      int e = d - 2 * D2;
+      v = cat_table[(size_t)cat[r] * Ec + e] * dropout_scale(seed, (uint64_t)r * (Ec + Es) + e, p, inv_keep);
+    } else {
+      int e = d - 2 * D2 - Ec;
+      v = sub_table[(size_t)sub[r] * Es + e] * dropout_scale(seed, (uint64_t)r * (Ec + Es) + Ec + e, p, inv_keep);
+    }
+    o[d] = v;
+  }
+}
+extern "C" int nnr_news_fuse_fwd(const float* t_self, const float* t_cross, const float* c_self, const float* c_cross,
+                                 const float* cat_table, const float* sub_table, const int32_t* cat, const int32_t* sub,
+                                 int N, int D2, int Ec, int Es, float p_drop, uint64_t seed, float* out, void* stream) {
+  NNR_REQUIRE(t_self && c_self && cat_table && sub_table && cat && sub && out && N > 0, NNR_ERR_ARG,
+              "nnr_news_fuse_fwd: bad arguments");
+  float inv_keep = 1.0f / (1.0f - p_drop);
+  news_fuse_fwd_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(t_self, t_cross, c_self, c_cross, cat_table, sub_table, cat,
+                                                           sub, D2, Ec, Es, p_drop, inv_keep, seed, out);
+  NNR_LAUNCH_CHECK("news_fuse_fwd_kernel");
+  return 0;
+}
+
+__global__ void news_fuse_split_kernel(const float* __restrict__ dout, int D2, int Dout, float* __restrict__ d_a,
+                                       float* __restrict__ d_b) {
+  int r = blockIdx.x;
+  for (int d = threadIdx.x; d < 2 * D2; d += blockDim.x) {
+    float v = dout[(size_t)r * Dout + d];
+    if (d < D2) d_a[(size_t)r * D2 + d] = v;
+    else d_b[(size_t)r * D2 + d - D2] = v;
+  }
+}
+// one block per table row; scans the N news rows in order (deterministic)
+__global__ void news_fuse_table_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ idx, int N, int Dout,
+                                           int col0, int Edim, int Etot, int eoff, float p, float inv_keep, uint64_t seed,
+                                           float* __restrict__ dtable, int accumulate) {
+  int row = blockIdx.x;
+  int e = threadIdx.x;
+  if (e >= Edim) return;
+  float acc = 0.f;
+  for (int r = 0; r < N; ++r) {
+    if (idx[r] == row)
+      acc += dout[(size_t)r * Dout + col0 + e] * dropout_scale(seed, (uint64_t)r * Etot + eoff + e, p, inv_keep);
+  }
+  float* d = dtable + (size_t)row * Edim + e;
+  *d = accumulate ? (*d + acc) : acc;
+}
+extern "C" int nnr_news_fuse_bwd(const float* dout, const int32_t* cat, const int32_t* sub, int N, int D2, int Ec, int Es,
+                                 int n_cat, int n_sub, float p_drop, uint64_t seed, float* d_a, float* d_b,
+                                 float* dcat_table, float* dsub_table, int accumulate, void* stream) {
+  NNR_REQUIRE(dout && cat && sub && d_a && d_b && dcat_table && dsub_table && N > 0, NNR_ERR_ARG,
+              "nnr_news_fuse_bwd: bad arguments");
+  NNR_REQUIRE(Ec <= 1024 && Es <= 1024, NNR_ERR_UNSUPPORTED, "nnr_news_fuse_bwd: embedding dim > 1024");
+  cudaStream_t st = (cudaStream_t)stream;
+  int Dout = 2 * D2 + Ec + Es;
+  float inv_keep = 1.0f / (1.0f - p_drop);
+  news_fuse_split_kernel<<<N, 256, 0, st>>>(dout, D2, Dout, d_a, d_b);
+  NNR_LAUNCH_CHECK("news_fuse_split_kernel");
+  news_fuse_table_bwd_kernel<<<n_cat, ((Ec + 31) / 32) * 32, 0, st>>>(dout, cat, N, Dout, 2 * D2, Ec, Ec + Es, 0, p_drop,
+                                                                     inv_keep, seed, dcat_table, accumulate);
+  NNR_LAUNCH_CHECK("news_fuse_table_bwd_kernel(cat)");
+  news_fuse_table_bwd_kernel<<<n_sub, ((Es + 31) / 32) * 32, 0, st>>>(dout, sub, N, Dout, 2 * D2 + Ec, Es, Ec + Es, Ec,
+                                                                     p_drop, inv_keep, seed, dsub_table, accumulate);
+  NNR_LAUNCH_CHECK("news_fuse_table_bwd_kernel(sub)");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// click predictor (model.py:127)
+// ------------------------------------------------------------------------------------------
+__global__ void rowdot_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, int R, int D, float* __restrict__ out) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float acc = 0.f;
+  for (int d = lane; d < D; d += 32) acc += a[(size_t)r * D + d] * b[(size_t)r * D + d];
+  acc = warp_sum(acc);
+  if (lane == 0) out[r] = acc;
+}
+extern "C" int nnr_rowdot_fwd(const float* a, const float* b, int R, int D, float* out, void* stream) {
+  NNR_REQUIRE(a && b && out && R > 0 && D > 0, NNR_ERR_ARG, "nnr_rowdot_fwd: bad arguments");
+  rowdot_fwd_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(a, b, R, D, out);
+  NNR_LAUNCH_CHECK("rowdot_fwd_kernel");
+  return 0;
+}
+__global__ void rowdot_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ a, const float* __restrict__ b, int D,
+                                  float* __restrict__ da, int acc_a, float* __restrict__ db, int acc_b) {
+  int r = blockIdx.x;
+  float g = dout[r];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    size_t i = (size_t)r * D + d;
+    float av = a[i], bv = b[i];
+    if (da) da[i] = acc_a ? da[i] + g * bv : g * bv;
+    if (db) db[i] = acc_b ? db[i] + g * av : g * av;
+  }
+}
+extern "C" int nnr_rowdot_bwd(const float* dout, const float* a, const float* b, int R, int D, float* da, int accumulate_a,
+                              float* db, int accumulate_b, void* stream) {
+  NNR_REQUIRE(dout && a && b && R > 0 && D > 0, NNR_ERR_ARG, "nnr_rowdot_bwd: bad arguments");
+  rowdot_bwd_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(dout, a, b, D, da, accumulate_a, db, accumulate_b);
+  NNR_LAUNCH_CHECK("rowdot_bwd_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// dropout
+// ------------------------------------------------------------------------------------------
+__global__ void dropout_kernel(const float* __restrict__ x, int64_t n, float p, float inv_keep, uint64_t seed, float* __restrict__ y) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  y[i] = x[i] * dropout_scale(seed, (uint64_t)i, p, inv_keep);
+}
+extern "C" int nnr_dropout(const float* x, int64_t n, float p_drop, uint64_t seed, float* y, void* stream) {
+  NNR_REQUIRE(x && y && n > 0 && p_drop >= 0.f && p_drop < 1.f, NNR_ERR_ARG, "nnr_dropout: bad arguments");
+  dropout_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, p_drop, 1.0f / (1.0f - p_drop), seed, y);
+  NNR_LAUNCH_CHECK("dropout_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// clip_grad_norm_ + Adam over one flat buffer (trainer.py:118-120)
+// ------------------------------------------------------------------------------------------
+#define CA_BLOCKS 1184  // 148 SMs x 8
+__global__ void sumsq_stage1(const float* __restrict__ g, int64_t n, double* __restrict__ part) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      float4 v = *reinterpret_cast<const float4*>(g + i);
+      acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    } else {
+      for (int64_t j = i; j < n; ++j) acc += (double)g[j] * g[j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    part[blockIdx.x] = t;
+  }
+}
+__global__ void sumsq_stage2(const double* __restrict__ part, int nparts, float grad_scale, float* __restrict__ norm_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < nparts; ++i) t += part[i];
+    norm_out[0] = (float)(sqrt(t) * (double)grad_scale);
+  }
+}
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            int64_t n, float lr, float b1, float b2, float eps, float max_norm, float grad_scale,
+                            float bc1, float bc2_sqrt, const float* __restrict__ norm) {
+  float total = norm[0];
+  float coef = 1.0f;
+  if (max_norm > 0.f) coef = fminf(max_norm / (total + 1e-6f), 1.0f);   // torch clip_grad_norm_
+  coef *= grad_scale;
+  float step_size = lr / bc1;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float gi = g[i] * coef;
+    float mi = m[i] * b1 + (1.f - b1) * gi;          // exp_avg.lerp_(grad, 1-beta1)
+    float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+  }
+}
+extern "C" size_t nnr_flat_clip_adam_workspace_bytes(int64_t n) { (void)n; return CA_BLOCKS * sizeof(double); }
+extern "C" int nnr_flat_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                  float beta1, float beta2, float eps, float max_norm, float grad_scale, int32_t step,
+                                  float* norm_out, void* workspace, size_t workspace_bytes, void* stream) {
+  NNR_REQUIRE(param && grad && exp_avg && exp_avg_sq && norm_out && workspace && n > 0 && step >= 1, NNR_ERR_ARG,
+              "nnr_flat_clip_adam: bad arguments");
+  NNR_REQUIRE(workspace_bytes >= CA_BLOCKS * sizeof(double), NNR_ERR_WORKSPACE, "nnr_flat_clip_adam: workspace too small");
+  NNR_REQUIRE(nnr_aligned16(grad), NNR_ERR_ALIGN, "nnr_flat_clip_adam: grad must be 16B aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  sumsq_stage1<<<CA_BLOCKS, 256, 0, st>>>(grad, n, (double*)workspace);
+  NNR_LAUNCH_CHECK("sumsq_stage1");
+  sumsq_stage2<<<1, 32, 0, st>>>((const double*)workspace, CA_BLOCKS, grad_scale, norm_out);
+  NNR_LAUNCH_CHECK("sumsq_stage2");
+  float bc1 = 1.0f - powf(beta1, (float)step);
+  float bc2 = 1.0f - powf(beta2, (float)step);
+  double bc1d = 1.0 - pow((double)beta1, (double)step), bc2d = 1.0 - pow((double)beta2, (double)step);
+  (void)bc1; (void)bc2;
+  adam_kernel<<<CA_BLOCKS, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, max_norm, grad_scale,
+                                         (float)bc1d, (float)sqrt(bc2d), norm_out);
+  NNR_LAUNCH_CHECK("adam_kernel");
+  return 0;
+}

@@ -1,0 +1,291 @@
+// SUE user-encoder kernels: history-graph construction (bit-exact integer/fp32 work), dense graph ->
+// compressed neighbour lists, deterministic GCN aggregation, intra-cluster (segment) attention.
+//
+// Replaces: MIND_corpus.py:162-216 (numpy preprocessing), torch.bmm(graph, feature) at layers.py:286,
+// and torch_scatter.scatter_softmax / scatter_sum at userEncoders.py:88-89.
+#include "common.cuh"
+#include "../../include/nnr_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// nnr_sue_graph_build : one CTA per behaviour
+// ------------------------------------------------------------------------------------------------
+#define GB_MAXC 64
+#define GB_MAXH 256
+__global__ void sue_graph_build_kernel(const int32_t* __restrict__ categories, const int32_t* __restrict__ history_len,
+                                       int H, int C, float* __restrict__ graph, uint8_t* __restrict__ cmask,
+                                       int64_t* __restrict__ cidx) {
+  __shared__ int s_cat[GB_MAXH];     // category of slot, or C for padding
+  __shared__ int s_cnt[GB_MAXC];
+  __shared__ float s_d[GB_MAXH + GB_MAXC];
+  __shared__ int s_P;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int G = H + C;
+  int hl = history_len[b];
+  hl = min(max(hl, 0), H);
+  for (int i = tid; i < H; i += blockDim.x) {
+    int c = (i < hl) ? categories[(size_t)b * H + i] : C;
+    if (c < 0 || c > C) c = C;
+    s_cat[i] = c;
+  }
+  for (int c = tid; c < C; c += blockDim.x) s_cnt[c] = 0;
+  __syncthreads();
+  if (tid < C) {   // counts (integer, order independent)
+    int n = 0;
+    for (int i = 0; i < hl; ++i) n += (s_cat[i] == tid);
+    s_cnt[tid] = n;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int P = 0;
+    for (int c = 0; c < C; ++c) P += (s_cnt[c] > 0);
+    s_P = P;
+  }
+  __syncthreads();
+  const int P = s_P;
+  // d = sqrt(1/deg) in fp32, correctly rounded like numpy (MIND_corpus.py:211-212)
+  for (int v = tid; v < G; v += blockDim.x) {
+    int deg;
+    if (v < H) deg = (v < hl) ? (s_cnt[s_cat[v]] + 1) : 1;
+    else { int c = v - H; deg = (s_cnt[c] > 0) ? (1 + s_cnt[c] + (P - 1)) : 1; }
+    s_d[v] = __fsqrt_rn(__fdiv_rn(1.0f, (float)deg));
+  }
+  __syncthreads();
+  if (cidx) for (int i = tid; i < H; i += blockDim.x) cidx[(size_t)b * H + i] = (int64_t)s_cat[i];
+  if (cmask) for (int c = tid; c <= C; c += blockDim.x) cmask[(size_t)b * (C + 1) + c] = (c < C && s_cnt[c] > 0) ? 1 : 0;
+  if (graph) {
+    float* g = graph + (size_t)b * G * G;
+    for (int e = tid; e < G * G; e += blockDim.x) {
+      int i = e / G, j = e - i * G;
+      bool edge;
+      if (i == j) edge = true;
+      else if (i < H && j < H) edge = (i < hl && j < hl && s_cat[i] == s_cat[j]);
+      else if (i < H) edge = (i < hl && s_cat[i] == j - H);
+      else if (j < H) edge = (j < hl && s_cat[j] == i - H);
+      else edge = (s_cnt[i - H] > 0 && s_cnt[j - H] > 0);
+      // (D A) D with A in {0,1}: fl(fl(d_i * 1) * d_j)
+      g[e] = edge ? __fmul_rn(s_d[i], s_d[j]) : 0.0f;
+    }
+  }
+}
+
+extern "C" int nnr_sue_graph_build(const int32_t* categories, const int32_t* history_len, int B, int H, int C, float* graph,
+                                   uint8_t* category_mask, int64_t* category_indices, void* stream) {
+  NNR_REQUIRE(categories && history_len && B > 0 && H > 0 && C > 0, NNR_ERR_ARG, "nnr_sue_graph_build: bad arguments");
+  NNR_REQUIRE(H <= GB_MAXH && C <= GB_MAXC, NNR_ERR_UNSUPPORTED, "nnr_sue_graph_build: H<=%d, C<=%d", GB_MAXH, GB_MAXC);
+  sue_graph_build_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(categories, history_len, H, C, graph, category_mask,
+                                                            category_indices);
+  NNR_LAUNCH_CHECK("sue_graph_build_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nnr_graph_to_csr : one warp per graph row, ballot compaction (ascending column order)
+// ------------------------------------------------------------------------------------------------
+__global__ void graph_to_csr_kernel(const float* __restrict__ graph, int BG, int G, int transpose, int32_t* __restrict__ nnz,
+                                    int32_t* __restrict__ col, float* __restrict__ val) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= BG) return;
+  int b = row / G, i = row - b * G;
+  const float* g = graph + (size_t)b * G * G;
+  int cnt = 0;
+  for (int j0 = 0; j0 < G; j0 += 32) {
+    int j = j0 + lane;
+    float v = 0.f;
+    if (j < G) v = transpose ? g[(size_t)j * G + i] : g[(size_t)i * G + j];
+    bool nz = (v != 0.0f);
+    unsigned m = __ballot_sync(0xffffffffu, nz);
+    if (nz) {
+      int pos = cnt + __popc(m & ((1u << lane) - 1));
+      col[(size_t)row * G + pos] = j;
+      val[(size_t)row * G + pos] = v;
+    }
+    cnt += __popc(m);
+  }
+  if (lane == 0) nnz[row] = cnt;
+}
+extern "C" int nnr_graph_to_csr(const float* graph, int B, int G, int transpose, int32_t* nnz, int32_t* col, float* val,
+                                void* stream) {
+  NNR_REQUIRE(graph && nnz && col && val && B > 0 && G > 0, NNR_ERR_ARG, "nnr_graph_to_csr: bad arguments");
+  int rows = B * G;
+  graph_to_csr_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(graph, rows, G, transpose, nnz, col, val);
+  NNR_LAUNCH_CHECK("graph_to_csr_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nnr_gcn_aggregate : out[b,i,:] = sum_e val[e] * x[b,col[e],:]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gcn_aggregate_kernel(const int32_t* __restrict__ nnz, const int32_t* __restrict__ col,
+                                                            const float* __restrict__ val, const float* __restrict__ x, int G,
+                                                            int D, float* __restrict__ out) {
+  extern __shared__ unsigned char smraw[];
+  int* s_col = reinterpret_cast<int*>(smraw);
+  float* s_val = reinterpret_cast<float*>(smraw + sizeof(int) * G);
+  const int row = blockIdx.x;
+  const int b = row / G;
+  const int n = nnz[row];
+  for (int e = threadIdx.x; e < n; e += blockDim.x) { s_col[e] = col[(size_t)row * G + e]; s_val[e] = val[(size_t)row * G + e]; }
+  __syncthreads();
+  const float* xb = x + (size_t)b * G * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int e = 0; e < n; ++e) acc = fmaf(s_val[e], xb[(size_t)s_col[e] * D + d], acc);
+    out[(size_t)row * D + d] = acc;
+  }
+}
+extern "C" int nnr_gcn_aggregate(const int32_t* nnz, const int32_t* col, const float* val, const float* x, int B, int G, int D,
+                                 float* out, void* stream) {
+  NNR_REQUIRE(nnz && col && val && x && out && B > 0 && G > 0 && D > 0, NNR_ERR_ARG, "nnr_gcn_aggregate: bad arguments");
+  gcn_aggregate_kernel<<<B * G, 256, (sizeof(int) + sizeof(float)) * G, (cudaStream_t)stream>>>(nnz, col, val, x, G, D, out);
+  NNR_LAUNCH_CHECK("gcn_aggregate_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// intra-cluster attention (segment softmax by category + segment weighted sum)
+// ------------------------------------------------------------------------------------------------
+#define CI_MAXH 256
+#define CI_MAXC 72
+__global__ void __launch_bounds__(256) cluster_intra_fwd_kernel(const float* __restrict__ Kp, const float* __restrict__ Qp,
+                                                                const float* __restrict__ g, const int64_t* __restrict__ idx,
+                                                                int n, int H, int Au, int D, int C1, float scale,
+                                                                float* __restrict__ alpha, float* __restrict__ intra) {
+  __shared__ float s_a[CI_MAXH];
+  __shared__ int s_idx[CI_MAXH];
+  __shared__ int s_perm[CI_MAXH];
+  __shared__ int s_start[CI_MAXC + 1];
+  const int bk = blockIdx.x, b = bk / n;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int h = tid; h < H; h += 256) { int c = (int)idx[(size_t)b * H + h]; s_idx[h] = min(max(c, 0), C1 - 1); }
+  const float* q = Qp + (size_t)bk * Au;
+  for (int h = w; h < H; h += 8) {
+    const float* kp = Kp + ((size_t)b * H + h) * Au;
+    float v = 0.f;
+    for (int a = lane; a < Au; a += 32) v += kp[a] * q[a];
+    v = warp_sum(v);
+    if (lane == 0) s_a[h] = v * scale;
+  }
+  __syncthreads();
+  if (tid == 0) {   // stable counting sort of the H slots by cluster (H <= 256: trivial)
+    int pos = 0;
+    for (int c = 0; c < C1; ++c) {
+      s_start[c] = pos;
+      for (int h = 0; h < H; ++h) if (s_idx[h] == c) s_perm[pos++] = h;
+    }
+    s_start[C1] = pos;
+  }
+  __syncthreads();
+  // per-slot softmax within its cluster (max-shifted, like torch_scatter.scatter_softmax)
+  float my_alpha = 0.f;
+  if (tid < H) {
+    int c = s_idx[tid];
+    float m = -INFINITY;
+    for (int e = s_start[c]; e < s_start[c + 1]; ++e) m = fmaxf(m, s_a[s_perm[e]]);
+    float sum = 0.f;
+    for (int e = s_start[c]; e < s_start[c + 1]; ++e) sum += expf(s_a[s_perm[e]] - m);
+    my_alpha = expf(s_a[tid] - m) / sum;
+    alpha[(size_t)bk * H + tid] = my_alpha;
+  }
+  __syncthreads();
+  if (tid < H) s_a[tid] = my_alpha;
+  __syncthreads();
+  const float* gb = g + (size_t)b * H * D;
+  float* ob = intra + (size_t)bk * C1 * D;
+  for (int d = tid; d < D; d += 256) {
+    for (int c = 0; c < C1; ++c) {
+      float acc = 0.f;
+      for (int e = s_start[c]; e < s_start[c + 1]; ++e) { int h = s_perm[e]; acc += s_a[h] * gb[(size_t)h * D + d]; }
+      ob[(size_t)c * D + d] = acc;
+    }
+  }
+}
+
+// A: per (b,k): da (scaled) -> da_ws, dQp
+__global__ void __launch_bounds__(256) cluster_intra_bwd_a_kernel(const float* __restrict__ dintra, const float* __restrict__ Kp,
+                                                                  const float* __restrict__ g, const int64_t* __restrict__ idx,
+                                                                  const float* __restrict__ alpha, int n, int H, int Au, int D,
+                                                                  int C1, float scale, float* __restrict__ da_ws,
+                                                                  float* __restrict__ dQp) {
+  __shared__ float s_da[CI_MAXH];
+  __shared__ float s_al[CI_MAXH];
+  __shared__ int s_idx[CI_MAXH];
+  const int bk = blockIdx.x, b = bk / n;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int h = tid; h < H; h += 256) {
+    int c = (int)idx[(size_t)b * H + h];
+    s_idx[h] = min(max(c, 0), C1 - 1);
+    s_al[h] = alpha[(size_t)bk * H + h];
+  }
+  __syncthreads();
+  for (int h = w; h < H; h += 8) {
+    const float* di = dintra + ((size_t)bk * C1 + s_idx[h]) * D;
+    const float* gh = g + ((size_t)b * H + h) * D;
+    float v = 0.f;
+    for (int d = lane; d < D; d += 32) v += di[d] * gh[d];
+    v = warp_sum(v);
+    if (lane == 0) s_da[h] = v;   // dL/dalpha
+  }
+  __syncthreads();
+  float out = 0.f;
+  if (tid < H) {
+    int c = s_idx[tid];
+    float dot = 0.f;
+    for (int h = 0; h < H; ++h) if (s_idx[h] == c) dot += s_al[h] * s_da[h];
+    out = s_al[tid] * (s_da[tid] - dot) * scale;
+  }
+  __syncthreads();
+  if (tid < H) { s_da[tid] = out; da_ws[(size_t)bk * H + tid] = out; }
+  __syncthreads();
+  for (int a = tid; a < Au; a += 256) {
+    float acc = 0.f;
+    for (int h = 0; h < H; ++h) acc += s_da[h] * Kp[((size_t)b * H + h) * Au + a];
+    dQp[(size_t)bk * Au + a] = acc;
+  }
+}
+// B: per (b,h): dKp, dg
+__global__ void __launch_bounds__(256) cluster_intra_bwd_b_kernel(const float* __restrict__ dintra, const float* __restrict__ Qp,
+                                                                  const int64_t* __restrict__ idx, const float* __restrict__ alpha,
+                                                                  const float* __restrict__ da_ws, int n, int H, int Au, int D,
+                                                                  int C1, float* __restrict__ dKp, float* __restrict__ dg,
+                                                                  int accumulate_dg) {
+  const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
+  const int tid = threadIdx.x;
+  int c = (int)idx[bh];
+  c = min(max(c, 0), C1 - 1);
+  for (int a = tid; a < Au; a += 256) {
+    float acc = 0.f;
+    for (int k = 0; k < n; ++k) acc += da_ws[((size_t)b * n + k) * H + h] * Qp[((size_t)b * n + k) * Au + a];
+    dKp[(size_t)bh * Au + a] = acc;
+  }
+  for (int d = tid; d < D; d += 256) {
+    float acc = 0.f;
+    for (int k = 0; k < n; ++k)
+      acc += alpha[((size_t)b * n + k) * H + h] * dintra[(((size_t)b * n + k) * C1 + c) * D + d];
+    float* o = dg + (size_t)bh * D + d;
+    *o = accumulate_dg ? (*o + acc) : acc;
+  }
+}
+
+extern "C" int nnr_cluster_intra_fwd(const float* Kp, const float* Qp, const float* g, const int64_t* idx, int B, int n, int H,
+                                     int Au, int D, int C1, float scale, float* alpha, float* intra, void* stream) {
+  NNR_REQUIRE(Kp && Qp && g && idx && alpha && intra && B > 0 && n > 0 && H > 0 && Au > 0 && D > 0 && C1 > 0, NNR_ERR_ARG,
+              "nnr_cluster_intra_fwd: bad arguments");
+  NNR_REQUIRE(H <= CI_MAXH && C1 <= CI_MAXC, NNR_ERR_UNSUPPORTED, "nnr_cluster_intra_fwd: H<=%d C1<=%d", CI_MAXH, CI_MAXC);
+  cluster_intra_fwd_kernel<<<B * n, 256, 0, (cudaStream_t)stream>>>(Kp, Qp, g, idx, n, H, Au, D, C1, scale, alpha, intra);
+  NNR_LAUNCH_CHECK("cluster_intra_fwd_kernel");
+  return 0;
+}
+extern "C" int nnr_cluster_intra_bwd(const float* dintra, const float* Kp, const float* Qp, const float* g, const int64_t* idx,
+                                     const float* alpha, int B, int n, int H, int Au, int D, int C1, float scale, float* da_ws,
+                                     float* dKp, float* dQp, float* dg, int accumulate_dg, void* stream) {
+  NNR_REQUIRE(dintra && Kp && Qp && g && idx && alpha && da_ws && dKp && dQp && dg && B > 0 && n > 0 && H > 0, NNR_ERR_ARG,
+              "nnr_cluster_intra_bwd: bad arguments");
+  NNR_REQUIRE(H <= CI_MAXH && C1 <= CI_MAXC, NNR_ERR_UNSUPPORTED, "nnr_cluster_intra_bwd: H<=%d C1<=%d", CI_MAXH, CI_MAXC);
+  cudaStream_t st = (cudaStream_t)stream;
+  cluster_intra_bwd_a_kernel<<<B * n, 256, 0, st>>>(dintra, Kp, g, idx, alpha, n, H, Au, D, C1, scale, da_ws, dQp);
+  NNR_LAUNCH_CHECK("cluster_intra_bwd_a_kernel");
+  cluster_intra_bwd_b_kernel<<<B * H, 256, 0, st>>>(dintra, Qp, idx, alpha, da_ws, n, H, Au, D, C1, dKp, dg, accumulate_dg);
+  NNR_LAUNCH_CHECK("cluster_intra_bwd_b_kernel");
+  return 0;
+}

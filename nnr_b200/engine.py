@@ -1,0 +1,487 @@
+"""Forward / backward schedules of the CNE news encoder and the SUE user encoder over the C-ABI ops.
+
+Each encoder call is ONE ``torch.autograd.Function`` whose forward and backward are explicit
+sequences of ``nnr_*`` kernel launches (no autograd graph inside, no ATen math on the per-token
+tensors).  Host PyTorch is used only for allocation, the [N]-sized permutation bookkeeping
+(``torch.sort`` exactly as the reference calls it, so tie-breaking matches on the same device) and
+slicing of the small per-news tensors.
+
+Reference spans: CNE = newsEncoders.py:102-141, SUE = userEncoders.py:68-98, GCN = layers.py:285-323.
+"""
+import math
+
+import torch
+
+from . import ops
+from .ops import (EPI_ADD_AUX, EPI_BIAS, EPI_BIAS_RELU_RES, EPI_BIAS_TANH, EPI_GATE, EPI_NONE)
+
+# torch.sort exactly as newsEncoders.py:112-115 calls it; tests swap in a stable sort on both sides
+sort_fn = torch.sort
+
+def fresh_seed():
+    """63-bit seed for the counter-based dropout RNG, drawn from torch's CPU RNG stream."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def _empty(shape, dev, dtype=torch.float32):
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM helpers (row-major; weights are nn.Linear layout [out, in])
+# ------------------------------------------------------------------------------------------------
+def linear(x, W, M, m_dev=None, bias=None, epilogue=None, out=None, **epi):
+    """out[M,N] = epi(x[M,K] @ W[N,K]^T)"""
+    N, K = W.shape
+    if out is None:
+        out = _empty((M, N), x.device)
+    if epilogue is None:
+        epilogue = EPI_BIAS if bias is not None else EPI_NONE
+    ops.gemm(x, W, out, M, N, K, x.stride(0), W.stride(0), out.stride(0), False, True, epilogue, bias=bias,
+             m_dev=m_dev, **epi)
+    return out
+
+
+def matmul_nn(x, W, M, m_dev=None, out=None, **epi):
+    """out[M,K] = x[M,N] @ W[N,K]   (dgrad of a Linear with weight W, or a fold K^T q)"""
+    N, K = W.shape
+    if out is None:
+        out = _empty((M, K), x.device)
+    ops.gemm(x, W, out, M, K, N, x.stride(0), W.stride(0), out.stride(0), False, False, m_dev=m_dev, **epi)
+    return out
+
+
+def wgrad(dy, x, M, N, K, k_dev=None, out=None, accumulate=False):
+    """out[N,K] = dy[M,N]^T @ x[M,K]   (contraction over the M rows / tokens)"""
+    if out is None:
+        out = _empty((N, K), dy.device)
+    ops.gemm(dy, x, out, N, K, M, dy.stride(0), x.stride(0), out.stride(0), True, False, k_dev=k_dev,
+             accumulate=accumulate)
+    return out
+
+
+def colsum(X, M, N, m_dev=None, out=None, accumulate=False):
+    if out is None:
+        out = _empty((N,), X.device)
+    ops.colsum(X, X.stride(0), M, N, out, accumulate, m_dev)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CNE
+# ------------------------------------------------------------------------------------------------
+CNE_PARAM_NAMES = (
+    ['word_embedding.weight', 'category_embedding.weight', 'subCategory_embedding.weight']
+    + ['%s_lstm.%s_l0%s' % (x, w, s) for x in ('title', 'content') for s in ('', '_reverse')
+       for w in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh')]
+    + ['%s_%s' % (x, w) for x in ('title', 'content') for w in ('H.weight', 'M.weight', 'M.bias')]
+    + ['%s_self_attention.%s' % (x, w) for x in ('title', 'content') for w in ('affine1.weight', 'affine1.bias', 'affine2.weight')]
+)
+CNE_CROSS_PARAM_NAMES = ['%s_cross_attention.%s' % (x, w) for x in ('title', 'content') for w in ('K.weight', 'Q.weight', 'Q.bias')]
+
+
+class _Mod:
+    """per-modality forward state"""
+    pass
+
+
+def _cne_modality_forward(P, x, ids, mask_u8, N, L, E, Hd, training, p_drop, seed):
+    dev = ids.device
+    cap = N * L
+    m = _Mod()
+    m.L, m.cap, m.ids = L, cap, ids
+    m.len = _empty((N,), dev, torch.int32)
+    m.off = _empty((N + 1,), dev, torch.int32)
+    m.tok_row = _empty((cap,), dev, torch.int32)
+    ops.seq_prepare(mask_u8, m.len, m.off, m.tok_row)
+    m.ntok = m.off[N:]                                         # device scalar (view), no sync
+    # newsEncoders.py:112-115 -- same torch.sort calls (tie-breaking of the device's sort)
+    _, m.sorted_idx = sort_fn(m.len.long(), descending=True)
+    _, m.desorted_idx = sort_fn(m.sorted_idx, descending=False)
+    m.order = m.sorted_idx.to(torch.int32)
+    m.seed = seed
+    m.p = p_drop if training else 0.0
+    m.emb = _empty((cap, E), dev)
+    ops.embed_gather_fwd(P['word_embedding.weight'], ids, m.len, m.off, m.emb, m.p, seed)
+    pre = x + '_lstm.'
+    m.w_ih = torch.cat([P[pre + 'weight_ih_l0'], P[pre + 'weight_ih_l0_reverse']], 0)          # [8H, E]
+    m.w_hh = torch.stack([P[pre + 'weight_hh_l0'], P[pre + 'weight_hh_l0_reverse']], 0)        # [2, 4H, H]
+    bias = torch.cat([P[pre + 'bias_ih_l0'] + P[pre + 'bias_hh_l0'],
+                      P[pre + 'bias_ih_l0_reverse'] + P[pre + 'bias_hh_l0_reverse']], 0)       # [8H]
+    m.gates = linear(m.emb, m.w_ih, cap, m.ntok, bias)                                        # gx, then the stash
+    m.h = _empty((cap, 2 * Hd), dev)
+    m.c_stash = _empty((cap, 2 * Hd), dev)
+    m.c_n = _empty((N, 2 * Hd), dev)
+    ops.lstm_fwd(m.gates, m.w_hh, m.len, m.off, m.order, N, L, Hd, m.h, m.c_stash, m.c_n)
+    return m
+
+
+def _cne_gate_self(P, x, m, m_other_cn, partner, N, Hd, A):
+    """selective gate (newsEncoders.py:128-131) + additive self attention (:133-134)"""
+    dev = m.h.device
+    D2 = 2 * Hd
+    m.partner = partner
+    m.cm_sel = m_other_cn.index_select(0, partner)                                            # [N, 2H]
+    m.mproj = linear(m.cm_sel, P[x + '_M.weight'], N, None, P[x + '_M.bias'])                 # [N, 2H]
+    m.g = _empty((m.cap, D2), dev)
+    m.hg = linear(m.h, P[x + '_H.weight'], m.cap, m.ntok, None, EPI_GATE, rowbias=m.mproj, ldrowbias=D2,
+                  rowmap=m.tok_row, aux=m.h, ldaux=D2, aux_out=m.g, ldaux_out=D2)
+    sa = x + '_self_attention.'
+    m.u = linear(m.hg, P[sa + 'affine1.weight'], m.cap, m.ntok, P[sa + 'affine1.bias'], EPI_BIAS_TANH)
+    m.self_out = _empty((N, D2), dev)
+    m.alpha_self = _empty((m.cap,), dev)
+    ops.attn_pool_fwd(X=m.hg, ldx=D2, D=D2, S=N, max_len=m.L, mode=0, seg_off=m.off, U=m.u, ldu=A, A=A,
+                      w2=P[sa + 'affine2.weight'], pooled=m.self_out, ldp=D2, alpha=m.alpha_self)
+
+
+def _cne_cross(P, x, m, other_self, N, Hd, A):
+    """cross attention (newsEncoders.py:136-137, layers.py:196-203) with K folded onto the query"""
+    dev = m.h.device
+    D2 = 2 * Hd
+    ca = x + '_cross_attention.'
+    m.other_self = other_self
+    m.q = linear(other_self, P[ca + 'Q.weight'], N, None, P[ca + 'Q.bias'])                    # [N, A]
+    m.qk = matmul_nn(m.q, P[ca + 'K.weight'], N)                                               # [N, 2H] = q K
+    m.cross_out = _empty((N, D2), dev)
+    m.alpha_cross = _empty((m.cap,), dev)
+    ops.attn_pool_fwd(X=m.hg, ldx=D2, D=D2, S=N, max_len=m.L, mode=1, seg_off=m.off, qvec=m.qk, ldq=D2,
+                      scale=1.0 / math.sqrt(float(A)), pooled=m.cross_out, ldp=D2, alpha=m.alpha_cross)
+
+
+class CNEFunction(torch.autograd.Function):
+    """rep[N, 4H+Ec+Es] = CNE(title, content, category, subCategory); params in CNE_PARAM_NAMES order."""
+
+    @staticmethod
+    def forward(ctx, meta, title_text, title_mask, content_text, content_mask, category, subCategory, *params):
+        names = CNE_PARAM_NAMES + (CNE_CROSS_PARAM_NAMES if meta['cross_attention'] else [])
+        P = dict(zip(names, params))
+        N, T, Lc = meta['N'], meta['T'], meta['A_len']
+        E, Hd, A = meta['E'], meta['Hd'], meta['att']
+        training, p = meta['training'], meta['p_drop']
+        seeds = [fresh_seed() for _ in range(3)] if (training and p > 0) else [0, 0, 0]
+        t = _cne_modality_forward(P, 'title', title_text.view(N, T), title_mask.reshape(N, T), N, T, E, Hd, training, p, seeds[0])
+        c = _cne_modality_forward(P, 'content', content_text.view(N, Lc), content_mask.reshape(N, Lc), N, Lc, E, Hd, training, p, seeds[1])
+        # pairing by sort rank (newsEncoders.py:124-129, SURVEY finding 2)
+        partner_t = c.sorted_idx.index_select(0, t.desorted_idx)
+        partner_c = t.sorted_idx.index_select(0, c.desorted_idx)
+        _cne_gate_self(P, 'title', t, c.c_n, partner_t, N, Hd, A)
+        _cne_gate_self(P, 'content', c, t.c_n, partner_c, N, Hd, A)
+        if meta['cross_attention']:
+            _cne_cross(P, 'title', t, c.self_out, N, Hd, A)
+            _cne_cross(P, 'content', c, t.self_out, N, Hd, A)
+        cat_t, sub_t = P['category_embedding.weight'], P['subCategory_embedding.weight']
+        Dout = 4 * Hd + cat_t.shape[1] + sub_t.shape[1]
+        rep = _empty((N, Dout), title_text.device)
+        cat_i, sub_i = category.reshape(N).contiguous(), subCategory.reshape(N).contiguous()
+        ops.news_fuse_fwd(t.self_out, t.cross_out if meta['cross_attention'] else None, c.self_out,
+                          c.cross_out if meta['cross_attention'] else None, cat_t, sub_t, cat_i, sub_i, N, 2 * Hd,
+                          p if training else 0.0, seeds[2], rep)
+        ctx.meta, ctx.P, ctx.t, ctx.c = meta, P, t, c
+        ctx.cat_i, ctx.sub_i, ctx.fuse_seed = cat_i, sub_i, seeds[2]
+        ctx.names = names
+        return rep
+
+    @staticmethod
+    def backward(ctx, drep):
+        meta, P, t, c = ctx.meta, ctx.P, ctx.t, ctx.c
+        N, E, Hd, A = meta['N'], meta['E'], meta['Hd'], meta['att']
+        D2 = 2 * Hd
+        dev = drep.device
+        drep = drep.contiguous()
+        G = {}
+        cross = meta['cross_attention']
+        training, p = meta['training'], meta['p_drop']
+        # 1. split + category tables
+        d_a, d_b = _empty((N, D2), dev), _empty((N, D2), dev)
+        G['category_embedding.weight'] = _empty(P['category_embedding.weight'].shape, dev)
+        G['subCategory_embedding.weight'] = _empty(P['subCategory_embedding.weight'].shape, dev)
+        ops.news_fuse_bwd(drep, ctx.cat_i, ctx.sub_i, N, D2, p if training else 0.0, ctx.fuse_seed, d_a, d_b,
+                          G['category_embedding.weight'], G['subCategory_embedding.weight'], False)
+        scale = 1.0 / math.sqrt(float(A))
+        d_self = {'title': d_a, 'content': d_b}
+        d_out = {'title': d_a, 'content': d_b}
+        mods = {'title': t, 'content': c}
+        other = {'title': 'content', 'content': 'title'}
+        for x, m in mods.items():
+            m.dhg = _empty((m.cap, D2), dev)
+        dhg_written = {'title': False, 'content': False}
+        # 2. cross attention backward (produces the extra gradient of the other modality's self vector)
+        if cross:
+            new_d_self = {}
+            for x, m in mods.items():
+                ca = x + '_cross_attention.'
+                dqk = _empty((N, D2), dev)
+                ops.attn_pool_bwd(X=m.hg, ldx=D2, D=D2, S=N, max_len=m.L, mode=1, seg_off=m.off, qvec=m.qk, ldq=D2,
+                                  scale=scale, alpha=m.alpha_cross, dpooled=d_out[x], lddp=D2, dX=m.dhg, lddx=D2,
+                                  accumulate_dx=False, dqvec=dqk, lddq=D2)
+                dhg_written[x] = True
+                dq = linear(dqk, P[ca + 'K.weight'], N)                                      # [N,A] = dqk K^T
+                G[ca + 'K.weight'] = wgrad(m.q, dqk, N, A, D2)                                # q^T dqk
+                G[ca + 'Q.weight'] = wgrad(dq, m.other_self, N, A, D2)
+                G[ca + 'Q.bias'] = colsum(dq, N, A)
+                # d(other self) = dq Q + its own output gradient
+                new_d_self[other[x]] = matmul_nn(dq, P[ca + 'Q.weight'], N, epilogue=EPI_ADD_AUX, aux=d_out[other[x]], ldaux=D2)
+            d_self = new_d_self
+        # 3. self attention backward
+        for x, m in mods.items():
+            sa = x + '_self_attention.'
+            dU = _empty((m.cap, A), dev)
+            dw2p = _empty((N, A), dev)
+            ops.attn_pool_bwd(X=m.hg, ldx=D2, D=D2, S=N, max_len=m.L, mode=0, seg_off=m.off, U=m.u, ldu=A, A=A,
+                              w2=P[sa + 'affine2.weight'], alpha=m.alpha_self, dpooled=d_self[x], lddp=D2, dX=m.dhg,
+                              lddx=D2, accumulate_dx=dhg_written[x], dU=dU, lddu=A, dw2_partial=dw2p)
+            G[sa + 'affine2.weight'] = colsum(dw2p, N, A).view(1, A)
+            matmul_nn(dU, P[sa + 'affine1.weight'], m.cap, m.ntok, out=m.dhg, accumulate=True)
+            G[sa + 'affine1.weight'] = wgrad(dU, m.hg, m.cap, A, D2, k_dev=m.ntok)
+            G[sa + 'affine1.bias'] = colsum(dU, m.cap, A, m.ntok)
+            del dU
+        # 4. selective gate backward
+        d_cm_sel = {}
+        for x, m in mods.items():
+            dz = _empty((m.cap, D2), dev)
+            dh0 = _empty((m.cap, D2), dev)
+            ops.gate_bwd_pre(m.dhg, m.h, m.g, m.cap * D2, m.ntok, D2, dz, dh0)
+            m.dh = matmul_nn(dz, P[x + '_H.weight'], m.cap, m.ntok, epilogue=EPI_ADD_AUX, aux=dh0, ldaux=D2, out=m.dhg)
+            G[x + '_H.weight'] = wgrad(dz, m.h, m.cap, D2, D2, k_dev=m.ntok)
+            dmproj = _empty((N, D2), dev)
+            ops.segment_colsum(dz, D2, m.off, N, D2, dmproj, D2)
+            G[x + '_M.weight'] = wgrad(dmproj, m.cm_sel, N, D2, D2)
+            G[x + '_M.bias'] = colsum(dmproj, N, D2)
+            d_cm_sel[x] = matmul_nn(dmproj, P[x + '_M.weight'], N)                            # grad of cn_other[partner]
+            del dz, dh0
+        # partner_t and partner_c are inverse permutations of each other
+        dcn = {'content': d_cm_sel['title'].index_select(0, c.partner),
+               'title': d_cm_sel['content'].index_select(0, t.partner)}
+        # 5. LSTM backward + input projection + embedding scatter
+        dtable = _empty(P['word_embedding.weight'].shape, dev)
+        first = True
+        for x, m in mods.items():
+            pre = x + '_lstm.'
+            ops.lstm_bwd(m.gates, m.c_stash, m.w_hh, m.len, m.off, m.order, N, m.L, Hd, m.dh, dcn[x].contiguous())
+            dz = m.gates                                                                      # [cap, 8H] = dL/dgx
+            hprev = _empty((m.cap, D2), dev)
+            ops.lstm_shift_h(m.h, m.len, m.off, m.tok_row, N, m.L, Hd, hprev)
+            for d, sfx in enumerate(('', '_reverse')):
+                G[pre + 'weight_hh_l0' + sfx] = wgrad(dz[:, d * 4 * Hd:(d + 1) * 4 * Hd], hprev[:, d * Hd:(d + 1) * Hd],
+                                                     m.cap, 4 * Hd, Hd, k_dev=m.ntok)
+            dwih = wgrad(dz, m.emb, m.cap, 8 * Hd, E, k_dev=m.ntok)
+            db = colsum(dz, m.cap, 8 * Hd, m.ntok)
+            for d, sfx in enumerate(('', '_reverse')):
+                G[pre + 'weight_ih_l0' + sfx] = dwih[d * 4 * Hd:(d + 1) * 4 * Hd]
+                G[pre + 'bias_ih_l0' + sfx] = db[d * 4 * Hd:(d + 1) * 4 * Hd]
+                G[pre + 'bias_hh_l0' + sfx] = db[d * 4 * Hd:(d + 1) * 4 * Hd]
+            demb = matmul_nn(dz, m.w_ih, m.cap, m.ntok)
+            ops.embed_gather_bwd(demb, m.ids, m.len, m.off, dtable, m.p, m.seed, not first)
+            first = False
+            del hprev, demb
+        G['word_embedding.weight'] = dtable
+        ctx.t = ctx.c = None
+        return (None,) * 7 + tuple(G[k] for k in ctx.names)
+
+
+# ------------------------------------------------------------------------------------------------
+# SUE
+# ------------------------------------------------------------------------------------------------
+def sue_param_names(L):
+    return (['proxy_node_embedding'] + ['gcn.gcn_layers.%d.W.%s' % (l, w) for l in range(L) for w in ('weight', 'bias')]
+            + ['intraCluster_K.weight', 'intraCluster_Q.weight', 'intraCluster_Q.bias', 'clusterFeatureAffine.weight',
+               'clusterFeatureAffine.bias', 'interClusterAttention.K.weight', 'interClusterAttention.Q.weight',
+               'interClusterAttention.Q.bias'])
+
+
+def sue_wo_hca_param_names(L):
+    return (['proxy_node_embedding'] + ['gcn.gcn_layers.%d.W.%s' % (l, w) for l in range(L) for w in ('weight', 'bias')]
+            + ['attention.affine1.weight', 'attention.affine1.bias', 'attention.affine2.weight'])
+
+
+class SUEFunction(torch.autograd.Function):
+    """user[B,n,D] = SUE(history_embedding[B,H,D], candidate[B,n,D], graph, cluster mask / indices)."""
+
+    @staticmethod
+    def forward(ctx, meta, hist, cand, graph, cmask, cidx, *params):
+        hca = meta['hca']
+        L = meta['gcn_layers']
+        names = sue_param_names(L) if hca else sue_wo_hca_param_names(L)
+        P = dict(zip(names, params))
+        B, H, D = hist.shape
+        n = cand.shape[1]
+        C = P['proxy_node_embedding'].shape[0]
+        Gn, C1 = H + C, C + 1
+        dev = hist.device
+        training, p = meta['training'], meta['p_drop']
+        pe = p if training else 0.0
+        residual = meta['residual']
+        seeds = [fresh_seed() for _ in range(L + 2)] if pe > 0 else [0] * (L + 2)
+        hist = hist.contiguous()
+        cand = cand.contiguous()
+        # X0 = [history | dropout_(proxy nodes)]   (userEncoders.py:80)
+        x0 = _empty((B, Gn, D), dev)
+        x0[:, :H] = hist
+        proxy = P['proxy_node_embedding'].unsqueeze(0).expand(B, -1, -1).contiguous()
+        if pe > 0:
+            ops.dropout(proxy, pe, seeds[L], proxy)
+        x0[:, H:] = proxy
+        # dense graph -> neighbour lists (and of the transpose for the backward pass)
+        graph = graph.contiguous()
+        nnz, col, val = _empty((B * Gn,), dev, torch.int32), _empty((B * Gn, Gn), dev, torch.int32), _empty((B * Gn, Gn), dev)
+        ops.graph_to_csr(graph, False, nnz, col, val)
+        # GCN layers: X <- drop(relu(W (A X) + b) + X)   (layers.py:285-292,318-323)
+        xs, rs, aggs = [x0], [], []
+        x = x0
+        for l in range(L):
+            agg = _empty((B * Gn, D), dev)
+            ops.gcn_aggregate(nnz, col, val, x, B, Gn, D, agg)
+            r = _empty((B * Gn, D), dev)
+            xv = x.view(B * Gn, D)
+            pl = (pe / 2.0) if l < L - 1 else 0.0
+            xn = linear(agg, P['gcn.gcn_layers.%d.W.weight' % l], B * Gn, None, P['gcn.gcn_layers.%d.W.bias' % l],
+                        EPI_BIAS_RELU_RES, aux=xv if residual else None, ldaux=D, aux_out=r, ldaux_out=D, p_drop=pl,
+                        seed=seeds[l])
+            aggs.append(agg)
+            rs.append(r)
+            x = xn.view(B, Gn, D)
+            xs.append(x)
+        gfeat = (x + x0)[:, :H, :].contiguous()                                              # userEncoders.py:81-82
+        ctx.meta, ctx.P, ctx.names = meta, P, names
+        ctx.dims = (B, H, D, n, C, Gn, C1)
+        ctx.seeds, ctx.graph = seeds, graph
+        ctx.xs, ctx.rs, ctx.aggs = xs, rs, aggs
+        ctx.gfeat, ctx.cand = gfeat, cand
+        if not hca:                                                                           # SUE_wo_HCA
+            A = P['attention.affine1.weight'].shape[0]
+            u = linear(gfeat.view(B * H, D), P['attention.affine1.weight'], B * H, None, P['attention.affine1.bias'], EPI_BIAS_TANH)
+            pooled = _empty((B, D), dev)
+            alpha = _empty((B * H,), dev)
+            ops.attn_pool_fwd(X=gfeat, ldx=D, D=D, S=B, max_len=H, mode=0, fixed_len=H, U=u, ldu=A, A=A,
+                              w2=P['attention.affine2.weight'], pooled=pooled, ldp=D, alpha=alpha)
+            ctx.u, ctx.alpha = u, alpha
+            return pooled.unsqueeze(1).repeat(1, n, 1)
+        Au = P['intraCluster_K.weight'].shape[0]
+        scale = 1.0 / math.sqrt(float(Au))
+        Kp = linear(gfeat.view(B * H, D), P['intraCluster_K.weight'], B * H)
+        Qp = linear(cand.view(B * n, D), P['intraCluster_Q.weight'], B * n, None, P['intraCluster_Q.bias'])
+        alpha = _empty((B * n, H), dev)
+        intra = _empty((B * n * C1, D), dev)
+        cidx = cidx.contiguous()
+        ops.cluster_intra_fwd(Kp, Qp, gfeat, cidx, B, n, H, Au, D, C1, scale, alpha, intra)
+        r_f = _empty((B * n * C1, D), dev)
+        f = linear(intra, P['clusterFeatureAffine.weight'], B * n * C1, None, P['clusterFeatureAffine.bias'],
+                   EPI_BIAS_RELU_RES, aux=intra, ldaux=D, aux_out=r_f, ldaux_out=D, p_drop=pe, seed=seeds[L + 1])
+        q2 = linear(cand.view(B * n, D), P['interClusterAttention.Q.weight'], B * n, None, P['interClusterAttention.Q.bias'])
+        qk2 = matmul_nn(q2, P['interClusterAttention.K.weight'], B * n)
+        cm = cmask.unsqueeze(1).expand(-1, n, -1).contiguous().view(torch.uint8)             # [B,n,C1]
+        user = _empty((B * n, D), dev)
+        alpha2 = _empty((B * n * C1,), dev)
+        ops.attn_pool_fwd(X=f, ldx=D, D=D, S=B * n, max_len=C1, mode=1, fixed_len=C1, qvec=qk2, ldq=D, scale=scale,
+                          mask=cm, pooled=user, ldp=D, alpha=alpha2)
+        ctx.sv = (Kp, Qp, alpha, intra, r_f, f, q2, qk2, cm, alpha2, cidx, Au, scale)
+        return user.view(B, n, D)
+
+    @staticmethod
+    def backward(ctx, duser):
+        meta, P = ctx.meta, ctx.P
+        B, H, D, n, C, Gn, C1 = ctx.dims
+        L = meta['gcn_layers']
+        dev = duser.device
+        G = {}
+        training, p = meta['training'], meta['p_drop']
+        pe = p if training else 0.0
+        seeds = ctx.seeds
+        gfeat, cand = ctx.gfeat, ctx.cand
+        dcand = None
+        if not meta['hca']:
+            A = P['attention.affine1.weight'].shape[0]
+            dpooled = duser.sum(dim=1).contiguous()                                          # repeat over candidates
+            dg = _empty((B * H, D), dev)
+            dU = _empty((B * H, A), dev)
+            dw2p = _empty((B, A), dev)
+            ops.attn_pool_bwd(X=gfeat, ldx=D, D=D, S=B, max_len=H, mode=0, fixed_len=H, U=ctx.u, ldu=A, A=A,
+                              w2=P['attention.affine2.weight'], alpha=ctx.alpha, dpooled=dpooled, lddp=D, dX=dg, lddx=D,
+                              accumulate_dx=False, dU=dU, lddu=A, dw2_partial=dw2p)
+            G['attention.affine2.weight'] = colsum(dw2p, B, A).view(1, A)
+            matmul_nn(dU, P['attention.affine1.weight'], B * H, out=dg, accumulate=True)
+            G['attention.affine1.weight'] = wgrad(dU, gfeat.view(B * H, D), B * H, A, D)
+            G['attention.affine1.bias'] = colsum(dU, B * H, A)
+        else:
+            Kp, Qp, alpha, intra, r_f, f, q2, qk2, cm, alpha2, cidx, Au, scale = ctx.sv
+            duser = duser.contiguous().view(B * n, D)
+            # inter-cluster attention backward
+            df = _empty((B * n * C1, D), dev)
+            dqk2 = _empty((B * n, D), dev)
+            ops.attn_pool_bwd(X=f, ldx=D, D=D, S=B * n, max_len=C1, mode=1, fixed_len=C1, qvec=qk2, ldq=D, scale=scale,
+                              mask=cm, alpha=alpha2, dpooled=duser, lddp=D, dX=df, lddx=D, accumulate_dx=False,
+                              dqvec=dqk2, lddq=D)
+            dq2 = linear(dqk2, P['interClusterAttention.K.weight'], B * n)                   # [B*n, Au]
+            G['interClusterAttention.K.weight'] = wgrad(q2, dqk2, B * n, Au, D)
+            G['interClusterAttention.Q.weight'] = wgrad(dq2, cand.view(B * n, D), B * n, Au, D)
+            G['interClusterAttention.Q.bias'] = colsum(dq2, B * n, Au)
+            dcand = matmul_nn(dq2, P['interClusterAttention.Q.weight'], B * n)               # [B*n, D]
+            # cluster affine backward: f = (relu(W intra + b) + intra) * drop
+            if pe > 0:
+                ops.dropout(df, pe, seeds[L + 1], df)
+            dpre = df * (r_f > 0)                                                             # relu mask
+            G['clusterFeatureAffine.weight'] = wgrad(dpre, intra, B * n * C1, D, D)
+            G['clusterFeatureAffine.bias'] = colsum(dpre, B * n * C1, D)
+            dintra = matmul_nn(dpre, P['clusterFeatureAffine.weight'], B * n * C1, epilogue=EPI_ADD_AUX, aux=df, ldaux=D)
+            # intra-cluster attention backward
+            da_ws = _empty((B * n, H), dev)
+            dKp, dQp = _empty((B * H, Au), dev), _empty((B * n, Au), dev)
+            dg = _empty((B * H, D), dev)
+            ops.cluster_intra_bwd(dintra, Kp, Qp, gfeat, cidx, alpha, B, n, H, Au, D, C1, scale, da_ws, dKp, dQp, dg, False)
+            G['intraCluster_K.weight'] = wgrad(dKp, gfeat.view(B * H, D), B * H, Au, D)
+            matmul_nn(dKp, P['intraCluster_K.weight'], B * H, out=dg, accumulate=True)
+            G['intraCluster_Q.weight'] = wgrad(dQp, cand.view(B * n, D), B * n, Au, D)
+            G['intraCluster_Q.bias'] = colsum(dQp, B * n, Au)
+            matmul_nn(dQp, P['intraCluster_Q.weight'], B * n, out=dcand, accumulate=True)
+        # GCN backward.  gfeat = (x_L + x0)[:, :H]
+        dxL = torch.zeros((B, Gn, D), device=dev)
+        dxL[:, :H] = dg.view(B, H, D)
+        dx0 = dxL.clone()
+        nnzT, colT, valT = _empty((B * Gn,), dev, torch.int32), _empty((B * Gn, Gn), dev, torch.int32), _empty((B * Gn, Gn), dev)
+        ops.graph_to_csr(ctx.graph, True, nnzT, colT, valT)
+        dx = dxL.view(B * Gn, D)
+        residual = meta['residual']
+        for l in range(L - 1, -1, -1):
+            pl = (pe / 2.0) if l < L - 1 else 0.0
+            if pl > 0:
+                dx = dx.clone() if dx.data_ptr() == dxL.data_ptr() else dx
+                ops.dropout(dx, pl, seeds[l], dx)
+            dpre = dx * (ctx.rs[l] > 0)
+            G['gcn.gcn_layers.%d.W.weight' % l] = wgrad(dpre, ctx.aggs[l], B * Gn, D, D)
+            G['gcn.gcn_layers.%d.W.bias' % l] = colsum(dpre, B * Gn, D)
+            dagg = matmul_nn(dpre, P['gcn.gcn_layers.%d.W.weight' % l], B * Gn)
+            dprev = _empty((B * Gn, D), dev)
+            ops.gcn_aggregate(nnzT, colT, valT, dagg, B, Gn, D, dprev)
+            if residual:
+                dprev += dx
+            dx = dprev
+        dx0 = dx0.view(B * Gn, D) + dx
+        dx0 = dx0.view(B, Gn, D)
+        dhist = dx0[:, :H].contiguous()
+        dproxy_b = dx0[:, H:].contiguous()
+        if pe > 0:
+            ops.dropout(dproxy_b, pe, seeds[L], dproxy_b)
+        G['proxy_node_embedding'] = dproxy_b.sum(dim=0)
+        ctx.xs = ctx.rs = ctx.aggs = ctx.sv = None
+        return (None, dhist, dcand.view(B, n, D) if dcand is not None else None, None, None, None) + tuple(G[k] for k in ctx.names)
+
+
+class RowDot(torch.autograd.Function):
+    """logits[b,k] = sum_d user[b,k,d] * news[b,k,d]   (model.py:127)"""
+
+    @staticmethod
+    def forward(ctx, user, news):
+        B, n, D = user.shape
+        user, news = user.contiguous(), news.contiguous()
+        out = _empty((B, n), user.device)
+        ops.rowdot_fwd(user, news, B * n, D, out)
+        ctx.save_for_backward(user, news)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        user, news = ctx.saved_tensors
+        B, n, D = user.shape
+        du, dn = torch.empty_like(user), torch.empty_like(news)
+        ops.rowdot_bwd(dout.contiguous(), user, news, B * n, D, du, False, dn, False)
+        return du, dn

@@ -1,0 +1,45 @@
+"""Drop-in ``Model`` (reference model.py:10-133) for the CNE / SUE family with the dot-product predictor."""
+import torch.nn as nn
+
+from . import engine, newsEncoders, userEncoders, variantEncoders
+
+
+class Model(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        if config.news_encoder == 'CNE':
+            self.news_encoder = newsEncoders.CNE(config)
+        elif config.news_encoder == 'CNE_wo_CA':
+            self.news_encoder = variantEncoders.CNE_wo_CA(config)
+        else:
+            raise Exception(config.news_encoder + ' is outside the nnr_b200 hot path (CNE, CNE_wo_CA)')
+        if config.user_encoder == 'SUE':
+            self.user_encoder = userEncoders.SUE(self.news_encoder, config)
+        elif config.user_encoder == 'SUE_wo_HCA':
+            self.user_encoder = variantEncoders.SUE_wo_HCA(self.news_encoder, config)
+        else:
+            raise Exception(config.user_encoder + ' is outside the nnr_b200 hot path (SUE, SUE_wo_HCA)')
+        self.model_name = config.news_encoder + '-' + config.user_encoder
+        self.news_embedding_dim = self.news_encoder.news_embedding_dim
+        self.dropout = nn.Dropout(p=config.dropout_rate)
+        self.use_user_embedding = False
+        if config.click_predictor != 'dot_product':
+            raise Exception('nnr_b200 implements the dot_product click predictor (reference default, config.py:76)')
+        self.click_predictor = config.click_predictor
+
+    def initialize(self):
+        self.news_encoder.initialize()
+        self.user_encoder.initialize()
+
+    def forward(self, user_ID, user_category, user_subCategory, user_title_text, user_title_mask, user_title_entity,
+                user_content_text, user_content_mask, user_content_entity, user_history_mask, user_history_graph,
+                user_history_category_mask, user_history_category_indices, news_category, news_subCategory,
+                news_title_text, news_title_mask, news_title_entity, news_content_text, news_content_mask,
+                news_content_entity):
+        news_representation = self.news_encoder(news_title_text, news_title_mask, news_title_entity, news_content_text,
+                                                news_content_mask, news_content_entity, news_category, news_subCategory, None)
+        user_representation = self.user_encoder(user_title_text, user_title_mask, user_title_entity, user_content_text,
+                                                user_content_mask, user_content_entity, user_category, user_subCategory,
+                                                user_history_mask, user_history_graph, user_history_category_mask,
+                                                user_history_category_indices, None, news_representation)
+        return engine.RowDot.apply(user_representation, news_representation)     # model.py:127

@@ -1,0 +1,262 @@
+"""torch-level wrappers over the C-ABI (``_lib``), registered as ``torch.ops.nnr.*`` custom ops.
+
+Every op is an out-variant: the caller (PyTorch's caching allocator) owns all buffers, the library
+only launches kernels on the current CUDA stream.  Ops are registered for the CUDA dispatch key
+only -- calling them with CPU tensors raises (there is no CPU fallback by design).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, PoolArgs, check, lib
+
+EPI_NONE, EPI_BIAS, EPI_BIAS_TANH, EPI_BIAS_RELU_RES, EPI_GATE, EPI_ADD_AUX = range(6)
+ALGO_AUTO, ALGO_SIMT, ALGO_TF32X3, ALGO_BF16 = range(4)
+
+_F32, _I32, _I64, _U8 = torch.float32, torch.int32, torch.int64, torch.uint8
+
+
+def _p(t, dtype=None):
+    """device pointer of a tensor (None -> NULL) with device/dtype checks"""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('nnr_b200 ops need CUDA tensors (no CPU fallback)')
+    if dtype is not None and t.dtype != dtype:
+        if not (dtype == _U8 and t.dtype == torch.bool):
+            raise RuntimeError('nnr_b200: expected %s, got %s' % (dtype, t.dtype))
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device, tag='default'):
+    """grow-only scratch buffer per (device, tag); safe because all launches are stream ordered"""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+# --------------------------------------------------------------------------------------------
+# implementations (plain python functions over tensors)
+# --------------------------------------------------------------------------------------------
+def seq_prepare(mask, len_, off, tok_row):
+    N, L = mask.shape
+    check(lib.nnr_seq_prepare(_p(mask, _U8), N, L, _p(len_, _I32), _p(off, _I32), _p(tok_row, _I32), _stream()),
+          'nnr_seq_prepare')
+
+
+def embed_gather_fwd(table, ids, len_, off, out, p_drop, seed):
+    N, L = ids.shape
+    V, E = table.shape
+    check(lib.nnr_embed_gather_fwd(_p(table, _F32), _p(ids, _I32), _p(len_, _I32), _p(off, _I32), N, L, E, V,
+                                   _p(out, _F32), float(p_drop), int(seed), _stream()), 'nnr_embed_gather_fwd')
+
+
+def embed_gather_bwd(dout, ids, len_, off, dtable, p_drop, seed, accumulate):
+    N, L = ids.shape
+    V, E = dtable.shape
+    nbytes = lib.nnr_embed_gather_bwd_workspace_bytes(N, L)
+    ws = workspace(nbytes, dout.device, 'embed')
+    check(lib.nnr_embed_gather_bwd(_p(dout, _F32), _p(ids, _I32), _p(len_, _I32), _p(off, _I32), N, L, E, V,
+                                   float(p_drop), int(seed), _p(dtable, _F32), int(accumulate), ws.data_ptr(),
+                                   ws.numel(), _stream()), 'nnr_embed_gather_bwd')
+
+
+def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, transA, transB, epilogue=EPI_NONE, accumulate=False, bias=None,
+         aux=None, ldaux=0, aux_out=None, ldaux_out=0, rowbias=None, ldrowbias=0, rowmap=None, m_dev=None,
+         k_dev=None, p_drop=0.0, seed=0, algo=ALGO_AUTO):
+    a = GemmArgs()
+    a.A, a.lda, a.transA = _p(A, _F32), lda, int(transA)
+    a.B, a.ldb, a.transB = _p(B, _F32), ldb, int(transB)
+    a.C, a.ldc = _p(Cout, _F32), ldc
+    a.M, a.N, a.K = M, N, K
+    a.m_dev, a.k_dev = _p(m_dev, _I32), _p(k_dev, _I32)
+    a.epilogue, a.accumulate = epilogue, int(accumulate)
+    a.bias = _p(bias, _F32)
+    a.aux, a.ldaux = _p(aux, _F32), ldaux
+    a.aux_out, a.ldaux_out = _p(aux_out, _F32), ldaux_out
+    a.rowbias, a.ldrowbias, a.rowmap = _p(rowbias, _F32), ldrowbias, _p(rowmap, _I32)
+    a.p_drop, a.seed, a.algo = float(p_drop), int(seed), algo
+    nbytes = lib.nnr_gemm_workspace_bytes(C.byref(a))
+    if nbytes:
+        ws = workspace(nbytes, A.device, 'gemm')
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    check(lib.nnr_gemm(C.byref(a), _stream()), 'nnr_gemm')
+
+
+def colsum(X, ldx, M, N, out, accumulate=False, m_dev=None):
+    nbytes = lib.nnr_colsum_workspace_bytes(M, N)
+    ws = workspace(nbytes, X.device, 'colsum')
+    check(lib.nnr_colsum(_p(X, _F32), ldx, M, N, _p(m_dev, _I32), _p(out, _F32), int(accumulate), ws.data_ptr(),
+                         ws.numel(), _stream()), 'nnr_colsum')
+
+
+def segment_colsum(X, ldx, off, N, D, out, ldo):
+    check(lib.nnr_segment_colsum(_p(X, _F32), ldx, _p(off, _I32), N, D, _p(out, _F32), ldo, _stream()),
+          'nnr_segment_colsum')
+
+
+def lstm_fwd(gx, w_hh, len_, off, order, N, L, H, h_out, c_stash, c_n):
+    check(lib.nnr_lstm_fwd(_p(gx, _F32), _p(w_hh, _F32), _p(len_, _I32), _p(off, _I32), _p(order, _I32), N, L, H,
+                           _p(h_out, _F32), _p(c_stash, _F32), _p(c_n, _F32), _stream()), 'nnr_lstm_fwd')
+
+
+def lstm_bwd(gates, c_stash, w_hh, len_, off, order, N, L, H, dh, dcn):
+    check(lib.nnr_lstm_bwd(_p(gates, _F32), _p(c_stash, _F32), _p(w_hh, _F32), _p(len_, _I32), _p(off, _I32),
+                           _p(order, _I32), N, L, H, _p(dh, _F32), _p(dcn, _F32), _stream()), 'nnr_lstm_bwd')
+
+
+def lstm_shift_h(h, len_, off, tok_row, N, L, H, hprev):
+    check(lib.nnr_lstm_shift_h(_p(h, _F32), _p(len_, _I32), _p(off, _I32), _p(tok_row, _I32), N, L, H,
+                               _p(hprev, _F32), _stream()), 'nnr_lstm_shift_h')
+
+
+def gate_bwd_pre(dhg, h, g, n_max, n_dev, D, dz, dh0):
+    check(lib.nnr_gate_bwd_pre(_p(dhg, _F32), _p(h, _F32), _p(g, _F32), n_max, _p(n_dev, _I32), D, _p(dz, _F32),
+                               _p(dh0, _F32), _stream()), 'nnr_gate_bwd_pre')
+
+
+def _pool_args(X, ldx, D, S, max_len, mode, seg_off=None, fixed_len=0, U=None, ldu=0, A=0, w2=None, qvec=None,
+               ldq=0, scale=1.0, mask=None, pooled=None, ldp=0, alpha=None, dpooled=None, lddp=0, dX=None, lddx=0,
+               accumulate_dx=False, dU=None, lddu=0, dw2_partial=None, dqvec=None, lddq=0):
+    a = PoolArgs()
+    a.X, a.ldx, a.D = _p(X, _F32), ldx, D
+    a.seg_off, a.S, a.fixed_len, a.max_len = _p(seg_off, _I32), S, fixed_len, max_len
+    a.mode = mode
+    a.U, a.ldu, a.A, a.w2 = _p(U, _F32), ldu, A, _p(w2, _F32)
+    a.qvec, a.ldq, a.scale = _p(qvec, _F32), ldq, float(scale)
+    a.mask = _p(mask, _U8)
+    a.pooled, a.ldp = _p(pooled, _F32), ldp
+    a.alpha = _p(alpha, _F32)
+    a.dpooled, a.lddp = _p(dpooled, _F32), lddp
+    a.dX, a.lddx, a.accumulate_dx = _p(dX, _F32), lddx, int(accumulate_dx)
+    a.dU, a.lddu = _p(dU, _F32), lddu
+    a.dw2_partial = _p(dw2_partial, _F32)
+    a.dqvec, a.lddq = _p(dqvec, _F32), lddq
+    return a
+
+
+def attn_pool_fwd(**kw):
+    a = _pool_args(**kw)
+    check(lib.nnr_attn_pool_fwd(C.byref(a), _stream()), 'nnr_attn_pool_fwd')
+
+
+def attn_pool_bwd(**kw):
+    a = _pool_args(**kw)
+    check(lib.nnr_attn_pool_bwd(C.byref(a), _stream()), 'nnr_attn_pool_bwd')
+
+
+def news_fuse_fwd(ts, tc, cs, cc, cat_table, sub_table, cat, sub, N, D2, p_drop, seed, out):
+    Ec, Es = cat_table.shape[1], sub_table.shape[1]
+    check(lib.nnr_news_fuse_fwd(_p(ts, _F32), _p(tc, _F32), _p(cs, _F32), _p(cc, _F32), _p(cat_table, _F32),
+                                _p(sub_table, _F32), _p(cat, _I32), _p(sub, _I32), N, D2, Ec, Es, float(p_drop),
+                                int(seed), _p(out, _F32), _stream()), 'nnr_news_fuse_fwd')
+
+
+def news_fuse_bwd(dout, cat, sub, N, D2, p_drop, seed, d_a, d_b, dcat_table, dsub_table, accumulate):
+    Ec, Es = dcat_table.shape[1], dsub_table.shape[1]
+    check(lib.nnr_news_fuse_bwd(_p(dout, _F32), _p(cat, _I32), _p(sub, _I32), N, D2, Ec, Es, dcat_table.shape[0],
+                                dsub_table.shape[0], float(p_drop), int(seed), _p(d_a, _F32), _p(d_b, _F32),
+                                _p(dcat_table, _F32), _p(dsub_table, _F32), int(accumulate), _stream()),
+          'nnr_news_fuse_bwd')
+
+
+def sue_graph_build(categories, history_len, C_num, graph=None, category_mask=None, category_indices=None):
+    B, H = categories.shape
+    check(lib.nnr_sue_graph_build(_p(categories, _I32), _p(history_len, _I32), B, H, C_num, _p(graph, _F32),
+                                  _p(category_mask, _U8), _p(category_indices, _I64), _stream()), 'nnr_sue_graph_build')
+
+
+def graph_to_csr(graph, transpose, nnz, col, val):
+    B, G, _ = graph.shape
+    check(lib.nnr_graph_to_csr(_p(graph, _F32), B, G, int(transpose), _p(nnz, _I32), _p(col, _I32), _p(val, _F32),
+                               _stream()), 'nnr_graph_to_csr')
+
+
+def gcn_aggregate(nnz, col, val, x, B, G, D, out):
+    check(lib.nnr_gcn_aggregate(_p(nnz, _I32), _p(col, _I32), _p(val, _F32), _p(x, _F32), B, G, D, _p(out, _F32),
+                                _stream()), 'nnr_gcn_aggregate')
+
+
+def cluster_intra_fwd(Kp, Qp, g, idx, B, n, H, Au, D, C1, scale, alpha, intra):
+    check(lib.nnr_cluster_intra_fwd(_p(Kp, _F32), _p(Qp, _F32), _p(g, _F32), _p(idx, _I64), B, n, H, Au, D, C1,
+                                    float(scale), _p(alpha, _F32), _p(intra, _F32), _stream()), 'nnr_cluster_intra_fwd')
+
+
+def cluster_intra_bwd(dintra, Kp, Qp, g, idx, alpha, B, n, H, Au, D, C1, scale, da_ws, dKp, dQp, dg, accumulate_dg):
+    check(lib.nnr_cluster_intra_bwd(_p(dintra, _F32), _p(Kp, _F32), _p(Qp, _F32), _p(g, _F32), _p(idx, _I64),
+                                    _p(alpha, _F32), B, n, H, Au, D, C1, float(scale), _p(da_ws, _F32), _p(dKp, _F32),
+                                    _p(dQp, _F32), _p(dg, _F32), int(accumulate_dg), _stream()), 'nnr_cluster_intra_bwd')
+
+
+def rowdot_fwd(a, b, R, D, out):
+    check(lib.nnr_rowdot_fwd(_p(a, _F32), _p(b, _F32), R, D, _p(out, _F32), _stream()), 'nnr_rowdot_fwd')
+
+
+def rowdot_bwd(dout, a, b, R, D, da, accumulate_a, db, accumulate_b):
+    check(lib.nnr_rowdot_bwd(_p(dout, _F32), _p(a, _F32), _p(b, _F32), R, D, _p(da, _F32), int(accumulate_a),
+                             _p(db, _F32), int(accumulate_b), _stream()), 'nnr_rowdot_bwd')
+
+
+def dropout(x, p_drop, seed, y):
+    check(lib.nnr_dropout(_p(x, _F32), x.numel(), float(p_drop), int(seed), _p(y, _F32), _stream()), 'nnr_dropout')
+
+
+def flat_clip_adam(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, max_norm, grad_scale, step, norm_out):
+    n = param.numel()
+    nbytes = lib.nnr_flat_clip_adam_workspace_bytes(n)
+    ws = workspace(nbytes, param.device, 'adam')
+    check(lib.nnr_flat_clip_adam(_p(param, _F32), _p(grad, _F32), _p(exp_avg, _F32), _p(exp_avg_sq, _F32), n, lr,
+                                 beta1, beta2, eps, max_norm, grad_scale, int(step), _p(norm_out, _F32),
+                                 ws.data_ptr(), ws.numel(), _stream()), 'nnr_flat_clip_adam')
+
+
+# --------------------------------------------------------------------------------------------
+# registration as torch custom ops (torch.ops.nnr.*), CUDA dispatch key only
+# --------------------------------------------------------------------------------------------
+_torch_lib = torch.library.Library('nnr', 'DEF')
+_SCHEMAS = {
+    'seq_prepare': ('(Tensor(a!) mask, Tensor(b!) len, Tensor(c!) off, Tensor(d!) tok_row) -> ()', seq_prepare),
+    'embed_gather_fwd': ('(Tensor table, Tensor ids, Tensor len, Tensor off, Tensor(a!) out, float p_drop, int seed) -> ()',
+                         embed_gather_fwd),
+    'embed_gather_bwd': ('(Tensor dout, Tensor ids, Tensor len, Tensor off, Tensor(a!) dtable, float p_drop, int seed, '
+                         'bool accumulate) -> ()', embed_gather_bwd),
+    'lstm_fwd': ('(Tensor(a!) gx, Tensor w_hh, Tensor len, Tensor off, Tensor order, int N, int L, int H, '
+                 'Tensor(b!) h_out, Tensor(c!) c_stash, Tensor(d!) c_n) -> ()', lstm_fwd),
+    'lstm_bwd': ('(Tensor(a!) gates, Tensor c_stash, Tensor w_hh, Tensor len, Tensor off, Tensor order, int N, int L, '
+                 'int H, Tensor dh, Tensor dcn) -> ()', lstm_bwd),
+    'lstm_shift_h': ('(Tensor h, Tensor len, Tensor off, Tensor tok_row, int N, int L, int H, Tensor(a!) hprev) -> ()',
+                     lstm_shift_h),
+    'gcn_aggregate': ('(Tensor nnz, Tensor col, Tensor val, Tensor x, int B, int G, int D, Tensor(a!) out) -> ()',
+                      gcn_aggregate),
+    'graph_to_csr': ('(Tensor graph, bool transpose, Tensor(a!) nnz, Tensor(b!) col, Tensor(c!) val) -> ()', graph_to_csr),
+    'cluster_intra_fwd': ('(Tensor Kp, Tensor Qp, Tensor g, Tensor idx, int B, int n, int H, int Au, int D, int C1, '
+                          'float scale, Tensor(a!) alpha, Tensor(b!) intra) -> ()', cluster_intra_fwd),
+    'rowdot_fwd': ('(Tensor a, Tensor b, int R, int D, Tensor(a!) out) -> ()', rowdot_fwd),
+    'dropout': ('(Tensor x, float p_drop, int seed, Tensor(a!) y) -> ()', dropout),
+    'flat_clip_adam': ('(Tensor(a!) param, Tensor grad, Tensor(b!) exp_avg, Tensor(c!) exp_avg_sq, float lr, float beta1, '
+                       'float beta2, float eps, float max_norm, float grad_scale, int step, Tensor(d!) norm_out) -> ()',
+                       flat_clip_adam),
+}
+
+
+def _noop(*a, **k):
+    return None
+
+
+for _name, (_schema, _fn) in _SCHEMAS.items():
+    _torch_lib.define(_name + _schema)
+    _torch_lib.impl(_name, _fn, 'CUDA')
+    _torch_lib.impl(_name, _noop, 'Meta')
+
+launch_count = _lib.launch_count

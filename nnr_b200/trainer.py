@@ -1,0 +1,75 @@
+"""The training-step contract of reference trainer.py:64-66,105-120 (single GPU) and :285-300 (DDP).
+
+    logits = model(*21 tensors); loss = mean(-log_softmax(logits)[:, 0]); zero_grad; backward;
+    clip_grad_norm_(params, 4); Adam(lr=1e-4).step()
+
+B200-native layout: all parameters live in ONE flat fp32 buffer (``param.data`` are views), gradients
+in a second flat buffer (``param.grad`` are views), Adam moments in two more.  Data parallelism is
+one process per GPU and exactly one ``ncclAllReduce`` over the flat gradient buffer per step
+(the reference's DDP issues bucketed all-reduces, trainer.py:219,297); the 1/world averaging is
+folded into the fused clip+Adam kernel (``nnr_flat_clip_adam``).
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def negative_log_softmax(logits):
+    """trainer.py:64-66"""
+    return (-torch.log_softmax(logits, dim=1).select(dim=1, index=0)).mean()
+
+
+class TrainStep:
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, gradient_clip_norm=4.0, process_group=None,
+                 world_size=None):
+        self.model = model
+        self.lr, self.betas, self.eps, self.max_norm = lr, betas, eps, gradient_clip_norm
+        self.pg = process_group
+        if world_size is None:
+            world_size = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.world_size = world_size
+        params = [p for p in model.parameters() if p.requires_grad]
+        dev = params[0].device
+        if dev.type != 'cuda':
+            raise RuntimeError('nnr_b200.TrainStep needs the model on a CUDA device')
+        sizes = [(p.numel() + 3) // 4 * 4 for p in params]            # keep every slice 16-byte aligned
+        total = sum(sizes)
+        self.flat = torch.zeros(total, device=dev)
+        self.gflat = torch.zeros(total, device=dev)
+        self.exp_avg = torch.zeros(total, device=dev)
+        self.exp_avg_sq = torch.zeros(total, device=dev)
+        o = 0
+        for p, s in zip(params, sizes):
+            n = p.numel()
+            self.flat[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + n].view(p.shape)
+            p.grad = self.gflat[o:o + n].view(p.shape)
+            o += s
+        self.params = params
+        self.step_count = 0
+        self.grad_norm = torch.zeros(1, device=dev)
+
+    def zero_grad(self):
+        self.gflat.zero_()
+        for p in self.params:                                          # keep .grad bound to the flat views
+            if p.grad is None or p.grad.data_ptr() < self.gflat.data_ptr() or \
+                    p.grad.data_ptr() >= self.gflat.data_ptr() + self.gflat.numel() * 4:
+                raise RuntimeError('parameter .grad was rebound; use TrainStep.zero_grad() only')
+
+    def step(self, *batch):
+        """one full training step; returns the (device) loss tensor without synchronising"""
+        self.model.train()
+        logits = self.model(*batch)
+        loss = negative_log_softmax(logits)
+        self.gflat.zero_()
+        loss.backward()
+        self.optimizer_step()
+        return loss
+
+    def optimizer_step(self):
+        if self.world_size > 1:
+            dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)     # the single collective of the step
+        self.step_count += 1
+        ops.flat_clip_adam(self.flat, self.gflat, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
+                           self.eps, self.max_norm, 1.0 / self.world_size, self.step_count, self.grad_norm)

@@ -1,0 +1,38 @@
+"""Ablation variants that run through the same kernels (reference variantEncoders.py:263-339, 393-419)."""
+import torch.nn as nn
+
+from .layers import GCN, Attention
+from .newsEncoders import CNE
+from .userEncoders import SUE, UserEncoder
+
+
+class CNE_wo_CA(CNE):
+    """CNE without cross attention: output [title_self | content_self]; gate weights Xavier with gain 1."""
+    cross_attention = False
+    gate_gain = None
+
+
+class SUE_wo_HCA(UserEncoder):
+    """GCN + plain additive attention over the history rows (no mask), repeated over candidates."""
+    hca = False
+    _params = SUE._params
+    forward = SUE.forward
+
+    def __init__(self, news_encoder, config):
+        super().__init__(news_encoder, config)
+        import torch
+        self.max_history_num = config.max_history_num
+        self.proxy_node_embedding = nn.Parameter(torch.zeros([config.category_num, self.news_embedding_dim]))
+        self.gcn = GCN(in_dim=self.news_embedding_dim, out_dim=self.news_embedding_dim, hidden_dim=self.news_embedding_dim,
+                       num_layers=config.gcn_layer_num, dropout=config.dropout_rate / 2, residual=not config.no_gcn_residual,
+                       layer_norm=config.gcn_layer_norm)
+        self.attention = Attention(self.news_embedding_dim, config.attention_dim)
+        self.dropout_rate = config.dropout_rate
+        self.dropout_ = nn.Dropout(p=config.dropout_rate, inplace=False)
+        self.gcn_layer_num = config.gcn_layer_num
+        self.gcn_residual = not config.no_gcn_residual
+
+    def initialize(self):
+        nn.init.zeros_(self.proxy_node_embedding)
+        self.gcn.initialize()
+        self.attention.initialize()

@@ -1,0 +1,58 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/nnr_b200.h declares."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, 'include', 'nnr_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(nnr_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from nnr_b200 import _lib
+    syms = declared_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(_lib.lib, s), 'missing symbol ' + s
+        assert s in _lib.SIGNATURES, 'no ctypes signature for ' + s
+    assert _lib.lib.nnr_abi_version() == 1
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    from nnr_b200 import _lib
+    rc = _lib.lib.nnr_seq_prepare(None, 0, 0, None, None, None, None)
+    assert rc < 0
+    assert b'nnr_seq_prepare' in _lib.lib.nnr_last_error()
+    a = _lib.GemmArgs()
+    assert _lib.lib.nnr_gemm(ctypes.byref(a), None) < 0
+
+
+def test_ops_reject_cpu_tensors():
+    import pytest
+    import torch
+    from nnr_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.rowdot_fwd(torch.zeros(2, 4), torch.zeros(2, 4), 2, 4, torch.zeros(2))
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        torch.ops.nnr.rowdot_fwd(torch.zeros(2, 4), torch.zeros(2, 4), 2, 4, torch.zeros(2))
+
+
+def test_state_dict_contract():
+    import torch
+    import nnr_b200
+    from oracle import nnr_oracle as O
+    cfg = O.make_config(vocabulary_size=300)
+    cfg.pretrained_word_embedding = torch.zeros(300, 300)
+    m = nnr_b200.Model(cfg)
+    m.initialize()
+    want = O.alias_state_dict(O.formula_params(cfg))
+    sd = m.state_dict()
+    assert set(sd) == set(want)
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(want[k].shape), k
+    assert m.model_name == 'CNE-SUE' and m.news_encoder.auxiliary_loss is None and m.user_encoder.auxiliary_loss is None
+    assert m.news_embedding_dim == 900

@@ -1,0 +1,487 @@
+"""GPU parity tests of the individual C-ABI ops (called through nnr_b200.ops -> ctypes -> libnnr_b200.so).
+
+Integer / index outputs are compared bit-exactly; floating point against fp64 torch math with the
+tolerance stated in each test.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph as OG
+from oracle import nnr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from nnr_b200 import ops
+    return ops
+
+
+def _prefix_masks(N, L, gen, allow_empty=True):
+    lens = torch.randint(0 if allow_empty else 1, L + 1, (N,), generator=gen)
+    return (torch.arange(L)[None, :] < lens[:, None]), lens
+
+
+# ---------------------------------------------------------------------------------------------
+def test_seq_prepare_bit_exact(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(0)
+    for N, L in [(1, 1), (7, 5), (320, 32), (3200, 128), (1500, 33)]:
+        mask, lens = _prefix_masks(N, L, g)
+        m = mask.to(cuda)
+        len_ = torch.empty(N, dtype=torch.int32, device=cuda)
+        off = torch.empty(N + 1, dtype=torch.int32, device=cuda)
+        tok_row = torch.full((N * L,), -1, dtype=torch.int32, device=cuda)
+        ops.seq_prepare(m, len_, off, tok_row)
+        ref_len = lens.clamp(min=1)
+        assert torch.equal(len_.cpu().long(), ref_len)
+        ref_off = torch.cat([torch.zeros(1, dtype=torch.long), ref_len.cumsum(0)])
+        assert torch.equal(off.cpu().long(), ref_off)
+        ref_rows = torch.repeat_interleave(torch.arange(N), ref_len)
+        assert torch.equal(tok_row.cpu()[:ref_rows.numel()].long(), ref_rows)
+        assert torch.all(m[:, 0])                                   # mutated in place like the reference
+
+
+def _packed(x, lens):
+    return torch.cat([x[r, :lens[r]] for r in range(x.shape[0])], 0)
+
+
+def test_embed_gather_fwd_bwd(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(1)
+    for (N, L, V, E) in [(37, 12, 50, 300), (400, 128, 60, 300), (64, 32, 5000, 300), (33, 7, 20, 52)]:
+        mask, lens = _prefix_masks(N, L, g, allow_empty=False)
+        ids = torch.randint(0, V, (N, L), generator=g, dtype=torch.int32)
+        table = torch.randn(V, E, generator=g)
+        d = dict(device=cuda)
+        len_ = lens.to(torch.int32).to(cuda)
+        off = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)]).to(torch.int32).to(cuda)
+        ntok = int(lens.sum())
+        out = torch.zeros(N * L, E, **d)
+        ops.embed_gather_fwd(table.to(cuda), ids.to(cuda), len_, off, out, 0.0, 0)
+        ref = _packed(table[ids.long()], lens)
+        assert torch.equal(out[:ntok].cpu(), ref)                  # pure copy: bit exact
+        # backward: dense table gradient == index_add in fp64
+        dout = torch.randn(N * L, E, generator=g)
+        dtab = torch.empty(V, E, **d)
+        ops.embed_gather_bwd(dout.to(cuda), ids.to(cuda), len_, off, dtab, 0.0, 0, False)
+        ref_g = torch.zeros(V, E, dtype=torch.float64)
+        ref_g.index_add_(0, _packed(ids.long().unsqueeze(-1), lens).squeeze(-1), dout[:ntok].double())
+        err = (dtab.cpu().double() - ref_g).abs().max().item() / max(ref_g.abs().max().item(), 1e-30)
+        assert err < 2e-6, (N, L, V, err)
+        # deterministic: bit-identical when repeated; accumulate doubles it
+        dtab2 = torch.empty(V, E, **d)
+        ops.embed_gather_bwd(dout.to(cuda), ids.to(cuda), len_, off, dtab2, 0.0, 0, False)
+        assert torch.equal(dtab, dtab2)
+        ops.embed_gather_bwd(dout.to(cuda), ids.to(cuda), len_, off, dtab2, 0.0, 0, True)
+        assert torch.allclose(dtab2, 2 * dtab, rtol=1e-6, atol=1e-6)
+
+
+def test_embed_dropout_consistency(cuda):
+    ops = _ops()
+    N, L, V, E, p = 64, 16, 100, 300, 0.2
+    g = torch.Generator().manual_seed(2)
+    lens = torch.full((N,), L)
+    len_ = lens.to(torch.int32).to(cuda)
+    off = (torch.arange(N + 1) * L).to(torch.int32).to(cuda)
+    ids = torch.randint(1, V, (N, L), generator=g, dtype=torch.int32).to(cuda)
+    table = torch.ones(V, E, device=cuda)
+    out = torch.empty(N * L, E, device=cuda)
+    ops.embed_gather_fwd(table, ids, len_, off, out, p, 1234)
+    keep = (out != 0)
+    assert abs(keep.float().mean().item() - (1 - p)) < 0.01
+    assert torch.allclose(out[keep], torch.full_like(out[keep], 1 / (1 - p)))
+    out2 = torch.empty_like(out)
+    ops.embed_gather_fwd(table, ids, len_, off, out2, p, 1234)
+    assert torch.equal(out, out2)                                    # same seed -> same mask
+    ops.embed_gather_fwd(table, ids, len_, off, out2, p, 99)
+    assert not torch.equal(out, out2)
+    # backward uses the same mask: d table = sum over tokens of dout * mask/(1-p)
+    dtab = torch.empty(V, E, device=cuda)
+    ops.embed_gather_bwd(torch.ones_like(out), ids, len_, off, dtab, p, 1234, False)
+    ref = torch.zeros(V, E, device=cuda, dtype=torch.float64)
+    ref.index_add_(0, ids.view(-1).long(), out.double())
+    assert torch.allclose(dtab.double(), ref, rtol=1e-5, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+def _gemm_ref(A, B, transA, transB):
+    a = A.double().t() if transA else A.double()
+    b = B.double().t() if transB else B.double()
+    return a @ b
+
+
+@pytest.mark.parametrize('algo', [1])
+def test_gemm_layouts_and_shapes(cuda, algo):
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    shapes = [(77, 225, 900), (128, 128, 16), (300, 1600, 300), (1, 5, 3), (513, 400, 400), (260, 200, 225), (64, 900, 225)]
+    for (M, N, K) in shapes:
+        for transA in (False, True):
+            for transB in (False, True):
+                A = torch.randn((K, M) if transA else (M, K), generator=g).to(cuda)
+                B = torch.randn((N, K) if transB else (K, N), generator=g).to(cuda)
+                Cc = torch.full((M, N), float('nan'), device=cuda)
+                ops.gemm(A, B, Cc, M, N, K, A.stride(0), B.stride(0), N, transA, transB, algo=algo)
+                ref = _gemm_ref(A, B, transA, transB)
+                err = (Cc.double() - ref).abs().max().item() / ref.abs().max().item()
+                assert err < 2e-6, (M, N, K, transA, transB, err)
+
+
+def test_gemm_splitk_and_device_bounds(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    M, N, K = 40000, 300, 800                                        # wgrad shape: contraction over M rows
+    dy = torch.randn(M, N, generator=g).to(cuda)
+    x = torch.randn(M, K, generator=g).to(cuda)
+    for kd in (M, 12345, 1):
+        k_dev = torch.tensor([kd], dtype=torch.int32, device=cuda)
+        out = torch.empty(N, K, device=cuda)
+        ops.gemm(dy, x, out, N, K, M, N, K, K, True, False, k_dev=k_dev, algo=1)
+        ref = dy[:kd].double().t() @ x[:kd].double()
+        err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 5e-6, (kd, err)
+        out2 = torch.empty(N, K, device=cuda)
+        ops.gemm(dy, x, out2, N, K, M, N, K, K, True, False, k_dev=k_dev, algo=1)
+        assert torch.equal(out, out2)                                # deterministic split-K
+    # m_dev: rows beyond *m_dev are not written
+    W = torch.randn(200, K, generator=g).to(cuda)
+    out = torch.full((M, 200), 7.0, device=cuda)
+    m_dev = torch.tensor([777], dtype=torch.int32, device=cuda)
+    ops.gemm(x, W, out, M, 200, K, K, K, 200, False, True, m_dev=m_dev, algo=1)
+    ref = x[:777].double() @ W.double().t()
+    assert (out[:777].double() - ref).abs().max().item() / ref.abs().max().item() < 2e-6
+    assert torch.all(out[777:] == 7.0)
+
+
+def test_gemm_epilogues(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 333, 400, 400
+    A = torch.randn(M, K, generator=g).to(cuda)
+    W = (torch.randn(N, K, generator=g) / 20).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    aux = torch.randn(M, N, generator=g).to(cuda)
+    acc = A.double() @ W.double().t()
+
+    def run(epi, **kw):
+        out = torch.empty(M, N, device=cuda)
+        ops.gemm(A, W, out, M, N, K, K, K, N, False, True, epi, algo=1, **kw)
+        return out
+
+    tol = 2e-6
+    assert (run(ops.EPI_BIAS, bias=bias).double() - (acc + bias.double())).abs().max() < 1e-4
+    assert (run(ops.EPI_BIAS_TANH, bias=bias).double() - torch.tanh(acc + bias.double())).abs().max() < 1e-5
+    r_out = torch.empty(M, N, device=cuda)
+    o = run(ops.EPI_BIAS_RELU_RES, bias=bias, aux=aux, ldaux=N, aux_out=r_out, ldaux_out=N)
+    r_ref = torch.relu(acc + bias.double())
+    assert (r_out.double() - r_ref).abs().max() < 1e-4
+    assert (o.double() - (r_ref + aux.double())).abs().max() < 1e-4
+    o = run(ops.EPI_ADD_AUX, aux=aux, ldaux=N)
+    assert (o.double() - (acc + aux.double())).abs().max() < 1e-4
+    # gate: rows map to 10 "news" rows
+    rowmap = torch.randint(0, 10, (M,), generator=g, dtype=torch.int32).to(cuda)
+    rowbias = torch.randn(10, N, generator=g).to(cuda)
+    g_out = torch.empty(M, N, device=cuda)
+    o = run(ops.EPI_GATE, rowbias=rowbias, ldrowbias=N, rowmap=rowmap, aux=aux, ldaux=N, aux_out=g_out, ldaux_out=N)
+    gate = torch.sigmoid(acc + rowbias.double()[rowmap.long()])
+    assert (g_out.double() - gate).abs().max() < 1e-5
+    assert (o.double() - aux.double() * gate).abs().max() < 1e-5
+    # accumulate
+    base = torch.randn(M, N, generator=g).to(cuda)
+    out = base.clone()
+    ops.gemm(A, W, out, M, N, K, K, K, N, False, True, ops.EPI_NONE, accumulate=True, algo=1)
+    assert (out.double() - (base.double() + acc)).abs().max() < 1e-4
+    # dropout in the relu/residual epilogue: kept entries scaled by 1/(1-p)
+    o2 = run(ops.EPI_BIAS_RELU_RES, bias=bias, aux=aux, ldaux=N, p_drop=0.25, seed=77)
+    full = (r_ref + aux.double())
+    kept = o2 != 0
+    assert abs(kept.float().mean().item() - 0.75) < 0.02
+    assert (o2.double()[kept] - full[kept] / 0.75).abs().max() < 1e-4
+    y = torch.empty(M * N, device=cuda)
+    ops.dropout(torch.ones(M * N, device=cuda), 0.25, 77, y)         # same counter RNG, same indexing
+    assert torch.equal((y != 0).view(M, N) | (full.float() == 0).to(cuda), kept | (full.float() == 0).to(cuda))
+
+
+def test_colsum_and_segment_colsum(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(6)
+    X = torch.randn(5000, 333, generator=g).to(cuda)
+    out = torch.empty(333, device=cuda)
+    ops.colsum(X, 333, 5000, 333, out)
+    assert (out.double() - X.double().sum(0)).abs().max() < 1e-3
+    m_dev = torch.tensor([1234], dtype=torch.int32, device=cuda)
+    ops.colsum(X, 333, 5000, 333, out, False, m_dev)
+    assert (out.double() - X[:1234].double().sum(0)).abs().max() < 1e-3
+    lens = torch.randint(1, 20, (100,), generator=g)
+    off = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)]).to(torch.int32).to(cuda)
+    seg = torch.empty(100, 333, device=cuda)
+    ops.segment_colsum(X, 333, off, 100, 333, seg, 333)
+    ref = torch.stack([X[int(off[i]):int(off[i + 1])].double().sum(0) for i in range(100)])
+    assert (seg.double() - ref).abs().max() < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+def _lstm_setup(N, L, Hd, E, g, full=False):
+    lens = torch.full((N,), L) if full else torch.randint(1, L + 1, (N,), generator=g)
+    x = torch.randn(N, L, E, generator=g) * 0.5
+    w = {}
+    for sfx in ('', '_reverse'):
+        w['weight_ih_l0' + sfx] = torch.randn(4 * Hd, E, generator=g) / math.sqrt(E)
+        w['weight_hh_l0' + sfx] = torch.randn(4 * Hd, Hd, generator=g) / math.sqrt(Hd)
+        w['bias_ih_l0' + sfx] = torch.randn(4 * Hd, generator=g) * 0.1
+        w['bias_hh_l0' + sfx] = torch.randn(4 * Hd, generator=g) * 0.1
+    return lens, x, w
+
+
+@pytest.mark.parametrize('N,L,full', [(70, 12, False), (32, 9, True), (129, 33, False), (5, 128, False)])
+def test_lstm_forward_backward(cuda, N, L, full):
+    ops = _ops()
+    Hd, E = 200, 24
+    g = torch.Generator().manual_seed(7 + N)
+    lens, x, w = _lstm_setup(N, L, Hd, E, g, full)
+    # oracle (fp64 loop restatement) with autograd
+    x64 = x.double().requires_grad_(True)
+    w64 = {k: v.double().requires_grad_(True) for k, v in w.items()}
+    h_ref, m_ref = O.bilstm(w64, '', x64, lens)
+    dh = torch.randn(N, L, 2 * Hd, generator=g)
+    dcn = torch.randn(N, 2 * Hd, generator=g)
+    valid = (torch.arange(L)[None, :] < lens[:, None])
+    ((h_ref * (dh.double() * valid[..., None])).sum() + (m_ref * dcn.double()).sum()).backward()
+    # device
+    len_ = lens.to(torch.int32).to(cuda)
+    off_l = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)])
+    off = off_l.to(torch.int32).to(cuda)
+    ntok = int(lens.sum())
+    order = torch.sort(lens, descending=True, stable=True)[1].to(torch.int32).to(cuda)
+    w_ih = torch.cat([w['weight_ih_l0'], w['weight_ih_l0_reverse']], 0)
+    b = torch.cat([w['bias_ih_l0'] + w['bias_hh_l0'], w['bias_ih_l0_reverse'] + w['bias_hh_l0_reverse']], 0)
+    xp = _packed(x, lens)
+    gx = (xp @ w_ih.t() + b).to(cuda).contiguous()                    # [ntok, 8H]
+    gx_full = torch.zeros(N * L, 8 * Hd, device=cuda)
+    gx_full[:ntok] = gx
+    w_hh = torch.stack([w['weight_hh_l0'], w['weight_hh_l0_reverse']], 0).to(cuda).contiguous()
+    h = torch.zeros(N * L, 2 * Hd, device=cuda)
+    cst = torch.zeros(N * L, 2 * Hd, device=cuda)
+    cn = torch.zeros(N, 2 * Hd, device=cuda)
+    ops.lstm_fwd(gx_full, w_hh, len_, off, order, N, L, Hd, h, cst, cn)
+    torch.cuda.synchronize()
+    h_ref_p = _packed(h_ref.detach(), lens)
+    e_h = (h[:ntok].cpu().double() - h_ref_p).abs().max().item()
+    e_c = (cn.cpu().double() - m_ref.detach()).abs().max().item()
+    assert e_h < 5e-6 and e_c < 2e-5, (e_h, e_c)
+    # backward
+    dh_p = torch.zeros(N * L, 2 * Hd, device=cuda)
+    dh_p[:ntok] = _packed(dh, lens).to(cuda)
+    ops.lstm_bwd(gx_full, cst, w_hh, len_, off, order, N, L, Hd, dh_p, dcn.to(cuda).contiguous())
+    torch.cuda.synchronize()
+    dgx = gx_full[:ntok].cpu().double()                               # dL/dgx, packed
+    # reference dL/dgx via the chain rule on x: dgx @ w_ih == dx  and dgx^T x == dW_ih
+    dW_ref = torch.cat([w64['weight_ih_l0'].grad, w64['weight_ih_l0_reverse'].grad], 0)
+    dW = dgx.t() @ xp.double()
+    assert (dW - dW_ref).abs().max().item() / dW_ref.abs().max().item() < 2e-5
+    db_ref = torch.cat([w64['bias_ih_l0'].grad, w64['bias_ih_l0_reverse'].grad], 0)
+    assert (dgx.sum(0) - db_ref).abs().max().item() / db_ref.abs().max().item() < 2e-5
+    dx_ref = _packed(x64.grad, lens)
+    dx = dgx @ w_ih.double()
+    assert (dx - dx_ref).abs().max().item() / dx_ref.abs().max().item() < 2e-5
+    # dW_hh through the shifted hidden states
+    tok_row = torch.repeat_interleave(torch.arange(N), lens).to(torch.int32).to(cuda)
+    hprev = torch.empty(N * L, 2 * Hd, device=cuda)
+    ops.lstm_shift_h(h, len_, off, tok_row, N, L, Hd, hprev)
+    hp = hprev[:ntok].cpu().double()
+    for d, sfx in enumerate(('', '_reverse')):
+        dWhh = dgx[:, d * 4 * Hd:(d + 1) * 4 * Hd].t() @ hp[:, d * Hd:(d + 1) * Hd]
+        ref = w64['weight_hh_l0' + sfx].grad
+        assert (dWhh - ref).abs().max().item() / ref.abs().max().item() < 2e-5, sfx
+
+
+# ---------------------------------------------------------------------------------------------
+def test_attn_pool_modes(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(8)
+    S, Lmax, D, A = 37, 20, 400, 200
+    lens = torch.randint(1, Lmax + 1, (S,), generator=g)
+    off_l = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)])
+    tot = int(off_l[-1])
+    off = off_l.to(torch.int32).to(cuda)
+    X = torch.randn(tot, D, generator=g)
+    U = torch.tanh(torch.randn(tot, A, generator=g))
+    w2 = torch.randn(1, A, generator=g) / 10
+    q = torch.randn(S, D, generator=g) / 10
+    dp = torch.randn(S, D, generator=g)
+    scale = 1 / math.sqrt(200.0)
+    seg = torch.repeat_interleave(torch.arange(S), lens)
+    for mode in (0, 1):
+        X64 = X.double().requires_grad_(True)
+        U64 = U.double().requires_grad_(True)
+        w64 = w2.double().requires_grad_(True)
+        q64 = q.double().requires_grad_(True)
+        sc = (U64 @ w64.t()).squeeze(1) if mode == 0 else (X64 * q64[seg]).sum(1) * scale
+        pooled_ref = []
+        alpha_ref = torch.zeros(tot, dtype=torch.float64)
+        for s in range(S):
+            a, b = int(off_l[s]), int(off_l[s + 1])
+            al = torch.softmax(sc[a:b], 0)
+            pooled_ref.append(al @ X64[a:b])
+        pooled_ref = torch.stack(pooled_ref)
+        (pooled_ref * dp.double()).sum().backward()
+        Xc, Uc = X.to(cuda), U.to(cuda)
+        pooled = torch.empty(S, D, device=cuda)
+        alpha = torch.empty(tot, device=cuda)
+        kw = dict(X=Xc, ldx=D, D=D, S=S, max_len=Lmax, mode=mode, seg_off=off, U=Uc, ldu=A, A=A, w2=w2.to(cuda),
+                  qvec=q.to(cuda), ldq=D, scale=scale)
+        ops.attn_pool_fwd(pooled=pooled, ldp=D, alpha=alpha, **kw)
+        assert (pooled.cpu().double() - pooled_ref.detach()).abs().max() < 1e-5
+        dX = torch.empty(tot, D, device=cuda)
+        dU = torch.empty(tot, A, device=cuda)
+        dw2p = torch.empty(S, A, device=cuda)
+        dq = torch.empty(S, D, device=cuda)
+        ops.attn_pool_bwd(alpha=alpha, dpooled=dp.to(cuda), lddp=D, dX=dX, lddx=D, accumulate_dx=False, dU=dU, lddu=A,
+                          dw2_partial=dw2p, dqvec=dq, lddq=D, **kw)
+        assert (dX.cpu().double() - X64.grad).abs().max() < 2e-5
+        if mode == 0:
+            # dU is dL/d(pre-tanh): compare through U = tanh(z)
+            assert (dU.cpu().double() - U64.grad * (1 - U.double() ** 2)).abs().max() < 2e-5
+            assert (dw2p.sum(0).cpu().double() - w64.grad.squeeze(0)).abs().max() < 2e-4
+        else:
+            assert (dq.cpu().double() - q64.grad).abs().max() < 2e-5
+        dX2 = dX.clone()
+        ops.attn_pool_bwd(alpha=alpha, dpooled=dp.to(cuda), lddp=D, dX=dX2, lddx=D, accumulate_dx=True, dU=dU, lddu=A,
+                          dw2_partial=dw2p, dqvec=dq, lddq=D, **kw)
+        assert torch.allclose(dX2, 2 * dX, rtol=1e-5, atol=1e-6)
+
+
+def test_attn_pool_fixed_len_mask(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    S, C1, D = 23, 19, 900
+    X = torch.randn(S * C1, D, generator=g)
+    q = torch.randn(S, D, generator=g) / 30
+    mask = torch.rand(S, C1, generator=g) < 0.5
+    mask[:, -1] = True
+    sc = (X.view(S, C1, D) * q[:, None, :]).sum(2) / 15.0
+    al = torch.softmax(sc.masked_fill(~mask, -1e9), 1)
+    ref = torch.bmm(al.unsqueeze(1), X.view(S, C1, D)).squeeze(1)
+    pooled = torch.empty(S, D, device=cuda)
+    alpha = torch.empty(S * C1, device=cuda)
+    ops.attn_pool_fwd(X=X.to(cuda), ldx=D, D=D, S=S, max_len=C1, mode=1, fixed_len=C1, qvec=q.to(cuda), ldq=D,
+                      scale=1 / 15.0, mask=mask.to(cuda).view(-1), pooled=pooled, ldp=D, alpha=alpha)
+    assert (pooled.cpu() - ref).abs().max() < 1e-5
+    assert torch.all(alpha.view(S, C1).cpu()[~mask] == 0)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_graph_build_bit_exact_and_aggregate(cuda):
+    ops = _ops()
+    rng = np.random.default_rng(10)
+    B, H, C, D = 40, 50, 18, 900
+    cats = rng.integers(0, C, size=(B, H)).astype(np.int32)
+    hl = rng.integers(0, H + 1, size=B).astype(np.int32)
+    hl[:3] = [0, 1, H]
+    G_ = H + C
+    graph = torch.empty(B, G_, G_, device=cuda)
+    cmask = torch.empty(B, C + 1, dtype=torch.bool, device=cuda)
+    cidx = torch.empty(B, H, dtype=torch.int64, device=cuda)
+    ops.sue_graph_build(torch.from_numpy(cats).to(cuda), torch.from_numpy(hl).to(cuda), C, graph, cmask, cidx)
+    for b in range(B):
+        g, m, i = OG.build_history_graph(cats[b, :hl[b]], H, C)
+        assert np.array_equal(g, graph[b].cpu().numpy()), b           # bit exact fp32 values
+        assert np.array_equal(m, cmask[b].cpu().numpy()), b
+        assert np.array_equal(i, cidx[b].cpu().numpy()), b
+    # dense -> neighbour lists -> aggregation == bmm
+    x = torch.randn(B, G_, D, device=cuda)
+    for transpose in (False, True):
+        nnz = torch.empty(B * G_, dtype=torch.int32, device=cuda)
+        col = torch.empty(B * G_, G_, dtype=torch.int32, device=cuda)
+        val = torch.empty(B * G_, G_, device=cuda)
+        ops.graph_to_csr(graph, transpose, nnz, col, val)
+        gm = graph.transpose(1, 2) if transpose else graph
+        assert torch.equal(nnz.view(B, G_).long(), (gm != 0).sum(2))
+        out = torch.empty(B * G_, D, device=cuda)
+        ops.gcn_aggregate(nnz, col, val, x, B, G_, D, out)
+        ref = torch.bmm(gm.double(), x.double())
+        assert (out.view(B, G_, D).double() - ref).abs().max() < 1e-5
+
+
+def test_cluster_intra_attention(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    B, n, H, Au, D, C1 = 5, 3, 50, 225, 900, 19
+    Kp = torch.randn(B, H, Au, generator=g) / 4
+    Qp = torch.randn(B, n, Au, generator=g) / 4
+    gf = torch.randn(B, H, D, generator=g)
+    idx = torch.randint(0, C1, (B, H), generator=g)
+    idx[0, :] = 18
+    scale = 1 / 15.0
+    K64, Q64, g64 = (t.double().requires_grad_(True) for t in (Kp, Qp, gf))
+    a = torch.einsum('bha,bka->bkh', K64, Q64) * scale
+    ix = idx.unsqueeze(1).expand(-1, n, -1)
+    alpha_ref = O.scatter_softmax(a, ix, 2)
+    intra_ref = O.scatter_sum(alpha_ref.unsqueeze(3) * g64.unsqueeze(1), ix, 2, C1)
+    dintra = torch.randn(B, n, C1, D, generator=g)
+    (intra_ref * dintra.double()).sum().backward()
+    alpha = torch.empty(B * n, H, device=cuda)
+    intra = torch.empty(B * n * C1, D, device=cuda)
+    c = lambda t: t.to(cuda).contiguous()
+    ops.cluster_intra_fwd(c(Kp), c(Qp), c(gf), c(idx), B, n, H, Au, D, C1, scale, alpha, intra)
+    assert (alpha.view(B, n, H).cpu().double() - alpha_ref.detach()).abs().max() < 1e-6
+    assert (intra.view(B, n, C1, D).cpu().double() - intra_ref.detach()).abs().max() < 1e-5
+    da = torch.empty(B * n, H, device=cuda)
+    dKp, dQp, dg = torch.empty(B * H, Au, device=cuda), torch.empty(B * n, Au, device=cuda), torch.empty(B * H, D, device=cuda)
+    ops.cluster_intra_bwd(c(dintra).view(-1, D), c(Kp), c(Qp), c(gf), c(idx), alpha, B, n, H, Au, D, C1, scale, da, dKp, dQp, dg, False)
+    assert (dKp.view(B, H, Au).cpu().double() - K64.grad).abs().max() < 2e-5
+    assert (dQp.view(B, n, Au).cpu().double() - Q64.grad).abs().max() < 2e-5
+    assert (dg.view(B, H, D).cpu().double() - g64.grad).abs().max() < 2e-5
+
+
+def test_news_fuse_and_rowdot(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(12)
+    N, D2, Ec, Es, nc, ns = 45, 400, 50, 50, 18, 30
+    ts, tc, cs, cc = (torch.randn(N, D2, generator=g).to(cuda) for _ in range(4))
+    ct, st = torch.randn(nc, Ec, generator=g).to(cuda), torch.randn(ns, Es, generator=g).to(cuda)
+    cat = torch.randint(0, nc, (N,), generator=g, dtype=torch.int32).to(cuda)
+    sub = torch.randint(0, ns, (N,), generator=g, dtype=torch.int32).to(cuda)
+    out = torch.empty(N, 2 * D2 + Ec + Es, device=cuda)
+    ops.news_fuse_fwd(ts, tc, cs, cc, ct, st, cat, sub, N, D2, 0.0, 0, out)
+    ref = torch.cat([ts + tc, cs + cc, ct[cat.long()], st[sub.long()]], 1)
+    assert torch.equal(out, ref)
+    dout = torch.randn_like(out)
+    d_a, d_b = torch.empty(N, D2, device=cuda), torch.empty(N, D2, device=cuda)
+    dct, dst = torch.empty_like(ct), torch.empty_like(st)
+    ops.news_fuse_bwd(dout, cat, sub, N, D2, 0.0, 0, d_a, d_b, dct, dst, False)
+    assert torch.equal(d_a, dout[:, :D2]) and torch.equal(d_b, dout[:, D2:2 * D2])
+    ref_c = torch.zeros_like(ct).index_add_(0, cat.long(), dout[:, 2 * D2:2 * D2 + Ec])
+    ref_s = torch.zeros_like(st).index_add_(0, sub.long(), dout[:, 2 * D2 + Ec:])
+    assert torch.allclose(dct, ref_c, atol=1e-5) and torch.allclose(dst, ref_s, atol=1e-5)
+    a, b = torch.randn(77, 900, generator=g).to(cuda), torch.randn(77, 900, generator=g).to(cuda)
+    o = torch.empty(77, device=cuda)
+    ops.rowdot_fwd(a, b, 77, 900, o)
+    assert torch.allclose(o, (a * b).sum(1), atol=1e-4)
+    do = torch.randn(77, device=cuda)
+    da, db = torch.empty_like(a), torch.empty_like(b)
+    ops.rowdot_bwd(do, a, b, 77, 900, da, False, db, False)
+    assert torch.allclose(da, do[:, None] * b) and torch.allclose(db, do[:, None] * a)
+
+
+def test_flat_clip_adam_matches_torch(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(13)
+    n = 100003
+    w = torch.randn(n, generator=g).to(cuda)
+    ref = w.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    m, v = torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+    norm = torch.zeros(1, device=cuda)
+    for step in range(1, 5):
+        grad = (torch.randn(n, generator=g) * (0.5 if step % 2 else 0.001)).to(cuda)
+        ref.grad = grad.clone()
+        total = torch.nn.utils.clip_grad_norm_([ref], 4.0)
+        opt.step()
+        ops.flat_clip_adam(w, grad, m, v, 1e-3, 0.9, 0.999, 1e-8, 4.0, 1.0, step, norm)
+        assert abs(norm.item() - total.item()) / total.item() < 1e-5
+        assert (w - ref.detach()).abs().max().item() < 2e-6, step
