@@ -17,5 +17,5 @@ done
 rc=0
 for p in "${pids[@]}"; do wait $p || rc=1; done
 [ $rc -eq 0 ] || { echo "compile failed"; exit 1; }
-$NVCC -shared -o "$OUT/libnnr_b200.so" "$HERE"/.obj/*.o -lcudart_static -lcuda -ldl -lrt -lpthread
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libnnr_b200.so" "$HERE"/.obj/*.o -lcudart_static -lcuda -ldl -lrt -lpthread
 echo "built $OUT/libnnr_b200.so"

@@ -83,7 +83,7 @@ __device__ __forceinline__ float4 load4(const float* __restrict__ base, int64_t 
 template <bool AKC, bool BKC>
 __global__ void __launch_bounds__(GT) gemm_simt_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
                                                        int64_t ldb, int M, int N, int K, const int32_t* __restrict__ m_dev,
-                                                       const int32_t* __restrict__ k_dev, int k_chunk, bool vecA, bool vecB,
+                                                       const int32_t* __restrict__ k_dev, int splits, bool vecA, bool vecB,
                                                        EpiP epi, float* __restrict__ partial) {
   __shared__ __align__(16) float As[2][BK][BM + PADM];
   __shared__ __align__(16) float Bs[2][BK][BN + PADM];
@@ -91,6 +91,8 @@ __global__ void __launch_bounds__(GT) gemm_simt_kernel(const float* __restrict__
   if (k_dev) K = min(K, *k_dev);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   if (m0 >= M) return;
+  // split-K over the EFFECTIVE contraction length (device-side token count), BK-aligned chunks
+  const int k_chunk = (((K + splits - 1) / splits) + BK - 1) / BK * BK;
   const int kb = blockIdx.z * k_chunk;
   const int ke = min(K, kb + k_chunk);
   const int tid = threadIdx.x;
@@ -207,15 +209,13 @@ int nnr_gemm_simt(const nnr_gemm_args* a, void* stream) {
                 "nnr_gemm: split-K needs %zu workspace bytes (got %zu)", need, a->workspace_bytes);
     partial = (float*)a->workspace;
   }
-  int k_chunk = (a->K + splits - 1) / splits;
-  k_chunk = (k_chunk + BK - 1) / BK * BK;
   bool akc = a->transA == 0, bkc = a->transB != 0;
   bool vecA = nnr_aligned16(a->A) && (a->lda % 4 == 0);
   bool vecB = nnr_aligned16(a->B) && (a->ldb % 4 == 0);
   dim3 grid((a->N + BN - 1) / BN, (a->M + BM - 1) / BM, splits);
 #define LAUNCH(AK, BKc)                                                                                          \
   gemm_simt_kernel<AK, BKc><<<grid, GT, 0, st>>>(a->A, a->lda, a->B, a->ldb, a->M, a->N, a->K, a->m_dev, a->k_dev, \
-                                                 k_chunk, vecA, vecB, e, partial)
+                                                 splits, vecA, vecB, e, partial)
   if (akc && bkc) LAUNCH(true, true);
   else if (akc && !bkc) LAUNCH(true, false);
   else if (!akc && bkc) LAUNCH(false, true);

@@ -168,36 +168,55 @@ __global__ void news_fuse_split_kernel(const float* __restrict__ dout, int D2, i
     else d_b[(size_t)r * D2 + d - D2] = v;
   }
 }
-// one block per table row; scans the N news rows in order (deterministic)
-__global__ void news_fuse_table_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ idx, int N, int Dout,
-                                           int col0, int Edim, int Etot, int eoff, float p, float inv_keep, uint64_t seed,
-                                           float* __restrict__ dtable, int accumulate) {
-  int row = blockIdx.x;
-  int e = threadIdx.x;
-  if (e >= Edim) return;
+// one block per table row: the matching news rows are compacted IN ORDER (ballot prefix) into shared
+// memory in chunks of 256, then summed in that order -> deterministic, no atomics
+__global__ void __launch_bounds__(256) news_fuse_table_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ idx,
+                                                                  int N, int Dout, int col0, int Edim, int Etot, int eoff,
+                                                                  float p, float inv_keep, uint64_t seed,
+                                                                  float* __restrict__ dtable, int accumulate) {
+  __shared__ int s_list[256];
+  __shared__ int s_wcnt[8];
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   float acc = 0.f;
-  for (int r = 0; r < N; ++r) {
-    if (idx[r] == row)
-      acc += dout[(size_t)r * Dout + col0 + e] * dropout_scale(seed, (uint64_t)r * Etot + eoff + e, p, inv_keep);
+  for (int base = 0; base < N; base += 256) {
+    int r = base + tid;
+    bool hit = (r < N) && (idx[r] == row);
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) s_wcnt[w] = __popc(m);
+    __syncthreads();
+    int wbase = 0, total = 0;
+    for (int j = 0; j < 8; ++j) { if (j < w) wbase += s_wcnt[j]; total += s_wcnt[j]; }
+    if (hit) s_list[wbase + __popc(m & ((1u << lane) - 1))] = r;
+    __syncthreads();
+    if (tid < Edim) {
+      for (int j = 0; j < total; ++j) {
+        int rr = s_list[j];
+        acc += dout[(size_t)rr * Dout + col0 + tid] * dropout_scale(seed, (uint64_t)rr * Etot + eoff + tid, p, inv_keep);
+      }
+    }
+    __syncthreads();
   }
-  float* d = dtable + (size_t)row * Edim + e;
-  *d = accumulate ? (*d + acc) : acc;
+  if (tid < Edim) {
+    float* d = dtable + (size_t)row * Edim + tid;
+    *d = accumulate ? (*d + acc) : acc;
+  }
 }
 extern "C" int nnr_news_fuse_bwd(const float* dout, const int32_t* cat, const int32_t* sub, int N, int D2, int Ec, int Es,
                                  int n_cat, int n_sub, float p_drop, uint64_t seed, float* d_a, float* d_b,
                                  float* dcat_table, float* dsub_table, int accumulate, void* stream) {
   NNR_REQUIRE(dout && cat && sub && d_a && d_b && dcat_table && dsub_table && N > 0, NNR_ERR_ARG,
               "nnr_news_fuse_bwd: bad arguments");
-  NNR_REQUIRE(Ec <= 1024 && Es <= 1024, NNR_ERR_UNSUPPORTED, "nnr_news_fuse_bwd: embedding dim > 1024");
+  NNR_REQUIRE(Ec <= 256 && Es <= 256, NNR_ERR_UNSUPPORTED, "nnr_news_fuse_bwd: embedding dim > 256");
   cudaStream_t st = (cudaStream_t)stream;
   int Dout = 2 * D2 + Ec + Es;
   float inv_keep = 1.0f / (1.0f - p_drop);
   news_fuse_split_kernel<<<N, 256, 0, st>>>(dout, D2, Dout, d_a, d_b);
   NNR_LAUNCH_CHECK("news_fuse_split_kernel");
-  news_fuse_table_bwd_kernel<<<n_cat, ((Ec + 31) / 32) * 32, 0, st>>>(dout, cat, N, Dout, 2 * D2, Ec, Ec + Es, 0, p_drop,
+  news_fuse_table_bwd_kernel<<<n_cat, 256, 0, st>>>(dout, cat, N, Dout, 2 * D2, Ec, Ec + Es, 0, p_drop,
                                                                      inv_keep, seed, dcat_table, accumulate);
   NNR_LAUNCH_CHECK("news_fuse_table_bwd_kernel(cat)");
-  news_fuse_table_bwd_kernel<<<n_sub, ((Es + 31) / 32) * 32, 0, st>>>(dout, sub, N, Dout, 2 * D2 + Ec, Es, Ec + Es, Ec,
+  news_fuse_table_bwd_kernel<<<n_sub, 256, 0, st>>>(dout, sub, N, Dout, 2 * D2 + Ec, Es, Ec + Es, Ec,
                                                                      p_drop, inv_keep, seed, dsub_table, accumulate);
   NNR_LAUNCH_CHECK("news_fuse_table_bwd_kernel(sub)");
   return 0;

@@ -222,23 +222,37 @@ __global__ void __launch_bounds__(256) eb_chunk_kernel(const float* __restrict__
     float4 acc[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = a; i < b; ++i) {
-      int slot = vals[cs + i];
-      int row = slot / L, t = slot - row * L;
-      const float4* src = reinterpret_cast<const float4*>(dout + ((size_t)off[row] + t) * E);
-      uint64_t ebase = (uint64_t)slot * (uint64_t)E;
+    // entries of the run in groups of 32: lanes fetch the slot ids / row offsets in parallel, then the
+    // warp walks the group with shuffles, four rows in flight at a time
+    for (int i0 = a; i0 < b; i0 += 32) {
+      const int gi = i0 + lane;
+      int slot_l = 0;
+      size_t src_l = 0;
+      if (gi < b) {
+        slot_l = vals[cs + gi];
+        int row = slot_l / L, t = slot_l - row * L;
+        src_l = ((size_t)off[row] + t) * E;
+      }
+      const int gn = min(32, b - i0);
+#pragma unroll 4
+      for (int j = 0; j < gn; ++j) {
+        const int slot = __shfl_sync(0xffffffffu, slot_l, j);
+        const size_t so = __shfl_sync(0xffffffffu, (unsigned long long)src_l, j);
+        const float4* src = reinterpret_cast<const float4*>(dout + so);
+        const uint64_t ebase = (uint64_t)slot * (uint64_t)E;
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        int c4 = lane + 32 * q;
-        if (c4 < E4) {
-          float4 v = __ldg(src + c4);
-          if (p > 0.0f) {
-            v.x *= dropout_scale(seed, ebase + 4 * c4 + 0, p, inv_keep);
-            v.y *= dropout_scale(seed, ebase + 4 * c4 + 1, p, inv_keep);
-            v.z *= dropout_scale(seed, ebase + 4 * c4 + 2, p, inv_keep);
-            v.w *= dropout_scale(seed, ebase + 4 * c4 + 3, p, inv_keep);
+        for (int q = 0; q < 3; ++q) {
+          int c4 = lane + 32 * q;
+          if (c4 < E4) {
+            float4 v = __ldg(src + c4);
+            if (p > 0.0f) {
+              v.x *= dropout_scale(seed, ebase + 4 * c4 + 0, p, inv_keep);
+              v.y *= dropout_scale(seed, ebase + 4 * c4 + 1, p, inv_keep);
+              v.z *= dropout_scale(seed, ebase + 4 * c4 + 2, p, inv_keep);
+              v.w *= dropout_scale(seed, ebase + 4 * c4 + 3, p, inv_keep);
+            }
+            acc[q].x += v.x; acc[q].y += v.y; acc[q].z += v.z; acc[q].w += v.w;
           }
-          acc[q].x += v.x; acc[q].y += v.y; acc[q].z += v.z; acc[q].w += v.w;
         }
       }
     }

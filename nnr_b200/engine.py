@@ -85,7 +85,19 @@ class _Mod:
     pass
 
 
-def _cne_modality_forward(P, x, ids, mask_u8, N, L, E, Hd, training, p_drop, seed):
+def _domain_sorts(len64, domains):
+    """newsEncoders.py:112-115 per pairing domain (one reference news_encoder(...) call each): the same two
+    torch.sort calls on that call's lengths; indices are returned in global row numbering."""
+    sorted_idx, desorted_idx = [], []
+    for start, count in domains:
+        _, si = sort_fn(len64[start:start + count], descending=True)
+        _, di = sort_fn(si, descending=False)
+        sorted_idx.append(si + start)
+        desorted_idx.append(di)
+    return sorted_idx, desorted_idx
+
+
+def _cne_modality_forward(P, x, ids, mask_u8, N, L, E, Hd, training, p_drop, seed, domains):
     dev = ids.device
     cap = N * L
     m = _Mod()
@@ -95,10 +107,13 @@ def _cne_modality_forward(P, x, ids, mask_u8, N, L, E, Hd, training, p_drop, see
     m.tok_row = _empty((cap,), dev, torch.int32)
     ops.seq_prepare(mask_u8, m.len, m.off, m.tok_row)
     m.ntok = m.off[N:]                                         # device scalar (view), no sync
-    # newsEncoders.py:112-115 -- same torch.sort calls (tie-breaking of the device's sort)
-    _, m.sorted_idx = sort_fn(m.len.long(), descending=True)
-    _, m.desorted_idx = sort_fn(m.sorted_idx, descending=False)
-    m.order = m.sorted_idx.to(torch.int32)
+    # newsEncoders.py:112-115 -- same torch.sort calls (tie-breaking of the device's sort), per domain
+    len64 = m.len.long()
+    m.sorted_idx, m.desorted_idx = _domain_sorts(len64, domains)
+    if len(domains) == 1:
+        m.order = m.sorted_idx[0].to(torch.int32)
+    else:                                                     # LSTM tiling only needs "longest first"
+        m.order = torch.sort(len64, descending=True)[1].to(torch.int32)
     m.seed = seed
     m.p = p_drop if training else 0.0
     m.emb = _empty((cap, E), dev)
@@ -159,11 +174,13 @@ class CNEFunction(torch.autograd.Function):
         E, Hd, A = meta['E'], meta['Hd'], meta['att']
         training, p = meta['training'], meta['p_drop']
         seeds = [fresh_seed() for _ in range(3)] if (training and p > 0) else [0, 0, 0]
-        t = _cne_modality_forward(P, 'title', title_text.view(N, T), title_mask.reshape(N, T), N, T, E, Hd, training, p, seeds[0])
-        c = _cne_modality_forward(P, 'content', content_text.view(N, Lc), content_mask.reshape(N, Lc), N, Lc, E, Hd, training, p, seeds[1])
-        # pairing by sort rank (newsEncoders.py:124-129, SURVEY finding 2)
-        partner_t = c.sorted_idx.index_select(0, t.desorted_idx)
-        partner_c = t.sorted_idx.index_select(0, c.desorted_idx)
+        domains = meta.get('domains') or [(0, N)]
+        t = _cne_modality_forward(P, 'title', title_text.view(N, T), title_mask.reshape(N, T), N, T, E, Hd, training, p, seeds[0], domains)
+        c = _cne_modality_forward(P, 'content', content_text.view(N, Lc), content_mask.reshape(N, Lc), N, Lc, E, Hd, training, p, seeds[1], domains)
+        # pairing by sort rank inside each domain (newsEncoders.py:124-129, SURVEY finding 2):
+        # title row r of a call is gated with the content memory of the news at the same sorted rank
+        partner_t = torch.cat([cs.index_select(0, td) for cs, td in zip(c.sorted_idx, t.desorted_idx)])
+        partner_c = torch.cat([ts.index_select(0, cd) for ts, cd in zip(t.sorted_idx, c.desorted_idx)])
         _cne_gate_self(P, 'title', t, c.c_n, partner_t, N, Hd, A)
         _cne_gate_self(P, 'content', c, t.c_n, partner_c, N, Hd, A)
         if meta['cross_attention']:

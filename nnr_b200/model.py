@@ -36,10 +36,11 @@ class Model(nn.Module):
                 user_history_category_mask, user_history_category_indices, news_category, news_subCategory,
                 news_title_text, news_title_mask, news_title_entity, news_content_text, news_content_mask,
                 news_content_entity):
-        news_representation = self.news_encoder(news_title_text, news_title_mask, news_title_entity, news_content_text,
-                                                news_content_mask, news_content_entity, news_category, news_subCategory, None)
-        user_representation = self.user_encoder(user_title_text, user_title_mask, user_title_entity, user_content_text,
-                                                user_content_mask, user_content_entity, user_category, user_subCategory,
-                                                user_history_mask, user_history_graph, user_history_category_mask,
-                                                user_history_category_indices, None, news_representation)
+        # One CNE kernel schedule for both reference calls (model.py:123 candidates, userEncoders.py:76-78 history);
+        # each keeps its own sort-rank pairing domain, so results equal two separate calls.
+        news_representation, history_embedding = self.news_encoder.encode_calls([
+            (news_title_text, news_title_mask, news_content_text, news_content_mask, news_category, news_subCategory),
+            (user_title_text, user_title_mask, user_content_text, user_content_mask, user_category, user_subCategory)])
+        user_representation = self.user_encoder.encode_user(history_embedding, user_history_graph, user_history_category_mask,
+                                                            user_history_category_indices, news_representation)
         return engine.RowDot.apply(user_representation, news_representation)     # model.py:127

@@ -97,14 +97,42 @@ class CNE(NewsEncoder):
         return [sd[k] for k in names]
 
     def forward(self, title_text, title_mask, title_entity, content_text, content_mask, content_entity, category, subCategory, user_embedding):
-        if not title_text.is_cuda:
+        return self.encode_calls([(title_text, title_mask, content_text, content_mask, category, subCategory)])[0]
+
+    def encode_calls(self, calls):
+        """Encode several reference-style ``news_encoder(...)`` calls with ONE kernel schedule.
+
+        Each element of ``calls`` is (title_text [B,n,T], title_mask, content_text [B,n,A], content_mask, category
+        [B,n], subCategory [B,n]) and is its own pairing domain for the cross-selective gate (newsEncoders.py:112-115,
+        124-129), exactly as if ``forward`` had been called once per element; everything else is row-independent,
+        so candidates (B*5 rows) and history (B*50 rows) share the GEMM / LSTM launches.  Returns one
+        [B, n, news_embedding_dim] tensor per call.  Masks are modified in place like the reference (:108-109).
+        """
+        if not calls[0][0].is_cuda:
             raise RuntimeError('nnr_b200.CNE runs on CUDA (sm_100a) only; there is no CPU path')
-        B, n = title_text.size(0), title_text.size(1)
-        meta = dict(N=B * n, T=self.max_title_length, A_len=self.max_content_length, E=self.word_embedding_dim,
-                    Hd=self.hidden_dim, att=self.attention_dim, training=self.training, p_drop=float(self.dropout_rate),
-                    cross_attention=self.cross_attention)
         i32 = torch.int32
-        rep = engine.CNEFunction.apply(
-            meta, title_text.to(i32).contiguous(), title_mask, content_text.to(i32).contiguous(), content_mask,
-            category.to(i32), subCategory.to(i32), *self._params())
-        return rep.view(B, n, self.news_embedding_dim)
+        T, A = self.max_title_length, self.max_content_length
+        domains, shapes, start = [], [], 0
+        for c in calls:
+            B, n = c[0].size(0), c[0].size(1)
+            domains.append((start, B * n))
+            shapes.append((B, n))
+            start += B * n
+        if len(calls) == 1:
+            tt, tm, ct, cm, cat, sub = calls[0]
+            tt, ct, cat, sub = tt.to(i32).contiguous(), ct.to(i32).contiguous(), cat.to(i32), sub.to(i32)
+        else:
+            for c in calls:                                    # the caller's masks are mutated like the reference does
+                c[1][..., 0] = True
+                c[3][..., 0] = True
+            tt = torch.cat([c[0].reshape(-1, T).to(i32) for c in calls])
+            tm = torch.cat([c[1].reshape(-1, T) for c in calls])
+            ct = torch.cat([c[2].reshape(-1, A).to(i32) for c in calls])
+            cm = torch.cat([c[3].reshape(-1, A) for c in calls])
+            cat = torch.cat([c[4].reshape(-1).to(i32) for c in calls])
+            sub = torch.cat([c[5].reshape(-1).to(i32) for c in calls])
+        meta = dict(N=start, T=T, A_len=A, E=self.word_embedding_dim, Hd=self.hidden_dim, att=self.attention_dim,
+                    training=self.training, p_drop=float(self.dropout_rate), cross_attention=self.cross_attention,
+                    domains=domains)
+        rep = engine.CNEFunction.apply(meta, tt, tm, ct, cm, cat, sub, *self._params())
+        return [rep[s:s + cnt].view(B, n, self.news_embedding_dim) for (s, cnt), (B, n) in zip(domains, shapes)]

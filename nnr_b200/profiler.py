@@ -1,0 +1,131 @@
+"""CUDA-event breakdown of a training step by C-ABI op, and the roofline entry bench.py prints.
+
+``capture()`` wraps every function of ``nnr_b200.ops`` that launches kernels with a pair of CUDA
+events recorded on the launching (current) stream; nothing synchronises until ``summary()``.
+Algorithmic work per call (SURVEY.md 8d / DESIGN.md "algorithmic work"):
+  gemm        2*M*N*K flop, M (or K) replaced by the device-side valid-token count when given
+  lstm_fwd    2 * (4H*H) flop per token per direction  (recurrent product only)
+  lstm_bwd    2 * (4H*H) flop per token per direction  (dh_{t-1} product; dW_hh is a separate GEMM)
+  embed_gather_fwd   tokens * (4 + 2*4*E) bytes      embed_gather_bwd   tokens * (4 + 4*E) + V*E*4 bytes
+  attn_pool_*        tokens * D * 4 * (reads+writes) bytes
+"""
+import contextlib
+import json
+import os
+
+import torch
+
+from . import ops
+
+_TIMED = ['seq_prepare', 'embed_gather_fwd', 'embed_gather_bwd', 'gemm', 'colsum', 'segment_colsum', 'lstm_fwd',
+          'lstm_bwd', 'lstm_shift_h', 'gate_bwd_pre', 'attn_pool_fwd', 'attn_pool_bwd', 'news_fuse_fwd', 'news_fuse_bwd',
+          'graph_to_csr', 'gcn_aggregate', 'cluster_intra_fwd', 'cluster_intra_bwd', 'rowdot_fwd', 'rowdot_bwd',
+          'dropout', 'flat_clip_adam', 'sue_graph_build']
+
+
+def _dev_int(t):
+    return int(t.item()) if t is not None else None
+
+
+class Capture:
+    def __init__(self):
+        self.records = []
+        self.t0 = self.t1 = None
+
+    def _work(self, name, args, kw):
+        """returns a closure evaluated after synchronisation -> (flops, bytes)"""
+        if name == 'gemm':
+            A, B, C, M, N, K = args[:6]
+            m_dev, k_dev = kw.get('m_dev'), kw.get('k_dev')
+            return lambda: (2.0 * (min(M, _dev_int(m_dev)) if m_dev is not None else M) * N *
+                            (min(K, _dev_int(k_dev)) if k_dev is not None else K), None)
+        if name in ('lstm_fwd', 'lstm_bwd'):
+            if name == 'lstm_fwd':
+                off, N, H = args[3], args[5], args[7]
+            else:
+                off, N, H = args[4], args[6], args[8]
+            return lambda: (2.0 * 4 * H * H * 2 * int(off[N].item()), None)
+        if name == 'embed_gather_fwd':
+            table, ids, len_, off = args[:4]
+            E = table.shape[1]
+            return lambda: (None, float(off[ids.shape[0]].item()) * (4 + 8 * E))
+        if name == 'embed_gather_bwd':
+            dout, ids, len_, off, dtable = args[:5]
+            V, E = dtable.shape
+            return lambda: (None, float(off[ids.shape[0]].item()) * (4 + 4 * E) + V * E * 4.0)
+        return lambda: (None, None)
+
+    def wrap(self, name, fn):
+        def wrapped(*args, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            work = self._work(name, args, kw)
+            e0.record()
+            r = fn(*args, **kw)
+            e1.record()
+            self.records.append((name, e0, e1, work))
+            return r
+        return wrapped
+
+    def summary(self, steps=1):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1, work in self.records:
+            ms = e0.elapsed_time(e1)
+            fl, by = work()
+            a = agg.setdefault(name, {'ms': 0.0, 'calls': 0, 'flops': 0.0, 'bytes': 0.0})
+            a['ms'] += ms
+            a['calls'] += 1
+            a['flops'] += fl or 0.0
+            a['bytes'] += by or 0.0
+        out = {}
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1]['ms']):
+            out[k] = {'ms': a['ms'] / steps, 'calls': a['calls'] / steps}
+            if a['flops']:
+                out[k]['tflops'] = a['flops'] / (a['ms'] * 1e-3) / 1e12
+            if a['bytes']:
+                out[k]['gbs'] = a['bytes'] / (a['ms'] * 1e-3) / 1e9
+        return out
+
+
+@contextlib.contextmanager
+def capture():
+    cap = Capture()
+    saved = {}
+    for name in _TIMED:
+        saved[name] = getattr(ops, name)
+        setattr(ops, name, cap.wrap(name, saved[name]))
+    try:
+        yield cap
+    finally:
+        for name, fn in saved.items():
+            setattr(ops, name, fn)
+
+
+def measured_peaks(root):
+    path = os.path.join(root, 'MEASURED_PEAKS.json')
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {'hbm_gbs': p['hbm_gbs'], 'bf16_tflops': p.get('bf16_tflops_sustained', p['bf16_tflops']), 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1400.0, 'source': 'fallback'}
+
+
+def roofline(breakdown, tokens_per_step, batch, root):
+    """roofline entry for the dominant op of the step (largest share of device time)"""
+    if not breakdown:
+        return None
+    name, top = next(iter(breakdown.items()))
+    peaks = measured_peaks(root)
+    total = sum(v['ms'] for v in breakdown.values())
+    if 'tflops' in top:
+        # fp32-parity math on the tensor pipe is kind::tf32 = half the bf16 rate; algorithmic flops
+        peak = peaks['bf16_tflops'] / 2.0
+        return {'kernel': name, 'bound': 'tensor', 'achieved': top['tflops'], 'peak': peak, 'unit': 'TFLOP/s',
+                'frac': top['tflops'] / peak, 'traffic': None, 'share_of_step': top['ms'] / total,
+                'peak_note': 'tf32 dense = 0.5 x %s bf16 cuBLAS (%s sustained)' % (peaks['source'], peaks['bf16_tflops'])}
+    if 'gbs' in top:
+        return {'kernel': name, 'bound': 'hbm', 'achieved': top['gbs'], 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                'frac': top['gbs'] / peaks['hbm_gbs'], 'traffic': None, 'share_of_step': top['ms'] / total,
+                'peak_note': '%s HBM copy bandwidth' % peaks['source']}
+    return {'kernel': name, 'bound': 'hbm', 'achieved': None, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': None,
+            'traffic': None, 'share_of_step': top['ms'] / total}

@@ -62,10 +62,17 @@ class SUE(UserEncoder):
     def forward(self, user_title_text, user_title_mask, user_title_entity, user_content_text, user_content_mask, user_content_entity,
                 user_category, user_subCategory, user_history_mask, user_history_graph, user_history_category_mask,
                 user_history_category_indices, user_embedding, candidate_news_representation):
-        user_history_category_mask[:, -1] = 1                                    # userEncoders.py:73 (in place, like the reference)
         history_embedding = self.news_encoder(user_title_text, user_title_mask, user_title_entity, user_content_text,
                                               user_content_mask, user_content_entity, user_category, user_subCategory,
                                               user_embedding)                     # [B, H, D]  (its own pairing domain)
+        return self.encode_user(history_embedding, user_history_graph, user_history_category_mask,
+                                user_history_category_indices, candidate_news_representation)
+
+    def encode_user(self, history_embedding, user_history_graph, user_history_category_mask, user_history_category_indices,
+                    candidate_news_representation):
+        """userEncoders.py:73-97 given the already encoded history (Model.forward encodes candidates and history
+        with one CNE schedule, see CNE.encode_calls)."""
+        user_history_category_mask[:, -1] = 1                                    # userEncoders.py:73 (in place, like the reference)
         meta = dict(hca=self.hca, gcn_layers=self.gcn_layer_num, residual=self.gcn_residual, training=self.training,
                     p_drop=float(self.dropout_rate))
         return engine.SUEFunction.apply(meta, history_embedding, candidate_news_representation, user_history_graph,

@@ -17,6 +17,7 @@ class SUE_wo_HCA(UserEncoder):
     hca = False
     _params = SUE._params
     forward = SUE.forward
+    encode_user = SUE.encode_user
 
     def __init__(self, news_encoder, config):
         super().__init__(news_encoder, config)
