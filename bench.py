@@ -39,6 +39,7 @@ def parse():
     ap.add_argument('--cpu-sample', type=int, default=4, help='impressions in the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true', help='skip the per-op CUDA-event breakdown')
+    ap.add_argument('--gemm-detail', action='store_true', help='print the per-shape GEMM table to stderr')
     return ap.parse_args()
 
 
@@ -239,6 +240,9 @@ def main():
                 ts.step(*fresh(devb[i % nb]))
             torch.cuda.synchronize()
         breakdown = prof.summary(steps=2)
+        if a.gemm_detail:
+            for k, v in prof.detail.items():
+                print('%-44s %8.3f ms  %4.1f calls  %7.1f TFLOP/s' % (k, v['ms'], v['calls'], v['tflops']), file=sys.stderr)
         roofline = profiler.roofline(breakdown, tokens_per_step=tok, batch=a.batch, root=ROOT)
     if world > 1:
         dist.barrier()

@@ -248,8 +248,8 @@ __global__ void tc_split_rowmajor_kernel(const float* __restrict__ src, int64_t 
   if (r_dev) R = min(R, *r_dev);
   int Kv = k_dev ? min(K, *k_dev) : K;                      // valid k
   int Kw = k_dev ? min(Kp, (Kv + 2 * TC_BK - 1) / (2 * TC_BK) * (2 * TC_BK)) : Kp;   // written k (zero tail)
-  const int kq = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int r = blockIdx.y;
+  const int kq = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  const int r = blockIdx.x;
   if (r >= R || kq >= Kw) return;
   float x[4] = {0.f, 0.f, 0.f, 0.f};
   const float* s = src + (size_t)r * ld + kq;
@@ -281,7 +281,7 @@ __global__ void tc_split_transpose_kernel(const float* __restrict__ src, int64_t
   if (r_dev) R = min(R, *r_dev);
   int Kv = k_dev ? min(K, *k_dev) : K;
   int Kw = k_dev ? min(Kp, (Kv + 2 * TC_BK - 1) / (2 * TC_BK) * (2 * TC_BK)) : Kp;
-  const int k0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int k0 = blockIdx.y * 32, r0 = blockIdx.x * 32;
   if (k0 >= Kw || r0 >= R) return;
   const int tx = threadIdx.x, ty = threadIdx.y;           // 32 x 8
   for (int i = ty; i < 32; i += 8) {
@@ -364,9 +364,10 @@ static TcPlan make_plan(const nnr_gemm_args* a, bool bf16) {
   }
   // bound the length of one TMEM accumulation chain: the tensor core truncates when it adds into the fp32
   // accumulator, which biases long sums (~2^-24 per MMA); partial sums are combined in exact fp32 order instead
-  const int max_chain = 4096;
-  if ((a->K + splits - 1) / splits > max_chain) splits = (a->K + max_chain - 1) / max_chain;
-  if (splits > 512) splits = 512;
+  // (only for the small-output / long-contraction GEMMs = wgrad; K <= 1600 elsewhere on this path)
+  const int max_chain = 1024;
+  if (tiles < 148 && (a->K + splits - 1) / splits > max_chain) splits = (a->K + max_chain - 1) / max_chain;
+  if (splits > 1024) splits = 1024;
   pl.splits = splits;
   size_t stage = up((size_t)TC_BM * 128 + (size_t)pl.block_n * 128, 1024);
   int stages = (int)((100 * 1024) / stage);              // <= ~100 KB -> two CTAs per SM
@@ -421,10 +422,10 @@ static int split_operand(const float* X, int64_t ld, bool k_contig, int R, int K
                          const int32_t* k_dev, void* out, size_t plane_stride, cudaStream_t st) {
   if (k_contig) {
     bool vec = nnr_aligned16(X) && (ld % 4 == 0);
-    dim3 grid((Kp / 4 + 63) / 64, R);
+    dim3 grid(R, (Kp / 4 + 63) / 64);
     tc_split_rowmajor_kernel<BF16><<<grid, 64, 0, st>>>(X, ld, R, K, Kp, r_dev, k_dev, vec, out, plane_stride);
   } else {
-    dim3 grid((Kp + 31) / 32, (R + 31) / 32);
+    dim3 grid((R + 31) / 32, (Kp + 31) / 32);
     tc_split_transpose_kernel<BF16><<<grid, dim3(32, 8), 0, st>>>(X, ld, R, K, Kp, r_dev, k_dev, out, plane_stride);
   }
   NNR_LAUNCH_CHECK("tc_split_kernel");

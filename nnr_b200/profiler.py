@@ -62,21 +62,30 @@ class Capture:
             e0.record()
             r = fn(*args, **kw)
             e1.record()
-            self.records.append((name, e0, e1, work))
+            label = name
+            if name == 'gemm':
+                label = 'gemm[%dx%dx%d %s%s e%d]' % (args[3], args[4], args[5], 'T' if args[9] else 'N', 'T' if args[10] else 'N',
+                                                   kw.get('epilogue', args[11] if len(args) > 11 else 0))
+            self.records.append((name, e0, e1, work, label))
             return r
         return wrapped
 
     def summary(self, steps=1):
         torch.cuda.synchronize()
         agg = {}
-        for name, e0, e1, work in self.records:
+        self.detail = {}
+        for name, e0, e1, work, label in self.records:
             ms = e0.elapsed_time(e1)
             fl, by = work()
-            a = agg.setdefault(name, {'ms': 0.0, 'calls': 0, 'flops': 0.0, 'bytes': 0.0})
-            a['ms'] += ms
-            a['calls'] += 1
-            a['flops'] += fl or 0.0
-            a['bytes'] += by or 0.0
+            for key, table in ((name, agg), (label, self.detail)):
+                a = table.setdefault(key, {'ms': 0.0, 'calls': 0, 'flops': 0.0, 'bytes': 0.0})
+                a['ms'] += ms
+                a['calls'] += 1
+                a['flops'] += fl or 0.0
+                a['bytes'] += by or 0.0
+        self.detail = {k: {'ms': round(a['ms'] / steps, 3), 'calls': a['calls'] / steps,
+                           'tflops': round(a['flops'] / max(a['ms'], 1e-9) / 1e9, 1)}
+                       for k, a in sorted(self.detail.items(), key=lambda kv: -kv[1]['ms']) if k.startswith('gemm[')}
         out = {}
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1]['ms']):
             out[k] = {'ms': a['ms'] / steps, 'calls': a['calls'] / steps}

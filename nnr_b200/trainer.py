@@ -30,9 +30,7 @@ class TrainStep:
             world_size = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.world_size = world_size
         params = [p for p in model.parameters() if p.requires_grad]
-        dev = params[0].device
-        if dev.type != 'cuda':
-            raise RuntimeError('nnr_b200.TrainStep needs the model on a CUDA device')
+        dev = params[0].device          # flat buffers / all-reduce are device agnostic; the optimizer kernel is CUDA only
         sizes = [(p.numel() + 3) // 4 * 4 for p in params]            # keep every slice 16-byte aligned
         total = sum(sizes)
         self.flat = torch.zeros(total, device=dev)
@@ -67,9 +65,33 @@ class TrainStep:
         self.optimizer_step()
         return loss
 
-    def optimizer_step(self):
+    def reduce_gradients(self):
+        """the single collective of the step: SUM over ranks of the flat gradient buffer (the 1/world average
+        of DDP, trainer.py:219, is applied inside the fused clip+Adam kernel as grad_scale)"""
         if self.world_size > 1:
-            dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)     # the single collective of the step
+            dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def optimizer_step(self):
+        self.reduce_gradients()
+        if self.flat.device.type != 'cuda':
+            raise RuntimeError('nnr_b200.TrainStep.optimizer_step needs CUDA (nnr_flat_clip_adam has no CPU path)')
         self.step_count += 1
         ops.flat_clip_adam(self.flat, self.gflat, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
                            self.eps, self.max_norm, 1.0 / self.world_size, self.step_count, self.grad_norm)
+
+
+def shard_batch(batch, rank, world_size):
+    """Reference DDP sharding (trainer.py:218,256-258): rank r takes impressions [r*B/W, (r+1)*B/W) of a global
+    batch whose size is divisible by the world size (config.py:116).  Works on dicts or sequences of tensors;
+    non-tensor entries (the unused entity fields may be None) are passed through."""
+    def cut(v):
+        if not torch.is_tensor(v):
+            return v
+        B = v.shape[0]
+        if B % world_size:
+            raise ValueError('batch size %d not divisible by world size %d' % (B, world_size))
+        per = B // world_size
+        return v[rank * per:(rank + 1) * per]
+    if isinstance(batch, dict):
+        return {k: cut(v) for k, v in batch.items()}
+    return [cut(v) for v in batch]

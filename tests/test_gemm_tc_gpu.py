@@ -6,7 +6,7 @@ pytestmark = pytest.mark.gpu
 
 # max|err| / max|ref|.  The hi/lo split itself is good to ~2^-21, but the tensor core adds the products of one
 # tcgen05.mma into the fp32 TMEM accumulator with truncation, which leaves ~2^-24 x (MMAs in the chain) of bias:
-# measured 4e-6 at K=400, 1.1e-5 at K=1600.  nnr_gemm bounds the chain with split-K (<= 4096 k per partial sum).
+# measured 4e-6 at K=400, 1.1e-5 at K=1600.  nnr_gemm bounds the chain with split-K (<= 1024 k per partial sum).
 TF32X3_TOL = 2e-5
 BF16_TOL = 2e-2
 
