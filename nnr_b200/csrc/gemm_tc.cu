@@ -4,22 +4,26 @@
 //
 // Arithmetic: 3xTF32.  Every fp32 operand x is split into hi = rna_tf32(x) and lo = rna_tf32(x - hi);
 // D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi on the 5th-generation tensor cores (tcgen05.mma kind::tf32,
-// fp32 accumulation in TMEM).  The dropped lo*lo term and the rounding of lo are ~2^-21 relative, i.e.
-// the result is within a few fp32 ulps of an exact-fp32 product and passes the same parity tests as
-// the FFMA backend.  algo NNR_GEMM_TC_BF16 runs one pass of kind::f16 on bf16-rounded operands.
+// fp32 accumulation in TMEM).  The split is good to ~2^-21; what remains (4e-6 at K=400 ... 1e-5 at K=1600,
+// relative to max|C|) comes from the tensor core truncating when it adds into the TMEM accumulator, so long
+// contractions (wgrad: K = tokens) are cut into chains of <= 1024 k whose partial sums are combined in a
+// fixed order in exact fp32.  algo NNR_GEMM_TC_BF16 runs one kind::f16 pass on bf16-rounded operands.
 //
-// Pipeline (one 128 x BLOCK_N output tile per CTA, two CTAs co-resident per SM so one CTA's
-// epilogue overlaps the other's main loop):
-//   pre-pass   tc_split_kernel: op(X) -> K-major planes [2][rows][Kp] (hi, lo) in the workspace; handles
-//              the transposed operands of dgrad/wgrad, zero-fills the K tail, honours m_dev/k_dev.
-//   warp 0     TMA producer: cp.async.bulk.tensor (3-D map: k, row, plane; SWIZZLE_128B) into a ring of
-//              smem stages, completion on mbarriers (expect_tx).
-//   warp 1     allocates TMEM, then one elected lane issues tcgen05.mma (M=128, N=BLOCK_N, K=8 per
-//              instruction, 4 per 128-byte swizzle atom) and tcgen05.commit to free stages / signal the
-//              epilogue.
-//   warps 2-5  epilogue: tcgen05.ld the accumulator rows (one row per thread), apply the fused epilogue
-//              (bias / tanh / relu+residual / sigmoid gate / add) and store.
-// Split-K (wgrad: K = tokens) writes partials and reuses the deterministic reduce of the FFMA backend.
+// Structure
+//   pre-pass   tc_split_kernel: row-major operand -> planes [hi|lo][rows][cols] in the workspace (elementwise,
+//              16-byte accesses); zero-fills the column pad and, for device-bounded row counts, the row tail.
+//              No transposes: an operand whose contraction index runs along its ROWS (dgrad weights, both
+//              wgrad operands) is consumed MN-major straight from the same row-major planes.
+//   main       persistent kernel, one CTA per SM, static round-robin over (m-tile, n-tile, k-split) with the
+//              valid tile count computed on the device from m_dev / k_dev (no host synchronisation):
+//     warp 0     TMA producer: cp.async.bulk.tensor.3d (SWIZZLE_128B) of A_hi, A_lo, B_hi, B_lo for one
+//                32-wide k-block into a ring of shared-memory stages; mbarrier expect_tx completion.
+//     warp 1     TMEM allocator (512 columns = two accumulators) and single-thread tcgen05.mma issuer:
+//                12 MMAs per stage (4 k-steps x 3 split products), tcgen05.commit frees the stage / publishes
+//                the accumulator.
+//     warps 2-5  epilogue: tcgen05.ld one accumulator row per thread, fused bias / tanh / relu+residual(+dropout)
+//                / sigmoid-gate / add, 16-byte stores; overlaps the next tile's main loop (double-buffered TMEM).
+//   split-K    partials + a deterministic fixed-order reduce.
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include <cuda.h>
@@ -27,9 +31,11 @@
 #include <stdlib.h>
 
 #define TC_BM 128
-#define TC_BK 32          // fp32 elements per k-block = one 128-byte swizzle atom row
 #define TC_THREADS 192
-#define TC_TMEM_COLS 256
+#define TC_TMEM_COLS 512
+#define TC_ACC_COLS 256
+#define TC_SMEM_BUDGET (200 * 1024)
+#define TC_CHAIN_K 1024      // max contraction length accumulated in TMEM before an fp32 combine (split-K GEMMs)
 
 // ------------------------------------------------------------------------------------------------
 // device helpers (raw PTX)
@@ -41,6 +47,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -55,10 +64,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -95,15 +104,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): rows of 128 bytes, 8-row
-// groups 1024 bytes apart (SBO), LBO unused, version 1, layout type 2 (= 128B swizzle).
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+// sm_100 shared-memory matrix descriptor, SWIZZLE_128B (layout type 2), version 1.
+//   K-major : rows of 128 B, 8-row groups SBO = 1024 B apart, LBO unused.
+//   MN-major: atoms of 8 k-rows x 128 B (one TMA box row each); k-groups SBO = 1024 B apart, successive
+//             groups of 128 B along M/N are LBO bytes apart (= one TMA box).
+//   MN-major TF32 is special: the only legal layout is SWIZZLE_128B_BASE32B (layout type 1: 32-byte chunks
+//             swizzled within 128 B, TMA mode SWIZZLE_128B_ATOM_32B), whose atom holds 4 k-rows -> SBO = 512 B.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address, bits [0,14)
-  d |= (uint64_t)0 << 16;                              // leading byte offset (ignored for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset, bits [32,46)
-  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 
@@ -111,45 +124,130 @@ struct TcParams {
   int M, N, K;                 // capacities
   const int32_t* m_dev;
   const int32_t* k_dev;
-  int block_n, stages, splits, passes;
+  int block_n, stages, nplanes;
+  int a_mn, b_mn;              // operand is MN-major (contraction index along its rows)
+  int split_k;                 // 0: one pass over all of K;  1: chains of chain_kb k-blocks, partials
+  int chain_kb;
   uint32_t idesc;
   float* partial;
   EpiP epi;
 };
 
+// ---- vectorised epilogue over 16 consecutive columns of one row --------------------------------------------
+__device__ __forceinline__ void ld16(const float* p, bool vec, float* o) {
+  if (vec) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
+      o[4 * q] = t.x; o[4 * q + 1] = t.y; o[4 * q + 2] = t.z; o[4 * q + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = __ldg(p + i);
+  }
+}
+__device__ __forceinline__ void st16(float* p, bool vec, const float* o) {
+  if (vec) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(p)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p[i] = o[i];
+  }
+}
+__device__ __forceinline__ bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+__device__ __forceinline__ void epi_store16(const EpiP& e, int m, int n, float* v) {
+  // caller guarantees n + 16 <= N
+  float t[16];
+  switch (e.epilogue) {
+    case NNR_EPI_BIAS:
+    case NNR_EPI_BIAS_TANH:
+    case NNR_EPI_BIAS_RELU_RES:
+      if (e.bias) {
+        ld16(e.bias + n, al16(e.bias + n), t);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += t[i];
+      }
+      break;
+    default: break;
+  }
+  if (e.epilogue == NNR_EPI_BIAS_TANH) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
+  } else if (e.epilogue == NNR_EPI_BIAS_RELU_RES) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+    if (e.aux_out) { float* p = e.aux_out + (size_t)m * e.ldaux_out + n; st16(p, al16(p), v); }
+    if (e.aux) {
+      const float* p = e.aux + (size_t)m * e.ldaux + n;
+      ld16(p, al16(p), t);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += t[i];
+    }
+    if (e.p_drop > 0.f) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] *= dropout_scale(e.seed, (uint64_t)m * (uint64_t)e.N + n + i, e.p_drop, e.inv_keep);
+    }
+  } else if (e.epilogue == NNR_EPI_GATE) {
+    const float* rb = e.rowbias + (size_t)e.rowmap[m] * e.ldrowbias + n;
+    ld16(rb, al16(rb), t);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = sigmoidf_(v[i] + t[i]);
+    if (e.aux_out) { float* p = e.aux_out + (size_t)m * e.ldaux_out + n; st16(p, al16(p), v); }
+    const float* p = e.aux + (size_t)m * e.ldaux + n;
+    ld16(p, al16(p), t);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= t[i];
+  } else if (e.epilogue == NNR_EPI_ADD_AUX) {
+    const float* p = e.aux + (size_t)m * e.ldaux + n;
+    ld16(p, al16(p), t);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += t[i];
+  }
+  float* c = e.C + (size_t)m * e.ldc + n;
+  const bool cv = al16(c);
+  if (e.accumulate) {
+    ld16(c, cv, t);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += t[i];
+  }
+  st16(c, cv, v);
+}
+
 template <bool BF16>
-__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                             const __grid_constant__ CUtensorMap map_b, TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                const __grid_constant__ CUtensorMap map_b, TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int KELEM = BF16 ? 64 : 32;                 // elements per 128 bytes = k-block depth = MN group width
   int M = p.M, K = p.K;
   if (p.m_dev) M = min(M, *p.m_dev);
   if (p.k_dev) K = min(K, *p.k_dev);
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * p.block_n;
-  if (m0 >= M) return;                                   // whole CTA leaves before any barrier / TMEM use
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // smem carve-up: [stages][A 16 KB | B block_n*128 B] (1024-aligned), then barriers
-  const uint32_t a_bytes = TC_BM * 128, b_bytes = (uint32_t)p.block_n * 128;
-  const uint32_t stage_bytes = (a_bytes + b_bytes + 1023) & ~1023u;
+  // ---- tile space (device-side effective sizes) ----
+  const int m_tiles = (M + TC_BM - 1) / TC_BM;
+  const int n_tiles = (p.N + p.block_n - 1) / p.block_n;
+  const int nkb = (K + KELEM - 1) / KELEM;
+  const int kb_per = p.split_k ? p.chain_kb : max(nkb, 1);
+  const int splits = p.split_k ? max(1, (nkb + kb_per - 1) / kb_per) : 1;
+  const int total_tiles = m_tiles * n_tiles * splits;
+
+  // ---- smem carve-up ----
+  const uint32_t a_tile = TC_BM * 128, b_tile = (uint32_t)p.block_n * 128;
+  const uint32_t stage_bytes = (uint32_t)p.nplanes * (a_tile + b_tile);       // multiples of 1024
   unsigned char* tiles = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full_bar = empty_bar + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-
-  // k-block range of this split
-  constexpr int KELEM = BF16 ? 2 * TC_BK : TC_BK;        // elements per 128-byte k-block
-  const int nkb_total = (K + KELEM - 1) / KELEM;
-  const int kb_per = (nkb_total + p.splits - 1) / p.splits;
-  const int kb0 = blockIdx.z * kb_per;
-  const int kb1 = min(nkb_total, kb0 + kb_per);
-  const int iters = max(0, kb1 - kb0) * p.passes;
+  uint64_t* tmem_full = empty_bar + p.stages;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -164,65 +262,108 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        const int kb = kb0 + it / p.passes;
-        const int pass = it % p.passes;
-        // 3xTF32 passes per k-block: (A_hi,B_hi) (A_hi,B_lo) (A_lo,B_hi)
-        const int plane_a = (pass == 2) ? 1 : 0;
-        const int plane_b = (pass == 1) ? 1 : 0;
-        unsigned char* sa = tiles + (size_t)s * stage_bytes;
-        unsigned char* sb = sa + a_bytes;
-        mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
-        tma_load_3d(&map_a, &full_bar[s], sa, kb * KELEM, m0, plane_a);
-        tma_load_3d(&map_b, &full_bar[s], sb, kb * KELEM, n0, plane_b);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_idx = tile % n_tiles, rest = tile / n_tiles;
+        const int m0 = (rest % m_tiles) * TC_BM, n0 = n_idx * p.block_n, z = rest / m_tiles;
+        const int kb0 = z * kb_per, kb1 = min(nkb, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const uint32_t base = smem_u32(tiles + (size_t)s * stage_bytes);
+          mbar_expect_tx(&full_bar[s], stage_bytes);
+          for (int pl = 0; pl < p.nplanes; ++pl) {
+            const uint32_t sa = base + pl * a_tile;
+            const uint32_t sb = base + p.nplanes * a_tile + pl * b_tile;
+            if (!p.a_mn) tma_load_3d(&map_a, &full_bar[s], sa, kb * KELEM, m0, pl);
+            else for (int g = 0; g < TC_BM / KELEM; ++g) tma_load_3d(&map_a, &full_bar[s], sa + g * (KELEM * 128), m0 + g * KELEM, kb * KELEM, pl);
+            if (!p.b_mn) tma_load_3d(&map_b, &full_bar[s], sb, kb * KELEM, n0, pl);
+            else for (int g = 0; g < p.block_n / KELEM; ++g) tma_load_3d(&map_b, &full_bar[s], sb + g * (KELEM * 128), n0 + g * KELEM, kb * KELEM, pl);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int it = 0, tl = 0;
+      const uint32_t lbo = KELEM * 128;                               // bytes of one MN-group box
+      const uint64_t a_step = p.a_mn ? (uint64_t)((BF16 ? 2048 : 1024) >> 4) : 2;   // descriptor advance per MMA
+      const uint64_t b_step = p.b_mn ? (uint64_t)((BF16 ? 2048 : 1024) >> 4) : 2;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+        const int rest = tile / n_tiles;
+        const int z = rest / m_tiles;
+        const int kb0 = z * kb_per, kb1 = min(nkb, kb0 + kb_per);
+        const int buf = tl & 1;
+        mbar_wait(&tmem_empty[buf], ((tl >> 1) & 1) ^ 1);              // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(tiles + (size_t)s * stage_bytes);
-        const uint64_t da = make_kmajor_sw128_desc(sa);
-        const uint64_t db = make_kmajor_sw128_desc(sa + a_bytes);
+        const uint32_t d_tmem = tmem_base + buf * TC_ACC_COLS;
+        uint32_t first = 1;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(&full_bar[s], (it / p.stages) & 1);
+          tc_fence_after();
+          const uint32_t base = smem_u32(tiles + (size_t)s * stage_bytes);
+          // MN-major fp32 operands use the BASE32B layout (type 1, 4-row atoms); everything else plain SW128
+          const uint32_t a_lt = (p.a_mn && !BF16) ? 1u : 2u, a_sbo = (p.a_mn && !BF16) ? 512u : 1024u;
+          const uint32_t b_lt = (p.b_mn && !BF16) ? 1u : 2u, b_sbo = (p.b_mn && !BF16) ? 512u : 1024u;
+          const uint64_t a_hi = make_sw128_desc(base, p.a_mn ? lbo : 0, a_sbo, a_lt);
+          const uint64_t a_lo = make_sw128_desc(base + a_tile, p.a_mn ? lbo : 0, a_sbo, a_lt);
+          const uint64_t b_hi = make_sw128_desc(base + p.nplanes * a_tile, p.b_mn ? lbo : 0, b_sbo, b_lt);
+          const uint64_t b_lo = make_sw128_desc(base + p.nplanes * a_tile + b_tile, p.b_mn ? lbo : 0, b_sbo, b_lt);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {       // 4 MMAs of K = 32 bytes inside the 128-byte swizzle atom
-          tc_mma<BF16>(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ao = a_step * k, bo = b_step * k;
+            tc_mma<BF16>(d_tmem, a_hi + ao, b_hi + bo, p.idesc, first ? 0u : 1u);
+            first = 0;
+            if (!BF16) {
+              tc_mma<BF16>(d_tmem, a_hi + ao, b_lo + bo, p.idesc, 1u);
+              tc_mma<BF16>(d_tmem, a_lo + ao, b_hi + bo, p.idesc, 1u);
+            }
+          }
+          tc_commit(&empty_bar[s]);
         }
-        tc_commit(&empty_bar[s]);           // frees the smem stage once these MMAs have read it
+        tc_commit(&tmem_full[buf]);
       }
-      tc_commit(tmem_full_bar);             // accumulator complete
     }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
     const int q = warp & 3;
-    const int m = m0 + q * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-      float v[16];
-      if (iters > 0) tmem_ld16(lane_addr + (uint32_t)c0, v);
-      else {
+    int tl = 0;
+    const bool nvec = (p.N % 4) == 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      const int n_idx = tile % n_tiles, rest = tile / n_tiles;
+      const int m0 = (rest % m_tiles) * TC_BM, n0 = n_idx * p.block_n, z = rest / m_tiles;
+      const int kb0 = z * kb_per, kb1 = min(nkb, kb0 + kb_per);
+      const int buf = tl & 1;
+      const int m = m0 + q * 32 + lane;
+      mbar_wait(&tmem_full[buf], (tl >> 1) & 1);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + buf * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        float v[16];
+        if (kb1 > kb0) tmem_ld16(lane_addr + (uint32_t)c0, v);
+        else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0.f;
-      }
-      if (m < M) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int n = n0 + c0 + i;
-          if (n < p.N) {
-            if (p.partial) p.partial[((size_t)blockIdx.z * M + m) * p.N + n] = v[i];
-            else epi_store(p.epi, m, n, v[i]);
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        }
+        const int n = n0 + c0;
+        if (m < M && n < p.N) {
+          if (p.partial) {
+            float* dst = p.partial + ((size_t)z * M + m) * p.N + n;
+            if (n + 16 <= p.N) st16(dst, nvec && al16(dst), v);
+            else for (int i = 0; i < 16 && n + i < p.N; ++i) dst[i] = v[i];
+          } else if (n + 16 <= p.N) {
+            epi_store16(p.epi, m, n, v);
+          } else {
+            for (int i = 0; i < 16 && n + i < p.N; ++i) epi_store(p.epi, m, n + i, v[i]);
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
     }
   }
   tc_fence_before();
@@ -232,75 +373,60 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   }
 }
 
+// deterministic combine of the split-K partials (number of active splits is recomputed from k_dev)
+__global__ void tc_splitk_reduce_kernel(const float* __restrict__ partial, int K, const int32_t* __restrict__ k_dev, int kelem,
+                                        int chain_kb, int M, int N, const int32_t* __restrict__ m_dev, EpiP epi) {
+  if (m_dev) M = min(M, *m_dev);
+  if (k_dev) K = min(K, *k_dev);
+  const int nkb = (K + kelem - 1) / kelem;
+  const int splits = max(1, (nkb + chain_kb - 1) / chain_kb);
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)M * N) return;
+  int m = (int)(i / N), n = (int)(i - (size_t)m * N);
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * M + m) * N + n];
+  epi_store(epi, m, n, acc);
+}
+
 // ------------------------------------------------------------------------------------------------
-// pre-pass: op(X)[R,K] -> K-major planes.  TF32: planes (hi, lo) fp32 [2][R][Kp].  BF16: one bf16 plane.
+// pre-pass: row-major X[R, C] (ld) -> planes.  TF32: fp32 [2][R][Cp] (hi, lo).  BF16: bf16 [1][R][Cp].
+// Columns [C, Cp) are written as zeros; with r_dev, rows [R_eff, round_up(R_eff, 64)) are zeros too (they
+// are the k tail of an MN-major operand) and rows beyond are left untouched.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float rna_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-// contiguous-in-k source (src[r*ld + k]); one thread per 4 k's.  Kz: k >= Kz is written as zero.
 template <bool BF16>
-__global__ void tc_split_rowmajor_kernel(const float* __restrict__ src, int64_t ld, int R, int K, int Kp,
-                                         const int32_t* __restrict__ r_dev, const int32_t* __restrict__ k_dev, bool vec,
-                                         void* __restrict__ out, size_t plane_stride) {
-  if (r_dev) R = min(R, *r_dev);
-  int Kv = k_dev ? min(K, *k_dev) : K;                      // valid k
-  int Kw = k_dev ? min(Kp, (Kv + 2 * TC_BK - 1) / (2 * TC_BK) * (2 * TC_BK)) : Kp;   // written k (zero tail)
-  const int kq = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+__global__ void tc_split_kernel(const float* __restrict__ src, int64_t ld, int R, int C, int Cp, const int32_t* __restrict__ r_dev,
+                                bool vec, void* __restrict__ out, size_t plane_stride) {
+  int Rv = R;
+  if (r_dev) Rv = min(R, *r_dev);
+  const int Rw = r_dev ? min(R, (Rv + 63) / 64 * 64) : R;
+  const int cq = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   const int r = blockIdx.x;
-  if (r >= R || kq >= Kw) return;
+  if (r >= Rw || cq >= Cp) return;
   float x[4] = {0.f, 0.f, 0.f, 0.f};
-  const float* s = src + (size_t)r * ld + kq;
-  if (vec && kq + 3 < Kv) { float4 v = __ldg(reinterpret_cast<const float4*>(s)); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
-  else {
+  if (r < Rv) {
+    const float* s = src + (size_t)r * ld + cq;
+    if (vec && cq + 3 < C) { float4 v = __ldg(reinterpret_cast<const float4*>(s)); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+    else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) if (kq + i < Kv) x[i] = __ldg(s + i);
+      for (int i = 0; i < 4; ++i) if (cq + i < C) x[i] = __ldg(s + i);
+    }
   }
   if (BF16) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + (size_t)r * Kp + kq;
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + (size_t)r * Cp + cq;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) if (kq + i < Kp) o[i] = __float2bfloat16_rn(x[i]);
+    for (int i = 0; i < 4; ++i) o[i] = __float2bfloat16_rn(x[i]);      // Cp % 8 == 0
   } else {
-    float* hi = reinterpret_cast<float*>(out) + (size_t)r * Kp + kq;
-    float* lo = hi + plane_stride;
+    float* hi = reinterpret_cast<float*>(out) + (size_t)r * Cp + cq;
     float h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { h[i] = rna_tf32(x[i]); l[i] = rna_tf32(x[i] - h[i]); }
-    *reinterpret_cast<float4*>(hi) = make_float4(h[0], h[1], h[2], h[3]);     // Kp % 4 == 0, 16B aligned planes
-    *reinterpret_cast<float4*>(lo) = make_float4(l[0], l[1], l[2], l[3]);
-  }
-}
-// transposed source (src[k*ld + r]) -> planes[r][k] through a 32x32 smem tile
-template <bool BF16>
-__global__ void tc_split_transpose_kernel(const float* __restrict__ src, int64_t ld, int R, int K, int Kp,
-                                          const int32_t* __restrict__ r_dev, const int32_t* __restrict__ k_dev,
-                                          void* __restrict__ out, size_t plane_stride) {
-  __shared__ float tile[32][33];
-  if (r_dev) R = min(R, *r_dev);
-  int Kv = k_dev ? min(K, *k_dev) : K;
-  int Kw = k_dev ? min(Kp, (Kv + 2 * TC_BK - 1) / (2 * TC_BK) * (2 * TC_BK)) : Kp;
-  const int k0 = blockIdx.y * 32, r0 = blockIdx.x * 32;
-  if (k0 >= Kw || r0 >= R) return;
-  const int tx = threadIdx.x, ty = threadIdx.y;           // 32 x 8
-  for (int i = ty; i < 32; i += 8) {
-    int k = k0 + i, r = r0 + tx;
-    tile[i][tx] = (k < Kv && r < R) ? __ldg(src + (size_t)k * ld + r) : 0.f;
-  }
-  __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    int r = r0 + i, k = k0 + tx;
-    if (r < R && k < Kw) {
-      float x = tile[tx][i];
-      if (BF16) reinterpret_cast<__nv_bfloat16*>(out)[(size_t)r * Kp + k] = __float2bfloat16_rn(x);
-      else {
-        float h = rna_tf32(x);
-        float* hi = reinterpret_cast<float*>(out) + (size_t)r * Kp + k;
-        hi[0] = h;
-        hi[plane_stride] = rna_tf32(x - h);
-      }
-    }
+    *reinterpret_cast<float4*>(hi) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(hi + plane_stride) = make_float4(l[0], l[1], l[2], l[3]);
   }
 }
 
@@ -328,17 +454,17 @@ static size_t up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct TcPlan {
   bool bf16;
-  int block_n, stages, splits, passes;
-  int Kp;                       // plane pitch in elements
-  size_t a_plane, b_plane;      // elements per plane
-  size_t a_off, b_off, partial_off, total;
-  size_t smem;
+  int a_mn, b_mn;               // MN-major flags
+  int a_rows, a_cols, b_rows, b_cols;   // stored (row-major) shapes of the operands
+  int a_cp, b_cp;               // plane pitches
+  int block_n, stages, split_k, chain_kb, max_splits, nplanes, kelem;
+  size_t a_plane, b_plane, a_off, b_off, partial_off, total, smem;
 };
 
-static int pick_block_n(int N) {
-  int best = 64;
+static int pick_block_n(int N, int step) {
+  int best = step;
   double best_cost = 1e30;
-  for (int bn = 256; bn >= 32; bn -= 16) {
+  for (int bn = 256; bn >= 32; bn -= step) {
     double padded = (double)((N + bn - 1) / bn) * bn;
     double cost = padded * (1.0 + 40.0 / bn);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
@@ -349,41 +475,35 @@ static int pick_block_n(int N) {
 static TcPlan make_plan(const nnr_gemm_args* a, bool bf16) {
   TcPlan pl;
   pl.bf16 = bf16;
-  pl.block_n = pick_block_n(a->N);
-  pl.passes = bf16 ? 1 : 3;
-  const int kelem = bf16 ? 2 * TC_BK : TC_BK;            // elements per 128-byte row
-  pl.Kp = (int)up((size_t)a->K, bf16 ? 8 : 4);           // 16-byte row pitch
-  // split-K when the output grid is small and the contraction long (wgrad)
+  pl.kelem = bf16 ? 64 : 32;
+  pl.nplanes = bf16 ? 1 : 2;
+  pl.a_mn = a->transA ? 1 : 0;                 // A stored [K, M]: contraction along rows
+  pl.b_mn = a->transB ? 0 : 1;                 // B stored [K, N]: contraction along rows
+  pl.a_rows = a->transA ? a->K : a->M; pl.a_cols = a->transA ? a->M : a->K;
+  pl.b_rows = a->transB ? a->N : a->K; pl.b_cols = a->transB ? a->K : a->N;
+  const size_t pad = bf16 ? 8 : 4;             // 16-byte row pitch
+  pl.a_cp = (int)up((size_t)pl.a_cols, pad);
+  pl.b_cp = (int)up((size_t)pl.b_cols, pad);
+  pl.block_n = pick_block_n(a->N, pl.b_mn ? pl.kelem : 16);
   long tiles = (long)((a->M + TC_BM - 1) / TC_BM) * ((a->N + pl.block_n - 1) / pl.block_n);
-  int splits = 1;
-  if (tiles < 148 && a->K >= 4096) {
-    splits = (int)((296 + tiles - 1) / tiles);
-    int maxs = a->K / (kelem * 8);
-    if (splits > maxs) splits = maxs;
-    if (splits < 1) splits = 1;
-  }
-  // bound the length of one TMEM accumulation chain: the tensor core truncates when it adds into the fp32
-  // accumulator, which biases long sums (~2^-24 per MMA); partial sums are combined in exact fp32 order instead
-  // (only for the small-output / long-contraction GEMMs = wgrad; K <= 1600 elsewhere on this path)
-  const int max_chain = 1024;
-  if (tiles < 148 && (a->K + splits - 1) / splits > max_chain) splits = (a->K + max_chain - 1) / max_chain;
-  if (splits > 1024) splits = 1024;
-  pl.splits = splits;
-  size_t stage = up((size_t)TC_BM * 128 + (size_t)pl.block_n * 128, 1024);
-  int stages = (int)((100 * 1024) / stage);              // <= ~100 KB -> two CTAs per SM
+  pl.split_k = (tiles < 148 && a->K >= 4096) ? 1 : 0;
+  pl.chain_kb = TC_CHAIN_K / pl.kelem;
+  int nkb_cap = (a->K + pl.kelem - 1) / pl.kelem;
+  pl.max_splits = pl.split_k ? (nkb_cap + pl.chain_kb - 1) / pl.chain_kb : 1;
+  size_t stage = (size_t)pl.nplanes * ((size_t)TC_BM * 128 + (size_t)pl.block_n * 128);
+  int stages = (int)(TC_SMEM_BUDGET / stage);
   if (stages < 2) stages = 2;
-  if (stages > 8) stages = 8;
+  if (stages > 6) stages = 6;
   pl.stages = stages;
-  pl.smem = 1024 + (size_t)stages * stage + (2 * stages + 1) * 8 + 16;
+  pl.smem = 1024 + (size_t)stages * stage + (2 * stages + 4) * 8 + 16;
   const size_t esz = bf16 ? 2 : 4;
-  const int nplanes = bf16 ? 1 : 2;
-  pl.a_plane = (size_t)a->M * pl.Kp;
-  pl.b_plane = (size_t)a->N * pl.Kp;
+  pl.a_plane = (size_t)pl.a_rows * pl.a_cp;
+  pl.b_plane = (size_t)pl.b_rows * pl.b_cp;
   size_t o = 0;
-  pl.a_off = o; o = up(o + pl.a_plane * esz * nplanes, 1024);
-  pl.b_off = o; o = up(o + pl.b_plane * esz * nplanes, 1024);
+  pl.a_off = o; o = up(o + pl.a_plane * esz * pl.nplanes, 1024);
+  pl.b_off = o; o = up(o + pl.b_plane * esz * pl.nplanes, 1024);
   pl.partial_off = o;
-  if (splits > 1) o = up(o + (size_t)splits * a->M * a->N * sizeof(float), 1024);
+  if (pl.split_k) o = up(o + (size_t)pl.max_splits * a->M * a->N * sizeof(float), 1024);
   pl.total = o;
   return pl;
 }
@@ -396,38 +516,34 @@ int nnr_gemm_tc_supported(const nnr_gemm_args* a) {
   // tiny problems are launch-bound either way; the FFMA kernel handles them exactly
   if ((double)a->M * a->N * a->K < 2.0e6) return 0;
   if (a->K < 8) return 0;
+  // device-side bounds: m_dev needs row-major A (rows = M); k_dev needs both operands stored [K, .]
+  if (a->m_dev && a->transA) return 0;
+  if (a->k_dev && !(a->transA && !a->transB)) return 0;
   return 1;
 }
 
-size_t nnr_gemm_tc_workspace_bytes(const nnr_gemm_args* a) {
-  int algo = a->algo;
-  return make_plan(a, algo == NNR_GEMM_TC_BF16).total;
-}
+size_t nnr_gemm_tc_workspace_bytes(const nnr_gemm_args* a) { return make_plan(a, a->algo == NNR_GEMM_TC_BF16).total; }
 
-static int encode_map(CUtensorMap* map, void* base, bool bf16, int Kp, int rows, int nplanes, int box_rows) {
-  cuuint64_t gdim[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)nplanes};
+static int encode_map(CUtensorMap* map, void* base, bool bf16, int cols_p, int rows, int nplanes, int box_c, int box_r, bool mn) {
+  cuuint64_t gdim[3] = {(cuuint64_t)cols_p, (cuuint64_t)rows, (cuuint64_t)nplanes};
   const size_t esz = bf16 ? 2 : 4;
-  cuuint64_t gstr[2] = {(cuuint64_t)Kp * esz, (cuuint64_t)Kp * esz * (cuuint64_t)rows};
-  cuuint32_t box[3] = {(cuuint32_t)(bf16 ? 2 * TC_BK : TC_BK), (cuuint32_t)box_rows, 1};
+  cuuint64_t gstr[2] = {(cuuint64_t)cols_p * esz, (cuuint64_t)cols_p * esz * (cuuint64_t)rows};
+  cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_r, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = get_encode()(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, gdim, gstr,
-                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            (mn && !bf16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { nnr_set_error("nnr_gemm(tc): cuTensorMapEncodeTiled failed (%d)", (int)r); return NNR_ERR_ARG; }
   return 0;
 }
 
 template <bool BF16>
-static int split_operand(const float* X, int64_t ld, bool k_contig, int R, int K, int Kp, const int32_t* r_dev,
-                         const int32_t* k_dev, void* out, size_t plane_stride, cudaStream_t st) {
-  if (k_contig) {
-    bool vec = nnr_aligned16(X) && (ld % 4 == 0);
-    dim3 grid(R, (Kp / 4 + 63) / 64);
-    tc_split_rowmajor_kernel<BF16><<<grid, 64, 0, st>>>(X, ld, R, K, Kp, r_dev, k_dev, vec, out, plane_stride);
-  } else {
-    dim3 grid((R + 31) / 32, (Kp + 31) / 32);
-    tc_split_transpose_kernel<BF16><<<grid, dim3(32, 8), 0, st>>>(X, ld, R, K, Kp, r_dev, k_dev, out, plane_stride);
-  }
+static int split_operand(const float* X, int64_t ld, int R, int C, int Cp, const int32_t* r_dev, void* out, size_t plane_stride,
+                         cudaStream_t st) {
+  bool vec = nnr_aligned16(X) && (ld % 4 == 0);
+  dim3 grid(R, (Cp / 4 + 127) / 128);
+  tc_split_kernel<BF16><<<grid, 128, 0, st>>>(X, ld, R, C, Cp, r_dev, vec, out, plane_stride);
   NNR_LAUNCH_CHECK("tc_split_kernel");
   return 0;
 }
@@ -438,42 +554,52 @@ static int run_tc(const nnr_gemm_args* a, cudaStream_t st) {
   NNR_REQUIRE(a->workspace && a->workspace_bytes >= pl.total, NNR_ERR_WORKSPACE, "nnr_gemm(tc): workspace %zu < %zu",
               a->workspace_bytes, pl.total);
   NNR_REQUIRE(nnr_aligned16(a->workspace), NNR_ERR_ALIGN, "nnr_gemm(tc): workspace must be 16B aligned");
+  NNR_REQUIRE(pl.smem <= 227 * 1024, NNR_ERR_UNSUPPORTED, "nnr_gemm(tc): smem plan too large");
   char* ws = (char*)a->workspace;
   void* pa = ws + pl.a_off;
   void* pb = ws + pl.b_off;
-  // op(A)[m,k]: contiguous in k when transA == 0.  op(B)[k,n] as rows n: contiguous in k when transB != 0.
-  int rc = split_operand<BF16>(a->A, a->lda, a->transA == 0, a->M, a->K, pl.Kp, a->m_dev, a->k_dev, pa, pl.a_plane, st);
+  // rows of A are M (m_dev) when row-major, K (k_dev) when MN-major; rows of B are K (k_dev) when MN-major
+  int rc = split_operand<BF16>(a->A, a->lda, pl.a_rows, pl.a_cols, pl.a_cp, pl.a_mn ? a->k_dev : a->m_dev, pa, pl.a_plane, st);
   if (rc) return rc;
-  rc = split_operand<BF16>(a->B, a->ldb, a->transB != 0, a->N, a->K, pl.Kp, nullptr, a->k_dev, pb, pl.b_plane, st);
+  rc = split_operand<BF16>(a->B, a->ldb, pl.b_rows, pl.b_cols, pl.b_cp, pl.b_mn ? a->k_dev : nullptr, pb, pl.b_plane, st);
   if (rc) return rc;
   CUtensorMap map_a, map_b;
-  const int nplanes = BF16 ? 1 : 2;
-  rc = encode_map(&map_a, pa, BF16, pl.Kp, a->M, nplanes, TC_BM);
+  const int ke = pl.kelem;
+  rc = encode_map(&map_a, pa, BF16, pl.a_cp, pl.a_rows, pl.nplanes, ke, pl.a_mn ? ke : TC_BM, pl.a_mn != 0);
   if (rc) return rc;
-  rc = encode_map(&map_b, pb, BF16, pl.Kp, a->N, nplanes, pl.block_n);
+  rc = encode_map(&map_b, pb, BF16, pl.b_cp, pl.b_rows, pl.nplanes, ke, pl.b_mn ? ke : pl.block_n, pl.b_mn != 0);
   if (rc) return rc;
   TcParams p;
   p.M = a->M; p.N = a->N; p.K = a->K; p.m_dev = a->m_dev; p.k_dev = a->k_dev;
-  p.block_n = pl.block_n; p.stages = pl.stages; p.splits = pl.splits; p.passes = pl.passes;
-  // instruction descriptor: D=f32 (bits 4-5 = 1), A/B format (tf32 = 2, bf16 = 1) at bits 7-9 / 10-12, K-major A and B,
-  // N >> 3 at bits 17-22, M >> 4 at bits 24-28
+  p.block_n = pl.block_n; p.stages = pl.stages; p.nplanes = pl.nplanes;
+  p.a_mn = pl.a_mn; p.b_mn = pl.b_mn; p.split_k = pl.split_k; p.chain_kb = pl.chain_kb;
+  // instruction descriptor: D=f32 (bits 4-5 = 1), A/B format (tf32 = 2, bf16 = 1) at bits 7-9 / 10-12, A/B major at
+  // bits 15 / 16 (1 = MN-major), N >> 3 at bits 17-22, M >> 4 at bits 24-28
   const uint32_t fmt = BF16 ? 1u : 2u;
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(pl.block_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-  p.partial = pl.splits > 1 ? (float*)(ws + pl.partial_off) : nullptr;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)pl.a_mn << 15) | ((uint32_t)pl.b_mn << 16) |
+            ((uint32_t)(pl.block_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  p.partial = pl.split_k ? (float*)(ws + pl.partial_off) : nullptr;
   p.epi = make_epi(a);
   static bool attr_set[2] = {false, false};
+  static int num_sms = 0;
   if (!attr_set[BF16 ? 1 : 0]) {
-    NNR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    NNR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[BF16 ? 1 : 0] = true;
   }
-  NNR_REQUIRE(pl.smem <= 112 * 1024, NNR_ERR_UNSUPPORTED, "nnr_gemm(tc): smem plan too large");
-  dim3 grid((a->N + pl.block_n - 1) / pl.block_n, (a->M + TC_BM - 1) / TC_BM, pl.splits);
+  if (num_sms == 0) {
+    int dev = 0;
+    NNR_CUDA(cudaGetDevice(&dev));
+    NNR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  long cap_tiles = (long)((a->M + TC_BM - 1) / TC_BM) * ((a->N + pl.block_n - 1) / pl.block_n) * pl.max_splits;
+  int grid = (int)(cap_tiles < num_sms ? cap_tiles : num_sms);
   gemm_tc_kernel<BF16><<<grid, TC_THREADS, pl.smem, st>>>(map_a, map_b, p);
   NNR_LAUNCH_CHECK("gemm_tc_kernel");
-  if (pl.splits > 1) {
+  if (pl.split_k) {
     size_t tot = (size_t)a->M * a->N;
-    gemm_splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p.partial, pl.splits, a->M, a->N, a->m_dev, p.epi);
-    NNR_LAUNCH_CHECK("gemm_splitk_reduce_kernel");
+    tc_splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p.partial, a->K, a->k_dev, pl.kelem, pl.chain_kb, a->M,
+                                                                          a->N, a->m_dev, p.epi);
+    NNR_LAUNCH_CHECK("tc_splitk_reduce_kernel");
   }
   return 0;
 }

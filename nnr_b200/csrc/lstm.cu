@@ -2,20 +2,22 @@
 // cluster kernels (sm_100a).  Replaces cuDNN's RNN behind nn.LSTM at newsEncoders.py:66-67,119-127.
 //
 // Design
-//   * One cluster of CL = 4 CTAs owns a tile of MT = 32 sequences and one direction.  CTA r of the
-//     cluster owns hidden units [r*H/4, (r+1)*H/4): the i,f,g,o rows of those units, i.e. a
-//     [4*H/4, H] slice of W_hh = 160 KB fp32 for H = 200, which stays in shared memory for every
-//     time step of every tile the cluster processes (the kernel is persistent over tiles).
-//   * forward step: z = gx_t + h_{t-1} W_slice^T (register-tiled FFMA: 2 units x 4 gates x 4 rows per
-//     thread), fused sigmoid/tanh/cell update with c_t kept in registers, then the new h slice is
-//     broadcast into all four CTAs' h buffers through distributed shared memory and one
-//     barrier.cluster per step publishes it.
-//   * backward step: each CTA turns dh_t (+ recurrent part) into d(pre-activations) for its own
-//     units, multiplies them with its W slice to get a PARTIAL dh_{t-1} over all H units, and
+//   * One cluster of CL = 4 CTAs owns a tile of sequences and one direction.  CTA r of the cluster owns
+//     hidden units [r*H/4, (r+1)*H/4): the i,f,g,o rows of those units, i.e. a [4*H/4, H] slice of
+//     W_hh = 160 KB fp32 for H = 200, which stays in shared memory for every time step of every tile the
+//     cluster processes (the kernel is persistent over tiles).
+//   * forward step (64-row tiles, 13 warps): z = gx_t + h_{t-1} W_slice^T, register tiled FFMA (2 units x
+//     4 gates x 4 rows per thread), fused sigmoid/tanh/cell update with c_t kept in registers, then the new
+//     h slice is broadcast into all four CTAs' h buffers through distributed shared memory.  The h buffer
+//     is single (W + a 64-row h tile fill the 227 KB), so a step uses two split-phase cluster barriers:
+//     "h complete" (B) and "everyone finished reading h" (A); the gate math sits between arrive(A) and
+//     wait(A).
+//   * backward step (32-row tiles): each CTA turns dh_t (+ recurrent part) into d(pre-activations) for its
+//     own units, multiplies them with its W slice to get a PARTIAL dh_{t-1} over all H units, and
 //     reduce-scatters the partials to the owning CTAs through DSMEM (fixed summation order ->
-//     deterministic).  Split arrive/wait cluster barriers overlap the exchange with compute.
-//   * variable lengths: rows are tiled in length-sorted order; a row is active for its own `len`
-//     steps only (packed-sequence semantics); the reverse direction walks t = len-1 .. 0.
+//     deterministic).  Same A/B barrier protocol.
+//   * variable lengths: rows are tiled in length-sorted order; a row is active for its own `len` steps only
+//     (packed-sequence semantics); the reverse direction walks t = len-1 .. 0.
 //   * the input projection gx (a dense GEMM) is computed outside (nnr_gemm); the activated gates
 //     overwrite gx in place as the stash for BPTT, and BPTT overwrites them with dL/dgx.
 #include "common.cuh"
@@ -23,24 +25,26 @@
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
-template <int HID_, int CL_, int MT_>
+template <int HID_, int CL_, int MT_, int UPT_>   // hidden, cluster size, rows per tile, units per thread (phase 1)
 struct LCfg {
-  static constexpr int HID = HID_, CL = CL_, MT = MT_;
+  static constexpr int HID = HID_, CL = CL_, MT = MT_, UPT = UPT_;
   static constexpr int UPC = HID / CL;        // hidden units per CTA
   static constexpr int COLS = 4 * UPC;        // gate columns per CTA
-  static constexpr int UP = UPC / 2;          // unit pairs
+  static constexpr int UG = UPC / UPT;        // unit groups
   static constexpr int RG = MT / 4;           // row groups of 4
-  static constexpr int NWORK = UP * RG;       // working threads
+  static constexpr int NWORK = UG * RG;       // working threads
   static constexpr int NT = ((NWORK + 31) / 32) * 32;
-  static constexpr int KG = HID / 8;          // backward: groups of 8 k's
-  static_assert(HID % CL == 0 && UPC % 2 == 0 && MT % 4 == 0 && HID % 8 == 0, "unsupported LSTM geometry");
-  static_assert(KG * RG <= NT, "backward thread mapping does not fit");
-  static constexpr size_t FWD_SMEM = sizeof(float) * ((size_t)HID * COLS + 2 * (size_t)HID * MT) + 3 * MT * sizeof(int);
+  static_assert(HID % CL == 0 && UPC % UPT == 0 && MT % 4 == 0 && HID % 4 == 0, "unsupported LSTM geometry");
+  static constexpr size_t FWD_SMEM = sizeof(float) * ((size_t)HID * COLS + (size_t)HID * MT) + 3 * MT * sizeof(int);
   static constexpr size_t BWD_SMEM = sizeof(float) * ((size_t)COLS * HID + (size_t)COLS * MT + (size_t)CL * UPC * MT) + 3 * MT * sizeof(int);
 };
 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// gate non-linearities on the SFU (ex2 + rcp): absolute error ~1e-7, far inside the 1e-4 parity budget
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
 // ------------------------------------------------------------------------------------------------
 // forward
@@ -50,11 +54,12 @@ __global__ void __launch_bounds__(C::NT, 1)
 lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const int32_t* __restrict__ len,
                 const int32_t* __restrict__ off, const int32_t* __restrict__ order, int N, int ntiles,
                 float* __restrict__ h_out, float* __restrict__ c_stash, float* __restrict__ c_n) {
-  constexpr int HID = C::HID, CL = C::CL, MT = C::MT, UPC = C::UPC, COLS = C::COLS, UP = C::UP;
+  constexpr int HID = C::HID, CL = C::CL, MT = C::MT, UPC = C::UPC, COLS = C::COLS, UG = C::UG;
+  static_assert(C::UPT == 2, "forward kernel is written for 2 units per thread");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* Wt = reinterpret_cast<float*>(smem_raw);                 // [HID][COLS]
-  float* hT = Wt + (size_t)HID * COLS;                            // [2][HID][MT]
-  int* s_row = reinterpret_cast<int*>(hT + 2 * (size_t)HID * MT); // [MT]
+  float* hT = Wt + (size_t)HID * COLS;                            // [HID][MT]
+  int* s_row = reinterpret_cast<int*>(hT + (size_t)HID * MT);     // [MT]
   int* s_len = s_row + MT;
   int* s_off = s_len + MT;
 
@@ -65,7 +70,7 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
   const int dir = cluster_id & 1;
   const int tid = threadIdx.x;
   const bool worker = tid < C::NWORK;
-  const int up = tid % UP, rg = tid / UP;
+  const int up = tid % UG, rg = tid / UG;
   const int j0 = 2 * up;                       // local unit of this thread (and j0+1)
   const int unit0 = rank * UPC + j0;           // global hidden unit
 
@@ -92,7 +97,7 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
       s_len[tid] = (r >= 0) ? len[r] : 0;
       s_off[tid] = (r >= 0) ? off[r] : 0;
     }
-    for (int idx = tid; idx < HID * MT; idx += C::NT) hT[idx] = 0.f;   // h_0 = 0 in buffer 0
+    for (int idx = tid; idx < HID * MT; idx += C::NT) hT[idx] = 0.f;   // h_0 = 0
     __syncthreads();
     int maxlen = 0;
     for (int i = 0; i < MT; ++i) maxlen = max(maxlen, s_len[i]);
@@ -106,7 +111,6 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
       rrow[i] = worker ? s_row[4 * rg + i] : -1;
       cst[0][i] = cst[1][i] = hst[0][i] = hst[1][i] = 0.f;
     }
-    // prefetch gx for step 0
     float2 gxr[4][4];  // [gate][row]
     auto load_gx = [&](int s) {
 #pragma unroll
@@ -124,16 +128,17 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
     };
     if (worker) load_gx(0);
 
+    cluster_arrive();                         // B0: my h buffer is zeroed
     for (int s = 0; s < maxlen; ++s) {
-      const int cur = s & 1, nxt = cur ^ 1;
+      cluster_wait();                         // B: h_{t-1} of all units is in my buffer
+      float acc[4][2][4];
       if (worker) {
-        float acc[4][2][4];
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
           for (int i = 0; i < 4; ++i) { acc[g][0][i] = gxr[g][i].x; acc[g][1][i] = gxr[g][i].y; }
         if (s + 1 < maxlen) load_gx(s + 1);   // in flight during the k loop
-        const float* hb = hT + (size_t)cur * HID * MT + 4 * rg;
+        const float* hb = hT + 4 * rg;
         const float* wb = Wt + j0;
 #pragma unroll 4
         for (int k = 0; k < HID; ++k) {
@@ -147,6 +152,9 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
             acc[g][1][2] = fmaf(w.y, hv.z, acc[g][1][2]); acc[g][1][3] = fmaf(w.y, hv.w, acc[g][1][3]);
           }
         }
+      }
+      cluster_arrive();                       // A: this CTA no longer reads h_{t-1}
+      if (worker) {
         // gates, state update, stash
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -156,12 +164,12 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
             float ig[2], fg[2], gg[2], og[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              ig[u] = sigmoidf_(acc[0][u][i]);
-              fg[u] = sigmoidf_(acc[1][u][i]);
-              gg[u] = tanhf(acc[2][u][i]);
-              og[u] = sigmoidf_(acc[3][u][i]);
+              ig[u] = fast_sigmoid(acc[0][u][i]);
+              fg[u] = fast_sigmoid(acc[1][u][i]);
+              gg[u] = fast_tanh(acc[2][u][i]);
+              og[u] = fast_sigmoid(acc[3][u][i]);
               cst[u][i] = fg[u] * cst[u][i] + ig[u] * gg[u];
-              hst[u][i] = og[u] * tanhf(cst[u][i]);
+              hst[u][i] = og[u] * fast_tanh(cst[u][i]);
             }
             float* gp = gx + p * GS + (size_t)dir * 4 * HID + unit0;
             *reinterpret_cast<float2*>(gp) = make_float2(ig[0], ig[1]);
@@ -175,19 +183,22 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
                   make_float2(cst[0][i], cst[1][i]);
           }
         }
+      }
+      cluster_wait();                         // A: every CTA finished reading -> the h buffers may be overwritten
+      if (worker) {
         // broadcast the new h slice to every CTA of the cluster (frozen rows re-send their state)
         float4 h0 = make_float4(hst[0][0], hst[0][1], hst[0][2], hst[0][3]);
         float4 h1 = make_float4(hst[1][0], hst[1][1], hst[1][2], hst[1][3]);
 #pragma unroll
         for (int d = 0; d < CL; ++d) {
-          float* dst = remote_hT[d] + (size_t)nxt * HID * MT + (size_t)unit0 * MT + 4 * rg;
+          float* dst = remote_hT[d] + (size_t)unit0 * MT + 4 * rg;
           *reinterpret_cast<float4*>(dst) = h0;
           *reinterpret_cast<float4*>(dst + MT) = h1;
         }
       }
-      cluster_arrive();
-      cluster_wait();
+      cluster_arrive();                       // B
     }
+    cluster_wait();                           // balance the last arrive(B): all remote writes have landed
   }
   // no CTA may exit while a peer can still write into its shared memory
   cluster_arrive();
@@ -202,7 +213,10 @@ __global__ void __launch_bounds__(C::NT, 1)
 lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, const float* __restrict__ w_hh,
                 const int32_t* __restrict__ len, const int32_t* __restrict__ off, const int32_t* __restrict__ order,
                 int N, int ntiles, const float* __restrict__ dh, const float* __restrict__ dcn) {
-  constexpr int HID = C::HID, CL = C::CL, MT = C::MT, UPC = C::UPC, COLS = C::COLS, UP = C::UP, KG = C::KG;
+  constexpr int HID = C::HID, CL = C::CL, MT = C::MT, UPC = C::UPC, COLS = C::COLS, UG = C::UG;
+  static_assert(C::UPT == 1, "backward kernel is written for 1 unit per thread");
+  constexpr int KG = HID / 4;                  // phase 2: groups of 4 k's
+  static_assert(KG * C::RG <= C::NT, "backward phase-2 mapping does not fit");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* Wc = reinterpret_cast<float*>(smem_raw);                 // [COLS][HID]  (c-major)
   float* dzT = Wc + (size_t)COLS * HID;                           // [COLS][MT]
@@ -218,19 +232,17 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, co
   const int dir = cluster_id & 1;
   const int tid = threadIdx.x;
   const bool worker = tid < C::NWORK;
-  const int up = tid % UP, rg = tid / UP;
-  const int j0 = 2 * up;
-  const int unit0 = rank * UPC + j0;
-  // phase-2 mapping
-  const bool worker2 = tid < KG * C::RG;
+  const int j = tid % UG, rg = tid / UG;       // phase 1: one hidden unit x 4 rows
+  const int unit = rank * UPC + j;
+  const bool worker2 = tid < KG * C::RG;       // phase 2: 4 k's x 4 rows
   const int kg = tid % KG, rg2 = tid / KG;
 
   {
     const float* W = w_hh + (size_t)dir * 4 * HID * HID;
     for (int idx = tid; idx < COLS * HID; idx += C::NT) {
       int c = idx / HID, k = idx - c * HID;
-      int g = c / UPC, j = c - g * UPC;
-      Wc[idx] = W[(size_t)(g * HID + rank * UPC + j) * HID + k];
+      int g = c / UPC, jj = c - g * UPC;
+      Wc[idx] = W[(size_t)(g * HID + rank * UPC + jj) * HID + k];
     }
   }
   float* remote_recv[CL];
@@ -251,13 +263,13 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, co
     int maxlen = 0;
     for (int i = 0; i < MT; ++i) maxlen = max(maxlen, s_len[i]);
     int rlen[4], roff[4], rrow[4];
-    float dcc[2][4];   // dL/dc carried to the previous step
+    float dcc[4];      // dL/dc carried to the previous step
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       rlen[i] = worker ? s_len[4 * rg + i] : 0;
       roff[i] = worker ? s_off[4 * rg + i] : 0;
       rrow[i] = worker ? s_row[4 * rg + i] : -1;
-      dcc[0][i] = dcc[1][i] = 0.f;
+      dcc[i] = 0.f;
     }
     cluster_arrive();   // pairs with the first "wait B" below
     for (int s = maxlen - 1; s >= 0; --s) {
@@ -265,89 +277,74 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, co
       if (worker) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float dz[4][2];
+          float dz[4];
           if (s < rlen[i]) {
             int t = dir ? (rlen[i] - 1 - s) : s;
             size_t p = (size_t)roff[i] + t;
-            float* gp = gates + p * GS + (size_t)dir * 4 * HID + unit0;
-            float2 ig = *reinterpret_cast<const float2*>(gp);
-            float2 fg = *reinterpret_cast<const float2*>(gp + HID);
-            float2 gg = *reinterpret_cast<const float2*>(gp + 2 * HID);
-            float2 og = *reinterpret_cast<const float2*>(gp + 3 * HID);
-            float2 ct = *reinterpret_cast<const float2*>(c_stash + (p * 2 + dir) * HID + unit0);
-            float2 cp = make_float2(0.f, 0.f);
+            float* gp = gates + p * GS + (size_t)dir * 4 * HID + unit;
+            float iv = gp[0], fv = gp[HID], gv = gp[2 * HID], ov = gp[3 * HID];
+            float cv = c_stash[(p * 2 + dir) * HID + unit];
+            float cpv = 0.f;
             if (s > 0) {
               size_t pp = dir ? p + 1 : p - 1;
-              cp = *reinterpret_cast<const float2*>(c_stash + (pp * 2 + dir) * HID + unit0);
+              cpv = c_stash[(pp * 2 + dir) * HID + unit];
             }
-            float2 dhu = *reinterpret_cast<const float2*>(dh + p * 2 * HID + (size_t)dir * HID + unit0);
-            float dht[2] = {dhu.x, dhu.y};
+            float dht = dh[p * 2 * HID + (size_t)dir * HID + unit];
             if (s == rlen[i] - 1) {   // the row's last step: start of its backward recursion
-              float2 d0 = *reinterpret_cast<const float2*>(dcn + (size_t)rrow[i] * 2 * HID + (size_t)dir * HID + unit0);
-              dcc[0][i] = d0.x; dcc[1][i] = d0.y;
-            } else if (s < maxlen - 1) {
+              dcc[i] = dcn[(size_t)rrow[i] * 2 * HID + (size_t)dir * HID + unit];
+            } else {
               // recurrent part: sum of the CL partials in fixed order
+              float r = 0.f;
 #pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                float r = 0.f;
-#pragma unroll
-                for (int src = 0; src < CL; ++src) r += recv[((size_t)src * UPC + j0 + u) * MT + 4 * rg + i];
-                dht[u] += r;
-              }
+              for (int src = 0; src < CL; ++src) r += recv[((size_t)src * UPC + j) * MT + 4 * rg + i];
+              dht += r;
             }
-            float iv[2] = {ig.x, ig.y}, fv[2] = {fg.x, fg.y}, gv[2] = {gg.x, gg.y}, ov[2] = {og.x, og.y};
-            float cv[2] = {ct.x, ct.y}, cpv[2] = {cp.x, cp.y};
+            float tc = fast_tanh(cv);
+            float dc = dcc[i] + dht * ov * (1.f - tc * tc);
+            dz[3] = dht * tc * ov * (1.f - ov);
+            dz[0] = dc * gv * iv * (1.f - iv);
+            dz[2] = dc * iv * (1.f - gv * gv);
+            dz[1] = dc * cpv * fv * (1.f - fv);
+            dcc[i] = dc * fv;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              float tc = tanhf(cv[u]);
-              float dc = dcc[u][i] + dht[u] * ov[u] * (1.f - tc * tc);
-              dz[3][u] = dht[u] * tc * ov[u] * (1.f - ov[u]);
-              dz[0][u] = dc * gv[u] * iv[u] * (1.f - iv[u]);
-              dz[2][u] = dc * iv[u] * (1.f - gv[u] * gv[u]);
-              dz[1][u] = dc * cpv[u] * fv[u] * (1.f - fv[u]);
-              dcc[u][i] = dc * fv[u];
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) *reinterpret_cast<float2*>(gp + g * HID) = make_float2(dz[g][0], dz[g][1]);
+            for (int g = 0; g < 4; ++g) gp[g * HID] = dz[g];
           } else {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) dz[g][0] = dz[g][1] = 0.f;
+            for (int g = 0; g < 4; ++g) dz[g] = 0.f;
           }
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            dzT[(size_t)(g * UPC + j0) * MT + 4 * rg + i] = dz[g][0];
-            dzT[(size_t)(g * UPC + j0 + 1) * MT + 4 * rg + i] = dz[g][1];
-          }
+          for (int g = 0; g < 4; ++g) dzT[(size_t)(g * UPC + j) * MT + 4 * rg + i] = dz[g];
         }
       }
       cluster_arrive();   // A: this CTA no longer reads recv
       __syncthreads();    // dzT complete
-      float acc[8][4];
+      float acc[4][4];
       if (worker2 && s > 0) {
 #pragma unroll
-        for (int a = 0; a < 8; ++a)
+        for (int a = 0; a < 4; ++a)
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[a][i] = 0.f;
-        const float* wb = Wc + 8 * kg;
+        const float* wb = Wc + 4 * kg;
         const float* zb = dzT + 4 * rg2;
-#pragma unroll 4
+#pragma unroll 8
         for (int c = 0; c < COLS; ++c) {
           float4 z = *reinterpret_cast<const float4*>(zb + (size_t)c * MT);
-          float4 w0 = *reinterpret_cast<const float4*>(wb + (size_t)c * HID);
-          float4 w1 = *reinterpret_cast<const float4*>(wb + (size_t)c * HID + 4);
-          float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-          for (int a = 0; a < 8; ++a) {
-            acc[a][0] = fmaf(wv[a], z.x, acc[a][0]); acc[a][1] = fmaf(wv[a], z.y, acc[a][1]);
-            acc[a][2] = fmaf(wv[a], z.z, acc[a][2]); acc[a][3] = fmaf(wv[a], z.w, acc[a][3]);
-          }
+          float4 w = *reinterpret_cast<const float4*>(wb + (size_t)c * HID);
+          acc[0][0] = fmaf(w.x, z.x, acc[0][0]); acc[0][1] = fmaf(w.x, z.y, acc[0][1]);
+          acc[0][2] = fmaf(w.x, z.z, acc[0][2]); acc[0][3] = fmaf(w.x, z.w, acc[0][3]);
+          acc[1][0] = fmaf(w.y, z.x, acc[1][0]); acc[1][1] = fmaf(w.y, z.y, acc[1][1]);
+          acc[1][2] = fmaf(w.y, z.z, acc[1][2]); acc[1][3] = fmaf(w.y, z.w, acc[1][3]);
+          acc[2][0] = fmaf(w.z, z.x, acc[2][0]); acc[2][1] = fmaf(w.z, z.y, acc[2][1]);
+          acc[2][2] = fmaf(w.z, z.z, acc[2][2]); acc[2][3] = fmaf(w.z, z.w, acc[2][3]);
+          acc[3][0] = fmaf(w.w, z.x, acc[3][0]); acc[3][1] = fmaf(w.w, z.y, acc[3][1]);
+          acc[3][2] = fmaf(w.w, z.z, acc[3][2]); acc[3][3] = fmaf(w.w, z.w, acc[3][3]);
         }
       }
       cluster_wait();     // A: every CTA has finished reading its recv -> safe to overwrite
       if (worker2 && s > 0) {
 #pragma unroll
-        for (int a = 0; a < 8; ++a) {
-          int k = 8 * kg + a;
+        for (int a = 0; a < 4; ++a) {
+          int k = 4 * kg + a;
           int owner = k / UPC, kl = k - owner * UPC;
           float* dst = remote_recv[owner] + ((size_t)rank * UPC + kl) * MT + 4 * rg2;
           *reinterpret_cast<float4*>(dst) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
@@ -364,28 +361,32 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, co
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef LCfg<200, 4, 32> Cfg200;
+typedef LCfg<200, 4, 64, 2> FwdCfg200;     // 25 unit pairs x 16 row groups = 400 threads
+typedef LCfg<200, 4, 32, 1> BwdCfg200;     // 50 units x 8 row groups = 400 threads
 
 template <class C, class K>
 static int launch_cluster(K kernel, size_t smem, int ntiles, cudaStream_t st, void** args, const char* name) {
-  static int max_clusters_cache[2] = {0, 0};
-  NNR_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static int max_clusters_cache = 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NNR_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = C::CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cfg.blockDim = dim3(C::NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  int slot = (smem == C::FWD_SMEM) ? 0 : 1;
-  if (max_clusters_cache[slot] == 0) {
+  if (max_clusters_cache == 0) {
     cfg.gridDim = dim3(C::CL * 2);
     int nc = 0;
     cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, (const void*)kernel, &cfg);
     if (e != cudaSuccess || nc < 2) { (void)cudaGetLastError(); nc = 32; }
-    max_clusters_cache[slot] = nc & ~1;
+    max_clusters_cache = nc & ~1;
   }
   int want = 2 * ntiles;                      // (tile, direction) pairs
-  int nclusters = want < max_clusters_cache[slot] ? want : max_clusters_cache[slot];
+  int nclusters = want < max_clusters_cache ? want : max_clusters_cache;
   if (nclusters < 2) nclusters = 2;
   cfg.gridDim = dim3(nclusters * C::CL);
   cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)kernel, args);
@@ -401,7 +402,7 @@ extern "C" int nnr_lstm_fwd(float* gx, const float* w_hh, const int32_t* len, co
   NNR_REQUIRE(H == 200, NNR_ERR_UNSUPPORTED, "nnr_lstm_fwd: hidden_dim %d not instantiated (200 only)", H);
   NNR_REQUIRE(nnr_aligned16(gx) && nnr_aligned16(h_out) && nnr_aligned16(c_stash) && nnr_aligned16(c_n), NNR_ERR_ALIGN,
               "nnr_lstm_fwd: buffers must be 16B aligned");
-  typedef Cfg200 C;
+  typedef FwdCfg200 C;
   int ntiles = (N + C::MT - 1) / C::MT;
   void* args[] = {&gx, &w_hh, &len, &off, &order, &N, &ntiles, &h_out, &c_stash, &c_n};
   return launch_cluster<C>(lstm_fwd_kernel<C>, C::FWD_SMEM, ntiles, (cudaStream_t)stream, args, "lstm_fwd_kernel");
@@ -414,7 +415,7 @@ extern "C" int nnr_lstm_bwd(float* gates, const float* c_stash, const float* w_h
   NNR_REQUIRE(H == 200, NNR_ERR_UNSUPPORTED, "nnr_lstm_bwd: hidden_dim %d not instantiated (200 only)", H);
   NNR_REQUIRE(nnr_aligned16(gates) && nnr_aligned16(c_stash) && nnr_aligned16(dh) && nnr_aligned16(dcn), NNR_ERR_ALIGN,
               "nnr_lstm_bwd: buffers must be 16B aligned");
-  typedef Cfg200 C;
+  typedef BwdCfg200 C;
   int ntiles = (N + C::MT - 1) / C::MT;
   void* args[] = {&gates, &c_stash, &w_hh, &len, &off, &order, &N, &ntiles, &dh, &dcn};
   return launch_cluster<C>(lstm_bwd_kernel<C>, C::BWD_SMEM, ntiles, (cudaStream_t)stream, args, "lstm_bwd_kernel");
