@@ -107,15 +107,16 @@ int nnr_segment_colsum(const float* X, int64_t ldx, const int32_t* off, int N, i
  *   order   [N]              rows sorted by length, longest first (tile homogeneity only)
  *   h_out   [tokens, 2H]     h_t, forward | reverse
  *   c_stash [tokens, 2, H]   c_t for the backward pass
- *   c_n     [N, 2H]          final cell state per row (forward | reverse)  (newsEncoders.py:124) */
+ *   c_n     [N, 2H]          final cell state per row (forward | reverse)  (newsEncoders.py:124)
+ *   tile_counters [2] int32  scratch for the dynamic (longest-tile-first) scheduler; zeroed by the call */
 int nnr_lstm_fwd(float* gx, const float* w_hh, const int32_t* len, const int32_t* off,
                  const int32_t* order, int N, int L, int H, float* h_out, float* c_stash,
-                 float* c_n, void* stream);
+                 float* c_n, int32_t* tile_counters, void* stream);
 /* BPTT.  gates (the stash written by nnr_lstm_fwd) is overwritten IN PLACE with dL/d(pre-
  * activation) = dL/d(gx).  dh [tokens,2H] and dcn [N,2H] are the upstream gradients.            */
 int nnr_lstm_bwd(float* gates, const float* c_stash, const float* w_hh, const int32_t* len,
                  const int32_t* off, const int32_t* order, int N, int L, int H, const float* dh,
-                 const float* dcn, void* stream);
+                 const float* dcn, int32_t* tile_counters, void* stream);
 /* hprev[p, 0:H] = h[p-1, 0:H] (0 at t=0); hprev[p, H:2H] = h[p+1, H:2H] (0 at t=len-1): the
  * recurrent input of every step, needed for dW_hh = dgates^T hprev.                             */
 int nnr_lstm_shift_h(const float* h, const int32_t* len, const int32_t* off,

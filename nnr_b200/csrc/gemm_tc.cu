@@ -399,34 +399,55 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r);
 }
 template <bool BF16>
-__global__ void tc_split_kernel(const float* __restrict__ src, int64_t ld, int R, int C, int Cp, const int32_t* __restrict__ r_dev,
-                                bool vec, void* __restrict__ out, size_t plane_stride) {
+__global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__ src, int64_t ld, int R, int C, int Cp,
+                                                       const int32_t* __restrict__ r_dev, bool vec, void* __restrict__ out,
+                                                       size_t plane_stride) {
   int Rv = R;
   if (r_dev) Rv = min(R, *r_dev);
   const int Rw = r_dev ? min(R, (Rv + 63) / 64 * 64) : R;
-  const int cq = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
-  const int r = blockIdx.x;
-  if (r >= Rw || cq >= Cp) return;
-  float x[4] = {0.f, 0.f, 0.f, 0.f};
-  if (r < Rv) {
-    const float* s = src + (size_t)r * ld + cq;
-    if (vec && cq + 3 < C) { float4 v = __ldg(reinterpret_cast<const float4*>(s)); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
-    else {
+  const int cq_per_row = Cp >> 2;                                   // float4 groups per row
+  const long long total = (long long)Rw * cq_per_row;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // grid-stride over (row, 4-column group); four independent 16-byte loads in flight per thread
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    float4 x[4];
+    int rr[4], cc[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) if (cq + i < C) x[i] = __ldg(s + i);
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rr[u] = -1;
+      if (i < total) {
+        const int r = (int)(i / cq_per_row), cq = (int)(i - (long long)r * cq_per_row) * 4;
+        rr[u] = r; cc[u] = cq;
+        if (r < Rv) {
+          const float* sp = src + (size_t)r * ld + cq;
+          if (vec && cq + 3 < C) x[u] = __ldg(reinterpret_cast<const float4*>(sp));
+          else {
+            if (cq < C) x[u].x = __ldg(sp);
+            if (cq + 1 < C) x[u].y = __ldg(sp + 1);
+            if (cq + 2 < C) x[u].z = __ldg(sp + 2);
+            if (cq + 3 < C) x[u].w = __ldg(sp + 3);
+          }
+        }
+      }
     }
-  }
-  if (BF16) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + (size_t)r * Cp + cq;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] = __float2bfloat16_rn(x[i]);      // Cp % 8 == 0
-  } else {
-    float* hi = reinterpret_cast<float*>(out) + (size_t)r * Cp + cq;
-    float h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { h[i] = rna_tf32(x[i]); l[i] = rna_tf32(x[i] - h[i]); }
-    *reinterpret_cast<float4*>(hi) = make_float4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<float4*>(hi + plane_stride) = make_float4(l[0], l[1], l[2], l[3]);
+    for (int u = 0; u < 4; ++u) {
+      if (rr[u] < 0) continue;
+      if (BF16) {
+        __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(out) + (size_t)rr[u] * Cp + cc[u]);
+        o[0] = __floats2bfloat162_rn(x[u].x, x[u].y);                // Cp % 8 == 0 -> 8-byte aligned
+        o[1] = __floats2bfloat162_rn(x[u].z, x[u].w);
+      } else {
+        float* hi = reinterpret_cast<float*>(out) + (size_t)rr[u] * Cp + cc[u];
+        float4 h, l;
+        h.x = rna_tf32(x[u].x); h.y = rna_tf32(x[u].y); h.z = rna_tf32(x[u].z); h.w = rna_tf32(x[u].w);
+        l.x = rna_tf32(x[u].x - h.x); l.y = rna_tf32(x[u].y - h.y); l.z = rna_tf32(x[u].z - h.z); l.w = rna_tf32(x[u].w - h.w);
+        *reinterpret_cast<float4*>(hi) = h;
+        *reinterpret_cast<float4*>(hi + plane_stride) = l;
+      }
+    }
   }
 }
 
@@ -486,9 +507,17 @@ static TcPlan make_plan(const nnr_gemm_args* a, bool bf16) {
   pl.b_cp = (int)up((size_t)pl.b_cols, pad);
   pl.block_n = pick_block_n(a->N, pl.b_mn ? pl.kelem : 16);
   long tiles = (long)((a->M + TC_BM - 1) / TC_BM) * ((a->N + pl.block_n - 1) / pl.block_n);
-  pl.split_k = (tiles < 148 && a->K >= 4096) ? 1 : 0;
-  pl.chain_kb = TC_CHAIN_K / pl.kelem;
+  // split-K: (a) fill the machine when the output grid is small, (b) bound the TMEM accumulation chain
   int nkb_cap = (a->K + pl.kelem - 1) / pl.kelem;
+  pl.split_k = 0;
+  pl.chain_kb = TC_CHAIN_K / pl.kelem;
+  if (tiles < 148 && nkb_cap >= 8) {
+    int target = (int)((148 + tiles - 1) / tiles);
+    int chain = (nkb_cap + target - 1) / target;
+    if (chain < 4) chain = 4;
+    if (chain > TC_CHAIN_K / pl.kelem) chain = TC_CHAIN_K / pl.kelem;
+    if (chain < nkb_cap) { pl.split_k = 1; pl.chain_kb = chain; }
+  }
   pl.max_splits = pl.split_k ? (nkb_cap + pl.chain_kb - 1) / pl.chain_kb : 1;
   size_t stage = (size_t)pl.nplanes * ((size_t)TC_BM * 128 + (size_t)pl.block_n * 128);
   int stages = (int)(TC_SMEM_BUDGET / stage);
@@ -542,8 +571,11 @@ template <bool BF16>
 static int split_operand(const float* X, int64_t ld, int R, int C, int Cp, const int32_t* r_dev, void* out, size_t plane_stride,
                          cudaStream_t st) {
   bool vec = nnr_aligned16(X) && (ld % 4 == 0);
-  dim3 grid(R, (Cp / 4 + 127) / 128);
-  tc_split_kernel<BF16><<<grid, 128, 0, st>>>(X, ld, R, C, Cp, r_dev, vec, out, plane_stride);
+  long long total = (long long)R * (Cp / 4);
+  long long want = (total + 256 * 4 - 1) / (256 * 4);
+  int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+  if (grid < 1) grid = 1;
+  tc_split_kernel<BF16><<<grid, 256, 0, st>>>(X, ld, R, C, Cp, r_dev, vec, out, plane_stride);
   NNR_LAUNCH_CHECK("tc_split_kernel");
   return 0;
 }

@@ -6,12 +6,12 @@
 //     hidden units [r*H/4, (r+1)*H/4): the i,f,g,o rows of those units, i.e. a [4*H/4, H] slice of
 //     W_hh = 160 KB fp32 for H = 200, which stays in shared memory for every time step of every tile the
 //     cluster processes (the kernel is persistent over tiles).
-//   * forward step (64-row tiles, 13 warps): z = gx_t + h_{t-1} W_slice^T, register tiled FFMA (2 units x
-//     4 gates x 4 rows per thread), fused sigmoid/tanh/cell update with c_t kept in registers, then the new
-//     h slice is broadcast into all four CTAs' h buffers through distributed shared memory.  The h buffer
-//     is single (W + a 64-row h tile fill the 227 KB), so a step uses two split-phase cluster barriers:
-//     "h complete" (B) and "everyone finished reading h" (A); the gate math sits between arrive(A) and
-//     wait(A).
+//   * forward step (32-row tiles): z = gx_t + h_{t-1} W_slice^T, register tiled FFMA (2 units x 4 gates x
+//     4 rows per thread), fused sigmoid/tanh/cell update with c_t kept in registers, then the new h slice is
+//     broadcast into all four CTAs' (double-buffered) h tiles through distributed shared memory and one
+//     barrier.cluster per step publishes it.  (A 64-row single-buffer variant was measured: better FFMA
+//     efficiency but a longer per-step latency, which loses on MIND-like length distributions where the
+//     longest sequences set the critical path.)
 //   * backward step (32-row tiles): each CTA turns dh_t (+ recurrent part) into d(pre-activations) for its
 //     own units, multiplies them with its W slice to get a PARTIAL dh_{t-1} over all H units, and
 //     reduce-scatters the partials to the owning CTAs through DSMEM (fixed summation order ->
@@ -35,7 +35,7 @@ struct LCfg {
   static constexpr int NWORK = UG * RG;       // working threads
   static constexpr int NT = ((NWORK + 31) / 32) * 32;
   static_assert(HID % CL == 0 && UPC % UPT == 0 && MT % 4 == 0 && HID % 4 == 0, "unsupported LSTM geometry");
-  static constexpr size_t FWD_SMEM = sizeof(float) * ((size_t)HID * COLS + (size_t)HID * MT) + 3 * MT * sizeof(int);
+  static constexpr size_t FWD_SMEM = sizeof(float) * ((size_t)HID * COLS + 2 * (size_t)HID * MT) + 3 * MT * sizeof(int);
   static constexpr size_t BWD_SMEM = sizeof(float) * ((size_t)COLS * HID + (size_t)COLS * MT + (size_t)CL * UPC * MT) + 3 * MT * sizeof(int);
 };
 
@@ -53,13 +53,12 @@ template <class C>
 __global__ void __launch_bounds__(C::NT, 1)
 lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const int32_t* __restrict__ len,
                 const int32_t* __restrict__ off, const int32_t* __restrict__ order, int N, int ntiles,
-                float* __restrict__ h_out, float* __restrict__ c_stash, float* __restrict__ c_n) {
-  constexpr int HID = C::HID, CL = C::CL, MT = C::MT, UPC = C::UPC, COLS = C::COLS, UG = C::UG;
-  static_assert(C::UPT == 2, "forward kernel is written for 2 units per thread");
+                float* __restrict__ h_out, float* __restrict__ c_stash, float* __restrict__ c_n, int* __restrict__ tile_counter) {
+  constexpr int HID = C::HID, CL = C::CL, MT = C::MT, UPC = C::UPC, COLS = C::COLS, UP = C::UG;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* Wt = reinterpret_cast<float*>(smem_raw);                 // [HID][COLS]
-  float* hT = Wt + (size_t)HID * COLS;                            // [HID][MT]
-  int* s_row = reinterpret_cast<int*>(hT + (size_t)HID * MT);     // [MT]
+  float* hT = Wt + (size_t)HID * COLS;                            // [2][HID][MT]
+  int* s_row = reinterpret_cast<int*>(hT + 2 * (size_t)HID * MT); // [MT]
   int* s_len = s_row + MT;
   int* s_off = s_len + MT;
 
@@ -70,7 +69,7 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
   const int dir = cluster_id & 1;
   const int tid = threadIdx.x;
   const bool worker = tid < C::NWORK;
-  const int up = tid % UG, rg = tid / UG;
+  const int up = tid % UP, rg = tid / UP;
   const int j0 = 2 * up;                       // local unit of this thread (and j0+1)
   const int unit0 = rank * UPC + j0;           // global hidden unit
 
@@ -88,7 +87,23 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
   for (int d = 0; d < CL; ++d) remote_hT[d] = cluster.map_shared_rank(hT, d);
 
   const size_t GS = (size_t)2 * 4 * HID;  // gx row stride (both directions)
-  for (int tile = cluster_id >> 1; tile < ntiles; tile += (nclusters >> 1)) {
+  // dynamic tile scheduling: tiles are sorted longest-first, so handing the next tile to whichever cluster
+  // becomes free is longest-processing-time-first list scheduling (one atomic per tile, broadcast via DSMEM)
+  __shared__ int s_tile;
+  int* remote_tile[CL];
+#pragma unroll
+  for (int d = 0; d < CL; ++d) remote_tile[d] = cluster.map_shared_rank(&s_tile, d);
+  (void)nclusters;
+  for (;;) {
+    if (rank == 0 && tid == 0) {
+      int t = atomicAdd(&tile_counter[dir], 1);
+#pragma unroll
+      for (int d = 0; d < CL; ++d) *remote_tile[d] = t;
+    }
+    cluster_arrive();
+    cluster_wait();
+    const int tile = s_tile;
+    if (tile >= ntiles) break;
     __syncthreads();
     if (tid < MT) {
       int i = tile * MT + tid;
@@ -97,7 +112,7 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
       s_len[tid] = (r >= 0) ? len[r] : 0;
       s_off[tid] = (r >= 0) ? off[r] : 0;
     }
-    for (int idx = tid; idx < HID * MT; idx += C::NT) hT[idx] = 0.f;   // h_0 = 0
+    for (int idx = tid; idx < HID * MT; idx += C::NT) hT[idx] = 0.f;   // h_0 = 0 in buffer 0
     __syncthreads();
     int maxlen = 0;
     for (int i = 0; i < MT; ++i) maxlen = max(maxlen, s_len[i]);
@@ -111,6 +126,7 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
       rrow[i] = worker ? s_row[4 * rg + i] : -1;
       cst[0][i] = cst[1][i] = hst[0][i] = hst[1][i] = 0.f;
     }
+    // prefetch gx for step 0
     float2 gxr[4][4];  // [gate][row]
     auto load_gx = [&](int s) {
 #pragma unroll
@@ -128,17 +144,16 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
     };
     if (worker) load_gx(0);
 
-    cluster_arrive();                         // B0: my h buffer is zeroed
     for (int s = 0; s < maxlen; ++s) {
-      cluster_wait();                         // B: h_{t-1} of all units is in my buffer
-      float acc[4][2][4];
+      const int cur = s & 1, nxt = cur ^ 1;
       if (worker) {
+        float acc[4][2][4];
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
           for (int i = 0; i < 4; ++i) { acc[g][0][i] = gxr[g][i].x; acc[g][1][i] = gxr[g][i].y; }
         if (s + 1 < maxlen) load_gx(s + 1);   // in flight during the k loop
-        const float* hb = hT + 4 * rg;
+        const float* hb = hT + (size_t)cur * HID * MT + 4 * rg;
         const float* wb = Wt + j0;
 #pragma unroll 4
         for (int k = 0; k < HID; ++k) {
@@ -152,9 +167,6 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
             acc[g][1][2] = fmaf(w.y, hv.z, acc[g][1][2]); acc[g][1][3] = fmaf(w.y, hv.w, acc[g][1][3]);
           }
         }
-      }
-      cluster_arrive();                       // A: this CTA no longer reads h_{t-1}
-      if (worker) {
         // gates, state update, stash
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -183,22 +195,19 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
                   make_float2(cst[0][i], cst[1][i]);
           }
         }
-      }
-      cluster_wait();                         // A: every CTA finished reading -> the h buffers may be overwritten
-      if (worker) {
         // broadcast the new h slice to every CTA of the cluster (frozen rows re-send their state)
         float4 h0 = make_float4(hst[0][0], hst[0][1], hst[0][2], hst[0][3]);
         float4 h1 = make_float4(hst[1][0], hst[1][1], hst[1][2], hst[1][3]);
 #pragma unroll
         for (int d = 0; d < CL; ++d) {
-          float* dst = remote_hT[d] + (size_t)unit0 * MT + 4 * rg;
+          float* dst = remote_hT[d] + (size_t)nxt * HID * MT + (size_t)unit0 * MT + 4 * rg;
           *reinterpret_cast<float4*>(dst) = h0;
           *reinterpret_cast<float4*>(dst + MT) = h1;
         }
       }
-      cluster_arrive();                       // B
+      cluster_arrive();
+      cluster_wait();
     }
-    cluster_wait();                           // balance the last arrive(B): all remote writes have landed
   }
   // no CTA may exit while a peer can still write into its shared memory
   cluster_arrive();
@@ -212,7 +221,7 @@ template <class C>
 __global__ void __launch_bounds__(C::NT, 1)
 lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, const float* __restrict__ w_hh,
                 const int32_t* __restrict__ len, const int32_t* __restrict__ off, const int32_t* __restrict__ order,
-                int N, int ntiles, const float* __restrict__ dh, const float* __restrict__ dcn) {
+                int N, int ntiles, const float* __restrict__ dh, const float* __restrict__ dcn, int* __restrict__ tile_counter) {
   constexpr int HID = C::HID, CL = C::CL, MT = C::MT, UPC = C::UPC, COLS = C::COLS, UG = C::UG;
   static_assert(C::UPT == 1, "backward kernel is written for 1 unit per thread");
   constexpr int KG = HID / 4;                  // phase 2: groups of 4 k's
@@ -250,7 +259,23 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, co
   for (int d = 0; d < CL; ++d) remote_recv[d] = cluster.map_shared_rank(recv, d);
 
   const size_t GS = (size_t)2 * 4 * HID;
-  for (int tile = cluster_id >> 1; tile < ntiles; tile += (nclusters >> 1)) {
+  // dynamic tile scheduling: tiles are sorted longest-first, so handing the next tile to whichever cluster
+  // becomes free is longest-processing-time-first list scheduling (one atomic per tile, broadcast via DSMEM)
+  __shared__ int s_tile;
+  int* remote_tile[CL];
+#pragma unroll
+  for (int d = 0; d < CL; ++d) remote_tile[d] = cluster.map_shared_rank(&s_tile, d);
+  (void)nclusters;
+  for (;;) {
+    if (rank == 0 && tid == 0) {
+      int t = atomicAdd(&tile_counter[dir], 1);
+#pragma unroll
+      for (int d = 0; d < CL; ++d) *remote_tile[d] = t;
+    }
+    cluster_arrive();
+    cluster_wait();
+    const int tile = s_tile;
+    if (tile >= ntiles) break;
     __syncthreads();
     if (tid < MT) {
       int i = tile * MT + tid;
@@ -361,7 +386,7 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, co
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef LCfg<200, 4, 64, 2> FwdCfg200;     // 25 unit pairs x 16 row groups = 400 threads
+typedef LCfg<200, 4, 32, 2> FwdCfg200;     // 25 unit pairs x 8 row groups = 200 threads, double-buffered h
 typedef LCfg<200, 4, 32, 1> BwdCfg200;     // 50 units x 8 row groups = 400 threads
 
 template <class C, class K>
@@ -396,27 +421,31 @@ static int launch_cluster(K kernel, size_t smem, int ntiles, cudaStream_t st, vo
 }
 
 extern "C" int nnr_lstm_fwd(float* gx, const float* w_hh, const int32_t* len, const int32_t* off, const int32_t* order,
-                            int N, int L, int H, float* h_out, float* c_stash, float* c_n, void* stream) {
-  NNR_REQUIRE(gx && w_hh && len && off && order && h_out && c_stash && c_n && N > 0 && L > 0, NNR_ERR_ARG,
+                            int N, int L, int H, float* h_out, float* c_stash, float* c_n, int32_t* tile_counters,
+                            void* stream) {
+  NNR_REQUIRE(gx && w_hh && len && off && order && h_out && c_stash && c_n && tile_counters && N > 0 && L > 0, NNR_ERR_ARG,
               "nnr_lstm_fwd: bad arguments");
   NNR_REQUIRE(H == 200, NNR_ERR_UNSUPPORTED, "nnr_lstm_fwd: hidden_dim %d not instantiated (200 only)", H);
   NNR_REQUIRE(nnr_aligned16(gx) && nnr_aligned16(h_out) && nnr_aligned16(c_stash) && nnr_aligned16(c_n), NNR_ERR_ALIGN,
               "nnr_lstm_fwd: buffers must be 16B aligned");
   typedef FwdCfg200 C;
   int ntiles = (N + C::MT - 1) / C::MT;
-  void* args[] = {&gx, &w_hh, &len, &off, &order, &N, &ntiles, &h_out, &c_stash, &c_n};
+  NNR_CUDA(cudaMemsetAsync(tile_counters, 0, 2 * sizeof(int32_t), (cudaStream_t)stream));
+  void* args[] = {&gx, &w_hh, &len, &off, &order, &N, &ntiles, &h_out, &c_stash, &c_n, &tile_counters};
   return launch_cluster<C>(lstm_fwd_kernel<C>, C::FWD_SMEM, ntiles, (cudaStream_t)stream, args, "lstm_fwd_kernel");
 }
 
 extern "C" int nnr_lstm_bwd(float* gates, const float* c_stash, const float* w_hh, const int32_t* len, const int32_t* off,
-                            const int32_t* order, int N, int L, int H, const float* dh, const float* dcn, void* stream) {
-  NNR_REQUIRE(gates && c_stash && w_hh && len && off && order && dh && dcn && N > 0 && L > 0, NNR_ERR_ARG,
+                            const int32_t* order, int N, int L, int H, const float* dh, const float* dcn,
+                            int32_t* tile_counters, void* stream) {
+  NNR_REQUIRE(gates && c_stash && w_hh && len && off && order && dh && dcn && tile_counters && N > 0 && L > 0, NNR_ERR_ARG,
               "nnr_lstm_bwd: bad arguments");
   NNR_REQUIRE(H == 200, NNR_ERR_UNSUPPORTED, "nnr_lstm_bwd: hidden_dim %d not instantiated (200 only)", H);
   NNR_REQUIRE(nnr_aligned16(gates) && nnr_aligned16(c_stash) && nnr_aligned16(dh) && nnr_aligned16(dcn), NNR_ERR_ALIGN,
               "nnr_lstm_bwd: buffers must be 16B aligned");
   typedef BwdCfg200 C;
   int ntiles = (N + C::MT - 1) / C::MT;
-  void* args[] = {&gates, &c_stash, &w_hh, &len, &off, &order, &N, &ntiles, &dh, &dcn};
+  NNR_CUDA(cudaMemsetAsync(tile_counters, 0, 2 * sizeof(int32_t), (cudaStream_t)stream));
+  void* args[] = {&gates, &c_stash, &w_hh, &len, &off, &order, &N, &ntiles, &dh, &dcn, &tile_counters};
   return launch_cluster<C>(lstm_bwd_kernel<C>, C::BWD_SMEM, ntiles, (cudaStream_t)stream, args, "lstm_bwd_kernel");
 }

@@ -161,7 +161,81 @@ __global__ void eb_keys_kernel(const int32_t* __restrict__ ids, const int32_t* _
   vals[slot] = slot;
 }
 
-// one CTA per chunk of EB_CHUNK sorted slots; one warp per run of equal keys inside the chunk
+// Sum the dout rows of sorted entries first, first+stride, ... (< end) of a chunk into acc (one warp; lane l
+// owns float4 columns l, l+32, l+64).  Slot ids / row offsets are fetched 32 at a time by the lanes and
+// broadcast with shuffles; rows are loaded four at a time so 12 independent 16-byte loads are in flight per
+// lane, and added in entry order (the summation order is a pure function of the sorted order).
+__device__ __forceinline__ void eb_warp_accumulate(float4 (&acc)[3], const float* __restrict__ dout,
+                                                   const int32_t* __restrict__ vals, const int32_t* __restrict__ off, int cs,
+                                                   int L, int E, int E4, int first, int end, int stride, int lane, float p,
+                                                   float inv_keep, uint64_t seed) {
+  for (int base = first; base < end; base += 32 * stride) {
+    const int e = base + lane * stride;
+    int slot_l = 0;
+    unsigned long long src_l = 0;
+    if (e < end) {
+      slot_l = vals[cs + e];
+      int row = slot_l / L, t = slot_l - row * L;
+      src_l = ((unsigned long long)off[row] + t) * (unsigned long long)E;
+    }
+    const int gn = min(32, (end - base + stride - 1) / stride);
+    int j = 0;
+    for (; j + 4 <= gn; j += 4) {
+      float4 v[4][3];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int slot = __shfl_sync(0xffffffffu, slot_l, j + u);
+        const unsigned long long so = __shfl_sync(0xffffffffu, src_l, j + u);
+        const float4* src = reinterpret_cast<const float4*>(dout + so);
+        const uint64_t ebase = (uint64_t)slot * (uint64_t)E;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int c4 = lane + 32 * q;
+          v[u][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c4 < E4) {
+            float4 x = __ldg(src + c4);
+            if (p > 0.0f) {
+              x.x *= dropout_scale(seed, ebase + 4 * c4 + 0, p, inv_keep);
+              x.y *= dropout_scale(seed, ebase + 4 * c4 + 1, p, inv_keep);
+              x.z *= dropout_scale(seed, ebase + 4 * c4 + 2, p, inv_keep);
+              x.w *= dropout_scale(seed, ebase + 4 * c4 + 3, p, inv_keep);
+            }
+            v[u][q] = x;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { acc[q].x += v[u][q].x; acc[q].y += v[u][q].y; acc[q].z += v[u][q].z; acc[q].w += v[u][q].w; }
+    }
+    for (; j < gn; ++j) {
+      const int slot = __shfl_sync(0xffffffffu, slot_l, j);
+      const unsigned long long so = __shfl_sync(0xffffffffu, src_l, j);
+      const float4* src = reinterpret_cast<const float4*>(dout + so);
+      const uint64_t ebase = (uint64_t)slot * (uint64_t)E;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int c4 = lane + 32 * q;
+        if (c4 < E4) {
+          float4 x = __ldg(src + c4);
+          if (p > 0.0f) {
+            x.x *= dropout_scale(seed, ebase + 4 * c4 + 0, p, inv_keep);
+            x.y *= dropout_scale(seed, ebase + 4 * c4 + 1, p, inv_keep);
+            x.z *= dropout_scale(seed, ebase + 4 * c4 + 2, p, inv_keep);
+            x.w *= dropout_scale(seed, ebase + 4 * c4 + 3, p, inv_keep);
+          }
+          acc[q].x += x.x; acc[q].y += x.y; acc[q].z += x.z; acc[q].w += x.w;
+        }
+      }
+    }
+  }
+}
+
+#define EB_LONG 48   // runs at least this long are summed by all 8 warps of the CTA
+
+// one CTA per chunk of EB_CHUNK sorted slots.  Short runs of equal keys: one warp each.  Long runs (frequent
+// words, the <PAD> token): the 8 warps take every 8th entry and their partial sums are combined in warp order.
 __global__ void __launch_bounds__(256) eb_chunk_kernel(const float* __restrict__ dout, const int32_t* __restrict__ keys,
                                                        const int32_t* __restrict__ vals,
                                                        const int32_t* __restrict__ off, int N, int L, int E, float p,
@@ -172,6 +246,7 @@ __global__ void __launch_bounds__(256) eb_chunk_kernel(const float* __restrict__
   __shared__ int32_t s_start[EB_CHUNK + 1];
   __shared__ int32_t s_wcnt[8];
   __shared__ int32_t s_nruns;
+  __shared__ __align__(16) float s_part[8][384];
   const int n_valid = off[N];
   const int chunk = blockIdx.x;
   const int cs = chunk * EB_CHUNK;
@@ -216,54 +291,27 @@ __global__ void __launch_bounds__(256) eb_chunk_kernel(const float* __restrict__
     meta[chunk] = m;
   }
   const int E4 = E >> 2;  // host guarantees E % 4 == 0
-  for (int r = w; r < nruns; r += 8) {
+  // destination of run r: the table row, or a boundary slot when the run crosses the chunk edge
+  auto run_dst = [&](int r, bool& add) -> float* {
+    const bool hc = (r == 0) && head_cross;
+    const bool tc = (r == nruns - 1) && tail_cross;
+    add = false;
+    if (!hc && !tc) { add = accumulate != 0; return dtable + (size_t)s_key[s_start[r] + 1] * E; }
+    if (hc) return slots_ws + (size_t)(2 * chunk) * E;          // head (or covering) piece
+    return slots_ws + (size_t)(2 * chunk + 1) * E;              // tail piece
+  };
+  // phase A: short runs, one warp each
+  int ri = 0;
+  for (int r = 0; r < nruns; ++r) {
     const int a = s_start[r], b = s_start[r + 1];
-    const int key = s_key[a + 1];
+    if (b - a >= EB_LONG) continue;
+    if ((ri++ & 7) != w) continue;
     float4 acc[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    // entries of the run in groups of 32: lanes fetch the slot ids / row offsets in parallel, then the
-    // warp walks the group with shuffles, four rows in flight at a time
-    for (int i0 = a; i0 < b; i0 += 32) {
-      const int gi = i0 + lane;
-      int slot_l = 0;
-      size_t src_l = 0;
-      if (gi < b) {
-        slot_l = vals[cs + gi];
-        int row = slot_l / L, t = slot_l - row * L;
-        src_l = ((size_t)off[row] + t) * E;
-      }
-      const int gn = min(32, b - i0);
-#pragma unroll 4
-      for (int j = 0; j < gn; ++j) {
-        const int slot = __shfl_sync(0xffffffffu, slot_l, j);
-        const size_t so = __shfl_sync(0xffffffffu, (unsigned long long)src_l, j);
-        const float4* src = reinterpret_cast<const float4*>(dout + so);
-        const uint64_t ebase = (uint64_t)slot * (uint64_t)E;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          int c4 = lane + 32 * q;
-          if (c4 < E4) {
-            float4 v = __ldg(src + c4);
-            if (p > 0.0f) {
-              v.x *= dropout_scale(seed, ebase + 4 * c4 + 0, p, inv_keep);
-              v.y *= dropout_scale(seed, ebase + 4 * c4 + 1, p, inv_keep);
-              v.z *= dropout_scale(seed, ebase + 4 * c4 + 2, p, inv_keep);
-              v.w *= dropout_scale(seed, ebase + 4 * c4 + 3, p, inv_keep);
-            }
-            acc[q].x += v.x; acc[q].y += v.y; acc[q].z += v.z; acc[q].w += v.w;
-          }
-        }
-      }
-    }
-    const bool hc = (r == 0) && head_cross;
-    const bool tc = (r == nruns - 1) && tail_cross;
-    float* dst;
+    eb_warp_accumulate(acc, dout, vals, off, cs, L, E, E4, a, b, 1, lane, p, inv_keep, seed);
     bool add;
-    if (!hc && !tc) { dst = dtable + (size_t)key * E; add = accumulate != 0; }
-    else if (hc) { dst = slots_ws + (size_t)(2 * chunk) * E; add = false; }       // head (or covering) piece
-    else { dst = slots_ws + (size_t)(2 * chunk + 1) * E; add = false; }           // tail piece
-    // a run that starts exactly at the chunk start, fills it and continues (covering==2) is a tail piece
+    float* dst = run_dst(r, add);
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
       int c4 = lane + 32 * q;
@@ -274,6 +322,30 @@ __global__ void __launch_bounds__(256) eb_chunk_kernel(const float* __restrict__
         *d4 = v;
       }
     }
+  }
+  // phase B: long runs, all warps cooperate (uniform control flow: every thread sees the same run list)
+  for (int r = 0; r < nruns; ++r) {
+    const int a = s_start[r], b = s_start[r + 1];
+    if (b - a < EB_LONG) continue;
+    float4 acc[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    eb_warp_accumulate(acc, dout, vals, off, cs, L, E, E4, a + w, b, 8, lane, p, inv_keep, seed);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      int c4 = lane + 32 * q;
+      if (c4 < E4) reinterpret_cast<float4*>(s_part[w])[c4] = acc[q];
+    }
+    __syncthreads();
+    bool add;
+    float* dst = run_dst(r, add);
+    for (int e = tid; e < E; e += 256) {
+      float v = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) v += s_part[ww][e];
+      dst[e] = add ? dst[e] + v : v;
+    }
+    __syncthreads();
   }
 }
 

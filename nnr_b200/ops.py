@@ -106,14 +106,20 @@ def segment_colsum(X, ldx, off, N, D, out, ldo):
           'nnr_segment_colsum')
 
 
+def _tile_counters(dev):
+    return workspace(64, dev, 'lstm_counters').view(torch.int32)
+
+
 def lstm_fwd(gx, w_hh, len_, off, order, N, L, H, h_out, c_stash, c_n):
     check(lib.nnr_lstm_fwd(_p(gx, _F32), _p(w_hh, _F32), _p(len_, _I32), _p(off, _I32), _p(order, _I32), N, L, H,
-                           _p(h_out, _F32), _p(c_stash, _F32), _p(c_n, _F32), _stream()), 'nnr_lstm_fwd')
+                           _p(h_out, _F32), _p(c_stash, _F32), _p(c_n, _F32), _tile_counters(gx.device).data_ptr(),
+                           _stream()), 'nnr_lstm_fwd')
 
 
 def lstm_bwd(gates, c_stash, w_hh, len_, off, order, N, L, H, dh, dcn):
     check(lib.nnr_lstm_bwd(_p(gates, _F32), _p(c_stash, _F32), _p(w_hh, _F32), _p(len_, _I32), _p(off, _I32),
-                           _p(order, _I32), N, L, H, _p(dh, _F32), _p(dcn, _F32), _stream()), 'nnr_lstm_bwd')
+                           _p(order, _I32), N, L, H, _p(dh, _F32), _p(dcn, _F32), _tile_counters(gates.device).data_ptr(),
+                           _stream()), 'nnr_lstm_bwd')
 
 
 def lstm_shift_h(h, len_, off, tok_row, N, L, H, hprev):
