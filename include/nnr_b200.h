@@ -35,6 +35,11 @@ const char* nnr_last_error(void);
 int nnr_abi_version(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t nnr_launch_count(void);
+/* kernel-level timing of the kernels inside the composite nnr_gemm op (CUDA events on the launching stream).
+ * tags: 0 gemm_tc_kernel, 1 tc_split_kernel, 2 tc_splitk_reduce_kernel, 3 gemm_simt_kernel.
+ * nnr_profile_read synchronises the device, fills out[3*tag + {0: ms, 1: launches, 2: reserved}] and clears the log. */
+int nnr_profile_enable(int on);
+int nnr_profile_read(double* out, int ntags);
 
 /* ---- sequence bookkeeping: newsEncoders.py:106-111 (mask[:,0]=1 in place, lengths) ---------- */
 int nnr_seq_prepare(uint8_t* mask, int N, int L, int32_t* len, int32_t* off, int32_t* tok_row,

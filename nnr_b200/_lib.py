@@ -55,6 +55,8 @@ SIGNATURES = {
     'nnr_last_error': (C.c_char_p, []),
     'nnr_abi_version': (C.c_int, []),
     'nnr_launch_count': (u64, []),
+    'nnr_profile_enable': (C.c_int, [C.c_int]),
+    'nnr_profile_read': (C.c_int, [C.POINTER(C.c_double), C.c_int]),
     'nnr_seq_prepare': (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),
     'nnr_embed_gather_fwd': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, f32, u64, vp]),
     'nnr_embed_gather_bwd_workspace_bytes': (sz, [C.c_int, C.c_int]),

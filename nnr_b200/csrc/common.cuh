@@ -12,6 +12,9 @@
 
 void nnr_set_error(const char* fmt, ...);
 void nnr_count_launch(int n);
+// kernel-level timing hooks (api_common.cu); tags: 0 gemm_tc_kernel, 1 tc_split_kernel, 2 tc_splitk_reduce, 3 gemm_simt_kernel
+void* nnr_prof_begin(int tag, double flops, void* stream);
+void nnr_prof_end(void* h, void* stream);
 
 #define NNR_REQUIRE(cond, code, ...)              \
   do {                                            \

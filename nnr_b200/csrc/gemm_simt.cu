@@ -169,11 +169,13 @@ int nnr_gemm_simt(const nnr_gemm_args* a, void* stream) {
 #define LAUNCH(AK, BKc)                                                                                          \
   gemm_simt_kernel<AK, BKc><<<grid, GT, 0, st>>>(a->A, a->lda, a->B, a->ldb, a->M, a->N, a->K, a->m_dev, a->k_dev, \
                                                  splits, vecA, vecB, e, partial)
+  void* ph = nnr_prof_begin(3, 0.0, st);
   if (akc && bkc) LAUNCH(true, true);
   else if (akc && !bkc) LAUNCH(true, false);
   else if (!akc && bkc) LAUNCH(false, true);
   else LAUNCH(false, false);
 #undef LAUNCH
+  nnr_prof_end(ph, st);
   NNR_LAUNCH_CHECK("gemm_simt_kernel");
   if (splits > 1) {
     size_t tot = (size_t)a->M * a->N;

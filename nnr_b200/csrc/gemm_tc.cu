@@ -575,7 +575,9 @@ static int split_operand(const float* X, int64_t ld, int R, int C, int Cp, const
   long long want = (total + 256 * 4 - 1) / (256 * 4);
   int grid = (int)(want < 148 * 16 ? want : 148 * 16);
   if (grid < 1) grid = 1;
+  void* ph = nnr_prof_begin(1, 0.0, st);
   tc_split_kernel<BF16><<<grid, 256, 0, st>>>(X, ld, R, C, Cp, r_dev, vec, out, plane_stride);
+  nnr_prof_end(ph, st);
   NNR_LAUNCH_CHECK("tc_split_kernel");
   return 0;
 }
@@ -625,12 +627,16 @@ static int run_tc(const nnr_gemm_args* a, cudaStream_t st) {
   }
   long cap_tiles = (long)((a->M + TC_BM - 1) / TC_BM) * ((a->N + pl.block_n - 1) / pl.block_n) * pl.max_splits;
   int grid = (int)(cap_tiles < num_sms ? cap_tiles : num_sms);
+  void* ph = nnr_prof_begin(0, -1.0, st);     // flops are filled in by the caller-side profiler (needs m_dev/k_dev)
   gemm_tc_kernel<BF16><<<grid, TC_THREADS, pl.smem, st>>>(map_a, map_b, p);
+  nnr_prof_end(ph, st);
   NNR_LAUNCH_CHECK("gemm_tc_kernel");
   if (pl.split_k) {
     size_t tot = (size_t)a->M * a->N;
+    void* ph2 = nnr_prof_begin(2, 0.0, st);
     tc_splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p.partial, a->K, a->k_dev, pl.kelem, pl.chain_kb, a->M,
                                                                           a->N, a->m_dev, p.epi);
+    nnr_prof_end(ph2, st);
     NNR_LAUNCH_CHECK("tc_splitk_reduce_kernel");
   }
   return 0;

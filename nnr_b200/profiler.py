@@ -10,12 +10,28 @@ Algorithmic work per call (SURVEY.md 8d / DESIGN.md "algorithmic work"):
   attn_pool_*        tokens * D * 4 * (reads+writes) bytes
 """
 import contextlib
+import ctypes
 import json
 import os
 
 import torch
 
-from . import ops
+from . import _lib, ops
+
+_KERNEL_TAGS = ['gemm_tc_kernel', 'tc_split_kernel', 'tc_splitk_reduce_kernel', 'gemm_simt_kernel']
+
+
+def _tc_class(M, N, K, transA, transB, m_dev, k_dev):
+    """mirror of nnr_gemm_tc_supported (gemm_tc.cu): which nnr_gemm calls run on the tcgen05 kernel"""
+    if os.environ.get('NNR_GEMM_ALGO') == 'simt' or os.environ.get('NNR_DISABLE_TC') == '1':
+        return False
+    if float(M) * N * K < 2.0e6 or K < 8:
+        return False
+    if m_dev is not None and transA:
+        return False
+    if k_dev is not None and not (transA and not transB):
+        return False
+    return True
 
 _TIMED = ['seq_prepare', 'embed_gather_fwd', 'embed_gather_bwd', 'gemm', 'colsum', 'segment_colsum', 'lstm_fwd',
           'lstm_bwd', 'lstm_shift_h', 'gate_bwd_pre', 'attn_pool_fwd', 'attn_pool_bwd', 'news_fuse_fwd', 'news_fuse_bwd',
@@ -37,8 +53,9 @@ class Capture:
         if name == 'gemm':
             A, B, C, M, N, K = args[:6]
             m_dev, k_dev = kw.get('m_dev'), kw.get('k_dev')
+            tc = _tc_class(M, N, K, args[9], args[10], m_dev, k_dev)
             return lambda: (2.0 * (min(M, _dev_int(m_dev)) if m_dev is not None else M) * N *
-                            (min(K, _dev_int(k_dev)) if k_dev is not None else K), None)
+                            (min(K, _dev_int(k_dev)) if k_dev is not None else K), None, tc)
         if name in ('lstm_fwd', 'lstm_bwd'):
             if name == 'lstm_fwd':
                 off, N, H = args[3], args[5], args[7]
@@ -74,9 +91,16 @@ class Capture:
         torch.cuda.synchronize()
         agg = {}
         self.detail = {}
+        tc_flops = simt_flops = 0.0
         for name, e0, e1, work, label in self.records:
             ms = e0.elapsed_time(e1)
-            fl, by = work()
+            w = work()
+            fl, by = w[0], w[1]
+            if name == 'gemm':
+                if w[2]:
+                    tc_flops += fl
+                else:
+                    simt_flops += fl
             for key, table in ((name, agg), (label, self.detail)):
                 a = table.setdefault(key, {'ms': 0.0, 'calls': 0, 'flops': 0.0, 'bytes': 0.0})
                 a['ms'] += ms
@@ -86,8 +110,18 @@ class Capture:
         self.detail = {k: {'ms': round(a['ms'] / steps, 3), 'calls': a['calls'] / steps,
                            'tflops': round(a['flops'] / max(a['ms'], 1e-9) / 1e9, 1)}
                        for k, a in sorted(self.detail.items(), key=lambda kv: -kv[1]['ms']) if k.startswith('gemm[')}
+        # kernel-level times of the composite gemm op (events recorded inside the library around each kernel)
+        buf = (ctypes.c_double * (3 * len(_KERNEL_TAGS)))()
+        _lib.lib.nnr_profile_read(buf, len(_KERNEL_TAGS))
+        if 'gemm' in agg:
+            agg['gemm (op total: split + main + reduce)'] = agg.pop('gemm')
+            agg['gemm (op total: split + main + reduce)']['flops'] = 0.0
+        for i, tag in enumerate(_KERNEL_TAGS):
+            if buf[3 * i + 1] > 0:
+                agg[tag] = {'ms': buf[3 * i], 'calls': buf[3 * i + 1], 'bytes': 0.0,
+                            'flops': tc_flops if tag == 'gemm_tc_kernel' else (simt_flops if tag == 'gemm_simt_kernel' else 0.0)}
         out = {}
-        for k, a in sorted(agg.items(), key=lambda kv: -kv[1]['ms']):
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1]['ms'] if not kv[0].startswith('gemm (op') else 1.0):
             out[k] = {'ms': a['ms'] / steps, 'calls': a['calls'] / steps}
             if a['flops']:
                 out[k]['tflops'] = a['flops'] / (a['ms'] * 1e-3) / 1e12
@@ -99,6 +133,7 @@ class Capture:
 @contextlib.contextmanager
 def capture():
     cap = Capture()
+    _lib.lib.nnr_profile_enable(1)
     saved = {}
     for name in _TIMED:
         saved[name] = getattr(ops, name)
@@ -106,6 +141,7 @@ def capture():
     try:
         yield cap
     finally:
+        _lib.lib.nnr_profile_enable(0)
         for name, fn in saved.items():
             setattr(ops, name, fn)
 
@@ -125,7 +161,7 @@ def roofline(breakdown, tokens_per_step, batch, root):
         return None
     name, top = next(iter(breakdown.items()))
     peaks = measured_peaks(root)
-    total = sum(v['ms'] for v in breakdown.values())
+    total = sum(v['ms'] for k, v in breakdown.items() if k not in _KERNEL_TAGS)
     if 'tflops' in top:
         # fp32-parity math on the tensor pipe is kind::tf32 = half the bf16 rate; algorithmic flops
         peak = peaks['bf16_tflops'] / 2.0
