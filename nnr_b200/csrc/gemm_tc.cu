@@ -34,7 +34,7 @@
 #define TC_THREADS 192
 #define TC_TMEM_COLS 512
 #define TC_ACC_COLS 256
-#define TC_SMEM_BUDGET (200 * 1024)
+#define TC_SMEM_BUDGET (221 * 1024)
 #define TC_CHAIN_K 1024      // max contraction length accumulated in TMEM before an fp32 combine (split-K GEMMs)
 
 // ------------------------------------------------------------------------------------------------
@@ -482,12 +482,15 @@ struct TcPlan {
   size_t a_plane, b_plane, a_off, b_off, partial_off, total, smem;
 };
 
-static int pick_block_n(int N, int step) {
+static int pick_block_n(int N, int step, int nplanes) {
   int best = step;
   double best_cost = 1e30;
   for (int bn = 256; bn >= 32; bn -= step) {
     double padded = (double)((N + bn - 1) / bn) * bn;
     double cost = padded * (1.0 + 40.0 / bn);
+    // a two-stage ring cannot hide the TMA latency behind one stage of MMAs: prefer tiles that leave room for three
+    size_t stage = (size_t)nplanes * ((size_t)TC_BM * 128 + (size_t)bn * 128);
+    if (TC_SMEM_BUDGET / stage < 3) cost *= 1.15;
     if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
   }
   return best;
@@ -505,7 +508,7 @@ static TcPlan make_plan(const nnr_gemm_args* a, bool bf16) {
   const size_t pad = bf16 ? 8 : 4;             // 16-byte row pitch
   pl.a_cp = (int)up((size_t)pl.a_cols, pad);
   pl.b_cp = (int)up((size_t)pl.b_cols, pad);
-  pl.block_n = pick_block_n(a->N, pl.b_mn ? pl.kelem : 16);
+  pl.block_n = pick_block_n(a->N, pl.b_mn ? pl.kelem : 16, pl.nplanes);
   long tiles = (long)((a->M + TC_BM - 1) / TC_BM) * ((a->N + pl.block_n - 1) / pl.block_n);
   // split-K: (a) fill the machine when the output grid is small, (b) bound the TMEM accumulation chain
   int nkb_cap = (a->K + pl.kelem - 1) / pl.kelem;

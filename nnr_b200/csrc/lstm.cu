@@ -15,7 +15,9 @@
 //   * backward step (32-row tiles): each CTA turns dh_t (+ recurrent part) into d(pre-activations) for its
 //     own units, multiplies them with its W slice to get a PARTIAL dh_{t-1} over all H units, and
 //     reduce-scatters the partials to the owning CTAs through DSMEM (fixed summation order ->
-//     deterministic).  Same A/B barrier protocol.
+//     deterministic).
+//   * the per-step exchange uses st.async into the peers' shared memory with mbarrier transaction counts
+//     (and, in BPTT, a "recv is free" barrier fed by remote arrives) - no barrier.cluster inside the time loop.
 //   * variable lengths: rows are tiled in length-sorted order; a row is active for its own `len` steps only
 //     (packed-sequence semantics); the reverse direction walks t = len-1 .. 0.
 //   * the input projection gx (a dense GEMM) is computed outside (nnr_gemm); the activated gates
@@ -41,6 +43,44 @@ struct LCfg {
 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// ---- DSMEM producer/consumer primitives: st.async + mbarrier complete_tx instead of barrier.cluster.
+// (barrier.cluster.arrive.release compiles to MEMBAR.ALL.GPU, which makes every step wait for the drain of the
+//  stash stores to global memory; the transaction barrier orders exactly the shared::cluster bytes we exchange.)
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void lbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void lbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LW_LOOP:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LW_DONE;\n"
+      "bra LW_LOOP;\n"
+      "LW_DONE:\n"
+      "}\n" ::"r"(smem_addr_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void rbar_arrive_release(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void st_async_f4(uint32_t remote_addr, float4 v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_addr),
+               "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)),
+               "r"(remote_bar)
+               : "memory");
+}
 
 // gate non-linearities on the SFU (ex2 + rcp): absolute error ~1e-7, far inside the 1e-4 parity budget
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -82,9 +122,19 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
       Wt[(size_t)k * COLS + c] = W[(size_t)(g * HID + rank * UPC + j) * HID + k];
     }
   }
-  float* remote_hT[CL];
+  __shared__ __align__(8) uint64_t hfull[2];        // "all of h for the next step has landed in buffer b"
+  uint32_t remote_hT[CL], remote_bar[CL];
 #pragma unroll
-  for (int d = 0; d < CL; ++d) remote_hT[d] = cluster.map_shared_rank(hT, d);
+  for (int d = 0; d < CL; ++d) {
+    remote_hT[d] = mapa_u32(smem_addr_u32(hT), d);
+    remote_bar[d] = mapa_u32(smem_addr_u32(&hfull[0]), d);
+  }
+  if (tid == 0) {
+    lbar_init(&hfull[0], 1);
+    lbar_init(&hfull[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t hph[2] = {0u, 0u};                       // phase parity per buffer (identical in every thread)
 
   const size_t GS = (size_t)2 * 4 * HID;  // gx row stride (both directions)
   // dynamic tile scheduling: tiles are sorted longest-first, so handing the next tile to whichever cluster
@@ -146,27 +196,37 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
 
     for (int s = 0; s < maxlen; ++s) {
       const int cur = s & 1, nxt = cur ^ 1;
+      if (tid == 0 && s + 1 < maxlen) lbar_expect_tx(&hfull[nxt], (uint32_t)(HID * MT * sizeof(float)));  // arm for h_{s+1}
+      if (s > 0) { lbar_wait_cluster(&hfull[cur], hph[cur]); hph[cur] ^= 1u; }                          // h_s landed
       if (worker) {
-        float acc[4][2][4];
+        // accumulators as packed pairs (unit j0, unit j0+1): one FFMA2 (fma.rn.f32x2) per gate and row
+        float2 acc2[4][4];
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { acc[g][0][i] = gxr[g][i].x; acc[g][1][i] = gxr[g][i].y; }
+          for (int i = 0; i < 4; ++i) acc2[g][i] = gxr[g][i];
         if (s + 1 < maxlen) load_gx(s + 1);   // in flight during the k loop
         const float* hb = hT + (size_t)cur * HID * MT + 4 * rg;
         const float* wb = Wt + j0;
 #pragma unroll 4
         for (int k = 0; k < HID; ++k) {
-          float4 hv = *reinterpret_cast<const float4*>(hb + (size_t)k * MT);
+          const float4 hv = *reinterpret_cast<const float4*>(hb + (size_t)k * MT);
+          const float2 h0 = make_float2(hv.x, hv.x), h1 = make_float2(hv.y, hv.y);
+          const float2 h2 = make_float2(hv.z, hv.z), h3 = make_float2(hv.w, hv.w);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            float2 w = *reinterpret_cast<const float2*>(wb + (size_t)k * COLS + g * UPC);
-            acc[g][0][0] = fmaf(w.x, hv.x, acc[g][0][0]); acc[g][0][1] = fmaf(w.x, hv.y, acc[g][0][1]);
-            acc[g][0][2] = fmaf(w.x, hv.z, acc[g][0][2]); acc[g][0][3] = fmaf(w.x, hv.w, acc[g][0][3]);
-            acc[g][1][0] = fmaf(w.y, hv.x, acc[g][1][0]); acc[g][1][1] = fmaf(w.y, hv.y, acc[g][1][1]);
-            acc[g][1][2] = fmaf(w.y, hv.z, acc[g][1][2]); acc[g][1][3] = fmaf(w.y, hv.w, acc[g][1][3]);
+            const float2 w = *reinterpret_cast<const float2*>(wb + (size_t)k * COLS + g * UPC);
+            acc2[g][0] = __ffma2_rn(w, h0, acc2[g][0]);
+            acc2[g][1] = __ffma2_rn(w, h1, acc2[g][1]);
+            acc2[g][2] = __ffma2_rn(w, h2, acc2[g][2]);
+            acc2[g][3] = __ffma2_rn(w, h3, acc2[g][3]);
           }
         }
+        float acc[4][2][4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { acc[g][0][i] = acc2[g][i].x; acc[g][1][i] = acc2[g][i].y; }
         // gates, state update, stash
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -195,18 +255,20 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
                   make_float2(cst[0][i], cst[1][i]);
           }
         }
-        // broadcast the new h slice to every CTA of the cluster (frozen rows re-send their state)
-        float4 h0 = make_float4(hst[0][0], hst[0][1], hst[0][2], hst[0][3]);
-        float4 h1 = make_float4(hst[1][0], hst[1][1], hst[1][2], hst[1][3]);
+        // send the new h slice into every CTA's next buffer (frozen rows re-send their state); the bytes are
+        // counted on the receiver's transaction barrier.  Double buffering + the data dependency of the
+        // recurrence make the write-after-read safe without a second barrier.
+        if (s + 1 < maxlen) {
+          float4 h0 = make_float4(hst[0][0], hst[0][1], hst[0][2], hst[0][3]);
+          float4 h1 = make_float4(hst[1][0], hst[1][1], hst[1][2], hst[1][3]);
+          const uint32_t o = (uint32_t)(((size_t)nxt * HID * MT + (size_t)unit0 * MT + 4 * rg) * sizeof(float));
 #pragma unroll
-        for (int d = 0; d < CL; ++d) {
-          float* dst = remote_hT[d] + (size_t)nxt * HID * MT + (size_t)unit0 * MT + 4 * rg;
-          *reinterpret_cast<float4*>(dst) = h0;
-          *reinterpret_cast<float4*>(dst + MT) = h1;
+          for (int d = 0; d < CL; ++d) {
+            st_async_f4(remote_hT[d] + o, h0, remote_bar[d] + nxt * 8);
+            st_async_f4(remote_hT[d] + o + MT * sizeof(float), h1, remote_bar[d] + nxt * 8);
+          }
         }
       }
-      cluster_arrive();
-      cluster_wait();
     }
   }
   // no CTA may exit while a peer can still write into its shared memory
@@ -254,9 +316,24 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, co
       Wc[idx] = W[(size_t)(g * HID + rank * UPC + jj) * HID + k];
     }
   }
-  float* remote_recv[CL];
+  // rfull: the CL partial slices of dh for the next iteration have landed in my recv (transaction barrier)
+  // rfree: every CTA of the cluster has finished reading ITS recv, so mine may send (CL arrivals)
+  __shared__ __align__(8) uint64_t rbar[2];
+  uint64_t* rfull = &rbar[0];
+  uint64_t* rfree = &rbar[1];
+  uint32_t remote_recv[CL], remote_rfull[CL], remote_rfree[CL];
 #pragma unroll
-  for (int d = 0; d < CL; ++d) remote_recv[d] = cluster.map_shared_rank(recv, d);
+  for (int d = 0; d < CL; ++d) {
+    remote_recv[d] = mapa_u32(smem_addr_u32(recv), d);
+    remote_rfull[d] = mapa_u32(smem_addr_u32(rfull), d);
+    remote_rfree[d] = mapa_u32(smem_addr_u32(rfree), d);
+  }
+  if (tid == 0) {
+    lbar_init(rfull, 1);
+    lbar_init(rfree, CL);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t ph_full = 0u, ph_free = 0u;
 
   const size_t GS = (size_t)2 * 4 * HID;
   // dynamic tile scheduling: tiles are sorted longest-first, so handing the next tile to whichever cluster
@@ -296,9 +373,8 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, co
       rrow[i] = worker ? s_row[4 * rg + i] : -1;
       dcc[i] = 0.f;
     }
-    cluster_arrive();   // pairs with the first "wait B" below
     for (int s = maxlen - 1; s >= 0; --s) {
-      cluster_wait();   // B: partials of the previous iteration have landed in recv
+      if (s < maxlen - 1) { lbar_wait_cluster(rfull, ph_full); ph_full ^= 1u; }   // partials of iteration s+1 landed
       if (worker) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -341,43 +417,49 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, co
           for (int g = 0; g < 4; ++g) dzT[(size_t)(g * UPC + j) * MT + 4 * rg + i] = dz[g];
         }
       }
-      cluster_arrive();   // A: this CTA no longer reads recv
-      __syncthreads();    // dzT complete
+      __syncthreads();    // dzT complete; every thread of this CTA has consumed its recv values
+      if (tid == 0 && s > 0) {
+        lbar_expect_tx(rfull, (uint32_t)(CL * UPC * MT * sizeof(float)));           // arm for the partials of iteration s
+#pragma unroll
+        for (int d = 0; d < CL; ++d) rbar_arrive_release(remote_rfree[d]);           // "my recv may be overwritten"
+      }
       float acc[4][4];
       if (worker2 && s > 0) {
+        // packed pairs over rows (0,1) and (2,3): one FFMA2 per k and row pair
+        float2 a2[4][2];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) acc[a][i] = 0.f;
+        for (int a = 0; a < 4; ++a) { a2[a][0] = make_float2(0.f, 0.f); a2[a][1] = make_float2(0.f, 0.f); }
         const float* wb = Wc + 4 * kg;
         const float* zb = dzT + 4 * rg2;
 #pragma unroll 8
         for (int c = 0; c < COLS; ++c) {
-          float4 z = *reinterpret_cast<const float4*>(zb + (size_t)c * MT);
-          float4 w = *reinterpret_cast<const float4*>(wb + (size_t)c * HID);
-          acc[0][0] = fmaf(w.x, z.x, acc[0][0]); acc[0][1] = fmaf(w.x, z.y, acc[0][1]);
-          acc[0][2] = fmaf(w.x, z.z, acc[0][2]); acc[0][3] = fmaf(w.x, z.w, acc[0][3]);
-          acc[1][0] = fmaf(w.y, z.x, acc[1][0]); acc[1][1] = fmaf(w.y, z.y, acc[1][1]);
-          acc[1][2] = fmaf(w.y, z.z, acc[1][2]); acc[1][3] = fmaf(w.y, z.w, acc[1][3]);
-          acc[2][0] = fmaf(w.z, z.x, acc[2][0]); acc[2][1] = fmaf(w.z, z.y, acc[2][1]);
-          acc[2][2] = fmaf(w.z, z.z, acc[2][2]); acc[2][3] = fmaf(w.z, z.w, acc[2][3]);
-          acc[3][0] = fmaf(w.w, z.x, acc[3][0]); acc[3][1] = fmaf(w.w, z.y, acc[3][1]);
-          acc[3][2] = fmaf(w.w, z.z, acc[3][2]); acc[3][3] = fmaf(w.w, z.w, acc[3][3]);
+          const float4 z = *reinterpret_cast<const float4*>(zb + (size_t)c * MT);
+          const float4 w = *reinterpret_cast<const float4*>(wb + (size_t)c * HID);
+          const float2 z01 = make_float2(z.x, z.y), z23 = make_float2(z.z, z.w);
+          const float2 w0 = make_float2(w.x, w.x), w1 = make_float2(w.y, w.y), w2 = make_float2(w.z, w.z), w3 = make_float2(w.w, w.w);
+          a2[0][0] = __ffma2_rn(w0, z01, a2[0][0]); a2[0][1] = __ffma2_rn(w0, z23, a2[0][1]);
+          a2[1][0] = __ffma2_rn(w1, z01, a2[1][0]); a2[1][1] = __ffma2_rn(w1, z23, a2[1][1]);
+          a2[2][0] = __ffma2_rn(w2, z01, a2[2][0]); a2[2][1] = __ffma2_rn(w2, z23, a2[2][1]);
+          a2[3][0] = __ffma2_rn(w3, z01, a2[3][0]); a2[3][1] = __ffma2_rn(w3, z23, a2[3][1]);
         }
-      }
-      cluster_wait();     // A: every CTA has finished reading its recv -> safe to overwrite
-      if (worker2 && s > 0) {
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          int k = 4 * kg + a;
-          int owner = k / UPC, kl = k - owner * UPC;
-          float* dst = remote_recv[owner] + ((size_t)rank * UPC + kl) * MT + 4 * rg2;
-          *reinterpret_cast<float4*>(dst) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+        for (int a = 0; a < 4; ++a) { acc[a][0] = a2[a][0].x; acc[a][1] = a2[a][0].y; acc[a][2] = a2[a][1].x; acc[a][3] = a2[a][1].y; }
+      }
+      if (s > 0) {
+        lbar_wait_cluster(rfree, ph_free);   // every CTA has finished reading its recv -> safe to overwrite
+        ph_free ^= 1u;
+        if (worker2) {
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            int k = 4 * kg + a;
+            int owner = k / UPC, kl = k - owner * UPC;
+            const uint32_t o = (uint32_t)((((size_t)rank * UPC + kl) * MT + 4 * rg2) * sizeof(float));
+            st_async_f4(remote_recv[owner] + o, make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]), remote_rfull[owner]);
+          }
         }
       }
-      cluster_arrive();   // B
+      __syncthreads();    // dzT is rewritten by the next iteration's phase 1
     }
-    cluster_wait();       // balance the last "arrive B" (or the initial one when maxlen == 0)
   }
   cluster_arrive();
   cluster_wait();
