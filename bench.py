@@ -233,17 +233,23 @@ def main():
     # ---- per-op breakdown with CUDA events (dominant kernel -> roofline) ---------------------------
     roofline = None
     breakdown = None
-    if not a.no_profile and rank == 0:
+    if not a.no_profile:
+        # every rank runs the two extra steps (they contain the gradient all-reduce); only rank 0 records events
         from nnr_b200 import profiler
-        with profiler.capture() as prof:
+        if rank == 0:
+            with profiler.capture() as prof:
+                for i in range(2):
+                    ts.step(*fresh(devb[i % nb]))
+                torch.cuda.synchronize()
+            breakdown = prof.summary(steps=2)
+            if a.gemm_detail:
+                for k, v in prof.detail.items():
+                    print('%-44s %8.3f ms  %4.1f calls  %7.1f TFLOP/s' % (k, v['ms'], v['calls'], v['tflops']), file=sys.stderr)
+            roofline = profiler.roofline(breakdown, tokens_per_step=tok, batch=a.batch, root=ROOT)
+        else:
             for i in range(2):
                 ts.step(*fresh(devb[i % nb]))
             torch.cuda.synchronize()
-        breakdown = prof.summary(steps=2)
-        if a.gemm_detail:
-            for k, v in prof.detail.items():
-                print('%-44s %8.3f ms  %4.1f calls  %7.1f TFLOP/s' % (k, v['ms'], v['calls'], v['tflops']), file=sys.stderr)
-        roofline = profiler.roofline(breakdown, tokens_per_step=tok, batch=a.batch, root=ROOT)
     if world > 1:
         dist.barrier()
     if rank != 0:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NNR_ABI_VERSION 1
+#define NNR_ABI_VERSION 2
 
 const char* nnr_last_error(void);
 int nnr_abi_version(void);
@@ -91,10 +91,25 @@ typedef struct {
   const float* rowbias; int64_t ldrowbias; const int32_t* rowmap;
   float p_drop; uint64_t seed;
   int32_t algo;
-  void* workspace; size_t workspace_bytes;   /* split-K partials (see nnr_gemm_workspace_bytes) */
+  void* workspace; size_t workspace_bytes;   /* operand planes + split-K partials (see nnr_gemm_workspace_bytes) */
+  /* optional: operands already split by nnr_tc_split (tensor-core backend only; A/B must still be given).
+   * X_planes points at the first plane of the (possibly column-sliced) stored matrix, pitch in elements,
+   * plane_rows = rows of the full planes (plane stride = plane_rows * pitch). */
+  const void* A_planes; int64_t a_planes_pitch; int64_t a_planes_rows;
+  const void* B_planes; int64_t b_planes_pitch; int64_t b_planes_rows;
 } nnr_gemm_args;
 size_t nnr_gemm_workspace_bytes(const nnr_gemm_args* args);
 int nnr_gemm(const nnr_gemm_args* args, void* stream);
+/* Split a row-major fp32 matrix X[R,C] (ld) into the operand planes of the tensor-core backend so that several
+ * GEMMs can share them: 3xTF32 -> fp32 [hi|lo][R][pitch], BF16 -> bf16 [1][R][pitch]; pitch = C rounded up to 16
+ * bytes.  With r_dev, rows [*r_dev, round_up(*r_dev, 64)) are zero-filled (contraction tail) and later rows
+ * are left untouched.  algo = NNR_GEMM_TC_TF32X3 or NNR_GEMM_TC_BF16 (NNR_GEMM_AUTO = the library default). */
+int64_t nnr_tc_split_pitch(int C, int algo);
+size_t nnr_tc_split_bytes(int R, int C, int algo);
+int nnr_tc_split(const float* X, int64_t ld, int R, int C, const int32_t* r_dev, int algo, void* planes,
+                 size_t planes_bytes, void* stream);
+/* the algorithm NNR_GEMM_AUTO resolves to (env NNR_GEMM_ALGO = simt | tf32x3 | bf16; default tf32x3) */
+int nnr_gemm_default_algo(void);
 
 /* column sums: out[n] (+)= sum_m X[m,n]   (bias gradients; deterministic two-stage)            */
 size_t nnr_colsum_workspace_bytes(int M, int N);

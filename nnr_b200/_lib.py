@@ -31,7 +31,9 @@ class GemmArgs(C.Structure):
                 ('rowbias', vp), ('ldrowbias', i64), ('rowmap', vp),
                 ('p_drop', f32), ('seed', u64),
                 ('algo', i32),
-                ('workspace', vp), ('workspace_bytes', sz)]
+                ('workspace', vp), ('workspace_bytes', sz),
+                ('A_planes', vp), ('a_planes_pitch', i64), ('a_planes_rows', i64),
+                ('B_planes', vp), ('b_planes_pitch', i64), ('b_planes_rows', i64)]
 
 
 class PoolArgs(C.Structure):
@@ -63,6 +65,10 @@ SIGNATURES = {
     'nnr_embed_gather_bwd': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, u64, vp, C.c_int, vp, sz, vp]),
     'nnr_gemm_workspace_bytes': (sz, [C.POINTER(GemmArgs)]),
     'nnr_gemm': (C.c_int, [C.POINTER(GemmArgs), vp]),
+    'nnr_tc_split_pitch': (i64, [C.c_int, C.c_int]),
+    'nnr_tc_split_bytes': (sz, [C.c_int, C.c_int, C.c_int]),
+    'nnr_tc_split': (C.c_int, [vp, i64, C.c_int, C.c_int, vp, C.c_int, vp, sz, vp]),
+    'nnr_gemm_default_algo': (C.c_int, []),
     'nnr_colsum_workspace_bytes': (sz, [C.c_int, C.c_int]),
     'nnr_colsum': (C.c_int, [vp, i64, C.c_int, C.c_int, vp, vp, C.c_int, vp, sz, vp]),
     'nnr_segment_colsum': (C.c_int, [vp, i64, vp, C.c_int, C.c_int, vp, i64, vp]),

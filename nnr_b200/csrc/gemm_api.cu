@@ -10,6 +10,7 @@ int nnr_gemm_tc_supported(const nnr_gemm_args* a);
 size_t nnr_gemm_tc_workspace_bytes(const nnr_gemm_args* a);
 int nnr_gemm_tc(const nnr_gemm_args* a, void* stream);
 
+extern "C" int nnr_gemm_default_algo(void);
 static int default_algo() {
   static int algo = -1;
   if (algo < 0) {
@@ -48,10 +49,14 @@ static int validate(const nnr_gemm_args* a) {
   return 0;
 }
 
+extern "C" int nnr_gemm_default_algo(void) { return default_algo(); }
+
 extern "C" size_t nnr_gemm_workspace_bytes(const nnr_gemm_args* a) {
   if (!a || a->M <= 0 || a->N <= 0 || a->K <= 0) return 0;
   size_t s = nnr_gemm_simt_workspace_bytes(a);
-  size_t t = nnr_gemm_tc_supported(a) ? nnr_gemm_tc_workspace_bytes(a) : 0;
+  nnr_gemm_args b = *a;
+  b.algo = pick_algo(a);
+  size_t t = (b.algo != NNR_GEMM_SIMT_FP32 && nnr_gemm_tc_supported(a)) ? nnr_gemm_tc_workspace_bytes(&b) : 0;
   return s > t ? s : t;
 }
 

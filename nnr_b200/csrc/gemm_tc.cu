@@ -532,8 +532,8 @@ static TcPlan make_plan(const nnr_gemm_args* a, bool bf16) {
   pl.a_plane = (size_t)pl.a_rows * pl.a_cp;
   pl.b_plane = (size_t)pl.b_rows * pl.b_cp;
   size_t o = 0;
-  pl.a_off = o; o = up(o + pl.a_plane * esz * pl.nplanes, 1024);
-  pl.b_off = o; o = up(o + pl.b_plane * esz * pl.nplanes, 1024);
+  pl.a_off = o; if (!a->A_planes) o = up(o + pl.a_plane * esz * pl.nplanes, 1024);
+  pl.b_off = o; if (!a->B_planes) o = up(o + pl.b_plane * esz * pl.nplanes, 1024);
   pl.partial_off = o;
   if (pl.split_k) o = up(o + (size_t)pl.max_splits * a->M * a->N * sizeof(float), 1024);
   pl.total = o;
@@ -556,13 +556,14 @@ int nnr_gemm_tc_supported(const nnr_gemm_args* a) {
 
 size_t nnr_gemm_tc_workspace_bytes(const nnr_gemm_args* a) { return make_plan(a, a->algo == NNR_GEMM_TC_BF16).total; }
 
-static int encode_map(CUtensorMap* map, void* base, bool bf16, int cols_p, int rows, int nplanes, int box_c, int box_r, bool mn) {
-  cuuint64_t gdim[3] = {(cuuint64_t)cols_p, (cuuint64_t)rows, (cuuint64_t)nplanes};
+static int encode_map(CUtensorMap* map, const void* base, bool bf16, int cols, int64_t pitch, int rows, int64_t plane_rows,
+                      int nplanes, int box_c, int box_r, bool mn) {
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)nplanes};
   const size_t esz = bf16 ? 2 : 4;
-  cuuint64_t gstr[2] = {(cuuint64_t)cols_p * esz, (cuuint64_t)cols_p * esz * (cuuint64_t)rows};
+  cuuint64_t gstr[2] = {(cuuint64_t)pitch * esz, (cuuint64_t)pitch * esz * (cuuint64_t)plane_rows};
   cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_r, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = get_encode()(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, gdim, gstr,
+  CUresult r = get_encode()(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr,
                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             (mn && !bf16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -588,23 +589,36 @@ static int split_operand(const float* X, int64_t ld, int R, int C, int Cp, const
 template <bool BF16>
 static int run_tc(const nnr_gemm_args* a, cudaStream_t st) {
   TcPlan pl = make_plan(a, BF16);
-  NNR_REQUIRE(a->workspace && a->workspace_bytes >= pl.total, NNR_ERR_WORKSPACE, "nnr_gemm(tc): workspace %zu < %zu",
-              a->workspace_bytes, pl.total);
+  NNR_REQUIRE(pl.total == 0 || (a->workspace && a->workspace_bytes >= pl.total), NNR_ERR_WORKSPACE,
+              "nnr_gemm(tc): workspace %zu < %zu", a->workspace_bytes, pl.total);
   NNR_REQUIRE(nnr_aligned16(a->workspace), NNR_ERR_ALIGN, "nnr_gemm(tc): workspace must be 16B aligned");
+  NNR_REQUIRE(nnr_aligned16(a->A_planes) && nnr_aligned16(a->B_planes) && a->a_planes_pitch % (BF16 ? 8 : 4) == 0 &&
+                  a->b_planes_pitch % (BF16 ? 8 : 4) == 0,
+              NNR_ERR_ALIGN, "nnr_gemm(tc): operand planes must be 16B aligned with a 16B pitch");
   NNR_REQUIRE(pl.smem <= 227 * 1024, NNR_ERR_UNSUPPORTED, "nnr_gemm(tc): smem plan too large");
   char* ws = (char*)a->workspace;
-  void* pa = ws + pl.a_off;
-  void* pb = ws + pl.b_off;
+  const void* pa = a->A_planes;
+  const void* pb = a->B_planes;
+  int64_t a_pitch = a->a_planes_pitch, a_prow = a->a_planes_rows, b_pitch = a->b_planes_pitch, b_prow = a->b_planes_rows;
+  int rc;
   // rows of A are M (m_dev) when row-major, K (k_dev) when MN-major; rows of B are K (k_dev) when MN-major
-  int rc = split_operand<BF16>(a->A, a->lda, pl.a_rows, pl.a_cols, pl.a_cp, pl.a_mn ? a->k_dev : a->m_dev, pa, pl.a_plane, st);
-  if (rc) return rc;
-  rc = split_operand<BF16>(a->B, a->ldb, pl.b_rows, pl.b_cols, pl.b_cp, pl.b_mn ? a->k_dev : nullptr, pb, pl.b_plane, st);
-  if (rc) return rc;
+  if (!pa) {
+    void* w = ws + pl.a_off;
+    rc = split_operand<BF16>(a->A, a->lda, pl.a_rows, pl.a_cols, pl.a_cp, pl.a_mn ? a->k_dev : a->m_dev, w, pl.a_plane, st);
+    if (rc) return rc;
+    pa = w; a_pitch = pl.a_cp; a_prow = pl.a_rows;
+  }
+  if (!pb) {
+    void* w = ws + pl.b_off;
+    rc = split_operand<BF16>(a->B, a->ldb, pl.b_rows, pl.b_cols, pl.b_cp, pl.b_mn ? a->k_dev : nullptr, w, pl.b_plane, st);
+    if (rc) return rc;
+    pb = w; b_pitch = pl.b_cp; b_prow = pl.b_rows;
+  }
   CUtensorMap map_a, map_b;
   const int ke = pl.kelem;
-  rc = encode_map(&map_a, pa, BF16, pl.a_cp, pl.a_rows, pl.nplanes, ke, pl.a_mn ? ke : TC_BM, pl.a_mn != 0);
+  rc = encode_map(&map_a, pa, BF16, pl.a_cols, a_pitch, pl.a_rows, a_prow, pl.nplanes, ke, pl.a_mn ? ke : TC_BM, pl.a_mn != 0);
   if (rc) return rc;
-  rc = encode_map(&map_b, pb, BF16, pl.b_cp, pl.b_rows, pl.nplanes, ke, pl.b_mn ? ke : pl.block_n, pl.b_mn != 0);
+  rc = encode_map(&map_b, pb, BF16, pl.b_cols, b_pitch, pl.b_rows, b_prow, pl.nplanes, ke, pl.b_mn ? ke : pl.block_n, pl.b_mn != 0);
   if (rc) return rc;
   TcParams p;
   p.M = a->M; p.N = a->N; p.K = a->K; p.m_dev = a->m_dev; p.k_dev = a->k_dev;
@@ -649,4 +663,29 @@ int nnr_gemm_tc(const nnr_gemm_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (a->algo == NNR_GEMM_TC_BF16) return run_tc<true>(a, st);
   return run_tc<false>(a, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// public pre-split entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int nnr_gemm_default_algo(void);
+static bool split_is_bf16(int algo) {
+  if (algo == NNR_GEMM_AUTO) algo = nnr_gemm_default_algo();
+  return algo == NNR_GEMM_TC_BF16;
+}
+extern "C" int64_t nnr_tc_split_pitch(int C, int algo) { return (int64_t)up((size_t)C, split_is_bf16(algo) ? 8 : 4); }
+extern "C" size_t nnr_tc_split_bytes(int R, int C, int algo) {
+  if (R <= 0 || C <= 0) return 0;
+  bool bf = split_is_bf16(algo);
+  return (size_t)R * (size_t)nnr_tc_split_pitch(C, algo) * (bf ? 2 : 8);
+}
+extern "C" int nnr_tc_split(const float* X, int64_t ld, int R, int C, const int32_t* r_dev, int algo, void* planes,
+                            size_t planes_bytes, void* stream) {
+  NNR_REQUIRE(X && planes && R > 0 && C > 0 && ld >= C, NNR_ERR_ARG, "nnr_tc_split: bad arguments");
+  NNR_REQUIRE(planes_bytes >= nnr_tc_split_bytes(R, C, algo), NNR_ERR_WORKSPACE, "nnr_tc_split: planes buffer too small");
+  NNR_REQUIRE(nnr_aligned16(planes), NNR_ERR_ALIGN, "nnr_tc_split: planes must be 16B aligned");
+  bool bf = split_is_bf16(algo);
+  int Cp = (int)nnr_tc_split_pitch(C, algo);
+  if (bf) return split_operand<true>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (cudaStream_t)stream);
+  return split_operand<false>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (cudaStream_t)stream);
 }

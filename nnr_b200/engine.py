@@ -30,7 +30,7 @@ def _empty(shape, dev, dtype=torch.float32):
 # ------------------------------------------------------------------------------------------------
 # GEMM helpers (row-major; weights are nn.Linear layout [out, in])
 # ------------------------------------------------------------------------------------------------
-def linear(x, W, M, m_dev=None, bias=None, epilogue=None, out=None, **epi):
+def linear(x, W, M, m_dev=None, bias=None, epilogue=None, out=None, x_planes=None, **epi):
     """out[M,N] = epi(x[M,K] @ W[N,K]^T)"""
     N, K = W.shape
     if out is None:
@@ -38,26 +38,33 @@ def linear(x, W, M, m_dev=None, bias=None, epilogue=None, out=None, **epi):
     if epilogue is None:
         epilogue = EPI_BIAS if bias is not None else EPI_NONE
     ops.gemm(x, W, out, M, N, K, x.stride(0), W.stride(0), out.stride(0), False, True, epilogue, bias=bias,
-             m_dev=m_dev, **epi)
+             m_dev=m_dev, a_planes=x_planes, **epi)
     return out
 
 
-def matmul_nn(x, W, M, m_dev=None, out=None, **epi):
+def matmul_nn(x, W, M, m_dev=None, out=None, x_planes=None, **epi):
     """out[M,K] = x[M,N] @ W[N,K]   (dgrad of a Linear with weight W, or a fold K^T q)"""
     N, K = W.shape
     if out is None:
         out = _empty((M, K), x.device)
-    ops.gemm(x, W, out, M, K, N, x.stride(0), W.stride(0), out.stride(0), False, False, m_dev=m_dev, **epi)
+    ops.gemm(x, W, out, M, K, N, x.stride(0), W.stride(0), out.stride(0), False, False, m_dev=m_dev,
+             a_planes=x_planes, **epi)
     return out
 
 
-def wgrad(dy, x, M, N, K, k_dev=None, out=None, accumulate=False):
+def wgrad(dy, x, M, N, K, k_dev=None, out=None, accumulate=False, dy_planes=None, x_planes=None):
     """out[N,K] = dy[M,N]^T @ x[M,K]   (contraction over the M rows / tokens)"""
     if out is None:
         out = _empty((N, K), dy.device)
     ops.gemm(dy, x, out, N, K, M, dy.stride(0), x.stride(0), out.stride(0), True, False, k_dev=k_dev,
-             accumulate=accumulate)
+             accumulate=accumulate, a_planes=dy_planes, b_planes=x_planes)
     return out
+
+
+def split_tokens(x, cap, cols, ntok):
+    """hi/lo operand planes of a packed per-token tensor, shared by every GEMM that consumes it (forward,
+    dgrad and wgrad read the same row-major planes; the row tail beyond the token count is zero-filled)"""
+    return ops.tc_split(x, cap, cols, x.stride(0), ntok)
 
 
 def colsum(X, M, N, m_dev=None, out=None, accumulate=False):
@@ -123,7 +130,8 @@ def _cne_modality_forward(P, x, ids, mask_u8, N, L, E, Hd, training, p_drop, see
     m.w_hh = torch.stack([P[pre + 'weight_hh_l0'], P[pre + 'weight_hh_l0_reverse']], 0)        # [2, 4H, H]
     bias = torch.cat([P[pre + 'bias_ih_l0'] + P[pre + 'bias_hh_l0'],
                       P[pre + 'bias_ih_l0_reverse'] + P[pre + 'bias_hh_l0_reverse']], 0)       # [8H]
-    m.gates = linear(m.emb, m.w_ih, cap, m.ntok, bias)                                        # gx, then the stash
+    m.emb_pl = split_tokens(m.emb, cap, E, m.ntok)
+    m.gates = linear(m.emb, m.w_ih, cap, m.ntok, bias, x_planes=m.emb_pl)                      # gx, then the stash
     m.h = _empty((cap, 2 * Hd), dev)
     m.c_stash = _empty((cap, 2 * Hd), dev)
     m.c_n = _empty((N, 2 * Hd), dev)
@@ -139,10 +147,12 @@ def _cne_gate_self(P, x, m, m_other_cn, partner, N, Hd, A):
     m.cm_sel = m_other_cn.index_select(0, partner)                                            # [N, 2H]
     m.mproj = linear(m.cm_sel, P[x + '_M.weight'], N, None, P[x + '_M.bias'])                 # [N, 2H]
     m.g = _empty((m.cap, D2), dev)
+    m.h_pl = split_tokens(m.h, m.cap, D2, m.ntok)
     m.hg = linear(m.h, P[x + '_H.weight'], m.cap, m.ntok, None, EPI_GATE, rowbias=m.mproj, ldrowbias=D2,
-                  rowmap=m.tok_row, aux=m.h, ldaux=D2, aux_out=m.g, ldaux_out=D2)
+                  rowmap=m.tok_row, aux=m.h, ldaux=D2, aux_out=m.g, ldaux_out=D2, x_planes=m.h_pl)
     sa = x + '_self_attention.'
-    m.u = linear(m.hg, P[sa + 'affine1.weight'], m.cap, m.ntok, P[sa + 'affine1.bias'], EPI_BIAS_TANH)
+    m.hg_pl = split_tokens(m.hg, m.cap, D2, m.ntok)
+    m.u = linear(m.hg, P[sa + 'affine1.weight'], m.cap, m.ntok, P[sa + 'affine1.bias'], EPI_BIAS_TANH, x_planes=m.hg_pl)
     m.self_out = _empty((N, D2), dev)
     m.alpha_self = _empty((m.cap,), dev)
     ops.attn_pool_fwd(X=m.hg, ldx=D2, D=D2, S=N, max_len=m.L, mode=0, seg_off=m.off, U=m.u, ldu=A, A=A,
@@ -248,24 +258,29 @@ class CNEFunction(torch.autograd.Function):
                               w2=P[sa + 'affine2.weight'], alpha=m.alpha_self, dpooled=d_self[x], lddp=D2, dX=m.dhg,
                               lddx=D2, accumulate_dx=dhg_written[x], dU=dU, lddu=A, dw2_partial=dw2p)
             G[sa + 'affine2.weight'] = colsum(dw2p, N, A).view(1, A)
-            matmul_nn(dU, P[sa + 'affine1.weight'], m.cap, m.ntok, out=m.dhg, accumulate=True)
-            G[sa + 'affine1.weight'] = wgrad(dU, m.hg, m.cap, A, D2, k_dev=m.ntok)
+            dU_pl = split_tokens(dU, m.cap, A, m.ntok)
+            matmul_nn(dU, P[sa + 'affine1.weight'], m.cap, m.ntok, out=m.dhg, accumulate=True, x_planes=dU_pl)
+            G[sa + 'affine1.weight'] = wgrad(dU, m.hg, m.cap, A, D2, k_dev=m.ntok, dy_planes=dU_pl, x_planes=m.hg_pl)
             G[sa + 'affine1.bias'] = colsum(dU, m.cap, A, m.ntok)
-            del dU
+            del dU, dU_pl
+            m.hg_pl = None
         # 4. selective gate backward
         d_cm_sel = {}
         for x, m in mods.items():
             dz = _empty((m.cap, D2), dev)
             dh0 = _empty((m.cap, D2), dev)
             ops.gate_bwd_pre(m.dhg, m.h, m.g, m.cap * D2, m.ntok, D2, dz, dh0)
-            m.dh = matmul_nn(dz, P[x + '_H.weight'], m.cap, m.ntok, epilogue=EPI_ADD_AUX, aux=dh0, ldaux=D2, out=m.dhg)
-            G[x + '_H.weight'] = wgrad(dz, m.h, m.cap, D2, D2, k_dev=m.ntok)
+            dz_pl = split_tokens(dz, m.cap, D2, m.ntok)
+            m.dh = matmul_nn(dz, P[x + '_H.weight'], m.cap, m.ntok, epilogue=EPI_ADD_AUX, aux=dh0, ldaux=D2, out=m.dhg,
+                             x_planes=dz_pl)
+            G[x + '_H.weight'] = wgrad(dz, m.h, m.cap, D2, D2, k_dev=m.ntok, dy_planes=dz_pl, x_planes=m.h_pl)
+            m.h_pl = None
             dmproj = _empty((N, D2), dev)
             ops.segment_colsum(dz, D2, m.off, N, D2, dmproj, D2)
             G[x + '_M.weight'] = wgrad(dmproj, m.cm_sel, N, D2, D2)
             G[x + '_M.bias'] = colsum(dmproj, N, D2)
             d_cm_sel[x] = matmul_nn(dmproj, P[x + '_M.weight'], N)                            # grad of cn_other[partner]
-            del dz, dh0
+            del dz, dh0, dz_pl
         # partner_t and partner_c are inverse permutations of each other
         dcn = {'content': d_cm_sel['title'].index_select(0, c.partner),
                'title': d_cm_sel['content'].index_select(0, t.partner)}
@@ -278,16 +293,20 @@ class CNEFunction(torch.autograd.Function):
             dz = m.gates                                                                      # [cap, 8H] = dL/dgx
             hprev = _empty((m.cap, D2), dev)
             ops.lstm_shift_h(m.h, m.len, m.off, m.tok_row, N, m.L, Hd, hprev)
+            dz_pl = split_tokens(dz, m.cap, 8 * Hd, m.ntok)
             for d, sfx in enumerate(('', '_reverse')):
                 G[pre + 'weight_hh_l0' + sfx] = wgrad(dz[:, d * 4 * Hd:(d + 1) * 4 * Hd], hprev[:, d * Hd:(d + 1) * Hd],
-                                                     m.cap, 4 * Hd, Hd, k_dev=m.ntok)
-            dwih = wgrad(dz, m.emb, m.cap, 8 * Hd, E, k_dev=m.ntok)
+                                                     m.cap, 4 * Hd, Hd, k_dev=m.ntok,
+                                                     dy_planes=dz_pl.cols(d * 4 * Hd, (d + 1) * 4 * Hd) if dz_pl else None)
+            dwih = wgrad(dz, m.emb, m.cap, 8 * Hd, E, k_dev=m.ntok, dy_planes=dz_pl, x_planes=m.emb_pl)
+            m.emb_pl = None
             db = colsum(dz, m.cap, 8 * Hd, m.ntok)
             for d, sfx in enumerate(('', '_reverse')):
                 G[pre + 'weight_ih_l0' + sfx] = dwih[d * 4 * Hd:(d + 1) * 4 * Hd]
                 G[pre + 'bias_ih_l0' + sfx] = db[d * 4 * Hd:(d + 1) * 4 * Hd]
                 G[pre + 'bias_hh_l0' + sfx] = db[d * 4 * Hd:(d + 1) * 4 * Hd]
-            demb = matmul_nn(dz, m.w_ih, m.cap, m.ntok)
+            demb = matmul_nn(dz, m.w_ih, m.cap, m.ntok, x_planes=dz_pl)
+            del dz_pl
             ops.embed_gather_bwd(demb, m.ids, m.len, m.off, dtable, m.p, m.seed, not first)
             first = False
             del hprev, demb

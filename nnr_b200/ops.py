@@ -72,9 +72,41 @@ def embed_gather_bwd(dout, ids, len_, off, dtable, p_drop, seed, accumulate):
                                    ws.numel(), _stream()), 'nnr_embed_gather_bwd')
 
 
+class Planes:
+    """Operand planes of the tensor-core GEMM backend (nnr_tc_split): fp32 [hi|lo][rows][pitch] for 3xTF32,
+    bf16 [1][rows][pitch] for the bf16 variant.  ``cols(a, b)`` is a column-slice view (same planes)."""
+    __slots__ = ('buf', 'rows', 'ncols', 'pitch', 'esz', 'col_off')
+
+    def __init__(self, buf, rows, ncols, pitch, esz, col_off=0):
+        self.buf, self.rows, self.ncols, self.pitch, self.esz, self.col_off = buf, rows, ncols, pitch, esz, col_off
+
+    def ptr(self):
+        return self.buf.data_ptr() + self.col_off * self.esz
+
+    def cols(self, a, b):
+        return Planes(self.buf, self.rows, b - a, self.pitch, self.esz, self.col_off + a)
+
+
+def default_algo():
+    return int(lib.nnr_gemm_default_algo())
+
+
+def tc_split(x, rows, cols, ld, r_dev=None):
+    """pre-split a row-major [rows, cols] fp32 matrix once so several GEMMs can share the planes; returns None
+    when the exact-fp32 backend is selected (NNR_GEMM_ALGO=simt)"""
+    algo = default_algo()
+    if algo == ALGO_SIMT:
+        return None
+    nbytes = int(lib.nnr_tc_split_bytes(rows, cols, algo))
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    check(lib.nnr_tc_split(_p(x, _F32), ld, rows, cols, _p(r_dev, _I32), algo, buf.data_ptr(), nbytes, _stream()),
+          'nnr_tc_split')
+    return Planes(buf, rows, cols, int(lib.nnr_tc_split_pitch(cols, algo)), 2 if algo == ALGO_BF16 else 4)
+
+
 def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, transA, transB, epilogue=EPI_NONE, accumulate=False, bias=None,
          aux=None, ldaux=0, aux_out=None, ldaux_out=0, rowbias=None, ldrowbias=0, rowmap=None, m_dev=None,
-         k_dev=None, p_drop=0.0, seed=0, algo=ALGO_AUTO):
+         k_dev=None, p_drop=0.0, seed=0, algo=ALGO_AUTO, a_planes=None, b_planes=None):
     a = GemmArgs()
     a.A, a.lda, a.transA = _p(A, _F32), lda, int(transA)
     a.B, a.ldb, a.transB = _p(B, _F32), ldb, int(transB)
@@ -87,6 +119,10 @@ def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, transA, transB, epilogue=EPI_NONE, 
     a.aux_out, a.ldaux_out = _p(aux_out, _F32), ldaux_out
     a.rowbias, a.ldrowbias, a.rowmap = _p(rowbias, _F32), ldrowbias, _p(rowmap, _I32)
     a.p_drop, a.seed, a.algo = float(p_drop), int(seed), algo
+    if a_planes is not None and algo == ALGO_AUTO:
+        a.A_planes, a.a_planes_pitch, a.a_planes_rows = a_planes.ptr(), a_planes.pitch, a_planes.rows
+    if b_planes is not None and algo == ALGO_AUTO:
+        a.B_planes, a.b_planes_pitch, a.b_planes_rows = b_planes.ptr(), b_planes.pitch, b_planes.rows
     nbytes = lib.nnr_gemm_workspace_bytes(C.byref(a))
     if nbytes:
         ws = workspace(nbytes, A.device, 'gemm')

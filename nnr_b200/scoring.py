@@ -1,0 +1,62 @@
+"""Cached-corpus dev/test scoring (BASELINE config 3).
+
+The reference's ``util.compute_scores`` re-encodes the user's 50 history news for every (impression,
+candidate) pair (util.py:19-50, README.md:125).  Here the news corpus is encoded ONCE with the CNE kernels
+and kept resident in HBM as a [news_num, 900] table; an impression is then just 50 history ids + n candidate
+ids: the history graph / category mask / cluster indices are built on the device from the cached category ids
+(``nnr_sue_graph_build``, bit-exact with MIND_corpus.py:178-213), followed by SUE and the dot product.
+
+Parity note (SURVEY finding 2): a news vector depends on the composition of the ``news_encoder`` call it is
+encoded in (sort-rank pairing of the selective gate).  The cache is therefore defined per corpus chunk: news
+[c*chunk, (c+1)*chunk) are encoded as ONE call of shape [1, chunk]; the oracle test encodes the same chunks.
+"""
+import torch
+
+from . import engine, ops
+
+
+class CorpusScorer:
+    def __init__(self, model, news_title_text, news_title_mask, news_content_text, news_content_mask, news_category,
+                 news_subCategory, chunk=4096):
+        self.model = model
+        self.dev = next(model.parameters()).device
+        to = lambda t: torch.as_tensor(t).to(self.dev)
+        self.tt, self.tm, self.ct, self.cm = to(news_title_text), to(news_title_mask).clone(), to(news_content_text), to(news_content_mask).clone()
+        self.cat, self.sub = to(news_category).to(torch.int32), to(news_subCategory).to(torch.int32)
+        self.chunk = chunk
+        self.cache = None
+
+    @torch.no_grad()
+    def encode_corpus(self):
+        """news table -> [news_num, news_embedding_dim] fp32 cache; returns it"""
+        self.model.eval()
+        enc = self.model.news_encoder
+        n = self.tt.shape[0]
+        out = torch.empty(n, enc.news_embedding_dim, device=self.dev)
+        for a in range(0, n, self.chunk):
+            b = min(n, a + self.chunk)
+            rep = enc(self.tt[a:b].unsqueeze(0), self.tm[a:b].unsqueeze(0), None, self.ct[a:b].unsqueeze(0),
+                      self.cm[a:b].unsqueeze(0), None, self.cat[a:b].unsqueeze(0), self.sub[a:b].unsqueeze(0), None)
+            out[a:b] = rep[0]
+        self.cache = out
+        return out
+
+    @torch.no_grad()
+    def score(self, history_ids, history_len, candidate_ids):
+        """history_ids [B,H] (0-padded at the end), history_len [B], candidate_ids [B,n] -> scores [B,n]"""
+        assert self.cache is not None, 'call encode_corpus() first'
+        ue = self.model.user_encoder
+        hid = torch.as_tensor(history_ids).to(self.dev).long()
+        cid = torch.as_tensor(candidate_ids).to(self.dev).long()
+        hl = torch.as_tensor(history_len).to(self.dev).to(torch.int32)
+        B, H = hid.shape
+        C = ue.proxy_node_embedding.shape[0]
+        cats = self.cat[hid].contiguous()
+        graph = torch.empty(B, H + C, H + C, device=self.dev)
+        cmask = torch.empty(B, C + 1, dtype=torch.bool, device=self.dev)
+        cidx = torch.empty(B, H, dtype=torch.int64, device=self.dev)
+        ops.sue_graph_build(cats, hl, C, graph, cmask, cidx)
+        hist = self.cache[hid]                                  # [B, H, D]
+        cand = self.cache[cid]                                  # [B, n, D]
+        user = ue.encode_user(hist, graph, cmask, cidx, cand)
+        return engine.RowDot.apply(user, cand)

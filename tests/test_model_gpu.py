@@ -236,3 +236,40 @@ def test_fused_call_equals_separate_reference_style_calls(cuda):
                               a['user_history_category_indices'], None, news)
         sep = engine.RowDot.apply(user, news)
     assert (fused - sep).abs().max().item() < 1e-6
+
+
+def test_cached_corpus_scoring_matches_oracle_at_equal_chunking(cuda):
+    """BASELINE config 3: encode the corpus once (chunked), build the graph on the device from category ids,
+    score impressions; the oracle encodes the same chunks as [1, chunk] calls (SURVEY 8c parity protocol)."""
+    from nnr_b200 import engine
+    from nnr_b200.scoring import CorpusScorer
+    from nnr_b200.synthetic import SyntheticMIND
+    from oracle import graph as OG
+    cfg = O.make_config(vocabulary_size=600, max_history_num=8, max_title_length=10, max_abstract_length=20,
+                        subCategory_num=30, gcn_layer_num=2)
+    syn = SyntheticMIND(news_num=150, vocabulary_size=600, subCategory_num=30, max_title_length=10, max_abstract_length=20,
+                        max_history_num=8, lengths='uniform', seed=21)
+    p = O.formula_params(cfg)
+    m = _build(cfg, p, cuda)
+    sc = CorpusScorer(m, syn.news_title_text, syn.news_title_mask, syn.news_abstract_text, syn.news_abstract_mask,
+                      syn.news_category, syn.news_subCategory, chunk=64)
+    cache = sc.encode_corpus()
+    hist, hl, cand = syn.sample_behaviors(6, news_num=3, seed=4)
+    scores = sc.score(hist, hl, cand)
+    # oracle: same chunk composition, stable sort
+    t = torch.from_numpy
+    chunks = []
+    with torch.no_grad():
+        for a in range(0, 150, 64):
+            b = min(150, a + 64)
+            chunks.append(O.cne_forward(p, cfg, t(syn.news_title_text[a:b])[None], t(syn.news_title_mask[a:b].copy())[None],
+                                        t(syn.news_abstract_text[a:b])[None], t(syn.news_abstract_mask[a:b].copy())[None],
+                                        t(syn.news_category[a:b])[None], t(syn.news_subCategory[a:b])[None],
+                                        sort_fn=O.stable_sort)[0])
+        ocache = torch.cat(chunks)
+        assert rel_err(cache, ocache) < TOL
+        import numpy as np
+        g, cm, ci = zip(*[OG.build_history_graph(syn.news_category[hist[b, :hl[b]]], 8, 18) for b in range(6)])
+        user = O.sue_forward(p, cfg, ocache[t(hist)], t(np.stack(g)), t(np.stack(cm)), t(np.stack(ci)), ocache[t(cand)])
+        ref = (user * ocache[t(cand)]).sum(2)
+    assert rel_err(scores, ref) < TOL
