@@ -74,7 +74,8 @@ enum {
   NNR_GEMM_AUTO = 0,
   NNR_GEMM_SIMT_FP32 = 1,    /* exact fp32 FFMA tiles                                           */
   NNR_GEMM_TC_TF32X3 = 2,    /* tcgen05 kind::tf32, hi/lo split (3 MMAs), fp32-grade accuracy   */
-  NNR_GEMM_TC_BF16 = 3       /* tcgen05 kind::f16 bf16 operands, fp32 accumulate                */
+  NNR_GEMM_TC_BF16 = 3,      /* tcgen05 kind::f16 bf16 operands, fp32 accumulate                */
+  NNR_GEMM_TC_BF16X3 = 4     /* tcgen05 kind::f16, bf16 hi/lo split (3 MMAs): ~2^-17 operand error, half the bytes */
 };
 typedef struct {
   const float* A; int64_t lda; int32_t transA;

@@ -18,6 +18,7 @@ static int default_algo() {
     if (e && !strcmp(e, "simt")) algo = NNR_GEMM_SIMT_FP32;
     else if (e && !strcmp(e, "tf32x3")) algo = NNR_GEMM_TC_TF32X3;
     else if (e && !strcmp(e, "bf16")) algo = NNR_GEMM_TC_BF16;
+    else if (e && !strcmp(e, "bf16x3")) algo = NNR_GEMM_TC_BF16X3;
     else algo = NNR_GEMM_TC_TF32X3;
   }
   return algo;

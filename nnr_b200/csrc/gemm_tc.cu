@@ -21,7 +21,7 @@
 //     warp 1     TMEM allocator (512 columns = two accumulators) and single-thread tcgen05.mma issuer:
 //                12 MMAs per stage (4 k-steps x 3 split products), tcgen05.commit frees the stage / publishes
 //                the accumulator.
-//     warps 2-5  epilogue: tcgen05.ld one accumulator row per thread, fused bias / tanh / relu+residual(+dropout)
+//     warps 2-9  epilogue (two warps per TMEM lane quarter, half the columns each): tcgen05.ld one accumulator row per thread, fused bias / tanh / relu+residual(+dropout)
 //                / sigmoid-gate / add, 16-byte stores; overlaps the next tile's main loop (double-buffered TMEM).
 //   split-K    partials + a deterministic fixed-order reduce.
 #include "common.cuh"
@@ -30,8 +30,10 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
+extern "C" int nnr_gemm_default_algo(void);
+
 #define TC_BM 128
-#define TC_THREADS 192
+#define TC_THREADS 320        // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 #define TC_TMEM_COLS 512
 #define TC_ACC_COLS 256
 #define TC_SMEM_BUDGET (221 * 1024)
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             const uint64_t ao = a_step * k, bo = b_step * k;
             tc_mma<BF16>(d_tmem, a_hi + ao, b_hi + bo, p.idesc, first ? 0u : 1u);
             first = 0;
-            if (!BF16) {
+            if (p.nplanes == 2) {           // split operands: the two cross products (lo*lo is below fp32 resolution)
               tc_mma<BF16>(d_tmem, a_hi + ao, b_lo + bo, p.idesc, 1u);
               tc_mma<BF16>(d_tmem, a_lo + ao, b_hi + bo, p.idesc, 1u);
             }
@@ -328,8 +330,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
     }
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+    // ===== epilogue: warps 2..9; warp % 4 selects the TMEM lane quarter, (warp-2)/4 the column half =====
     const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    const int nchunks = p.block_n >> 4;
+    const int c_begin = chalf ? ((nchunks + 1) >> 1) << 4 : 0;
+    const int c_end = chalf ? p.block_n : ((nchunks + 1) >> 1) << 4;
     int tl = 0;
     const bool nvec = (p.N % 4) == 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       mbar_wait(&tmem_full[buf], (tl >> 1) & 1);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + buf * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 16) {
         float v[16];
         if (kb1 > kb0) tmem_ld16(lane_addr + (uint32_t)c0, v);
         else {
@@ -398,7 +404,7 @@ __device__ __forceinline__ float rna_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-template <bool BF16>
+template <int MODE>   // 0: fp32 planes (rna_tf32 hi, lo)   1: one bf16 plane   2: bf16 hi, lo planes
 __global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__ src, int64_t ld, int R, int C, int Cp,
                                                        const int32_t* __restrict__ r_dev, bool vec, void* __restrict__ out,
                                                        size_t plane_stride) {
@@ -435,10 +441,17 @@ __global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (rr[u] < 0) continue;
-      if (BF16) {
-        __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(out) + (size_t)rr[u] * Cp + cc[u]);
-        o[0] = __floats2bfloat162_rn(x[u].x, x[u].y);                // Cp % 8 == 0 -> 8-byte aligned
-        o[1] = __floats2bfloat162_rn(x[u].z, x[u].w);
+      if (MODE >= 1) {
+        __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out) + (size_t)rr[u] * Cp + cc[u];
+        __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(ob);
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(x[u].x, x[u].y), h23 = __floats2bfloat162_rn(x[u].z, x[u].w);
+        o[0] = h01;                                                  // Cp % 8 == 0 -> 8-byte aligned
+        o[1] = h23;
+        if (MODE == 2) {
+          __nv_bfloat162* l = reinterpret_cast<__nv_bfloat162*>(ob + plane_stride);
+          l[0] = __floats2bfloat162_rn(x[u].x - __low2float(h01), x[u].y - __high2float(h01));
+          l[1] = __floats2bfloat162_rn(x[u].z - __low2float(h23), x[u].w - __high2float(h23));
+        }
       } else {
         float* hi = reinterpret_cast<float*>(out) + (size_t)rr[u] * Cp + cc[u];
         float4 h, l;
@@ -496,11 +509,17 @@ static int pick_block_n(int N, int step, int nplanes) {
   return best;
 }
 
-static TcPlan make_plan(const nnr_gemm_args* a, bool bf16) {
+// mode: 0 = 3xTF32 (fp32 hi/lo planes), 1 = BF16 (one plane), 2 = BF16x3 (bf16 hi/lo planes)
+static int algo_mode(int algo) {
+  if (algo == NNR_GEMM_AUTO) algo = nnr_gemm_default_algo();
+  return algo == NNR_GEMM_TC_BF16 ? 1 : (algo == NNR_GEMM_TC_BF16X3 ? 2 : 0);
+}
+static TcPlan make_plan(const nnr_gemm_args* a, int mode) {
   TcPlan pl;
+  const bool bf16 = mode != 0;
   pl.bf16 = bf16;
   pl.kelem = bf16 ? 64 : 32;
-  pl.nplanes = bf16 ? 1 : 2;
+  pl.nplanes = mode == 1 ? 1 : 2;
   pl.a_mn = a->transA ? 1 : 0;                 // A stored [K, M]: contraction along rows
   pl.b_mn = a->transB ? 0 : 1;                 // B stored [K, N]: contraction along rows
   pl.a_rows = a->transA ? a->K : a->M; pl.a_cols = a->transA ? a->M : a->K;
@@ -554,7 +573,7 @@ int nnr_gemm_tc_supported(const nnr_gemm_args* a) {
   return 1;
 }
 
-size_t nnr_gemm_tc_workspace_bytes(const nnr_gemm_args* a) { return make_plan(a, a->algo == NNR_GEMM_TC_BF16).total; }
+size_t nnr_gemm_tc_workspace_bytes(const nnr_gemm_args* a) { return make_plan(a, algo_mode(a->algo)).total; }
 
 static int encode_map(CUtensorMap* map, const void* base, bool bf16, int cols, int64_t pitch, int rows, int64_t plane_rows,
                       int nplanes, int box_c, int box_r, bool mn) {
@@ -571,7 +590,7 @@ static int encode_map(CUtensorMap* map, const void* base, bool bf16, int cols, i
   return 0;
 }
 
-template <bool BF16>
+template <int MODE>
 static int split_operand(const float* X, int64_t ld, int R, int C, int Cp, const int32_t* r_dev, void* out, size_t plane_stride,
                          cudaStream_t st) {
   bool vec = nnr_aligned16(X) && (ld % 4 == 0);
@@ -580,15 +599,16 @@ static int split_operand(const float* X, int64_t ld, int R, int C, int Cp, const
   int grid = (int)(want < 148 * 16 ? want : 148 * 16);
   if (grid < 1) grid = 1;
   void* ph = nnr_prof_begin(1, 0.0, st);
-  tc_split_kernel<BF16><<<grid, 256, 0, st>>>(X, ld, R, C, Cp, r_dev, vec, out, plane_stride);
+  tc_split_kernel<MODE><<<grid, 256, 0, st>>>(X, ld, R, C, Cp, r_dev, vec, out, plane_stride);
   nnr_prof_end(ph, st);
   NNR_LAUNCH_CHECK("tc_split_kernel");
   return 0;
 }
 
-template <bool BF16>
+template <int MODE>
 static int run_tc(const nnr_gemm_args* a, cudaStream_t st) {
-  TcPlan pl = make_plan(a, BF16);
+  constexpr bool BF16 = MODE != 0;
+  TcPlan pl = make_plan(a, MODE);
   NNR_REQUIRE(pl.total == 0 || (a->workspace && a->workspace_bytes >= pl.total), NNR_ERR_WORKSPACE,
               "nnr_gemm(tc): workspace %zu < %zu", a->workspace_bytes, pl.total);
   NNR_REQUIRE(nnr_aligned16(a->workspace), NNR_ERR_ALIGN, "nnr_gemm(tc): workspace must be 16B aligned");
@@ -604,13 +624,13 @@ static int run_tc(const nnr_gemm_args* a, cudaStream_t st) {
   // rows of A are M (m_dev) when row-major, K (k_dev) when MN-major; rows of B are K (k_dev) when MN-major
   if (!pa) {
     void* w = ws + pl.a_off;
-    rc = split_operand<BF16>(a->A, a->lda, pl.a_rows, pl.a_cols, pl.a_cp, pl.a_mn ? a->k_dev : a->m_dev, w, pl.a_plane, st);
+    rc = split_operand<MODE>(a->A, a->lda, pl.a_rows, pl.a_cols, pl.a_cp, pl.a_mn ? a->k_dev : a->m_dev, w, pl.a_plane, st);
     if (rc) return rc;
     pa = w; a_pitch = pl.a_cp; a_prow = pl.a_rows;
   }
   if (!pb) {
     void* w = ws + pl.b_off;
-    rc = split_operand<BF16>(a->B, a->ldb, pl.b_rows, pl.b_cols, pl.b_cp, pl.b_mn ? a->k_dev : nullptr, w, pl.b_plane, st);
+    rc = split_operand<MODE>(a->B, a->ldb, pl.b_rows, pl.b_cols, pl.b_cp, pl.b_mn ? a->k_dev : nullptr, w, pl.b_plane, st);
     if (rc) return rc;
     pb = w; b_pitch = pl.b_cp; b_prow = pl.b_rows;
   }
@@ -661,31 +681,29 @@ static int run_tc(const nnr_gemm_args* a, cudaStream_t st) {
 
 int nnr_gemm_tc(const nnr_gemm_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->algo == NNR_GEMM_TC_BF16) return run_tc<true>(a, st);
-  return run_tc<false>(a, st);
+  const int mode = algo_mode(a->algo);
+  if (mode == 1) return run_tc<1>(a, st);
+  if (mode == 2) return run_tc<2>(a, st);
+  return run_tc<0>(a, st);
 }
 
 // ------------------------------------------------------------------------------------------------
 // public pre-split entry points
 // ------------------------------------------------------------------------------------------------
-extern "C" int nnr_gemm_default_algo(void);
-static bool split_is_bf16(int algo) {
-  if (algo == NNR_GEMM_AUTO) algo = nnr_gemm_default_algo();
-  return algo == NNR_GEMM_TC_BF16;
-}
-extern "C" int64_t nnr_tc_split_pitch(int C, int algo) { return (int64_t)up((size_t)C, split_is_bf16(algo) ? 8 : 4); }
+extern "C" int64_t nnr_tc_split_pitch(int C, int algo) { return (int64_t)up((size_t)C, algo_mode(algo) ? 8 : 4); }
 extern "C" size_t nnr_tc_split_bytes(int R, int C, int algo) {
   if (R <= 0 || C <= 0) return 0;
-  bool bf = split_is_bf16(algo);
-  return (size_t)R * (size_t)nnr_tc_split_pitch(C, algo) * (bf ? 2 : 8);
+  const int mode = algo_mode(algo);
+  return (size_t)R * (size_t)nnr_tc_split_pitch(C, algo) * (mode == 0 ? 8 : (mode == 1 ? 2 : 4));
 }
 extern "C" int nnr_tc_split(const float* X, int64_t ld, int R, int C, const int32_t* r_dev, int algo, void* planes,
                             size_t planes_bytes, void* stream) {
   NNR_REQUIRE(X && planes && R > 0 && C > 0 && ld >= C, NNR_ERR_ARG, "nnr_tc_split: bad arguments");
   NNR_REQUIRE(planes_bytes >= nnr_tc_split_bytes(R, C, algo), NNR_ERR_WORKSPACE, "nnr_tc_split: planes buffer too small");
   NNR_REQUIRE(nnr_aligned16(planes), NNR_ERR_ALIGN, "nnr_tc_split: planes must be 16B aligned");
-  bool bf = split_is_bf16(algo);
+  const int mode = algo_mode(algo);
   int Cp = (int)nnr_tc_split_pitch(C, algo);
-  if (bf) return split_operand<true>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (cudaStream_t)stream);
-  return split_operand<false>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (cudaStream_t)stream);
+  if (mode == 1) return split_operand<1>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (cudaStream_t)stream);
+  if (mode == 2) return split_operand<2>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (cudaStream_t)stream);
+  return split_operand<0>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (cudaStream_t)stream);
 }

@@ -65,27 +65,28 @@ extern "C" int nnr_segment_colsum(const float* X, int64_t ldx, const int32_t* of
 // ------------------------------------------------------------------------------------------
 // hprev for dW_hh
 // ------------------------------------------------------------------------------------------
-__global__ void lstm_shift_h_kernel(const float* __restrict__ h, const int32_t* __restrict__ len,
-                                    const int32_t* __restrict__ off, const int32_t* __restrict__ tok_row, int N, int H,
-                                    float* __restrict__ hprev) {
-  int ntok = off[N];
-  int p = blockIdx.x;
-  if (p >= ntok) return;
-  int r = tok_row[p];
-  int t = p - off[r];
-  int l = len[r];
-  int H2 = 2 * H;
-  for (int k = threadIdx.x; k < H2; k += blockDim.x) {
-    float v;
-    if (k < H) v = (t > 0) ? h[(size_t)(p - 1) * H2 + k] : 0.f;
-    else v = (t < l - 1) ? h[(size_t)(p + 1) * H2 + k] : 0.f;
-    hprev[(size_t)p * H2 + k] = v;
+__global__ void __launch_bounds__(256) lstm_shift_h_kernel(const float* __restrict__ h, const int32_t* __restrict__ len,
+                                                           const int32_t* __restrict__ off, const int32_t* __restrict__ tok_row,
+                                                           int N, int H, float* __restrict__ hprev) {
+  // grid-stride over (token, float4 column group); the token count is read on the device
+  const int ntok = off[N];
+  const int H2 = 2 * H, q_per_tok = H2 >> 2, hq = H >> 2;
+  const long long total = (long long)ntok * q_per_tok;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i / q_per_tok), q = (int)(i - (long long)p * q_per_tok);
+    const int r = tok_row[p];
+    const int t = p - off[r];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < hq) { if (t > 0) v = __ldg(reinterpret_cast<const float4*>(h + (size_t)(p - 1) * H2) + q); }
+    else { if (t < len[r] - 1) v = __ldg(reinterpret_cast<const float4*>(h + (size_t)(p + 1) * H2) + q); }
+    reinterpret_cast<float4*>(hprev + (size_t)p * H2)[q] = v;
   }
 }
 extern "C" int nnr_lstm_shift_h(const float* h, const int32_t* len, const int32_t* off, const int32_t* tok_row, int N,
                                 int L, int H, float* hprev, void* stream) {
   NNR_REQUIRE(h && len && off && tok_row && hprev && N > 0 && L > 0 && H > 0, NNR_ERR_ARG, "nnr_lstm_shift_h: bad arguments");
-  lstm_shift_h_kernel<<<N * L, 128, 0, (cudaStream_t)stream>>>(h, len, off, tok_row, N, H, hprev);
+  NNR_REQUIRE(H % 4 == 0 && nnr_aligned16(h) && nnr_aligned16(hprev), NNR_ERR_ALIGN, "nnr_lstm_shift_h: H %% 4 == 0, 16B alignment");
+  lstm_shift_h_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(h, len, off, tok_row, N, H, hprev);
   NNR_LAUNCH_CHECK("lstm_shift_h_kernel");
   return 0;
 }
@@ -93,22 +94,24 @@ extern "C" int nnr_lstm_shift_h(const float* h, const int32_t* len, const int32_
 // ------------------------------------------------------------------------------------------
 // selective gate backward prologue
 // ------------------------------------------------------------------------------------------
-__global__ void gate_bwd_pre_kernel(const float* __restrict__ dhg, const float* __restrict__ h, const float* __restrict__ g,
-                                    int64_t n_max, const int32_t* __restrict__ n_dev, int D, float* __restrict__ dz,
-                                    float* __restrict__ dh0) {
-  int64_t n = n_dev ? min(n_max, (int64_t)(*n_dev) * D) : n_max;
-  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i >= n) return;
-  float4 a = *reinterpret_cast<const float4*>(dhg + i);
-  float4 hh = *reinterpret_cast<const float4*>(h + i);
-  float4 gg = *reinterpret_cast<const float4*>(g + i);
-  float4 z, d0;
-  z.x = a.x * hh.x * gg.x * (1.f - gg.x); d0.x = a.x * gg.x;
-  z.y = a.y * hh.y * gg.y * (1.f - gg.y); d0.y = a.y * gg.y;
-  z.z = a.z * hh.z * gg.z * (1.f - gg.z); d0.z = a.z * gg.z;
-  z.w = a.w * hh.w * gg.w * (1.f - gg.w); d0.w = a.w * gg.w;
-  *reinterpret_cast<float4*>(dz + i) = z;
-  *reinterpret_cast<float4*>(dh0 + i) = d0;
+__global__ void __launch_bounds__(256) gate_bwd_pre_kernel(const float* __restrict__ dhg, const float* __restrict__ h,
+                                                           const float* __restrict__ g, int64_t n_max,
+                                                           const int32_t* __restrict__ n_dev, int D, float* __restrict__ dz,
+                                                           float* __restrict__ dh0) {
+  const int64_t n = n_dev ? min(n_max, (int64_t)(*n_dev) * D) : n_max;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    float4 a = *reinterpret_cast<const float4*>(dhg + i);
+    float4 hh = *reinterpret_cast<const float4*>(h + i);
+    float4 gg = *reinterpret_cast<const float4*>(g + i);
+    float4 z, d0;
+    z.x = a.x * hh.x * gg.x * (1.f - gg.x); d0.x = a.x * gg.x;
+    z.y = a.y * hh.y * gg.y * (1.f - gg.y); d0.y = a.y * gg.y;
+    z.z = a.z * hh.z * gg.z * (1.f - gg.z); d0.z = a.z * gg.z;
+    z.w = a.w * hh.w * gg.w * (1.f - gg.w); d0.w = a.w * gg.w;
+    *reinterpret_cast<float4*>(dz + i) = z;
+    *reinterpret_cast<float4*>(dh0 + i) = d0;
+  }
 }
 extern "C" int nnr_gate_bwd_pre(const float* dhg, const float* h, const float* g, int64_t n_max, const int32_t* n_dev,
                                 int D, float* dz, float* dh0, void* stream) {
@@ -116,8 +119,7 @@ extern "C" int nnr_gate_bwd_pre(const float* dhg, const float* h, const float* g
   NNR_REQUIRE(n_max % 4 == 0 && D % 4 == 0 && nnr_aligned16(dhg) && nnr_aligned16(h) && nnr_aligned16(g) &&
                   nnr_aligned16(dz) && nnr_aligned16(dh0),
               NNR_ERR_ALIGN, "nnr_gate_bwd_pre: needs 16B alignment and D %% 4 == 0");
-  int64_t n4 = n_max / 4;
-  gate_bwd_pre_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dhg, h, g, n_max, n_dev, D, dz, dh0);
+  gate_bwd_pre_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(dhg, h, g, n_max, n_dev, D, dz, dh0);
   NNR_LAUNCH_CHECK("gate_bwd_pre_kernel");
   return 0;
 }

@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import GemmArgs, PoolArgs, check, lib
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_TANH, EPI_BIAS_RELU_RES, EPI_GATE, EPI_ADD_AUX = range(6)
-ALGO_AUTO, ALGO_SIMT, ALGO_TF32X3, ALGO_BF16 = range(4)
+ALGO_AUTO, ALGO_SIMT, ALGO_TF32X3, ALGO_BF16, ALGO_BF16X3 = range(5)
 
 _F32, _I32, _I64, _U8 = torch.float32, torch.int32, torch.int64, torch.uint8
 
@@ -101,7 +101,7 @@ def tc_split(x, rows, cols, ld, r_dev=None):
     buf = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     check(lib.nnr_tc_split(_p(x, _F32), ld, rows, cols, _p(r_dev, _I32), algo, buf.data_ptr(), nbytes, _stream()),
           'nnr_tc_split')
-    return Planes(buf, rows, cols, int(lib.nnr_tc_split_pitch(cols, algo)), 2 if algo == ALGO_BF16 else 4)
+    return Planes(buf, rows, cols, int(lib.nnr_tc_split_pitch(cols, algo)), 2 if algo in (ALGO_BF16, ALGO_BF16X3) else 4)
 
 
 def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, transA, transB, epilogue=EPI_NONE, accumulate=False, bias=None,

@@ -125,3 +125,20 @@ def test_bf16_variant(cuda):
             b = (B.t() if transB else B).bfloat16().double()
             err2 = (C.double() - a @ b).abs().max().item() / ref.abs().max().item()
             assert err2 < 1e-5, (M, N, K, err2)
+
+
+def test_bf16x3_variant(cuda):
+    """bf16 hi/lo split (3 MMAs of kind::f16): operands carry 16 mantissa bits -> ~1e-5 of max|C|"""
+    from nnr_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    worst = 0.0
+    for (M, N, K) in [(1000, 1600, 300), (513, 400, 400), (3000, 300, 1600), (777, 225, 900)]:
+        for transA, transB in ((False, True), (False, False), (True, False), (True, True)):
+            A = torch.randn((K, M) if transA else (M, K), generator=g).to(cuda)
+            B = torch.randn((N, K) if transB else (K, N), generator=g).to(cuda)
+            C = _run(ops, A, B, M, N, K, transA, transB, ops.ALGO_BF16X3)
+            ref = _ref(A, B, transA, transB)
+            err = (C.double() - ref).abs().max().item() / ref.abs().max().item()
+            worst = max(worst, err)
+            assert err < 4e-5, (M, N, K, transA, transB, err)
+    print('bf16x3 worst rel err', worst)
