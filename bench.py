@@ -87,7 +87,7 @@ class Clocks:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def __enter__(self):
         if self.nv:

@@ -19,7 +19,7 @@ static int default_algo() {
     else if (e && !strcmp(e, "tf32x3")) algo = NNR_GEMM_TC_TF32X3;
     else if (e && !strcmp(e, "bf16")) algo = NNR_GEMM_TC_BF16;
     else if (e && !strcmp(e, "bf16x3")) algo = NNR_GEMM_TC_BF16X3;
-    else algo = NNR_GEMM_TC_TF32X3;
+    else algo = NNR_GEMM_TC_BF16X3;   // measured: 6e-6 of max|C| (tf32x3: 1.1e-5), half the operand bytes, 2x MMA rate
   }
   return algo;
 }

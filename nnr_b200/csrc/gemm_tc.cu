@@ -37,6 +37,7 @@ extern "C" int nnr_gemm_default_algo(void);
 #define TC_TMEM_COLS 512
 #define TC_ACC_COLS 256
 #define TC_SMEM_BUDGET (221 * 1024)
+#define TC_PREFETCH_KB 1000000   // L2 prefetch distance in k-blocks; measured slower when enabled (6), so effectively off
 #define TC_CHAIN_K 1024      // max contraction length accumulated in TMEM before an fp32 combine (split-K GEMMs)
 
 // ------------------------------------------------------------------------------------------------
@@ -71,6 +72,10 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// L2 prefetch of a TMA box: hides the DRAM latency of operand planes behind L2 capacity instead of smem stages
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -275,6 +280,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           mbar_wait(&empty_bar[s], ph ^ 1);
           const uint32_t base = smem_u32(tiles + (size_t)s * stage_bytes);
           mbar_expect_tx(&full_bar[s], stage_bytes);
+          const int kpf = kb + TC_PREFETCH_KB;                 // L2 prefetch distance (k-blocks)
+          if (kpf < kb1) {
+            for (int pl = 0; pl < p.nplanes; ++pl) {
+              if (!p.a_mn) tma_prefetch_3d(&map_a, kpf * KELEM, m0, pl);
+              else for (int g = 0; g < TC_BM / KELEM; ++g) tma_prefetch_3d(&map_a, m0 + g * KELEM, kpf * KELEM, pl);
+              if (!p.b_mn) tma_prefetch_3d(&map_b, kpf * KELEM, n0, pl);
+              else for (int g = 0; g < p.block_n / KELEM; ++g) tma_prefetch_3d(&map_b, n0 + g * KELEM, kpf * KELEM, pl);
+            }
+          }
           for (int pl = 0; pl < p.nplanes; ++pl) {
             const uint32_t sa = base + pl * a_tile;
             const uint32_t sb = base + p.nplanes * a_tile + pl * b_tile;

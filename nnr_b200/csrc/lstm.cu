@@ -27,16 +27,17 @@
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
-template <int HID_, int CL_, int MT_, int UPT_>   // hidden, cluster size, rows per tile, units per thread (phase 1)
+template <int HID_, int CL_, int MT_, int UPT_, int RPT_ = 4>   // hidden, cluster size, rows per tile, units / rows per thread
 struct LCfg {
-  static constexpr int HID = HID_, CL = CL_, MT = MT_, UPT = UPT_;
+  static constexpr int HID = HID_, CL = CL_, MT = MT_, UPT = UPT_, RPT = RPT_;
   static constexpr int UPC = HID / CL;        // hidden units per CTA
   static constexpr int COLS = 4 * UPC;        // gate columns per CTA
   static constexpr int UG = UPC / UPT;        // unit groups
-  static constexpr int RG = MT / 4;           // row groups of 4
-  static constexpr int NWORK = UG * RG;       // working threads
-  static constexpr int NT = ((NWORK + 31) / 32) * 32;
-  static_assert(HID % CL == 0 && UPC % UPT == 0 && MT % 4 == 0 && HID % 4 == 0, "unsupported LSTM geometry");
+  static constexpr int RG = MT / RPT;         // row groups (one warp each)
+  static constexpr int NT = RG * 32;          // one warp per row group; lanes [0, UG) work (warp-aligned: no
+                                              // shared-memory bank conflicts between row groups, h loads broadcast)
+  static_assert(UG <= 32, "unit groups must fit one warp");
+  static_assert(HID % CL == 0 && UPC % UPT == 0 && MT % RPT == 0 && RPT % 4 == 0 && HID % 4 == 0, "unsupported LSTM geometry");
   static constexpr size_t FWD_SMEM = sizeof(float) * ((size_t)HID * COLS + 2 * (size_t)HID * MT) + 3 * MT * sizeof(int);
   static constexpr size_t BWD_SMEM = sizeof(float) * ((size_t)COLS * HID + (size_t)COLS * MT + (size_t)CL * UPC * MT) + 3 * MT * sizeof(int);
 };
@@ -59,12 +60,14 @@ __device__ __forceinline__ void lbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void lbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
 }
+// default (acquire.cta) wait: the complete_tx of st.async makes the bytes visible to the waiter, exactly as for
+// TMA loads; a cluster-scope acquire would add CCTL.IVALL (L1 invalidate) to every step
 __device__ __forceinline__ void lbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "LW_LOOP:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra LW_DONE;\n"
       "bra LW_LOOP;\n"
       "LW_DONE:\n"
@@ -95,6 +98,7 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
                 const int32_t* __restrict__ off, const int32_t* __restrict__ order, int N, int ntiles,
                 float* __restrict__ h_out, float* __restrict__ c_stash, float* __restrict__ c_n, int* __restrict__ tile_counter) {
   constexpr int HID = C::HID, CL = C::CL, MT = C::MT, UPC = C::UPC, COLS = C::COLS, UP = C::UG;
+  constexpr int RPT = C::RPT;                  // rows per thread (register tile: 2 units x 4 gates x RPT rows)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* Wt = reinterpret_cast<float*>(smem_raw);                 // [HID][COLS]
   float* hT = Wt + (size_t)HID * COLS;                            // [2][HID][MT]
@@ -108,9 +112,9 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
   const int nclusters = gridDim.x / CL;
   const int dir = cluster_id & 1;
   const int tid = threadIdx.x;
-  const bool worker = tid < C::NWORK;
-  const int up = tid % UP, rg = tid / UP;
-  const int j0 = 2 * up;                       // local unit of this thread (and j0+1)
+  const int up = tid & 31, rg = tid >> 5;      // lane = unit pair, warp = row group
+  const bool worker = up < UP;
+  const int j0 = 2 * min(up, UP - 1);          // local unit of this thread (and j0+1)
   const int unit0 = rank * UPC + j0;           // global hidden unit
 
   // W slice -> smem, transposed to k-major: Wt[k][g*UPC + j] = W_hh[dir][g*HID + rank*UPC + j][k]
@@ -167,20 +171,20 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
     int maxlen = 0;
     for (int i = 0; i < MT; ++i) maxlen = max(maxlen, s_len[i]);
 
-    int rlen[4], roff[4], rrow[4];
-    float cst[2][4], hst[2][4];
+    int rlen[RPT], roff[RPT], rrow[RPT];
+    float cst[2][RPT], hst[2][RPT];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      rlen[i] = worker ? s_len[4 * rg + i] : 0;
-      roff[i] = worker ? s_off[4 * rg + i] : 0;
-      rrow[i] = worker ? s_row[4 * rg + i] : -1;
+    for (int i = 0; i < RPT; ++i) {
+      rlen[i] = worker ? s_len[RPT * rg + i] : 0;
+      roff[i] = worker ? s_off[RPT * rg + i] : 0;
+      rrow[i] = worker ? s_row[RPT * rg + i] : -1;
       cst[0][i] = cst[1][i] = hst[0][i] = hst[1][i] = 0.f;
     }
     // prefetch gx for step 0
-    float2 gxr[4][4];  // [gate][row]
+    float2 gxr[4][RPT];  // [gate][row]
     auto load_gx = [&](int s) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < RPT; ++i) {
         if (s < rlen[i]) {
           int t = dir ? (rlen[i] - 1 - s) : s;
           const float* p = gx + ((size_t)roff[i] + t) * GS + (size_t)dir * 4 * HID + unit0;
@@ -200,36 +204,37 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
       if (s > 0) { lbar_wait_cluster(&hfull[cur], hph[cur]); hph[cur] ^= 1u; }                          // h_s landed
       if (worker) {
         // accumulators as packed pairs (unit j0, unit j0+1): one FFMA2 (fma.rn.f32x2) per gate and row
-        float2 acc2[4][4];
+        float2 acc2[4][RPT];
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) acc2[g][i] = gxr[g][i];
+          for (int i = 0; i < RPT; ++i) acc2[g][i] = gxr[g][i];
         if (s + 1 < maxlen) load_gx(s + 1);   // in flight during the k loop
-        const float* hb = hT + (size_t)cur * HID * MT + 4 * rg;
+        const float* hb = hT + (size_t)cur * HID * MT + RPT * rg;
         const float* wb = Wt + j0;
 #pragma unroll 4
         for (int k = 0; k < HID; ++k) {
-          const float4 hv = *reinterpret_cast<const float4*>(hb + (size_t)k * MT);
-          const float2 h0 = make_float2(hv.x, hv.x), h1 = make_float2(hv.y, hv.y);
-          const float2 h2 = make_float2(hv.z, hv.z), h3 = make_float2(hv.w, hv.w);
+          float hv[RPT];
+#pragma unroll
+          for (int q = 0; q < RPT / 4; ++q) {
+            const float4 t4 = *reinterpret_cast<const float4*>(hb + (size_t)k * MT + 4 * q);
+            hv[4 * q] = t4.x; hv[4 * q + 1] = t4.y; hv[4 * q + 2] = t4.z; hv[4 * q + 3] = t4.w;
+          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const float2 w = *reinterpret_cast<const float2*>(wb + (size_t)k * COLS + g * UPC);
-            acc2[g][0] = __ffma2_rn(w, h0, acc2[g][0]);
-            acc2[g][1] = __ffma2_rn(w, h1, acc2[g][1]);
-            acc2[g][2] = __ffma2_rn(w, h2, acc2[g][2]);
-            acc2[g][3] = __ffma2_rn(w, h3, acc2[g][3]);
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) acc2[g][i] = __ffma2_rn(w, make_float2(hv[i], hv[i]), acc2[g][i]);
           }
         }
-        float acc[4][2][4];
+        float acc[4][2][RPT];
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { acc[g][0][i] = acc2[g][i].x; acc[g][1][i] = acc2[g][i].y; }
+          for (int i = 0; i < RPT; ++i) { acc[g][0][i] = acc2[g][i].x; acc[g][1][i] = acc2[g][i].y; }
         // gates, state update, stash
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < RPT; ++i) {
           if (s < rlen[i]) {
             int t = dir ? (rlen[i] - 1 - s) : s;
             size_t p = (size_t)roff[i] + t;
@@ -259,13 +264,16 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
         // counted on the receiver's transaction barrier.  Double buffering + the data dependency of the
         // recurrence make the write-after-read safe without a second barrier.
         if (s + 1 < maxlen) {
-          float4 h0 = make_float4(hst[0][0], hst[0][1], hst[0][2], hst[0][3]);
-          float4 h1 = make_float4(hst[1][0], hst[1][1], hst[1][2], hst[1][3]);
-          const uint32_t o = (uint32_t)(((size_t)nxt * HID * MT + (size_t)unit0 * MT + 4 * rg) * sizeof(float));
+          const uint32_t o = (uint32_t)(((size_t)nxt * HID * MT + (size_t)unit0 * MT + RPT * rg) * sizeof(float));
 #pragma unroll
-          for (int d = 0; d < CL; ++d) {
-            st_async_f4(remote_hT[d] + o, h0, remote_bar[d] + nxt * 8);
-            st_async_f4(remote_hT[d] + o + MT * sizeof(float), h1, remote_bar[d] + nxt * 8);
+          for (int q = 0; q < RPT / 4; ++q) {
+            const float4 h0 = make_float4(hst[0][4 * q], hst[0][4 * q + 1], hst[0][4 * q + 2], hst[0][4 * q + 3]);
+            const float4 h1 = make_float4(hst[1][4 * q], hst[1][4 * q + 1], hst[1][4 * q + 2], hst[1][4 * q + 3]);
+#pragma unroll
+            for (int d = 0; d < CL; ++d) {
+              st_async_f4(remote_hT[d] + o + 16 * q, h0, remote_bar[d] + nxt * 8);
+              st_async_f4(remote_hT[d] + o + 16 * q + MT * sizeof(float), h1, remote_bar[d] + nxt * 8);
+            }
           }
         }
       }
@@ -284,10 +292,10 @@ __global__ void __launch_bounds__(C::NT, 1)
 lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, const float* __restrict__ w_hh,
                 const int32_t* __restrict__ len, const int32_t* __restrict__ off, const int32_t* __restrict__ order,
                 int N, int ntiles, const float* __restrict__ dh, const float* __restrict__ dcn, int* __restrict__ tile_counter) {
-  constexpr int HID = C::HID, CL = C::CL, MT = C::MT, UPC = C::UPC, COLS = C::COLS, UG = C::UG;
-  static_assert(C::UPT == 1, "backward kernel is written for 1 unit per thread");
-  constexpr int KG = HID / 4;                  // phase 2: groups of 4 k's
-  static_assert(KG * C::RG <= C::NT, "backward phase-2 mapping does not fit");
+  constexpr int HID = C::HID, CL = C::CL, MT = C::MT, UPC = C::UPC, COLS = C::COLS, UP = C::UG;
+  static_assert(C::UPT == 2 && MT == 32 && C::NT == 256, "backward kernel: 2 units per lane, 32-row tiles, 8 warps");
+  constexpr int KG = HID / 4;                  // phase 2: groups of 4 k's (two warps of KG/2 lanes per 8-row group)
+  static_assert(KG % 2 == 0 && KG / 2 <= 32, "phase-2 mapping");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* Wc = reinterpret_cast<float*>(smem_raw);                 // [COLS][HID]  (c-major)
   float* dzT = Wc + (size_t)COLS * HID;                           // [COLS][MT]
@@ -299,14 +307,17 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, co
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int cluster_id = blockIdx.x / CL;
-  const int nclusters = gridDim.x / CL;
   const int dir = cluster_id & 1;
-  const int tid = threadIdx.x;
-  const bool worker = tid < C::NWORK;
-  const int j = tid % UG, rg = tid / UG;       // phase 1: one hidden unit x 4 rows
-  const int unit = rank * UPC + j;
-  const bool worker2 = tid < KG * C::RG;       // phase 2: 4 k's x 4 rows
-  const int kg = tid % KG, rg2 = tid / KG;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // phase 1: lane = unit pair, warp = group of 4 rows
+  const bool worker = lane < UP;
+  const int rg = warp;
+  const int j0 = 2 * min(lane, UP - 1);
+  const int unit0 = rank * UPC + j0;
+  // phase 2: warps (2q, 2q+1) own rows 8q..8q+7; lanes own 4 consecutive k's
+  const bool worker2 = lane < KG / 2;
+  const int rg2 = warp >> 1;
+  const int kg = (warp & 1) * (KG / 2) + min(lane, KG / 2 - 1);
 
   {
     const float* W = w_hh + (size_t)dir * 4 * HID * HID;
@@ -336,13 +347,10 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, co
   uint32_t ph_full = 0u, ph_free = 0u;
 
   const size_t GS = (size_t)2 * 4 * HID;
-  // dynamic tile scheduling: tiles are sorted longest-first, so handing the next tile to whichever cluster
-  // becomes free is longest-processing-time-first list scheduling (one atomic per tile, broadcast via DSMEM)
   __shared__ int s_tile;
   int* remote_tile[CL];
 #pragma unroll
   for (int d = 0; d < CL; ++d) remote_tile[d] = cluster.map_shared_rank(&s_tile, d);
-  (void)nclusters;
   for (;;) {
     if (rank == 0 && tid == 0) {
       int t = atomicAdd(&tile_counter[dir], 1);
@@ -365,56 +373,87 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, co
     int maxlen = 0;
     for (int i = 0; i < MT; ++i) maxlen = max(maxlen, s_len[i]);
     int rlen[4], roff[4], rrow[4];
-    float dcc[4];      // dL/dc carried to the previous step
+    float dcc[2][4];   // dL/dc carried to the previous step
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       rlen[i] = worker ? s_len[4 * rg + i] : 0;
       roff[i] = worker ? s_off[4 * rg + i] : 0;
       rrow[i] = worker ? s_row[4 * rg + i] : -1;
-      dcc[i] = 0.f;
+      dcc[0][i] = dcc[1][i] = 0.f;
     }
+    // stash of one iteration (gates, c_t, c_{t-1}, dh); (prefetching it a whole iteration ahead was measured
+    // slower: the extra 56 live registers cost more than the hidden latency)
+    float2 p_ig[4], p_fg[4], p_gg[4], p_og[4], p_ct[4], p_cp[4], p_dh[4];
+    auto load_stash = [&](int s) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (s >= 0 && s < rlen[i]) {
+          int t = dir ? (rlen[i] - 1 - s) : s;
+          size_t p = (size_t)roff[i] + t;
+          const float* gp = gates + p * GS + (size_t)dir * 4 * HID + unit0;
+          p_ig[i] = *reinterpret_cast<const float2*>(gp);
+          p_fg[i] = *reinterpret_cast<const float2*>(gp + HID);
+          p_gg[i] = *reinterpret_cast<const float2*>(gp + 2 * HID);
+          p_og[i] = *reinterpret_cast<const float2*>(gp + 3 * HID);
+          p_ct[i] = *reinterpret_cast<const float2*>(c_stash + (p * 2 + dir) * HID + unit0);
+          p_cp[i] = make_float2(0.f, 0.f);
+          if (s > 0) {
+            size_t pp = dir ? p + 1 : p - 1;
+            p_cp[i] = *reinterpret_cast<const float2*>(c_stash + (pp * 2 + dir) * HID + unit0);
+          }
+          p_dh[i] = *reinterpret_cast<const float2*>(dh + p * 2 * HID + (size_t)dir * HID + unit0);
+        }
+      }
+    };
     for (int s = maxlen - 1; s >= 0; --s) {
+      if (worker) load_stash(s);          // issued before the wait so the loads overlap the DSMEM latency
       if (s < maxlen - 1) { lbar_wait_cluster(rfull, ph_full); ph_full ^= 1u; }   // partials of iteration s+1 landed
       if (worker) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float dz[4];
+          float dz[4][2];
           if (s < rlen[i]) {
             int t = dir ? (rlen[i] - 1 - s) : s;
             size_t p = (size_t)roff[i] + t;
-            float* gp = gates + p * GS + (size_t)dir * 4 * HID + unit;
-            float iv = gp[0], fv = gp[HID], gv = gp[2 * HID], ov = gp[3 * HID];
-            float cv = c_stash[(p * 2 + dir) * HID + unit];
-            float cpv = 0.f;
-            if (s > 0) {
-              size_t pp = dir ? p + 1 : p - 1;
-              cpv = c_stash[(pp * 2 + dir) * HID + unit];
-            }
-            float dht = dh[p * 2 * HID + (size_t)dir * HID + unit];
+            float* gp = gates + p * GS + (size_t)dir * 4 * HID + unit0;
+            const float2 ig = p_ig[i], fg = p_fg[i], gg = p_gg[i], og = p_og[i], ct = p_ct[i], cp = p_cp[i], dhu = p_dh[i];
+            float dht[2] = {dhu.x, dhu.y};
             if (s == rlen[i] - 1) {   // the row's last step: start of its backward recursion
-              dcc[i] = dcn[(size_t)rrow[i] * 2 * HID + (size_t)dir * HID + unit];
+              float2 d0 = *reinterpret_cast<const float2*>(dcn + (size_t)rrow[i] * 2 * HID + (size_t)dir * HID + unit0);
+              dcc[0][i] = d0.x; dcc[1][i] = d0.y;
             } else {
               // recurrent part: sum of the CL partials in fixed order
-              float r = 0.f;
 #pragma unroll
-              for (int src = 0; src < CL; ++src) r += recv[((size_t)src * UPC + j) * MT + 4 * rg + i];
-              dht += r;
+              for (int u = 0; u < 2; ++u) {
+                float r = 0.f;
+#pragma unroll
+                for (int src = 0; src < CL; ++src) r += recv[((size_t)src * UPC + j0 + u) * MT + 4 * rg + i];
+                dht[u] += r;
+              }
             }
-            float tc = fast_tanh(cv);
-            float dc = dcc[i] + dht * ov * (1.f - tc * tc);
-            dz[3] = dht * tc * ov * (1.f - ov);
-            dz[0] = dc * gv * iv * (1.f - iv);
-            dz[2] = dc * iv * (1.f - gv * gv);
-            dz[1] = dc * cpv * fv * (1.f - fv);
-            dcc[i] = dc * fv;
+            float iv[2] = {ig.x, ig.y}, fv[2] = {fg.x, fg.y}, gv[2] = {gg.x, gg.y}, ov[2] = {og.x, og.y};
+            float cv[2] = {ct.x, ct.y}, cpv[2] = {cp.x, cp.y};
 #pragma unroll
-            for (int g = 0; g < 4; ++g) gp[g * HID] = dz[g];
+            for (int u = 0; u < 2; ++u) {
+              float tc = fast_tanh(cv[u]);
+              float dc = dcc[u][i] + dht[u] * ov[u] * (1.f - tc * tc);
+              dz[3][u] = dht[u] * tc * ov[u] * (1.f - ov[u]);
+              dz[0][u] = dc * gv[u] * iv[u] * (1.f - iv[u]);
+              dz[2][u] = dc * iv[u] * (1.f - gv[u] * gv[u]);
+              dz[1][u] = dc * cpv[u] * fv[u] * (1.f - fv[u]);
+              dcc[u][i] = dc * fv[u];
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<float2*>(gp + g * HID) = make_float2(dz[g][0], dz[g][1]);
           } else {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) dz[g] = 0.f;
+            for (int g = 0; g < 4; ++g) dz[g][0] = dz[g][1] = 0.f;
           }
 #pragma unroll
-          for (int g = 0; g < 4; ++g) dzT[(size_t)(g * UPC + j) * MT + 4 * rg + i] = dz[g];
+          for (int g = 0; g < 4; ++g) {
+            dzT[(size_t)(g * UPC + j0) * MT + 4 * rg + i] = dz[g][0];
+            dzT[(size_t)(g * UPC + j0 + 1) * MT + 4 * rg + i] = dz[g][1];
+          }
         }
       }
       __syncthreads();    // dzT complete; every thread of this CTA has consumed its recv values
@@ -423,27 +462,32 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, co
 #pragma unroll
         for (int d = 0; d < CL; ++d) rbar_arrive_release(remote_rfree[d]);           // "my recv may be overwritten"
       }
-      float acc[4][4];
+      // phase 2: partial dh_{t-1}[8 rows][4 k's] = sum_c dz[c][rows] * W[c][k]; packed pairs over rows (FFMA2)
+      float2 a2[4][4];
       if (worker2 && s > 0) {
-        // packed pairs over rows (0,1) and (2,3): one FFMA2 per k and row pair
-        float2 a2[4][2];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) { a2[a][0] = make_float2(0.f, 0.f); a2[a][1] = make_float2(0.f, 0.f); }
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a2[a][i] = make_float2(0.f, 0.f);
         const float* wb = Wc + 4 * kg;
-        const float* zb = dzT + 4 * rg2;
-#pragma unroll 8
+        const float* zb = dzT + 8 * rg2;
+#pragma unroll 4
         for (int c = 0; c < COLS; ++c) {
-          const float4 z = *reinterpret_cast<const float4*>(zb + (size_t)c * MT);
+          const float4 z0 = *reinterpret_cast<const float4*>(zb + (size_t)c * MT);
+          const float4 z1 = *reinterpret_cast<const float4*>(zb + (size_t)c * MT + 4);
           const float4 w = *reinterpret_cast<const float4*>(wb + (size_t)c * HID);
-          const float2 z01 = make_float2(z.x, z.y), z23 = make_float2(z.z, z.w);
-          const float2 w0 = make_float2(w.x, w.x), w1 = make_float2(w.y, w.y), w2 = make_float2(w.z, w.z), w3 = make_float2(w.w, w.w);
-          a2[0][0] = __ffma2_rn(w0, z01, a2[0][0]); a2[0][1] = __ffma2_rn(w0, z23, a2[0][1]);
-          a2[1][0] = __ffma2_rn(w1, z01, a2[1][0]); a2[1][1] = __ffma2_rn(w1, z23, a2[1][1]);
-          a2[2][0] = __ffma2_rn(w2, z01, a2[2][0]); a2[2][1] = __ffma2_rn(w2, z23, a2[2][1]);
-          a2[3][0] = __ffma2_rn(w3, z01, a2[3][0]); a2[3][1] = __ffma2_rn(w3, z23, a2[3][1]);
-        }
+          const float2 z01 = make_float2(z0.x, z0.y), z23 = make_float2(z0.z, z0.w);
+          const float2 z45 = make_float2(z1.x, z1.y), z67 = make_float2(z1.z, z1.w);
+          const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-        for (int a = 0; a < 4; ++a) { acc[a][0] = a2[a][0].x; acc[a][1] = a2[a][0].y; acc[a][2] = a2[a][1].x; acc[a][3] = a2[a][1].y; }
+          for (int a = 0; a < 4; ++a) {
+            const float2 ww = make_float2(wv[a], wv[a]);
+            a2[a][0] = __ffma2_rn(ww, z01, a2[a][0]);
+            a2[a][1] = __ffma2_rn(ww, z23, a2[a][1]);
+            a2[a][2] = __ffma2_rn(ww, z45, a2[a][2]);
+            a2[a][3] = __ffma2_rn(ww, z67, a2[a][3]);
+          }
+        }
       }
       if (s > 0) {
         lbar_wait_cluster(rfree, ph_free);   // every CTA has finished reading its recv -> safe to overwrite
@@ -453,8 +497,9 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, co
           for (int a = 0; a < 4; ++a) {
             int k = 4 * kg + a;
             int owner = k / UPC, kl = k - owner * UPC;
-            const uint32_t o = (uint32_t)((((size_t)rank * UPC + kl) * MT + 4 * rg2) * sizeof(float));
-            st_async_f4(remote_recv[owner] + o, make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]), remote_rfull[owner]);
+            const uint32_t o = (uint32_t)((((size_t)rank * UPC + kl) * MT + 8 * rg2) * sizeof(float));
+            st_async_f4(remote_recv[owner] + o, make_float4(a2[a][0].x, a2[a][0].y, a2[a][1].x, a2[a][1].y), remote_rfull[owner]);
+            st_async_f4(remote_recv[owner] + o + 16, make_float4(a2[a][2].x, a2[a][2].y, a2[a][3].x, a2[a][3].y), remote_rfull[owner]);
           }
         }
       }
@@ -468,8 +513,8 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, co
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef LCfg<200, 4, 32, 2> FwdCfg200;     // 25 unit pairs x 8 row groups = 200 threads, double-buffered h
-typedef LCfg<200, 4, 32, 1> BwdCfg200;     // 50 units x 8 row groups = 400 threads
+typedef LCfg<200, 4, 32, 2, 4> FwdCfg200;  // 8 warps of 4 rows x 25 unit pairs, double-buffered h (8 rows per thread measured slower)
+typedef LCfg<200, 4, 32, 2> BwdCfg200;     // 8 warps: phase 1 (25 unit pairs x 4 rows per warp), phase 2 (8 rows x 4 k's per lane)
 
 template <class C, class K>
 static int launch_cluster(K kernel, size_t smem, int ntiles, cudaStream_t st, void** args, const char* name) {

@@ -163,11 +163,16 @@ def roofline(breakdown, tokens_per_step, batch, root):
     peaks = measured_peaks(root)
     total = sum(v['ms'] for k, v in breakdown.items() if k not in _KERNEL_TAGS)
     if 'tflops' in top:
-        # fp32-parity math on the tensor pipe is kind::tf32 = half the bf16 rate; algorithmic flops
-        peak = peaks['bf16_tflops'] / 2.0
+        # algorithmic flops (the 3 split products count once).  Denominator: the tensor rate of the MMA kind the
+        # kernel issues -- bf16 cuBLAS (measured, sustained) for bf16x3 / bf16, half of it for tf32x3.
+        algo = ops.default_algo()
+        tf32 = (algo == ops.ALGO_TF32X3) and name == 'gemm_tc_kernel'
+        peak = peaks['bf16_tflops'] / (2.0 if tf32 else 1.0)
+        note = '%s bf16 cuBLAS %s TFLOP/s sustained%s; algorithmic flops, split products not counted' % (
+            peaks['source'], peaks['bf16_tflops'], ' x 0.5 (kind::tf32)' if tf32 else '')
         return {'kernel': name, 'bound': 'tensor', 'achieved': top['tflops'], 'peak': peak, 'unit': 'TFLOP/s',
                 'frac': top['tflops'] / peak, 'traffic': None, 'share_of_step': top['ms'] / total,
-                'peak_note': 'tf32 dense = 0.5 x %s bf16 cuBLAS (%s sustained)' % (peaks['source'], peaks['bf16_tflops'])}
+                'gemm_algo': {1: 'simt', 2: 'tf32x3', 3: 'bf16', 4: 'bf16x3'}.get(algo, str(algo)), 'peak_note': note}
     if 'gbs' in top:
         return {'kernel': name, 'bound': 'hbm', 'achieved': top['gbs'], 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                 'frac': top['gbs'] / peaks['hbm_gbs'], 'traffic': None, 'share_of_step': top['ms'] / total,
