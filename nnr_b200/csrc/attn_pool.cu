@@ -60,10 +60,18 @@ __global__ void __launch_bounds__(POOL_THREADS) attn_pool_fwd_kernel(nnr_pool_ar
   }
   __syncthreads();
   for (int d = tid; d < a.D; d += POOL_THREADS) {
-    float acc = 0.f;
+    // four independent partial sums keep four loads in flight; combined in a fixed order
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     const float* x = a.X + (size_t)beg * a.ldx + d;
-    for (int t = 0; t < n; ++t) acc += sc[t] * x[(size_t)t * a.ldx];
-    a.pooled[(size_t)s * a.ldp + d] = acc;
+    int t = 0;
+    for (; t + 4 <= n; t += 4) {
+      a0 += sc[t] * x[(size_t)t * a.ldx];
+      a1 += sc[t + 1] * x[(size_t)(t + 1) * a.ldx];
+      a2 += sc[t + 2] * x[(size_t)(t + 2) * a.ldx];
+      a3 += sc[t + 3] * x[(size_t)(t + 3) * a.ldx];
+    }
+    for (; t < n; ++t) a0 += sc[t] * x[(size_t)t * a.ldx];
+    a.pooled[(size_t)s * a.ldp + d] = (a0 + a1) + (a2 + a3);
   }
 }
 
@@ -105,6 +113,7 @@ __global__ void __launch_bounds__(POOL_THREADS) attn_pool_bwd_kernel(nnr_pool_ar
     const float g = dp[d];
     const float q = (a.mode == 1) ? a.qvec[(size_t)s * a.ldq + d] : 0.f;
     float accq = 0.f;
+#pragma unroll 4
     for (int t = 0; t < n; ++t) {
       const size_t p = (size_t)beg + t;
       float v = al[t] * g;
@@ -118,6 +127,7 @@ __global__ void __launch_bounds__(POOL_THREADS) attn_pool_bwd_kernel(nnr_pool_ar
     for (int k = tid; k < a.A; k += POOL_THREADS) {
       const float wk = a.w2[k];
       float accw = 0.f;
+#pragma unroll 4
       for (int t = 0; t < n; ++t) {
         const size_t p = (size_t)beg + t;
         float u = a.U[p * a.ldu + k];

@@ -18,9 +18,11 @@ __global__ void colsum_stage1(const float* __restrict__ X, int64_t ldx, int M, i
   for (int r = r0; r < r1; ++r) acc += X[(size_t)r * ldx + n];
   part[(size_t)blockIdx.y * N + n] = acc;
 }
-__global__ void colsum_stage2(const float* __restrict__ part, int nparts, int N, float* __restrict__ out, int accumulate) {
+__global__ void colsum_stage2(const float* __restrict__ part, int nparts, int N, int M, const int32_t* __restrict__ m_dev,
+                              float* __restrict__ out, int accumulate) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
+  if (m_dev) nparts = min(nparts, (min(M, *m_dev) + CS_ROWS - 1) / CS_ROWS);   // partials beyond the valid rows are zero
   float acc = 0.f;
   for (int p = 0; p < nparts; ++p) acc += part[(size_t)p * N + n];
   out[n] = accumulate ? out[n] + acc : acc;
@@ -38,7 +40,7 @@ extern "C" int nnr_colsum(const float* X, int64_t ldx, int M, int N, const int32
   dim3 g1((N + 127) / 128, nparts);
   colsum_stage1<<<g1, 128, 0, st>>>(X, ldx, M, N, m_dev, (float*)workspace);
   NNR_LAUNCH_CHECK("colsum_stage1");
-  colsum_stage2<<<(N + 127) / 128, 128, 0, st>>>((const float*)workspace, nparts, N, out, accumulate);
+  colsum_stage2<<<(N + 127) / 128, 128, 0, st>>>((const float*)workspace, nparts, N, M, m_dev, out, accumulate);
   NNR_LAUNCH_CHECK("colsum_stage2");
   return 0;
 }
@@ -170,38 +172,44 @@ __global__ void news_fuse_split_kernel(const float* __restrict__ dout, int D2, i
     else d_b[(size_t)r * D2 + d - D2] = v;
   }
 }
-// one block per table row: the matching news rows are compacted IN ORDER (ballot prefix) into shared
-// memory in chunks of 256, then summed in that order -> deterministic, no atomics
+// one block per table row.  Thread t owns news rows t, t+256, ... (fixed partition), accumulates the matching
+// rows in registers, then the 256 partials are combined by a fixed shuffle tree + fixed warp order:
+// deterministic, no atomics, no serial scan.
+#define NF_MAXE 64
 __global__ void __launch_bounds__(256) news_fuse_table_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ idx,
                                                                   int N, int Dout, int col0, int Edim, int Etot, int eoff,
                                                                   float p, float inv_keep, uint64_t seed,
                                                                   float* __restrict__ dtable, int accumulate) {
-  __shared__ int s_list[256];
-  __shared__ int s_wcnt[8];
+  __shared__ float s_part[8][NF_MAXE];
   const int row = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  float acc = 0.f;
-  for (int base = 0; base < N; base += 256) {
-    int r = base + tid;
-    bool hit = (r < N) && (idx[r] == row);
-    unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) s_wcnt[w] = __popc(m);
-    __syncthreads();
-    int wbase = 0, total = 0;
-    for (int j = 0; j < 8; ++j) { if (j < w) wbase += s_wcnt[j]; total += s_wcnt[j]; }
-    if (hit) s_list[wbase + __popc(m & ((1u << lane) - 1))] = r;
-    __syncthreads();
-    if (tid < Edim) {
-      for (int j = 0; j < total; ++j) {
-        int rr = s_list[j];
-        acc += dout[(size_t)rr * Dout + col0 + tid] * dropout_scale(seed, (uint64_t)rr * Etot + eoff + tid, p, inv_keep);
-      }
+  float acc[NF_MAXE];
+#pragma unroll
+  for (int e = 0; e < NF_MAXE; ++e) acc[e] = 0.f;
+  for (int r = tid; r < N; r += 256) {
+    if (idx[r] == row) {
+      const float* src = dout + (size_t)r * Dout + col0;
+#pragma unroll
+      for (int e = 0; e < NF_MAXE; ++e)
+        if (e < Edim) acc[e] += src[e] * dropout_scale(seed, (uint64_t)r * Etot + eoff + e, p, inv_keep);
     }
-    __syncthreads();
   }
+#pragma unroll
+  for (int e = 0; e < NF_MAXE; ++e) {
+    if (e < Edim) {
+      float v = acc[e];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_part[w][e] = v;
+    }
+  }
+  __syncthreads();
   if (tid < Edim) {
+    float v = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) v += s_part[ww][tid];
     float* d = dtable + (size_t)row * Edim + tid;
-    *d = accumulate ? (*d + acc) : acc;
+    *d = accumulate ? (*d + v) : v;
   }
 }
 extern "C" int nnr_news_fuse_bwd(const float* dout, const int32_t* cat, const int32_t* sub, int N, int D2, int Ec, int Es,
@@ -209,7 +217,7 @@ extern "C" int nnr_news_fuse_bwd(const float* dout, const int32_t* cat, const in
                                  float* dcat_table, float* dsub_table, int accumulate, void* stream) {
   NNR_REQUIRE(dout && cat && sub && d_a && d_b && dcat_table && dsub_table && N > 0, NNR_ERR_ARG,
               "nnr_news_fuse_bwd: bad arguments");
-  NNR_REQUIRE(Ec <= 256 && Es <= 256, NNR_ERR_UNSUPPORTED, "nnr_news_fuse_bwd: embedding dim > 256");
+  NNR_REQUIRE(Ec <= NF_MAXE && Es <= NF_MAXE, NNR_ERR_UNSUPPORTED, "nnr_news_fuse_bwd: embedding dim > %d", NF_MAXE);
   cudaStream_t st = (cudaStream_t)stream;
   int Dout = 2 * D2 + Ec + Es;
   float inv_keep = 1.0f / (1.0f - p_drop);

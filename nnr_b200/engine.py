@@ -98,7 +98,9 @@ def _domain_sorts(len64, domains):
     sorted_idx, desorted_idx = [], []
     for start, count in domains:
         _, si = sort_fn(len64[start:start + count], descending=True)
-        _, di = sort_fn(si, descending=False)
+        # newsEncoders.py:113,115 sort the permutation again to invert it; the inverse of a permutation is
+        # unique, so a scatter gives the identical result without a second radix sort
+        di = torch.empty_like(si).scatter_(0, si, torch.arange(count, device=si.device))
         sorted_idx.append(si + start)
         desorted_idx.append(di)
     return sorted_idx, desorted_idx
