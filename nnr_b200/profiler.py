@@ -155,12 +155,23 @@ def measured_peaks(root):
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1400.0, 'source': 'fallback'}
 
 
+def _ncu_traffic(root, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None"""
+    path = os.path.join(root, 'profiles', 'traffic.json')
+    if not os.path.isfile(path):
+        return None
+    with open(path) as f:
+        entry = json.load(f).get(kernel)
+    return entry['dram_bytes_per_launch'] if entry else None
+
+
 def roofline(breakdown, tokens_per_step, batch, root):
     """roofline entry for the dominant op of the step (largest share of device time)"""
     if not breakdown:
         return None
     name, top = next(iter(breakdown.items()))
     peaks = measured_peaks(root)
+    traffic = _ncu_traffic(root, name)
     total = sum(v['ms'] for k, v in breakdown.items() if k not in _KERNEL_TAGS)
     if 'tflops' in top:
         # algorithmic flops (the 3 split products count once).  Denominator: the tensor rate of the MMA kind the
@@ -171,11 +182,11 @@ def roofline(breakdown, tokens_per_step, batch, root):
         note = '%s bf16 cuBLAS %s TFLOP/s sustained%s; algorithmic flops, split products not counted' % (
             peaks['source'], peaks['bf16_tflops'], ' x 0.5 (kind::tf32)' if tf32 else '')
         return {'kernel': name, 'bound': 'tensor', 'achieved': top['tflops'], 'peak': peak, 'unit': 'TFLOP/s',
-                'frac': top['tflops'] / peak, 'traffic': None, 'share_of_step': top['ms'] / total,
+                'frac': top['tflops'] / peak, 'traffic': traffic, 'share_of_step': top['ms'] / total,
                 'gemm_algo': {1: 'simt', 2: 'tf32x3', 3: 'bf16', 4: 'bf16x3'}.get(algo, str(algo)), 'peak_note': note}
     if 'gbs' in top:
         return {'kernel': name, 'bound': 'hbm', 'achieved': top['gbs'], 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                'frac': top['gbs'] / peaks['hbm_gbs'], 'traffic': None, 'share_of_step': top['ms'] / total,
+                'frac': top['gbs'] / peaks['hbm_gbs'], 'traffic': traffic, 'share_of_step': top['ms'] / total,
                 'peak_note': '%s HBM copy bandwidth' % peaks['source']}
     return {'kernel': name, 'bound': 'hbm', 'achieved': None, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': None,
-            'traffic': None, 'share_of_step': top['ms'] / total}
+            'traffic': traffic, 'share_of_step': top['ms'] / total}
