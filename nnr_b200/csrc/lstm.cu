@@ -22,10 +22,10 @@
 //     (packed-sequence semantics); the reverse direction walks t = len-1 .. 0.
 //   * the input projection gx (a dense GEMM) is computed outside (nnr_gemm); the activated gates
 //     overwrite gx in place as the stash for BPTT, and BPTT overwrites them with dL/dgx.
-#include "common.cuh"
+#include "lstm_common.cuh"
 #include "../../include/nnr_b200.h"
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
+#include <stdlib.h>
+#include <string.h>
 
 template <int HID_, int CL_, int MT_, int UPT_, int RPT_ = 4>   // hidden, cluster size, rows per tile, units / rows per thread
 struct LCfg {
@@ -41,53 +41,6 @@ struct LCfg {
   static constexpr size_t FWD_SMEM = sizeof(float) * ((size_t)HID * COLS + 2 * (size_t)HID * MT) + 3 * MT * sizeof(int);
   static constexpr size_t BWD_SMEM = sizeof(float) * ((size_t)COLS * HID + (size_t)COLS * MT + (size_t)CL * UPC * MT) + 3 * MT * sizeof(int);
 };
-
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-
-// ---- DSMEM producer/consumer primitives: st.async + mbarrier complete_tx instead of barrier.cluster.
-// (barrier.cluster.arrive.release compiles to MEMBAR.ALL.GPU, which makes every step wait for the drain of the
-//  stash stores to global memory; the transaction barrier orders exactly the shared::cluster bytes we exchange.)
-__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void lbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void lbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
-}
-// default (acquire.cta) wait: the complete_tx of st.async makes the bytes visible to the waiter, exactly as for
-// TMA loads; a cluster-scope acquire would add CCTL.IVALL (L1 invalidate) to every step
-__device__ __forceinline__ void lbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "LW_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra LW_DONE;\n"
-      "bra LW_LOOP;\n"
-      "LW_DONE:\n"
-      "}\n" ::"r"(smem_addr_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void rbar_arrive_release(uint32_t remote_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
-}
-__device__ __forceinline__ void st_async_f4(uint32_t remote_addr, float4 v, uint32_t remote_bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_addr),
-               "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)),
-               "r"(remote_bar)
-               : "memory");
-}
-
-// gate non-linearities on the SFU (ex2 + rcp): absolute error ~1e-7, far inside the 1e-4 parity budget
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
 // ------------------------------------------------------------------------------------------------
 // forward
@@ -547,6 +500,20 @@ static int launch_cluster(K kernel, size_t smem, int ntiles, cudaStream_t st, vo
   return 0;
 }
 
+// tensor-core variant (lstm_mma.cu); NNR_LSTM_ALGO=ffma selects the exact-fp32 FFMA kernels of this file
+int nnr_lstm_fwd_mma(float* gx, const float* w_hh, const int32_t* len, const int32_t* off, const int32_t* order, int N,
+                     float* h_out, float* c_stash, float* c_n, int32_t* tile_counters, cudaStream_t st);
+int nnr_lstm_bwd_mma(float* gates, const float* c_stash, const float* w_hh, const int32_t* len, const int32_t* off,
+                     const int32_t* order, int N, const float* dh, const float* dcn, int32_t* tile_counters, cudaStream_t st);
+static bool lstm_use_mma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NNR_LSTM_ALGO");
+    v = (e && !strcmp(e, "ffma")) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 extern "C" int nnr_lstm_fwd(float* gx, const float* w_hh, const int32_t* len, const int32_t* off, const int32_t* order,
                             int N, int L, int H, float* h_out, float* c_stash, float* c_n, int32_t* tile_counters,
                             void* stream) {
@@ -555,6 +522,7 @@ extern "C" int nnr_lstm_fwd(float* gx, const float* w_hh, const int32_t* len, co
   NNR_REQUIRE(H == 200, NNR_ERR_UNSUPPORTED, "nnr_lstm_fwd: hidden_dim %d not instantiated (200 only)", H);
   NNR_REQUIRE(nnr_aligned16(gx) && nnr_aligned16(h_out) && nnr_aligned16(c_stash) && nnr_aligned16(c_n), NNR_ERR_ALIGN,
               "nnr_lstm_fwd: buffers must be 16B aligned");
+  if (lstm_use_mma()) return nnr_lstm_fwd_mma(gx, w_hh, len, off, order, N, h_out, c_stash, c_n, tile_counters, (cudaStream_t)stream);
   typedef FwdCfg200 C;
   int ntiles = (N + C::MT - 1) / C::MT;
   NNR_CUDA(cudaMemsetAsync(tile_counters, 0, 2 * sizeof(int32_t), (cudaStream_t)stream));
@@ -570,6 +538,7 @@ extern "C" int nnr_lstm_bwd(float* gates, const float* c_stash, const float* w_h
   NNR_REQUIRE(H == 200, NNR_ERR_UNSUPPORTED, "nnr_lstm_bwd: hidden_dim %d not instantiated (200 only)", H);
   NNR_REQUIRE(nnr_aligned16(gates) && nnr_aligned16(c_stash) && nnr_aligned16(dh) && nnr_aligned16(dcn), NNR_ERR_ALIGN,
               "nnr_lstm_bwd: buffers must be 16B aligned");
+  if (lstm_use_mma()) return nnr_lstm_bwd_mma(gates, c_stash, w_hh, len, off, order, N, dh, dcn, tile_counters, (cudaStream_t)stream);
   typedef BwdCfg200 C;
   int ntiles = (N + C::MT - 1) / C::MT;
   NNR_CUDA(cudaMemsetAsync(tile_counters, 0, 2 * sizeof(int32_t), (cudaStream_t)stream));

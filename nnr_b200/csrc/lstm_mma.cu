@@ -1,0 +1,866 @@
+// Tensor-core variant of the persistent bidirectional LSTM kernels (forward and BPTT) for H = 200.
+// Same interface, data layout and stash protocol as lstm.cu; replaces cuDNN's RNN behind nn.LSTM at
+// newsEncoders.py:66-67,119-127.
+//
+// What changes against the FFMA kernels of lstm.cu:
+//   * the recurrent product of a time step -- [32 rows x 200] x [200 x 4*units] -- runs on the tensor cores
+//     (mma.sync m16n8k16, fp32 accumulate) with SPLIT operands: x = hi + lo in 16-bit, and
+//     x*y ~= hi*hi + hi*lo + lo*hi (3 MMAs).  Forward splits h and W_hh in fp16 (|h| < 1: 22 mantissa bits
+//     survive), BPTT splits d(pre-activations) and W_hh in bf16 (gradients need the fp32 exponent range;
+//     16 mantissa bits, same grade as the bf16x3 GEMMs the gradients flow through next).
+//   * a cluster is FIVE CTAs of 40 hidden units (160 gate columns): 40 units = 4 warps x 10 units = 4 x 5 n8 tiles,
+//     so each of the four SM sub-partitions runs one warp with a 32 x 40 accumulator tile, and the operands
+//     (W slice 2 x 69 KB, h tile) fit shared memory with conflict-free ldmatrix pitches.
+//   * the n8 tile column order is (gate, unit) = 2g + u for two units, so after a 4x4 shuffle transpose inside
+//     each lane quad every lane owns ONE row and TEN consecutive units with all four gates: the point-wise LSTM
+//     cell, the stash stores (32 B aligned runs) and the h broadcast (16 B chunks of the next step's A operand)
+//     need no shared-memory staging.
+//   * the K order of the h operand is a permutation of the units (the W slice is permuted identically when it
+//     is loaded), chosen so that each lane's ten units land in one 16 B chunk + one 4 B chunk of the peers' tiles.
+// The exchange protocol (st.async + mbarrier transaction counts, double-buffered h, rfull/rfree in BPTT), the
+// longest-first dynamic tile scheduling and the packed-sequence semantics are those of lstm.cu.
+#include "lstm_common.cuh"
+#include "../../include/nnr_b200.h"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+// optional in-kernel phase timing (clock64 of one lane of CTA 0), compiled in with -DNNR_LSTM_PROF
+#ifdef NNR_LSTM_PROF
+__device__ unsigned long long g_lstm_prof[16];
+#define PROF_DECL unsigned long long pt0 = clock64(), pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const bool prof_on = (blockIdx.x == 0 && threadIdx.x == 0);
+#define PROF_MARK(i) { unsigned long long t_ = clock64(); pacc[i] += t_ - pt0; pt0 = t_; }
+#define PROF_FLUSH(base) if (prof_on) { for (int i_ = 0; i_ < 8; ++i_) g_lstm_prof[base + i_] = pacc[i_]; }
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#define PROF_FLUSH(base)
+#endif
+
+namespace {
+
+struct G {
+  static constexpr int HID = 200, CL = 5, MT = 32, UPC = 40, COLS = 160, CT = 128, NT = 256, UPW = 10, NTW = 5;   // CT compute + 128 copy threads
+  // forward: A = h [32][K=208 (200 + zero pad)], B = W slice [160 cols][208]; pitch 432 B -> ldmatrix conflict free
+  static constexpr int FK = 208, FKS = 13, FPITCH = 432;
+  // h tile = [source CTA j][plane hi/lo][32 rows][40 slots = 80 B]: the slice a CTA produces is ONE contiguous 5120 B
+  // block (a single cp.async.bulk per peer); row pitch 80 B keeps ldmatrix conflict free.  A 16 B zero chunk pads K.
+  static constexpr int F_W_PLANE = COLS * FPITCH, F_HROW = 80, F_HPLANE = MT * F_HROW, F_HBLK = 2 * F_HPLANE, F_HBUF = CL * F_HBLK;
+  // staging tile for coalesced global traffic: [array][32 rows][40 units fp32 + 16 B pad]; the CTA's 128 threads move
+  // it to / from global memory in 16 B pieces (a row segment = 160 contiguous bytes), the owners access it per row
+  static constexpr int SROW = 176, SARR = MT * SROW, SCHUNKS = MT * 10;   // 10 x 16 B chunks per row segment
+  static constexpr int F_NARR = 6;                       // i, f, g, o (gx in, activated gates out), c, h
+  static constexpr size_t FWD_SMEM = 2 * (size_t)F_W_PLANE + 2 * (size_t)F_HBUF + 16 + F_NARR * (size_t)SARR + 3 * MT * sizeof(int);
+  static constexpr uint32_t F_TX = (CL - 1) * F_HBLK;    // bytes the peers copy into one CTA's next h tile per step
+  // backward: A = dz [32][K'=160], B = W slice^T [200 units][160]; recv = partial dh from every CTA
+  // ([source CTA][32 rows][40 units] fp32 = 5120 B blocks: one bulk copy each) and the staging tile of the same shape
+  // the partials are copied from.  The W slice is XOR-swizzled (16 B chunk ^= (row >> 1) & 3) instead of padded.
+  static constexpr int BK = 160, BKS = 10, BPITCH = 336, BWPITCH = 320, RPITCH = UPC * 4;
+  static constexpr int B_W_PLANE = HID * BWPITCH, B_Z_PLANE = MT * BPITCH, B_RBLK = MT * RPITCH, B_RECV = CL * B_RBLK;
+  static constexpr int B_NARR = 5;                       // i, f, g, o (stash in, dz out), dh
+  static constexpr size_t BWD_SMEM = 2 * (size_t)B_W_PLANE + 2 * (size_t)B_Z_PLANE + 2 * (size_t)B_RECV + B_NARR * (size_t)SARR + 3 * MT * sizeof(int);
+  static constexpr uint32_t B_TX = CL * B_RBLK;
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+template <bool F16>
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (F16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (a, b) -> packed 16-bit pairs hi, lo with a ~= hi.x + lo.x, b ~= hi.y + lo.y (a at the lower address)
+template <bool F16>
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  if (F16) {
+    __half2 h = __floats2half2_rn(a, b);
+    float2 f = __half22float2(h);
+    __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+  } else {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    float2 f = __bfloat1622float2(h);
+    __nv_bfloat162 l = __floats2bfloat162_rn(a - f.x, b - f.y);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+  }
+}
+template <bool F16>
+__device__ __forceinline__ void split1(float a, uint16_t& hi, uint16_t& lo) {
+  uint32_t h, l;
+  split2<F16>(a, 0.f, h, l);
+  hi = (uint16_t)(h & 0xffffu);
+  lo = (uint16_t)(l & 0xffffu);
+}
+
+// local shared memory -> a peer CTA's shared memory through the bulk-copy engine; the bytes are counted on the
+// destination's transaction barrier.  (Thousands of 4-16 B st.async packets per step were measured to cost ~10 us:
+// DSMEM wants few, large, contiguous transfers.)
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes, uint32_t remote_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster_addr),
+               "r"(src_cta_addr), "r"(bytes), "r"(remote_bar)
+               : "memory");
+}
+// named barriers: 1 = the four compute warps; 2 = "staging tile written" (compute arrives, copy waits);
+// 3 = "staging tile loaded" (copy arrives, compute waits)
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 4x4 transpose of float2 blocks inside a lane quad: on return lane q holds in X[s] what lane s held in X[q]
+__device__ __forceinline__ void quad_transpose(float2 (&X)[4], int q) {
+  {
+    const bool odd = q & 1;
+    float2 s0 = odd ? X[0] : X[1], s1 = odd ? X[2] : X[3];
+    float2 r0, r1;
+    r0.x = __shfl_xor_sync(0xffffffffu, s0.x, 1); r0.y = __shfl_xor_sync(0xffffffffu, s0.y, 1);
+    r1.x = __shfl_xor_sync(0xffffffffu, s1.x, 1); r1.y = __shfl_xor_sync(0xffffffffu, s1.y, 1);
+    if (odd) { X[0] = r0; X[2] = r1; } else { X[1] = r0; X[3] = r1; }
+  }
+  {
+    const bool up = q & 2;
+    float2 s0 = up ? X[0] : X[2], s1 = up ? X[1] : X[3];
+    float2 r0, r1;
+    r0.x = __shfl_xor_sync(0xffffffffu, s0.x, 2); r0.y = __shfl_xor_sync(0xffffffffu, s0.y, 2);
+    r1.x = __shfl_xor_sync(0xffffffffu, s1.x, 2); r1.y = __shfl_xor_sync(0xffffffffu, s1.y, 2);
+    if (up) { X[0] = r0; X[1] = r1; } else { X[2] = r0; X[3] = r1; }
+  }
+}
+
+// forward K order: slot -> hidden unit.  CTA j owns slots 40j .. 40j+39: warp w's first 8 units at 40j + 8w .. +7 (one
+// 16 B chunk), its last 2 at 40j + 32 + 2w, +1
+__device__ __forceinline__ int fwd_slot_unit(int kk) {
+  const int j = kk / 40, rem = kk - 40 * j;
+  if (rem < 32) return 40 * j + 10 * (rem >> 3) + (rem & 7);
+  const int t = rem - 32;
+  return 40 * j + 10 * (t >> 1) + 8 + (t & 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(G::NT, 1)
+lstm_fwd_mma_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const int32_t* __restrict__ len,
+                    const int32_t* __restrict__ off, const int32_t* __restrict__ order, int N, int ntiles,
+                    float* __restrict__ h_out, float* __restrict__ c_stash, float* __restrict__ c_n, int* __restrict__ tile_counter) {
+  constexpr int HID = G::HID, CL = G::CL, MT = G::MT, UPC = G::UPC, COLS = G::COLS, NTW = G::NTW, UPW = G::UPW;
+  constexpr int PITCH = G::FPITCH;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* Wsm = smem_raw;                                   // [2 planes][COLS][PITCH]
+  unsigned char* Hsm = smem_raw + 2 * G::F_W_PLANE;                // [2 buffers][CL blocks][2 planes][MT][80 B]
+  unsigned char* Zero16 = Hsm + 2 * G::F_HBUF;                     // the K pad chunk
+  unsigned char* Stg = Zero16 + 16;                                // [F_NARR][MT][SROW] staging tile
+  int* s_row = reinterpret_cast<int*>(Stg + G::F_NARR * G::SARR);
+  int* s_len = s_row + MT;
+  int* s_off = s_len + MT;
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cluster_id = blockIdx.x / CL;
+  const int dir = cluster_id & 1;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int q = lane & 3, r8 = lane >> 2;
+  const int R = r8 + 8 * q;                     // the tile row this lane owns in the point-wise phase
+  const int unit0 = rank * UPC + w * UPW;       // first of the lane's ten hidden units
+
+  // W slice -> smem as fp16 hi / lo planes, rows = gate columns in (warp, n-tile, gate, unit) order, K permuted
+  {
+    const float* W = w_hh + (size_t)dir * 4 * HID * HID;
+    for (int idx = tid; idx < COLS * G::FK; idx += G::NT) {
+      const int n = idx / G::FK, kk = idx - n * G::FK;
+      const int ww = n / 40, rem = n - ww * 40, nt = rem >> 3, c = rem & 7, g = c >> 1, u = c & 1;
+      float v = 0.f;
+      if (kk < HID) v = W[(size_t)(g * HID + rank * UPC + ww * UPW + 2 * nt + u) * HID + fwd_slot_unit(kk)];
+      uint16_t hi, lo;
+      split1<true>(v, hi, lo);
+      *reinterpret_cast<uint16_t*>(Wsm + (size_t)n * PITCH + kk * 2) = hi;
+      *reinterpret_cast<uint16_t*>(Wsm + G::F_W_PLANE + (size_t)n * PITCH + kk * 2) = lo;
+    }
+    for (int idx = tid; idx < (2 * G::F_HBUF + 16) / 16; idx += G::NT) reinterpret_cast<uint4*>(Hsm)[idx] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __shared__ __align__(8) uint64_t hfull[2];        // "all of h for the next step has landed in buffer b"
+  __shared__ int s_tile;
+  const uint32_t h_local = smem_addr_u32(Hsm), w_local = smem_addr_u32(Wsm), bar_local = smem_addr_u32(&hfull[0]);
+  if (tid == 0) {
+    lbar_init(&hfull[0], 1);
+    lbar_init(&hfull[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t hph[2] = {0u, 0u};
+  const size_t GS = (size_t)2 * 4 * HID;
+  PROF_DECL
+
+  // per-lane fragment offsets (bytes)
+  const uint32_t a_row = (uint32_t)((lane & 15) * G::F_HROW);   // A: lanes 0-15 address k chunk 2ks, lanes 16-31 chunk 2ks+1
+  const bool a_hi = (lane >> 4) != 0;
+  const uint32_t zero_local = smem_addr_u32(Zero16), stg_local = smem_addr_u32(Stg);
+  const bool copy_role = w >= 4;                                 // warps 4-7 move the staging tile to / from global memory
+  const int c_ch = tid & 15, c_rs = (tid - G::CT) >> 4;          // cooperative copy: chunk and row slot of a copy thread
+  const uint32_t c_so = (uint32_t)(c_rs * G::SROW + c_ch * 16);  // its offset inside an array of the staging tile
+  const uint32_t b_off = (uint32_t)((w * 40 + (lane >> 4) * 8 + (lane & 7)) * PITCH + ((lane >> 3) & 1) * 16);
+  const uint32_t b_off4 = (uint32_t)((w * 40 + 32 + (lane & 7)) * PITCH + ((lane >> 3) & 1) * 16);
+  // where this lane's h values go inside this CTA's block of an h tile (plane 0; plane 1 is F_HPLANE further)
+  const uint32_t stage_v4 = (uint32_t)(rank * G::F_HBLK + R * G::F_HROW + w * 16);
+  const uint32_t stage_b32 = (uint32_t)(rank * G::F_HBLK + R * G::F_HROW + 64 + w * 4);
+
+  for (;;) {
+    if (rank == 0 && tid == 0) {
+      int t = atomicAdd(&tile_counter[dir], 1);
+#pragma unroll
+      for (int d = 0; d < CL; ++d) *cluster.map_shared_rank(&s_tile, d) = t;
+    }
+    cluster_arrive();
+    cluster_wait();
+    const int tile = s_tile;
+    if (tile >= ntiles) break;
+    __syncthreads();
+    if (tid < MT) {
+      int i = tile * MT + tid;
+      int rr = (i < N) ? order[i] : -1;
+      s_row[tid] = rr;
+      s_len[tid] = (rr >= 0) ? len[rr] : 0;
+      s_off[tid] = (rr >= 0) ? off[rr] : 0;
+    }
+    for (int idx = tid; idx < G::F_HBUF / 16; idx += G::NT) reinterpret_cast<uint4*>(Hsm)[idx] = make_uint4(0u, 0u, 0u, 0u);  // h_0 = 0
+    __syncthreads();
+    int maxlen = 0;
+    for (int i = 0; i < MT; ++i) maxlen = max(maxlen, s_len[i]);
+    const int rlen = s_len[R], roff = s_off[R], rrow = s_row[R];
+
+    if (copy_role) {
+      // ---- copy warps: coalesced traffic between the staging tile and global memory, off the compute warps' critical
+      // path.  Thread t moves the 16 B chunk ch = t & 15 (10 of 16 lanes active) of the 160 B row segments of rows
+      // (t >> 4) + 8 rr, rr = 0..3, of every array.
+      int c_len[4], c_off[4];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) { c_len[rr] = s_len[c_rs + 8 * rr]; c_off[rr] = s_off[c_rs + 8 * rr]; }
+      if (c_ch < 10) {                    // gx of step 0
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          if (0 < c_len[rr]) {
+            const int t = dir ? (c_len[rr] - 1) : 0;
+            const float* g1 = gx + ((size_t)c_off[rr] + t) * GS + (size_t)dir * 4 * HID + rank * UPC + c_ch * 4;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) cp_async16(stg_local + c_so + rr * 8 * G::SROW + a * G::SARR, g1 + a * HID);
+          }
+        }
+      }
+      cp_async_commit();
+      cp_async_wait_all();
+      bar_arrive(3, G::NT);
+      for (int s = 0; s < maxlen; ++s) {
+        bar_sync(2, G::NT);              // the staging tile holds the stash of step s
+        if (c_ch < 10) {
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const int rl = c_len[rr];
+            if (s < rl) {
+              const int t = dir ? (rl - 1 - s) : s;
+              const size_t p = (size_t)c_off[rr] + t;
+              const unsigned char* sp = Stg + c_so + rr * 8 * G::SROW;
+              float* g0 = gx + p * GS + (size_t)dir * 4 * HID + rank * UPC + c_ch * 4;
+#pragma unroll
+              for (int a = 0; a < 4; ++a) *reinterpret_cast<float4*>(g0 + a * HID) = *reinterpret_cast<const float4*>(sp + a * G::SARR);
+              const float4 cv = *reinterpret_cast<const float4*>(sp + 4 * G::SARR);
+              *reinterpret_cast<float4*>(c_stash + (p * 2 + dir) * HID + rank * UPC + c_ch * 4) = cv;
+              *reinterpret_cast<float4*>(h_out + p * 2 * HID + (size_t)dir * HID + rank * UPC + c_ch * 4) =
+                  *reinterpret_cast<const float4*>(sp + 5 * G::SARR);
+              if (s == rl - 1)
+                *reinterpret_cast<float4*>(c_n + (size_t)s_row[c_rs + 8 * rr] * 2 * HID + (size_t)dir * HID + rank * UPC + c_ch * 4) = cv;
+              if (s + 1 < rl) {            // the row's next token is the adjacent one
+                const float* g1 = dir ? g0 - GS : g0 + GS;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) cp_async16(stg_local + c_so + rr * 8 * G::SROW + a * G::SARR, g1 + a * HID);
+              }
+            }
+          }
+        }
+        if (s + 1 < maxlen) {
+          cp_async_commit();
+          cp_async_wait_all();
+          bar_arrive(3, G::NT);          // gx of step s+1 is in the staging tile
+        }
+      }
+      continue;
+    }
+
+    // ---- compute warps ---------------------------------------------------------------------------------------------
+    float cst[UPW], hst[UPW];
+#pragma unroll
+    for (int i = 0; i < UPW; ++i) cst[i] = hst[i] = 0.f;
+
+    for (int s = 0; s < maxlen; ++s) {
+      const int cur = s & 1, nxt = cur ^ 1;
+      PROF_MARK(5)
+      if (tid == 0 && s + 1 < maxlen) lbar_expect_tx(&hfull[nxt], G::F_TX);
+      if (s > 0) { lbar_wait_cluster(&hfull[cur], hph[cur]); hph[cur] ^= 1u; }
+      PROF_MARK(0)
+
+      // ---- recurrent product on the tensor cores: acc[mt][nt] (16 x 8) += h_tile x W_slice^T --------------
+      float acc[2][NTW][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+      const uint32_t hA = h_local + (uint32_t)(cur * G::F_HBUF) + a_row;
+      // fragments of k-step ks+1 are loaded before the MMAs of k-step ks are issued (register double buffer);
+      // consecutive MMAs on one accumulator are ten instructions apart
+      struct Frag { uint32_t ah[2][4], al[2][4], bh[NTW][2], bl[NTW][2]; };
+      auto load_frags = [&](Frag& f, int ks) {
+        // k chunks 2ks and 2ks+1 of the global slot order: chunk c lives in block c / 5 at 16 B offset c % 5
+        const int c0 = 2 * ks, c1 = 2 * ks + 1;
+        const uint32_t o0 = (uint32_t)((c0 / 5) * G::F_HBLK + (c0 % 5) * 16), o1 = (uint32_t)((c1 / 5) * G::F_HBLK + (c1 % 5) * 16);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          uint32_t ad_h, ad_l;
+          if (c1 < 25) {
+            ad_h = hA + mt * 16 * G::F_HROW + (a_hi ? o1 : o0);
+            ad_l = ad_h + G::F_HPLANE;
+          } else {                      // K pad: the upper chunk reads zeros
+            ad_h = a_hi ? zero_local : hA + mt * 16 * G::F_HROW + o0;
+            ad_l = a_hi ? zero_local : ad_h + G::F_HPLANE;
+          }
+          ldsm_x4(ad_h, f.ah[mt][0], f.ah[mt][1], f.ah[mt][2], f.ah[mt][3]);
+          ldsm_x4(ad_l, f.al[mt][0], f.al[mt][1], f.al[mt][2], f.al[mt][3]);
+        }
+        ldsm_x4(w_local + b_off + ks * 32, f.bh[0][0], f.bh[0][1], f.bh[1][0], f.bh[1][1]);
+        ldsm_x4(w_local + b_off + 16 * PITCH + ks * 32, f.bh[2][0], f.bh[2][1], f.bh[3][0], f.bh[3][1]);
+        ldsm_x2(w_local + b_off4 + ks * 32, f.bh[4][0], f.bh[4][1]);
+        ldsm_x4(w_local + G::F_W_PLANE + b_off + ks * 32, f.bl[0][0], f.bl[0][1], f.bl[1][0], f.bl[1][1]);
+        ldsm_x4(w_local + G::F_W_PLANE + b_off + 16 * PITCH + ks * 32, f.bl[2][0], f.bl[2][1], f.bl[3][0], f.bl[3][1]);
+        ldsm_x2(w_local + G::F_W_PLANE + b_off4 + ks * 32, f.bl[4][0], f.bl[4][1]);
+      };
+      auto mma_all = [&](const Frag& f) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NTW; ++nt) mma16816<true>(acc[mt][nt], f.al[mt], f.bh[nt][0], f.bh[nt][1]);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NTW; ++nt) mma16816<true>(acc[mt][nt], f.ah[mt], f.bl[nt][0], f.bl[nt][1]);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NTW; ++nt) mma16816<true>(acc[mt][nt], f.ah[mt], f.bh[nt][0], f.bh[nt][1]);
+      };
+      {
+        Frag f0, f1;
+        load_frags(f0, 0);
+#pragma unroll
+        for (int ks = 0; ks < G::FKS; ks += 2) {
+          if (ks + 1 < G::FKS) load_frags(f1, ks + 1);
+          mma_all(f0);
+          if (ks + 1 < G::FKS) {
+            if (ks + 2 < G::FKS) load_frags(f0, ks + 2);
+            mma_all(f1);
+          }
+        }
+      }
+
+      PROF_MARK(1)
+      // ---- quad transpose: lane (r8, q) ends with row R = r8 + 8q, gates x 10 units -------------------------
+      float2 pre[NTW][4];
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt) {
+        float2 X[4] = {make_float2(acc[0][nt][0], acc[0][nt][1]), make_float2(acc[0][nt][2], acc[0][nt][3]),
+                       make_float2(acc[1][nt][0], acc[1][nt][1]), make_float2(acc[1][nt][2], acc[1][nt][3])};
+        quad_transpose(X, q);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) pre[nt][g] = X[g];
+      }
+
+      // ---- LSTM cell on the lane's row: gx comes from the staging tile, the stash goes back into it --------------
+      bar_sync(3, G::NT);            // the copy warps have stored step s-1 and fetched gx of step s
+      if (s < rlen) {
+        unsigned char* sp = Stg + R * G::SROW + w * (UPW * 4);
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt) {
+          float2* gi = reinterpret_cast<float2*>(sp + 0 * G::SARR + nt * 8);
+          float2* gf = reinterpret_cast<float2*>(sp + 1 * G::SARR + nt * 8);
+          float2* gg_ = reinterpret_cast<float2*>(sp + 2 * G::SARR + nt * 8);
+          float2* go = reinterpret_cast<float2*>(sp + 3 * G::SARR + nt * 8);
+          const float2 xi = *gi, xf = *gf, xg = *gg_, xo = *go;
+          float ig[2], fg[2], gg[2], og[2];
+          const float zi[2] = {pre[nt][0].x + xi.x, pre[nt][0].y + xi.y};
+          const float zf[2] = {pre[nt][1].x + xf.x, pre[nt][1].y + xf.y};
+          const float zg[2] = {pre[nt][2].x + xg.x, pre[nt][2].y + xg.y};
+          const float zo[2] = {pre[nt][3].x + xo.x, pre[nt][3].y + xo.y};
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            ig[u] = fast_sigmoid(zi[u]);
+            fg[u] = fast_sigmoid(zf[u]);
+            gg[u] = fast_tanh(zg[u]);
+            og[u] = fast_sigmoid(zo[u]);
+            cst[2 * nt + u] = fg[u] * cst[2 * nt + u] + ig[u] * gg[u];
+            hst[2 * nt + u] = og[u] * fast_tanh(cst[2 * nt + u]);
+          }
+          *gi = make_float2(ig[0], ig[1]);
+          *gf = make_float2(fg[0], fg[1]);
+          *gg_ = make_float2(gg[0], gg[1]);
+          *go = make_float2(og[0], og[1]);
+          *reinterpret_cast<float2*>(sp + 4 * G::SARR + nt * 8) = make_float2(cst[2 * nt], cst[2 * nt + 1]);
+          *reinterpret_cast<float2*>(sp + 5 * G::SARR + nt * 8) = make_float2(hst[2 * nt], hst[2 * nt + 1]);
+        }
+      }
+      PROF_MARK(2)
+      // ---- the lane's ten h values (fp16 hi / lo) go into this CTA's block of the next tile; one bulk copy per peer
+      if (s + 1 < maxlen) {
+        uint32_t hi[NTW], lo[NTW];
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt) split2<true>(hst[2 * nt], hst[2 * nt + 1], hi[nt], lo[nt]);
+        unsigned char* blk = Hsm + (size_t)nxt * G::F_HBUF;
+        *reinterpret_cast<uint4*>(blk + stage_v4) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint32_t*>(blk + stage_b32) = hi[4];
+        *reinterpret_cast<uint4*>(blk + G::F_HPLANE + stage_v4) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint32_t*>(blk + G::F_HPLANE + stage_b32) = lo[4];
+      }
+      bar_sync(1, G::CT);              // the CTA's h block is complete
+      if (s + 1 < maxlen && tid == 0) {
+        fence_proxy_async_smem();
+        const uint32_t src = h_local + (uint32_t)(nxt * G::F_HBUF + rank * G::F_HBLK);
+        const uint32_t bar = bar_local + nxt * 8;
+#pragma unroll
+        for (int d = 1; d < CL; ++d) {
+          const int peer = (rank + d) % CL;
+          bulk_copy_to_peer(mapa_u32(src, peer), src, G::F_HBLK, mapa_u32(bar, peer));
+        }
+      }
+      bar_arrive(2, G::NT);            // hand the staging tile (stash of step s) to the copy warps
+      PROF_MARK(3)
+    }
+  }
+  PROF_FLUSH(0)
+  cluster_arrive();
+  cluster_wait();
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward through time
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(G::NT, 1)
+lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, const float* __restrict__ w_hh,
+                    const int32_t* __restrict__ len, const int32_t* __restrict__ off, const int32_t* __restrict__ order,
+                    int N, int ntiles, const float* __restrict__ dh, const float* __restrict__ dcn, int* __restrict__ tile_counter) {
+  constexpr int HID = G::HID, CL = G::CL, MT = G::MT, UPC = G::UPC, UPW = G::UPW, NTW = G::NTW;
+  constexpr int PITCH = G::BPITCH, WP = G::BWPITCH, RP = G::RPITCH;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* Wsm = smem_raw;                                   // [2 planes][HID units][WP] swizzled  (B operand)
+  unsigned char* Zsm = Wsm + 2 * G::B_W_PLANE;                     // [2 planes][MT][PITCH]          (A operand: dz)
+  unsigned char* Rsm = Zsm + 2 * G::B_Z_PLANE;                     // [CL sources][MT][40] fp32 partial dh from each CTA
+  unsigned char* Ssm = Rsm + G::B_RECV;                            // [CL owners][MT][40]  fp32 partials staged for the bulk copies
+  unsigned char* Stg = Ssm + G::B_RECV;                            // [B_NARR][MT][SROW] staging tile
+  int* s_row = reinterpret_cast<int*>(Stg + G::B_NARR * G::SARR);
+  int* s_len = s_row + MT;
+  int* s_off = s_len + MT;
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cluster_id = blockIdx.x / CL;
+  const int dir = cluster_id & 1;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int q = lane & 3, r8 = lane >> 2;
+  const int R = r8 + 8 * q;
+  const int unit0 = rank * UPC + w * UPW;
+
+  // W slice -> smem (bf16 hi / lo): row n = hidden unit k of the OUTPUT dh, column kk = own gate column in
+  // (warp, gate, unit) order -- the order phase 1 writes dz in
+  {
+    const float* W = w_hh + (size_t)dir * 4 * HID * HID;
+    for (int idx = tid; idx < G::BK * HID; idx += G::NT) {
+      const int kk = idx / HID, n = idx - kk * HID;
+      const int ww = kk / 40, rem = kk - ww * 40, g = rem / UPW, i = rem - g * UPW;
+      const float v = W[(size_t)(g * HID + rank * UPC + ww * UPW + i) * HID + n];
+      uint16_t hi, lo;
+      split1<false>(v, hi, lo);
+      const size_t o = (size_t)n * WP + (((kk >> 3) ^ ((n >> 1) & 3)) << 4) + (kk & 7) * 2;
+      *reinterpret_cast<uint16_t*>(Wsm + o) = hi;
+      *reinterpret_cast<uint16_t*>(Wsm + G::B_W_PLANE + o) = lo;
+    }
+  }
+  __shared__ __align__(8) uint64_t rbar[2];
+  __shared__ int s_tile;
+  uint64_t* rfull = &rbar[0];      // the CL partial slices for the next iteration have landed in my recv
+  uint64_t* rfree = &rbar[1];      // every CTA of the cluster has consumed ITS recv (CL arrivals)
+  const uint32_t w_local = smem_addr_u32(Wsm), z_local = smem_addr_u32(Zsm), r_local = smem_addr_u32(Rsm), s_local = smem_addr_u32(Ssm);
+  const uint32_t stg_local = smem_addr_u32(Stg);
+  const uint32_t rfull_local = smem_addr_u32(rfull), rfree_local = smem_addr_u32(rfree);
+  if (tid == 0) {
+    lbar_init(rfull, 1);
+    lbar_init(rfree, CL);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t ph_full = 0u, ph_free = 0u;
+  const size_t GS = (size_t)2 * 4 * HID;
+  PROF_DECL
+
+  // phase 2 tiling: 25 n8 tiles of output units over 4 warps: 7, 6, 6, 6
+  const int nt0 = w * 6 + (w > 0 ? 1 : 0);
+  const bool seven = (w == 0);
+  const uint32_t a_off = (uint32_t)((lane & 15) * PITCH + (lane >> 4) * 16);
+  // B: row = n-tile row (lane & 7), logical chunk 2ks + kh, physical chunk = logical ^ ((row >> 1) & 3)
+  const uint32_t b_row = (uint32_t)(((nt0 + (lane >> 4)) * 8 + (lane & 7)) * WP);
+  const uint32_t b_row6 = (uint32_t)(((nt0 + 6) * 8 + (lane & 7)) * WP);
+  const uint32_t b_kh = (uint32_t)((lane >> 3) & 1), b_x = (uint32_t)((lane & 7) >> 1);
+  const bool copy_role = w >= 4;                                 // warps 4-7 move the staging tile to / from global memory
+  const int c_ch = tid & 15, c_rs = (tid - G::CT) >> 4;
+  const uint32_t c_so = (uint32_t)(c_rs * G::SROW + c_ch * 16);
+  const bool leader = (tid == 96);                               // barrier / copy-engine duties (a warp with six n-tiles)
+
+  for (;;) {
+    if (rank == 0 && tid == 0) {
+      int t = atomicAdd(&tile_counter[dir], 1);
+#pragma unroll
+      for (int d = 0; d < CL; ++d) *cluster.map_shared_rank(&s_tile, d) = t;
+    }
+    cluster_arrive();
+    cluster_wait();
+    const int tile = s_tile;
+    if (tile >= ntiles) break;
+    __syncthreads();
+    if (tid < MT) {
+      int i = tile * MT + tid;
+      int rr = (i < N) ? order[i] : -1;
+      s_row[tid] = rr;
+      s_len[tid] = (rr >= 0) ? len[rr] : 0;
+      s_off[tid] = (rr >= 0) ? off[rr] : 0;
+    }
+    __syncthreads();
+    int maxlen = 0;
+    for (int i = 0; i < MT; ++i) maxlen = max(maxlen, s_len[i]);
+    const int rlen = s_len[R], roff = s_off[R], rrow = s_row[R];
+    if (copy_role) {
+      // ---- copy warps: the activated gates and dh of iteration s-1 come into the staging tile, dL/dgx of iteration s
+      // goes out, with the same chunk mapping as the forward kernel
+      int c_len[4], c_off[4];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) { c_len[rr] = s_len[c_rs + 8 * rr]; c_off[rr] = s_off[c_rs + 8 * rr]; }
+      auto prefetch_stash = [&](int s1) {
+        if (c_ch < 10) {
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            if (s1 < c_len[rr]) {
+              const int t = dir ? (c_len[rr] - 1 - s1) : s1;
+              const size_t p = (size_t)c_off[rr] + t;
+              const float* g1 = gates + p * GS + (size_t)dir * 4 * HID + rank * UPC + c_ch * 4;
+#pragma unroll
+              for (int a = 0; a < 4; ++a) cp_async16(stg_local + c_so + rr * 8 * G::SROW + a * G::SARR, g1 + a * HID);
+              cp_async16(stg_local + c_so + rr * 8 * G::SROW + 4 * G::SARR, dh + p * 2 * HID + (size_t)dir * HID + rank * UPC + c_ch * 4);
+            }
+          }
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+        bar_arrive(3, G::NT);
+      };
+      prefetch_stash(maxlen - 1);
+      for (int s = maxlen - 1; s >= 0; --s) {
+        bar_sync(2, G::NT);              // the staging tile holds dL/dgx of iteration s
+        if (c_ch < 10) {
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            if (s < c_len[rr]) {
+              const int t = dir ? (c_len[rr] - 1 - s) : s;
+              const size_t p = (size_t)c_off[rr] + t;
+              const unsigned char* spc = Stg + c_so + rr * 8 * G::SROW;
+              float* g0 = gates + p * GS + (size_t)dir * 4 * HID + rank * UPC + c_ch * 4;
+#pragma unroll
+              for (int a = 0; a < 4; ++a) *reinterpret_cast<float4*>(g0 + a * HID) = *reinterpret_cast<const float4*>(spc + a * G::SARR);
+            }
+          }
+        }
+        if (s > 0) prefetch_stash(s - 1);
+      }
+      continue;
+    }
+
+    // ---- compute warps ---------------------------------------------------------------------------------------------
+    float dcc[UPW];       // dL/dc carried to the previous step
+    float2 ccur[NTW];     // c_t of the current iteration (= the c_{t-1} read one iteration earlier)
+#pragma unroll
+    for (int i = 0; i < UPW; ++i) dcc[i] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) ccur[nt] = make_float2(0.f, 0.f);
+
+    for (int s = maxlen - 1; s >= 0; --s) {
+      PROF_MARK(5)
+      // c_{t-1} of this lane's row and units, straight from global memory (in flight during the wait below)
+      float2 p_cp[NTW];
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt) p_cp[nt] = make_float2(0.f, 0.f);
+      if (s < rlen) {
+        const int t = dir ? (rlen - 1 - s) : s;
+        const size_t p = (size_t)roff + t;
+        if (s > 0) {
+          const float* cpp = c_stash + ((dir ? p + 1 : p - 1) * 2 + dir) * HID + unit0;
+#pragma unroll
+          for (int nt = 0; nt < NTW; ++nt) p_cp[nt] = *reinterpret_cast<const float2*>(cpp + 2 * nt);
+        }
+        if (s == rlen - 1) {          // first iteration of the row: its c_t has not been seen as a c_{t-1} yet
+          const float* cp = c_stash + (p * 2 + dir) * HID + unit0;
+#pragma unroll
+          for (int nt = 0; nt < NTW; ++nt) ccur[nt] = *reinterpret_cast<const float2*>(cp + 2 * nt);
+        }
+      }
+      PROF_MARK(0)
+      if (s < maxlen - 1) { lbar_wait_cluster(rfull, ph_full); ph_full ^= 1u; }   // partials of iteration s+1 landed
+      bar_sync(3, G::NT);            // the copy warps have fetched the stash of iteration s
+      PROF_MARK(1)
+      // ---- phase 1: d(pre-activations) of this lane's row and ten units ---------------------------------------
+      {
+        float dz[4][UPW];
+        unsigned char* sp = Stg + R * G::SROW + w * (UPW * 4);
+        if (s < rlen) {
+          float dht[UPW];
+#pragma unroll
+          for (int nt = 0; nt < NTW; ++nt) {
+            const float2 v = *reinterpret_cast<const float2*>(sp + 4 * G::SARR + nt * 8);
+            dht[2 * nt] = v.x; dht[2 * nt + 1] = v.y;
+          }
+          if (s == rlen - 1) {       // the row's last step: start of its backward recursion
+            const float* d0 = dcn + (size_t)rrow * 2 * HID + (size_t)dir * HID + unit0;
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) {
+              const float2 v = *reinterpret_cast<const float2*>(d0 + 2 * nt);
+              dcc[2 * nt] = v.x; dcc[2 * nt + 1] = v.y;
+            }
+          } else {                   // recurrent part: the CL partials summed in fixed order
+            const float* rv = reinterpret_cast<const float*>(Rsm + (size_t)R * RP) + w * UPW;
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) {
+              float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int src = 0; src < CL; ++src) {
+                const float2 v = *reinterpret_cast<const float2*>(rv + (size_t)src * MT * (RP / 4) + 2 * nt);
+                acc2.x += v.x; acc2.y += v.y;
+              }
+              dht[2 * nt] += acc2.x; dht[2 * nt + 1] += acc2.y;
+            }
+          }
+#pragma unroll
+          for (int nt = 0; nt < NTW; ++nt) {
+            const float2 ig = *reinterpret_cast<const float2*>(sp + 0 * G::SARR + nt * 8);
+            const float2 fg = *reinterpret_cast<const float2*>(sp + 1 * G::SARR + nt * 8);
+            const float2 gg = *reinterpret_cast<const float2*>(sp + 2 * G::SARR + nt * 8);
+            const float2 og = *reinterpret_cast<const float2*>(sp + 3 * G::SARR + nt * 8);
+            const float iv[2] = {ig.x, ig.y}, fv[2] = {fg.x, fg.y}, gv[2] = {gg.x, gg.y}, ov[2] = {og.x, og.y};
+            const float cv[2] = {ccur[nt].x, ccur[nt].y}, cpv[2] = {p_cp[nt].x, p_cp[nt].y};
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int i = 2 * nt + u;
+              const float tc = fast_tanh(cv[u]);
+              const float dc = dcc[i] + dht[i] * ov[u] * (1.f - tc * tc);
+              dz[3][i] = dht[i] * tc * ov[u] * (1.f - ov[u]);
+              dz[0][i] = dc * gv[u] * iv[u] * (1.f - iv[u]);
+              dz[2][i] = dc * iv[u] * (1.f - gv[u] * gv[u]);
+              dz[1][i] = dc * cpv[u] * fv[u] * (1.f - fv[u]);
+              dcc[i] = dc * fv[u];
+            }
+            ccur[nt] = p_cp[nt];
+          }
+          // dL/dgx of this step goes back into the staging tile (stored to global memory cooperatively below)
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) *reinterpret_cast<float2*>(sp + g * G::SARR + nt * 8) = make_float2(dz[g][2 * nt], dz[g][2 * nt + 1]);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int i = 0; i < UPW; ++i) dz[g][i] = 0.f;
+        }
+        // dz -> A operand (bf16 hi / lo), 40 consecutive k' = (gate, unit) of this warp: 5 x 16 B per plane
+        if (s > 0) {
+          uint32_t hi[20], lo[20];
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) split2<false>(dz[g][2 * nt], dz[g][2 * nt + 1], hi[g * 5 + nt], lo[g * 5 + nt]);
+          uint4* zh = reinterpret_cast<uint4*>(Zsm + (size_t)R * PITCH + w * 80);
+          uint4* zl = reinterpret_cast<uint4*>(Zsm + G::B_Z_PLANE + (size_t)R * PITCH + w * 80);
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {
+            zh[c] = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+            zl[c] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+          }
+        }
+      }
+      PROF_MARK(2)
+      bar_sync(1, G::CT);   // dz tile complete; every compute thread has consumed its recv values
+      if (leader && s > 0) {
+        lbar_expect_tx(rfull, G::B_TX);                                             // arm for the partials of iteration s
+#pragma unroll
+        for (int d = 0; d < CL; ++d) rbar_arrive_relaxed(mapa_u32(rfree_local, d));  // "my recv may be overwritten"
+      }
+      bar_arrive(2, G::NT);  // hand the staging tile (dL/dgx of iteration s) to the copy warps
+      if (s == 0) break;
+      PROF_MARK(3)
+      // ---- phase 2: partial dh_{t-1}[32 x units of this warp's n-tiles] = dz[32 x 160] x W_slice --------------
+      float acc[2][7][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 7; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+      struct Frag { uint32_t ah[2][4], al[2][4], bh[7][2], bl[7][2]; };
+      auto load_frags = [&](Frag& f, int ks) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          ldsm_x4(z_local + a_off + mt * 16 * PITCH + ks * 32, f.ah[mt][0], f.ah[mt][1], f.ah[mt][2], f.ah[mt][3]);
+          ldsm_x4(z_local + G::B_Z_PLANE + a_off + mt * 16 * PITCH + ks * 32, f.al[mt][0], f.al[mt][1], f.al[mt][2], f.al[mt][3]);
+        }
+        const uint32_t bc = (((uint32_t)(2 * ks) + b_kh) ^ b_x) << 4;    // swizzled 16 B chunk of this lane
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr) {
+          ldsm_x4(w_local + b_row + pr * 16 * WP + bc, f.bh[2 * pr][0], f.bh[2 * pr][1], f.bh[2 * pr + 1][0], f.bh[2 * pr + 1][1]);
+          ldsm_x4(w_local + G::B_W_PLANE + b_row + pr * 16 * WP + bc, f.bl[2 * pr][0], f.bl[2 * pr][1], f.bl[2 * pr + 1][0],
+                  f.bl[2 * pr + 1][1]);
+        }
+        if (seven) {
+          ldsm_x2(w_local + b_row6 + bc, f.bh[6][0], f.bh[6][1]);
+          ldsm_x2(w_local + G::B_W_PLANE + b_row6 + bc, f.bl[6][0], f.bl[6][1]);
+        }
+      };
+      auto mma_all = [&](const Frag& f) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 7; ++nt)
+            if (nt < 6 || seven) mma16816<false>(acc[mt][nt], f.al[mt], f.bh[nt][0], f.bh[nt][1]);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 7; ++nt)
+            if (nt < 6 || seven) mma16816<false>(acc[mt][nt], f.ah[mt], f.bl[nt][0], f.bl[nt][1]);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 7; ++nt)
+            if (nt < 6 || seven) mma16816<false>(acc[mt][nt], f.ah[mt], f.bh[nt][0], f.bh[nt][1]);
+      };
+      {
+        Frag f0, f1;
+        load_frags(f0, 0);
+#pragma unroll
+        for (int ks = 0; ks < G::BKS; ks += 2) {
+          load_frags(f1, ks + 1);
+          mma_all(f0);
+          if (ks + 2 < G::BKS) load_frags(f0, ks + 2);
+          mma_all(f1);
+        }
+      }
+      PROF_MARK(4)
+      // rfree: every CTA has finished reading its recv -> it may be overwritten; it also tells that every peer has
+      // received the partials of the previous iteration, i.e. the copy engine is done with the staging tile
+      lbar_wait_cluster(rfree, ph_free);
+      ph_free ^= 1u;
+      PROF_MARK(6)
+#pragma unroll
+      for (int nt = 0; nt < 7; ++nt) {
+        if (nt < 6 || seven) {
+          const int k = 8 * (nt0 + nt) + 2 * q;          // output hidden unit of acc[..][nt][0]
+          const int owner = k / UPC, kl = k - owner * UPC;
+          unsigned char* dst = Ssm + (size_t)owner * G::B_RBLK + kl * 4;
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            *reinterpret_cast<float2*>(dst + (16 * mt + r8) * RP) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+            *reinterpret_cast<float2*>(dst + (16 * mt + r8 + 8) * RP) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+          }
+        }
+      }
+      bar_sync(1, G::CT);   // partials staged (also: every warp is done with the dz tile before the next phase 1 rewrites it)
+      PROF_MARK(7)
+      if (leader) {
+        fence_proxy_async_smem();
+#pragma unroll
+        for (int d = 0; d < CL; ++d) {
+          const int owner = (rank + d) % CL;
+          bulk_copy_to_peer(mapa_u32(r_local + (uint32_t)(rank * G::B_RBLK), owner), s_local + (uint32_t)(owner * G::B_RBLK), G::B_RBLK,
+                            mapa_u32(rfull_local, owner));
+        }
+      }
+    }
+  }
+  PROF_FLUSH(8)
+  cluster_arrive();
+  cluster_wait();
+}
+
+template <class K>
+int launch_cluster5(K kernel, size_t smem, int ntiles, cudaStream_t st, void** args, const char* name, int* cache, bool* attr_set) {
+  if (!*attr_set) {
+    NNR_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    *attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = G::CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.blockDim = dim3(G::NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  if (*cache == 0) {
+    cfg.gridDim = dim3(G::CL * 2);
+    int nc = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, (const void*)kernel, &cfg);
+    if (e != cudaSuccess || nc < 2) { (void)cudaGetLastError(); nc = 24; }
+    *cache = nc & ~1;
+  }
+  int want = 2 * ntiles;                      // (tile, direction) pairs
+  int nclusters = want < *cache ? want : *cache;
+  if (nclusters < 2) nclusters = 2;
+  cfg.gridDim = dim3(nclusters * G::CL);
+  cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)kernel, args);
+  nnr_count_launch(1);
+  if (e != cudaSuccess) { nnr_set_error("%s: launch failed: %s", name, cudaGetErrorString(e)); return (int)e; }
+  return 0;
+}
+
+}  // namespace
+
+#ifdef NNR_LSTM_PROF
+extern "C" int nnr_debug_lstm_prof(unsigned long long* out16) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out16, g_lstm_prof, 16 * sizeof(unsigned long long));
+}
+#endif
+int nnr_lstm_mma_max_clusters = 0;   // reported by nnr_lstm_info
+
+int nnr_lstm_fwd_mma(float* gx, const float* w_hh, const int32_t* len, const int32_t* off, const int32_t* order, int N,
+                     float* h_out, float* c_stash, float* c_n, int32_t* tile_counters, cudaStream_t st) {
+  static int cache = 0;
+  static bool attr_set = false;
+  int ntiles = (N + G::MT - 1) / G::MT;
+  NNR_CUDA(cudaMemsetAsync(tile_counters, 0, 2 * sizeof(int32_t), st));
+  void* args[] = {&gx, &w_hh, &len, &off, &order, &N, &ntiles, &h_out, &c_stash, &c_n, &tile_counters};
+  int rc = launch_cluster5(lstm_fwd_mma_kernel, G::FWD_SMEM, ntiles, st, args, "lstm_fwd_mma_kernel", &cache, &attr_set);
+  nnr_lstm_mma_max_clusters = cache;
+  return rc;
+}
+
+int nnr_lstm_bwd_mma(float* gates, const float* c_stash, const float* w_hh, const int32_t* len, const int32_t* off,
+                     const int32_t* order, int N, const float* dh, const float* dcn, int32_t* tile_counters, cudaStream_t st) {
+  static int cache = 0;
+  static bool attr_set = false;
+  int ntiles = (N + G::MT - 1) / G::MT;
+  NNR_CUDA(cudaMemsetAsync(tile_counters, 0, 2 * sizeof(int32_t), st));
+  void* args[] = {&gates, &c_stash, &w_hh, &len, &off, &order, &N, &ntiles, &dh, &dcn, &tile_counters};
+  return launch_cluster5(lstm_bwd_mma_kernel, G::BWD_SMEM, ntiles, st, args, "lstm_bwd_mma_kernel", &cache, &attr_set);
+}
