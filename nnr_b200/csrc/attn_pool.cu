@@ -108,30 +108,62 @@ __global__ void __launch_bounds__(POOL_THREADS) attn_pool_bwd_kernel(nnr_pool_ar
     da[t] = v;
   }
   __syncthreads();
-  // dX and (mode 1) dqvec
+  // dX and (mode 1) dqvec.  Loads of four tokens are issued before the first store (the compiler cannot move a load
+  // across a store through a possibly aliasing pointer), so four rows are in flight per thread.
+  const float* __restrict__ Xr = a.X;
+  float* __restrict__ dXw = a.dX;
   for (int d = tid; d < a.D; d += POOL_THREADS) {
     const float g = dp[d];
     const float q = (a.mode == 1) ? a.qvec[(size_t)s * a.ldq + d] : 0.f;
     float accq = 0.f;
-#pragma unroll 4
-    for (int t = 0; t < n; ++t) {
+    int t = 0;
+    for (; t + 4 <= n; t += 4) {
+      float xv[4] = {0.f, 0.f, 0.f, 0.f}, old[4] = {0.f, 0.f, 0.f, 0.f};
+      if (a.mode == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xv[j] = Xr[((size_t)beg + t + j) * a.ldx + d];
+      }
+      if (a.accumulate_dx) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) old[j] = dXw[((size_t)beg + t + j) * a.lddx + d];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = al[t + j] * g;
+        if (a.mode == 1) { v += da[t + j] * q; accq += da[t + j] * xv[j]; }
+        dXw[((size_t)beg + t + j) * a.lddx + d] = old[j] + v;
+      }
+    }
+    for (; t < n; ++t) {
       const size_t p = (size_t)beg + t;
       float v = al[t] * g;
-      if (a.mode == 1) { v += da[t] * q; accq += da[t] * a.X[p * a.ldx + d]; }
-      float* o = a.dX + p * a.lddx + d;
+      if (a.mode == 1) { v += da[t] * q; accq += da[t] * Xr[p * a.ldx + d]; }
+      float* o = dXw + p * a.lddx + d;
       *o = a.accumulate_dx ? (*o + v) : v;
     }
     if (a.mode == 1 && a.dqvec) a.dqvec[(size_t)s * a.lddq + d] = accq;
   }
   if (a.mode == 0) {
+    const float* __restrict__ Ur = a.U;
+    float* __restrict__ dUw = a.dU;
     for (int k = tid; k < a.A; k += POOL_THREADS) {
       const float wk = a.w2[k];
       float accw = 0.f;
-#pragma unroll 4
-      for (int t = 0; t < n; ++t) {
+      int t = 0;
+      for (; t + 4 <= n; t += 4) {
+        float u[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) u[j] = Ur[((size_t)beg + t + j) * a.ldu + k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dUw[((size_t)beg + t + j) * a.lddu + k] = da[t + j] * wk * (1.f - u[j] * u[j]);
+          accw += da[t + j] * u[j];
+        }
+      }
+      for (; t < n; ++t) {
         const size_t p = (size_t)beg + t;
-        float u = a.U[p * a.ldu + k];
-        a.dU[p * a.lddu + k] = da[t] * wk * (1.f - u * u);
+        const float u = Ur[p * a.ldu + k];
+        dUw[p * a.lddu + k] = da[t] * wk * (1.f - u * u);
         accw += da[t] * u;
       }
       a.dw2_partial[(size_t)s * a.A + k] = accw;

@@ -36,7 +36,9 @@ extern "C" int nnr_gemm_default_algo(void);
 #define TC_THREADS 320        // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 #define TC_TMEM_COLS 512
 #define TC_ACC_COLS 256
-#define TC_SMEM_BUDGET (221 * 1024)
+#define TC_EPI_PITCH 80       // bytes per row of an epilogue warp's 32 x 16 fp32 transpose tile (conflict-free 16 B accesses)
+#define TC_EPI_SCRATCH (8 * 32 * TC_EPI_PITCH)
+#define TC_SMEM_BUDGET (205 * 1024)   // pipeline stages; + TC_EPI_SCRATCH + alignment slack + barriers <= 227 KB
 #define TC_PREFETCH_KB 1000000   // L2 prefetch distance in k-blocks; measured slower when enabled (6), so effectively off
 #define TC_CHAIN_K 1024      // max contraction length accumulated in TMEM before an fp32 combine (split-K GEMMs)
 
@@ -222,6 +224,74 @@ __device__ __forceinline__ void epi_store16(const EpiP& e, int m, int n, float* 
   st16(c, cv, v);
 }
 
+// ---- epilogue over 4 consecutive columns of one row (the coalesced layout: a quad of lanes covers 64 contiguous
+// bytes of a row, a warp instruction 8 rows x 64 B), cnt = valid columns (N tail) --------------------------------
+__device__ __forceinline__ void ld4(const float* p, int cnt, float* o) {
+  if (cnt == 4 && al16(p)) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = (i < cnt) ? __ldg(p + i) : 0.f;
+  }
+}
+__device__ __forceinline__ void st4(float* p, int cnt, const float* o) {
+  if (cnt == 4 && al16(p)) {
+    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (i < cnt) p[i] = o[i];
+  }
+}
+// The epilogue of one 4-column item is split in a load part and a finish part so that the loads of the four items a
+// lane handles per chunk are all in flight before the first store (a store would otherwise fence the next item's loads).
+struct Epi4In { float rb[4], ax[4], cc[4]; };
+__device__ __forceinline__ void epi_load4(const EpiP& e, int m, int n, int cnt, Epi4In& in) {
+  if (e.epilogue == NNR_EPI_GATE) {
+    ld4(e.rowbias + (size_t)__ldg(e.rowmap + m) * e.ldrowbias + n, cnt, in.rb);
+    ld4(e.aux + (size_t)m * e.ldaux + n, cnt, in.ax);
+  } else if (e.epilogue == NNR_EPI_ADD_AUX || (e.epilogue == NNR_EPI_BIAS_RELU_RES && e.aux)) {
+    ld4(e.aux + (size_t)m * e.ldaux + n, cnt, in.ax);
+  }
+  if (e.accumulate) ld4(e.C + (size_t)m * e.ldc + n, cnt, in.cc);
+}
+__device__ __forceinline__ void epi_finish4(const EpiP& e, int m, int n, float* v, int cnt, const float* bias4, const Epi4In& in) {
+  if (e.epilogue == NNR_EPI_BIAS || e.epilogue == NNR_EPI_BIAS_TANH || e.epilogue == NNR_EPI_BIAS_RELU_RES) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] += bias4[i];
+  }
+  if (e.epilogue == NNR_EPI_BIAS_TANH) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = tanhf(v[i]);
+  } else if (e.epilogue == NNR_EPI_BIAS_RELU_RES) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
+    if (e.aux_out) st4(e.aux_out + (size_t)m * e.ldaux_out + n, cnt, v);
+    if (e.aux) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] += in.ax[i];
+    }
+    if (e.p_drop > 0.f) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] *= dropout_scale(e.seed, (uint64_t)m * (uint64_t)e.N + n + i, e.p_drop, e.inv_keep);
+    }
+  } else if (e.epilogue == NNR_EPI_GATE) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = sigmoidf_(v[i] + in.rb[i]);
+    if (e.aux_out) st4(e.aux_out + (size_t)m * e.ldaux_out + n, cnt, v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] *= in.ax[i];
+  } else if (e.epilogue == NNR_EPI_ADD_AUX) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] += in.ax[i];
+  }
+  if (e.accumulate) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] += in.cc[i];
+  }
+  st4(e.C + (size_t)m * e.ldc + n, cnt, v);
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b, TcParams p) {
@@ -244,7 +314,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   const uint32_t a_tile = TC_BM * 128, b_tile = (uint32_t)p.block_n * 128;
   const uint32_t stage_bytes = (uint32_t)p.nplanes * (a_tile + b_tile);       // multiples of 1024
   unsigned char* tiles = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + (size_t)p.stages * stage_bytes);
+  unsigned char* epi_scratch = tiles + (size_t)p.stages * stage_bytes;          // [8 epilogue warps][32][TC_EPI_PITCH]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_scratch + TC_EPI_SCRATCH);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;            // [2]
@@ -361,6 +432,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       mbar_wait(&tmem_full[buf], (tl >> 1) & 1);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + buf * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
+      // Each thread reads one accumulator row (tcgen05.ld 32x32b), the warp transposes 32 x 16 chunks through its
+      // shared-memory tile, and all global traffic of the epilogue (C, aux, row bias, accumulate) then runs in the
+      // coalesced layout: lane -> (row = lane / 4 + 8 i, 4 columns = 4 (lane % 4)), 64 contiguous bytes per row.
+      unsigned char* my_tile = epi_scratch + (size_t)(warp - 2) * 32 * TC_EPI_PITCH;
+      const int tr = lane >> 2, tc4 = (lane & 3) * 4;
       for (int c0 = c_begin; c0 < c_end; c0 += 16) {
         float v[16];
         if (kb1 > kb0) tmem_ld16(lane_addr + (uint32_t)c0, v);
@@ -368,18 +444,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = 0.f;
         }
-        const int n = n0 + c0;
-        if (m < M && n < p.N) {
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd)
+          *reinterpret_cast<float4*>(my_tile + lane * TC_EPI_PITCH + qd * 16) = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+        __syncwarp();
+        const int n = n0 + c0 + tc4;
+        const int cnt = min(4, p.N - n);
+        float o[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 x = *reinterpret_cast<const float4*>(my_tile + (tr + 8 * i) * TC_EPI_PITCH + tc4 * 4);
+          o[i][0] = x.x; o[i][1] = x.y; o[i][2] = x.z; o[i][3] = x.w;
+        }
+        if (cnt > 0) {
           if (p.partial) {
-            float* dst = p.partial + ((size_t)z * M + m) * p.N + n;
-            if (n + 16 <= p.N) st16(dst, nvec && al16(dst), v);
-            else for (int i = 0; i < 16 && n + i < p.N; ++i) dst[i] = v[i];
-          } else if (n + 16 <= p.N) {
-            epi_store16(p.epi, m, n, v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int mm = m0 + q * 32 + tr + 8 * i;
+              if (mm < M) st4(p.partial + ((size_t)z * M + mm) * p.N + n, cnt, o[i]);
+            }
           } else {
-            for (int i = 0; i < 16 && n + i < p.N; ++i) epi_store(p.epi, m, n + i, v[i]);
+            Epi4In in[4];
+            float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p.epi.bias && (p.epi.epilogue == NNR_EPI_BIAS || p.epi.epilogue == NNR_EPI_BIAS_TANH || p.epi.epilogue == NNR_EPI_BIAS_RELU_RES))
+              ld4(p.epi.bias + n, cnt, bias4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int mm = m0 + q * 32 + tr + 8 * i;
+              if (mm < M) epi_load4(p.epi, mm, n, cnt, in[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int mm = m0 + q * 32 + tr + 8 * i;
+              if (mm < M) epi_finish4(p.epi, mm, n, o[i], cnt, bias4, in[i]);
+            }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -547,7 +648,7 @@ static TcPlan make_plan(const nnr_gemm_args* a, int mode) {
   int nkb_cap = (a->K + pl.kelem - 1) / pl.kelem;
   pl.split_k = 0;
   pl.chain_kb = TC_CHAIN_K / pl.kelem;
-  if (tiles < 148 && nkb_cap >= 8) {
+  if (tiles * 2 <= 148 && nkb_cap >= 8) {   // an output grid that already fills more than half the SMs is not split
     int target = (int)((148 + tiles - 1) / tiles);
     int chain = (nkb_cap + target - 1) / target;
     if (chain < 4) chain = 4;
@@ -560,7 +661,7 @@ static TcPlan make_plan(const nnr_gemm_args* a, int mode) {
   if (stages < 2) stages = 2;
   if (stages > 6) stages = 6;
   pl.stages = stages;
-  pl.smem = 1024 + (size_t)stages * stage + (2 * stages + 4) * 8 + 16;
+  pl.smem = 1024 + (size_t)stages * stage + TC_EPI_SCRATCH + (2 * stages + 4) * 8 + 16;
   const size_t esz = bf16 ? 2 : 4;
   pl.a_plane = (size_t)pl.a_rows * pl.a_cp;
   pl.b_plane = (size_t)pl.b_rows * pl.b_cp;

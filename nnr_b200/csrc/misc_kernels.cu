@@ -172,9 +172,9 @@ __global__ void news_fuse_split_kernel(const float* __restrict__ dout, int D2, i
     else d_b[(size_t)r * D2 + d - D2] = v;
   }
 }
-// one block per table row.  Thread t owns news rows t, t+256, ... (fixed partition), accumulates the matching
-// rows in registers, then the 256 partials are combined by a fixed shuffle tree + fixed warp order:
-// deterministic, no atomics, no serial scan.
+// one block per table row.  Warp w scans news rows [w*span, (w+1)*span) 32 at a time; the matches of a ballot are
+// accumulated in row order by the whole warp (lane = embedding column: one coalesced 200 B read per match), and the
+// eight per-warp partials are combined in warp order: deterministic, no atomics, no serial per-thread scan.
 #define NF_MAXE 64
 __global__ void __launch_bounds__(256) news_fuse_table_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ idx,
                                                                   int N, int Dout, int col0, int Edim, int Etot, int eoff,
@@ -183,26 +183,23 @@ __global__ void __launch_bounds__(256) news_fuse_table_bwd_kernel(const float* _
   __shared__ float s_part[8][NF_MAXE];
   const int row = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  float acc[NF_MAXE];
-#pragma unroll
-  for (int e = 0; e < NF_MAXE; ++e) acc[e] = 0.f;
-  for (int r = tid; r < N; r += 256) {
-    if (idx[r] == row) {
-      const float* src = dout + (size_t)r * Dout + col0;
-#pragma unroll
-      for (int e = 0; e < NF_MAXE; ++e)
-        if (e < Edim) acc[e] += src[e] * dropout_scale(seed, (uint64_t)r * Etot + eoff + e, p, inv_keep);
+  const int span = ((N + 7) / 8 + 31) & ~31;
+  const int r_begin = w * span, r_end = min(N, r_begin + span);
+  float acc0 = 0.f, acc1 = 0.f;                       // columns lane and lane + 32
+  for (int r0 = r_begin; r0 < r_end; r0 += 32) {
+    const int r = r0 + lane;
+    unsigned m = __ballot_sync(0xffffffffu, r < r_end && idx[r] == row);
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const int rr = r0 + j;
+      const float* src = dout + (size_t)rr * Dout + col0;
+      if (lane < Edim) acc0 += src[lane] * dropout_scale(seed, (uint64_t)rr * Etot + eoff + lane, p, inv_keep);
+      if (lane + 32 < Edim) acc1 += src[lane + 32] * dropout_scale(seed, (uint64_t)rr * Etot + eoff + lane + 32, p, inv_keep);
     }
   }
-#pragma unroll
-  for (int e = 0; e < NF_MAXE; ++e) {
-    if (e < Edim) {
-      float v = acc[e];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) s_part[w][e] = v;
-    }
-  }
+  s_part[w][lane] = acc0;
+  s_part[w][lane + 32] = acc1;
   __syncthreads();
   if (tid < Edim) {
     float v = 0.f;

@@ -9,6 +9,7 @@ slicing of the small per-news tensors.
 Reference spans: CNE = newsEncoders.py:102-141, SUE = userEncoders.py:68-98, GCN = layers.py:285-323.
 """
 import math
+import weakref
 
 import torch
 
@@ -30,7 +31,37 @@ def _empty(shape, dev, dtype=torch.float32):
 # ------------------------------------------------------------------------------------------------
 # GEMM helpers (row-major; weights are nn.Linear layout [out, in])
 # ------------------------------------------------------------------------------------------------
-def linear(x, W, M, m_dev=None, bias=None, epilogue=None, out=None, x_planes=None, **epi):
+# Operand planes of WEIGHT matrices are split once per parameter version and shared by the forward and the dgrad
+# GEMMs of every call until the parameters change.  In-place updates through torch bump ``_version``; the fused
+# clip+Adam kernel writes through raw pointers, so trainer.TrainStep calls ``weights_changed()`` after it.
+_weight_planes = {}
+_weight_epoch = 0
+
+
+def weights_changed():
+    global _weight_epoch
+    _weight_epoch += 1
+    _weight_planes.clear()
+
+
+def weight_planes(W):
+    # only nn.Parameter objects: a temporary (e.g. a torch.cat of two weights) can be freed and its address reused by a
+    # different matrix of the same shape within one parameter version
+    if not (isinstance(W, torch.nn.Parameter) or (W.is_leaf and W.requires_grad)) or W.dim() != 2 or W.stride(1) != 1 or not W.is_cuda:
+        return None
+    key = id(W)
+    tag = (_weight_epoch, W._version, W.data_ptr(), W.shape[0], W.shape[1], W.stride(0))
+    hit = _weight_planes.get(key)
+    if hit is not None and hit[0] == tag and hit[2]() is W:     # the weak reference guards against a recycled id / address
+        return hit[1]
+    planes = ops.tc_split(W, W.shape[0], W.shape[1], W.stride(0))
+    if len(_weight_planes) > 4096:
+        _weight_planes.clear()
+    _weight_planes[key] = (tag, planes, weakref.ref(W))
+    return planes
+
+
+def linear(x, W, M, m_dev=None, bias=None, epilogue=None, out=None, x_planes=None, w_planes=None, **epi):
     """out[M,N] = epi(x[M,K] @ W[N,K]^T)"""
     N, K = W.shape
     if out is None:
@@ -38,17 +69,17 @@ def linear(x, W, M, m_dev=None, bias=None, epilogue=None, out=None, x_planes=Non
     if epilogue is None:
         epilogue = EPI_BIAS if bias is not None else EPI_NONE
     ops.gemm(x, W, out, M, N, K, x.stride(0), W.stride(0), out.stride(0), False, True, epilogue, bias=bias,
-             m_dev=m_dev, a_planes=x_planes, **epi)
+             m_dev=m_dev, a_planes=x_planes, b_planes=w_planes if w_planes is not None else weight_planes(W), **epi)
     return out
 
 
-def matmul_nn(x, W, M, m_dev=None, out=None, x_planes=None, **epi):
+def matmul_nn(x, W, M, m_dev=None, out=None, x_planes=None, w_planes=None, **epi):
     """out[M,K] = x[M,N] @ W[N,K]   (dgrad of a Linear with weight W, or a fold K^T q)"""
     N, K = W.shape
     if out is None:
         out = _empty((M, K), x.device)
     ops.gemm(x, W, out, M, K, N, x.stride(0), W.stride(0), out.stride(0), False, False, m_dev=m_dev,
-             a_planes=x_planes, **epi)
+             a_planes=x_planes, b_planes=w_planes if w_planes is not None else weight_planes(W), **epi)
     return out
 
 
@@ -133,7 +164,8 @@ def _cne_modality_forward(P, x, ids, mask_u8, N, L, E, Hd, training, p_drop, see
     bias = torch.cat([P[pre + 'bias_ih_l0'] + P[pre + 'bias_hh_l0'],
                       P[pre + 'bias_ih_l0_reverse'] + P[pre + 'bias_hh_l0_reverse']], 0)       # [8H]
     m.emb_pl = split_tokens(m.emb, cap, E, m.ntok)
-    m.gates = linear(m.emb, m.w_ih, cap, m.ntok, bias, x_planes=m.emb_pl)                      # gx, then the stash
+    m.w_ih_pl = ops.tc_split(m.w_ih, 8 * Hd, E, m.w_ih.stride(0))                              # shared with the dgrad GEMM
+    m.gates = linear(m.emb, m.w_ih, cap, m.ntok, bias, x_planes=m.emb_pl, w_planes=m.w_ih_pl)  # gx, then the stash
     m.h = _empty((cap, 2 * Hd), dev)
     m.c_stash = _empty((cap, 2 * Hd), dev)
     m.c_n = _empty((N, 2 * Hd), dev)
@@ -307,7 +339,7 @@ class CNEFunction(torch.autograd.Function):
                 G[pre + 'weight_ih_l0' + sfx] = dwih[d * 4 * Hd:(d + 1) * 4 * Hd]
                 G[pre + 'bias_ih_l0' + sfx] = db[d * 4 * Hd:(d + 1) * 4 * Hd]
                 G[pre + 'bias_hh_l0' + sfx] = db[d * 4 * Hd:(d + 1) * 4 * Hd]
-            demb = matmul_nn(dz, m.w_ih, m.cap, m.ntok, x_planes=dz_pl)
+            demb = matmul_nn(dz, m.w_ih, m.cap, m.ntok, x_planes=dz_pl, w_planes=m.w_ih_pl)
             del dz_pl
             ops.embed_gather_bwd(demb, m.ids, m.len, m.off, dtable, m.p, m.seed, not first)
             first = False

@@ -30,6 +30,12 @@ class Model(nn.Module):
     def initialize(self):
         self.news_encoder.initialize()
         self.user_encoder.initialize()
+        engine.weights_changed()
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        engine.weights_changed()       # cached operand planes of the weight matrices are stale
+        return out
 
     def forward(self, user_ID, user_category, user_subCategory, user_title_text, user_title_mask, user_title_entity,
                 user_content_text, user_content_mask, user_content_entity, user_history_mask, user_history_graph,

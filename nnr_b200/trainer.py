@@ -12,7 +12,7 @@ folded into the fused clip+Adam kernel (``nnr_flat_clip_adam``).
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import engine, ops
 
 
 def negative_log_softmax(logits):
@@ -78,6 +78,7 @@ class TrainStep:
         self.step_count += 1
         ops.flat_clip_adam(self.flat, self.gflat, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
                            self.eps, self.max_norm, 1.0 / self.world_size, self.step_count, self.grad_norm)
+        engine.weights_changed()   # the kernel updates the parameters through raw pointers: drop their cached operand planes
 
 
 def shard_batch(batch, rank, world_size):
