@@ -610,6 +610,16 @@ struct TcPlan {
   size_t a_plane, b_plane, a_off, b_off, partial_off, total, smem;
 };
 
+static double stage_penalty() {
+  static double v = -1.0;
+  if (v < 0) { const char* e = getenv("NNR_TC_STAGE_PENALTY"); v = e ? atof(e) : 1.3; }   // measured: a two-stage ring loses more than the larger tile gains
+  return v;
+}
+static double stage_penalty3() {
+  static double v = -1.0;
+  if (v < 0) { const char* e = getenv("NNR_TC_STAGE_PENALTY3"); v = e ? atof(e) : 1.0; }
+  return v;
+}
 static int pick_block_n(int N, int step, int nplanes) {
   int best = step;
   double best_cost = 1e30;
@@ -618,7 +628,8 @@ static int pick_block_n(int N, int step, int nplanes) {
     double cost = padded * (1.0 + 40.0 / bn);
     // a two-stage ring cannot hide the TMA latency behind one stage of MMAs: prefer tiles that leave room for three
     size_t stage = (size_t)nplanes * ((size_t)TC_BM * 128 + (size_t)bn * 128);
-    if (TC_SMEM_BUDGET / stage < 3) cost *= 1.15;
+    if (TC_SMEM_BUDGET / stage < 3) cost *= stage_penalty();
+    else if (TC_SMEM_BUDGET / stage < 4) cost *= stage_penalty3();
     if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
   }
   return best;

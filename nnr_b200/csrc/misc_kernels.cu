@@ -172,30 +172,42 @@ __global__ void news_fuse_split_kernel(const float* __restrict__ dout, int D2, i
     else d_b[(size_t)r * D2 + d - D2] = v;
   }
 }
-// one block per table row.  Warp w scans news rows [w*span, (w+1)*span) 32 at a time; the matches of a ballot are
-// accumulated in row order by the whole warp (lane = embedding column: one coalesced 200 B read per match), and the
-// eight per-warp partials are combined in warp order: deterministic, no atomics, no serial per-thread scan.
+// one block per table row, 32 warps.  Warp w walks news rows [w*span, (w+1)*span) four at a time: the four index loads
+// and then the (warp-uniformly predicated) row loads are issued together, so a category that matches a large share of
+// the rows (e.g. the padding category of the history) costs pipelined loads rather than one exposed latency per match.
+// Lane = embedding column; rows are accumulated in order and the 32 per-warp partials are combined in warp order:
+// deterministic, no atomics.
 #define NF_MAXE 64
-__global__ void __launch_bounds__(256) news_fuse_table_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ idx,
-                                                                  int N, int Dout, int col0, int Edim, int Etot, int eoff,
-                                                                  float p, float inv_keep, uint64_t seed,
-                                                                  float* __restrict__ dtable, int accumulate) {
-  __shared__ float s_part[8][NF_MAXE];
+#define NF_WARPS 32
+__global__ void __launch_bounds__(NF_WARPS * 32) news_fuse_table_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ idx,
+                                                                          int N, int Dout, int col0, int Edim, int Etot, int eoff,
+                                                                          float p, float inv_keep, uint64_t seed,
+                                                                          float* __restrict__ dtable, int accumulate) {
+  __shared__ float s_part[NF_WARPS][NF_MAXE];
   const int row = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int span = ((N + 7) / 8 + 31) & ~31;
+  const int span = (N + NF_WARPS - 1) / NF_WARPS;
   const int r_begin = w * span, r_end = min(N, r_begin + span);
+  const bool c0 = lane < Edim, c1 = lane + 32 < Edim;
   float acc0 = 0.f, acc1 = 0.f;                       // columns lane and lane + 32
-  for (int r0 = r_begin; r0 < r_end; r0 += 32) {
-    const int r = r0 + lane;
-    unsigned m = __ballot_sync(0xffffffffu, r < r_end && idx[r] == row);
-    while (m) {
-      const int j = __ffs(m) - 1;
-      m &= m - 1;
-      const int rr = r0 + j;
-      const float* src = dout + (size_t)rr * Dout + col0;
-      if (lane < Edim) acc0 += src[lane] * dropout_scale(seed, (uint64_t)rr * Etot + eoff + lane, p, inv_keep);
-      if (lane + 32 < Edim) acc1 += src[lane + 32] * dropout_scale(seed, (uint64_t)rr * Etot + eoff + lane + 32, p, inv_keep);
+  for (int r0 = r_begin; r0 < r_end; r0 += 4) {
+    bool hit[4];
+    float v0[4], v1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hit[j] = (r0 + j < r_end) && (idx[r0 + j] == row);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float* src = dout + (size_t)(r0 + j) * Dout + col0;
+      v0[j] = (hit[j] && c0) ? src[lane] : 0.f;
+      v1[j] = (hit[j] && c1) ? src[lane + 32] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (hit[j]) {
+        const uint64_t base = (uint64_t)(r0 + j) * Etot + eoff;
+        if (c0) acc0 += v0[j] * dropout_scale(seed, base + lane, p, inv_keep);
+        if (c1) acc1 += v1[j] * dropout_scale(seed, base + lane + 32, p, inv_keep);
+      }
     }
   }
   s_part[w][lane] = acc0;
@@ -204,7 +216,7 @@ __global__ void __launch_bounds__(256) news_fuse_table_bwd_kernel(const float* _
   if (tid < Edim) {
     float v = 0.f;
 #pragma unroll
-    for (int ww = 0; ww < 8; ++ww) v += s_part[ww][tid];
+    for (int ww = 0; ww < NF_WARPS; ++ww) v += s_part[ww][tid];
     float* d = dtable + (size_t)row * Edim + tid;
     *d = accumulate ? (*d + v) : v;
   }
@@ -220,10 +232,10 @@ extern "C" int nnr_news_fuse_bwd(const float* dout, const int32_t* cat, const in
   float inv_keep = 1.0f / (1.0f - p_drop);
   news_fuse_split_kernel<<<N, 256, 0, st>>>(dout, D2, Dout, d_a, d_b);
   NNR_LAUNCH_CHECK("news_fuse_split_kernel");
-  news_fuse_table_bwd_kernel<<<n_cat, 256, 0, st>>>(dout, cat, N, Dout, 2 * D2, Ec, Ec + Es, 0, p_drop,
+  news_fuse_table_bwd_kernel<<<n_cat, NF_WARPS * 32, 0, st>>>(dout, cat, N, Dout, 2 * D2, Ec, Ec + Es, 0, p_drop,
                                                                      inv_keep, seed, dcat_table, accumulate);
   NNR_LAUNCH_CHECK("news_fuse_table_bwd_kernel(cat)");
-  news_fuse_table_bwd_kernel<<<n_sub, 256, 0, st>>>(dout, sub, N, Dout, 2 * D2 + Ec, Es, Ec + Es, Ec,
+  news_fuse_table_bwd_kernel<<<n_sub, NF_WARPS * 32, 0, st>>>(dout, sub, N, Dout, 2 * D2 + Ec, Es, Ec + Es, Ec,
                                                                      p_drop, inv_keep, seed, dsub_table, accumulate);
   NNR_LAUNCH_CHECK("news_fuse_table_bwd_kernel(sub)");
   return 0;

@@ -299,6 +299,18 @@ def test_lstm_forward_backward(cuda, N, L, full):
         assert (dWhh - ref).abs().max().item() / ref.abs().max().item() < 2e-5, sfx
 
 
+def test_lstm_ffma_variant_subprocess(cuda):
+    """NNR_LSTM_ALGO=ffma (exact fp32 FFMA kernels of lstm.cu) is read once per process: exercise it in a child."""
+    import os, subprocess, sys
+    env = dict(os.environ, NNR_LSTM_ALGO='ffma')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import torch, tests.test_ops_gpu as t; "
+            "t.test_lstm_forward_backward(torch.device('cuda:0'), 70, 12, False); "
+            "t.test_lstm_forward_backward(torch.device('cuda:0'), 5, 128, False); print('ffma-ok')")
+    r = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'ffma-ok' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 # ---------------------------------------------------------------------------------------------
 def test_attn_pool_modes(cuda):
     ops = _ops()
