@@ -8,3 +8,4 @@ from .newsEncoders import CNE, NewsEncoder  # noqa: F401
 from .userEncoders import SUE, UserEncoder  # noqa: F401
 from .variantEncoders import CNE_wo_CA, SUE_wo_HCA  # noqa: F401
 from .model import Model                 # noqa: F401
+from . import corpus, metrics, scoring, trainer  # noqa: F401

@@ -12,7 +12,7 @@ encoded in (sort-rank pairing of the selective gate).  The cache is therefore de
 """
 import torch
 
-from . import engine, ops
+from . import engine, metrics, ops
 
 
 class CorpusScorer:
@@ -60,3 +60,18 @@ class CorpusScorer:
         cand = self.cache[cid]                                  # [B, n, D]
         user = ue.encode_user(hist, graph, cmask, cidx, cand)
         return engine.RowDot.apply(user, cand)
+
+    @torch.no_grad()
+    def evaluate(self, history_ids, history_len, candidate_ids, candidate_count, labels, batch=256):
+        """Dev-set metrics with the cached corpus and on-device ranking (replaces util.compute_scores +
+        evaluate.scoring): impressions are padded to [I, n_max] candidate ids with ``candidate_count`` valid entries
+        and 0/1 ``labels``.  Returns (auc, mrr, ndcg5, ndcg10, ranks [I, n_max])."""
+        cid = torch.as_tensor(candidate_ids)
+        out = []
+        for a in range(0, cid.shape[0], batch):
+            out.append(self.score(history_ids[a:a + batch], history_len[a:a + batch], cid[a:a + batch]))
+        scores = torch.cat(out)
+        cnt = torch.as_tensor(candidate_count).to(self.dev)
+        lab = torch.as_tensor(labels).to(self.dev)
+        ranks, _ = metrics.rank_impressions(scores, cnt)
+        return metrics.scoring(scores, lab, cnt) + (ranks,)

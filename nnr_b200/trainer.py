@@ -65,6 +65,10 @@ class TrainStep:
         self.optimizer_step()
         return loss
 
+    def step_ids(self, corpus, history_ids, history_len, candidate_ids):
+        """index-only training step: the batch is gathered from a ``corpus.DeviceCorpus`` on the device"""
+        return self.step(*corpus.batch_from_ids(history_ids, history_len, candidate_ids))
+
     def reduce_gradients(self):
         """the single collective of the step: SUM over ranks of the flat gradient buffer (the 1/world average
         of DDP, trainer.py:219, is applied inside the fused clip+Adam kernel as grad_scale)"""

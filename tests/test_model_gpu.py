@@ -273,3 +273,50 @@ def test_cached_corpus_scoring_matches_oracle_at_equal_chunking(cuda):
         user = O.sue_forward(p, cfg, ocache[t(hist)], t(np.stack(g)), t(np.stack(cm)), t(np.stack(ci)), ocache[t(cand)])
         ref = (user * ocache[t(cand)]).sum(2)
     assert rel_err(scores, ref) < TOL
+
+
+def test_index_only_batch_equals_host_materialised_batch(cuda):
+    """a batch gathered from the device-resident corpus (ids only cross PCIe, graph built by
+    nnr_sue_graph_build) feeds the model the same 21 tensors as the reference-style host materialisation."""
+    from nnr_b200.corpus import DeviceCorpus
+    from nnr_b200.synthetic import SyntheticMIND, batch_args
+    cfg = O.make_config(vocabulary_size=600, max_history_num=8, max_title_length=10, max_abstract_length=20,
+                        subCategory_num=30, gcn_layer_num=2)
+    syn = SyntheticMIND(news_num=150, vocabulary_size=600, subCategory_num=30, max_title_length=10, max_abstract_length=20,
+                        max_history_num=8, lengths='mind', seed=5)
+    m = _build(cfg, O.formula_params(cfg), cuda)
+    corpus = DeviceCorpus.from_synthetic(syn, cuda)
+    hist, hl, cand = syn.sample_behaviors(7, seed=9)
+    host = batch_args(syn.materialize(hist, hl, cand), cuda)
+    devb = corpus.batch_from_ids(hist, hl, cand)
+    for i, (a, b) in enumerate(zip(host, devb)):
+        if a is None:
+            assert b is None
+        elif i == 0:
+            continue                                     # user_ID is unused by CNE+SUE
+        else:
+            assert a.shape == b.shape and a.dtype == b.dtype, i
+            assert torch.equal(a, b), i                  # bit-exact, including the fp32 normalised adjacency
+    with torch.no_grad():
+        assert torch.equal(m(*[x.clone() if torch.is_tensor(x) else x for x in host]), m(*devb))
+
+
+def test_device_negative_sampling_semantics(cuda):
+    """MIND_dataset.py:27-45: cyclic when the pool is not larger than K, K distinct uniform draws otherwise"""
+    from nnr_b200.corpus import DeviceCorpus
+    from nnr_b200.synthetic import SyntheticMIND
+    syn = SyntheticMIND(news_num=60, vocabulary_size=100, subCategory_num=10, max_title_length=6, max_abstract_length=8,
+                        max_history_num=4, seed=1)
+    corpus = DeviceCorpus.from_synthetic(syn, cuda)
+    pool = torch.arange(1, 41).reshape(4, 10)
+    plen = torch.tensor([1, 3, 4, 10])
+    g = torch.Generator(device=cuda).manual_seed(3)
+    out = corpus.sample_negatives(pool, plen, 4, generator=g).cpu()
+    assert out[0].tolist() == [1, 1, 1, 1]
+    assert out[1].tolist() == [11, 12, 13, 11]
+    assert out[2].tolist() == [21, 22, 23, 24]
+    assert len(set(out[3].tolist())) == 4 and all(31 <= v <= 40 for v in out[3].tolist())
+    seen = set()
+    for _ in range(50):
+        seen.update(corpus.sample_negatives(pool, plen, 4, generator=g)[3].tolist())
+    assert seen == set(range(31, 41))                    # every pool entry is reachable
