@@ -100,6 +100,54 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
         : "memory");
   }
 }
+// ---- CTA-pair (cta_group::2) variants: one 256 x BLOCK_N tile per pair of SMs; each CTA loads its own 128 rows of A
+// and HALF of the B tile, the leader CTA issues the MMAs for both, so every SM ingests A + B/2 per k-block ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the bytes land in THIS CTA's shared memory but are counted on the LEADER's full barrier
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (BF16) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc),
+        "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc),
+        "r"(accumulate)
+        : "memory");
+  }
+}
+
 // 32 lanes x 16 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
@@ -292,18 +340,23 @@ __device__ __forceinline__ void epi_finish4(const EpiP& e, int m, int n, float* 
   st4(e.C + (size_t)m * e.ldc + n, cnt, v);
 }
 
-template <bool BF16>
+template <bool BF16, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b, TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int KELEM = BF16 ? 64 : 32;                 // elements per 128 bytes = k-block depth = MN group width
+  constexpr int TILE_M = PAIR ? 2 * TC_BM : TC_BM;      // output rows per scheduled tile (a CTA always owns 128 of them)
   int M = p.M, K = p.K;
   if (p.m_dev) M = min(M, *p.m_dev);
   if (p.k_dev) K = min(K, *p.k_dev);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs of the pair)
+  const int sched_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int sched_n = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int b_rows = PAIR ? (p.block_n >> 1) : p.block_n;   // rows of the B tile this CTA holds
 
   // ---- tile space (device-side effective sizes) ----
-  const int m_tiles = (M + TC_BM - 1) / TC_BM;
+  const int m_tiles = (M + TILE_M - 1) / TILE_M;
   const int n_tiles = (p.N + p.block_n - 1) / p.block_n;
   const int nkb = (K + KELEM - 1) / KELEM;
   const int kb_per = p.split_k ? p.chain_kb : max(nkb, 1);
@@ -311,7 +364,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   const int total_tiles = m_tiles * n_tiles * splits;
 
   // ---- smem carve-up ----
-  const uint32_t a_tile = TC_BM * 128, b_tile = (uint32_t)p.block_n * 128;
+  const uint32_t a_tile = TC_BM * 128, b_tile = (uint32_t)b_rows * 128;
   const uint32_t stage_bytes = (uint32_t)p.nplanes * (a_tile + b_tile);       // multiples of 1024
   unsigned char* tiles = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* epi_scratch = tiles + (size_t)p.stages * stage_bytes;          // [8 epilogue warps][32][TC_EPI_PITCH]
@@ -325,12 +378,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], PAIR ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (PAIR) cluster_sync_all();         // the peer's barriers exist before anything is signalled across the pair
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -341,44 +400,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     // ===== TMA producer =====
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = sched_id; tile < total_tiles; tile += sched_n) {
         const int n_idx = tile % n_tiles, rest = tile / n_tiles;
-        const int m0 = (rest % m_tiles) * TC_BM, n0 = n_idx * p.block_n, z = rest / m_tiles;
+        const int m0 = (rest % m_tiles) * TILE_M + (int)rank * TC_BM, n0 = n_idx * p.block_n + (int)rank * b_rows, z = rest / m_tiles;
         const int kb0 = z * kb_per, kb1 = min(nkb, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           const uint32_t base = smem_u32(tiles + (size_t)s * stage_bytes);
-          mbar_expect_tx(&full_bar[s], stage_bytes);
-          const int kpf = kb + TC_PREFETCH_KB;                 // L2 prefetch distance (k-blocks)
-          if (kpf < kb1) {
-            for (int pl = 0; pl < p.nplanes; ++pl) {
-              if (!p.a_mn) tma_prefetch_3d(&map_a, kpf * KELEM, m0, pl);
-              else for (int g = 0; g < TC_BM / KELEM; ++g) tma_prefetch_3d(&map_a, m0 + g * KELEM, kpf * KELEM, pl);
-              if (!p.b_mn) tma_prefetch_3d(&map_b, kpf * KELEM, n0, pl);
-              else for (int g = 0; g < p.block_n / KELEM; ++g) tma_prefetch_3d(&map_b, n0 + g * KELEM, kpf * KELEM, pl);
-            }
-          }
+          if (!PAIR) mbar_expect_tx(&full_bar[s], stage_bytes);
+          else if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * stage_bytes);      // both CTAs' loads complete on the leader's barrier
+          const uint32_t lbar = PAIR ? mapa_rank(smem_u32(&full_bar[s]), 0) : 0u;
+          auto load_a = [&](uint32_t dst, int c0, int c1, int c2) {
+            if (PAIR) tma_load_3d_pair(&map_a, lbar, dst, c0, c1, c2); else tma_load_3d(&map_a, &full_bar[s], dst, c0, c1, c2);
+          };
+          auto load_b = [&](uint32_t dst, int c0, int c1, int c2) {
+            if (PAIR) tma_load_3d_pair(&map_b, lbar, dst, c0, c1, c2); else tma_load_3d(&map_b, &full_bar[s], dst, c0, c1, c2);
+          };
           for (int pl = 0; pl < p.nplanes; ++pl) {
             const uint32_t sa = base + pl * a_tile;
             const uint32_t sb = base + p.nplanes * a_tile + pl * b_tile;
-            if (!p.a_mn) tma_load_3d(&map_a, &full_bar[s], sa, kb * KELEM, m0, pl);
-            else for (int g = 0; g < TC_BM / KELEM; ++g) tma_load_3d(&map_a, &full_bar[s], sa + g * (KELEM * 128), m0 + g * KELEM, kb * KELEM, pl);
-            if (!p.b_mn) tma_load_3d(&map_b, &full_bar[s], sb, kb * KELEM, n0, pl);
-            else for (int g = 0; g < p.block_n / KELEM; ++g) tma_load_3d(&map_b, &full_bar[s], sb + g * (KELEM * 128), n0 + g * KELEM, kb * KELEM, pl);
+            if (!p.a_mn) load_a(sa, kb * KELEM, m0, pl);
+            else for (int g = 0; g < TC_BM / KELEM; ++g) load_a(sa + g * (KELEM * 128), m0 + g * KELEM, kb * KELEM, pl);
+            if (!p.b_mn) load_b(sb, kb * KELEM, n0, pl);
+            else for (int g = 0; g < b_rows / KELEM; ++g) load_b(sb + g * (KELEM * 128), n0 + g * KELEM, kb * KELEM, pl);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer (in a CTA pair: the leader only, for both CTAs) =====
+    if (lane == 0 && rank == 0) {
       int it = 0, tl = 0;
       const uint32_t lbo = KELEM * 128;                               // bytes of one MN-group box
       const uint64_t a_step = p.a_mn ? (uint64_t)((BF16 ? 2048 : 1024) >> 4) : 2;   // descriptor advance per MMA
       const uint64_t b_step = p.b_mn ? (uint64_t)((BF16 ? 2048 : 1024) >> 4) : 2;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      for (int tile = sched_id; tile < total_tiles; tile += sched_n, ++tl) {
         const int rest = tile / n_tiles;
         const int z = rest / m_tiles;
         const int kb0 = z * kb_per, kb1 = min(nkb, kb0 + kb_per);
@@ -402,16 +460,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t ao = a_step * k, bo = b_step * k;
-            tc_mma<BF16>(d_tmem, a_hi + ao, b_hi + bo, p.idesc, first ? 0u : 1u);
+            if (PAIR) tc_mma_pair<BF16>(d_tmem, a_hi + ao, b_hi + bo, p.idesc, first ? 0u : 1u);
+            else tc_mma<BF16>(d_tmem, a_hi + ao, b_hi + bo, p.idesc, first ? 0u : 1u);
             first = 0;
             if (p.nplanes == 2) {           // split operands: the two cross products (lo*lo is below fp32 resolution)
-              tc_mma<BF16>(d_tmem, a_hi + ao, b_lo + bo, p.idesc, 1u);
-              tc_mma<BF16>(d_tmem, a_lo + ao, b_hi + bo, p.idesc, 1u);
+              if (PAIR) {
+                tc_mma_pair<BF16>(d_tmem, a_hi + ao, b_lo + bo, p.idesc, 1u);
+                tc_mma_pair<BF16>(d_tmem, a_lo + ao, b_hi + bo, p.idesc, 1u);
+              } else {
+                tc_mma<BF16>(d_tmem, a_hi + ao, b_lo + bo, p.idesc, 1u);
+                tc_mma<BF16>(d_tmem, a_lo + ao, b_hi + bo, p.idesc, 1u);
+              }
             }
           }
-          tc_commit(&empty_bar[s]);
+          if (PAIR) tc_commit_pair(&empty_bar[s]); else tc_commit(&empty_bar[s]);     // frees the stage in both CTAs
         }
-        tc_commit(&tmem_full[buf]);
+        if (PAIR) tc_commit_pair(&tmem_full[buf]); else tc_commit(&tmem_full[buf]);
       }
     }
   } else {
@@ -423,9 +487,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     const int c_end = chalf ? p.block_n : ((nchunks + 1) >> 1) << 4;
     int tl = 0;
     const bool nvec = (p.N % 4) == 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = sched_id; tile < total_tiles; tile += sched_n, ++tl) {
       const int n_idx = tile % n_tiles, rest = tile / n_tiles;
-      const int m0 = (rest % m_tiles) * TC_BM, n0 = n_idx * p.block_n, z = rest / m_tiles;
+      const int m0 = (rest % m_tiles) * TILE_M + (int)rank * TC_BM, n0 = n_idx * p.block_n, z = rest / m_tiles;
       const int kb0 = z * kb_per, kb1 = min(nkb, kb0 + kb_per);
       const int buf = tl & 1;
       const int m = m0 + q * 32 + lane;
@@ -484,13 +548,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (lane == 0) {
+        if (PAIR && rank != 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[buf]), 0));   // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(&tmem_empty[buf]);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();         // no CTA leaves while its peer may still read its operands / signal its barriers
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
   }
 }
 
@@ -607,6 +676,7 @@ struct TcPlan {
   int a_rows, a_cols, b_rows, b_cols;   // stored (row-major) shapes of the operands
   int a_cp, b_cp;               // plane pitches
   int block_n, stages, split_k, chain_kb, max_splits, nplanes, kelem;
+  int pair;                     // 1: CTA-pair kernel (256-row tiles, B tile split across the pair)
   size_t a_plane, b_plane, a_off, b_off, partial_off, total, smem;
 };
 
@@ -635,6 +705,27 @@ static int pick_block_n(int N, int step, int nplanes) {
   return best;
 }
 
+// CTA-pair tiles: 256 x bn with bn <= 256, bn % 16 == 0 (K-major B) or % 128 == 0 (MN-major B: each CTA holds whole 64-wide
+// groups), three pipeline stages required.  Returns 0 when no such tile keeps the padding reasonable.
+static int pair_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NNR_TC_PAIR"); v = e ? atoi(e) : 1; }
+  return v;
+}
+static int pick_block_n_pair(int N, int step, int nplanes) {
+  int best = 0;
+  double best_cost = 1e30;
+  for (int bn = 256; bn >= 64; bn -= step) {
+    size_t stage = (size_t)nplanes * ((size_t)TC_BM * 128 + (size_t)(bn / 2) * 128);
+    if (TC_SMEM_BUDGET / stage < 3) continue;
+    double padded = (double)((N + bn - 1) / bn) * bn;
+    if (padded > 1.15 * N) continue;
+    double cost = padded * (1.0 + 40.0 / bn);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
 // mode: 0 = 3xTF32 (fp32 hi/lo planes), 1 = BF16 (one plane), 2 = BF16x3 (bf16 hi/lo planes)
 static int algo_mode(int algo) {
   if (algo == NNR_GEMM_AUTO) algo = nnr_gemm_default_algo();
@@ -654,12 +745,18 @@ static TcPlan make_plan(const nnr_gemm_args* a, int mode) {
   pl.a_cp = (int)up((size_t)pl.a_cols, pad);
   pl.b_cp = (int)up((size_t)pl.b_cols, pad);
   pl.block_n = pick_block_n(a->N, pl.b_mn ? pl.kelem : 16, pl.nplanes);
+  // large row counts (token-level GEMMs) are bound by L2->SM operand delivery: use 256-row tiles on CTA pairs
+  pl.pair = 0;
+  if (pair_mode() && a->M >= 2 * TC_BM * 148 && !(a->transA) && a->k_dev == nullptr) {
+    int bnp = pick_block_n_pair(a->N, pl.b_mn ? 2 * pl.kelem : 16, pl.nplanes);
+    if (bnp) { pl.pair = 1; pl.block_n = bnp; }
+  }
   long tiles = (long)((a->M + TC_BM - 1) / TC_BM) * ((a->N + pl.block_n - 1) / pl.block_n);
   // split-K: (a) fill the machine when the output grid is small, (b) bound the TMEM accumulation chain
   int nkb_cap = (a->K + pl.kelem - 1) / pl.kelem;
   pl.split_k = 0;
   pl.chain_kb = TC_CHAIN_K / pl.kelem;
-  if (tiles * 2 <= 148 && nkb_cap >= 8) {   // an output grid that already fills more than half the SMs is not split
+  if (!pl.pair && tiles * 2 <= 148 && nkb_cap >= 8) {   // an output grid that already fills more than half the SMs is not split
     int target = (int)((148 + tiles - 1) / tiles);
     int chain = (nkb_cap + target - 1) / target;
     if (chain < 4) chain = 4;
@@ -667,7 +764,7 @@ static TcPlan make_plan(const nnr_gemm_args* a, int mode) {
     if (chain < nkb_cap) { pl.split_k = 1; pl.chain_kb = chain; }
   }
   pl.max_splits = pl.split_k ? (nkb_cap + pl.chain_kb - 1) / pl.chain_kb : 1;
-  size_t stage = (size_t)pl.nplanes * ((size_t)TC_BM * 128 + (size_t)pl.block_n * 128);
+  size_t stage = (size_t)pl.nplanes * ((size_t)TC_BM * 128 + (size_t)(pl.pair ? pl.block_n / 2 : pl.block_n) * 128);
   int stages = (int)(TC_SMEM_BUDGET / stage);
   if (stages < 2) stages = 2;
   if (stages > 6) stages = 6;
@@ -764,7 +861,8 @@ static int run_tc(const nnr_gemm_args* a, cudaStream_t st) {
   const int ke = pl.kelem;
   rc = encode_map(&map_a, pa, BF16, pl.a_cols, a_pitch, pl.a_rows, a_prow, pl.nplanes, ke, pl.a_mn ? ke : TC_BM, pl.a_mn != 0);
   if (rc) return rc;
-  rc = encode_map(&map_b, pb, BF16, pl.b_cols, b_pitch, pl.b_rows, b_prow, pl.nplanes, ke, pl.b_mn ? ke : pl.block_n, pl.b_mn != 0);
+  rc = encode_map(&map_b, pb, BF16, pl.b_cols, b_pitch, pl.b_rows, b_prow, pl.nplanes, ke,
+                  pl.b_mn ? ke : (pl.pair ? pl.block_n / 2 : pl.block_n), pl.b_mn != 0);
   if (rc) return rc;
   TcParams p;
   p.M = a->M; p.N = a->N; p.K = a->K; p.m_dev = a->m_dev; p.k_dev = a->k_dev;
@@ -774,26 +872,43 @@ static int run_tc(const nnr_gemm_args* a, cudaStream_t st) {
   // bits 15 / 16 (1 = MN-major), N >> 3 at bits 17-22, M >> 4 at bits 24-28
   const uint32_t fmt = BF16 ? 1u : 2u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)pl.a_mn << 15) | ((uint32_t)pl.b_mn << 16) |
-            ((uint32_t)(pl.block_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            ((uint32_t)(pl.block_n >> 3) << 17) | ((uint32_t)((pl.pair ? 2 * TC_BM : TC_BM) >> 4) << 24);
   p.partial = pl.split_k ? (float*)(ws + pl.partial_off) : nullptr;
   p.epi = make_epi(a);
-  static bool attr_set[2] = {false, false};
+  static bool attr_set[2][2] = {{false, false}, {false, false}};
   static int num_sms = 0;
-  if (!attr_set[BF16 ? 1 : 0]) {
-    NNR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set[BF16 ? 1 : 0] = true;
+  if (!attr_set[BF16 ? 1 : 0][pl.pair]) {
+    if (pl.pair) NNR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    else NNR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[BF16 ? 1 : 0][pl.pair] = true;
   }
   if (num_sms == 0) {
     int dev = 0;
     NNR_CUDA(cudaGetDevice(&dev));
     NNR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  long cap_tiles = (long)((a->M + TC_BM - 1) / TC_BM) * ((a->N + pl.block_n - 1) / pl.block_n) * pl.max_splits;
-  int grid = (int)(cap_tiles < num_sms ? cap_tiles : num_sms);
   void* ph = nnr_prof_begin(0, -1.0, st);     // flops are filled in by the caller-side profiler (needs m_dev/k_dev)
-  gemm_tc_kernel<BF16><<<grid, TC_THREADS, pl.smem, st>>>(map_a, map_b, p);
-  nnr_prof_end(ph, st);
-  NNR_LAUNCH_CHECK("gemm_tc_kernel");
+  if (pl.pair) {
+    long cap_tiles = (long)((a->M + 2 * TC_BM - 1) / (2 * TC_BM)) * ((a->N + pl.block_n - 1) / pl.block_n);
+    long pairs = cap_tiles < num_sms / 2 ? cap_tiles : num_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3((unsigned)(2 * pairs)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+    void* kargs[] = {(void*)&map_a, (void*)&map_b, (void*)&p};
+    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)gemm_tc_kernel<BF16, true>, kargs);
+    nnr_count_launch(1);
+    if (e != cudaSuccess) { nnr_set_error("gemm_tc_kernel(pair): launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+    nnr_prof_end(ph, st);
+  } else {
+    long cap_tiles = (long)((a->M + TC_BM - 1) / TC_BM) * ((a->N + pl.block_n - 1) / pl.block_n) * pl.max_splits;
+    int grid = (int)(cap_tiles < num_sms ? cap_tiles : num_sms);
+    gemm_tc_kernel<BF16, false><<<grid, TC_THREADS, pl.smem, st>>>(map_a, map_b, p);
+    nnr_prof_end(ph, st);
+    NNR_LAUNCH_CHECK("gemm_tc_kernel");
+  }
   if (pl.split_k) {
     size_t tot = (size_t)a->M * a->N;
     void* ph2 = nnr_prof_begin(2, 0.0, st);

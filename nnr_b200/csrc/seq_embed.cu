@@ -147,7 +147,7 @@ extern "C" int nnr_embed_gather_fwd(const float* table, const int32_t* ids, cons
 // ------------------------------------------------------------------------------------------
 // nnr_embed_gather_bwd : sort slots by id, then chunked segment reduce (deterministic)
 // ------------------------------------------------------------------------------------------
-#define EB_CHUNK 512
+#define EB_CHUNK 256   // sorted slots per CTA: small chunks = more CTAs in flight (the per-run work is latency bound)
 struct EbMeta { int32_t head_cross, tail_cross, covering, head_key, tail_key, pad0, pad1, pad2; };
 
 __global__ void eb_keys_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ len, int N, int L, int V,
@@ -260,18 +260,17 @@ __global__ void __launch_bounds__(256) eb_chunk_kernel(const float* __restrict__
     s_key[i] = (pos >= 0 && pos < n_valid) ? keys[pos] : -1;
   }
   __syncthreads();
-  // run-start flags -> compact list (each warp owns 64 consecutive entries)
-  int f0 = 0, f1 = 0;
-  int i0 = w * 64 + lane, i1 = i0 + 32;
+  // run-start flags -> compact list (each warp owns 32 consecutive entries)
+  static_assert(EB_CHUNK == 256, "one entry per thread");
+  int f0 = 0;
+  const int i0 = tid;
   if (i0 < cnt) f0 = (i0 == 0) || (s_key[i0 + 1] != s_key[i0]);
-  if (i1 < cnt) f1 = (i1 == 0) || (s_key[i1 + 1] != s_key[i1]);
-  unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
-  if (lane == 0) s_wcnt[w] = __popc(b0) + __popc(b1);
+  const unsigned b0 = __ballot_sync(0xffffffffu, f0);
+  if (lane == 0) s_wcnt[w] = __popc(b0);
   __syncthreads();
   int wbase = 0;
   for (int j = 0; j < w; ++j) wbase += s_wcnt[j];
   if (f0) s_start[wbase + __popc(b0 & ((1u << lane) - 1))] = i0;
-  if (f1) s_start[wbase + __popc(b0) + __popc(b1 & ((1u << lane) - 1))] = i1;
   if (tid == 0) {
     int tot = 0;
     for (int j = 0; j < 8; ++j) tot += s_wcnt[j];
@@ -359,14 +358,32 @@ __global__ void eb_fix_kernel(const int32_t* __restrict__ off, int N, int E, con
   if (!m.tail_cross) return;
   if (m.covering == 1) return;  // middle of a run that started in an earlier chunk
   const int key = m.tail_key;
+  // the run continues through every following chunk it covers entirely and ends in the head piece of the next one:
+  // find that chunk first (warp-parallel scan of the flags), then add the pieces in order with independent loads
+  __shared__ int s_end;
+  if (threadIdx.x < 32) {
+    int k = j + 1;
+    const int nchunks = (n_valid + EB_CHUNK - 1) / EB_CHUNK;
+    while (true) {
+      const int kk = k + (int)threadIdx.x;
+      const bool cover = (kk < nchunks) && (meta[kk].covering == 1);
+      const unsigned m32 = __ballot_sync(0xffffffffu, cover);
+      if (m32 != 0xffffffffu) { k += __ffs(~m32) - 1; break; }
+      k += 32;
+    }
+    if (threadIdx.x == 0) s_end = k;           // last piece = head slot of chunk k
+  }
+  __syncthreads();
+  const int kend = s_end;
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
     float acc = slots_ws[(size_t)(2 * j + 1) * E + e];
     int k = j + 1;
-    while (true) {
-      acc += slots_ws[(size_t)(2 * k) * E + e];
-      if (meta[k].covering == 1) { ++k; continue; }
-      break;
+    for (; k + 4 <= kend + 1; k += 4) {
+      const float v0 = slots_ws[(size_t)(2 * k) * E + e], v1 = slots_ws[(size_t)(2 * k + 2) * E + e];
+      const float v2 = slots_ws[(size_t)(2 * k + 4) * E + e], v3 = slots_ws[(size_t)(2 * k + 6) * E + e];
+      acc += v0; acc += v1; acc += v2; acc += v3;
     }
+    for (; k <= kend; ++k) acc += slots_ws[(size_t)(2 * k) * E + e];
     float* d = dtable + (size_t)key * E + e;
     *d = accumulate ? (*d + acc) : acc;
   }

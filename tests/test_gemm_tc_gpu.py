@@ -142,3 +142,37 @@ def test_bf16x3_variant(cuda):
             worst = max(worst, err)
             assert err < 4e-5, (M, N, K, transA, transB, err)
     print('bf16x3 worst rel err', worst)
+
+
+@pytest.mark.parametrize('algo_name', ['ALGO_BF16X3', 'ALGO_TF32X3'])
+def test_cta_pair_tiles_large_m(cuda, algo_name):
+    """Row counts >= 2*128*148 run on CTA pairs (cta_group::2, 256-row tiles, B tile split across the pair):
+    device-side row bound, N tails, every epilogue input, both B layouts that qualify."""
+    from nnr_b200 import ops
+    algo = getattr(ops, algo_name)
+    g = torch.Generator().manual_seed(17)
+    cap, Mv = 40000, 38211                                     # capacity and device-side valid rows (odd tail)
+    m_dev = torch.tensor([Mv], dtype=torch.int32, device=cuda)
+    for (N, K, transB) in [(1600, 300, True), (400, 400, True), (200, 400, True), (300, 96, True), (256, 200, False)]:
+        A = torch.randn(cap, K, generator=g).to(cuda)
+        B = torch.randn((N, K) if transB else (K, N), generator=g).to(cuda)
+        bias = torch.randn(N, generator=g).to(cuda)
+        C = torch.full((cap, N), float('nan'), device=cuda)
+        ops.gemm(A, B, C, cap, N, K, A.stride(0), B.stride(0), N, False, transB, ops.EPI_BIAS, bias=bias, m_dev=m_dev, algo=algo)
+        ref = A[:Mv].double() @ (B.double().t() if transB else B.double()) + bias.double()
+        err = (C[:Mv].double() - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 4e-5, (N, K, transB, err)
+        assert torch.isnan(C[Mv:]).all()                       # rows beyond the device bound are not written
+    # gate epilogue (row bias through a row map, aux in, aux out) on the pair path
+    N, K = 400, 400
+    A = torch.randn(cap, K, generator=g).to(cuda)
+    W = torch.randn(N, K, generator=g).to(cuda) * 0.05
+    rb = torch.randn(77, N, generator=g).to(cuda)
+    rmap = torch.randint(0, 77, (cap,), generator=g).to(torch.int32).to(cuda)
+    gate = torch.empty(cap, N, device=cuda)
+    C = torch.empty(cap, N, device=cuda)
+    ops.gemm(A, W, C, cap, N, K, K, K, N, False, True, ops.EPI_GATE, rowbias=rb, ldrowbias=N, rowmap=rmap, aux=A, ldaux=K,
+             aux_out=gate, ldaux_out=N, m_dev=m_dev, algo=algo)
+    gref = torch.sigmoid(A[:Mv].double() @ W.double().t() + rb.double()[rmap[:Mv].long()])
+    assert (gate[:Mv].double() - gref).abs().max().item() < 2e-5
+    assert (C[:Mv].double() - gref * A[:Mv].double()).abs().max().item() < 1e-4
