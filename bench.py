@@ -217,6 +217,8 @@ def main():
     value = a.batch * world * a.steps / (ms / 1e3)
 
     # ---- end to end: pinned host batch -> device every step, loss read back every step ----------
+    for i in range(2):                                        # untimed warm-up of this path (allocator, copy engine)
+        ts.step(*batch_args(host[i % nb], dev)).item()
     barrier()
     e0.record()
     for i in range(a.steps):

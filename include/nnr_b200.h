@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NNR_ABI_VERSION 2
+#define NNR_ABI_VERSION 3
 
 const char* nnr_last_error(void);
 int nnr_abi_version(void);
@@ -109,6 +109,18 @@ int64_t nnr_tc_split_pitch(int C, int algo);
 size_t nnr_tc_split_bytes(int R, int C, int algo);
 int nnr_tc_split(const float* X, int64_t ld, int R, int C, const int32_t* r_dev, int algo, void* planes,
                  size_t planes_bytes, void* stream);
+/* Stable descending sort of small integer keys (the sequence lengths of newsEncoders.py:112,114):
+ * sorted_idx[rank] = original index, ties in ascending original index (= torch.sort on CUDA).  N <= 8192,
+ * 0 <= key <= max_key <= 1024 (keys are clamped). */
+int nnr_length_sort_desc(const int64_t* keys, int N, int max_key, int64_t* sorted_idx, void* stream);
+
+/* nnr_tc_split plus the column sums of X (rows < *r_dev) in the same pass: a bias gradient (trainer-side
+ * `dy.sum(0)`, i.e. the bias part of every nn.Linear / nn.LSTM backward) is the column sum of the dL/dy whose planes feed
+ * the dgrad / wgrad GEMMs.  Deterministic (fixed partial order).  colsum[C] is overwritten, or added to if accumulate. */
+size_t nnr_tc_split_colsum_workspace_bytes(int R, int C, int algo);
+int nnr_tc_split_colsum(const float* X, int64_t ld, int R, int C, const int32_t* r_dev, int algo, void* planes,
+                        size_t planes_bytes, float* colsum, int accumulate, void* workspace, size_t workspace_bytes,
+                        void* stream);
 /* the algorithm NNR_GEMM_AUTO resolves to (env NNR_GEMM_ALGO = simt | tf32x3 | bf16; default tf32x3) */
 int nnr_gemm_default_algo(void);
 

@@ -648,6 +648,127 @@ __global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__
   }
 }
 
+template <int MODE>
+__device__ __forceinline__ void tc_split_store4(void* out, size_t plane_stride, int Cp, int r, int c, float4 x) {
+  if (MODE >= 1) {
+    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out) + (size_t)r * Cp + c;
+    __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(ob);
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(x.x, x.y), h23 = __floats2bfloat162_rn(x.z, x.w);
+    o[0] = h01;
+    o[1] = h23;
+    if (MODE == 2) {
+      __nv_bfloat162* l = reinterpret_cast<__nv_bfloat162*>(ob + plane_stride);
+      l[0] = __floats2bfloat162_rn(x.x - __low2float(h01), x.y - __high2float(h01));
+      l[1] = __floats2bfloat162_rn(x.z - __low2float(h23), x.w - __high2float(h23));
+    }
+  } else {
+    float* hi = reinterpret_cast<float*>(out) + (size_t)r * Cp + c;
+    float4 h, l;
+    h.x = rna_tf32(x.x); h.y = rna_tf32(x.y); h.z = rna_tf32(x.z); h.w = rna_tf32(x.w);
+    l.x = rna_tf32(x.x - h.x); l.y = rna_tf32(x.y - h.y); l.z = rna_tf32(x.z - h.z); l.w = rna_tf32(x.w - h.w);
+    *reinterpret_cast<float4*>(hi) = h;
+    *reinterpret_cast<float4*>(hi + plane_stride) = l;
+  }
+}
+
+// Split + column sums in one pass over the matrix (a bias gradient is the column sum of the same dL/dy whose planes
+// feed the dgrad / wgrad GEMMs): one CTA per TCS_ROWS rows; thread (rs, g) owns 4-column groups g, g + G, ... and rows
+// r0 + rs, r0 + rs + RS, ...; per-CTA partial sums (row slots combined in fixed order) go to `partial`, a second
+// kernel adds the partials of the valid row blocks in block order -> deterministic.
+#define TCS_ROWS 64
+#define TCS_MAXG 2            // 4-column groups per thread: C <= 2048
+template <int MODE>
+__global__ void __launch_bounds__(256) tc_split_colsum_kernel(const float* __restrict__ src, int64_t ld, int R, int C, int Cp,
+                                                              const int32_t* __restrict__ r_dev, void* __restrict__ out,
+                                                              size_t plane_stride, float* __restrict__ partial) {
+  __shared__ float4 s_acc[256];
+  int Rv = R;
+  if (r_dev) Rv = min(R, *r_dev);
+  const int Rw = r_dev ? min(R, (Rv + 63) / 64 * 64) : R;        // rows whose planes must be defined (zero tail)
+  const int r0 = blockIdx.x * TCS_ROWS;
+  if (r0 >= Rw) return;
+  const int ncq = Cp >> 2;
+  const int G = min(ncq, 256), RS = 256 / G;
+  const int tid = threadIdx.x, g = tid % G, rs = tid / G;
+  const bool active = rs < RS;
+  float4 acc[TCS_MAXG];
+#pragma unroll
+  for (int j = 0; j < TCS_MAXG; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int r1 = min(r0 + TCS_ROWS, Rw);
+  if (active) {
+    for (int rb = r0 + rs; rb < r1; rb += 4 * RS) {
+      float4 x[4][TCS_MAXG];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u * RS;
+#pragma unroll
+        for (int j = 0; j < TCS_MAXG; ++j) {
+          const int cq = (g + j * G) * 4;
+          x[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < r1 && r < Rv && cq < Cp) {
+            const float* sp = src + (size_t)r * ld + cq;
+            if (cq + 3 < C) x[u][j] = __ldg(reinterpret_cast<const float4*>(sp));
+            else {
+              if (cq < C) x[u][j].x = __ldg(sp);
+              if (cq + 1 < C) x[u][j].y = __ldg(sp + 1);
+              if (cq + 2 < C) x[u][j].z = __ldg(sp + 2);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u * RS;
+        if (r >= r1) continue;
+#pragma unroll
+        for (int j = 0; j < TCS_MAXG; ++j) {
+          const int cq = (g + j * G) * 4;
+          if (cq >= Cp) continue;
+          tc_split_store4<MODE>(out, plane_stride, Cp, r, cq, x[u][j]);
+          acc[j].x += x[u][j].x; acc[j].y += x[u][j].y; acc[j].z += x[u][j].z; acc[j].w += x[u][j].w;
+        }
+      }
+    }
+  }
+  // combine the row slots in fixed order, one group pass at a time
+  for (int j = 0; j < TCS_MAXG; ++j) {
+    __syncthreads();
+    if (active) s_acc[rs * G + g] = acc[j];
+    __syncthreads();
+    const int cq = (g + j * G) * 4;
+    if (rs == 0 && cq < Cp) {
+      float4 t = s_acc[g];
+      for (int q = 1; q < RS; ++q) { const float4 o = s_acc[q * G + g]; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
+      float* dst = partial + (size_t)blockIdx.x * Cp + cq;
+      *reinterpret_cast<float4*>(dst) = t;
+    }
+  }
+}
+// out[c] = sum over the valid row blocks; 16 slices per column (slice s takes blocks s, s+16, ...) combined in slice order
+__global__ void __launch_bounds__(512) tc_split_colsum_reduce(const float* __restrict__ partial, int nblocks, int R, int C, int Cp,
+                                                              const int32_t* __restrict__ r_dev, float* __restrict__ out, int accumulate) {
+  __shared__ float s_sum[16][33];
+  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  int Rv = R;
+  if (r_dev) Rv = min(R, *r_dev);
+  const int nb = min(nblocks, (Rv + TCS_ROWS - 1) / TCS_ROWS);
+  float a0 = 0.f, a1 = 0.f;
+  if (c < C) {
+    int b = sl;
+    for (; b + 16 < nb; b += 32) { a0 += partial[(size_t)b * Cp + c]; a1 += partial[(size_t)(b + 16) * Cp + c]; }
+    if (b < nb) a0 += partial[(size_t)b * Cp + c];
+  }
+  s_sum[sl][cl] = a0 + a1;
+  __syncthreads();
+  if (sl == 0 && c < C) {
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc += s_sum[q][cl];
+    out[c] = accumulate ? out[c] + acc : acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -947,4 +1068,34 @@ extern "C" int nnr_tc_split(const float* X, int64_t ld, int R, int C, const int3
   if (mode == 1) return split_operand<1>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (cudaStream_t)stream);
   if (mode == 2) return split_operand<2>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (cudaStream_t)stream);
   return split_operand<0>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (cudaStream_t)stream);
+}
+
+// split + column sums of the same matrix in one pass (see tc_split_colsum_kernel); workspace = per-row-block partials
+extern "C" size_t nnr_tc_split_colsum_workspace_bytes(int R, int C, int algo) {
+  if (R <= 0 || C <= 0) return 0;
+  return (size_t)((R + TCS_ROWS - 1) / TCS_ROWS) * (size_t)nnr_tc_split_pitch(C, algo) * sizeof(float);
+}
+extern "C" int nnr_tc_split_colsum(const float* X, int64_t ld, int R, int C, const int32_t* r_dev, int algo, void* planes,
+                                   size_t planes_bytes, float* colsum, int accumulate, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  NNR_REQUIRE(X && planes && colsum && workspace && R > 0 && C > 0 && ld >= C, NNR_ERR_ARG, "nnr_tc_split_colsum: bad arguments");
+  NNR_REQUIRE(planes_bytes >= nnr_tc_split_bytes(R, C, algo), NNR_ERR_WORKSPACE, "nnr_tc_split_colsum: planes buffer too small");
+  NNR_REQUIRE(workspace_bytes >= nnr_tc_split_colsum_workspace_bytes(R, C, algo), NNR_ERR_WORKSPACE,
+              "nnr_tc_split_colsum: workspace too small");
+  NNR_REQUIRE(nnr_aligned16(planes) && nnr_aligned16(workspace) && nnr_aligned16(X) && ld % 4 == 0, NNR_ERR_ALIGN,
+              "nnr_tc_split_colsum: X, planes, workspace must be 16B aligned and ld %% 4 == 0");
+  const int mode = algo_mode(algo);
+  const int Cp = (int)nnr_tc_split_pitch(C, algo);
+  NNR_REQUIRE(Cp <= 4 * 256 * TCS_MAXG, NNR_ERR_UNSUPPORTED, "nnr_tc_split_colsum: more than %d columns", 4 * 256 * TCS_MAXG);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblocks = (R + TCS_ROWS - 1) / TCS_ROWS;
+  void* ph = nnr_prof_begin(1, 0.0, st);
+  if (mode == 1) tc_split_colsum_kernel<1><<<nblocks, 256, 0, st>>>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (float*)workspace);
+  else if (mode == 2) tc_split_colsum_kernel<2><<<nblocks, 256, 0, st>>>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (float*)workspace);
+  else tc_split_colsum_kernel<0><<<nblocks, 256, 0, st>>>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (float*)workspace);
+  nnr_prof_end(ph, st);
+  NNR_LAUNCH_CHECK("tc_split_colsum_kernel");
+  tc_split_colsum_reduce<<<(C + 31) / 32, 512, 0, st>>>((const float*)workspace, nblocks, R, C, Cp, r_dev, colsum, accumulate);
+  NNR_LAUNCH_CHECK("tc_split_colsum_reduce");
+  return 0;
 }

@@ -92,10 +92,11 @@ def wgrad(dy, x, M, N, K, k_dev=None, out=None, accumulate=False, dy_planes=None
     return out
 
 
-def split_tokens(x, cap, cols, ntok):
+def split_tokens(x, cap, cols, ntok, colsum_out=None):
     """hi/lo operand planes of a packed per-token tensor, shared by every GEMM that consumes it (forward,
-    dgrad and wgrad read the same row-major planes; the row tail beyond the token count is zero-filled)"""
-    return ops.tc_split(x, cap, cols, x.stride(0), ntok)
+    dgrad and wgrad read the same row-major planes; the row tail beyond the token count is zero-filled).
+    ``colsum_out`` [cols]: also the column sums over the valid tokens (a bias gradient) from the same pass."""
+    return ops.tc_split(x, cap, cols, x.stride(0), ntok, colsum_out=colsum_out)
 
 
 def colsum(X, M, N, m_dev=None, out=None, accumulate=False):
@@ -123,12 +124,20 @@ class _Mod:
     pass
 
 
-def _domain_sorts(len64, domains):
+def _sort_desc(keys, max_key):
+    """sorted indices of ``sort_fn(keys, descending=True)``.  With the default ``torch.sort`` on a CUDA tensor the
+    counting-sort kernel gives the same permutation (stable, like ATen's radix sort) in one small launch."""
+    if sort_fn is torch.sort and keys.is_cuda and keys.numel() <= 8192 and max_key <= 1024:
+        return ops.length_sort_desc(keys.contiguous(), max_key)
+    return sort_fn(keys, descending=True)[1]
+
+
+def _domain_sorts(len64, domains, max_key):
     """newsEncoders.py:112-115 per pairing domain (one reference news_encoder(...) call each): the same two
     torch.sort calls on that call's lengths; indices are returned in global row numbering."""
     sorted_idx, desorted_idx = [], []
     for start, count in domains:
-        _, si = sort_fn(len64[start:start + count], descending=True)
+        si = _sort_desc(len64[start:start + count], max_key)
         # newsEncoders.py:113,115 sort the permutation again to invert it; the inverse of a permutation is
         # unique, so a scatter gives the identical result without a second radix sort
         di = torch.empty_like(si).scatter_(0, si, torch.arange(count, device=si.device))
@@ -149,11 +158,11 @@ def _cne_modality_forward(P, x, ids, mask_u8, N, L, E, Hd, training, p_drop, see
     m.ntok = m.off[N:]                                         # device scalar (view), no sync
     # newsEncoders.py:112-115 -- same torch.sort calls (tie-breaking of the device's sort), per domain
     len64 = m.len.long()
-    m.sorted_idx, m.desorted_idx = _domain_sorts(len64, domains)
+    m.sorted_idx, m.desorted_idx = _domain_sorts(len64, domains, L)
     if len(domains) == 1:
         m.order = m.sorted_idx[0].to(torch.int32)
     else:                                                     # LSTM tiling only needs "longest first"
-        m.order = torch.sort(len64, descending=True)[1].to(torch.int32)
+        m.order = _sort_desc(len64, L).to(torch.int32)
     m.seed = seed
     m.p = p_drop if training else 0.0
     m.emb = _empty((cap, E), dev)
@@ -292,10 +301,11 @@ class CNEFunction(torch.autograd.Function):
                               w2=P[sa + 'affine2.weight'], alpha=m.alpha_self, dpooled=d_self[x], lddp=D2, dX=m.dhg,
                               lddx=D2, accumulate_dx=dhg_written[x], dU=dU, lddu=A, dw2_partial=dw2p)
             G[sa + 'affine2.weight'] = colsum(dw2p, N, A).view(1, A)
-            dU_pl = split_tokens(dU, m.cap, A, m.ntok)
+            db1 = _empty((A,), dev)
+            dU_pl = split_tokens(dU, m.cap, A, m.ntok, colsum_out=db1)
             matmul_nn(dU, P[sa + 'affine1.weight'], m.cap, m.ntok, out=m.dhg, accumulate=True, x_planes=dU_pl)
             G[sa + 'affine1.weight'] = wgrad(dU, m.hg, m.cap, A, D2, k_dev=m.ntok, dy_planes=dU_pl, x_planes=m.hg_pl)
-            G[sa + 'affine1.bias'] = colsum(dU, m.cap, A, m.ntok)
+            G[sa + 'affine1.bias'] = db1
             del dU, dU_pl
             m.hg_pl = None
         # 4. selective gate backward
@@ -327,14 +337,14 @@ class CNEFunction(torch.autograd.Function):
             dz = m.gates                                                                      # [cap, 8H] = dL/dgx
             hprev = _empty((m.cap, D2), dev)
             ops.lstm_shift_h(m.h, m.len, m.off, m.tok_row, N, m.L, Hd, hprev)
-            dz_pl = split_tokens(dz, m.cap, 8 * Hd, m.ntok)
+            db = _empty((8 * Hd,), dev)
+            dz_pl = split_tokens(dz, m.cap, 8 * Hd, m.ntok, colsum_out=db)
             for d, sfx in enumerate(('', '_reverse')):
                 G[pre + 'weight_hh_l0' + sfx] = wgrad(dz[:, d * 4 * Hd:(d + 1) * 4 * Hd], hprev[:, d * Hd:(d + 1) * Hd],
                                                      m.cap, 4 * Hd, Hd, k_dev=m.ntok,
                                                      dy_planes=dz_pl.cols(d * 4 * Hd, (d + 1) * 4 * Hd) if dz_pl else None)
             dwih = wgrad(dz, m.emb, m.cap, 8 * Hd, E, k_dev=m.ntok, dy_planes=dz_pl, x_planes=m.emb_pl)
             m.emb_pl = None
-            db = colsum(dz, m.cap, 8 * Hd, m.ntok)
             for d, sfx in enumerate(('', '_reverse')):
                 G[pre + 'weight_ih_l0' + sfx] = dwih[d * 4 * Hd:(d + 1) * 4 * Hd]
                 G[pre + 'bias_ih_l0' + sfx] = db[d * 4 * Hd:(d + 1) * 4 * Hd]

@@ -91,14 +91,26 @@ def default_algo():
     return int(lib.nnr_gemm_default_algo())
 
 
-def tc_split(x, rows, cols, ld, r_dev=None):
+def tc_split(x, rows, cols, ld, r_dev=None, colsum_out=None, accumulate=False):
     """pre-split a row-major [rows, cols] fp32 matrix once so several GEMMs can share the planes; returns None
-    when the exact-fp32 backend is selected (NNR_GEMM_ALGO=simt)"""
+    when the exact-fp32 backend is selected (NNR_GEMM_ALGO=simt).  With ``colsum_out`` the column sums of the valid
+    rows are produced by the same pass (nnr_tc_split_colsum)."""
     algo = default_algo()
     if algo == ALGO_SIMT:
+        if colsum_out is not None:
+            colsum(x, ld, rows, cols, colsum_out, accumulate, r_dev)
         return None
     nbytes = int(lib.nnr_tc_split_bytes(rows, cols, algo))
     buf = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    if colsum_out is not None and cols <= 2048 and ld % 4 == 0 and x.data_ptr() % 16 == 0:
+        wsb = int(lib.nnr_tc_split_colsum_workspace_bytes(rows, cols, algo))
+        ws = workspace(wsb, x.device, 'split_colsum')
+        check(lib.nnr_tc_split_colsum(_p(x, _F32), ld, rows, cols, _p(r_dev, _I32), algo, buf.data_ptr(), nbytes,
+                                      _p(colsum_out, _F32), int(accumulate), ws.data_ptr(), ws.numel(), _stream()),
+              'nnr_tc_split_colsum')
+        return Planes(buf, rows, cols, int(lib.nnr_tc_split_pitch(cols, algo)), 2 if algo in (ALGO_BF16, ALGO_BF16X3) else 4)
+    if colsum_out is not None:
+        colsum(x, ld, rows, cols, colsum_out, accumulate, r_dev)
     check(lib.nnr_tc_split(_p(x, _F32), ld, rows, cols, _p(r_dev, _I32), algo, buf.data_ptr(), nbytes, _stream()),
           'nnr_tc_split')
     return Planes(buf, rows, cols, int(lib.nnr_tc_split_pitch(cols, algo)), 2 if algo in (ALGO_BF16, ALGO_BF16X3) else 4)
@@ -135,6 +147,14 @@ def colsum(X, ldx, M, N, out, accumulate=False, m_dev=None):
     ws = workspace(nbytes, X.device, 'colsum')
     check(lib.nnr_colsum(_p(X, _F32), ldx, M, N, _p(m_dev, _I32), _p(out, _F32), int(accumulate), ws.data_ptr(),
                          ws.numel(), _stream()), 'nnr_colsum')
+
+
+def length_sort_desc(len64, max_key):
+    """sorted_idx of torch.sort(len64, descending=True) for small integer keys (stable: ties by original index)"""
+    N = len64.numel()
+    out = torch.empty(N, dtype=torch.int64, device=len64.device)
+    check(lib.nnr_length_sort_desc(_p(len64, _I64), N, int(max_key), _p(out, _I64), _stream()), 'nnr_length_sort_desc')
+    return out
 
 
 def segment_colsum(X, ldx, off, N, D, out, ldo):

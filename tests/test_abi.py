@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(_lib.lib, s), 'missing symbol ' + s
         assert s in _lib.SIGNATURES, 'no ctypes signature for ' + s
-    assert _lib.lib.nnr_abi_version() == 2
+    assert _lib.lib.nnr_abi_version() == 3
 
 
 def test_argument_errors_are_reported_without_a_gpu():

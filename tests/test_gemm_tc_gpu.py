@@ -176,3 +176,29 @@ def test_cta_pair_tiles_large_m(cuda, algo_name):
     gref = torch.sigmoid(A[:Mv].double() @ W.double().t() + rb.double()[rmap[:Mv].long()])
     assert (gate[:Mv].double() - gref).abs().max().item() < 2e-5
     assert (C[:Mv].double() - gref * A[:Mv].double()).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize('cols', [1600, 200, 300, 96])
+def test_split_with_column_sums(cuda, cols):
+    """nnr_tc_split_colsum: same planes as nnr_tc_split (bit-exact), column sums over the device-side valid rows"""
+    from nnr_b200 import ops
+    g = torch.Generator().manual_seed(cols)
+    cap, valid = 5000, 4321
+    x = torch.randn(cap, cols, generator=g).to(cuda)
+    r_dev = torch.tensor([valid], dtype=torch.int32, device=cuda)
+    ref_pl = ops.tc_split(x, cap, cols, cols, r_dev)
+    out = torch.full((cols,), float('nan'), device=cuda)
+    pl = ops.tc_split(x, cap, cols, cols, r_dev, colsum_out=out)
+    rows_w = (valid + 63) // 64 * 64
+    pitch = pl.pitch
+    a = ref_pl.buf.view(torch.int16).view(2, cap, pitch)[:, :rows_w]
+    b = pl.buf.view(torch.int16).view(2, cap, pitch)[:, :rows_w]
+    assert torch.equal(a, b)
+    ref = x[:valid].double().sum(0)
+    assert (out.double() - ref).abs().max().item() < 1e-3 * ref.abs().max().item() + 1e-3
+    out2 = out.clone()
+    ops.tc_split(x, cap, cols, cols, r_dev, colsum_out=out2, accumulate=True)
+    assert torch.allclose(out2, 2 * out, rtol=1e-6, atol=1e-6)
+    out3 = torch.empty_like(out)
+    ops.tc_split(x, cap, cols, cols, r_dev, colsum_out=out3)
+    assert torch.equal(out3, out)                                  # deterministic

@@ -497,3 +497,17 @@ def test_flat_clip_adam_matches_torch(cuda):
         ops.flat_clip_adam(w, grad, m, v, 1e-3, 0.9, 0.999, 1e-8, 4.0, 1.0, step, norm)
         assert abs(norm.item() - total.item()) / total.item() < 1e-5
         assert (w - ref.detach()).abs().max().item() < 2e-6, step
+
+
+def test_length_sort_matches_torch_sort_on_device(cuda):
+    """nnr_length_sort_desc == torch.sort(len, descending=True) on CUDA, including the order of ties
+    (newsEncoders.py:112-115 semantics on the device)"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(77)
+    for N, maxk in [(3520, 128), (3520, 32), (320, 128), (1, 5), (4097, 7), (8192, 1024)]:
+        keys = torch.randint(1, maxk + 1, (N,), generator=g).to(cuda)
+        ref = torch.sort(keys, descending=True)[1]
+        got = ops.length_sort_desc(keys, maxk)
+        assert torch.equal(ref, got), (N, maxk)
+        stable = torch.sort(keys, descending=True, stable=True)[1]
+        assert torch.equal(stable, got)
