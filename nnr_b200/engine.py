@@ -117,6 +117,14 @@ CNE_PARAM_NAMES = (
     + ['%s_self_attention.%s' % (x, w) for x in ('title', 'content') for w in ('affine1.weight', 'affine1.bias', 'affine2.weight')]
 )
 CNE_CROSS_PARAM_NAMES = ['%s_cross_attention.%s' % (x, w) for x in ('title', 'content') for w in ('K.weight', 'Q.weight', 'Q.bias')]
+CNE_GATE_PARAM_NAMES = ['%s_%s' % (x, w) for x in ('title', 'content') for w in ('H.weight', 'M.weight', 'M.bias')]
+
+
+def cne_param_names(cross_attention=True, gate=True):
+    """parameter order of CNEFunction for a variant: CNE (both), CNE_wo_CA (no cross attention,
+    variantEncoders.py:263-339), CNE_wo_CS (no selective gate, variantEncoders.py:190-260)"""
+    names = [n for n in CNE_PARAM_NAMES if gate or n not in CNE_GATE_PARAM_NAMES]
+    return names + (CNE_CROSS_PARAM_NAMES if cross_attention else [])
 
 
 class _Mod:
@@ -182,17 +190,21 @@ def _cne_modality_forward(P, x, ids, mask_u8, N, L, E, Hd, training, p_drop, see
     return m
 
 
-def _cne_gate_self(P, x, m, m_other_cn, partner, N, Hd, A):
-    """selective gate (newsEncoders.py:128-131) + additive self attention (:133-134)"""
+def _cne_gate_self(P, x, m, m_other_cn, partner, N, Hd, A, gate=True):
+    """selective gate (newsEncoders.py:128-131) + additive self attention (:133-134); gate=False (CNE_wo_CS,
+    variantEncoders.py:250-252): the attentions read the LSTM states directly"""
     dev = m.h.device
     D2 = 2 * Hd
-    m.partner = partner
-    m.cm_sel = m_other_cn.index_select(0, partner)                                            # [N, 2H]
-    m.mproj = linear(m.cm_sel, P[x + '_M.weight'], N, None, P[x + '_M.bias'])                 # [N, 2H]
-    m.g = _empty((m.cap, D2), dev)
-    m.h_pl = split_tokens(m.h, m.cap, D2, m.ntok)
-    m.hg = linear(m.h, P[x + '_H.weight'], m.cap, m.ntok, None, EPI_GATE, rowbias=m.mproj, ldrowbias=D2,
-                  rowmap=m.tok_row, aux=m.h, ldaux=D2, aux_out=m.g, ldaux_out=D2, x_planes=m.h_pl)
+    if gate:
+        m.partner = partner
+        m.cm_sel = m_other_cn.index_select(0, partner)                                            # [N, 2H]
+        m.mproj = linear(m.cm_sel, P[x + '_M.weight'], N, None, P[x + '_M.bias'])                 # [N, 2H]
+        m.g = _empty((m.cap, D2), dev)
+        m.h_pl = split_tokens(m.h, m.cap, D2, m.ntok)
+        m.hg = linear(m.h, P[x + '_H.weight'], m.cap, m.ntok, None, EPI_GATE, rowbias=m.mproj, ldrowbias=D2,
+                      rowmap=m.tok_row, aux=m.h, ldaux=D2, aux_out=m.g, ldaux_out=D2, x_planes=m.h_pl)
+    else:
+        m.hg = m.h
     sa = x + '_self_attention.'
     m.hg_pl = split_tokens(m.hg, m.cap, D2, m.ntok)
     m.u = linear(m.hg, P[sa + 'affine1.weight'], m.cap, m.ntok, P[sa + 'affine1.bias'], EPI_BIAS_TANH, x_planes=m.hg_pl)
@@ -221,7 +233,8 @@ class CNEFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, meta, title_text, title_mask, content_text, content_mask, category, subCategory, *params):
-        names = CNE_PARAM_NAMES + (CNE_CROSS_PARAM_NAMES if meta['cross_attention'] else [])
+        gate = meta.get('gate', True)
+        names = cne_param_names(meta['cross_attention'], gate)
         P = dict(zip(names, params))
         N, T, Lc = meta['N'], meta['T'], meta['A_len']
         E, Hd, A = meta['E'], meta['Hd'], meta['att']
@@ -234,8 +247,8 @@ class CNEFunction(torch.autograd.Function):
         # title row r of a call is gated with the content memory of the news at the same sorted rank
         partner_t = torch.cat([cs.index_select(0, td) for cs, td in zip(c.sorted_idx, t.desorted_idx)])
         partner_c = torch.cat([ts.index_select(0, cd) for ts, cd in zip(t.sorted_idx, c.desorted_idx)])
-        _cne_gate_self(P, 'title', t, c.c_n, partner_t, N, Hd, A)
-        _cne_gate_self(P, 'content', c, t.c_n, partner_c, N, Hd, A)
+        _cne_gate_self(P, 'title', t, c.c_n, partner_t, N, Hd, A, gate)
+        _cne_gate_self(P, 'content', c, t.c_n, partner_c, N, Hd, A, gate)
         if meta['cross_attention']:
             _cne_cross(P, 'title', t, c.self_out, N, Hd, A)
             _cne_cross(P, 'content', c, t.self_out, N, Hd, A)
@@ -310,7 +323,12 @@ class CNEFunction(torch.autograd.Function):
             m.hg_pl = None
         # 4. selective gate backward
         d_cm_sel = {}
+        gate = meta.get('gate', True)
         for x, m in mods.items():
+            if not gate:                       # CNE_wo_CS: hg is h, nothing flows into the other modality's cell state
+                m.dh = m.dhg
+                d_cm_sel[x] = None
+                continue
             dz = _empty((m.cap, D2), dev)
             dh0 = _empty((m.cap, D2), dev)
             ops.gate_bwd_pre(m.dhg, m.h, m.g, m.cap * D2, m.ntok, D2, dz, dh0)
@@ -326,8 +344,11 @@ class CNEFunction(torch.autograd.Function):
             d_cm_sel[x] = matmul_nn(dmproj, P[x + '_M.weight'], N)                            # grad of cn_other[partner]
             del dz, dh0, dz_pl
         # partner_t and partner_c are inverse permutations of each other
-        dcn = {'content': d_cm_sel['title'].index_select(0, c.partner),
-               'title': d_cm_sel['content'].index_select(0, t.partner)}
+        if gate:
+            dcn = {'content': d_cm_sel['title'].index_select(0, c.partner),
+                   'title': d_cm_sel['content'].index_select(0, t.partner)}
+        else:
+            dcn = {'content': torch.zeros(N, D2, device=dev), 'title': torch.zeros(N, D2, device=dev)}
         # 5. LSTM backward + input projection + embedding scatter
         dtable = _empty(P['word_embedding.weight'].shape, dev)
         first = True

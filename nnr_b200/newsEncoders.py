@@ -48,6 +48,7 @@ class NewsEncoder(nn.Module):
 
 class CNE(NewsEncoder):
     cross_attention = True
+    selective_gate = True
     gate_gain = 'sigmoid'
 
     def __init__(self, config):
@@ -60,10 +61,11 @@ class CNE(NewsEncoder):
         # parameter holders only: the LSTM recurrence runs in nnr_lstm_fwd/bwd, never through cuDNN
         self.title_lstm = nn.LSTM(self.word_embedding_dim, self.hidden_dim, batch_first=True, bidirectional=True)
         self.content_lstm = nn.LSTM(self.word_embedding_dim, self.hidden_dim, batch_first=True, bidirectional=True)
-        self.title_H = nn.Linear(self.hidden_dim * 2, self.hidden_dim * 2, bias=False)
-        self.title_M = nn.Linear(self.hidden_dim * 2, self.hidden_dim * 2, bias=True)
-        self.content_H = nn.Linear(self.hidden_dim * 2, self.hidden_dim * 2, bias=False)
-        self.content_M = nn.Linear(self.hidden_dim * 2, self.hidden_dim * 2, bias=True)
+        if self.selective_gate:
+            self.title_H = nn.Linear(self.hidden_dim * 2, self.hidden_dim * 2, bias=False)
+            self.title_M = nn.Linear(self.hidden_dim * 2, self.hidden_dim * 2, bias=True)
+            self.content_H = nn.Linear(self.hidden_dim * 2, self.hidden_dim * 2, bias=False)
+            self.content_M = nn.Linear(self.hidden_dim * 2, self.hidden_dim * 2, bias=True)
         self.title_self_attention = Attention(self.hidden_dim * 2, config.attention_dim)
         self.content_self_attention = Attention(self.hidden_dim * 2, config.attention_dim)
         if self.cross_attention:
@@ -78,13 +80,14 @@ class CNE(NewsEncoder):
                     nn.init.orthogonal_(parameter.data)
                 else:
                     nn.init.zeros_(parameter.data)
-        gain = nn.init.calculate_gain(self.gate_gain) if self.gate_gain else 1.0
-        nn.init.xavier_uniform_(self.title_H.weight, gain=gain)
-        nn.init.xavier_uniform_(self.title_M.weight, gain=gain)
-        nn.init.zeros_(self.title_M.bias)
-        nn.init.xavier_uniform_(self.content_H.weight, gain=gain)
-        nn.init.xavier_uniform_(self.content_M.weight, gain=gain)
-        nn.init.zeros_(self.content_M.bias)
+        if self.selective_gate:
+            gain = nn.init.calculate_gain(self.gate_gain) if self.gate_gain else 1.0
+            nn.init.xavier_uniform_(self.title_H.weight, gain=gain)
+            nn.init.xavier_uniform_(self.title_M.weight, gain=gain)
+            nn.init.zeros_(self.title_M.bias)
+            nn.init.xavier_uniform_(self.content_H.weight, gain=gain)
+            nn.init.xavier_uniform_(self.content_M.weight, gain=gain)
+            nn.init.zeros_(self.content_M.bias)
         self.title_self_attention.initialize()
         self.content_self_attention.initialize()
         if self.cross_attention:
@@ -92,9 +95,15 @@ class CNE(NewsEncoder):
             self.content_cross_attention.initialize()
 
     def _params(self):
-        names = engine.CNE_PARAM_NAMES + (engine.CNE_CROSS_PARAM_NAMES if self.cross_attention else [])
-        sd = dict(self.named_parameters())
-        return [sd[k] for k in names]
+        # the Parameter OBJECTS are fixed for the life of the module (optimizers / TrainStep rebind .data, not the
+        # objects), so the module tree is walked once, not on every forward
+        cached = self.__dict__.get('_param_list')
+        if cached is None:
+            names = engine.cne_param_names(self.cross_attention, self.selective_gate)
+            sd = dict(self.named_parameters())
+            cached = [sd[k] for k in names]
+            self.__dict__['_param_list'] = cached
+        return cached
 
     def forward(self, title_text, title_mask, title_entity, content_text, content_mask, content_entity, category, subCategory, user_embedding):
         return self.encode_calls([(title_text, title_mask, content_text, content_mask, category, subCategory)])[0]
@@ -133,6 +142,6 @@ class CNE(NewsEncoder):
             sub = torch.cat([c[5].reshape(-1).to(i32) for c in calls])
         meta = dict(N=start, T=T, A_len=A, E=self.word_embedding_dim, Hd=self.hidden_dim, att=self.attention_dim,
                     training=self.training, p_drop=float(self.dropout_rate), cross_attention=self.cross_attention,
-                    domains=domains)
+                    gate=self.selective_gate, domains=domains)
         rep = engine.CNEFunction.apply(meta, tt, tm, ct, cm, cat, sub, *self._params())
         return [rep[s:s + cnt].view(B, n, self.news_embedding_dim) for (s, cnt), (B, n) in zip(domains, shapes)]

@@ -57,7 +57,8 @@ class TrainStep:
 
     def step(self, *batch):
         """one full training step; returns the (device) loss tensor without synchronising"""
-        self.model.train()
+        if not self.model.training:
+            self.model.train()
         logits = self.model(*batch)
         loss = negative_log_softmax(logits)
         self.gflat.zero_()

@@ -55,9 +55,13 @@ class SUE(UserEncoder):
         self.interClusterAttention.initialize()
 
     def _params(self):
-        names = engine.sue_param_names(self.gcn_layer_num) if self.hca else engine.sue_wo_hca_param_names(self.gcn_layer_num)
-        sd = {k: v for k, v in self.named_parameters() if not k.startswith('news_encoder.')}
-        return [sd[k] for k in names]
+        cached = self.__dict__.get('_param_list')      # see newsEncoders.CNE._params
+        if cached is None:
+            names = engine.sue_param_names(self.gcn_layer_num) if self.hca else engine.sue_wo_hca_param_names(self.gcn_layer_num)
+            sd = {k: v for k, v in self.named_parameters() if not k.startswith('news_encoder.')}
+            cached = [sd[k] for k in names]
+            self.__dict__['_param_list'] = cached
+        return cached
 
     def forward(self, user_title_text, user_title_mask, user_title_entity, user_content_text, user_content_mask, user_content_entity,
                 user_category, user_subCategory, user_history_mask, user_history_graph, user_history_category_mask,

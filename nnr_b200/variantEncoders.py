@@ -12,6 +12,11 @@ class CNE_wo_CA(CNE):
     gate_gain = None
 
 
+class CNE_wo_CS(CNE):
+    """CNE without the cross-selective gate (variantEncoders.py:190-260): both attentions read the LSTM states."""
+    selective_gate = False
+
+
 class SUE_wo_HCA(UserEncoder):
     """GCN + plain additive attention over the history rows (no mask), repeated over candidates."""
     hca = False

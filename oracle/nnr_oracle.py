@@ -52,15 +52,16 @@ def param_shapes(cfg):
             s[ne + f'{x}_lstm.weight_hh_l0{sfx}'] = (4 * Hd, Hd)
             s[ne + f'{x}_lstm.bias_ih_l0{sfx}'] = (4 * Hd,)
             s[ne + f'{x}_lstm.bias_hh_l0{sfx}'] = (4 * Hd,)
-    for x in ('title', 'content'):
-        s[ne + f'{x}_H.weight'] = (2 * Hd, 2 * Hd)
-        s[ne + f'{x}_M.weight'] = (2 * Hd, 2 * Hd)
-        s[ne + f'{x}_M.bias'] = (2 * Hd,)
+    if cfg.news_encoder != 'CNE_wo_CS':                 # variantEncoders.py:190-206 has no gate parameters
+        for x in ('title', 'content'):
+            s[ne + f'{x}_H.weight'] = (2 * Hd, 2 * Hd)
+            s[ne + f'{x}_M.weight'] = (2 * Hd, 2 * Hd)
+            s[ne + f'{x}_M.bias'] = (2 * Hd,)
     for x in ('title', 'content'):
         s[ne + f'{x}_self_attention.affine1.weight'] = (A, 2 * Hd)
         s[ne + f'{x}_self_attention.affine1.bias'] = (A,)
         s[ne + f'{x}_self_attention.affine2.weight'] = (1, A)
-    if cfg.news_encoder == 'CNE':
+    if cfg.news_encoder in ('CNE', 'CNE_wo_CS'):
         for x in ('title', 'content'):
             s[ne + f'{x}_cross_attention.K.weight'] = (A, 2 * Hd)
             s[ne + f'{x}_cross_attention.Q.weight'] = (A, 2 * Hd)
@@ -247,7 +248,7 @@ def scaled_dot_candidate_attention(p, prefix, feature, query, mask=None):
 
 def cne_forward(p, cfg, title_text, title_mask, content_text, content_mask, category, subCategory,
                 pre='news_encoder.', sort_fn=None, lstm_impl='loop', dropout_masks=None,
-                cross_attention=True):
+                cross_attention=True, gate=True):
     """newsEncoders.py:102-141 (eval mode, or train mode with externally supplied keep-masks).
 
     The reference runs the LSTM in length-sorted order and adds the *other* modality's memory
@@ -269,14 +270,15 @@ def cne_forward(p, cfg, title_text, title_mask, content_text, content_mask, cate
         content = content * dropout_masks['content']
     th, t_m = bilstm(p, pre + 'title_lstm.', title, tl, lstm_impl)
     ch, c_m = bilstm(p, pre + 'content_lstm.', content, cl, lstm_impl)
-    c_m_for_title = c_m[sc[dt]]                       # content memory paired by sort rank
-    t_m_for_content = t_m[st[dc]]
-    t_gate = torch.sigmoid(th @ p[pre + 'title_H.weight'].t()
-                           + (c_m_for_title @ p[pre + 'title_M.weight'].t() + p[pre + 'title_M.bias']).unsqueeze(1))
-    c_gate = torch.sigmoid(ch @ p[pre + 'content_H.weight'].t()
-                           + (t_m_for_content @ p[pre + 'content_M.weight'].t() + p[pre + 'content_M.bias']).unsqueeze(1))
-    th = th * t_gate
-    ch = ch * c_gate
+    if gate:                                          # CNE_wo_CS (variantEncoders.py:244-252) skips the selective gate
+        c_m_for_title = c_m[sc[dt]]                   # content memory paired by sort rank
+        t_m_for_content = t_m[st[dc]]
+        t_gate = torch.sigmoid(th @ p[pre + 'title_H.weight'].t()
+                               + (c_m_for_title @ p[pre + 'title_M.weight'].t() + p[pre + 'title_M.bias']).unsqueeze(1))
+        c_gate = torch.sigmoid(ch @ p[pre + 'content_H.weight'].t()
+                               + (t_m_for_content @ p[pre + 'content_M.weight'].t() + p[pre + 'content_M.bias']).unsqueeze(1))
+        th = th * t_gate
+        ch = ch * c_gate
     t_self = additive_attention(p, pre + 'title_self_attention.', th, tm)
     c_self = additive_attention(p, pre + 'content_self_attention.', ch, cm)
     if cross_attention:
@@ -359,14 +361,15 @@ def model_forward(p, cfg, batch, sort_fn=None, lstm_impl='loop', dropout_masks=N
     """batch: dict over BATCH_FIELDS (CPU tensors; masks are cloned here because the reference
     mutates them in place).  Returns logits [B, n]  (model.py:123-127)."""
     b = {k: (v.clone() if torch.is_tensor(v) and v.dtype == torch.bool else v) for k, v in batch.items()}
-    ca = cfg.news_encoder == 'CNE'
+    ca = cfg.news_encoder in ('CNE', 'CNE_wo_CS')
+    gt = cfg.news_encoder != 'CNE_wo_CS'
     dm = dropout_masks or {}
     news = cne_forward(p, cfg, b['news_title_text'], b['news_title_mask'], b['news_content_text'],
                        b['news_content_mask'], b['news_category'], b['news_subCategory'],
-                       sort_fn=sort_fn, lstm_impl=lstm_impl, dropout_masks=dm.get('news'), cross_attention=ca)
+                       sort_fn=sort_fn, lstm_impl=lstm_impl, dropout_masks=dm.get('news'), cross_attention=ca, gate=gt)
     hist = cne_forward(p, cfg, b['user_title_text'], b['user_title_mask'], b['user_content_text'],
                        b['user_content_mask'], b['user_category'], b['user_subCategory'],
-                       sort_fn=sort_fn, lstm_impl=lstm_impl, dropout_masks=dm.get('history'), cross_attention=ca)
+                       sort_fn=sort_fn, lstm_impl=lstm_impl, dropout_masks=dm.get('history'), cross_attention=ca, gate=gt)
     user = sue_forward(p, cfg, hist, b['user_history_graph'], b['user_history_category_mask'],
                        b['user_history_category_indices'], news, dropout_masks=dm.get('sue'))
     return (user * news).sum(dim=2)

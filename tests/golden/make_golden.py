@@ -33,6 +33,9 @@ CASES = {
     'ablation': (dict(vocabulary_size=500, max_history_num=8, max_title_length=10, max_abstract_length=20,
                       subCategory_num=30, gcn_layer_num=1, news_encoder='CNE_wo_CA', user_encoder='SUE_wo_HCA'),
                  dict(news_num=200, lengths='uniform', seed=9), 3, None, 4),
+    'wo_cs': (dict(vocabulary_size=500, max_history_num=8, max_title_length=10, max_abstract_length=20,
+                   subCategory_num=30, gcn_layer_num=2, news_encoder='CNE_wo_CS'),
+              dict(news_num=200, lengths='mind', seed=11), 3, None, 5),
 }
 
 SAMPLE = 8
