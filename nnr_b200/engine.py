@@ -390,6 +390,13 @@ def sue_param_names(L):
                'interClusterAttention.Q.bias'])
 
 
+def sue_wo_gcn_param_names():
+    """SUE_wo_GCN (variantEncoders.py:342-390): no proxy nodes / GCN; intraCluster_K has a bias there"""
+    return ['intraCluster_K.weight', 'intraCluster_K.bias', 'intraCluster_Q.weight', 'intraCluster_Q.bias',
+            'clusterFeatureAffine.weight', 'clusterFeatureAffine.bias', 'interClusterAttention.K.weight',
+            'interClusterAttention.Q.weight', 'interClusterAttention.Q.bias']
+
+
 def sue_wo_hca_param_names(L):
     return (['proxy_node_embedding'] + ['gcn.gcn_layers.%d.W.%s' % (l, w) for l in range(L) for w in ('weight', 'bias')]
             + ['attention.affine1.weight', 'attention.affine1.bias', 'attention.affine2.weight'])
@@ -401,12 +408,13 @@ class SUEFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, meta, hist, cand, graph, cmask, cidx, *params):
         hca = meta['hca']
-        L = meta['gcn_layers']
-        names = sue_param_names(L) if hca else sue_wo_hca_param_names(L)
+        gcn = meta.get('gcn', True)
+        L = meta['gcn_layers'] if gcn else 0
+        names = (sue_param_names(L) if hca else sue_wo_hca_param_names(L)) if gcn else sue_wo_gcn_param_names()
         P = dict(zip(names, params))
         B, H, D = hist.shape
         n = cand.shape[1]
-        C = P['proxy_node_embedding'].shape[0]
+        C = P['proxy_node_embedding'].shape[0] if gcn else meta['category_num']
         Gn, C1 = H + C, C + 1
         dev = hist.device
         training, p = meta['training'], meta['p_drop']
@@ -415,6 +423,8 @@ class SUEFunction(torch.autograd.Function):
         seeds = [fresh_seed() for _ in range(L + 2)] if pe > 0 else [0] * (L + 2)
         hist = hist.contiguous()
         cand = cand.contiguous()
+        if not gcn:                                                                           # SUE_wo_GCN: clusters over the raw history
+            return SUEFunction._clusters_forward(ctx, meta, P, names, hist, cand, cmask, cidx, seeds, (B, H, D, n, C, Gn, C1), L, pe)
         # X0 = [history | dropout_(proxy nodes)]   (userEncoders.py:80)
         x0 = _empty((B, Gn, D), dev)
         x0[:, :H] = hist
@@ -457,8 +467,26 @@ class SUEFunction(torch.autograd.Function):
                               w2=P['attention.affine2.weight'], pooled=pooled, ldp=D, alpha=alpha)
             ctx.u, ctx.alpha = u, alpha
             return pooled.unsqueeze(1).repeat(1, n, 1)
+        return SUEFunction._clusters_tail(ctx, P, gfeat, cand, cmask, cidx, seeds, (B, H, D, n, C, Gn, C1), L, pe)
+
+    @staticmethod
+    def _clusters_forward(ctx, meta, P, names, hist, cand, cmask, cidx, seeds, dims, L, pe):
+        ctx.meta, ctx.P, ctx.names = meta, P, names
+        ctx.dims = dims
+        ctx.seeds, ctx.graph = seeds, None
+        ctx.xs, ctx.rs, ctx.aggs = None, None, None
+        ctx.gfeat, ctx.cand = hist, cand
+        return SUEFunction._clusters_tail(ctx, P, hist, cand, cmask, cidx, seeds, dims, L, pe)
+
+    @staticmethod
+    def _clusters_tail(ctx, P, gfeat, cand, cmask, cidx, seeds, dims, L, pe):
+        """intra-cluster attention, cluster affine, inter-cluster attention (userEncoders.py:83-97)"""
+        B, H, D, n, C, Gn, C1 = dims
+        dev = gfeat.device
         Au = P['intraCluster_K.weight'].shape[0]
         scale = 1.0 / math.sqrt(float(Au))
+        # (an intraCluster_K.bias -- SUE_wo_GCN only -- shifts every score of a (user, candidate) pair equally and
+        #  cancels in the per-cluster softmax: it is not applied, and its gradient is exactly zero)
         Kp = linear(gfeat.view(B * H, D), P['intraCluster_K.weight'], B * H)
         Qp = linear(cand.view(B * n, D), P['intraCluster_Q.weight'], B * n, None, P['intraCluster_Q.bias'])
         alpha = _empty((B * n, H), dev)
@@ -478,11 +506,12 @@ class SUEFunction(torch.autograd.Function):
         ctx.sv = (Kp, Qp, alpha, intra, r_f, f, q2, qk2, cm, alpha2, cidx, Au, scale)
         return user.view(B, n, D)
 
+
     @staticmethod
     def backward(ctx, duser):
         meta, P = ctx.meta, ctx.P
         B, H, D, n, C, Gn, C1 = ctx.dims
-        L = meta['gcn_layers']
+        L = meta['gcn_layers'] if meta.get('gcn', True) else 0
         dev = duser.device
         G = {}
         training, p = meta['training'], meta['p_drop']
@@ -534,6 +563,10 @@ class SUEFunction(torch.autograd.Function):
             G['intraCluster_Q.weight'] = wgrad(dQp, cand.view(B * n, D), B * n, Au, D)
             G['intraCluster_Q.bias'] = colsum(dQp, B * n, Au)
             matmul_nn(dQp, P['intraCluster_Q.weight'], B * n, out=dcand, accumulate=True)
+        if not meta.get('gcn', True):                  # SUE_wo_GCN: gfeat is the history embedding itself
+            G['intraCluster_K.bias'] = torch.zeros_like(P['intraCluster_K.bias'])
+            ctx.sv = None
+            return (None, dg.view(B, H, D), dcand.view(B, n, D), None, None, None) + tuple(G[k] for k in ctx.names)
         # GCN backward.  gfeat = (x_L + x0)[:, :H]
         dxL = torch.zeros((B, Gn, D), device=dev)
         dxL[:, :H] = dg.view(B, H, D)

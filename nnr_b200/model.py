@@ -19,8 +19,10 @@ class Model(nn.Module):
             self.user_encoder = userEncoders.SUE(self.news_encoder, config)
         elif config.user_encoder == 'SUE_wo_HCA':
             self.user_encoder = variantEncoders.SUE_wo_HCA(self.news_encoder, config)
+        elif config.user_encoder == 'SUE_wo_GCN':
+            self.user_encoder = variantEncoders.SUE_wo_GCN(self.news_encoder, config)
         else:
-            raise Exception(config.user_encoder + ' is outside the nnr_b200 hot path (SUE, SUE_wo_HCA)')
+            raise Exception(config.user_encoder + ' is outside the nnr_b200 hot path (SUE, SUE_wo_HCA, SUE_wo_GCN)')
         self.model_name = config.news_encoder + '-' + config.user_encoder
         self.news_embedding_dim = self.news_encoder.news_embedding_dim
         self.dropout = nn.Dropout(p=config.dropout_rate)

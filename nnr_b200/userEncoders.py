@@ -23,6 +23,7 @@ class UserEncoder(nn.Module):
 
 class SUE(UserEncoder):
     hca = True
+    use_gcn = True
 
     def __init__(self, news_encoder: NewsEncoder, config):
         super().__init__(news_encoder, config)
@@ -57,7 +58,8 @@ class SUE(UserEncoder):
     def _params(self):
         cached = self.__dict__.get('_param_list')      # see newsEncoders.CNE._params
         if cached is None:
-            names = engine.sue_param_names(self.gcn_layer_num) if self.hca else engine.sue_wo_hca_param_names(self.gcn_layer_num)
+            names = ((engine.sue_param_names(self.gcn_layer_num) if self.hca else engine.sue_wo_hca_param_names(self.gcn_layer_num))
+                     if self.use_gcn else engine.sue_wo_gcn_param_names())
             sd = {k: v for k, v in self.named_parameters() if not k.startswith('news_encoder.')}
             cached = [sd[k] for k in names]
             self.__dict__['_param_list'] = cached
@@ -77,7 +79,7 @@ class SUE(UserEncoder):
         """userEncoders.py:73-97 given the already encoded history (Model.forward encodes candidates and history
         with one CNE schedule, see CNE.encode_calls)."""
         user_history_category_mask[:, -1] = 1                                    # userEncoders.py:73 (in place, like the reference)
-        meta = dict(hca=self.hca, gcn_layers=self.gcn_layer_num, residual=self.gcn_residual, training=self.training,
-                    p_drop=float(self.dropout_rate))
+        meta = dict(hca=self.hca, gcn=self.use_gcn, gcn_layers=self.gcn_layer_num, residual=self.gcn_residual,
+                    training=self.training, p_drop=float(self.dropout_rate), category_num=self.category_num - 1 if self.hca else 0)
         return engine.SUEFunction.apply(meta, history_embedding, candidate_news_representation, user_history_graph,
                                         user_history_category_mask, user_history_category_indices.long(), *self._params())

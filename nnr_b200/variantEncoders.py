@@ -1,7 +1,7 @@
 """Ablation variants that run through the same kernels (reference variantEncoders.py:263-339, 393-419)."""
 import torch.nn as nn
 
-from .layers import GCN, Attention
+from .layers import GCN, Attention, ScaledDotProduct_CandidateAttention
 from .newsEncoders import CNE
 from .userEncoders import SUE, UserEncoder
 
@@ -17,9 +17,45 @@ class CNE_wo_CS(CNE):
     selective_gate = False
 
 
+class SUE_wo_GCN(UserEncoder):
+    """SUE without the graph convolution (variantEncoders.py:342-390): the hierarchical cluster attention runs on the
+    history embedding itself; the graph input is ignored.  intraCluster_K has a bias in this variant."""
+    hca = True
+    use_gcn = False
+    _params = SUE._params
+    forward = SUE.forward
+    encode_user = SUE.encode_user
+
+    def __init__(self, news_encoder, config):
+        super().__init__(news_encoder, config)
+        import math
+        self.attention_dim = max(config.attention_dim, self.news_embedding_dim // 4)
+        self.intraCluster_K = nn.Linear(self.news_embedding_dim, self.attention_dim, bias=True)
+        self.intraCluster_Q = nn.Linear(self.news_embedding_dim, self.attention_dim, bias=True)
+        self.clusterFeatureAffine = nn.Linear(self.news_embedding_dim, self.news_embedding_dim, bias=True)
+        self.interClusterAttention = ScaledDotProduct_CandidateAttention(self.news_embedding_dim, self.news_embedding_dim, self.attention_dim)
+        self.dropout_rate = config.dropout_rate
+        self.dropout = nn.Dropout(p=config.dropout_rate, inplace=True)
+        self.category_num = config.category_num + 1
+        self.max_history_num = config.max_history_num
+        self.gcn_layer_num = 0
+        self.gcn_residual = True
+        self.attention_scalar = math.sqrt(float(self.attention_dim))
+
+    def initialize(self):
+        nn.init.xavier_uniform_(self.intraCluster_K.weight)
+        nn.init.zeros_(self.intraCluster_K.bias)
+        nn.init.xavier_uniform_(self.intraCluster_Q.weight)
+        nn.init.zeros_(self.intraCluster_Q.bias)
+        nn.init.xavier_uniform_(self.clusterFeatureAffine.weight, gain=nn.init.calculate_gain('relu'))
+        nn.init.zeros_(self.clusterFeatureAffine.bias)
+        self.interClusterAttention.initialize()
+
+
 class SUE_wo_HCA(UserEncoder):
     """GCN + plain additive attention over the history rows (no mask), repeated over candidates."""
     hca = False
+    use_gcn = True
     _params = SUE._params
     forward = SUE.forward
     encode_user = SUE.encode_user

@@ -67,12 +67,15 @@ def param_shapes(cfg):
             s[ne + f'{x}_cross_attention.Q.weight'] = (A, 2 * Hd)
             s[ne + f'{x}_cross_attention.Q.bias'] = (A,)
     ue = 'user_encoder.'
-    s[ue + 'proxy_node_embedding'] = (cfg.category_num, D)
-    for l in range(cfg.gcn_layer_num):
-        s[ue + f'gcn.gcn_layers.{l}.W.weight'] = (D, D)
-        s[ue + f'gcn.gcn_layers.{l}.W.bias'] = (D,)
-    if cfg.user_encoder == 'SUE':
+    if cfg.user_encoder != 'SUE_wo_GCN':                # variantEncoders.py:342-353: no proxy nodes, no GCN
+        s[ue + 'proxy_node_embedding'] = (cfg.category_num, D)
+        for l in range(cfg.gcn_layer_num):
+            s[ue + f'gcn.gcn_layers.{l}.W.weight'] = (D, D)
+            s[ue + f'gcn.gcn_layers.{l}.W.bias'] = (D,)
+    if cfg.user_encoder in ('SUE', 'SUE_wo_GCN'):
         s[ue + 'intraCluster_K.weight'] = (Au, D)
+        if cfg.user_encoder == 'SUE_wo_GCN':
+            s[ue + 'intraCluster_K.bias'] = (Au,)
         s[ue + 'intraCluster_Q.weight'] = (Au, D)
         s[ue + 'intraCluster_Q.bias'] = (Au,)
         s[ue + 'clusterFeatureAffine.weight'] = (D, D)
@@ -321,17 +324,22 @@ def sue_forward(p, cfg, history_embedding, graph, category_mask, category_indice
     n = candidate.shape[1]
     C1 = cfg.category_num + 1
     category_mask[:, -1] = 1                                                       # :73
-    proxy = p[pre + 'proxy_node_embedding'].unsqueeze(0).expand(B, -1, -1)
-    if dropout_masks is not None:
-        proxy = proxy * dropout_masks['proxy']
-    x0 = torch.cat([history_embedding, proxy], dim=1)                              # :80
-    g = gcn_forward(p, cfg, x0, graph, pre + 'gcn.', dropout_masks) + x0           # :81
-    g = g[:, :H, :]                                                                # :82
+    if cfg.user_encoder == 'SUE_wo_GCN':                                           # variantEncoders.py:364-390: no graph
+        g = history_embedding
+    else:
+        proxy = p[pre + 'proxy_node_embedding'].unsqueeze(0).expand(B, -1, -1)
+        if dropout_masks is not None:
+            proxy = proxy * dropout_masks['proxy']
+        x0 = torch.cat([history_embedding, proxy], dim=1)                          # :80
+        g = gcn_forward(p, cfg, x0, graph, pre + 'gcn.', dropout_masks) + x0       # :81
+        g = g[:, :H, :]                                                            # :82
     if cfg.user_encoder == 'SUE_wo_HCA':                                           # variantEncoders.py:416-419
         u = additive_attention(p, pre + 'attention.', g, None)
         return u.unsqueeze(1).repeat(1, n, 1)
     Au = p[pre + 'intraCluster_K.weight'].shape[0]
     K = g @ p[pre + 'intraCluster_K.weight'].t()                                   # [B,H,Au]   :85
+    if (pre + 'intraCluster_K.bias') in p:                                         # SUE_wo_GCN (variantEncoders.py:346)
+        K = K + p[pre + 'intraCluster_K.bias']
     Q = candidate @ p[pre + 'intraCluster_Q.weight'].t() + p[pre + 'intraCluster_Q.bias']  # [B,n,Au] :86
     a = torch.einsum('bha,bka->bkh', K, Q) / math.sqrt(float(Au))                  # :87
     idx = category_indices.unsqueeze(1).expand(-1, n, -1)

@@ -36,6 +36,9 @@ CASES = {
     'wo_cs': (dict(vocabulary_size=500, max_history_num=8, max_title_length=10, max_abstract_length=20,
                    subCategory_num=30, gcn_layer_num=2, news_encoder='CNE_wo_CS'),
               dict(news_num=200, lengths='mind', seed=11), 3, None, 5),
+    'wo_gcn': (dict(vocabulary_size=500, max_history_num=8, max_title_length=10, max_abstract_length=20,
+                    subCategory_num=30, gcn_layer_num=2, user_encoder='SUE_wo_GCN'),
+               dict(news_num=200, lengths='mind', seed=13), 3, None, 6),
 }
 
 SAMPLE = 8

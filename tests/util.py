@@ -18,6 +18,8 @@ GOLDEN_CASES = {
                      subCategory_num=30, gcn_layer_num=1, news_encoder='CNE_wo_CA', user_encoder='SUE_wo_HCA'),
     'wo_cs': dict(vocabulary_size=500, max_history_num=8, max_title_length=10, max_abstract_length=20,
                   subCategory_num=30, gcn_layer_num=2, news_encoder='CNE_wo_CS'),
+    'wo_gcn': dict(vocabulary_size=500, max_history_num=8, max_title_length=10, max_abstract_length=20,
+                   subCategory_num=30, gcn_layer_num=2, user_encoder='SUE_wo_GCN'),
 }
 SAMPLE = 8
 
