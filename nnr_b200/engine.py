@@ -38,6 +38,18 @@ _weight_planes = {}
 _weight_epoch = 0
 
 
+def _param_grads(P, names, G):
+    """Gradients of the parameters for the tail of an autograd.Function.backward.  When every parameter's ``.grad`` is a
+    preallocated buffer managed by trainer.TrainStep (flat gradient buffer, marked ``_nnr_flat_grad``), the gradients
+    are added into those buffers with ONE multi-tensor add and ``None`` is returned to autograd, instead of ~70
+    per-parameter AccumulateGrad add kernels per step."""
+    params = [P[k] for k in names]
+    if all(getattr(q, '_nnr_flat_grad', False) and q.grad is not None for q in params):
+        torch._foreach_add_([q.grad for q in params], [G[k] for k in names])
+        return (None,) * len(names)
+    return tuple(G[k] for k in names)
+
+
 def weights_changed():
     global _weight_epoch
     _weight_epoch += 1
@@ -377,7 +389,7 @@ class CNEFunction(torch.autograd.Function):
             del hprev, demb
         G['word_embedding.weight'] = dtable
         ctx.t = ctx.c = None
-        return (None,) * 7 + tuple(G[k] for k in ctx.names)
+        return (None,) * 7 + _param_grads(P, ctx.names, G)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -566,7 +578,7 @@ class SUEFunction(torch.autograd.Function):
         if not meta.get('gcn', True):                  # SUE_wo_GCN: gfeat is the history embedding itself
             G['intraCluster_K.bias'] = torch.zeros_like(P['intraCluster_K.bias'])
             ctx.sv = None
-            return (None, dg.view(B, H, D), dcand.view(B, n, D), None, None, None) + tuple(G[k] for k in ctx.names)
+            return (None, dg.view(B, H, D), dcand.view(B, n, D), None, None, None) + _param_grads(P, ctx.names, G)
         # GCN backward.  gfeat = (x_L + x0)[:, :H]
         dxL = torch.zeros((B, Gn, D), device=dev)
         dxL[:, :H] = dg.view(B, H, D)
@@ -597,7 +609,7 @@ class SUEFunction(torch.autograd.Function):
             ops.dropout(dproxy_b, pe, seeds[L], dproxy_b)
         G['proxy_node_embedding'] = dproxy_b.sum(dim=0)
         ctx.xs = ctx.rs = ctx.aggs = ctx.sv = None
-        return (None, dhist, dcand.view(B, n, D) if dcand is not None else None, None, None, None) + tuple(G[k] for k in ctx.names)
+        return (None, dhist, dcand.view(B, n, D) if dcand is not None else None, None, None, None) + _param_grads(P, ctx.names, G)
 
 
 class RowDot(torch.autograd.Function):

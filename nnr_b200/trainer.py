@@ -43,6 +43,7 @@ class TrainStep:
             self.flat[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.flat[o:o + n].view(p.shape)
             p.grad = self.gflat[o:o + n].view(p.shape)
+            p._nnr_flat_grad = True          # engine._param_grads adds straight into these views
             o += s
         self.params = params
         self.step_count = 0
