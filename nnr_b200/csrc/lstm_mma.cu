@@ -642,13 +642,17 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
               dcc[2 * nt] = v.x; dcc[2 * nt + 1] = v.y;
             }
           } else {                   // recurrent part: the CL partials summed in fixed order
-            const float* rv = reinterpret_cast<const float*>(Rsm + (size_t)R * RP) + w * UPW;
+            // unit u of row r sits at column (u + 10 (r >> 2)) % 40 of its block: without the rotation the 32 row owners
+            // of a warp hit 4 bank groups (8-way conflicts), with it 16
+            const float* rv = reinterpret_cast<const float*>(Rsm + (size_t)R * RP);
+            const int rot = w * UPW + 10 * (R >> 2);
 #pragma unroll
             for (int nt = 0; nt < NTW; ++nt) {
               float2 acc2 = make_float2(0.f, 0.f);
+              const int col = (rot + 2 * nt) % UPC;
 #pragma unroll
               for (int src = 0; src < CL; ++src) {
-                const float2 v = *reinterpret_cast<const float2*>(rv + (size_t)src * MT * (RP / 4) + 2 * nt);
+                const float2 v = *reinterpret_cast<const float2*>(rv + (size_t)src * MT * (RP / 4) + col);
                 acc2.x += v.x; acc2.y += v.y;
               }
               dht[2 * nt] += acc2.x; dht[2 * nt + 1] += acc2.y;
@@ -778,11 +782,12 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
         if (nt < 6 || seven) {
           const int k = 8 * (nt0 + nt) + 2 * q;          // output hidden unit of acc[..][nt][0]
           const int owner = k / UPC, kl = k - owner * UPC;
-          unsigned char* dst = Ssm + (size_t)owner * G::B_RBLK + kl * 4;
+          unsigned char* dst = Ssm + (size_t)owner * G::B_RBLK;
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
-            *reinterpret_cast<float2*>(dst + (16 * mt + r8) * RP) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
-            *reinterpret_cast<float2*>(dst + (16 * mt + r8 + 8) * RP) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+            const int ra = 16 * mt + r8, rb = ra + 8;      // rotated columns, see the reader in phase 1
+            *reinterpret_cast<float2*>(dst + ra * RP + ((kl + 10 * (ra >> 2)) % UPC) * 4) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+            *reinterpret_cast<float2*>(dst + rb * RP + ((kl + 10 * (rb >> 2)) % UPC) * 4) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
           }
         }
       }
