@@ -185,6 +185,8 @@ int nnr_attn_pool_bwd(const nnr_pool_args* args, void* stream);
 
 /* ---- news vector assembly: newsEncoders.py:50-54,138 ----------------------------------------
  * out[r] = [ts+tc | cs+cc | drop(cat_table[cat[r]]) | drop(sub_table[sub[r]])]                  */
+/* c_self = NULL (fwd) / d_b = NULL (bwd): single-modality encoders, layout [self | category | subCategory]
+ * (variantEncoders.py:14-99). */
 int nnr_news_fuse_fwd(const float* t_self, const float* t_cross, const float* c_self,
                       const float* c_cross, const float* cat_table, const float* sub_table,
                       const int32_t* cat, const int32_t* sub, int N, int D2, int Ec, int Es,

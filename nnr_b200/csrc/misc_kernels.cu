@@ -135,17 +135,18 @@ __global__ void news_fuse_fwd_kernel(const float* __restrict__ ts, const float* 
                                      const int32_t* __restrict__ sub, int D2, int Ec, int Es, float p, float inv_keep,
                                      uint64_t seed, float* __restrict__ out) {
   int r = blockIdx.x;
-  int Dout = 2 * D2 + Ec + Es;
+  const int DM = cs ? 2 * D2 : D2;                  // one or two modalities (CNE_Title / CNE_Content pass c_self = NULL)
+  int Dout = DM + Ec + Es;
   float* o = out + (size_t)r * Dout;
   for (int d = threadIdx.x; d < Dout; d += blockDim.x) {
     float v;
     if (d < D2) v = ts[(size_t)r * D2 + d] + (tc ? tc[(size_t)r * D2 + d] : 0.f);
-    else if (d < 2 * D2) v = cs[(size_t)r * D2 + d - D2] + (cc ? cc[(size_t)r * D2 + d - D2] : 0.f);
-    else if (d < 2 * D2 + Ec) {
-      int e = d - 2 * D2;
+    else if (d < DM) v = cs[(size_t)r * D2 + d - D2] + (cc ? cc[(size_t)r * D2 + d - D2] : 0.f);
+    else if (d < DM + Ec) {
+      int e = d - DM;
       v = cat_table[(size_t)cat[r] * Ec + e] * dropout_scale(seed, (uint64_t)r * (Ec + Es) + e, p, inv_keep);
     } else {
-      int e = d - 2 * D2 - Ec;
+      int e = d - DM - Ec;
       v = sub_table[(size_t)sub[r] * Es + e] * dropout_scale(seed, (uint64_t)r * (Ec + Es) + Ec + e, p, inv_keep);
     }
     o[d] = v;
@@ -154,7 +155,7 @@ __global__ void news_fuse_fwd_kernel(const float* __restrict__ ts, const float* 
 extern "C" int nnr_news_fuse_fwd(const float* t_self, const float* t_cross, const float* c_self, const float* c_cross,
                                  const float* cat_table, const float* sub_table, const int32_t* cat, const int32_t* sub,
                                  int N, int D2, int Ec, int Es, float p_drop, uint64_t seed, float* out, void* stream) {
-  NNR_REQUIRE(t_self && c_self && cat_table && sub_table && cat && sub && out && N > 0, NNR_ERR_ARG,
+  NNR_REQUIRE(t_self && cat_table && sub_table && cat && sub && out && N > 0, NNR_ERR_ARG,
               "nnr_news_fuse_fwd: bad arguments");
   float inv_keep = 1.0f / (1.0f - p_drop);
   news_fuse_fwd_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(t_self, t_cross, c_self, c_cross, cat_table, sub_table, cat,
@@ -166,7 +167,7 @@ extern "C" int nnr_news_fuse_fwd(const float* t_self, const float* t_cross, cons
 __global__ void news_fuse_split_kernel(const float* __restrict__ dout, int D2, int Dout, float* __restrict__ d_a,
                                        float* __restrict__ d_b) {
   int r = blockIdx.x;
-  for (int d = threadIdx.x; d < 2 * D2; d += blockDim.x) {
+  for (int d = threadIdx.x; d < (d_b ? 2 * D2 : D2); d += blockDim.x) {
     float v = dout[(size_t)r * Dout + d];
     if (d < D2) d_a[(size_t)r * D2 + d] = v;
     else d_b[(size_t)r * D2 + d - D2] = v;
@@ -224,18 +225,19 @@ __global__ void __launch_bounds__(NF_WARPS * 32) news_fuse_table_bwd_kernel(cons
 extern "C" int nnr_news_fuse_bwd(const float* dout, const int32_t* cat, const int32_t* sub, int N, int D2, int Ec, int Es,
                                  int n_cat, int n_sub, float p_drop, uint64_t seed, float* d_a, float* d_b,
                                  float* dcat_table, float* dsub_table, int accumulate, void* stream) {
-  NNR_REQUIRE(dout && cat && sub && d_a && d_b && dcat_table && dsub_table && N > 0, NNR_ERR_ARG,
+  NNR_REQUIRE(dout && cat && sub && d_a && dcat_table && dsub_table && N > 0, NNR_ERR_ARG,
               "nnr_news_fuse_bwd: bad arguments");
   NNR_REQUIRE(Ec <= NF_MAXE && Es <= NF_MAXE, NNR_ERR_UNSUPPORTED, "nnr_news_fuse_bwd: embedding dim > %d", NF_MAXE);
   cudaStream_t st = (cudaStream_t)stream;
-  int Dout = 2 * D2 + Ec + Es;
+  const int DM = d_b ? 2 * D2 : D2;                 // d_b = NULL: single-modality encoders (CNE_Title / CNE_Content)
+  int Dout = DM + Ec + Es;
   float inv_keep = 1.0f / (1.0f - p_drop);
   news_fuse_split_kernel<<<N, 256, 0, st>>>(dout, D2, Dout, d_a, d_b);
   NNR_LAUNCH_CHECK("news_fuse_split_kernel");
-  news_fuse_table_bwd_kernel<<<n_cat, NF_WARPS * 32, 0, st>>>(dout, cat, N, Dout, 2 * D2, Ec, Ec + Es, 0, p_drop,
+  news_fuse_table_bwd_kernel<<<n_cat, NF_WARPS * 32, 0, st>>>(dout, cat, N, Dout, DM, Ec, Ec + Es, 0, p_drop,
                                                                      inv_keep, seed, dcat_table, accumulate);
   NNR_LAUNCH_CHECK("news_fuse_table_bwd_kernel(cat)");
-  news_fuse_table_bwd_kernel<<<n_sub, NF_WARPS * 32, 0, st>>>(dout, sub, N, Dout, 2 * D2 + Ec, Es, Ec + Es, Ec,
+  news_fuse_table_bwd_kernel<<<n_sub, NF_WARPS * 32, 0, st>>>(dout, sub, N, Dout, DM + Ec, Es, Ec + Es, Ec,
                                                                      p_drop, inv_keep, seed, dsub_table, accumulate);
   NNR_LAUNCH_CHECK("news_fuse_table_bwd_kernel(sub)");
   return 0;

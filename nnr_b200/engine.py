@@ -132,11 +132,17 @@ CNE_CROSS_PARAM_NAMES = ['%s_cross_attention.%s' % (x, w) for x in ('title', 'co
 CNE_GATE_PARAM_NAMES = ['%s_%s' % (x, w) for x in ('title', 'content') for w in ('H.weight', 'M.weight', 'M.bias')]
 
 
-def cne_param_names(cross_attention=True, gate=True):
+def cne_param_names(cross_attention=True, gate=True, modalities=('title', 'content')):
     """parameter order of CNEFunction for a variant: CNE (both), CNE_wo_CA (no cross attention,
-    variantEncoders.py:263-339), CNE_wo_CS (no selective gate, variantEncoders.py:190-260)"""
-    names = [n for n in CNE_PARAM_NAMES if gate or n not in CNE_GATE_PARAM_NAMES]
-    return names + (CNE_CROSS_PARAM_NAMES if cross_attention else [])
+    variantEncoders.py:263-339), CNE_wo_CS (no selective gate, :190-260), CNE_Title / CNE_Content (one modality,
+    LSTM + self attention only, :14-99)"""
+    single = len(modalities) == 1
+    names = [n for n in CNE_PARAM_NAMES if (gate and not single) or n not in CNE_GATE_PARAM_NAMES]
+    names += CNE_CROSS_PARAM_NAMES if (cross_attention and not single) else []
+    if single:
+        drop = 'content_' if modalities[0] == 'title' else 'title_'
+        names = [n for n in names if not n.startswith(drop)]
+    return names
 
 
 class _Mod:
@@ -246,13 +252,29 @@ class CNEFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, meta, title_text, title_mask, content_text, content_mask, category, subCategory, *params):
         gate = meta.get('gate', True)
-        names = cne_param_names(meta['cross_attention'], gate)
+        modalities = meta.get('modalities', ('title', 'content'))
+        names = cne_param_names(meta['cross_attention'], gate, modalities)
         P = dict(zip(names, params))
         N, T, Lc = meta['N'], meta['T'], meta['A_len']
         E, Hd, A = meta['E'], meta['Hd'], meta['att']
         training, p = meta['training'], meta['p_drop']
         seeds = [fresh_seed() for _ in range(3)] if (training and p > 0) else [0, 0, 0]
         domains = meta.get('domains') or [(0, N)]
+        if len(modalities) == 1:                      # CNE_Title / CNE_Content: LSTM -> self attention -> fusion
+            x = modalities[0]
+            if x == 'title':
+                m = _cne_modality_forward(P, x, title_text.view(N, T), title_mask.reshape(N, T), N, T, E, Hd, training, p, seeds[0], domains)
+            else:
+                m = _cne_modality_forward(P, x, content_text.view(N, Lc), content_mask.reshape(N, Lc), N, Lc, E, Hd, training, p, seeds[1], domains)
+            _cne_gate_self(P, x, m, None, None, N, Hd, A, False)
+            cat_t, sub_t = P['category_embedding.weight'], P['subCategory_embedding.weight']
+            rep = _empty((N, 2 * Hd + cat_t.shape[1] + sub_t.shape[1]), title_text.device)
+            cat_i, sub_i = category.reshape(N).contiguous(), subCategory.reshape(N).contiguous()
+            ops.news_fuse_fwd(m.self_out, None, None, None, cat_t, sub_t, cat_i, sub_i, N, 2 * Hd, p if training else 0.0, seeds[2], rep)
+            ctx.meta, ctx.P, ctx.t, ctx.c = meta, P, (m if x == 'title' else None), (m if x == 'content' else None)
+            ctx.cat_i, ctx.sub_i, ctx.fuse_seed = cat_i, sub_i, seeds[2]
+            ctx.names = names
+            return rep
         t = _cne_modality_forward(P, 'title', title_text.view(N, T), title_mask.reshape(N, T), N, T, E, Hd, training, p, seeds[0], domains)
         c = _cne_modality_forward(P, 'content', content_text.view(N, Lc), content_mask.reshape(N, Lc), N, Lc, E, Hd, training, p, seeds[1], domains)
         # pairing by sort rank inside each domain (newsEncoders.py:124-129, SURVEY finding 2):
@@ -284,18 +306,24 @@ class CNEFunction(torch.autograd.Function):
         dev = drep.device
         drep = drep.contiguous()
         G = {}
-        cross = meta['cross_attention']
+        modalities = meta.get('modalities', ('title', 'content'))
+        single = len(modalities) == 1
+        cross = meta['cross_attention'] and not single
         training, p = meta['training'], meta['p_drop']
         # 1. split + category tables
-        d_a, d_b = _empty((N, D2), dev), _empty((N, D2), dev)
+        d_a, d_b = _empty((N, D2), dev), (None if single else _empty((N, D2), dev))
         G['category_embedding.weight'] = _empty(P['category_embedding.weight'].shape, dev)
         G['subCategory_embedding.weight'] = _empty(P['subCategory_embedding.weight'].shape, dev)
         ops.news_fuse_bwd(drep, ctx.cat_i, ctx.sub_i, N, D2, p if training else 0.0, ctx.fuse_seed, d_a, d_b,
                           G['category_embedding.weight'], G['subCategory_embedding.weight'], False)
         scale = 1.0 / math.sqrt(float(A))
-        d_self = {'title': d_a, 'content': d_b}
-        d_out = {'title': d_a, 'content': d_b}
-        mods = {'title': t, 'content': c}
+        if single:
+            d_self = d_out = {modalities[0]: d_a}
+            mods = {modalities[0]: t if modalities[0] == 'title' else c}
+        else:
+            d_self = {'title': d_a, 'content': d_b}
+            d_out = {'title': d_a, 'content': d_b}
+            mods = {'title': t, 'content': c}
         other = {'title': 'content', 'content': 'title'}
         for x, m in mods.items():
             m.dhg = _empty((m.cap, D2), dev)
@@ -335,9 +363,9 @@ class CNEFunction(torch.autograd.Function):
             m.hg_pl = None
         # 4. selective gate backward
         d_cm_sel = {}
-        gate = meta.get('gate', True)
+        gate = meta.get('gate', True) and not single
         for x, m in mods.items():
-            if not gate:                       # CNE_wo_CS: hg is h, nothing flows into the other modality's cell state
+            if not gate:                       # CNE_wo_CS / single modality: hg is h, nothing flows into another cell state
                 m.dh = m.dhg
                 d_cm_sel[x] = None
                 continue
@@ -360,7 +388,7 @@ class CNEFunction(torch.autograd.Function):
             dcn = {'content': d_cm_sel['title'].index_select(0, c.partner),
                    'title': d_cm_sel['content'].index_select(0, t.partner)}
         else:
-            dcn = {'content': torch.zeros(N, D2, device=dev), 'title': torch.zeros(N, D2, device=dev)}
+            dcn = {x: torch.zeros(N, D2, device=dev) for x in mods}
         # 5. LSTM backward + input projection + embedding scatter
         dtable = _empty(P['word_embedding.weight'].shape, dev)
         first = True

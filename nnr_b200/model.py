@@ -11,10 +11,10 @@ class Model(nn.Module):
             self.news_encoder = newsEncoders.CNE(config)
         elif config.news_encoder == 'CNE_wo_CA':
             self.news_encoder = variantEncoders.CNE_wo_CA(config)
-        elif config.news_encoder == 'CNE_wo_CS':
-            self.news_encoder = variantEncoders.CNE_wo_CS(config)
+        elif config.news_encoder in ('CNE_wo_CS', 'CNE_Title', 'CNE_Content'):
+            self.news_encoder = getattr(variantEncoders, config.news_encoder)(config)
         else:
-            raise Exception(config.news_encoder + ' is outside the nnr_b200 hot path (CNE, CNE_wo_CA, CNE_wo_CS)')
+            raise Exception(config.news_encoder + ' is outside the nnr_b200 hot path (CNE and its ablations)')
         if config.user_encoder == 'SUE':
             self.user_encoder = userEncoders.SUE(self.news_encoder, config)
         elif config.user_encoder == 'SUE_wo_HCA':

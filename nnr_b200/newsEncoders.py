@@ -50,6 +50,7 @@ class CNE(NewsEncoder):
     cross_attention = True
     selective_gate = True
     gate_gain = 'sigmoid'
+    modalities = ('title', 'content')
 
     def __init__(self, config):
         super().__init__(config)
@@ -57,24 +58,29 @@ class CNE(NewsEncoder):
         self.max_content_length = config.max_abstract_length
         self.hidden_dim = config.hidden_dim
         self.attention_dim = config.attention_dim
-        self.news_embedding_dim = config.hidden_dim * 4 + config.category_embedding_dim + config.subCategory_embedding_dim
+        self.news_embedding_dim = (config.hidden_dim * 2 * len(self.modalities) + config.category_embedding_dim
+                                   + config.subCategory_embedding_dim)
         # parameter holders only: the LSTM recurrence runs in nnr_lstm_fwd/bwd, never through cuDNN
-        self.title_lstm = nn.LSTM(self.word_embedding_dim, self.hidden_dim, batch_first=True, bidirectional=True)
-        self.content_lstm = nn.LSTM(self.word_embedding_dim, self.hidden_dim, batch_first=True, bidirectional=True)
+        if 'title' in self.modalities:
+            self.title_lstm = nn.LSTM(self.word_embedding_dim, self.hidden_dim, batch_first=True, bidirectional=True)
+        if 'content' in self.modalities:
+            self.content_lstm = nn.LSTM(self.word_embedding_dim, self.hidden_dim, batch_first=True, bidirectional=True)
         if self.selective_gate:
             self.title_H = nn.Linear(self.hidden_dim * 2, self.hidden_dim * 2, bias=False)
             self.title_M = nn.Linear(self.hidden_dim * 2, self.hidden_dim * 2, bias=True)
             self.content_H = nn.Linear(self.hidden_dim * 2, self.hidden_dim * 2, bias=False)
             self.content_M = nn.Linear(self.hidden_dim * 2, self.hidden_dim * 2, bias=True)
-        self.title_self_attention = Attention(self.hidden_dim * 2, config.attention_dim)
-        self.content_self_attention = Attention(self.hidden_dim * 2, config.attention_dim)
+        if 'title' in self.modalities:
+            self.title_self_attention = Attention(self.hidden_dim * 2, config.attention_dim)
+        if 'content' in self.modalities:
+            self.content_self_attention = Attention(self.hidden_dim * 2, config.attention_dim)
         if self.cross_attention:
             self.title_cross_attention = ScaledDotProduct_CandidateAttention(self.hidden_dim * 2, self.hidden_dim * 2, config.attention_dim)
             self.content_cross_attention = ScaledDotProduct_CandidateAttention(self.hidden_dim * 2, self.hidden_dim * 2, config.attention_dim)
 
     def initialize(self):
         super().initialize()
-        for lstm in (self.title_lstm, self.content_lstm):
+        for lstm in [getattr(self, x + '_lstm') for x in self.modalities]:
             for parameter in lstm.parameters():
                 if len(parameter.size()) >= 2:
                     nn.init.orthogonal_(parameter.data)
@@ -88,8 +94,8 @@ class CNE(NewsEncoder):
             nn.init.xavier_uniform_(self.content_H.weight, gain=gain)
             nn.init.xavier_uniform_(self.content_M.weight, gain=gain)
             nn.init.zeros_(self.content_M.bias)
-        self.title_self_attention.initialize()
-        self.content_self_attention.initialize()
+        for x in self.modalities:
+            getattr(self, x + '_self_attention').initialize()
         if self.cross_attention:
             self.title_cross_attention.initialize()
             self.content_cross_attention.initialize()
@@ -99,7 +105,7 @@ class CNE(NewsEncoder):
         # objects), so the module tree is walked once, not on every forward
         cached = self.__dict__.get('_param_list')
         if cached is None:
-            names = engine.cne_param_names(self.cross_attention, self.selective_gate)
+            names = engine.cne_param_names(self.cross_attention, self.selective_gate, self.modalities)
             sd = dict(self.named_parameters())
             cached = [sd[k] for k in names]
             self.__dict__['_param_list'] = cached
@@ -142,6 +148,6 @@ class CNE(NewsEncoder):
             sub = torch.cat([c[5].reshape(-1).to(i32) for c in calls])
         meta = dict(N=start, T=T, A_len=A, E=self.word_embedding_dim, Hd=self.hidden_dim, att=self.attention_dim,
                     training=self.training, p_drop=float(self.dropout_rate), cross_attention=self.cross_attention,
-                    gate=self.selective_gate, domains=domains)
+                    gate=self.selective_gate, modalities=self.modalities, domains=domains)
         rep = engine.CNEFunction.apply(meta, tt, tm, ct, cm, cat, sub, *self._params())
         return [rep[s:s + cnt].view(B, n, self.news_embedding_dim) for (s, cnt), (B, n) in zip(domains, shapes)]

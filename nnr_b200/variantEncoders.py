@@ -17,6 +17,20 @@ class CNE_wo_CS(CNE):
     selective_gate = False
 
 
+class CNE_Title(CNE):
+    """title LSTM + self attention only (variantEncoders.py:14-55): output [title_self | category | subCategory]"""
+    modalities = ('title',)
+    cross_attention = False
+    selective_gate = False
+
+
+class CNE_Content(CNE):
+    """abstract LSTM + self attention only (variantEncoders.py:58-99)"""
+    modalities = ('content',)
+    cross_attention = False
+    selective_gate = False
+
+
 class SUE_wo_GCN(UserEncoder):
     """SUE without the graph convolution (variantEncoders.py:342-390): the hierarchical cluster attention runs on the
     history embedding itself; the graph input is ignored.  intraCluster_K has a bias in this variant."""

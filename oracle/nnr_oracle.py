@@ -33,31 +33,36 @@ def make_config(**kw):
     return SimpleNamespace(**cfg)
 
 
+def cne_modalities(cfg):
+    return {'CNE_Title': ('title',), 'CNE_Content': ('content',)}.get(cfg.news_encoder, ('title', 'content'))
+
+
 def param_shapes(cfg):
     """Unique parameter tensors of Model(CNE, SUE) with their reference checkpoint names
     (newsEncoders.py:12-77, userEncoders.py:43-56, layers.py:151-155,178-183,265-311).
     Variants: CNE_wo_CA has no cross-attention (variantEncoders.py:263-281); SUE_wo_HCA replaces
     the cluster attention by ``attention`` (variantEncoders.py:393-400)."""
     E, Hd, A = cfg.word_embedding_dim, cfg.hidden_dim, cfg.attention_dim
-    D = 4 * Hd + cfg.category_embedding_dim + cfg.subCategory_embedding_dim
+    mods = cne_modalities(cfg)                          # CNE_Title / CNE_Content: one modality (variantEncoders.py:14-99)
+    D = 2 * Hd * len(mods) + cfg.category_embedding_dim + cfg.subCategory_embedding_dim
     Au = max(A, D // 4)
     s = {}
     ne = 'news_encoder.'
     s[ne + 'word_embedding.weight'] = (cfg.vocabulary_size, E)
     s[ne + 'category_embedding.weight'] = (cfg.category_num, cfg.category_embedding_dim)
     s[ne + 'subCategory_embedding.weight'] = (cfg.subCategory_num, cfg.subCategory_embedding_dim)
-    for x in ('title', 'content'):
+    for x in mods:
         for sfx in ('', '_reverse'):
             s[ne + f'{x}_lstm.weight_ih_l0{sfx}'] = (4 * Hd, E)
             s[ne + f'{x}_lstm.weight_hh_l0{sfx}'] = (4 * Hd, Hd)
             s[ne + f'{x}_lstm.bias_ih_l0{sfx}'] = (4 * Hd,)
             s[ne + f'{x}_lstm.bias_hh_l0{sfx}'] = (4 * Hd,)
-    if cfg.news_encoder != 'CNE_wo_CS':                 # variantEncoders.py:190-206 has no gate parameters
+    if cfg.news_encoder in ('CNE', 'CNE_wo_CA'):        # the other variants have no gate parameters
         for x in ('title', 'content'):
             s[ne + f'{x}_H.weight'] = (2 * Hd, 2 * Hd)
             s[ne + f'{x}_M.weight'] = (2 * Hd, 2 * Hd)
             s[ne + f'{x}_M.bias'] = (2 * Hd,)
-    for x in ('title', 'content'):
+    for x in mods:
         s[ne + f'{x}_self_attention.affine1.weight'] = (A, 2 * Hd)
         s[ne + f'{x}_self_attention.affine1.bias'] = (A,)
         s[ne + f'{x}_self_attention.affine2.weight'] = (1, A)
@@ -251,7 +256,7 @@ def scaled_dot_candidate_attention(p, prefix, feature, query, mask=None):
 
 def cne_forward(p, cfg, title_text, title_mask, content_text, content_mask, category, subCategory,
                 pre='news_encoder.', sort_fn=None, lstm_impl='loop', dropout_masks=None,
-                cross_attention=True, gate=True):
+                cross_attention=True, gate=True, modalities=('title', 'content')):
     """newsEncoders.py:102-141 (eval mode, or train mode with externally supplied keep-masks).
 
     The reference runs the LSTM in length-sorted order and adds the *other* modality's memory
@@ -266,6 +271,20 @@ def cne_forward(p, cfg, title_text, title_mask, content_text, content_mask, cate
     cm = content_mask.view(N, A_len)
     tl, cl, st, dt, sc, dc = lengths_and_perms(tm, cm, sort_fn)
     table = p[pre + 'word_embedding.weight']
+    if len(modalities) == 1:                          # CNE_Title / CNE_Content (variantEncoders.py:35-55, 79-99)
+        x = modalities[0]
+        text, L, mask, ln = (title_text, T, tm, tl) if x == 'title' else (content_text, A_len, cm, cl)
+        emb = table[text.reshape(N, L).long()]
+        if dropout_masks is not None:
+            emb = emb * dropout_masks[x]
+        h, _ = bilstm(p, pre + x + '_lstm.', emb, ln, lstm_impl)
+        rep = additive_attention(p, pre + x + '_self_attention.', h, mask).view(B, n, -1)
+        cat_e = p[pre + 'category_embedding.weight'][category.long()]
+        sub_e = p[pre + 'subCategory_embedding.weight'][subCategory.long()]
+        if dropout_masks is not None:
+            cat_e = cat_e * dropout_masks['category']
+            sub_e = sub_e * dropout_masks['subCategory']
+        return torch.cat([rep, cat_e, sub_e], dim=2)
     title = table[title_text.reshape(N, T).long()]
     content = table[content_text.reshape(N, A_len).long()]
     if dropout_masks is not None:                     # nn.Dropout: x * keep / (1 - p)
@@ -370,14 +389,15 @@ def model_forward(p, cfg, batch, sort_fn=None, lstm_impl='loop', dropout_masks=N
     mutates them in place).  Returns logits [B, n]  (model.py:123-127)."""
     b = {k: (v.clone() if torch.is_tensor(v) and v.dtype == torch.bool else v) for k, v in batch.items()}
     ca = cfg.news_encoder in ('CNE', 'CNE_wo_CS')
-    gt = cfg.news_encoder != 'CNE_wo_CS'
+    gt = cfg.news_encoder in ('CNE', 'CNE_wo_CA')
+    md = cne_modalities(cfg)
     dm = dropout_masks or {}
     news = cne_forward(p, cfg, b['news_title_text'], b['news_title_mask'], b['news_content_text'],
                        b['news_content_mask'], b['news_category'], b['news_subCategory'],
-                       sort_fn=sort_fn, lstm_impl=lstm_impl, dropout_masks=dm.get('news'), cross_attention=ca, gate=gt)
+                       sort_fn=sort_fn, lstm_impl=lstm_impl, dropout_masks=dm.get('news'), cross_attention=ca, gate=gt, modalities=md)
     hist = cne_forward(p, cfg, b['user_title_text'], b['user_title_mask'], b['user_content_text'],
                        b['user_content_mask'], b['user_category'], b['user_subCategory'],
-                       sort_fn=sort_fn, lstm_impl=lstm_impl, dropout_masks=dm.get('history'), cross_attention=ca, gate=gt)
+                       sort_fn=sort_fn, lstm_impl=lstm_impl, dropout_masks=dm.get('history'), cross_attention=ca, gate=gt, modalities=md)
     user = sue_forward(p, cfg, hist, b['user_history_graph'], b['user_history_category_mask'],
                        b['user_history_category_indices'], news, dropout_masks=dm.get('sue'))
     return (user * news).sum(dim=2)

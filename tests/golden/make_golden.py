@@ -39,6 +39,12 @@ CASES = {
     'wo_gcn': (dict(vocabulary_size=500, max_history_num=8, max_title_length=10, max_abstract_length=20,
                     subCategory_num=30, gcn_layer_num=2, user_encoder='SUE_wo_GCN'),
                dict(news_num=200, lengths='mind', seed=13), 3, None, 6),
+    'title_only': (dict(vocabulary_size=500, max_history_num=8, max_title_length=10, max_abstract_length=20,
+                        subCategory_num=30, gcn_layer_num=2, news_encoder='CNE_Title'),
+                   dict(news_num=200, lengths='mind', seed=15), 3, None, 7),
+    'content_only': (dict(vocabulary_size=500, max_history_num=8, max_title_length=10, max_abstract_length=20,
+                          subCategory_num=30, gcn_layer_num=2, news_encoder='CNE_Content'),
+                     dict(news_num=200, lengths='mind', seed=17), 3, None, 8),
 }
 
 SAMPLE = 8

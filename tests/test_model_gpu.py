@@ -86,7 +86,7 @@ def _check_grads(name, model, g64, tol, golden=None):
     assert worst[0][0] < 1.0, (name, worst[:5])
 
 
-@pytest.mark.parametrize('name', ['tiny', 'mind_shape', 'ablation', 'wo_cs', 'wo_gcn'])
+@pytest.mark.parametrize('name', ['tiny', 'mind_shape', 'ablation', 'wo_cs', 'wo_gcn', 'title_only', 'content_only'])
 def test_train_loss_and_gradients_match_reference_golden(cuda, name):
     from nnr_b200.trainer import negative_log_softmax
     cfg, batch, z = load_golden(name)

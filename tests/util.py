@@ -20,6 +20,10 @@ GOLDEN_CASES = {
                   subCategory_num=30, gcn_layer_num=2, news_encoder='CNE_wo_CS'),
     'wo_gcn': dict(vocabulary_size=500, max_history_num=8, max_title_length=10, max_abstract_length=20,
                    subCategory_num=30, gcn_layer_num=2, user_encoder='SUE_wo_GCN'),
+    'title_only': dict(vocabulary_size=500, max_history_num=8, max_title_length=10, max_abstract_length=20,
+                       subCategory_num=30, gcn_layer_num=2, news_encoder='CNE_Title'),
+    'content_only': dict(vocabulary_size=500, max_history_num=8, max_title_length=10, max_abstract_length=20,
+                         subCategory_num=30, gcn_layer_num=2, news_encoder='CNE_Content'),
 }
 SAMPLE = 8
 
