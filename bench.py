@@ -254,6 +254,7 @@ def main():
 
     # ---- per-op breakdown with CUDA events (dominant kernel -> roofline) ---------------------------
     roofline = None
+    roofline_table = None
     breakdown = None
     if not a.no_profile:
         # every rank runs the two extra steps (they contain the gradient all-reduce); only rank 0 records events
@@ -268,6 +269,7 @@ def main():
                 for k, v in prof.detail.items():
                     print('%-44s %8.3f ms  %4.1f calls  %7.1f TFLOP/s' % (k, v['ms'], v['calls'], v['tflops']), file=sys.stderr)
             roofline = profiler.roofline(breakdown, tokens_per_step=tok, batch=a.batch, root=ROOT)
+            roofline_table = profiler.roofline_table(breakdown, ROOT)
         else:
             for i in range(2):
                 ts.step(*fresh(devb[i % nb]))
@@ -297,7 +299,7 @@ def main():
                                'corpus_bytes_resident': corpus.nbytes(),
                                'note': 'nnr_b200.corpus.DeviceCorpus + TrainStep.step_ids: ids in, batch gathered and graph built on the device'},
             'gpu_launches': int(launches),
-            'roofline': roofline, 'cpu_baseline': cpu, 'breakdown_ms_per_step': breakdown}
+            'roofline': roofline, 'roofline_by_kernel': roofline_table, 'cpu_baseline': cpu, 'breakdown_ms_per_step': breakdown}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

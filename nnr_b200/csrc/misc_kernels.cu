@@ -6,7 +6,7 @@
 // ------------------------------------------------------------------------------------------
 // column sums (bias gradients): two-stage, fixed partition -> deterministic
 // ------------------------------------------------------------------------------------------
-#define CS_ROWS 256
+#define CS_ROWS 64
 __global__ void colsum_stage1(const float* __restrict__ X, int64_t ldx, int M, int N, const int32_t* __restrict__ m_dev,
                               float* __restrict__ part) {
   int Me = m_dev ? min(M, *m_dev) : M;
@@ -15,7 +15,15 @@ __global__ void colsum_stage1(const float* __restrict__ X, int64_t ldx, int M, i
   if (n >= N) return;
   float acc = 0.f;
   int r1 = min(r0 + CS_ROWS, Me);
-  for (int r = r0; r < r1; ++r) acc += X[(size_t)r * ldx + n];
+  int r = r0;
+  for (; r + 8 <= r1; r += 8) {             // eight rows in flight, added in row order
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = X[(size_t)(r + j) * ldx + n];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += v[j];
+  }
+  for (; r < r1; ++r) acc += X[(size_t)r * ldx + n];
   part[(size_t)blockIdx.y * N + n] = acc;
 }
 __global__ void colsum_stage2(const float* __restrict__ part, int nparts, int N, int M, const int32_t* __restrict__ m_dev,

@@ -166,17 +166,18 @@ __global__ void eb_keys_kernel(const int32_t* __restrict__ ids, const int32_t* _
 // broadcast with shuffles; rows are loaded four at a time so 12 independent 16-byte loads are in flight per
 // lane, and added in entry order (the summation order is a pure function of the sorted order).
 __device__ __forceinline__ void eb_warp_accumulate(float4 (&acc)[3], const float* __restrict__ dout,
-                                                   const int32_t* __restrict__ vals, const int32_t* __restrict__ off, int cs,
-                                                   int L, int E, int E4, int first, int end, int stride, int lane, float p,
+                                                   const int32_t* __restrict__ s_slot, const unsigned long long* __restrict__ s_src,
+                                                   int E, int E4, int first, int end, int stride, int lane, float p,
                                                    float inv_keep, uint64_t seed) {
+  // s_slot / s_src: token slot and source offset of every sorted entry of the chunk, resolved once per CTA (the two
+  // dependent global loads per entry used to sit in front of every run's row loads)
   for (int base = first; base < end; base += 32 * stride) {
     const int e = base + lane * stride;
     int slot_l = 0;
     unsigned long long src_l = 0;
     if (e < end) {
-      slot_l = vals[cs + e];
-      int row = slot_l / L, t = slot_l - row * L;
-      src_l = ((unsigned long long)off[row] + t) * (unsigned long long)E;
+      slot_l = s_slot[e];
+      src_l = s_src[e];
     }
     const int gn = min(32, (end - base + stride - 1) / stride);
     int j = 0;
@@ -254,6 +255,14 @@ __global__ void __launch_bounds__(256) eb_chunk_kernel(const float* __restrict__
   const int ce = min(cs + EB_CHUNK, n_valid);
   const int cnt = ce - cs;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  __shared__ int32_t s_slot[EB_CHUNK];
+  __shared__ unsigned long long s_src[EB_CHUNK];
+  if (tid < cnt) {                                   // sorted entry -> (token slot, offset of its dL/dout row)
+    const int slot = vals[cs + tid];
+    const int row = slot / L, t = slot - row * L;
+    s_slot[tid] = slot;
+    s_src[tid] = ((unsigned long long)off[row] + t) * (unsigned long long)E;
+  }
   // keys of [cs-1, ce]  (s_key[i+1] = key[cs+i])
   for (int i = tid; i < cnt + 2; i += 256) {
     int pos = cs - 1 + i;
@@ -308,7 +317,7 @@ __global__ void __launch_bounds__(256) eb_chunk_kernel(const float* __restrict__
     float4 acc[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    eb_warp_accumulate(acc, dout, vals, off, cs, L, E, E4, a, b, 1, lane, p, inv_keep, seed);
+    eb_warp_accumulate(acc, dout, s_slot, s_src, E, E4, a, b, 1, lane, p, inv_keep, seed);
     bool add;
     float* dst = run_dst(r, add);
 #pragma unroll
@@ -329,7 +338,7 @@ __global__ void __launch_bounds__(256) eb_chunk_kernel(const float* __restrict__
     float4 acc[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    eb_warp_accumulate(acc, dout, vals, off, cs, L, E, E4, a + w, b, 8, lane, p, inv_keep, seed);
+    eb_warp_accumulate(acc, dout, s_slot, s_src, E, E4, a + w, b, 8, lane, p, inv_keep, seed);
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
       int c4 = lane + 32 * q;

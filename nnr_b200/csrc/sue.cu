@@ -130,7 +130,15 @@ __global__ void __launch_bounds__(256) gcn_aggregate_kernel(const int32_t* __res
   const float* xb = x + (size_t)b * G * D;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float acc = 0.f;
-    for (int e = 0; e < n; ++e) acc = fmaf(s_val[e], xb[(size_t)s_col[e] * D + d], acc);
+    int e = 0;
+    for (; e + 8 <= n; e += 8) {            // eight neighbour rows in flight, accumulated in edge order
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = xb[(size_t)s_col[e + j] * D + d];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(s_val[e + j], v[j], acc);
+    }
+    for (; e < n; ++e) acc = fmaf(s_val[e], xb[(size_t)s_col[e] * D + d], acc);
     out[(size_t)row * D + d] = acc;
   }
 }

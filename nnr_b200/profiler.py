@@ -70,6 +70,30 @@ class Capture:
             dout, ids, len_, off, dtable = args[:5]
             V, E = dtable.shape
             return lambda: (None, float(off[ids.shape[0]].item()) * (4 + 4 * E) + V * E * 4.0)
+        if name in ('attn_pool_fwd', 'attn_pool_bwd'):
+            S, D, A = kw['S'], kw['D'], kw.get('A', 0) or 0
+            seg_off, fixed = kw.get('seg_off'), kw.get('fixed_len', 0)
+            mode0 = kw.get('mode') == 0
+            fwd = name == 'attn_pool_fwd'
+            acc = bool(kw.get('accumulate_dx', False))
+
+            def pool_bytes():
+                rows = float(seg_off[S].item()) if seg_off is not None else float(S * fixed)
+                per_row = D * 4 + (A * 4 if mode0 else 0) + 4                  # X once (+ U), alpha
+                if not fwd:
+                    per_row += D * 4 * (2 if acc else 1) + (A * 4 if mode0 else 0)   # dX (read-modify-write if accumulating), dU
+                return (None, rows * per_row + S * D * 4.0)
+            return pool_bytes
+        if name == 'colsum':
+            X, ldx, M, N = args[:4]
+            m_dev = kw.get('m_dev', args[6] if len(args) > 6 else None)
+            return lambda: (None, (min(M, _dev_int(m_dev)) if m_dev is not None else M) * N * 4.0)
+        if name == 'flat_clip_adam':
+            n = args[0].numel()
+            return lambda: (None, n * 28.0)                                       # read p, g (x2: norm + update), m, v; write p, m, v
+        if name == 'gcn_aggregate':
+            B, Gn, D = args[4], args[5], args[6]
+            return lambda: (None, 2.0 * B * Gn * D * 4)                           # features in once, aggregated features out
         return lambda: (None, None)
 
     def wrap(self, name, fn):
@@ -194,3 +218,24 @@ def roofline(breakdown, tokens_per_step, batch, root):
                 'peak_note': '%s HBM copy bandwidth' % peaks['source']}
     return {'kernel': name, 'bound': 'hbm', 'achieved': None, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': None,
             'traffic': traffic, 'share_of_step': top['ms'] / total}
+
+
+def roofline_table(breakdown, root):
+    """one row per op that has algorithmic work attached: achieved rate against the measured peak that bounds it"""
+    peaks = measured_peaks(root)
+    algo = ops.default_algo()
+    products = 3 if algo in (ops.ALGO_TF32X3, ops.ALGO_BF16X3) else 1
+    rows = []
+    for name, v in breakdown.items():
+        if 'tflops' in v:
+            tensor = name in ('gemm_tc_kernel', 'lstm_fwd', 'lstm_bwd')
+            if not tensor:
+                continue
+            rows.append({'kernel': name, 'bound': 'tensor', 'ms': round(v['ms'], 3), 'achieved': round(v['tflops'], 1),
+                         'unit': 'TFLOP/s (algorithmic)', 'peak': peaks['bf16_tflops'], 'frac': round(v['tflops'] / peaks['bf16_tflops'], 4),
+                         'mma_per_algorithmic_flop': 3 if name != 'gemm_tc_kernel' else products,
+                         'frac_of_peak_in_issued_mma': round((3 if name != 'gemm_tc_kernel' else products) * v['tflops'] / peaks['bf16_tflops'], 4)})
+        elif 'gbs' in v:
+            rows.append({'kernel': name, 'bound': 'hbm', 'ms': round(v['ms'], 3), 'achieved': round(v['gbs'], 1), 'unit': 'GB/s (algorithmic)',
+                         'peak': peaks['hbm_gbs'], 'frac': round(v['gbs'] / peaks['hbm_gbs'], 4)})
+    return rows
