@@ -72,4 +72,22 @@ __device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, floa
   float u = (float)(r >> 8) * (1.0f / 16777216.0f);
   return u < p ? 0.0f : inv_keep;
 }
+// Four keep-scales from ONE 64-bit hash (16 uniform bits per element): used where the mask of a whole row of a
+// large tensor is regenerated (word-embedding gather / scatter: 300 elements per token), where the per-element
+// hash above is the bulk of the instruction count.  Element i of the tensor uses field (i & 3) of hash(i >> 2).
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return x;
+}
+__device__ __forceinline__ void dropout_scale4(uint64_t seed, uint64_t idx4, float p, float inv_keep, float (&s)[4]) {
+  const uint64_t r = mix64(seed * 0x9E3779B97F4A7C15ULL + idx4);
+  const uint32_t thr = (uint32_t)(p * 65536.0f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s[i] = ((uint32_t)(r >> (16 * i)) & 0xffffu) < thr ? 0.0f : inv_keep;
+}
+__device__ __forceinline__ float dropout_scale_e4(uint64_t seed, uint64_t idx, float p, float inv_keep) {
+  if (p <= 0.0f) return 1.0f;
+  const uint64_t r = mix64(seed * 0x9E3779B97F4A7C15ULL + (idx >> 2));
+  return ((uint32_t)(r >> (16 * (idx & 3))) & 0xffffu) < (uint32_t)(p * 65536.0f) ? 0.0f : inv_keep;
+}
 #endif

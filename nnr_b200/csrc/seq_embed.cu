@@ -111,16 +111,15 @@ __global__ void embed_gather_kernel(const float* __restrict__ table, const int32
     int E4 = E >> 2;
     for (int q = lane; q < E4; q += 32) {
       float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
-      if (p > 0.0f) {
-        v.x *= dropout_scale(seed, ebase + 4 * q + 0, p, inv_keep);
-        v.y *= dropout_scale(seed, ebase + 4 * q + 1, p, inv_keep);
-        v.z *= dropout_scale(seed, ebase + 4 * q + 2, p, inv_keep);
-        v.w *= dropout_scale(seed, ebase + 4 * q + 3, p, inv_keep);
+      if (p > 0.0f) {                 // E % 4 == 0 on this path, so ebase is a multiple of 4
+        float ks[4];
+        dropout_scale4(seed, (ebase >> 2) + q, p, inv_keep, ks);
+        v.x *= ks[0]; v.y *= ks[1]; v.z *= ks[2]; v.w *= ks[3];
       }
       reinterpret_cast<float4*>(dst)[q] = v;
     }
   } else {
-    for (int e = lane; e < E; e += 32) dst[e] = __ldg(src + e) * dropout_scale(seed, ebase + e, p, inv_keep);
+    for (int e = lane; e < E; e += 32) dst[e] = __ldg(src + e) * dropout_scale_e4(seed, ebase + e, p, inv_keep);
   }
 }
 
@@ -196,10 +195,9 @@ __device__ __forceinline__ void eb_warp_accumulate(float4 (&acc)[3], const float
           if (c4 < E4) {
             float4 x = __ldg(src + c4);
             if (p > 0.0f) {
-              x.x *= dropout_scale(seed, ebase + 4 * c4 + 0, p, inv_keep);
-              x.y *= dropout_scale(seed, ebase + 4 * c4 + 1, p, inv_keep);
-              x.z *= dropout_scale(seed, ebase + 4 * c4 + 2, p, inv_keep);
-              x.w *= dropout_scale(seed, ebase + 4 * c4 + 3, p, inv_keep);
+              float ks[4];
+              dropout_scale4(seed, (ebase >> 2) + c4, p, inv_keep, ks);
+              x.x *= ks[0]; x.y *= ks[1]; x.z *= ks[2]; x.w *= ks[3];
             }
             v[u][q] = x;
           }
@@ -221,10 +219,9 @@ __device__ __forceinline__ void eb_warp_accumulate(float4 (&acc)[3], const float
         if (c4 < E4) {
           float4 x = __ldg(src + c4);
           if (p > 0.0f) {
-            x.x *= dropout_scale(seed, ebase + 4 * c4 + 0, p, inv_keep);
-            x.y *= dropout_scale(seed, ebase + 4 * c4 + 1, p, inv_keep);
-            x.z *= dropout_scale(seed, ebase + 4 * c4 + 2, p, inv_keep);
-            x.w *= dropout_scale(seed, ebase + 4 * c4 + 3, p, inv_keep);
+            float ks[4];
+            dropout_scale4(seed, (ebase >> 2) + c4, p, inv_keep, ks);
+            x.x *= ks[0]; x.y *= ks[1]; x.z *= ks[2]; x.w *= ks[3];
           }
           acc[q].x += x.x; acc[q].y += x.y; acc[q].z += x.z; acc[q].w += x.w;
         }
