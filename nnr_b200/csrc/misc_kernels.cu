@@ -414,11 +414,49 @@ __global__ void __launch_bounds__(1024) length_sort_desc_kernel(const int64_t* _
     }
   }
 }
+// keys <= 255: one pass per 1024 elements.  Rank of an element = start of its key (larger keys first) + equal keys in
+// earlier chunks + equal keys in earlier warps of the chunk + equal keys in earlier lanes of the warp (__match_any).
+__global__ void __launch_bounds__(1024) length_sort_desc_small_kernel(const int64_t* __restrict__ keys, int N, int max_key,
+                                                                      int64_t* __restrict__ sorted_idx) {
+  __shared__ int s_base[256];            // running output position of each key
+  __shared__ int s_wcnt[32][256];        // per warp: count, then exclusive start, of each key in the current chunk
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid < 256) s_base[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < N; i += 1024) atomicAdd(&s_base[(int)min((long long)max_key, max(0ll, (long long)keys[i]))], 1);
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int k = max_key; k >= 0; --k) { const int c = s_base[k]; s_base[k] = run; run += c; }
+  }
+  __syncthreads();
+  for (int c0 = 0; c0 < N; c0 += 1024) {
+    for (int j = tid; j < 32 * 256; j += 1024) (&s_wcnt[0][0])[j] = 0;
+    __syncthreads();
+    const int i = c0 + tid;
+    const bool valid = i < N;
+    const int key = valid ? (int)min((long long)max_key, max(0ll, (long long)keys[i])) : -1;
+    const unsigned m = __match_any_sync(0xffffffffu, key);
+    const int rank = __popc(m & ((1u << lane) - 1));
+    if (valid && rank == 0) s_wcnt[w][key] = __popc(m);
+    __syncthreads();
+    if (tid <= max_key) {
+      int run = s_base[tid];
+#pragma unroll 8
+      for (int ww = 0; ww < 32; ++ww) { const int c = s_wcnt[ww][tid]; s_wcnt[ww][tid] = run; run += c; }
+      s_base[tid] = run;
+    }
+    __syncthreads();
+    if (valid) sorted_idx[s_wcnt[w][key] + rank] = i;
+    __syncthreads();
+  }
+}
 extern "C" int nnr_length_sort_desc(const int64_t* keys, int N, int max_key, int64_t* sorted_idx, void* stream) {
   NNR_REQUIRE(keys && sorted_idx && N > 0, NNR_ERR_ARG, "nnr_length_sort_desc: bad arguments");
   NNR_REQUIRE(N <= LS_MAXN && max_key >= 0 && max_key <= LS_MAXKEY, NNR_ERR_UNSUPPORTED,
               "nnr_length_sort_desc: N <= %d and max_key <= %d", LS_MAXN, LS_MAXKEY);
-  length_sort_desc_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(keys, N, max_key, sorted_idx);
+  if (max_key <= 255) length_sort_desc_small_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(keys, N, max_key, sorted_idx);
+  else length_sort_desc_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(keys, N, max_key, sorted_idx);
   NNR_LAUNCH_CHECK("length_sort_desc_kernel");
   return 0;
 }
