@@ -175,13 +175,18 @@ __global__ void __launch_bounds__(256) cluster_intra_fwd_kernel(const float* __r
     if (lane == 0) s_a[h] = v * scale;
   }
   __syncthreads();
-  if (tid == 0) {   // stable counting sort of the H slots by cluster (H <= 256: trivial)
+  // stable counting sort of the H slots by cluster, one thread per cluster start and one per slot
+  if (tid <= C1) {
     int pos = 0;
-    for (int c = 0; c < C1; ++c) {
-      s_start[c] = pos;
-      for (int h = 0; h < H; ++h) if (s_idx[h] == c) s_perm[pos++] = h;
-    }
-    s_start[C1] = pos;
+    for (int h = 0; h < H; ++h) pos += (s_idx[h] < tid);
+    s_start[tid] = pos;
+  }
+  __syncthreads();
+  if (tid < H) {
+    const int c = s_idx[tid];
+    int pos = s_start[c];
+    for (int h = 0; h < tid; ++h) pos += (s_idx[h] == c);
+    s_perm[pos] = tid;
   }
   __syncthreads();
   // per-slot softmax within its cluster (max-shifted, like torch_scatter.scatter_softmax)
@@ -201,11 +206,24 @@ __global__ void __launch_bounds__(256) cluster_intra_fwd_kernel(const float* __r
   const float* gb = g + (size_t)b * H * D;
   float* ob = intra + (size_t)bk * C1 * D;
   for (int d = tid; d < D; d += 256) {
-    for (int c = 0; c < C1; ++c) {
-      float acc = 0.f;
-      for (int e = s_start[c]; e < s_start[c + 1]; ++e) { int h = s_perm[e]; acc += s_a[h] * gb[(size_t)h * D + d]; }
-      ob[(size_t)c * D + d] = acc;
+    // one pass over the slots in cluster order, eight feature rows in flight; a cluster's sum is stored when the
+    // next cluster starts (empty clusters store 0); same summation order as a per-cluster loop
+    int c = 0;
+    float acc = 0.f;
+    for (int e0 = 0; e0 < H; e0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (e0 + j < H) ? gb[(size_t)s_perm[e0 + j] * D + d] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int e = e0 + j;
+        if (e < H) {
+          while (e == s_start[c + 1]) { ob[(size_t)c * D + d] = acc; acc = 0.f; ++c; }
+          acc += s_a[s_perm[e]] * v[j];
+        }
+      }
     }
+    for (; c < C1; ++c) { ob[(size_t)c * D + d] = acc; acc = 0.f; }
   }
 }
 
@@ -229,9 +247,13 @@ __global__ void __launch_bounds__(256) cluster_intra_bwd_a_kernel(const float* _
   for (int h = w; h < H; h += 8) {
     const float* di = dintra + ((size_t)bk * C1 + s_idx[h]) * D;
     const float* gh = g + ((size_t)b * H + h) * D;
-    float v = 0.f;
-    for (int d = lane; d < D; d += 32) v += di[d] * gh[d];
-    v = warp_sum(v);
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;          // four independent partial sums (fixed combination order)
+    int d = lane;
+    for (; d + 96 < D; d += 128) {
+      v0 += di[d] * gh[d]; v1 += di[d + 32] * gh[d + 32]; v2 += di[d + 64] * gh[d + 64]; v3 += di[d + 96] * gh[d + 96];
+    }
+    for (; d < D; d += 32) v0 += di[d] * gh[d];
+    float v = warp_sum((v0 + v1) + (v2 + v3));
     if (lane == 0) s_da[h] = v;   // dL/dalpha
   }
   __syncthreads();
@@ -247,7 +269,15 @@ __global__ void __launch_bounds__(256) cluster_intra_bwd_a_kernel(const float* _
   __syncthreads();
   for (int a = tid; a < Au; a += 256) {
     float acc = 0.f;
-    for (int h = 0; h < H; ++h) acc += s_da[h] * Kp[((size_t)b * H + h) * Au + a];
+    int h = 0;
+    for (; h + 8 <= H; h += 8) {             // eight rows of Kp in flight, accumulated in slot order
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = Kp[((size_t)b * H + h + j) * Au + a];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += s_da[h + j] * v[j];
+    }
+    for (; h < H; ++h) acc += s_da[h] * Kp[((size_t)b * H + h) * Au + a];
     dQp[(size_t)bk * Au + a] = acc;
   }
 }
