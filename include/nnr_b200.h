@@ -179,6 +179,8 @@ typedef struct {
   float* dU; int64_t lddu;        /* mode 0: dL/d(pre-tanh) = da * w2 * (1 - U^2)               */
   float* dw2_partial;             /* mode 0: [S, A] per-segment partials (reduce with colsum)   */
   float* dqvec; int64_t lddq;     /* mode 1: [S, D]                                              */
+  const int32_t* seg_order;       /* optional [S]: block b processes segment seg_order[b] (e.g. longest first, so the
+                                     long segments do not form the tail of the launch); NULL = identity          */
 } nnr_pool_args;
 int nnr_attn_pool_fwd(const nnr_pool_args* args, void* stream);
 int nnr_attn_pool_bwd(const nnr_pool_args* args, void* stream);

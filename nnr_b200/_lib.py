@@ -49,7 +49,8 @@ class PoolArgs(C.Structure):
                 ('dX', vp), ('lddx', i64), ('accumulate_dx', i32),
                 ('dU', vp), ('lddu', i64),
                 ('dw2_partial', vp),
-                ('dqvec', vp), ('lddq', i64)]
+                ('dqvec', vp), ('lddq', i64),
+                ('seg_order', vp)]
 
 
 # name -> (restype, argtypes); must list every symbol include/nnr_b200.h declares

@@ -15,25 +15,32 @@
 __global__ void __launch_bounds__(POOL_THREADS) attn_pool_fwd_kernel(nnr_pool_args a) {
   extern __shared__ float sc[];  // [max_len]
   __shared__ float red[POOL_THREADS / 32];
-  const int s = blockIdx.x;
+  const int s = a.seg_order ? a.seg_order[blockIdx.x] : blockIdx.x;
   const int beg = a.seg_off ? a.seg_off[s] : s * a.fixed_len;
   const int n = a.seg_off ? (a.seg_off[s + 1] - beg) : a.fixed_len;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = POOL_THREADS / 32;
-  for (int t = w; t < n; t += nw) {
-    const size_t p = (size_t)beg + t;
-    float v = 0.f;
-    if (a.mode == 0) {
-      const float* u = a.U + p * a.ldu;
-      for (int k = lane; k < a.A; k += 32) v += u[k] * a.w2[k];
-    } else {
-      const float* x = a.X + p * a.ldx;
-      const float* q = a.qvec + (size_t)s * a.ldq;
-      for (int d = lane; d < a.D; d += 32) v += x[d] * q[d];
+  // scores: a warp takes two rows per iteration so that both rows' loads are in flight before the shuffle reductions
+  {
+    const float* src = (a.mode == 0) ? a.U : a.X;
+    const int64_t lds = (a.mode == 0) ? a.ldu : a.ldx;
+    const float* wv = (a.mode == 0) ? a.w2 : a.qvec + (size_t)s * a.ldq;
+    const int nv = (a.mode == 0) ? a.A : a.D;
+    for (int t = w; t < n; t += 2 * nw) {
+      const int t1 = t + nw;
+      const bool two = t1 < n;
+      const float* r0 = src + ((size_t)beg + t) * lds;
+      const float* r1 = two ? src + ((size_t)beg + t1) * lds : r0;
+      float v0 = 0.f, v1 = 0.f;
+      for (int k = lane; k < nv; k += 32) { const float wk = wv[k]; v0 += r0[k] * wk; v1 += r1[k] * wk; }
+      v0 = warp_sum(v0);
+      v1 = warp_sum(v1);
+      if (a.mode == 1) { v0 *= a.scale; v1 *= a.scale; }
+      if (a.mask) {
+        if (a.mask[(size_t)beg + t] == 0) v0 = -1e9f;
+        if (two && a.mask[(size_t)beg + t1] == 0) v1 = -1e9f;
+      }
+      if (lane == 0) { sc[t] = v0; if (two) sc[t1] = v1; }
     }
-    v = warp_sum(v);
-    if (a.mode == 1) v *= a.scale;
-    if (a.mask && a.mask[p] == 0) v = -1e9f;
-    if (lane == 0) sc[t] = v;
   }
   __syncthreads();
   // softmax over the segment
@@ -78,7 +85,7 @@ __global__ void __launch_bounds__(POOL_THREADS) attn_pool_fwd_kernel(nnr_pool_ar
 __global__ void __launch_bounds__(POOL_THREADS) attn_pool_bwd_kernel(nnr_pool_args a) {
   extern __shared__ float sm[];  // [2*max_len]: alpha, da
   __shared__ float red[POOL_THREADS / 32];
-  const int s = blockIdx.x;
+  const int s = a.seg_order ? a.seg_order[blockIdx.x] : blockIdx.x;
   const int beg = a.seg_off ? a.seg_off[s] : s * a.fixed_len;
   const int n = a.seg_off ? (a.seg_off[s + 1] - beg) : a.fixed_len;
   float* al = sm;

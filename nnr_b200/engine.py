@@ -228,7 +228,7 @@ def _cne_gate_self(P, x, m, m_other_cn, partner, N, Hd, A, gate=True):
     m.u = linear(m.hg, P[sa + 'affine1.weight'], m.cap, m.ntok, P[sa + 'affine1.bias'], EPI_BIAS_TANH, x_planes=m.hg_pl)
     m.self_out = _empty((N, D2), dev)
     m.alpha_self = _empty((m.cap,), dev)
-    ops.attn_pool_fwd(X=m.hg, ldx=D2, D=D2, S=N, max_len=m.L, mode=0, seg_off=m.off, U=m.u, ldu=A, A=A,
+    ops.attn_pool_fwd(X=m.hg, ldx=D2, D=D2, S=N, max_len=m.L, mode=0, seg_off=m.off, seg_order=m.order, U=m.u, ldu=A, A=A,
                       w2=P[sa + 'affine2.weight'], pooled=m.self_out, ldp=D2, alpha=m.alpha_self)
 
 
@@ -242,7 +242,7 @@ def _cne_cross(P, x, m, other_self, N, Hd, A):
     m.qk = matmul_nn(m.q, P[ca + 'K.weight'], N)                                               # [N, 2H] = q K
     m.cross_out = _empty((N, D2), dev)
     m.alpha_cross = _empty((m.cap,), dev)
-    ops.attn_pool_fwd(X=m.hg, ldx=D2, D=D2, S=N, max_len=m.L, mode=1, seg_off=m.off, qvec=m.qk, ldq=D2,
+    ops.attn_pool_fwd(X=m.hg, ldx=D2, D=D2, S=N, max_len=m.L, mode=1, seg_off=m.off, seg_order=m.order, qvec=m.qk, ldq=D2,
                       scale=1.0 / math.sqrt(float(A)), pooled=m.cross_out, ldp=D2, alpha=m.alpha_cross)
 
 
@@ -334,7 +334,7 @@ class CNEFunction(torch.autograd.Function):
             for x, m in mods.items():
                 ca = x + '_cross_attention.'
                 dqk = _empty((N, D2), dev)
-                ops.attn_pool_bwd(X=m.hg, ldx=D2, D=D2, S=N, max_len=m.L, mode=1, seg_off=m.off, qvec=m.qk, ldq=D2,
+                ops.attn_pool_bwd(X=m.hg, ldx=D2, D=D2, S=N, max_len=m.L, mode=1, seg_off=m.off, seg_order=m.order, qvec=m.qk, ldq=D2,
                                   scale=scale, alpha=m.alpha_cross, dpooled=d_out[x], lddp=D2, dX=m.dhg, lddx=D2,
                                   accumulate_dx=False, dqvec=dqk, lddq=D2)
                 dhg_written[x] = True
@@ -350,7 +350,7 @@ class CNEFunction(torch.autograd.Function):
             sa = x + '_self_attention.'
             dU = _empty((m.cap, A), dev)
             dw2p = _empty((N, A), dev)
-            ops.attn_pool_bwd(X=m.hg, ldx=D2, D=D2, S=N, max_len=m.L, mode=0, seg_off=m.off, U=m.u, ldu=A, A=A,
+            ops.attn_pool_bwd(X=m.hg, ldx=D2, D=D2, S=N, max_len=m.L, mode=0, seg_off=m.off, seg_order=m.order, U=m.u, ldu=A, A=A,
                               w2=P[sa + 'affine2.weight'], alpha=m.alpha_self, dpooled=d_self[x], lddp=D2, dX=m.dhg,
                               lddx=D2, accumulate_dx=dhg_written[x], dU=dU, lddu=A, dw2_partial=dw2p)
             G[sa + 'affine2.weight'] = colsum(dw2p, N, A).view(1, A)

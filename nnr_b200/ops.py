@@ -197,7 +197,7 @@ def gate_bwd_pre(dhg, h, g, n_max, n_dev, D, dz, dh0):
 
 def _pool_args(X, ldx, D, S, max_len, mode, seg_off=None, fixed_len=0, U=None, ldu=0, A=0, w2=None, qvec=None,
                ldq=0, scale=1.0, mask=None, pooled=None, ldp=0, alpha=None, dpooled=None, lddp=0, dX=None, lddx=0,
-               accumulate_dx=False, dU=None, lddu=0, dw2_partial=None, dqvec=None, lddq=0):
+               accumulate_dx=False, dU=None, lddu=0, dw2_partial=None, dqvec=None, lddq=0, seg_order=None):
     a = PoolArgs()
     a.X, a.ldx, a.D = _p(X, _F32), ldx, D
     a.seg_off, a.S, a.fixed_len, a.max_len = _p(seg_off, _I32), S, fixed_len, max_len
@@ -209,6 +209,7 @@ def _pool_args(X, ldx, D, S, max_len, mode, seg_off=None, fixed_len=0, U=None, l
     a.alpha = _p(alpha, _F32)
     a.dpooled, a.lddp = _p(dpooled, _F32), lddp
     a.dX, a.lddx, a.accumulate_dx = _p(dX, _F32), lddx, int(accumulate_dx)
+    a.seg_order = _p(seg_order, _I32)
     a.dU, a.lddu = _p(dU, _F32), lddu
     a.dw2_partial = _p(dw2_partial, _F32)
     a.dqvec, a.lddq = _p(dqvec, _F32), lddq
