@@ -485,10 +485,11 @@ class SUEFunction(torch.autograd.Function):
             r = _empty((B * Gn, D), dev)
             xv = x.view(B * Gn, D)
             pl = (pe / 2.0) if l < L - 1 else 0.0
+            agg_pl = ops.tc_split(agg, B * Gn, D, D)             # shared with the weight-gradient GEMM of the backward
             xn = linear(agg, P['gcn.gcn_layers.%d.W.weight' % l], B * Gn, None, P['gcn.gcn_layers.%d.W.bias' % l],
                         EPI_BIAS_RELU_RES, aux=xv if residual else None, ldaux=D, aux_out=r, ldaux_out=D, p_drop=pl,
-                        seed=seeds[l])
-            aggs.append(agg)
+                        seed=seeds[l], x_planes=agg_pl)
+            aggs.append((agg, agg_pl))
             rs.append(r)
             x = xn.view(B, Gn, D)
             xs.append(x)
@@ -534,8 +535,10 @@ class SUEFunction(torch.autograd.Function):
         cidx = cidx.contiguous()
         ops.cluster_intra_fwd(Kp, Qp, gfeat, cidx, B, n, H, Au, D, C1, scale, alpha, intra)
         r_f = _empty((B * n * C1, D), dev)
+        intra_pl = ops.tc_split(intra, B * n * C1, D, D)         # shared with the weight-gradient GEMM of the backward
         f = linear(intra, P['clusterFeatureAffine.weight'], B * n * C1, None, P['clusterFeatureAffine.bias'],
-                   EPI_BIAS_RELU_RES, aux=intra, ldaux=D, aux_out=r_f, ldaux_out=D, p_drop=pe, seed=seeds[L + 1])
+                   EPI_BIAS_RELU_RES, aux=intra, ldaux=D, aux_out=r_f, ldaux_out=D, p_drop=pe, seed=seeds[L + 1],
+                   x_planes=intra_pl)
         q2 = linear(cand.view(B * n, D), P['interClusterAttention.Q.weight'], B * n, None, P['interClusterAttention.Q.bias'])
         qk2 = matmul_nn(q2, P['interClusterAttention.K.weight'], B * n)
         cm = cmask.unsqueeze(1).expand(-1, n, -1).contiguous().view(torch.uint8)             # [B,n,C1]
@@ -543,7 +546,7 @@ class SUEFunction(torch.autograd.Function):
         alpha2 = _empty((B * n * C1,), dev)
         ops.attn_pool_fwd(X=f, ldx=D, D=D, S=B * n, max_len=C1, mode=1, fixed_len=C1, qvec=qk2, ldq=D, scale=scale,
                           mask=cm, pooled=user, ldp=D, alpha=alpha2)
-        ctx.sv = (Kp, Qp, alpha, intra, r_f, f, q2, qk2, cm, alpha2, cidx, Au, scale)
+        ctx.sv = (Kp, Qp, alpha, intra, r_f, f, q2, qk2, cm, alpha2, cidx, Au, scale, intra_pl)
         return user.view(B, n, D)
 
 
@@ -573,7 +576,7 @@ class SUEFunction(torch.autograd.Function):
             G['attention.affine1.weight'] = wgrad(dU, gfeat.view(B * H, D), B * H, A, D)
             G['attention.affine1.bias'] = colsum(dU, B * H, A)
         else:
-            Kp, Qp, alpha, intra, r_f, f, q2, qk2, cm, alpha2, cidx, Au, scale = ctx.sv
+            Kp, Qp, alpha, intra, r_f, f, q2, qk2, cm, alpha2, cidx, Au, scale, intra_pl = ctx.sv
             duser = duser.contiguous().view(B * n, D)
             # inter-cluster attention backward
             df = _empty((B * n * C1, D), dev)
@@ -590,9 +593,11 @@ class SUEFunction(torch.autograd.Function):
             if pe > 0:
                 ops.dropout(df, pe, seeds[L + 1], df)
             dpre = df * (r_f > 0)                                                             # relu mask
-            G['clusterFeatureAffine.weight'] = wgrad(dpre, intra, B * n * C1, D, D)
+            dpre_pl = ops.tc_split(dpre, B * n * C1, D, D)
+            G['clusterFeatureAffine.weight'] = wgrad(dpre, intra, B * n * C1, D, D, dy_planes=dpre_pl, x_planes=intra_pl)
             G['clusterFeatureAffine.bias'] = colsum(dpre, B * n * C1, D)
-            dintra = matmul_nn(dpre, P['clusterFeatureAffine.weight'], B * n * C1, epilogue=EPI_ADD_AUX, aux=df, ldaux=D)
+            dintra = matmul_nn(dpre, P['clusterFeatureAffine.weight'], B * n * C1, epilogue=EPI_ADD_AUX, aux=df, ldaux=D,
+                               x_planes=dpre_pl)
             # intra-cluster attention backward
             da_ws = _empty((B * n, H), dev)
             dKp, dQp = _empty((B * H, Au), dev), _empty((B * n, Au), dev)
@@ -621,9 +626,10 @@ class SUEFunction(torch.autograd.Function):
                 dx = dx.clone() if dx.data_ptr() == dxL.data_ptr() else dx
                 ops.dropout(dx, pl, seeds[l], dx)
             dpre = dx * (ctx.rs[l] > 0)
-            G['gcn.gcn_layers.%d.W.weight' % l] = wgrad(dpre, ctx.aggs[l], B * Gn, D, D)
+            dpre_pl = ops.tc_split(dpre, B * Gn, D, D)            # one split for the wgrad and the dgrad GEMM
+            G['gcn.gcn_layers.%d.W.weight' % l] = wgrad(dpre, ctx.aggs[l][0], B * Gn, D, D, dy_planes=dpre_pl, x_planes=ctx.aggs[l][1])
             G['gcn.gcn_layers.%d.W.bias' % l] = colsum(dpre, B * Gn, D)
-            dagg = matmul_nn(dpre, P['gcn.gcn_layers.%d.W.weight' % l], B * Gn)
+            dagg = matmul_nn(dpre, P['gcn.gcn_layers.%d.W.weight' % l], B * Gn, x_planes=dpre_pl)
             dprev = _empty((B * Gn, D), dev)
             ops.gcn_aggregate(nnzT, colT, valT, dagg, B, Gn, D, dprev)
             if residual:
