@@ -19,7 +19,21 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(_lib.lib, s), 'missing symbol ' + s
         assert s in _lib.SIGNATURES, 'no ctypes signature for ' + s
-    assert _lib.lib.nnr_abi_version() == 3
+    header = open(os.path.join(ROOT, 'include', 'nnr_b200.h')).read()
+    assert _lib.lib.nnr_abi_version() == int(re.search(r'#define\s+NNR_ABI_VERSION\s+(\d+)', header).group(1))
+
+
+def test_graft_entry_build_check_accepts_the_current_library():
+    """__graft_entry__.build() asserts the loaded library matches the header's ABI version (no recompilation here)"""
+    import importlib
+    import subprocess
+    g = importlib.import_module('__graft_entry__')
+    real = subprocess.run
+    try:
+        subprocess.run = lambda *a, **k: None           # skip nvcc: the library is already built for this test session
+        g.build()
+    finally:
+        subprocess.run = real
 
 
 def test_argument_errors_are_reported_without_a_gpu():
