@@ -2,12 +2,14 @@
 //
 //   C[M,N] = epi( op(A)[M,K] * op(B)[K,N] )      fp32 in, fp32 out, fp32-grade accuracy
 //
-// Arithmetic: 3xTF32.  Every fp32 operand x is split into hi = rna_tf32(x) and lo = rna_tf32(x - hi);
-// D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi on the 5th-generation tensor cores (tcgen05.mma kind::tf32,
-// fp32 accumulation in TMEM).  The split is good to ~2^-21; what remains (4e-6 at K=400 ... 1e-5 at K=1600,
-// relative to max|C|) comes from the tensor core truncating when it adds into the TMEM accumulator, so long
-// contractions (wgrad: K = tokens) are cut into chains of <= 1024 k whose partial sums are combined in a
-// fixed order in exact fp32.  algo NNR_GEMM_TC_BF16 runs one kind::f16 pass on bf16-rounded operands.
+// Arithmetic: split operands.  Every fp32 operand x is split into hi and lo = round(x - hi) planes and
+// D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi runs on the 5th-generation tensor cores with fp32 accumulation in TMEM:
+//   NNR_GEMM_TC_BF16X3 (default)  bf16 hi / lo planes, tcgen05.mma kind::f16  -- measured 6e-6 of max|C|
+//   NNR_GEMM_TC_TF32X3            tf32 hi / lo planes, tcgen05.mma kind::tf32 -- 4e-6 (K=400) ... 1.1e-5 (K=1600)
+//   NNR_GEMM_TC_BF16              one bf16 plane (the reduced-precision variant)
+// What remains of the error comes from the tensor core truncating when it adds into the TMEM accumulator, so long
+// contractions (wgrad: K = tokens) are cut into chains of <= 1024 k whose partial sums are combined in a fixed order
+// in exact fp32.
 //
 // Structure
 //   pre-pass   tc_split_kernel: row-major operand -> planes [hi|lo][rows][cols] in the workspace (elementwise,
@@ -16,13 +18,17 @@
 //              wgrad operands) is consumed MN-major straight from the same row-major planes.
 //   main       persistent kernel, one CTA per SM, static round-robin over (m-tile, n-tile, k-split) with the
 //              valid tile count computed on the device from m_dev / k_dev (no host synchronisation):
-//     warp 0     TMA producer: cp.async.bulk.tensor.3d (SWIZZLE_128B) of A_hi, A_lo, B_hi, B_lo for one
-//                32-wide k-block into a ring of shared-memory stages; mbarrier expect_tx completion.
+//     warp 0     TMA producer: cp.async.bulk.tensor.3d (SWIZZLE_128B) of A_hi, A_lo, B_hi, B_lo for one 128-byte
+//                (64 bf16 / 32 tf32) k-block into a ring of shared-memory stages; mbarrier expect_tx completion.
 //     warp 1     TMEM allocator (512 columns = two accumulators) and single-thread tcgen05.mma issuer:
 //                12 MMAs per stage (4 k-steps x 3 split products), tcgen05.commit frees the stage / publishes
 //                the accumulator.
-//     warps 2-9  epilogue (two warps per TMEM lane quarter, half the columns each): tcgen05.ld one accumulator row per thread, fused bias / tanh / relu+residual(+dropout)
-//                / sigmoid-gate / add, 16-byte stores; overlaps the next tile's main loop (double-buffered TMEM).
+//     warps 2-9  epilogue (two warps per TMEM lane quarter, half the columns each): tcgen05.ld one accumulator row per
+//                thread, 32x16 transpose through a per-warp shared-memory tile, then fused bias / tanh / relu+residual
+//                (+dropout) / sigmoid-gate / add with coalesced 16-byte global accesses; overlaps the next tile's main
+//                loop (double-buffered TMEM).
+//   CTA pairs  row counts >= 2*128*148 run 256-row tiles on 2-CTA clusters (tcgen05.mma.cta_group::2): each CTA loads its
+//              128 rows of A and half of the B tile, the leader issues the MMAs for both (see the PAIR template flag).
 //   split-K    partials + a deterministic fixed-order reduce.
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
@@ -39,7 +45,6 @@ extern "C" int nnr_gemm_default_algo(void);
 #define TC_EPI_PITCH 80       // bytes per row of an epilogue warp's 32 x 16 fp32 transpose tile (conflict-free 16 B accesses)
 #define TC_EPI_SCRATCH (8 * 32 * TC_EPI_PITCH)
 #define TC_SMEM_BUDGET (205 * 1024)   // pipeline stages; + TC_EPI_SCRATCH + alignment slack + barriers <= 227 KB
-#define TC_PREFETCH_KB 1000000   // L2 prefetch distance in k-blocks; measured slower when enabled (6), so effectively off
 #define TC_CHAIN_K 1024      // max contraction length accumulated in TMEM before an fp32 combine (split-K GEMMs)
 
 // ------------------------------------------------------------------------------------------------
@@ -74,10 +79,6 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
-}
-// L2 prefetch of a TMA box: hides the DRAM latency of operand planes behind L2 capacity instead of smem stages
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -190,87 +191,7 @@ struct TcParams {
   EpiP epi;
 };
 
-// ---- vectorised epilogue over 16 consecutive columns of one row --------------------------------------------
-__device__ __forceinline__ void ld16(const float* p, bool vec, float* o) {
-  if (vec) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
-      o[4 * q] = t.x; o[4 * q + 1] = t.y; o[4 * q + 2] = t.z; o[4 * q + 3] = t.w;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) o[i] = __ldg(p + i);
-  }
-}
-__device__ __forceinline__ void st16(float* p, bool vec, const float* o) {
-  if (vec) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(p)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) p[i] = o[i];
-  }
-}
 __device__ __forceinline__ bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
-
-__device__ __forceinline__ void epi_store16(const EpiP& e, int m, int n, float* v) {
-  // caller guarantees n + 16 <= N
-  float t[16];
-  switch (e.epilogue) {
-    case NNR_EPI_BIAS:
-    case NNR_EPI_BIAS_TANH:
-    case NNR_EPI_BIAS_RELU_RES:
-      if (e.bias) {
-        ld16(e.bias + n, al16(e.bias + n), t);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += t[i];
-      }
-      break;
-    default: break;
-  }
-  if (e.epilogue == NNR_EPI_BIAS_TANH) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
-  } else if (e.epilogue == NNR_EPI_BIAS_RELU_RES) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-    if (e.aux_out) { float* p = e.aux_out + (size_t)m * e.ldaux_out + n; st16(p, al16(p), v); }
-    if (e.aux) {
-      const float* p = e.aux + (size_t)m * e.ldaux + n;
-      ld16(p, al16(p), t);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += t[i];
-    }
-    if (e.p_drop > 0.f) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] *= dropout_scale(e.seed, (uint64_t)m * (uint64_t)e.N + n + i, e.p_drop, e.inv_keep);
-    }
-  } else if (e.epilogue == NNR_EPI_GATE) {
-    const float* rb = e.rowbias + (size_t)e.rowmap[m] * e.ldrowbias + n;
-    ld16(rb, al16(rb), t);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = sigmoidf_(v[i] + t[i]);
-    if (e.aux_out) { float* p = e.aux_out + (size_t)m * e.ldaux_out + n; st16(p, al16(p), v); }
-    const float* p = e.aux + (size_t)m * e.ldaux + n;
-    ld16(p, al16(p), t);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] *= t[i];
-  } else if (e.epilogue == NNR_EPI_ADD_AUX) {
-    const float* p = e.aux + (size_t)m * e.ldaux + n;
-    ld16(p, al16(p), t);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += t[i];
-  }
-  float* c = e.C + (size_t)m * e.ldc + n;
-  const bool cv = al16(c);
-  if (e.accumulate) {
-    ld16(c, cv, t);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += t[i];
-  }
-  st16(c, cv, v);
-}
 
 // ---- epilogue over 4 consecutive columns of one row (the coalesced layout: a quad of lanes covers 64 contiguous
 // bytes of a row, a warp instruction 8 rows x 64 B), cnt = valid columns (N tail) --------------------------------
@@ -486,13 +407,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     const int c_begin = chalf ? ((nchunks + 1) >> 1) << 4 : 0;
     const int c_end = chalf ? p.block_n : ((nchunks + 1) >> 1) << 4;
     int tl = 0;
-    const bool nvec = (p.N % 4) == 0;
     for (int tile = sched_id; tile < total_tiles; tile += sched_n, ++tl) {
       const int n_idx = tile % n_tiles, rest = tile / n_tiles;
       const int m0 = (rest % m_tiles) * TILE_M + (int)rank * TC_BM, n0 = n_idx * p.block_n, z = rest / m_tiles;
       const int kb0 = z * kb_per, kb1 = min(nkb, kb0 + kb_per);
       const int buf = tl & 1;
-      const int m = m0 + q * 32 + lane;
       mbar_wait(&tmem_full[buf], (tl >> 1) & 1);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + buf * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
