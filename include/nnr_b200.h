@@ -109,6 +109,14 @@ int64_t nnr_tc_split_pitch(int C, int algo);
 size_t nnr_tc_split_bytes(int R, int C, int algo);
 int nnr_tc_split(const float* X, int64_t ld, int R, int C, const int32_t* r_dev, int algo, void* planes,
                  size_t planes_bytes, void* stream);
+/* nnr_tc_split of many matrices in ONE launch (e.g. every weight matrix right after the optimizer step).
+ * `descs` is a DEVICE array of n descriptors; planes = [hi|lo][rows][pitch] with pitch = nnr_tc_split_pitch(cols). */
+typedef struct nnr_split_desc {
+  const float* src; int64_t ld; int32_t rows, cols;
+  void* planes; int64_t pitch;
+} nnr_split_desc;
+int nnr_tc_split_many(const nnr_split_desc* descs, int n, int algo, void* stream);
+
 /* Stable descending sort of small integer keys (the sequence lengths of newsEncoders.py:112,114):
  * sorted_idx[rank] = original index, ties in ascending original index (= torch.sort on CUDA).  N <= 8192,
  * 0 <= key <= max_key <= 1024 (keys are clamped). */

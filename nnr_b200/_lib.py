@@ -53,6 +53,10 @@ class PoolArgs(C.Structure):
                 ('seg_order', vp)]
 
 
+class SplitDesc(C.Structure):
+    _fields_ = [('src', vp), ('ld', i64), ('rows', i32), ('cols', i32), ('planes', vp), ('pitch', i64)]
+
+
 # name -> (restype, argtypes); must list every symbol include/nnr_b200.h declares
 SIGNATURES = {
     'nnr_last_error': (C.c_char_p, []),
@@ -72,6 +76,7 @@ SIGNATURES = {
     'nnr_tc_split_colsum_workspace_bytes': (sz, [C.c_int, C.c_int, C.c_int]),
     'nnr_tc_split_colsum': (C.c_int, [vp, i64, C.c_int, C.c_int, vp, C.c_int, vp, sz, vp, C.c_int, vp, sz, vp]),
     'nnr_length_sort_desc': (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
+    'nnr_tc_split_many': (C.c_int, [vp, C.c_int, C.c_int, vp]),
     'nnr_gemm_default_algo': (C.c_int, []),
     'nnr_colsum_workspace_bytes': (sz, [C.c_int, C.c_int]),
     'nnr_colsum': (C.c_int, [vp, i64, C.c_int, C.c_int, vp, vp, C.c_int, vp, sz, vp]),

@@ -56,6 +56,11 @@ def weights_changed():
     _weight_planes.clear()
 
 
+def install_weight_planes(W, planes):
+    """register externally refreshed planes of W (trainer.TrainStep re-splits all weights in one launch per step)"""
+    _weight_planes[id(W)] = ((_weight_epoch, W._version, W.data_ptr(), W.shape[0], W.shape[1], W.stride(0)), planes, weakref.ref(W))
+
+
 def weight_planes(W):
     # only nn.Parameter objects: a temporary (e.g. a torch.cat of two weights) can be freed and its address reused by a
     # different matrix of the same shape within one parameter version

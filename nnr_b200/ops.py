@@ -123,6 +123,36 @@ def tc_split(x, rows, cols, ld, r_dev=None, colsum_out=None, accumulate=False):
     return Planes(buf, rows, cols, int(lib.nnr_tc_split_pitch(cols, algo)), 2 if algo in (ALGO_BF16, ALGO_BF16X3) else 4)
 
 
+class SplitMany:
+    """operand planes of a fixed set of row-major matrices (the weight matrices), refreshed by ONE kernel launch"""
+
+    def __init__(self, mats):
+        import ctypes as C_
+        from ._lib import SplitDesc
+        self.algo = default_algo()
+        self.planes = []
+        self.n = 0
+        if self.algo == ALGO_SIMT or not mats:
+            return
+        dev = mats[0].device
+        arr = (SplitDesc * len(mats))()
+        esz = 2 if self.algo in (ALGO_BF16, ALGO_BF16X3) else 4
+        for i, w in enumerate(mats):
+            rows, cols = w.shape
+            pitch = int(lib.nnr_tc_split_pitch(cols, self.algo))
+            buf = torch.empty(int(lib.nnr_tc_split_bytes(rows, cols, self.algo)), dtype=torch.uint8, device=dev)
+            arr[i].src, arr[i].ld, arr[i].rows, arr[i].cols = w.data_ptr(), w.stride(0), rows, cols
+            arr[i].planes, arr[i].pitch = buf.data_ptr(), pitch
+            self.planes.append(Planes(buf, rows, cols, pitch, esz))
+        raw = bytes(arr)
+        self.descs = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        self.n = len(mats)
+
+    def refresh(self):
+        if self.n:
+            check(lib.nnr_tc_split_many(self.descs.data_ptr(), self.n, self.algo, _stream()), 'nnr_tc_split_many')
+
+
 def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, transA, transB, epilogue=EPI_NONE, accumulate=False, bias=None,
          aux=None, ldaux=0, aux_out=None, ldaux_out=0, rowbias=None, ldrowbias=0, rowmap=None, m_dev=None,
          k_dev=None, p_drop=0.0, seed=0, algo=ALGO_AUTO, a_planes=None, b_planes=None):

@@ -46,8 +46,22 @@ class TrainStep:
             p._nnr_flat_grad = True          # engine._param_grads adds straight into these views
             o += s
         self.params = params
+        # operand planes of every GEMM weight matrix, refreshed by one launch after each optimizer step (instead of one
+        # small split launch per weight per step); embedding tables are gathered, not multiplied
+        self._gemm_weights = [p for n, p in model.named_parameters()
+                              if p.requires_grad and p.dim() == 2 and p.is_cuda and 'embedding' not in n and '_lstm.' not in n]
+        self._gemm_weights = list({id(p): p for p in self._gemm_weights}.values())
+        self._split = ops.SplitMany(self._gemm_weights) if dev.type == 'cuda' else None
+        self._refresh_weight_planes()
         self.step_count = 0
         self.grad_norm = torch.zeros(1, device=dev)
+
+    def _refresh_weight_planes(self):
+        engine.weights_changed()
+        if self._split is not None and self._split.n:
+            self._split.refresh()
+            for w, pl in zip(self._gemm_weights, self._split.planes):
+                engine.install_weight_planes(w, pl)
 
     def zero_grad(self):
         self.gflat.zero_()
@@ -84,7 +98,7 @@ class TrainStep:
         self.step_count += 1
         ops.flat_clip_adam(self.flat, self.gflat, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
                            self.eps, self.max_norm, 1.0 / self.world_size, self.step_count, self.grad_norm)
-        engine.weights_changed()   # the kernel updates the parameters through raw pointers: drop their cached operand planes
+        self._refresh_weight_planes()   # the kernel updates the parameters through raw pointers: re-split them (one launch)
 
 
 def shard_batch(batch, rank, world_size):
