@@ -747,6 +747,11 @@ static int pick_block_n(int N, int step, int nplanes) {
 
 // CTA-pair tiles: 256 x bn with bn <= 256, bn % 16 == 0 (K-major B) or % 128 == 0 (MN-major B: each CTA holds whole 64-wide
 // groups), three pipeline stages required.  Returns 0 when no such tile keeps the padding reasonable.
+static int chain_k_limit() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NNR_TC_CHAIN_K"); v = e ? atoi(e) : TC_CHAIN_K; if (v < 256) v = 256; }
+  return v;
+}
 static int pair_mode() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("NNR_TC_PAIR"); v = e ? atoi(e) : 1; }
@@ -795,12 +800,13 @@ static TcPlan make_plan(const nnr_gemm_args* a, int mode) {
   // split-K: (a) fill the machine when the output grid is small, (b) bound the TMEM accumulation chain
   int nkb_cap = (a->K + pl.kelem - 1) / pl.kelem;
   pl.split_k = 0;
-  pl.chain_kb = TC_CHAIN_K / pl.kelem;
+  const int chain_k = chain_k_limit();
+  pl.chain_kb = chain_k / pl.kelem;
   if (!pl.pair && tiles * 2 <= 148 && nkb_cap >= 8) {   // an output grid that already fills more than half the SMs is not split
     int target = (int)((148 + tiles - 1) / tiles);
     int chain = (nkb_cap + target - 1) / target;
     if (chain < 4) chain = 4;
-    if (chain > TC_CHAIN_K / pl.kelem) chain = TC_CHAIN_K / pl.kelem;
+    if (chain > chain_k / pl.kelem) chain = chain_k / pl.kelem;
     if (chain < nkb_cap) { pl.split_k = 1; pl.chain_kb = chain; }
   }
   pl.max_splits = pl.split_k ? (nkb_cap + pl.chain_kb - 1) / pl.chain_kb : 1;
