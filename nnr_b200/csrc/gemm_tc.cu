@@ -215,9 +215,9 @@ __device__ __forceinline__ void st4(float* p, int cnt, const float* o) {
 // The epilogue of one 4-column item is split in a load part and a finish part so that the loads of the four items a
 // lane handles per chunk are all in flight before the first store (a store would otherwise fence the next item's loads).
 struct Epi4In { float rb[4], ax[4], cc[4]; };
-__device__ __forceinline__ void epi_load4(const EpiP& e, int m, int n, int cnt, Epi4In& in) {
+__device__ __forceinline__ void epi_load4(const EpiP& e, int m, int n, int cnt, Epi4In& in, int rmap) {
   if (e.epilogue == NNR_EPI_GATE) {
-    ld4(e.rowbias + (size_t)__ldg(e.rowmap + m) * e.ldrowbias + n, cnt, in.rb);
+    ld4(e.rowbias + (size_t)rmap * e.ldrowbias + n, cnt, in.rb);     // rmap = rowmap[m], loaded once per tile by the caller
     ld4(e.aux + (size_t)m * e.ldaux + n, cnt, in.ax);
   } else if (e.epilogue == NNR_EPI_ADD_AUX || (e.epilogue == NNR_EPI_BIAS_RELU_RES && e.aux)) {
     ld4(e.aux + (size_t)m * e.ldaux + n, cnt, in.ax);
@@ -412,14 +412,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const int m0 = (rest % m_tiles) * TILE_M + (int)rank * TC_BM, n0 = n_idx * p.block_n, z = rest / m_tiles;
       const int kb0 = z * kb_per, kb1 = min(nkb, kb0 + kb_per);
       const int buf = tl & 1;
-      mbar_wait(&tmem_full[buf], (tl >> 1) & 1);
-      tc_fence_after();
       const uint32_t lane_addr = tmem_base + buf * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
       // Each thread reads one accumulator row (tcgen05.ld 32x32b), the warp transposes 32 x 16 chunks through its
       // shared-memory tile, and all global traffic of the epilogue (C, aux, row bias, accumulate) then runs in the
       // coalesced layout: lane -> (row = lane / 4 + 8 i, 4 columns = 4 (lane % 4)), 64 contiguous bytes per row.
       unsigned char* my_tile = epi_scratch + (size_t)(warp - 2) * 32 * TC_EPI_PITCH;
       const int tr = lane >> 2, tc4 = (lane & 3) * 4;
+      // a lane finishes the same four rows in every chunk of the tile: their row-map entries (gate epilogue) are fetched
+      // once, before the accumulator is waited for, so the row-bias loads of the chunks are not behind a dependent load
+      int rmap[4] = {0, 0, 0, 0};
+      if (p.epi.epilogue == NNR_EPI_GATE && !p.partial) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int mm = m0 + q * 32 + tr + 8 * i;
+          if (mm < M) rmap[i] = __ldg(p.epi.rowmap + mm);
+        }
+      }
+      mbar_wait(&tmem_full[buf], (tl >> 1) & 1);
+      tc_fence_after();
       for (int c0 = c_begin; c0 < c_end; c0 += 16) {
         float v[16];
         if (kb1 > kb0) tmem_ld16(lane_addr + (uint32_t)c0, v);
@@ -454,7 +464,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int mm = m0 + q * 32 + tr + 8 * i;
-              if (mm < M) epi_load4(p.epi, mm, n, cnt, in[i]);
+              if (mm < M) epi_load4(p.epi, mm, n, cnt, in[i], rmap[i]);
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
