@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NNR_ABI_VERSION 3
+#define NNR_ABI_VERSION 4
 
 const char* nnr_last_error(void);
 int nnr_abi_version(void);
@@ -50,6 +50,12 @@ int nnr_seq_prepare(uint8_t* mask, int N, int L, int32_t* len, int32_t* off, int
 int nnr_embed_gather_fwd(const float* table, const int32_t* ids, const int32_t* len,
                          const int32_t* off, int N, int L, int E, int V, float* out, float p_drop,
                          uint64_t seed, void* stream);
+/* the same gather + dropout written directly as operand planes of the tensor-core GEMM (layout of nnr_tc_split for a
+ * [cap, E] matrix, rows [ntok, round_up(ntok, 64)) zeroed): bit-identical to nnr_embed_gather_fwd followed by
+ * nnr_tc_split.  The consumer passes A = NULL / B = NULL with A_planes / B_planes to nnr_gemm.  E % 4 == 0.   */
+int nnr_embed_gather_planes_fwd(const float* table, const int32_t* ids, const int32_t* len,
+                                const int32_t* off, int N, int L, int E, int V, int cap, float p_drop,
+                                uint64_t seed, int algo, void* planes, size_t planes_bytes, void* stream);
 /* autograd of the above (ATen embedding_dense_backward): deterministic sort-by-id + segment
  * reduce into the dense [V,E] table gradient.  `dout` is packed [tokens,E].                      */
 size_t nnr_embed_gather_bwd_workspace_bytes(int N, int L);
@@ -93,7 +99,8 @@ typedef struct {
   float p_drop; uint64_t seed;
   int32_t algo;
   void* workspace; size_t workspace_bytes;   /* operand planes + split-K partials (see nnr_gemm_workspace_bytes) */
-  /* optional: operands already split by nnr_tc_split (tensor-core backend only; A/B must still be given).
+  /* optional: operands already split by nnr_tc_split (tensor-core backend only; A / B may then be NULL --
+   * an operand that exists only as planes makes nnr_gemm fail if the exact-fp32 kernel would have to run).
    * X_planes points at the first plane of the (possibly column-sliced) stored matrix, pitch in elements,
    * plane_rows = rows of the full planes (plane stride = plane_rows * pitch). */
   const void* A_planes; int64_t a_planes_pitch; int64_t a_planes_rows;

@@ -66,6 +66,7 @@ SIGNATURES = {
     'nnr_profile_read': (C.c_int, [C.POINTER(C.c_double), C.c_int]),
     'nnr_seq_prepare': (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),
     'nnr_embed_gather_fwd': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, f32, u64, vp]),
+    'nnr_embed_gather_planes_fwd': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32, u64, C.c_int, vp, sz, vp]),
     'nnr_embed_gather_bwd_workspace_bytes': (sz, [C.c_int, C.c_int]),
     'nnr_embed_gather_bwd': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, u64, vp, C.c_int, vp, sz, vp]),
     'nnr_gemm_workspace_bytes': (sz, [C.POINTER(GemmArgs)]),

@@ -35,7 +35,7 @@ static int pick_algo(const nnr_gemm_args* a) {
 }
 
 static int validate(const nnr_gemm_args* a) {
-  NNR_REQUIRE(a && a->A && a->B && a->C, NNR_ERR_ARG, "nnr_gemm: null operand");
+  NNR_REQUIRE(a && (a->A || a->A_planes) && (a->B || a->B_planes) && a->C, NNR_ERR_ARG, "nnr_gemm: null operand");
   NNR_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, NNR_ERR_ARG, "nnr_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
   NNR_REQUIRE(a->epilogue >= NNR_EPI_NONE && a->epilogue <= NNR_EPI_ADD_AUX, NNR_ERR_ARG, "nnr_gemm: bad epilogue %d", a->epilogue);
   NNR_REQUIRE(a->lda >= (a->transA ? a->M : a->K), NNR_ERR_ARG, "nnr_gemm: lda too small");
@@ -65,7 +65,10 @@ extern "C" int nnr_gemm(const nnr_gemm_args* a, void* stream) {
   int rc = validate(a);
   if (rc) return rc;
   int algo = pick_algo(a);
-  if (algo == NNR_GEMM_SIMT_FP32) return nnr_gemm_simt(a, stream);
+  if (algo == NNR_GEMM_SIMT_FP32) {
+    NNR_REQUIRE(a->A && a->B, NNR_ERR_UNSUPPORTED, "nnr_gemm: an operand given only as planes needs the tensor-core path");
+    return nnr_gemm_simt(a, stream);
+  }
   NNR_REQUIRE(nnr_gemm_tc_supported(a), NNR_ERR_UNSUPPORTED, "nnr_gemm: tensor-core path does not support this shape/layout");
   nnr_gemm_args b = *a;
   b.algo = algo;

@@ -844,7 +844,8 @@ int nnr_gemm_tc_supported(const nnr_gemm_args* a) {
   if (disabled) return 0;
   if (!get_encode()) return 0;
   // tiny problems are launch-bound either way; the FFMA kernel handles them exactly
-  if ((double)a->M * a->N * a->K < 2.0e6) return 0;
+  // (an operand that exists only as planes cannot go there, so it stays on this path whatever the size)
+  if ((double)a->M * a->N * a->K < 2.0e6 && a->A && a->B) return 0;
   if (a->K < 8) return 0;
   // device-side bounds: m_dev needs row-major A (rows = M); k_dev needs both operands stored [K, .]
   if (a->m_dev && a->transA) return 0;
@@ -1032,6 +1033,76 @@ extern "C" int nnr_tc_split_colsum(const float* X, int64_t ld, int R, int C, con
   NNR_LAUNCH_CHECK("tc_split_colsum_kernel");
   tc_split_colsum_reduce<<<(C + 31) / 32, 512, 0, st>>>((const float*)workspace, nblocks, R, C, Cp, r_dev, colsum, accumulate);
   NNR_LAUNCH_CHECK("tc_split_colsum_reduce");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Word-embedding gather + dropout written DIRECTLY as operand planes (newsEncoders.py:117-118): the embedded tokens
+// are only ever consumed by GEMMs (gx = x W_ih^T forward, dW_ih = dz^T x backward), so the packed fp32 [tokens, E]
+// tensor never has to exist: one warp per (row, t) token slot reads the table row, applies the keep mask of
+// nnr_embed_gather_fwd (same counter = (slot * E + e), same scale) and stores hi/lo.  Extra warps zero the row tail
+// [ntok, round_up(ntok, 64)) that the MN-major (wgrad) tiles read.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) embed_gather_planes_kernel(const float* __restrict__ table, const int32_t* __restrict__ ids,
+                                                                  const int32_t* __restrict__ len, const int32_t* __restrict__ off,
+                                                                  int N, int L, int E, int V, int cap, int Cp, void* __restrict__ out,
+                                                                  size_t plane_stride, float p, float inv_keep, uint64_t seed) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long slots = (long long)N * L;
+  const int ncq = Cp >> 2, E4 = E >> 2;
+  if (w >= slots) {                                                   // zero tail rows
+    const int ntok = off[N];
+    const long long row = (long long)ntok + (w - slots);
+    if (row >= min((long long)cap, ((long long)ntok + 63) / 64 * 64)) return;
+    for (int q = lane; q < ncq; q += 32) tc_split_store4<MODE>(out, plane_stride, Cp, (int)row, q * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    return;
+  }
+  const int slot = (int)w;
+  const int r = slot / L, t = slot - r * L;
+  if (t >= len[r]) return;
+  int id = ids[slot];
+  id = min(max(id, 0), V - 1);
+  const float4* src = reinterpret_cast<const float4*>(table + (size_t)id * E);
+  const int row = off[r] + t;
+  const uint64_t ebase4 = ((uint64_t)slot * (uint64_t)E) >> 2;        // E % 4 == 0
+  for (int q = lane; q < ncq; q += 32) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);                       // column pad [E, Cp)
+    if (q < E4) {
+      v = __ldg(src + q);
+      if (p > 0.0f) {
+        float ks[4];
+        dropout_scale4(seed, ebase4 + q, p, inv_keep, ks);
+        v.x *= ks[0]; v.y *= ks[1]; v.z *= ks[2]; v.w *= ks[3];
+      }
+    }
+    tc_split_store4<MODE>(out, plane_stride, Cp, row, q * 4, v);
+  }
+}
+
+extern "C" int nnr_embed_gather_planes_fwd(const float* table, const int32_t* ids, const int32_t* len, const int32_t* off,
+                                           int N, int L, int E, int V, int cap, float p_drop, uint64_t seed, int algo,
+                                           void* planes, size_t planes_bytes, void* stream) {
+  NNR_REQUIRE(table && ids && len && off && planes && N > 0 && L > 0 && E > 0 && V > 0 && cap > 0, NNR_ERR_ARG,
+              "nnr_embed_gather_planes_fwd: bad arguments");
+  NNR_REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, NNR_ERR_ARG, "nnr_embed_gather_planes_fwd: p_drop=%f", p_drop);
+  NNR_REQUIRE(E % 4 == 0 && nnr_aligned16(table) && nnr_aligned16(planes), NNR_ERR_ALIGN,
+              "nnr_embed_gather_planes_fwd: E %% 4 == 0 and 16B-aligned table / planes required");
+  NNR_REQUIRE(algo == NNR_GEMM_TC_TF32X3 || algo == NNR_GEMM_TC_BF16 || algo == NNR_GEMM_TC_BF16X3, NNR_ERR_UNSUPPORTED,
+              "nnr_embed_gather_planes_fwd: planes exist only for the tensor-core GEMM algorithms");
+  NNR_REQUIRE(planes_bytes >= nnr_tc_split_bytes(cap, E, algo), NNR_ERR_WORKSPACE, "nnr_embed_gather_planes_fwd: planes buffer too small");
+  const int mode = algo_mode(algo);
+  const int Cp = (int)nnr_tc_split_pitch(E, algo);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t warps = (size_t)N * L + 64;
+  const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+  const float inv_keep = 1.0f / (1.0f - p_drop);
+  const size_t ps = (size_t)cap * Cp;
+  if (mode == 1) embed_gather_planes_kernel<1><<<blocks, 256, 0, st>>>(table, ids, len, off, N, L, E, V, cap, Cp, planes, ps, p_drop, inv_keep, seed);
+  else if (mode == 2) embed_gather_planes_kernel<2><<<blocks, 256, 0, st>>>(table, ids, len, off, N, L, E, V, cap, Cp, planes, ps, p_drop, inv_keep, seed);
+  else embed_gather_planes_kernel<0><<<blocks, 256, 0, st>>>(table, ids, len, off, N, L, E, V, cap, Cp, planes, ps, p_drop, inv_keep, seed);
+  NNR_LAUNCH_CHECK("embed_gather_planes_kernel");
   return 0;
 }
 

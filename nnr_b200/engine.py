@@ -82,10 +82,10 @@ def linear(x, W, M, m_dev=None, bias=None, epilogue=None, out=None, x_planes=Non
     """out[M,N] = epi(x[M,K] @ W[N,K]^T)"""
     N, K = W.shape
     if out is None:
-        out = _empty((M, N), x.device)
+        out = _empty((M, N), W.device)
     if epilogue is None:
         epilogue = EPI_BIAS if bias is not None else EPI_NONE
-    ops.gemm(x, W, out, M, N, K, x.stride(0), W.stride(0), out.stride(0), False, True, epilogue, bias=bias,
+    ops.gemm(x, W, out, M, N, K, x.stride(0) if x is not None else K, W.stride(0), out.stride(0), False, True, epilogue, bias=bias,
              m_dev=m_dev, a_planes=x_planes, b_planes=w_planes if w_planes is not None else weight_planes(W), **epi)
     return out
 
@@ -104,7 +104,7 @@ def wgrad(dy, x, M, N, K, k_dev=None, out=None, accumulate=False, dy_planes=None
     """out[N,K] = dy[M,N]^T @ x[M,K]   (contraction over the M rows / tokens)"""
     if out is None:
         out = _empty((N, K), dy.device)
-    ops.gemm(dy, x, out, N, K, M, dy.stride(0), x.stride(0), out.stride(0), True, False, k_dev=k_dev,
+    ops.gemm(dy, x, out, N, K, M, dy.stride(0), x.stride(0) if x is not None else K, out.stride(0), True, False, k_dev=k_dev,
              accumulate=accumulate, a_planes=dy_planes, b_planes=x_planes)
     return out
 
@@ -196,14 +196,21 @@ def _cne_modality_forward(P, x, ids, mask_u8, N, L, E, Hd, training, p_drop, see
         m.order = _sort_desc(len64, L).to(torch.int32)
     m.seed = seed
     m.p = p_drop if training else 0.0
-    m.emb = _empty((cap, E), dev)
-    ops.embed_gather_fwd(P['word_embedding.weight'], ids, m.len, m.off, m.emb, m.p, seed)
+    table = P['word_embedding.weight']
+    fused_planes = ops.default_algo() != ops.ALGO_SIMT and E % 4 == 0 and table.data_ptr() % 16 == 0
+    if fused_planes:       # the embedded tokens feed GEMMs only: write them as operand planes, no fp32 [tokens, E] tensor
+        m.emb = None
+        m.emb_pl = ops.embed_gather_planes_fwd(table, ids, m.len, m.off, cap, m.p, seed)
+    else:
+        m.emb = _empty((cap, E), dev)
+        ops.embed_gather_fwd(table, ids, m.len, m.off, m.emb, m.p, seed)
     pre = x + '_lstm.'
     m.w_ih = torch.cat([P[pre + 'weight_ih_l0'], P[pre + 'weight_ih_l0_reverse']], 0)          # [8H, E]
     m.w_hh = torch.stack([P[pre + 'weight_hh_l0'], P[pre + 'weight_hh_l0_reverse']], 0)        # [2, 4H, H]
     bias = torch.cat([P[pre + 'bias_ih_l0'] + P[pre + 'bias_hh_l0'],
                       P[pre + 'bias_ih_l0_reverse'] + P[pre + 'bias_hh_l0_reverse']], 0)       # [8H]
-    m.emb_pl = split_tokens(m.emb, cap, E, m.ntok)
+    if not fused_planes:
+        m.emb_pl = split_tokens(m.emb, cap, E, m.ntok)
     m.w_ih_pl = ops.tc_split(m.w_ih, 8 * Hd, E, m.w_ih.stride(0))                              # shared with the dgrad GEMM
     m.gates = linear(m.emb, m.w_ih, cap, m.ntok, bias, x_planes=m.emb_pl, w_planes=m.w_ih_pl)  # gx, then the stash
     m.h = _empty((cap, 2 * Hd), dev)

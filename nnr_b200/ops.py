@@ -69,6 +69,19 @@ def embed_gather_fwd(table, ids, len_, off, out, p_drop, seed):
                                    _p(out, _F32), float(p_drop), int(seed), _stream()), 'nnr_embed_gather_fwd')
 
 
+def embed_gather_planes_fwd(table, ids, len_, off, cap, p_drop, seed):
+    """embedding gather + dropout emitted as GEMM operand planes (no fp32 [tokens, E] tensor); tensor-core algos only"""
+    N, L = ids.shape
+    V, E = table.shape
+    algo = default_algo()
+    nbytes = int(lib.nnr_tc_split_bytes(cap, E, algo))
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=table.device)
+    check(lib.nnr_embed_gather_planes_fwd(_p(table, _F32), _p(ids, _I32), _p(len_, _I32), _p(off, _I32), N, L, E, V, cap,
+                                          float(p_drop), int(seed), algo, buf.data_ptr(), nbytes, _stream()),
+          'nnr_embed_gather_planes_fwd')
+    return Planes(buf, cap, E, int(lib.nnr_tc_split_pitch(E, algo)), 2 if algo in (ALGO_BF16, ALGO_BF16X3) else 4)
+
+
 def embed_gather_bwd(dout, ids, len_, off, dtable, p_drop, seed, accumulate):
     N, L = ids.shape
     V, E = dtable.shape
@@ -174,7 +187,7 @@ def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, transA, transB, epilogue=EPI_NONE, 
         a.B_planes, a.b_planes_pitch, a.b_planes_rows = b_planes.ptr(), b_planes.pitch, b_planes.rows
     nbytes = lib.nnr_gemm_workspace_bytes(C.byref(a))
     if nbytes:
-        ws = workspace(nbytes, A.device, 'gemm')
+        ws = workspace(nbytes, Cout.device, 'gemm')
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     check(lib.nnr_gemm(C.byref(a), _stream()), 'nnr_gemm')
 

@@ -33,7 +33,7 @@ def _tc_class(M, N, K, transA, transB, m_dev, k_dev):
         return False
     return True
 
-_TIMED = ['seq_prepare', 'embed_gather_fwd', 'embed_gather_bwd', 'gemm', 'colsum', 'segment_colsum', 'lstm_fwd',
+_TIMED = ['seq_prepare', 'embed_gather_fwd', 'embed_gather_planes_fwd', 'embed_gather_bwd', 'gemm', 'colsum', 'segment_colsum', 'lstm_fwd',
           'lstm_bwd', 'lstm_shift_h', 'gate_bwd_pre', 'attn_pool_fwd', 'attn_pool_bwd', 'news_fuse_fwd', 'news_fuse_bwd',
           'graph_to_csr', 'gcn_aggregate', 'cluster_intra_fwd', 'cluster_intra_bwd', 'rowdot_fwd', 'rowdot_bwd',
           'dropout', 'flat_clip_adam', 'sue_graph_build']
@@ -62,7 +62,7 @@ class Capture:
             else:
                 off, N, H = args[4], args[6], args[8]
             return lambda: (2.0 * 4 * H * H * 2 * int(off[N].item()), None)
-        if name == 'embed_gather_fwd':
+        if name in ('embed_gather_fwd', 'embed_gather_planes_fwd'):      # planes: hi + lo bf16 = the same 4 bytes per element
             table, ids, len_, off = args[:4]
             E = table.shape[1]
             return lambda: (None, float(off[ids.shape[0]].item()) * (4 + 8 * E))
@@ -107,7 +107,7 @@ class Capture:
             if name == 'gemm':
                 label = 'gemm[%dx%dx%d %s%s e%d]' % (args[3], args[4], args[5], 'T' if args[9] else 'N', 'T' if args[10] else 'N',
                                                    kw.get('epilogue', args[11] if len(args) > 11 else 0))
-            self.records.append((name, e0, e1, work, label))
+            self.records.append(('embed_gather_fwd' if name == 'embed_gather_planes_fwd' else name, e0, e1, work, label))
             return r
         return wrapped
 

@@ -80,6 +80,40 @@ def test_embed_gather_fwd_bwd(cuda):
         assert torch.allclose(dtab2, 2 * dtab, rtol=1e-6, atol=1e-6)
 
 
+def test_embed_gather_as_operand_planes(cuda):
+    """nnr_embed_gather_planes_fwd == nnr_embed_gather_fwd + nnr_tc_split bit for bit (incl. the dropout mask, the column
+    pad and the zeroed row tail), and a GEMM fed with A = NULL + planes gives the same product"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    for (N, L, V, E, p) in [(37, 12, 50, 300, 0.0), (90, 32, 600, 300, 0.2), (33, 7, 20, 52, 0.2)]:
+        mask, lens = _prefix_masks(N, L, g, allow_empty=False)
+        ids = torch.randint(0, V, (N, L), generator=g, dtype=torch.int32).to(cuda)
+        table = torch.randn(V, E, generator=g).to(cuda)
+        len_ = lens.to(torch.int32).to(cuda)
+        off = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)]).to(torch.int32).to(cuda)
+        cap = N * L
+        ntok = int(lens.sum())
+        rows = min(cap, (ntok + 63) // 64 * 64)
+        out = torch.zeros(cap, E, device=cuda)
+        ops.embed_gather_fwd(table, ids, len_, off, out, p, 77)
+        ref = ops.tc_split(out, cap, E, E, off[N:])
+        got = ops.embed_gather_planes_fwd(table, ids, len_, off, cap, p, 77)
+        assert (got.pitch, got.rows, got.ncols, got.esz) == (ref.pitch, ref.rows, ref.ncols, ref.esz)
+        nplanes = ref.buf.numel() // (cap * ref.pitch * ref.esz)
+        a = ref.buf.view(nplanes, cap, ref.pitch * ref.esz)[:, :rows]
+        b = got.buf.view(nplanes, cap, got.pitch * got.esz)[:, :rows]
+        assert torch.equal(a, b), (N, L, E, p)
+        W = torch.randn(128, E, generator=g).to(cuda)
+        y = torch.empty(cap, 128, device=cuda)
+        ops.gemm(None, W, y, cap, 128, E, E, E, 128, False, True, m_dev=off[N:], a_planes=got)   # planes-only operand
+        y_ref = out[:ntok].double() @ W.double().t()
+        assert (y[:ntok].double() - y_ref).abs().max().item() / y_ref.abs().max().item() < 2e-5
+        if cap * 128 * E >= 2e6:             # same kernel on both sides (smaller problems take the exact-fp32 kernel when A is given)
+            y2 = torch.empty(cap, 128, device=cuda)
+            ops.gemm(out, W, y2, cap, 128, E, E, E, 128, False, True, m_dev=off[N:], a_planes=ref)
+            assert torch.equal(y[:ntok], y2[:ntok])
+
+
 def test_embed_dropout_consistency(cuda):
     ops = _ops()
     N, L, V, E, p = 64, 16, 100, 300, 0.2
