@@ -165,6 +165,18 @@ int nnr_lstm_fwd(float* gx, const float* w_hh, const int32_t* len, const int32_t
 int nnr_lstm_bwd(float* gates, const float* c_stash, const float* w_hh, const int32_t* len,
                  const int32_t* off, const int32_t* order, int N, int L, int H, const float* dh,
                  const float* dcn, int32_t* tile_counters, void* stream);
+/* The same BPTT with dL/d(gx) written as the operand planes of the tensor-core GEMM (layout of nnr_tc_split for a
+ * [cap, 8H] matrix, rows [tokens, round_up(tokens, 64)) zeroed) and db[8H] = its column sums over the tokens (the bias
+ * gradient; per-tile partials added in tile order, run-to-run identical).  dL/d(gx) feeds only GEMMs and that column
+ * sum, so the fp32 tensor is never written; `gates` is left untouched.  Bit-identical to nnr_lstm_bwd followed by
+ * nnr_tc_split (planes); db differs from nnr_colsum only by fp32 summation order.
+ * nnr_lstm_bwd_planes_supported: H == 200, tensor-core recurrence (NNR_LSTM_ALGO != ffma), algo BF16 / BF16X3.        */
+int nnr_lstm_bwd_planes_supported(int H, int algo);
+size_t nnr_lstm_bwd_planes_workspace_bytes(int N, int H);
+int nnr_lstm_bwd_planes(const float* gates, const float* c_stash, const float* w_hh, const int32_t* len,
+                        const int32_t* off, const int32_t* order, int N, int L, int H, const float* dh,
+                        const float* dcn, int32_t* tile_counters, int cap, int algo, void* dz_planes,
+                        size_t planes_bytes, float* db, void* workspace, size_t workspace_bytes, void* stream);
 /* hprev[p, 0:H] = h[p-1, 0:H] (0 at t=0); hprev[p, H:2H] = h[p+1, H:2H] (0 at t=len-1): the
  * recurrent input of every step, needed for dW_hh = dgates^T hprev.                             */
 int nnr_lstm_shift_h(const float* h, const int32_t* len, const int32_t* off,

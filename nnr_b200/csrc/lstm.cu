@@ -504,7 +504,8 @@ static int launch_cluster(K kernel, size_t smem, int ntiles, cudaStream_t st, vo
 int nnr_lstm_fwd_mma(float* gx, const float* w_hh, const int32_t* len, const int32_t* off, const int32_t* order, int N,
                      float* h_out, float* c_stash, float* c_n, int32_t* tile_counters, cudaStream_t st);
 int nnr_lstm_bwd_mma(float* gates, const float* c_stash, const float* w_hh, const int32_t* len, const int32_t* off,
-                     const int32_t* order, int N, const float* dh, const float* dcn, int32_t* tile_counters, cudaStream_t st);
+                     const int32_t* order, int N, const float* dh, const float* dcn, int32_t* tile_counters, cudaStream_t st,
+                     void* dz_planes, size_t plane_stride, int two_planes, float* db_partial, float* db, int cap);
 static bool lstm_use_mma() {
   static int v = -1;
   if (v < 0) {
@@ -538,10 +539,38 @@ extern "C" int nnr_lstm_bwd(float* gates, const float* c_stash, const float* w_h
   NNR_REQUIRE(H == 200, NNR_ERR_UNSUPPORTED, "nnr_lstm_bwd: hidden_dim %d not instantiated (200 only)", H);
   NNR_REQUIRE(nnr_aligned16(gates) && nnr_aligned16(c_stash) && nnr_aligned16(dh) && nnr_aligned16(dcn), NNR_ERR_ALIGN,
               "nnr_lstm_bwd: buffers must be 16B aligned");
-  if (lstm_use_mma()) return nnr_lstm_bwd_mma(gates, c_stash, w_hh, len, off, order, N, dh, dcn, tile_counters, (cudaStream_t)stream);
+  if (lstm_use_mma())
+    return nnr_lstm_bwd_mma(gates, c_stash, w_hh, len, off, order, N, dh, dcn, tile_counters, (cudaStream_t)stream, NULL, 0, 0, NULL, NULL, 0);
   typedef BwdCfg200 C;
   int ntiles = (N + C::MT - 1) / C::MT;
   NNR_CUDA(cudaMemsetAsync(tile_counters, 0, 2 * sizeof(int32_t), (cudaStream_t)stream));
   void* args[] = {&gates, &c_stash, &w_hh, &len, &off, &order, &N, &ntiles, &dh, &dcn, &tile_counters};
   return launch_cluster<C>(lstm_bwd_kernel<C>, C::BWD_SMEM, ntiles, (cudaStream_t)stream, args, "lstm_bwd_kernel");
+}
+
+// BPTT with dL/dgx emitted as GEMM operand planes + its column sums (the bias gradient): dL/dgx is only ever read by the
+// dW_ih / dW_hh / dx GEMMs and a column sum, so the fp32 tensor and the split pass over it are skipped.
+extern "C" int nnr_lstm_bwd_planes_supported(int H, int algo) {
+  if (algo == NNR_GEMM_AUTO) algo = nnr_gemm_default_algo();
+  return H == 200 && lstm_use_mma() && (algo == NNR_GEMM_TC_BF16 || algo == NNR_GEMM_TC_BF16X3);
+}
+extern "C" size_t nnr_lstm_bwd_planes_workspace_bytes(int N, int H) {
+  if (N <= 0 || H <= 0) return 0;
+  return (size_t)((N + 31) / 32) * 8 * (size_t)H * sizeof(float);
+}
+extern "C" int nnr_lstm_bwd_planes(const float* gates, const float* c_stash, const float* w_hh, const int32_t* len,
+                                   const int32_t* off, const int32_t* order, int N, int L, int H, const float* dh,
+                                   const float* dcn, int32_t* tile_counters, int cap, int algo, void* dz_planes,
+                                   size_t planes_bytes, float* db, void* workspace, size_t workspace_bytes, void* stream) {
+  NNR_REQUIRE(gates && c_stash && w_hh && len && off && order && dh && dcn && tile_counters && dz_planes && db && workspace &&
+                  N > 0 && L > 0 && cap > 0, NNR_ERR_ARG, "nnr_lstm_bwd_planes: bad arguments");
+  if (algo == NNR_GEMM_AUTO) algo = nnr_gemm_default_algo();
+  NNR_REQUIRE(nnr_lstm_bwd_planes_supported(H, algo), NNR_ERR_UNSUPPORTED,
+              "nnr_lstm_bwd_planes: needs hidden_dim 200, the tensor-core recurrence and a bf16 GEMM algorithm");
+  NNR_REQUIRE(nnr_aligned16(gates) && nnr_aligned16(c_stash) && nnr_aligned16(dh) && nnr_aligned16(dcn) && nnr_aligned16(dz_planes),
+              NNR_ERR_ALIGN, "nnr_lstm_bwd_planes: buffers must be 16B aligned");
+  NNR_REQUIRE(planes_bytes >= nnr_tc_split_bytes(cap, 8 * H, algo), NNR_ERR_WORKSPACE, "nnr_lstm_bwd_planes: planes buffer too small");
+  NNR_REQUIRE(workspace_bytes >= nnr_lstm_bwd_planes_workspace_bytes(N, H), NNR_ERR_WORKSPACE, "nnr_lstm_bwd_planes: workspace too small");
+  return nnr_lstm_bwd_mma(const_cast<float*>(gates), c_stash, w_hh, len, off, order, N, dh, dcn, tile_counters, (cudaStream_t)stream,
+                          dz_planes, (size_t)cap * 8 * H, algo == NNR_GEMM_TC_BF16X3 ? 1 : 0, (float*)workspace, db, cap);
 }

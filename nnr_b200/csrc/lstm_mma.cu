@@ -458,7 +458,12 @@ lstm_fwd_mma_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, cons
 __global__ void __launch_bounds__(G::NT, 1)
 lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, const float* __restrict__ w_hh,
                     const int32_t* __restrict__ len, const int32_t* __restrict__ off, const int32_t* __restrict__ order,
-                    int N, int ntiles, const float* __restrict__ dh, const float* __restrict__ dcn, int* __restrict__ tile_counter) {
+                    int N, int ntiles, const float* __restrict__ dh, const float* __restrict__ dcn, int* __restrict__ tile_counter,
+                    __nv_bfloat16* __restrict__ dzp, size_t dzp_stride, int dzp_lo, float* __restrict__ db_partial) {
+  // dzp != NULL: dL/dgx leaves as the bf16 operand planes of the tensor-core GEMMs ([hi|lo][cap][8H], plane stride
+  // dzp_stride elements, lo plane only if dzp_lo) instead of fp32 into `gates`, and the column sums of every tile (the
+  // bias gradient) go to db_partial[tile][8H] -- fixed summation order, so the result does not depend on which cluster
+  // ran the tile.
   constexpr int HID = G::HID, CL = G::CL, MT = G::MT, UPC = G::UPC, UPW = G::UPW, NTW = G::NTW;
   constexpr int PITCH = G::BPITCH, WP = G::BWPITCH, RP = G::RPITCH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -571,6 +576,11 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
         bar_arrive(3, G::NT);
       };
       prefetch_stash(maxlen - 1);
+      float csum[4][4];                  // column sums of this thread's 4 gates x 4 units over its rows and all steps
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) csum[a][j] = 0.f;
       for (int s = maxlen - 1; s >= 0; --s) {
         bar_sync(2, G::NT);              // the staging tile holds dL/dgx of iteration s
         if (c_ch < 10) {
@@ -580,13 +590,54 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
               const int t = dir ? (c_len[rr] - 1 - s) : s;
               const size_t p = (size_t)c_off[rr] + t;
               const unsigned char* spc = Stg + c_so + rr * 8 * G::SROW;
-              float* g0 = gates + p * GS + (size_t)dir * 4 * HID + rank * UPC + c_ch * 4;
+              const size_t go = p * GS + (size_t)dir * 4 * HID + rank * UPC + c_ch * 4;
+              if (dzp) {
 #pragma unroll
-              for (int a = 0; a < 4; ++a) *reinterpret_cast<float4*>(g0 + a * HID) = *reinterpret_cast<const float4*>(spc + a * G::SARR);
+                for (int a = 0; a < 4; ++a) {
+                  const float4 v = *reinterpret_cast<const float4*>(spc + a * G::SARR);
+                  csum[a][0] += v.x; csum[a][1] += v.y; csum[a][2] += v.z; csum[a][3] += v.w;
+                  // same rounding as tc_split_store4 (gemm_tc.cu): hi = rn(x), lo = rn(x - hi)
+                  const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+                  __nv_bfloat16* o = dzp + go + a * HID;
+                  uint2 hv;
+                  hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                  *reinterpret_cast<uint2*>(o) = hv;
+                  if (dzp_lo) {
+                    const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __low2float(h01), v.y - __high2float(h01));
+                    const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __low2float(h23), v.w - __high2float(h23));
+                    uint2 lv;
+                    lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                    *reinterpret_cast<uint2*>(o + dzp_stride) = lv;
+                  }
+                }
+              } else {
+                float* g0 = gates + go;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) *reinterpret_cast<float4*>(g0 + a * HID) = *reinterpret_cast<const float4*>(spc + a * G::SARR);
+              }
             }
           }
         }
         if (s > 0) prefetch_stash(s - 1);
+      }
+      if (dzp) {
+        // per-tile column sums: the 8 row-slot threads of a column group are combined through the (now idle) staging
+        // tile in slot order
+        float* scr = reinterpret_cast<float*>(Stg);
+        bar_sync(4, G::NT - G::CT);      // every copy warp is done reading the staging tile
+        if (c_ch < 10) {
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            *reinterpret_cast<float4*>(scr + c_rs * G::COLS + a * UPC + c_ch * 4) = make_float4(csum[a][0], csum[a][1], csum[a][2], csum[a][3]);
+        }
+        bar_sync(4, G::NT - G::CT);
+        for (int col = tid - G::CT; col < G::COLS; col += G::NT - G::CT) {
+          float sum = 0.f;
+#pragma unroll
+          for (int rs = 0; rs < 8; ++rs) sum += scr[rs * G::COLS + col];
+          const int a = col / UPC, u = col - a * UPC;
+          db_partial[(size_t)tile * GS + (size_t)dir * 4 * HID + a * HID + rank * UPC + u] = sum;
+        }
       }
       continue;
     }
@@ -860,12 +911,45 @@ int nnr_lstm_fwd_mma(float* gx, const float* w_hh, const int32_t* len, const int
   return rc;
 }
 
+// column sums of dL/dgx = the per-tile partials added in tile order; the same launch zeroes the plane rows
+// [ntok, round_up(ntok, 64)) that the MN-major tiles of the weight-gradient GEMMs read
+__global__ void lstm_dz_finish_kernel(const float* __restrict__ db_partial, int ntiles, int cols, float* __restrict__ db,
+                                      __nv_bfloat16* __restrict__ dzp, size_t dzp_stride, int nplanes, int cap,
+                                      const int32_t* __restrict__ ntok_dev) {
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  if (gt < cols) {
+    float s = 0.f;
+    for (int t = 0; t < ntiles; ++t) s += db_partial[(size_t)t * cols + gt];
+    db[gt] = s;
+  }
+  const int ntok = min(*ntok_dev, cap);
+  const int r1 = min(cap, (ntok + 63) / 64 * 64);
+  const int c8 = cols / 8;                                     // 16-byte groups per row
+  const long long total = (long long)(r1 - ntok) * c8 * nplanes;
+  for (long long i = gt; i < total; i += nthreads) {
+    const int pl = (int)(i / ((long long)(r1 - ntok) * c8));
+    const long long rem = i - (long long)pl * (r1 - ntok) * c8;
+    const int r = ntok + (int)(rem / c8), c = (int)(rem % c8) * 8;
+    *reinterpret_cast<uint4*>(dzp + (size_t)pl * dzp_stride + (size_t)r * cols + c) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 int nnr_lstm_bwd_mma(float* gates, const float* c_stash, const float* w_hh, const int32_t* len, const int32_t* off,
-                     const int32_t* order, int N, const float* dh, const float* dcn, int32_t* tile_counters, cudaStream_t st) {
+                     const int32_t* order, int N, const float* dh, const float* dcn, int32_t* tile_counters, cudaStream_t st,
+                     void* dz_planes, size_t plane_stride, int two_planes, float* db_partial, float* db, int cap) {
   static int cache = 0;
   static bool attr_set = false;
   int ntiles = (N + G::MT - 1) / G::MT;
   NNR_CUDA(cudaMemsetAsync(tile_counters, 0, 2 * sizeof(int32_t), st));
-  void* args[] = {&gates, &c_stash, &w_hh, &len, &off, &order, &N, &ntiles, &dh, &dcn, &tile_counters};
-  return launch_cluster5(lstm_bwd_mma_kernel, G::BWD_SMEM, ntiles, st, args, "lstm_bwd_mma_kernel", &cache, &attr_set);
+  __nv_bfloat16* dzp = (__nv_bfloat16*)dz_planes;
+  void* args[] = {&gates, &c_stash, &w_hh, &len, &off, &order, &N, &ntiles, &dh, &dcn, &tile_counters,
+                  &dzp, &plane_stride, &two_planes, &db_partial};
+  int rc = launch_cluster5(lstm_bwd_mma_kernel, G::BWD_SMEM, ntiles, st, args, "lstm_bwd_mma_kernel", &cache, &attr_set);
+  if (rc || !dz_planes) return rc;
+  const int cols = 8 * G::HID;
+  lstm_dz_finish_kernel<<<(cols + 255) / 256 * 4, 256, 0, st>>>(db_partial, ntiles, cols, db, dzp, plane_stride, two_planes ? 2 : 1, cap, off + N);
+  nnr_count_launch(1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { nnr_set_error("lstm_dz_finish_kernel: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+  return 0;
 }

@@ -94,8 +94,8 @@ def matmul_nn(x, W, M, m_dev=None, out=None, x_planes=None, w_planes=None, **epi
     """out[M,K] = x[M,N] @ W[N,K]   (dgrad of a Linear with weight W, or a fold K^T q)"""
     N, K = W.shape
     if out is None:
-        out = _empty((M, K), x.device)
-    ops.gemm(x, W, out, M, K, N, x.stride(0), W.stride(0), out.stride(0), False, False, m_dev=m_dev,
+        out = _empty((M, K), W.device)
+    ops.gemm(x, W, out, M, K, N, x.stride(0) if x is not None else x_planes.pitch, W.stride(0), out.stride(0), False, False, m_dev=m_dev,
              a_planes=x_planes, b_planes=w_planes if w_planes is not None else weight_planes(W), **epi)
     return out
 
@@ -103,8 +103,10 @@ def matmul_nn(x, W, M, m_dev=None, out=None, x_planes=None, w_planes=None, **epi
 def wgrad(dy, x, M, N, K, k_dev=None, out=None, accumulate=False, dy_planes=None, x_planes=None):
     """out[N,K] = dy[M,N]^T @ x[M,K]   (contraction over the M rows / tokens)"""
     if out is None:
-        out = _empty((N, K), dy.device)
-    ops.gemm(dy, x, out, N, K, M, dy.stride(0), x.stride(0) if x is not None else K, out.stride(0), True, False, k_dev=k_dev,
+        out = _empty((N, K), dy.device if dy is not None else dy_planes.buf.device)
+    # an operand may exist only as planes (None here): its leading dimension is then only checked against the shape
+    ops.gemm(dy, x, out, N, K, M, dy.stride(0) if dy is not None else dy_planes.pitch, x.stride(0) if x is not None else K,
+             out.stride(0), True, False, k_dev=k_dev,
              accumulate=accumulate, a_planes=dy_planes, b_planes=x_planes)
     return out
 
@@ -406,14 +408,21 @@ class CNEFunction(torch.autograd.Function):
         first = True
         for x, m in mods.items():
             pre = x + '_lstm.'
-            ops.lstm_bwd(m.gates, m.c_stash, m.w_hh, m.len, m.off, m.order, N, m.L, Hd, m.dh, dcn[x].contiguous())
-            dz = m.gates                                                                      # [cap, 8H] = dL/dgx
+            db = _empty((8 * Hd,), dev)
+            if m.emb is None and ops.lstm_bwd_planes_supported(Hd):
+                # dL/dgx only feeds GEMMs and the bias gradient: the recurrence writes its operand planes and column sums
+                dz = None
+                dz_pl = ops.lstm_bwd_planes(m.gates, m.c_stash, m.w_hh, m.len, m.off, m.order, N, m.L, Hd, m.dh,
+                                            dcn[x].contiguous(), m.cap, db)
+            else:
+                ops.lstm_bwd(m.gates, m.c_stash, m.w_hh, m.len, m.off, m.order, N, m.L, Hd, m.dh, dcn[x].contiguous())
+                dz = m.gates                                                                  # [cap, 8H] = dL/dgx
+                dz_pl = split_tokens(dz, m.cap, 8 * Hd, m.ntok, colsum_out=db)
             hprev = _empty((m.cap, D2), dev)
             ops.lstm_shift_h(m.h, m.len, m.off, m.tok_row, N, m.L, Hd, hprev)
-            db = _empty((8 * Hd,), dev)
-            dz_pl = split_tokens(dz, m.cap, 8 * Hd, m.ntok, colsum_out=db)
             for d, sfx in enumerate(('', '_reverse')):
-                G[pre + 'weight_hh_l0' + sfx] = wgrad(dz[:, d * 4 * Hd:(d + 1) * 4 * Hd], hprev[:, d * Hd:(d + 1) * Hd],
+                G[pre + 'weight_hh_l0' + sfx] = wgrad(dz[:, d * 4 * Hd:(d + 1) * 4 * Hd] if dz is not None else None,
+                                                     hprev[:, d * Hd:(d + 1) * Hd],
                                                      m.cap, 4 * Hd, Hd, k_dev=m.ntok,
                                                      dy_planes=dz_pl.cols(d * 4 * Hd, (d + 1) * 4 * Hd) if dz_pl else None)
             dwih = wgrad(dz, m.emb, m.cap, 8 * Hd, E, k_dev=m.ntok, dy_planes=dz_pl, x_planes=m.emb_pl)

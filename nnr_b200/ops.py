@@ -228,6 +228,24 @@ def lstm_bwd(gates, c_stash, w_hh, len_, off, order, N, L, H, dh, dcn):
                            _stream()), 'nnr_lstm_bwd')
 
 
+def lstm_bwd_planes_supported(H):
+    return bool(lib.nnr_lstm_bwd_planes_supported(H, default_algo()))
+
+
+def lstm_bwd_planes(gates, c_stash, w_hh, len_, off, order, N, L, H, dh, dcn, cap, db):
+    """BPTT whose dL/dgx leaves as GEMM operand planes (returned) and whose column sums land in db [8H]"""
+    algo = default_algo()
+    nbytes = int(lib.nnr_tc_split_bytes(cap, 8 * H, algo))
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=gates.device)
+    wsb = int(lib.nnr_lstm_bwd_planes_workspace_bytes(N, H))
+    ws = workspace(wsb, gates.device, 'lstm_db')
+    check(lib.nnr_lstm_bwd_planes(_p(gates, _F32), _p(c_stash, _F32), _p(w_hh, _F32), _p(len_, _I32), _p(off, _I32),
+                                  _p(order, _I32), N, L, H, _p(dh, _F32), _p(dcn, _F32),
+                                  _tile_counters(gates.device).data_ptr(), cap, algo, buf.data_ptr(), nbytes, _p(db, _F32),
+                                  ws.data_ptr(), ws.numel(), _stream()), 'nnr_lstm_bwd_planes')
+    return Planes(buf, cap, 8 * H, int(lib.nnr_tc_split_pitch(8 * H, algo)), 2)
+
+
 def lstm_shift_h(h, len_, off, tok_row, N, L, H, hprev):
     check(lib.nnr_lstm_shift_h(_p(h, _F32), _p(len_, _I32), _p(off, _I32), _p(tok_row, _I32), N, L, H,
                                _p(hprev, _F32), _stream()), 'nnr_lstm_shift_h')

@@ -310,9 +310,28 @@ def test_lstm_forward_backward(cuda, N, L, full):
     # backward
     dh_p = torch.zeros(N * L, 2 * Hd, device=cuda)
     dh_p[:ntok] = _packed(dh, lens).to(cuda)
+    planes_variant = ops.lstm_bwd_planes_supported(Hd)
+    if planes_variant:                                                # leaves the stash untouched: run it first
+        cap = N * L
+        db1, db2 = torch.empty(8 * Hd, device=cuda), torch.empty(8 * Hd, device=cuda)
+        pl = ops.lstm_bwd_planes(gx_full, cst, w_hh, len_, off, order, N, L, Hd, dh_p, dcn.to(cuda).contiguous(), cap, db1)
+        pl2 = ops.lstm_bwd_planes(gx_full, cst, w_hh, len_, off, order, N, L, Hd, dh_p, dcn.to(cuda).contiguous(), cap, db2)
     ops.lstm_bwd(gx_full, cst, w_hh, len_, off, order, N, L, Hd, dh_p, dcn.to(cuda).contiguous())
     torch.cuda.synchronize()
     dgx = gx_full[:ntok].cpu().double()                               # dL/dgx, packed
+    if planes_variant:
+        # operand planes == nnr_tc_split of the fp32 result, bit for bit (zeroed row tail included); the bias gradient
+        # is a fixed-order sum (identical run to run)
+        ref = ops.tc_split(gx_full, cap, 8 * Hd, 8 * Hd, off[N:])
+        rows = min(cap, (ntok + 63) // 64 * 64)
+        nplanes = ref.buf.numel() // (cap * ref.pitch * ref.esz)
+        a = ref.buf.view(nplanes, cap, ref.pitch * ref.esz)[:, :rows]
+        b = pl.buf.view(nplanes, cap, pl.pitch * pl.esz)[:, :rows]
+        assert (pl.pitch, pl.esz, pl.buf.numel()) == (ref.pitch, ref.esz, ref.buf.numel())
+        assert torch.equal(a, b)
+        assert torch.equal(db1, db2) and torch.equal(pl.buf.view(nplanes, cap, -1)[:, :rows], pl2.buf.view(nplanes, cap, -1)[:, :rows])
+        s_ref = dgx.sum(0)
+        assert (db1.cpu().double() - s_ref).abs().max().item() / s_ref.abs().max().item() < 2e-6
     # reference dL/dgx via the chain rule on x: dgx @ w_ih == dx  and dgx^T x == dW_ih
     dW_ref = torch.cat([w64['weight_ih_l0'].grad, w64['weight_ih_l0_reverse'].grad], 0)
     dW = dgx.t() @ xp.double()
