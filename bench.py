@@ -220,19 +220,35 @@ def main():
     for i in range(2):                                        # untimed warm-up of this path (allocator, copy engine)
         ts.step(*batch_args(host[i % nb], dev)).item()
     barrier()
-    e0.record()
-    args = batch_args(host[0], dev)                           # inside the timed region: every step's batch is copied H2D
-    for i in range(a.steps):
-        loss = ts.step(*args)
-        if i + 1 < a.steps:                                   # input prefetch, like a pinned-memory DataLoader: the next
-            args = batch_args(host[(i + 1) % nb], dev)        # batch's copies are enqueued before the host blocks on the loss
-        loss_host = loss.item()
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e = a.batch * world * a.steps / (t.item() / 1e3)
+    from nnr_b200.trainer import LossLog
+
+    def run_e2e(blocking):
+        """K steps from pinned host batches; every step's loss is read back to the host inside the timed region:
+        blocking = float(loss) before the next step is enqueued (reference trainer.py:115); otherwise through
+        trainer.LossLog (pinned slot + event, consumed while the next step runs; all K values read before the end)"""
+        log = LossLog()
+        vals = []
+        e0.record()
+        args = batch_args(host[0], dev)                       # inside the timed region: every step's batch is copied H2D
+        for i in range(a.steps):
+            loss = ts.step(*args)
+            if not blocking:
+                vals += log.push(loss, weight=a.batch)
+            if i + 1 < a.steps:                               # input prefetch, like a pinned-memory DataLoader: the next
+                args = batch_args(host[(i + 1) % nb], dev)    # batch's copies are enqueued before the host waits for a loss
+            if blocking:
+                vals.append(loss.item())
+        vals += log.drain()
+        e1.record()
+        barrier()
+        assert len(vals) == a.steps
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return a.batch * world * a.steps / (t.item() / 1e3), vals[-1]
+
+    e2e_blocking, _ = run_e2e(True)
+    e2e, loss_host = run_e2e(False)
 
     # ---- end to end, index-only batches (SURVEY 8f-1): the tokenised corpus lives in HBM; per step only the
     # history / candidate ids cross PCIe, the 21 model inputs are gathered and the graph is built on the device ------
@@ -244,9 +260,13 @@ def main():
         ts.step_ids(corpus, *ids_host[i % nb])
     barrier()
     e0.record()
+    log = LossLog()
+    n_read = 0
     for i in range(a.steps):
         loss = ts.step_ids(corpus, *ids_host[i % nb])
-        loss_host = loss.item()
+        n_read += len(log.push(loss, weight=a.batch))
+    n_read += len(log.drain())
+    assert n_read == a.steps
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -296,7 +316,10 @@ def main():
                        'l2_policy': 'per-step working set (activations+stashes, GBs) >> 126 MB L2; %d rotating batches' % nb,
                        'loss': loss_host},
             'clocks': clk.summary(),
-            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
+            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                    'loss_read': 'every step, pinned non-blocking D2H + event (trainer.LossLog), consumed while the next step '
+                                 'runs; all K losses are on the host before the timed region ends',
+                    'value_blocking_loss_read': e2e_blocking},
             'e2e_index_only': {'value': e2e_ids, 'unit': UNIT, 'h2d_bytes_per_step': ids_bytes, 'd2h_bytes_per_step': 4,
                                'corpus_bytes_resident': corpus.nbytes(),
                                'note': 'nnr_b200.corpus.DeviceCorpus + TrainStep.step_ids: ids in, batch gathered and graph built on the device'},

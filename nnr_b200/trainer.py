@@ -101,6 +101,62 @@ class TrainStep:
         self._refresh_weight_planes()   # the kernel updates the parameters through raw pointers: re-split them (one launch)
 
 
+class LossLog:
+    """Per-step loss read-back without stalling the launch queue.
+
+    The reference adds ``float(loss) * batch`` to the epoch loss every step (trainer.py:115,295), which blocks the host
+    until the step has finished before the next one is enqueued.  Here every step's loss is copied into a pinned host
+    slot with a non-blocking D2H copy + an event; ``push`` returns the values whose copies have completed (normally the
+    previous step's), ``drain`` waits for the rest.  Every step is still read exactly once and the epoch sum is the
+    same -- the host just consumes step i while the device runs step i+1."""
+
+    def __init__(self, slots=8):
+        self.buf = torch.empty(slots, dtype=torch.float32).pin_memory()
+        self.pending = []          # (slot, event, weight) in issue order
+        self.slots = slots
+        self.next = 0
+        self.total = 0.0           # sum of weight * loss over the consumed steps (the reference's epoch_loss)
+        self.count = 0
+
+    def _consume(self, block):
+        out = []
+        while self.pending and (block or self.pending[0][1].query()):
+            slot, ev, wt = self.pending.pop(0)
+            ev.synchronize()
+            v = float(self.buf[slot])
+            self.total += v * wt
+            self.count += 1
+            out.append(v)
+        return out
+
+    def push(self, loss, weight=1.0, lag=1):
+        """enqueue the read of this step's (device) loss; returns the losses that are complete, waiting only if more than
+        ``lag`` reads are outstanding"""
+        if len(self.pending) >= self.slots:
+            self._consume_one()
+        slot = self.next
+        self.next = (self.next + 1) % self.slots
+        self.buf[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.pending.append((slot, ev, weight))
+        out = []
+        while len(self.pending) > lag:
+            out += self._consume_one()
+        return out + self._consume(False)
+
+    def _consume_one(self):
+        slot, ev, wt = self.pending.pop(0)
+        ev.synchronize()
+        v = float(self.buf[slot])
+        self.total += v * wt
+        self.count += 1
+        return [v]
+
+    def drain(self):
+        return self._consume(True)
+
+
 def shard_batch(batch, rank, world_size):
     """Reference DDP sharding (trainer.py:218,256-258): rank r takes impressions [r*B/W, (r+1)*B/W) of a global
     batch whose size is divisible by the world size (config.py:116).  Works on dicts or sequences of tensors;

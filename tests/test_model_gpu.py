@@ -320,3 +320,20 @@ def test_device_negative_sampling_semantics(cuda):
     for _ in range(50):
         seen.update(corpus.sample_negatives(pool, plen, 4, generator=g)[3].tolist())
     assert seen == set(range(31, 41))                    # every pool entry is reachable
+
+
+def test_loss_log_reads_every_step_in_order(cuda):
+    """trainer.LossLog: non-blocking per-step loss read-back; every value arrives exactly once, in order, and the weighted
+    sum equals the reference's blocking epoch_loss accumulation (trainer.py:115)"""
+    from nnr_b200.trainer import LossLog
+    log = LossLog(slots=4)
+    got = []
+    want = []
+    for i in range(11):
+        v = torch.full((), float(i) * 0.5 + 0.25, device=cuda)
+        want.append(float(i) * 0.5 + 0.25)
+        got += log.push(v * 1.0, weight=3.0)
+        assert len(log.pending) <= 1
+    got += log.drain()
+    assert got == want and log.count == 11
+    assert abs(log.total - 3.0 * sum(want)) < 1e-4
