@@ -181,6 +181,11 @@ int nnr_lstm_bwd_planes(const float* gates, const float* c_stash, const float* w
  * recurrent input of every step, needed for dW_hh = dgates^T hprev.                             */
 int nnr_lstm_shift_h(const float* h, const int32_t* len, const int32_t* off,
                      const int32_t* tok_row, int N, int L, int H, float* hprev, void* stream);
+/* the same shifted states written directly as operand planes ([cap, 2H] layout of nnr_tc_split, zeroed row tail):
+ * bit-identical to nnr_lstm_shift_h followed by nnr_tc_split; hprev is only the B operand of dW_hh = dgates^T hprev. */
+int nnr_lstm_shift_h_planes(const float* h, const int32_t* len, const int32_t* off,
+                            const int32_t* tok_row, int N, int L, int H, int cap, int algo, void* planes,
+                            size_t planes_bytes, void* stream);
 /* dz = dhg*h*g*(1-g), dh0 = dhg*g : elementwise part of the selective-gate backward
  * (newsEncoders.py:128-131)                                                                     */
 int nnr_gate_bwd_pre(const float* dhg, const float* h, const float* g, int64_t n_max,

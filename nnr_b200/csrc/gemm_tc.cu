@@ -1107,6 +1107,49 @@ extern "C" int nnr_embed_gather_planes_fwd(const float* table, const int32_t* id
 }
 
 // ------------------------------------------------------------------------------------------------
+// The recurrent input of every LSTM step (h_{t-1} forward, h_{t+1} reverse; zero at the sequence ends) as operand
+// planes: nnr_lstm_shift_h + nnr_tc_split in one pass.  It is only ever the B operand of dW_hh = dz^T hprev.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) lstm_shift_h_planes_kernel(const float* __restrict__ h, const int32_t* __restrict__ len,
+                                                                  const int32_t* __restrict__ off, const int32_t* __restrict__ tok_row,
+                                                                  int N, int H, int cap, int Cp, void* __restrict__ out, size_t plane_stride) {
+  const int ntok = min(off[N], cap);
+  const int rows = min(cap, (ntok + 63) / 64 * 64);
+  const int H2 = 2 * H, hq = H >> 2, ncq = Cp >> 2, q_valid = H2 >> 2;
+  const long long total = (long long)rows * ncq;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i / ncq), q = (int)(i - (long long)p * ncq);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p < ntok && q < q_valid) {
+      const int r = tok_row[p];
+      const int t = p - off[r];
+      if (q < hq) { if (t > 0) v = __ldg(reinterpret_cast<const float4*>(h + (size_t)(p - 1) * H2) + q); }
+      else { if (t < len[r] - 1) v = __ldg(reinterpret_cast<const float4*>(h + (size_t)(p + 1) * H2) + q); }
+    }
+    tc_split_store4<MODE>(out, plane_stride, Cp, p, q * 4, v);
+  }
+}
+
+extern "C" int nnr_lstm_shift_h_planes(const float* h, const int32_t* len, const int32_t* off, const int32_t* tok_row, int N,
+                                       int L, int H, int cap, int algo, void* planes, size_t planes_bytes, void* stream) {
+  NNR_REQUIRE(h && len && off && tok_row && planes && N > 0 && L > 0 && H > 0 && cap > 0, NNR_ERR_ARG, "nnr_lstm_shift_h_planes: bad arguments");
+  NNR_REQUIRE(H % 4 == 0 && nnr_aligned16(h) && nnr_aligned16(planes), NNR_ERR_ALIGN, "nnr_lstm_shift_h_planes: H %% 4 == 0, 16B alignment");
+  NNR_REQUIRE(algo == NNR_GEMM_TC_TF32X3 || algo == NNR_GEMM_TC_BF16 || algo == NNR_GEMM_TC_BF16X3, NNR_ERR_UNSUPPORTED,
+              "nnr_lstm_shift_h_planes: planes exist only for the tensor-core GEMM algorithms");
+  NNR_REQUIRE(planes_bytes >= nnr_tc_split_bytes(cap, 2 * H, algo), NNR_ERR_WORKSPACE, "nnr_lstm_shift_h_planes: planes buffer too small");
+  const int mode = algo_mode(algo);
+  const int Cp = (int)nnr_tc_split_pitch(2 * H, algo);
+  const size_t ps = (size_t)cap * Cp;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 1) lstm_shift_h_planes_kernel<1><<<148 * 8, 256, 0, st>>>(h, len, off, tok_row, N, H, cap, Cp, planes, ps);
+  else if (mode == 2) lstm_shift_h_planes_kernel<2><<<148 * 8, 256, 0, st>>>(h, len, off, tok_row, N, H, cap, Cp, planes, ps);
+  else lstm_shift_h_planes_kernel<0><<<148 * 8, 256, 0, st>>>(h, len, off, tok_row, N, H, cap, Cp, planes, ps);
+  NNR_LAUNCH_CHECK("lstm_shift_h_planes_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Operand planes of MANY small matrices in one launch (all weight matrices after an optimizer step: ~50 launches of
 // 3-5 us each otherwise).  descs is a DEVICE array; eight CTAs per matrix.
 // ------------------------------------------------------------------------------------------------

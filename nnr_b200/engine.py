@@ -418,13 +418,19 @@ class CNEFunction(torch.autograd.Function):
                 ops.lstm_bwd(m.gates, m.c_stash, m.w_hh, m.len, m.off, m.order, N, m.L, Hd, m.dh, dcn[x].contiguous())
                 dz = m.gates                                                                  # [cap, 8H] = dL/dgx
                 dz_pl = split_tokens(dz, m.cap, 8 * Hd, m.ntok, colsum_out=db)
-            hprev = _empty((m.cap, D2), dev)
-            ops.lstm_shift_h(m.h, m.len, m.off, m.tok_row, N, m.L, Hd, hprev)
+            if dz_pl is not None:                 # hprev is only a GEMM operand: straight to planes
+                hprev = None
+                hprev_pl = ops.lstm_shift_h_planes(m.h, m.len, m.off, m.tok_row, N, m.L, Hd, m.cap)
+            else:
+                hprev_pl = None
+                hprev = _empty((m.cap, D2), dev)
+                ops.lstm_shift_h(m.h, m.len, m.off, m.tok_row, N, m.L, Hd, hprev)
             for d, sfx in enumerate(('', '_reverse')):
                 G[pre + 'weight_hh_l0' + sfx] = wgrad(dz[:, d * 4 * Hd:(d + 1) * 4 * Hd] if dz is not None else None,
-                                                     hprev[:, d * Hd:(d + 1) * Hd],
+                                                     hprev[:, d * Hd:(d + 1) * Hd] if hprev is not None else None,
                                                      m.cap, 4 * Hd, Hd, k_dev=m.ntok,
-                                                     dy_planes=dz_pl.cols(d * 4 * Hd, (d + 1) * 4 * Hd) if dz_pl else None)
+                                                     dy_planes=dz_pl.cols(d * 4 * Hd, (d + 1) * 4 * Hd) if dz_pl else None,
+                                                     x_planes=hprev_pl.cols(d * Hd, (d + 1) * Hd) if hprev_pl else None)
             dwih = wgrad(dz, m.emb, m.cap, 8 * Hd, E, k_dev=m.ntok, dy_planes=dz_pl, x_planes=m.emb_pl)
             m.emb_pl = None
             for d, sfx in enumerate(('', '_reverse')):
@@ -435,7 +441,7 @@ class CNEFunction(torch.autograd.Function):
             del dz_pl
             ops.embed_gather_bwd(demb, m.ids, m.len, m.off, dtable, m.p, m.seed, not first)
             first = False
-            del hprev, demb
+            del hprev, hprev_pl, demb
         G['word_embedding.weight'] = dtable
         ctx.t = ctx.c = None
         return (None,) * 7 + _param_grads(P, ctx.names, G)

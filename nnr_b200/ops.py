@@ -251,6 +251,16 @@ def lstm_shift_h(h, len_, off, tok_row, N, L, H, hprev):
                                _p(hprev, _F32), _stream()), 'nnr_lstm_shift_h')
 
 
+def lstm_shift_h_planes(h, len_, off, tok_row, N, L, H, cap):
+    """hprev (nnr_lstm_shift_h) emitted as GEMM operand planes; tensor-core algos only"""
+    algo = default_algo()
+    nbytes = int(lib.nnr_tc_split_bytes(cap, 2 * H, algo))
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
+    check(lib.nnr_lstm_shift_h_planes(_p(h, _F32), _p(len_, _I32), _p(off, _I32), _p(tok_row, _I32), N, L, H, cap, algo,
+                                      buf.data_ptr(), nbytes, _stream()), 'nnr_lstm_shift_h_planes')
+    return Planes(buf, cap, 2 * H, int(lib.nnr_tc_split_pitch(2 * H, algo)), 2 if algo in (ALGO_BF16, ALGO_BF16X3) else 4)
+
+
 def gate_bwd_pre(dhg, h, g, n_max, n_dev, D, dz, dh0):
     check(lib.nnr_gate_bwd_pre(_p(dhg, _F32), _p(h, _F32), _p(g, _F32), n_max, _p(n_dev, _I32), D, _p(dz, _F32),
                                _p(dh0, _F32), _stream()), 'nnr_gate_bwd_pre')

@@ -346,6 +346,14 @@ def test_lstm_forward_backward(cuda, N, L, full):
     hprev = torch.empty(N * L, 2 * Hd, device=cuda)
     ops.lstm_shift_h(h, len_, off, tok_row, N, L, Hd, hprev)
     hp = hprev[:ntok].cpu().double()
+    if ops.default_algo() != 1:
+        # the planes variant == shift + split, bit for bit (rows beyond the tokens are zero)
+        hprev[ntok:] = 0
+        ref_pl = ops.tc_split(hprev, N * L, 2 * Hd, 2 * Hd, off[N:])
+        got_pl = ops.lstm_shift_h_planes(h, len_, off, tok_row, N, L, Hd, N * L)
+        rows_pl = min(N * L, (ntok + 63) // 64 * 64)
+        npl = ref_pl.buf.numel() // (N * L * ref_pl.pitch * ref_pl.esz)
+        assert torch.equal(ref_pl.buf.view(npl, N * L, -1)[:, :rows_pl], got_pl.buf.view(npl, N * L, -1)[:, :rows_pl])
     for d, sfx in enumerate(('', '_reverse')):
         dWhh = dgx[:, d * 4 * Hd:(d + 1) * 4 * Hd].t() @ hp[:, d * Hd:(d + 1) * Hd]
         ref = w64['weight_hh_l0' + sfx].grad
