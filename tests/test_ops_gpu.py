@@ -478,6 +478,22 @@ def test_graph_build_bit_exact_and_aggregate(cuda):
         ops.gcn_aggregate(nnz, col, val, x, B, G_, D, out)
         ref = torch.bmm(gm.double(), x.double())
         assert (out.view(B, G_, D).double() - ref).abs().max() < 1e-5
+        # other feature widths, and a larger graph
+        for D2_ in (20, 333):
+            x2 = torch.randn(B, G_, D2_, device=cuda)
+            out2 = torch.empty(B * G_, D2_, device=cuda)
+            ops.gcn_aggregate(nnz, col, val, x2, B, G_, D2_, out2)
+            assert (out2.view(B, G_, D2_).double() - torch.bmm(gm.double(), x2.double())).abs().max() < 1e-5
+    Gb = 600
+    gb = (torch.rand(2, Gb, Gb, device=cuda) < 0.05).float() * torch.rand(2, Gb, Gb, device=cuda)
+    nnz = torch.empty(2 * Gb, dtype=torch.int32, device=cuda)
+    col = torch.empty(2 * Gb, Gb, dtype=torch.int32, device=cuda)
+    val = torch.empty(2 * Gb, Gb, device=cuda)
+    ops.graph_to_csr(gb, False, nnz, col, val)
+    xb = torch.randn(2, Gb, 40, device=cuda)
+    ob = torch.empty(2 * Gb, 40, device=cuda)
+    ops.gcn_aggregate(nnz, col, val, xb, 2, Gb, 40, ob)
+    assert (ob.view(2, Gb, 40).double() - torch.bmm(gb.double(), xb.double())).abs().max() < 1e-5
 
 
 def test_cluster_intra_attention(cuda):
