@@ -1151,18 +1151,19 @@ extern "C" int nnr_lstm_shift_h_planes(const float* h, const int32_t* len, const
 
 // ------------------------------------------------------------------------------------------------
 // Operand planes of MANY small matrices in one launch (all weight matrices after an optimizer step: ~50 launches of
-// 3-5 us each otherwise).  descs is a DEVICE array; eight CTAs per matrix.
+// 3-5 us each otherwise).  descs is a DEVICE array; up to TSM_PARTS CTAs per matrix (grid.y = matrix).
 // ------------------------------------------------------------------------------------------------
+#define TSM_PARTS 64
 template <int MODE>
 __global__ void __launch_bounds__(256) tc_split_many_kernel(const nnr_split_desc* __restrict__ descs, int n) {
-  const int di = blockIdx.x >> 3, part = blockIdx.x & 7;
+  const int di = blockIdx.y, part = blockIdx.x;
   if (di >= n) return;
   const nnr_split_desc d = descs[di];
   const int Cp = (int)d.pitch;
   const int cq_per_row = Cp >> 2;
   const long long total = (long long)d.rows * cq_per_row;
   const bool vec = ((((uintptr_t)d.src) & 15) == 0) && (d.ld % 4 == 0);
-  for (long long i = (long long)part * 256 + threadIdx.x; i < total; i += 8 * 256) {
+  for (long long i = (long long)part * 256 + threadIdx.x; i < total; i += TSM_PARTS * 256) {
     const int r = (int)(i / cq_per_row), cq = (int)(i - (long long)r * cq_per_row) * 4;
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
     const float* sp = d.src + (size_t)r * d.ld + cq;
@@ -1177,13 +1178,13 @@ __global__ void __launch_bounds__(256) tc_split_many_kernel(const nnr_split_desc
   }
 }
 extern "C" int nnr_tc_split_many(const nnr_split_desc* descs, int n, int algo, void* stream) {
-  NNR_REQUIRE(descs && n > 0, NNR_ERR_ARG, "nnr_tc_split_many: bad arguments");
+  NNR_REQUIRE(descs && n > 0 && n <= 65535, NNR_ERR_ARG, "nnr_tc_split_many: bad arguments");
   const int mode = algo_mode(algo);
   cudaStream_t st = (cudaStream_t)stream;
   void* ph = nnr_prof_begin(1, 0.0, st);
-  if (mode == 1) tc_split_many_kernel<1><<<8 * n, 256, 0, st>>>(descs, n);
-  else if (mode == 2) tc_split_many_kernel<2><<<8 * n, 256, 0, st>>>(descs, n);
-  else tc_split_many_kernel<0><<<8 * n, 256, 0, st>>>(descs, n);
+  if (mode == 1) tc_split_many_kernel<1><<<dim3(TSM_PARTS, n), 256, 0, st>>>(descs, n);
+  else if (mode == 2) tc_split_many_kernel<2><<<dim3(TSM_PARTS, n), 256, 0, st>>>(descs, n);
+  else tc_split_many_kernel<0><<<dim3(TSM_PARTS, n), 256, 0, st>>>(descs, n);
   nnr_prof_end(ph, st);
   NNR_LAUNCH_CHECK("tc_split_many_kernel");
   return 0;

@@ -329,29 +329,58 @@ __global__ void sumsq_stage1(const float* __restrict__ g, int64_t n, double* __r
     part[blockIdx.x] = t;
   }
 }
-__global__ void sumsq_stage2(const double* __restrict__ part, int nparts, float grad_scale, float* __restrict__ norm_out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
+// total gradient norm from the per-CTA partials: every CTA adds them in the same fixed order (thread t takes partials
+// t, t + 256, ...; then a shuffle tree and the eight warp sums in order), so all CTAs hold the identical value
+__device__ __forceinline__ float grad_norm_from_partials(const double* __restrict__ part, int nparts, float grad_scale) {
+  __shared__ double sh[8];
+  __shared__ float s_norm;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += 256) acc += part[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int i = 0; i < nparts; ++i) t += part[i];
-    norm_out[0] = (float)(sqrt(t) * (double)grad_scale);
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    s_norm = (float)(sqrt(t) * (double)grad_scale);
   }
+  __syncthreads();
+  return s_norm;
 }
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            int64_t n, float lr, float b1, float b2, float eps, float max_norm, float grad_scale,
-                            float bc1, float bc2_sqrt, const float* __restrict__ norm) {
-  float total = norm[0];
+template <bool VEC>
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                                   float max_norm, float grad_scale, float bc1, float bc2_sqrt,
+                                                   const double* __restrict__ part, int nparts, float* __restrict__ norm_out) {
+  const float total = grad_norm_from_partials(part, nparts, grad_scale);
+  if (blockIdx.x == 0 && threadIdx.x == 0) norm_out[0] = total;
   float coef = 1.0f;
   if (max_norm > 0.f) coef = fminf(max_norm / (total + 1e-6f), 1.0f);   // torch clip_grad_norm_
   coef *= grad_scale;
-  float step_size = lr / bc1;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    float gi = g[i] * coef;
-    float mi = m[i] * b1 + (1.f - b1) * gi;          // exp_avg.lerp_(grad, 1-beta1)
-    float vi = v[i] * b2 + (1.f - b2) * gi * gi;
-    m[i] = mi; v[i] = vi;
-    float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p[i] - step_size * (mi / denom);
+  const float step_size = lr / bc1;
+  auto upd = [&](float gi, float& pi, float& mi, float& vi) {
+    gi *= coef;
+    mi = mi * b1 + (1.f - b1) * gi;                  // exp_avg.lerp_(grad, 1-beta1)
+    vi = vi * b2 + (1.f - b2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi = pi - step_size * (mi / denom);
+  };
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (VEC) {                                         // n % 4 == 0, 16-byte aligned buffers
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+      float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+      upd(g4.x, p4.x, m4.x, v4.x); upd(g4.y, p4.y, m4.y, v4.y); upd(g4.z, p4.z, m4.z, v4.z); upd(g4.w, p4.w, m4.w, v4.w);
+      reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4; reinterpret_cast<float4*>(p)[i] = p4;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      float pi = p[i], mi = m[i], vi = v[i];
+      upd(g[i], pi, mi, vi);
+      m[i] = mi; v[i] = vi; p[i] = pi;
+    }
   }
 }
 extern "C" size_t nnr_flat_clip_adam_workspace_bytes(int64_t n) { (void)n; return CA_BLOCKS * sizeof(double); }
@@ -365,14 +394,14 @@ extern "C" int nnr_flat_clip_adam(float* param, const float* grad, float* exp_av
   cudaStream_t st = (cudaStream_t)stream;
   sumsq_stage1<<<CA_BLOCKS, 256, 0, st>>>(grad, n, (double*)workspace);
   NNR_LAUNCH_CHECK("sumsq_stage1");
-  sumsq_stage2<<<1, 32, 0, st>>>((const double*)workspace, CA_BLOCKS, grad_scale, norm_out);
-  NNR_LAUNCH_CHECK("sumsq_stage2");
-  float bc1 = 1.0f - powf(beta1, (float)step);
-  float bc2 = 1.0f - powf(beta2, (float)step);
   double bc1d = 1.0 - pow((double)beta1, (double)step), bc2d = 1.0 - pow((double)beta2, (double)step);
-  (void)bc1; (void)bc2;
-  adam_kernel<<<CA_BLOCKS, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, max_norm, grad_scale,
-                                         (float)bc1d, (float)sqrt(bc2d), norm_out);
+  const bool vec = (n % 4 == 0) && nnr_aligned16(param) && nnr_aligned16(exp_avg) && nnr_aligned16(exp_avg_sq);
+  if (vec)
+    adam_kernel<true><<<CA_BLOCKS, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, max_norm, grad_scale,
+                                                 (float)bc1d, (float)sqrt(bc2d), (const double*)workspace, CA_BLOCKS, norm_out);
+  else
+    adam_kernel<false><<<CA_BLOCKS, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, max_norm, grad_scale,
+                                                  (float)bc1d, (float)sqrt(bc2d), (const double*)workspace, CA_BLOCKS, norm_out);
   NNR_LAUNCH_CHECK("adam_kernel");
   return 0;
 }

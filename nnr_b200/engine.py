@@ -43,11 +43,16 @@ def _param_grads(P, names, G):
     preallocated buffer managed by trainer.TrainStep (flat gradient buffer, marked ``_nnr_flat_grad``), the gradients
     are added into those buffers with ONE multi-tensor add and ``None`` is returned to autograd, instead of ~70
     per-parameter AccumulateGrad add kernels per step."""
-    params = [P[k] for k in names]
-    if all(getattr(q, '_nnr_flat_grad', False) and q.grad is not None for q in params):
-        torch._foreach_add_([q.grad for q in params], [G[k] for k in names])
+    if _flat_grads(P, names):
+        live = [k for k in names if G[k] is not None]        # None: already accumulated in place (embedding table)
+        torch._foreach_add_([P[k].grad for k in live], [G[k] for k in live])
         return (None,) * len(names)
     return tuple(G[k] for k in names)
+
+
+def _flat_grads(P, names):
+    """every parameter's .grad is a view of trainer.TrainStep's flat gradient buffer"""
+    return all(getattr(P[k], '_nnr_flat_grad', False) and P[k].grad is not None for k in names)
 
 
 def weights_changed():
@@ -404,8 +409,12 @@ class CNEFunction(torch.autograd.Function):
         else:
             dcn = {x: torch.zeros(N, D2, device=dev) for x in mods}
         # 5. LSTM backward + input projection + embedding scatter
-        dtable = _empty(P['word_embedding.weight'].shape, dev)
-        first = True
+        # with a flat gradient buffer (trainer.TrainStep) the scatter adds straight into the table's .grad view: no [V, E]
+        # temporary, no memset of it, no [V, E] add afterwards
+        wemb = P['word_embedding.weight']
+        in_place = _flat_grads(P, ctx.names) and wemb.grad.is_contiguous() and wemb.grad.data_ptr() % 16 == 0
+        dtable = wemb.grad if in_place else _empty(wemb.shape, dev)
+        first = not in_place
         for x, m in mods.items():
             pre = x + '_lstm.'
             db = _empty((8 * Hd,), dev)
@@ -442,7 +451,7 @@ class CNEFunction(torch.autograd.Function):
             ops.embed_gather_bwd(demb, m.ids, m.len, m.off, dtable, m.p, m.seed, not first)
             first = False
             del hprev, hprev_pl, demb
-        G['word_embedding.weight'] = dtable
+        G['word_embedding.weight'] = None if in_place else dtable
         ctx.t = ctx.c = None
         return (None,) * 7 + _param_grads(P, ctx.names, G)
 
