@@ -190,6 +190,12 @@ int nnr_lstm_shift_h_planes(const float* h, const int32_t* len, const int32_t* o
  * (newsEncoders.py:128-131)                                                                     */
 int nnr_gate_bwd_pre(const float* dhg, const float* h, const float* g, int64_t n_max,
                      const int32_t* n_dev, int D, float* dz, float* dh0, void* stream);
+/* nnr_gate_bwd_pre + nnr_tc_split(dz) + nnr_segment_colsum(dz) in one pass: dz leaves as operand planes ([cap, D] layout
+ * of nnr_tc_split, zeroed row tail), dmproj[r, :] = sum of dz over the tokens of news r (token order), dh0 stays fp32.
+ * Bit-identical to the three separate calls.                                                                      */
+int nnr_gate_bwd_planes(const float* dhg, const float* h, const float* g, const int32_t* off, int N, int D,
+                        int cap, int algo, void* dz_planes, size_t planes_bytes, float* dh0, float* dmproj,
+                        int64_t lddm, void* stream);
 
 /* ---- fused masked attention pooling over segments: layers.py:167-175 and :196-203 -----------
  * Segment s covers rows [seg_off[s], seg_off[s+1]) of X (or s*fixed_len.. when seg_off == NULL).

@@ -90,6 +90,7 @@ SIGNATURES = {
                                       vp, sz, vp]),
     'nnr_lstm_shift_h_planes': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, vp]),
     'nnr_lstm_shift_h': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
+    'nnr_gate_bwd_planes': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, vp, vp, i64, vp]),
     'nnr_gate_bwd_pre': (C.c_int, [vp, vp, vp, i64, vp, C.c_int, vp, vp, vp]),
     'nnr_attn_pool_fwd': (C.c_int, [C.POINTER(PoolArgs), vp]),
     'nnr_attn_pool_bwd': (C.c_int, [C.POINTER(PoolArgs), vp]),

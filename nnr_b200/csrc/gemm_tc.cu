@@ -1150,6 +1150,87 @@ extern "C" int nnr_lstm_shift_h_planes(const float* h, const int32_t* len, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// Selective-gate backward prologue, fused (nnr_gate_bwd_pre + nnr_tc_split + nnr_segment_colsum in one pass over the
+// tokens): per news r, dz = dhg * h * g * (1 - g) leaves as operand planes (it feeds the dW_H and dh GEMMs), its sum over
+// the news' tokens is dmproj[r] (gradient of the projected partner cell state), dh0 = dhg * g stays fp32.
+// One CTA per news, a thread per 4-column group, tokens in order (the same summation order as segment_colsum_kernel).
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(128) gate_bwd_planes_kernel(const float* __restrict__ dhg, const float* __restrict__ h,
+                                                              const float* __restrict__ g, const int32_t* __restrict__ off, int N,
+                                                              int D, int cap, int Cp, void* __restrict__ planes, size_t plane_stride,
+                                                              float* __restrict__ dh0, float* __restrict__ dmproj, int64_t lddm) {
+  const int r = blockIdx.x;
+  const int ncq = Cp >> 2, dq = D >> 2;
+  if (r >= N) {                                                  // zero row tail [ntok, round_up(ntok, 64)) of the planes
+    const int ntok = min(off[N], cap);
+    const int r1 = min(cap, (ntok + 63) / 64 * 64);
+    for (int i = (r - N) * 128 + threadIdx.x; i < (r1 - ntok) * ncq; i += (gridDim.x - N) * 128)
+      tc_split_store4<MODE>(planes, plane_stride, Cp, ntok + i / ncq, (i % ncq) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    return;
+  }
+  const int a = off[r], b = min(off[r + 1], cap);
+  for (int cq = threadIdx.x; cq < ncq; cq += 128) {
+    if (cq >= dq) {                                              // column pad
+      for (int p = a; p < b; ++p) tc_split_store4<MODE>(planes, plane_stride, Cp, p, cq * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+      continue;
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int p = a;
+    auto one = [&](const float4 x, const float4 hh, const float4 gg, int pp) {
+      float4 z, d0;      // explicit roundings: no contraction with the running sum, same bits as gate_bwd_pre_kernel
+      z.x = __fmul_rn(__fmul_rn(__fmul_rn(x.x, hh.x), gg.x), __fsub_rn(1.f, gg.x)); d0.x = __fmul_rn(x.x, gg.x);
+      z.y = __fmul_rn(__fmul_rn(__fmul_rn(x.y, hh.y), gg.y), __fsub_rn(1.f, gg.y)); d0.y = __fmul_rn(x.y, gg.y);
+      z.z = __fmul_rn(__fmul_rn(__fmul_rn(x.z, hh.z), gg.z), __fsub_rn(1.f, gg.z)); d0.z = __fmul_rn(x.z, gg.z);
+      z.w = __fmul_rn(__fmul_rn(__fmul_rn(x.w, hh.w), gg.w), __fsub_rn(1.f, gg.w)); d0.w = __fmul_rn(x.w, gg.w);
+      *reinterpret_cast<float4*>(dh0 + (size_t)pp * D + cq * 4) = d0;
+      tc_split_store4<MODE>(planes, plane_stride, Cp, pp, cq * 4, z);
+      acc.x = __fadd_rn(acc.x, z.x); acc.y = __fadd_rn(acc.y, z.y); acc.z = __fadd_rn(acc.z, z.z); acc.w = __fadd_rn(acc.w, z.w);
+    };
+    for (; p + 4 <= b; p += 4) {                                 // twelve 16-byte loads in flight
+      float4 x[4], hh[4], gg[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const size_t o = (size_t)(p + u) * D + cq * 4;
+        x[u] = __ldg(reinterpret_cast<const float4*>(dhg + o));
+        hh[u] = __ldg(reinterpret_cast<const float4*>(h + o));
+        gg[u] = __ldg(reinterpret_cast<const float4*>(g + o));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) one(x[u], hh[u], gg[u], p + u);
+    }
+    for (; p < b; ++p) {
+      const size_t o = (size_t)p * D + cq * 4;
+      one(__ldg(reinterpret_cast<const float4*>(dhg + o)), __ldg(reinterpret_cast<const float4*>(h + o)),
+          __ldg(reinterpret_cast<const float4*>(g + o)), p);
+    }
+    *reinterpret_cast<float4*>(dmproj + (size_t)r * lddm + cq * 4) = acc;
+  }
+}
+
+extern "C" int nnr_gate_bwd_planes(const float* dhg, const float* h, const float* g, const int32_t* off, int N, int D, int cap,
+                                   int algo, void* dz_planes, size_t planes_bytes, float* dh0, float* dmproj, int64_t lddm,
+                                   void* stream) {
+  NNR_REQUIRE(dhg && h && g && off && dz_planes && dh0 && dmproj && N > 0 && D > 0 && cap > 0 && lddm >= D, NNR_ERR_ARG,
+              "nnr_gate_bwd_planes: bad arguments");
+  NNR_REQUIRE(D % 4 == 0 && lddm % 4 == 0 && nnr_aligned16(dhg) && nnr_aligned16(h) && nnr_aligned16(g) && nnr_aligned16(dz_planes) &&
+                  nnr_aligned16(dh0) && nnr_aligned16(dmproj), NNR_ERR_ALIGN, "nnr_gate_bwd_planes: needs 16B alignment and D %% 4 == 0");
+  NNR_REQUIRE(algo == NNR_GEMM_TC_TF32X3 || algo == NNR_GEMM_TC_BF16 || algo == NNR_GEMM_TC_BF16X3, NNR_ERR_UNSUPPORTED,
+              "nnr_gate_bwd_planes: planes exist only for the tensor-core GEMM algorithms");
+  NNR_REQUIRE(planes_bytes >= nnr_tc_split_bytes(cap, D, algo), NNR_ERR_WORKSPACE, "nnr_gate_bwd_planes: planes buffer too small");
+  const int mode = algo_mode(algo);
+  const int Cp = (int)nnr_tc_split_pitch(D, algo);
+  const size_t ps = (size_t)cap * Cp;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)N + 8;
+  if (mode == 1) gate_bwd_planes_kernel<1><<<blocks, 128, 0, st>>>(dhg, h, g, off, N, D, cap, Cp, dz_planes, ps, dh0, dmproj, lddm);
+  else if (mode == 2) gate_bwd_planes_kernel<2><<<blocks, 128, 0, st>>>(dhg, h, g, off, N, D, cap, Cp, dz_planes, ps, dh0, dmproj, lddm);
+  else gate_bwd_planes_kernel<0><<<blocks, 128, 0, st>>>(dhg, h, g, off, N, D, cap, Cp, dz_planes, ps, dh0, dmproj, lddm);
+  NNR_LAUNCH_CHECK("gate_bwd_planes_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Operand planes of MANY small matrices in one launch (all weight matrices after an optimizer step: ~50 launches of
 // 3-5 us each otherwise).  descs is a DEVICE array; up to TSM_PARTS CTAs per matrix (grid.y = matrix).
 // ------------------------------------------------------------------------------------------------

@@ -388,16 +388,21 @@ class CNEFunction(torch.autograd.Function):
                 m.dh = m.dhg
                 d_cm_sel[x] = None
                 continue
-            dz = _empty((m.cap, D2), dev)
             dh0 = _empty((m.cap, D2), dev)
-            ops.gate_bwd_pre(m.dhg, m.h, m.g, m.cap * D2, m.ntok, D2, dz, dh0)
-            dz_pl = split_tokens(dz, m.cap, D2, m.ntok)
+            dmproj = _empty((N, D2), dev)
+            if ops.default_algo() != ops.ALGO_SIMT:
+                # dz only feeds the two GEMMs below and the per-news sum: one pass writes its planes, dmproj and dh0
+                dz = None
+                dz_pl = ops.gate_bwd_planes(m.dhg, m.h, m.g, m.off, N, D2, m.cap, dh0, dmproj)
+            else:
+                dz = _empty((m.cap, D2), dev)
+                ops.gate_bwd_pre(m.dhg, m.h, m.g, m.cap * D2, m.ntok, D2, dz, dh0)
+                dz_pl = split_tokens(dz, m.cap, D2, m.ntok)
+                ops.segment_colsum(dz, D2, m.off, N, D2, dmproj, D2)
             m.dh = matmul_nn(dz, P[x + '_H.weight'], m.cap, m.ntok, epilogue=EPI_ADD_AUX, aux=dh0, ldaux=D2, out=m.dhg,
                              x_planes=dz_pl)
             G[x + '_H.weight'] = wgrad(dz, m.h, m.cap, D2, D2, k_dev=m.ntok, dy_planes=dz_pl, x_planes=m.h_pl)
             m.h_pl = None
-            dmproj = _empty((N, D2), dev)
-            ops.segment_colsum(dz, D2, m.off, N, D2, dmproj, D2)
             G[x + '_M.weight'] = wgrad(dmproj, m.cm_sel, N, D2, D2)
             G[x + '_M.bias'] = colsum(dmproj, N, D2)
             d_cm_sel[x] = matmul_nn(dmproj, P[x + '_M.weight'], N)                            # grad of cn_other[partner]
@@ -629,9 +634,10 @@ class SUEFunction(torch.autograd.Function):
             if pe > 0:
                 ops.dropout(df, pe, seeds[L + 1], df)
             dpre = df * (r_f > 0)                                                             # relu mask
-            dpre_pl = ops.tc_split(dpre, B * n * C1, D, D)
+            db_f = _empty((D,), dev)
+            dpre_pl = ops.tc_split(dpre, B * n * C1, D, D, colsum_out=db_f)      # planes + bias gradient in one pass
             G['clusterFeatureAffine.weight'] = wgrad(dpre, intra, B * n * C1, D, D, dy_planes=dpre_pl, x_planes=intra_pl)
-            G['clusterFeatureAffine.bias'] = colsum(dpre, B * n * C1, D)
+            G['clusterFeatureAffine.bias'] = db_f
             dintra = matmul_nn(dpre, P['clusterFeatureAffine.weight'], B * n * C1, epilogue=EPI_ADD_AUX, aux=df, ldaux=D,
                                x_planes=dpre_pl)
             # intra-cluster attention backward
@@ -662,9 +668,10 @@ class SUEFunction(torch.autograd.Function):
                 dx = dx.clone() if dx.data_ptr() == dxL.data_ptr() else dx
                 ops.dropout(dx, pl, seeds[l], dx)
             dpre = dx * (ctx.rs[l] > 0)
-            dpre_pl = ops.tc_split(dpre, B * Gn, D, D)            # one split for the wgrad and the dgrad GEMM
+            db_l = _empty((D,), dev)
+            dpre_pl = ops.tc_split(dpre, B * Gn, D, D, colsum_out=db_l)   # one split for the wgrad and the dgrad GEMM, + bias gradient
             G['gcn.gcn_layers.%d.W.weight' % l] = wgrad(dpre, ctx.aggs[l][0], B * Gn, D, D, dy_planes=dpre_pl, x_planes=ctx.aggs[l][1])
-            G['gcn.gcn_layers.%d.W.bias' % l] = colsum(dpre, B * Gn, D)
+            G['gcn.gcn_layers.%d.W.bias' % l] = db_l
             dagg = matmul_nn(dpre, P['gcn.gcn_layers.%d.W.weight' % l], B * Gn, x_planes=dpre_pl)
             dprev = _empty((B * Gn, D), dev)
             ops.gcn_aggregate(nnzT, colT, valT, dagg, B, Gn, D, dprev)

@@ -266,6 +266,16 @@ def gate_bwd_pre(dhg, h, g, n_max, n_dev, D, dz, dh0):
                                _p(dh0, _F32), _stream()), 'nnr_gate_bwd_pre')
 
 
+def gate_bwd_planes(dhg, h, g, off, N, D, cap, dh0, dmproj):
+    """selective-gate backward prologue with dz emitted as GEMM operand planes and its per-news sums in dmproj"""
+    algo = default_algo()
+    nbytes = int(lib.nnr_tc_split_bytes(cap, D, algo))
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
+    check(lib.nnr_gate_bwd_planes(_p(dhg, _F32), _p(h, _F32), _p(g, _F32), _p(off, _I32), N, D, cap, algo, buf.data_ptr(),
+                                  nbytes, _p(dh0, _F32), _p(dmproj, _F32), dmproj.stride(0), _stream()), 'nnr_gate_bwd_planes')
+    return Planes(buf, cap, D, int(lib.nnr_tc_split_pitch(D, algo)), 2 if algo in (ALGO_BF16, ALGO_BF16X3) else 4)
+
+
 def _pool_args(X, ldx, D, S, max_len, mode, seg_off=None, fixed_len=0, U=None, ldu=0, A=0, w2=None, qvec=None,
                ldq=0, scale=1.0, mask=None, pooled=None, ldp=0, alpha=None, dpooled=None, lddp=0, dX=None, lddx=0,
                accumulate_dx=False, dU=None, lddu=0, dw2_partial=None, dqvec=None, lddq=0, seg_order=None):

@@ -588,3 +588,35 @@ def test_length_sort_matches_torch_sort_on_device(cuda):
         assert torch.equal(ref, got), (N, maxk)
         stable = torch.sort(keys, descending=True, stable=True)[1]
         assert torch.equal(stable, got)
+
+
+def test_gate_backward_prologue_planes(cuda):
+    """nnr_gate_bwd_planes == nnr_gate_bwd_pre + nnr_tc_split + nnr_segment_colsum, bit for bit; and gate_bwd_pre itself
+    against the closed form dz = dhg*h*g*(1-g), dh0 = dhg*g (newsEncoders.py:128-131 differentiated)"""
+    ops = _ops()
+    g_ = torch.Generator().manual_seed(21)
+    for (N, L, D) in [(37, 12, 400), (150, 32, 400), (9, 5, 52)]:
+        mask, lens = _prefix_masks(N, L, g_, allow_empty=False)
+        off = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)]).to(torch.int32).to(cuda)
+        cap, ntok = N * L, int(lens.sum())
+        dhg = torch.randn(cap, D, generator=g_).to(cuda)
+        h = torch.randn(cap, D, generator=g_).to(cuda)
+        gate = torch.sigmoid(torch.randn(cap, D, generator=g_)).to(cuda)
+        dz = torch.zeros(cap, D, device=cuda)
+        dh0 = torch.zeros(cap, D, device=cuda)
+        ops.gate_bwd_pre(dhg, h, gate, cap * D, off[N:], D, dz, dh0)
+        ref_dz = (dhg.double() * h.double() * gate.double() * (1 - gate.double()))[:ntok]
+        assert (dz[:ntok].double() - ref_dz).abs().max().item() < 1e-5
+        assert (dh0[:ntok].double() - (dhg.double() * gate.double())[:ntok]).abs().max().item() < 1e-6
+        dm_ref = torch.empty(N, D, device=cuda)
+        ops.segment_colsum(dz, D, off, N, D, dm_ref, D)
+        if ops.default_algo() == 1:
+            continue
+        ref_pl = ops.tc_split(dz, cap, D, D, off[N:])
+        dh0b = torch.zeros(cap, D, device=cuda)
+        dm = torch.empty(N, D, device=cuda)
+        pl = ops.gate_bwd_planes(dhg, h, gate, off, N, D, cap, dh0b, dm)
+        rows = min(cap, (ntok + 63) // 64 * 64)
+        npl = ref_pl.buf.numel() // (cap * ref_pl.pitch * ref_pl.esz)
+        assert torch.equal(ref_pl.buf.view(npl, cap, -1)[:, :rows], pl.buf.view(npl, cap, -1)[:, :rows])
+        assert torch.equal(dh0b[:ntok], dh0[:ntok]) and torch.equal(dm, dm_ref)
