@@ -146,7 +146,12 @@ extern "C" int nnr_embed_gather_fwd(const float* table, const int32_t* ids, cons
 // ------------------------------------------------------------------------------------------
 // nnr_embed_gather_bwd : sort slots by id, then chunked segment reduce (deterministic)
 // ------------------------------------------------------------------------------------------
-#define EB_CHUNK 256   // sorted slots per CTA: small chunks = more CTAs in flight (the per-run work is latency bound)
+#ifndef EB_CHUNK
+#define EB_CHUNK 128   // sorted slots per CTA = threads per CTA: small chunks = more CTAs in flight (the per-run work is latency
+                       // bound; only the first ~18 % of the sorted slots are valid tokens).  scripts/sweep_eb_chunk.sh: 256 -> 0.424 ms,
+                       // 128 / 64 -> 0.358 ms per step
+#endif
+#define EB_WARPS (EB_CHUNK / 32)
 struct EbMeta { int32_t head_cross, tail_cross, covering, head_key, tail_key, pad0, pad1, pad2; };
 
 __global__ void eb_keys_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ len, int N, int L, int V,
@@ -230,11 +235,11 @@ __device__ __forceinline__ void eb_warp_accumulate(float4 (&acc)[3], const float
   }
 }
 
-#define EB_LONG 48   // runs at least this long are summed by all 8 warps of the CTA
+#define EB_LONG 48   // runs at least this long are summed by all warps of the CTA
 
 // one CTA per chunk of EB_CHUNK sorted slots.  Short runs of equal keys: one warp each.  Long runs (frequent
 // words, the <PAD> token): the 8 warps take every 8th entry and their partial sums are combined in warp order.
-__global__ void __launch_bounds__(256) eb_chunk_kernel(const float* __restrict__ dout, const int32_t* __restrict__ keys,
+__global__ void __launch_bounds__(EB_CHUNK) eb_chunk_kernel(const float* __restrict__ dout, const int32_t* __restrict__ keys,
                                                        const int32_t* __restrict__ vals,
                                                        const int32_t* __restrict__ off, int N, int L, int E, float p,
                                                        float inv_keep, uint64_t seed, float* __restrict__ dtable,
@@ -242,9 +247,9 @@ __global__ void __launch_bounds__(256) eb_chunk_kernel(const float* __restrict__
                                                        EbMeta* __restrict__ meta) {
   __shared__ int32_t s_key[EB_CHUNK + 2];
   __shared__ int32_t s_start[EB_CHUNK + 1];
-  __shared__ int32_t s_wcnt[8];
+  __shared__ int32_t s_wcnt[EB_WARPS];
   __shared__ int32_t s_nruns;
-  __shared__ __align__(16) float s_part[8][384];
+  __shared__ __align__(16) float s_part[EB_WARPS][384];
   const int n_valid = off[N];
   const int chunk = blockIdx.x;
   const int cs = chunk * EB_CHUNK;
@@ -261,13 +266,13 @@ __global__ void __launch_bounds__(256) eb_chunk_kernel(const float* __restrict__
     s_src[tid] = ((unsigned long long)off[row] + t) * (unsigned long long)E;
   }
   // keys of [cs-1, ce]  (s_key[i+1] = key[cs+i])
-  for (int i = tid; i < cnt + 2; i += 256) {
+  for (int i = tid; i < cnt + 2; i += EB_CHUNK) {
     int pos = cs - 1 + i;
     s_key[i] = (pos >= 0 && pos < n_valid) ? keys[pos] : -1;
   }
   __syncthreads();
   // run-start flags -> compact list (each warp owns 32 consecutive entries)
-  static_assert(EB_CHUNK == 256, "one entry per thread");
+  static_assert(EB_CHUNK % 32 == 0 && EB_CHUNK >= 32 && EB_CHUNK <= 1024, "one entry per thread");
   int f0 = 0;
   const int i0 = tid;
   if (i0 < cnt) f0 = (i0 == 0) || (s_key[i0 + 1] != s_key[i0]);
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(256) eb_chunk_kernel(const float* __restrict__
   if (f0) s_start[wbase + __popc(b0 & ((1u << lane) - 1))] = i0;
   if (tid == 0) {
     int tot = 0;
-    for (int j = 0; j < 8; ++j) tot += s_wcnt[j];
+    for (int j = 0; j < EB_WARPS; ++j) tot += s_wcnt[j];
     s_nruns = tot;
     s_start[tot] = cnt;
   }
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(256) eb_chunk_kernel(const float* __restrict__
   for (int r = 0; r < nruns; ++r) {
     const int a = s_start[r], b = s_start[r + 1];
     if (b - a >= EB_LONG) continue;
-    if ((ri++ & 7) != w) continue;
+    if ((ri++ % EB_WARPS) != w) continue;
     float4 acc[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -335,7 +340,7 @@ __global__ void __launch_bounds__(256) eb_chunk_kernel(const float* __restrict__
     float4 acc[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    eb_warp_accumulate(acc, dout, s_slot, s_src, E, E4, a + w, b, 8, lane, p, inv_keep, seed);
+    eb_warp_accumulate(acc, dout, s_slot, s_src, E, E4, a + w, b, EB_WARPS, lane, p, inv_keep, seed);
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
       int c4 = lane + 32 * q;
@@ -344,10 +349,10 @@ __global__ void __launch_bounds__(256) eb_chunk_kernel(const float* __restrict__
     __syncthreads();
     bool add;
     float* dst = run_dst(r, add);
-    for (int e = tid; e < E; e += 256) {
+    for (int e = tid; e < E; e += EB_CHUNK) {
       float v = 0.f;
 #pragma unroll
-      for (int ww = 0; ww < 8; ++ww) v += s_part[ww][e];
+      for (int ww = 0; ww < EB_WARPS; ++ww) v += s_part[ww][e];
       dst[e] = add ? dst[e] + v : v;
     }
     __syncthreads();
@@ -452,7 +457,7 @@ extern "C" int nnr_embed_gather_bwd(const float* dout, const int32_t* ids, const
   nnr_count_launch(3);
   int nchunks = (n + EB_CHUNK - 1) / EB_CHUNK;
   float inv_keep = 1.0f / (1.0f - p_drop);
-  eb_chunk_kernel<<<nchunks, 256, 0, st>>>(dout, keys_out, vals_out, off, N, L, E, p_drop, inv_keep, seed, dtable,
+  eb_chunk_kernel<<<nchunks, EB_CHUNK, 0, st>>>(dout, keys_out, vals_out, off, N, L, E, p_drop, inv_keep, seed, dtable,
                                            accumulate, slots, meta);
   NNR_LAUNCH_CHECK("eb_chunk_kernel");
   eb_fix_kernel<<<nchunks, 128, 0, st>>>(off, N, E, slots, meta, dtable, accumulate);
