@@ -136,6 +136,14 @@ size_t nnr_tc_split_colsum_workspace_bytes(int R, int C, int algo);
 int nnr_tc_split_colsum(const float* X, int64_t ld, int R, int C, const int32_t* r_dev, int algo, void* planes,
                         size_t planes_bytes, float* colsum, int accumulate, void* workspace, size_t workspace_bytes,
                         void* stream);
+/* Backward of "dropout -> relu -> Linear" (GCN layer layers.py:286-289, cluster affine userEncoders.py:91) in the same
+ * pass: x = dy * keep(seed, r*C + c)/(1-p) (the mask of nnr_dropout; x is also stored to dy_dropped when given -- it
+ * feeds the residual branch; must not alias dy), z = x * (relu_out > 0); planes(z) and colsum[c] = sum_r z[r,c].
+ * Bit-identical to nnr_dropout + the elementwise product + nnr_tc_split_colsum.                                  */
+int nnr_relu_bwd_split_colsum(const float* dy, const float* relu_out, int64_t ld, int R, int C, float p_drop,
+                              uint64_t seed, float* dy_dropped, int algo, void* planes, size_t planes_bytes,
+                              float* colsum, int accumulate, void* workspace, size_t workspace_bytes,
+                              void* stream);
 /* the algorithm NNR_GEMM_AUTO resolves to (env NNR_GEMM_ALGO = simt | tf32x3 | bf16; default tf32x3) */
 int nnr_gemm_default_algo(void);
 

@@ -76,6 +76,7 @@ SIGNATURES = {
     'nnr_tc_split': (C.c_int, [vp, i64, C.c_int, C.c_int, vp, C.c_int, vp, sz, vp]),
     'nnr_tc_split_colsum_workspace_bytes': (sz, [C.c_int, C.c_int, C.c_int]),
     'nnr_tc_split_colsum': (C.c_int, [vp, i64, C.c_int, C.c_int, vp, C.c_int, vp, sz, vp, C.c_int, vp, sz, vp]),
+    'nnr_relu_bwd_split_colsum': (C.c_int, [vp, vp, i64, C.c_int, C.c_int, f32, u64, vp, C.c_int, vp, sz, vp, C.c_int, vp, sz, vp]),
     'nnr_length_sort_desc': (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
     'nnr_tc_split_many': (C.c_int, [vp, C.c_int, C.c_int, vp]),
     'nnr_gemm_default_algo': (C.c_int, []),

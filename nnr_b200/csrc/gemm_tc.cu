@@ -606,10 +606,14 @@ __device__ __forceinline__ void tc_split_store4(void* out, size_t plane_stride, 
 // kernel adds the partials of the valid row blocks in block order -> deterministic.
 #define TCS_ROWS 64
 #define TCS_MAXG 2            // 4-column groups per thread: C <= 2048
-template <int MODE>
+// PRE: the matrix is dL/d(relu output) and is first multiplied by the dropout mask of nnr_dropout (counter = r * C + c;
+// the masked values are also stored to `dropped`, the residual branch needs them) and then by (relu_out > 0): the
+// backward of "dropout -> relu -> Linear" without materialising either product (layers.py:286-289, userEncoders.py:91).
+struct SplitPre { const float* relu_out; float* dropped; float p, inv_keep; uint64_t seed; };
+template <int MODE, bool PRE>
 __global__ void __launch_bounds__(256) tc_split_colsum_kernel(const float* __restrict__ src, int64_t ld, int R, int C, int Cp,
                                                               const int32_t* __restrict__ r_dev, void* __restrict__ out,
-                                                              size_t plane_stride, float* __restrict__ partial) {
+                                                              size_t plane_stride, float* __restrict__ partial, SplitPre pre) {
   __shared__ float4 s_acc[256];
   int Rv = R;
   if (r_dev) Rv = min(R, *r_dev);
@@ -641,6 +645,18 @@ __global__ void __launch_bounds__(256) tc_split_colsum_kernel(const float* __res
               if (cq < C) x[u][j].x = __ldg(sp);
               if (cq + 1 < C) x[u][j].y = __ldg(sp + 1);
               if (cq + 2 < C) x[u][j].z = __ldg(sp + 2);
+            }
+            if (PRE) {
+              float* xv = reinterpret_cast<float*>(&x[u][j]);
+              const size_t o = (size_t)r * ld + cq;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (cq + e < C) {
+                  if (pre.p > 0.f) xv[e] *= dropout_scale(pre.seed, (uint64_t)r * (uint64_t)C + cq + e, pre.p, pre.inv_keep);
+                  if (pre.dropped) pre.dropped[o + e] = xv[e];
+                  xv[e] *= (__ldg(pre.relu_out + o + e) > 0.f) ? 1.f : 0.f;
+                }
+              }
             }
           }
         }
@@ -1026,12 +1042,42 @@ extern "C" int nnr_tc_split_colsum(const float* X, int64_t ld, int R, int C, con
   cudaStream_t st = (cudaStream_t)stream;
   const int nblocks = (R + TCS_ROWS - 1) / TCS_ROWS;
   void* ph = nnr_prof_begin(1, 0.0, st);
-  if (mode == 1) tc_split_colsum_kernel<1><<<nblocks, 256, 0, st>>>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (float*)workspace);
-  else if (mode == 2) tc_split_colsum_kernel<2><<<nblocks, 256, 0, st>>>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (float*)workspace);
-  else tc_split_colsum_kernel<0><<<nblocks, 256, 0, st>>>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (float*)workspace);
+  if (mode == 1) tc_split_colsum_kernel<1, false><<<nblocks, 256, 0, st>>>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (float*)workspace, SplitPre{});
+  else if (mode == 2) tc_split_colsum_kernel<2, false><<<nblocks, 256, 0, st>>>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (float*)workspace, SplitPre{});
+  else tc_split_colsum_kernel<0, false><<<nblocks, 256, 0, st>>>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (float*)workspace, SplitPre{});
   nnr_prof_end(ph, st);
   NNR_LAUNCH_CHECK("tc_split_colsum_kernel");
   tc_split_colsum_reduce<<<(C + 31) / 32, 512, 0, st>>>((const float*)workspace, nblocks, R, C, Cp, r_dev, colsum, accumulate);
+  NNR_LAUNCH_CHECK("tc_split_colsum_reduce");
+  return 0;
+}
+
+// dL/d(pre-activation) of "dropout -> relu -> Linear" as operand planes + column sums (bias gradient), see SplitPre
+extern "C" int nnr_relu_bwd_split_colsum(const float* dy, const float* relu_out, int64_t ld, int R, int C, float p_drop,
+                                         uint64_t seed, float* dy_dropped, int algo, void* planes, size_t planes_bytes,
+                                         float* colsum, int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  NNR_REQUIRE(dy && relu_out && planes && colsum && workspace && R > 0 && C > 0 && ld >= C, NNR_ERR_ARG,
+              "nnr_relu_bwd_split_colsum: bad arguments");
+  NNR_REQUIRE(p_drop >= 0.f && p_drop < 1.f, NNR_ERR_ARG, "nnr_relu_bwd_split_colsum: p_drop=%f", p_drop);
+  NNR_REQUIRE(algo == NNR_GEMM_TC_TF32X3 || algo == NNR_GEMM_TC_BF16 || algo == NNR_GEMM_TC_BF16X3, NNR_ERR_UNSUPPORTED,
+              "nnr_relu_bwd_split_colsum: planes exist only for the tensor-core GEMM algorithms");
+  NNR_REQUIRE(planes_bytes >= nnr_tc_split_bytes(R, C, algo), NNR_ERR_WORKSPACE, "nnr_relu_bwd_split_colsum: planes buffer too small");
+  NNR_REQUIRE(workspace_bytes >= nnr_tc_split_colsum_workspace_bytes(R, C, algo), NNR_ERR_WORKSPACE,
+              "nnr_relu_bwd_split_colsum: workspace too small");
+  NNR_REQUIRE(nnr_aligned16(planes) && nnr_aligned16(workspace) && nnr_aligned16(dy) && ld % 4 == 0, NNR_ERR_ALIGN,
+              "nnr_relu_bwd_split_colsum: dy, planes, workspace must be 16B aligned and ld %% 4 == 0");
+  const int mode = algo_mode(algo);
+  const int Cp = (int)nnr_tc_split_pitch(C, algo);
+  NNR_REQUIRE(Cp <= 4 * 256 * TCS_MAXG, NNR_ERR_UNSUPPORTED, "nnr_relu_bwd_split_colsum: more than %d columns", 4 * 256 * TCS_MAXG);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblocks = (R + TCS_ROWS - 1) / TCS_ROWS;
+  SplitPre pre;
+  pre.relu_out = relu_out; pre.dropped = dy_dropped; pre.p = p_drop; pre.inv_keep = 1.0f / (1.0f - p_drop); pre.seed = seed;
+  if (mode == 1) tc_split_colsum_kernel<1, true><<<nblocks, 256, 0, st>>>(dy, ld, R, C, Cp, nullptr, planes, (size_t)R * Cp, (float*)workspace, pre);
+  else if (mode == 2) tc_split_colsum_kernel<2, true><<<nblocks, 256, 0, st>>>(dy, ld, R, C, Cp, nullptr, planes, (size_t)R * Cp, (float*)workspace, pre);
+  else tc_split_colsum_kernel<0, true><<<nblocks, 256, 0, st>>>(dy, ld, R, C, Cp, nullptr, planes, (size_t)R * Cp, (float*)workspace, pre);
+  NNR_LAUNCH_CHECK("tc_split_colsum_kernel");
+  tc_split_colsum_reduce<<<(C + 31) / 32, 512, 0, st>>>((const float*)workspace, nblocks, R, C, Cp, nullptr, colsum, accumulate);
   NNR_LAUNCH_CHECK("tc_split_colsum_reduce");
   return 0;
 }

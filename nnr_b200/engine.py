@@ -50,6 +50,12 @@ def _param_grads(P, names, G):
     return tuple(G[k] for k in names)
 
 
+def _fused_relu_bwd(dy, cols):
+    """nnr_relu_bwd_split_colsum applies: tensor-core GEMM planes in use, contiguous 16-byte aligned rows, <= 2048 columns"""
+    return (ops.default_algo() != ops.ALGO_SIMT and cols <= 2048 and cols % 4 == 0 and dy.is_contiguous()
+            and dy.data_ptr() % 16 == 0)
+
+
 def _flat_grads(P, names):
     """every parameter's .grad is a view of trainer.TrainStep's flat gradient buffer"""
     return all(getattr(P[k], '_nnr_flat_grad', False) and P[k].grad is not None for k in names)
@@ -631,11 +637,18 @@ class SUEFunction(torch.autograd.Function):
             G['interClusterAttention.Q.bias'] = colsum(dq2, B * n, Au)
             dcand = matmul_nn(dq2, P['interClusterAttention.Q.weight'], B * n)               # [B*n, D]
             # cluster affine backward: f = (relu(W intra + b) + intra) * drop
-            if pe > 0:
-                ops.dropout(df, pe, seeds[L + 1], df)
-            dpre = df * (r_f > 0)                                                             # relu mask
             db_f = _empty((D,), dev)
-            dpre_pl = ops.tc_split(dpre, B * n * C1, D, D, colsum_out=db_f)      # planes + bias gradient in one pass
+            if _fused_relu_bwd(df, D):
+                # dropout mask, relu mask, operand planes and the bias gradient in one pass over df
+                df_d = _empty(df.shape, dev) if pe > 0 else None
+                dpre = None
+                dpre_pl = ops.relu_bwd_split_colsum(df, r_f, B * n * C1, D, pe, seeds[L + 1], df_d, db_f)
+                df = df_d if pe > 0 else df
+            else:
+                if pe > 0:
+                    ops.dropout(df, pe, seeds[L + 1], df)
+                dpre = df * (r_f > 0)                                                         # relu mask
+                dpre_pl = ops.tc_split(dpre, B * n * C1, D, D, colsum_out=db_f)  # planes + bias gradient in one pass
             G['clusterFeatureAffine.weight'] = wgrad(dpre, intra, B * n * C1, D, D, dy_planes=dpre_pl, x_planes=intra_pl)
             G['clusterFeatureAffine.bias'] = db_f
             dintra = matmul_nn(dpre, P['clusterFeatureAffine.weight'], B * n * C1, epilogue=EPI_ADD_AUX, aux=df, ldaux=D,
@@ -664,12 +677,18 @@ class SUEFunction(torch.autograd.Function):
         residual = meta['residual']
         for l in range(L - 1, -1, -1):
             pl = (pe / 2.0) if l < L - 1 else 0.0
-            if pl > 0:
-                dx = dx.clone() if dx.data_ptr() == dxL.data_ptr() else dx
-                ops.dropout(dx, pl, seeds[l], dx)
-            dpre = dx * (ctx.rs[l] > 0)
             db_l = _empty((D,), dev)
-            dpre_pl = ops.tc_split(dpre, B * Gn, D, D, colsum_out=db_l)   # one split for the wgrad and the dgrad GEMM, + bias gradient
+            if _fused_relu_bwd(dx, D):
+                dx_d = _empty(dx.shape, dev) if pl > 0 else None
+                dpre = None
+                dpre_pl = ops.relu_bwd_split_colsum(dx, ctx.rs[l], B * Gn, D, pl, seeds[l], dx_d, db_l)
+                dx = dx_d if pl > 0 else dx
+            else:
+                if pl > 0:
+                    dx = dx.clone() if dx.data_ptr() == dxL.data_ptr() else dx
+                    ops.dropout(dx, pl, seeds[l], dx)
+                dpre = dx * (ctx.rs[l] > 0)
+                dpre_pl = ops.tc_split(dpre, B * Gn, D, D, colsum_out=db_l)   # one split for the wgrad and the dgrad GEMM, + bias gradient
             G['gcn.gcn_layers.%d.W.weight' % l] = wgrad(dpre, ctx.aggs[l][0], B * Gn, D, D, dy_planes=dpre_pl, x_planes=ctx.aggs[l][1])
             G['gcn.gcn_layers.%d.W.bias' % l] = db_l
             dagg = matmul_nn(dpre, P['gcn.gcn_layers.%d.W.weight' % l], B * Gn, x_planes=dpre_pl)

@@ -136,6 +136,20 @@ def tc_split(x, rows, cols, ld, r_dev=None, colsum_out=None, accumulate=False):
     return Planes(buf, rows, cols, int(lib.nnr_tc_split_pitch(cols, algo)), 2 if algo in (ALGO_BF16, ALGO_BF16X3) else 4)
 
 
+def relu_bwd_split_colsum(dy, relu_out, rows, cols, p_drop, seed, dy_dropped, colsum_out):
+    """planes of dy * dropout_mask * (relu_out > 0) + their column sums in one pass; dy_dropped (optional, not aliasing dy)
+    receives dy * dropout_mask.  Tensor-core algos only."""
+    algo = default_algo()
+    nbytes = int(lib.nnr_tc_split_bytes(rows, cols, algo))
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=dy.device)
+    wsb = int(lib.nnr_tc_split_colsum_workspace_bytes(rows, cols, algo))
+    ws = workspace(wsb, dy.device, 'split_colsum')
+    check(lib.nnr_relu_bwd_split_colsum(_p(dy, _F32), _p(relu_out, _F32), dy.stride(0), rows, cols, float(p_drop), int(seed),
+                                        _p(dy_dropped, _F32), algo, buf.data_ptr(), nbytes, _p(colsum_out, _F32), 0,
+                                        ws.data_ptr(), ws.numel(), _stream()), 'nnr_relu_bwd_split_colsum')
+    return Planes(buf, rows, cols, int(lib.nnr_tc_split_pitch(cols, algo)), 2 if algo in (ALGO_BF16, ALGO_BF16X3) else 4)
+
+
 class SplitMany:
     """operand planes of a fixed set of row-major matrices (the weight matrices), refreshed by ONE kernel launch"""
 

@@ -36,7 +36,7 @@ def _tc_class(M, N, K, transA, transB, m_dev, k_dev):
 _TIMED = ['seq_prepare', 'embed_gather_fwd', 'embed_gather_planes_fwd', 'embed_gather_bwd', 'gemm', 'colsum', 'segment_colsum', 'lstm_fwd',
           'lstm_bwd', 'lstm_bwd_planes', 'lstm_shift_h', 'lstm_shift_h_planes', 'gate_bwd_pre', 'gate_bwd_planes', 'attn_pool_fwd', 'attn_pool_bwd', 'news_fuse_fwd', 'news_fuse_bwd',
           'graph_to_csr', 'gcn_aggregate', 'cluster_intra_fwd', 'cluster_intra_bwd', 'rowdot_fwd', 'rowdot_bwd',
-          'dropout', 'flat_clip_adam', 'sue_graph_build']
+          'dropout', 'flat_clip_adam', 'sue_graph_build', 'relu_bwd_split_colsum']
 
 
 def _dev_int(t):

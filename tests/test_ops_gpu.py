@@ -620,3 +620,28 @@ def test_gate_backward_prologue_planes(cuda):
         npl = ref_pl.buf.numel() // (cap * ref_pl.pitch * ref_pl.esz)
         assert torch.equal(ref_pl.buf.view(npl, cap, -1)[:, :rows], pl.buf.view(npl, cap, -1)[:, :rows])
         assert torch.equal(dh0b[:ntok], dh0[:ntok]) and torch.equal(dm, dm_ref)
+
+
+def test_relu_backward_split_colsum(cuda):
+    """nnr_relu_bwd_split_colsum == nnr_dropout, * (relu_out > 0), nnr_tc_split_colsum -- planes, masked gradient and bias
+    gradient bit for bit (layers.py:286-289 / userEncoders.py:91 differentiated)"""
+    ops = _ops()
+    if ops.default_algo() == 1:
+        pytest.skip('planes exist only for the tensor-core GEMM algorithms')
+    g = torch.Generator().manual_seed(31)
+    for (R, C, p) in [(4352, 900, 0.1), (5760, 900, 0.2), (130, 52, 0.0), (64, 900, 0.0)]:
+        dy = torch.randn(R, C, generator=g).to(cuda)
+        r = torch.relu(torch.randn(R, C, generator=g)).to(cuda)
+        ref_d = dy.clone()
+        if p > 0:
+            ops.dropout(ref_d, p, 99, ref_d)
+        dpre = ref_d * (r > 0)
+        cs_ref = torch.empty(C, device=cuda)
+        ref_pl = ops.tc_split(dpre, R, C, C, colsum_out=cs_ref)
+        cs = torch.empty(C, device=cuda)
+        dd = torch.empty(R, C, device=cuda) if p > 0 else None
+        pl = ops.relu_bwd_split_colsum(dy, r, R, C, p, 99, dd, cs)
+        assert torch.equal(pl.buf, ref_pl.buf), (R, C, p)
+        assert torch.equal(cs, cs_ref)
+        if p > 0:
+            assert torch.equal(dd, ref_d)
