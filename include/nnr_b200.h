@@ -260,6 +260,9 @@ int nnr_graph_to_csr(const float* graph, int B, int G, int transpose, int32_t* n
 /* out[b,i,:] = sum_{e < nnz[b,i]} val[b,i,e] * x[b,col[b,i,e],:]   (fixed order: deterministic) */
 int nnr_gcn_aggregate(const int32_t* nnz, const int32_t* col, const float* val, const float* x,
                       int B, int G, int D, float* out, void* stream);
+/* out = A x + add: the aggregation of the GCN backward with its residual term in the same pass (add != out) */
+int nnr_gcn_aggregate_add(const int32_t* nnz, const int32_t* col, const float* val, const float* x, int B,
+                          int G, int D, const float* add, float* out, void* stream);
 
 /* ---- intra-cluster attention: userEncoders.py:85-89 (torch_scatter softmax + sum) -----------
  *   Kp [B,H,Au], Qp [B,n,Au], g [B,H,D], idx [B,H] int64 in [0,C1)

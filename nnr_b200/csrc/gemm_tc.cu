@@ -601,10 +601,10 @@ __device__ __forceinline__ void tc_split_store4(void* out, size_t plane_stride, 
 }
 
 // Split + column sums in one pass over the matrix (a bias gradient is the column sum of the same dL/dy whose planes
-// feed the dgrad / wgrad GEMMs): one CTA per TCS_ROWS rows; thread (rs, g) owns 4-column groups g, g + G, ... and rows
+// feed the dgrad / wgrad GEMMs): one CTA per tcs_rows(R) rows (64, or 16 when the matrix is small so that the grid still covers the SMs); thread (rs, g) owns 4-column groups g, g + G, ... and rows
 // r0 + rs, r0 + rs + RS, ...; per-CTA partial sums (row slots combined in fixed order) go to `partial`, a second
 // kernel adds the partials of the valid row blocks in block order -> deterministic.
-#define TCS_ROWS 64
+static __host__ __device__ __forceinline__ int tcs_rows(int R) { return R >= 16384 ? 64 : 16; }
 #define TCS_MAXG 2            // 4-column groups per thread: C <= 2048
 // PRE: the matrix is dL/d(relu output) and is first multiplied by the dropout mask of nnr_dropout (counter = r * C + c;
 // the masked values are also stored to `dropped`, the residual branch needs them) and then by (relu_out > 0): the
@@ -618,7 +618,8 @@ __global__ void __launch_bounds__(256) tc_split_colsum_kernel(const float* __res
   int Rv = R;
   if (r_dev) Rv = min(R, *r_dev);
   const int Rw = r_dev ? min(R, (Rv + 63) / 64 * 64) : R;        // rows whose planes must be defined (zero tail)
-  const int r0 = blockIdx.x * TCS_ROWS;
+  const int rpc = tcs_rows(R);
+  const int r0 = blockIdx.x * rpc;
   if (r0 >= Rw) return;
   const int ncq = Cp >> 2;
   const int G = min(ncq, 256), RS = 256 / G;
@@ -627,7 +628,7 @@ __global__ void __launch_bounds__(256) tc_split_colsum_kernel(const float* __res
   float4 acc[TCS_MAXG];
 #pragma unroll
   for (int j = 0; j < TCS_MAXG; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int r1 = min(r0 + TCS_ROWS, Rw);
+  const int r1 = min(r0 + rpc, Rw);
   if (active) {
     for (int rb = r0 + rs; rb < r1; rb += 4 * RS) {
       float4 x[4][TCS_MAXG];
@@ -697,7 +698,7 @@ __global__ void __launch_bounds__(512) tc_split_colsum_reduce(const float* __res
   const int c = blockIdx.x * 32 + cl;
   int Rv = R;
   if (r_dev) Rv = min(R, *r_dev);
-  const int nb = min(nblocks, (Rv + TCS_ROWS - 1) / TCS_ROWS);
+  const int nb = min(nblocks, (Rv + tcs_rows(R) - 1) / tcs_rows(R));
   float a0 = 0.f, a1 = 0.f;
   if (c < C) {
     int b = sl;
@@ -1025,7 +1026,7 @@ extern "C" int nnr_tc_split(const float* X, int64_t ld, int R, int C, const int3
 // split + column sums of the same matrix in one pass (see tc_split_colsum_kernel); workspace = per-row-block partials
 extern "C" size_t nnr_tc_split_colsum_workspace_bytes(int R, int C, int algo) {
   if (R <= 0 || C <= 0) return 0;
-  return (size_t)((R + TCS_ROWS - 1) / TCS_ROWS) * (size_t)nnr_tc_split_pitch(C, algo) * sizeof(float);
+  return (size_t)((R + tcs_rows(R) - 1) / tcs_rows(R)) * (size_t)nnr_tc_split_pitch(C, algo) * sizeof(float);
 }
 extern "C" int nnr_tc_split_colsum(const float* X, int64_t ld, int R, int C, const int32_t* r_dev, int algo, void* planes,
                                    size_t planes_bytes, float* colsum, int accumulate, void* workspace, size_t workspace_bytes,
@@ -1040,7 +1041,7 @@ extern "C" int nnr_tc_split_colsum(const float* X, int64_t ld, int R, int C, con
   const int Cp = (int)nnr_tc_split_pitch(C, algo);
   NNR_REQUIRE(Cp <= 4 * 256 * TCS_MAXG, NNR_ERR_UNSUPPORTED, "nnr_tc_split_colsum: more than %d columns", 4 * 256 * TCS_MAXG);
   cudaStream_t st = (cudaStream_t)stream;
-  const int nblocks = (R + TCS_ROWS - 1) / TCS_ROWS;
+  const int nblocks = (R + tcs_rows(R) - 1) / tcs_rows(R);
   void* ph = nnr_prof_begin(1, 0.0, st);
   if (mode == 1) tc_split_colsum_kernel<1, false><<<nblocks, 256, 0, st>>>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (float*)workspace, SplitPre{});
   else if (mode == 2) tc_split_colsum_kernel<2, false><<<nblocks, 256, 0, st>>>(X, ld, R, C, Cp, r_dev, planes, (size_t)R * Cp, (float*)workspace, SplitPre{});
@@ -1070,7 +1071,7 @@ extern "C" int nnr_relu_bwd_split_colsum(const float* dy, const float* relu_out,
   const int Cp = (int)nnr_tc_split_pitch(C, algo);
   NNR_REQUIRE(Cp <= 4 * 256 * TCS_MAXG, NNR_ERR_UNSUPPORTED, "nnr_relu_bwd_split_colsum: more than %d columns", 4 * 256 * TCS_MAXG);
   cudaStream_t st = (cudaStream_t)stream;
-  const int nblocks = (R + TCS_ROWS - 1) / TCS_ROWS;
+  const int nblocks = (R + tcs_rows(R) - 1) / tcs_rows(R);
   SplitPre pre;
   pre.relu_out = relu_out; pre.dropped = dy_dropped; pre.p = p_drop; pre.inv_keep = 1.0f / (1.0f - p_drop); pre.seed = seed;
   if (mode == 1) tc_split_colsum_kernel<1, true><<<nblocks, 256, 0, st>>>(dy, ld, R, C, Cp, nullptr, planes, (size_t)R * Cp, (float*)workspace, pre);

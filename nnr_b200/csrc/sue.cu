@@ -118,7 +118,7 @@ extern "C" int nnr_graph_to_csr(const float* graph, int B, int G, int transpose,
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gcn_aggregate_kernel(const int32_t* __restrict__ nnz, const int32_t* __restrict__ col,
                                                             const float* __restrict__ val, const float* __restrict__ x, int G,
-                                                            int D, float* __restrict__ out) {
+                                                            int D, const float* __restrict__ add, float* __restrict__ out) {
   extern __shared__ unsigned char smraw[];
   int* s_col = reinterpret_cast<int*>(smraw);
   float* s_val = reinterpret_cast<float*>(smraw + sizeof(int) * G);
@@ -139,15 +139,25 @@ __global__ void __launch_bounds__(256) gcn_aggregate_kernel(const int32_t* __res
       for (int j = 0; j < 8; ++j) acc = fmaf(s_val[e + j], v[j], acc);
     }
     for (; e < n; ++e) acc = fmaf(s_val[e], xb[(size_t)s_col[e] * D + d], acc);
-    out[(size_t)row * D + d] = acc;
+    out[(size_t)row * D + d] = add ? acc + add[(size_t)row * D + d] : acc;     // + residual branch of the backward
   }
+}
+static int gcn_aggregate_launch(const int32_t* nnz, const int32_t* col, const float* val, const float* x, int B, int G, int D,
+                                const float* add, float* out, void* stream, const char* who) {
+  NNR_REQUIRE(nnz && col && val && x && out && B > 0 && G > 0 && D > 0, NNR_ERR_ARG, "%s: bad arguments", who);
+  gcn_aggregate_kernel<<<B * G, 256, (sizeof(int) + sizeof(float)) * G, (cudaStream_t)stream>>>(nnz, col, val, x, G, D, add, out);
+  NNR_LAUNCH_CHECK("gcn_aggregate_kernel");
+  return 0;
 }
 extern "C" int nnr_gcn_aggregate(const int32_t* nnz, const int32_t* col, const float* val, const float* x, int B, int G, int D,
                                  float* out, void* stream) {
-  NNR_REQUIRE(nnz && col && val && x && out && B > 0 && G > 0 && D > 0, NNR_ERR_ARG, "nnr_gcn_aggregate: bad arguments");
-  gcn_aggregate_kernel<<<B * G, 256, (sizeof(int) + sizeof(float)) * G, (cudaStream_t)stream>>>(nnz, col, val, x, G, D, out);
-  NNR_LAUNCH_CHECK("gcn_aggregate_kernel");
-  return 0;
+  return gcn_aggregate_launch(nnz, col, val, x, B, G, D, nullptr, out, stream, "nnr_gcn_aggregate");
+}
+// out = A x + add (the residual term of the GCN backward, layers.py:320-322 differentiated); add must not alias out
+extern "C" int nnr_gcn_aggregate_add(const int32_t* nnz, const int32_t* col, const float* val, const float* x, int B, int G,
+                                     int D, const float* add, float* out, void* stream) {
+  NNR_REQUIRE(add && add != out, NNR_ERR_ARG, "nnr_gcn_aggregate_add: add must be given and must not alias out");
+  return gcn_aggregate_launch(nnz, col, val, x, B, G, D, add, out, stream, "nnr_gcn_aggregate_add");
 }
 
 // ------------------------------------------------------------------------------------------------

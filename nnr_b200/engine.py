@@ -9,6 +9,7 @@ slicing of the small per-news tensors.
 Reference spans: CNE = newsEncoders.py:102-141, SUE = userEncoders.py:68-98, GCN = layers.py:285-323.
 """
 import math
+import os
 import weakref
 
 import torch
@@ -50,9 +51,12 @@ def _param_grads(P, names, G):
     return tuple(G[k] for k in names)
 
 
+_FUSE_SUE_BWD = os.environ.get('NNR_FUSE_SUE_BWD', '1') != '0'     # A/B switch for the fused relu-backward split
+
+
 def _fused_relu_bwd(dy, cols):
     """nnr_relu_bwd_split_colsum applies: tensor-core GEMM planes in use, contiguous 16-byte aligned rows, <= 2048 columns"""
-    return (ops.default_algo() != ops.ALGO_SIMT and cols <= 2048 and cols % 4 == 0 and dy.is_contiguous()
+    return (_FUSE_SUE_BWD and ops.default_algo() != ops.ALGO_SIMT and cols <= 2048 and cols % 4 == 0 and dy.is_contiguous()
             and dy.data_ptr() % 16 == 0)
 
 
@@ -693,9 +697,7 @@ class SUEFunction(torch.autograd.Function):
             G['gcn.gcn_layers.%d.W.bias' % l] = db_l
             dagg = matmul_nn(dpre, P['gcn.gcn_layers.%d.W.weight' % l], B * Gn, x_planes=dpre_pl)
             dprev = _empty((B * Gn, D), dev)
-            ops.gcn_aggregate(nnzT, colT, valT, dagg, B, Gn, D, dprev)
-            if residual:
-                dprev += dx
+            ops.gcn_aggregate(nnzT, colT, valT, dagg, B, Gn, D, dprev, add=dx if residual else None)   # + residual term
             dx = dprev
         dx0 = dx0.view(B * Gn, D) + dx
         dx0 = dx0.view(B, Gn, D)

@@ -348,7 +348,12 @@ def graph_to_csr(graph, transpose, nnz, col, val):
                                _stream()), 'nnr_graph_to_csr')
 
 
-def gcn_aggregate(nnz, col, val, x, B, G, D, out):
+def gcn_aggregate(nnz, col, val, x, B, G, D, out, add=None):
+    """out = A x (+ add: the residual term of the backward, same pass)"""
+    if add is not None:
+        check(lib.nnr_gcn_aggregate_add(_p(nnz, _I32), _p(col, _I32), _p(val, _F32), _p(x, _F32), B, G, D, _p(add, _F32),
+                                        _p(out, _F32), _stream()), 'nnr_gcn_aggregate_add')
+        return
     check(lib.nnr_gcn_aggregate(_p(nnz, _I32), _p(col, _I32), _p(val, _F32), _p(x, _F32), B, G, D, _p(out, _F32),
                                 _stream()), 'nnr_gcn_aggregate')
 

@@ -478,6 +478,10 @@ def test_graph_build_bit_exact_and_aggregate(cuda):
         ops.gcn_aggregate(nnz, col, val, x, B, G_, D, out)
         ref = torch.bmm(gm.double(), x.double())
         assert (out.view(B, G_, D).double() - ref).abs().max() < 1e-5
+        res = torch.randn(B * G_, D, device=cuda)
+        out_r = torch.empty(B * G_, D, device=cuda)
+        ops.gcn_aggregate(nnz, col, val, x, B, G_, D, out_r, add=res)              # residual term in the same pass
+        assert torch.equal(out_r, out + res)
         # other feature widths, and a larger graph
         for D2_ in (20, 333):
             x2 = torch.randn(B, G_, D2_, device=cuda)
