@@ -373,10 +373,12 @@ def test_lstm_ffma_variant_subprocess(cuda):
 
 
 # ---------------------------------------------------------------------------------------------
-def test_attn_pool_modes(cuda):
+@pytest.mark.parametrize('S,Lmax,D,A', [(37, 20, 400, 200),      # row-parallel backward, 4 column groups per lane
+                                        (9, 130, 900, 200),      # longer than one pass of the CTA, 8 column groups per lane
+                                        (11, 7, 50, 22)])        # widths that are not multiples of 4: column-per-thread kernel
+def test_attn_pool_modes(cuda, S, Lmax, D, A):
     ops = _ops()
     g = torch.Generator().manual_seed(8)
-    S, Lmax, D, A = 37, 20, 400, 200
     lens = torch.randint(1, Lmax + 1, (S,), generator=g)
     off_l = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)])
     tot = int(off_l[-1])
