@@ -4,6 +4,7 @@
 // Replaces: MIND_corpus.py:162-216 (numpy preprocessing), torch.bmm(graph, feature) at layers.py:286,
 // and torch_scatter.scatter_softmax / scatter_sum at userEncoders.py:88-89.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/nnr_b200.h"
 
 // ------------------------------------------------------------------------------------------------
@@ -142,10 +143,57 @@ __global__ void __launch_bounds__(256) gcn_aggregate_kernel(const int32_t* __res
     out[(size_t)row * D + d] = add ? acc + add[(size_t)row * D + d] : acc;     // + residual branch of the backward
   }
 }
+// D % 4 == 0: a thread owns 4 consecutive features (16-byte loads), one pass over the neighbour list per thread
+__global__ void __launch_bounds__(256) gcn_aggregate_vec_kernel(const int32_t* __restrict__ nnz, const int32_t* __restrict__ col,
+                                                                const float* __restrict__ val, const float* __restrict__ x, int G,
+                                                                int D, const float* __restrict__ add, float* __restrict__ out) {
+  extern __shared__ unsigned char smraw[];
+  int* s_col = reinterpret_cast<int*>(smraw);
+  float* s_val = reinterpret_cast<float*>(smraw + sizeof(int) * G);
+  const int row = blockIdx.x;
+  const int b = row / G;
+  const int n = nnz[row];
+  for (int e = threadIdx.x; e < n; e += blockDim.x) { s_col[e] = col[(size_t)row * G + e]; s_val[e] = val[(size_t)row * G + e]; }
+  __syncthreads();
+  const int D4 = D >> 2;
+  const float4* xb = reinterpret_cast<const float4*>(x + (size_t)b * G * D);
+  for (int d = threadIdx.x; d < D4; d += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int e = 0;
+    for (; e + 8 <= n; e += 8) {            // eight neighbour rows in flight, accumulated in edge order
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldg(xb + (size_t)s_col[e + j] * D4 + d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float w = s_val[e + j];
+        acc.x = fmaf(w, v[j].x, acc.x); acc.y = fmaf(w, v[j].y, acc.y); acc.z = fmaf(w, v[j].z, acc.z); acc.w = fmaf(w, v[j].w, acc.w);
+      }
+    }
+    for (; e < n; ++e) {
+      const float w = s_val[e];
+      const float4 v = __ldg(xb + (size_t)s_col[e] * D4 + d);
+      acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+    }
+    if (add) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(add + (size_t)row * D) + d);
+      acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+    }
+    reinterpret_cast<float4*>(out + (size_t)row * D)[d] = acc;
+  }
+}
 static int gcn_aggregate_launch(const int32_t* nnz, const int32_t* col, const float* val, const float* x, int B, int G, int D,
                                 const float* add, float* out, void* stream, const char* who) {
   NNR_REQUIRE(nnz && col && val && x && out && B > 0 && G > 0 && D > 0, NNR_ERR_ARG, "%s: bad arguments", who);
-  gcn_aggregate_kernel<<<B * G, 256, (sizeof(int) + sizeof(float)) * G, (cudaStream_t)stream>>>(nnz, col, val, x, G, D, add, out);
+  const size_t smem = (sizeof(int) + sizeof(float)) * G;
+  static int vec_mode = -1;
+  if (vec_mode < 0) { const char* e = getenv("NNR_GCN_VEC"); vec_mode = (e && e[0] == '0') ? 0 : 1; }
+  if (vec_mode && D % 4 == 0 && nnr_aligned16(x) && nnr_aligned16(out) && (!add || nnr_aligned16(add))) {
+    const int threads = ((D / 4 + 31) / 32 * 32) < 256 ? ((D / 4 + 31) / 32 * 32) : 256;
+    gcn_aggregate_vec_kernel<<<B * G, threads, smem, (cudaStream_t)stream>>>(nnz, col, val, x, G, D, add, out);
+  } else {
+    gcn_aggregate_kernel<<<B * G, 256, smem, (cudaStream_t)stream>>>(nnz, col, val, x, G, D, add, out);
+  }
   NNR_LAUNCH_CHECK("gcn_aggregate_kernel");
   return 0;
 }
