@@ -212,6 +212,7 @@ extern "C" int nnr_gcn_aggregate_add(const int32_t* nnz, const int32_t* col, con
 // intra-cluster attention (segment softmax by category + segment weighted sum)
 // ------------------------------------------------------------------------------------------------
 #define CI_MAXH 256
+__device__ __forceinline__ bool dev_al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 #define CI_MAXC 72
 __global__ void __launch_bounds__(256) cluster_intra_fwd_kernel(const float* __restrict__ Kp, const float* __restrict__ Qp,
                                                                 const float* __restrict__ g, const int64_t* __restrict__ idx,
@@ -263,6 +264,32 @@ __global__ void __launch_bounds__(256) cluster_intra_fwd_kernel(const float* __r
   __syncthreads();
   const float* gb = g + (size_t)b * H * D;
   float* ob = intra + (size_t)bk * C1 * D;
+  if ((D & 3) == 0 && dev_al16(g) && dev_al16(intra)) {
+    // 16-byte version of the loop below: a thread owns four features
+    const int D4 = D >> 2;
+    const float4* gb4 = reinterpret_cast<const float4*>(gb);
+    float4* ob4 = reinterpret_cast<float4*>(ob);
+    for (int d = tid; d < D4; d += 256) {
+      int c = 0;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int e0 = 0; e0 < H; e0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (e0 + j < H) ? __ldg(gb4 + (size_t)s_perm[e0 + j] * D4 + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int e = e0 + j;
+          if (e < H) {
+            while (e == s_start[c + 1]) { ob4[(size_t)c * D4 + d] = acc; acc = make_float4(0.f, 0.f, 0.f, 0.f); ++c; }
+            const float al = s_a[s_perm[e]];
+            acc.x += al * v[j].x; acc.y += al * v[j].y; acc.z += al * v[j].z; acc.w += al * v[j].w;
+          }
+        }
+      }
+      for (; c < C1; ++c) { ob4[(size_t)c * D4 + d] = acc; acc = make_float4(0.f, 0.f, 0.f, 0.f); }
+    }
+    return;
+  }
   for (int d = tid; d < D; d += 256) {
     // one pass over the slots in cluster order, eight feature rows in flight; a cluster's sum is stored when the
     // next cluster starts (empty clusters store 0); same summation order as a per-cluster loop
@@ -307,6 +334,15 @@ __global__ void __launch_bounds__(256) cluster_intra_bwd_a_kernel(const float* _
     const float* gh = g + ((size_t)b * H + h) * D;
     float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;          // four independent partial sums (fixed combination order)
     int d = lane;
+    if ((D & 3) == 0 && dev_al16(dintra) && dev_al16(g)) {      // 16-byte loads, lane partials per component
+      const float4* di4 = reinterpret_cast<const float4*>(di);
+      const float4* gh4 = reinterpret_cast<const float4*>(gh);
+      for (int q = lane; q < (D >> 2); q += 32) {
+        const float4 x = __ldg(di4 + q), y = __ldg(gh4 + q);
+        v0 += x.x * y.x; v1 += x.y * y.y; v2 += x.z * y.z; v3 += x.w * y.w;
+      }
+      d = D;
+    }
     for (; d + 96 < D; d += 128) {
       v0 += di[d] * gh[d]; v1 += di[d + 32] * gh[d + 32]; v2 += di[d + 64] * gh[d + 64]; v3 += di[d + 96] * gh[d + 96];
     }
@@ -353,6 +389,21 @@ __global__ void __launch_bounds__(256) cluster_intra_bwd_b_kernel(const float* _
     float acc = 0.f;
     for (int k = 0; k < n; ++k) acc += da_ws[((size_t)b * n + k) * H + h] * Qp[((size_t)b * n + k) * Au + a];
     dKp[(size_t)bh * Au + a] = acc;
+  }
+  if ((D & 3) == 0 && dev_al16(dintra) && dev_al16(dg)) {
+    const int D4 = D >> 2;
+    for (int d = tid; d < D4; d += 256) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < n; ++k) {
+        const float al = alpha[((size_t)b * n + k) * H + h];
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dintra + (((size_t)b * n + k) * C1 + c) * D) + d);
+        acc.x += al * v.x; acc.y += al * v.y; acc.z += al * v.z; acc.w += al * v.w;
+      }
+      float4* o = reinterpret_cast<float4*>(dg + (size_t)bh * D) + d;
+      if (accumulate_dg) { const float4 p = *o; acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w; }
+      *o = acc;
+    }
+    return;
   }
   for (int d = tid; d < D; d += 256) {
     float acc = 0.f;

@@ -502,10 +502,11 @@ def test_graph_build_bit_exact_and_aggregate(cuda):
     assert (ob.view(2, Gb, 40).double() - torch.bmm(gb.double(), xb.double())).abs().max() < 1e-5
 
 
-def test_cluster_intra_attention(cuda):
+@pytest.mark.parametrize('D', [900, 50])           # 16-byte feature loads / scalar path (D % 4 != 0)
+def test_cluster_intra_attention(cuda, D):
     ops = _ops()
     g = torch.Generator().manual_seed(11)
-    B, n, H, Au, D, C1 = 5, 3, 50, 225, 900, 19
+    B, n, H, Au, C1 = 5, 3, 50, 225, 19
     Kp = torch.randn(B, H, Au, generator=g) / 4
     Qp = torch.randn(B, n, Au, generator=g) / 4
     gf = torch.randn(B, H, D, generator=g)
