@@ -506,6 +506,42 @@ __global__ void tc_splitk_reduce_kernel(const float* __restrict__ partial, int K
   for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * M + m) * N + n];
   epi_store(epi, m, n, acc);
 }
+// N % 4 == 0: a thread combines four adjacent outputs with 16-byte loads, four splits in flight; the splits are added in
+// the same ascending order as above (same bits), the epilogue is the 4-wide one of the main kernel
+__global__ void __launch_bounds__(256) tc_splitk_reduce4_kernel(const float* __restrict__ partial, int K, const int32_t* __restrict__ k_dev,
+                                                                int kelem, int chain_kb, int M, int N, const int32_t* __restrict__ m_dev,
+                                                                EpiP epi) {
+  if (m_dev) M = min(M, *m_dev);
+  if (k_dev) K = min(K, *k_dev);
+  const int nkb = (K + kelem - 1) / kelem;
+  const int splits = max(1, (nkb + chain_kb - 1) / chain_kb);
+  const int N4 = N >> 2;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)M * N4) return;
+  const int m = (int)(i / N4), n = (int)(i - (size_t)m * N4) * 4;
+  const size_t plane = (size_t)M * N;
+  const float* src = partial + (size_t)m * N + n;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int s = 0;
+  for (; s + 4 <= splits; s += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(s + u) * plane));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+  }
+  for (; s < splits; ++s) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)s * plane));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  float o[4] = {acc.x, acc.y, acc.z, acc.w};
+  float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (epi.bias && (epi.epilogue == NNR_EPI_BIAS || epi.epilogue == NNR_EPI_BIAS_TANH || epi.epilogue == NNR_EPI_BIAS_RELU_RES))
+    ld4(epi.bias + n, 4, bias4);
+  Epi4In in;
+  epi_load4(epi, m, n, 4, in, epi.epilogue == NNR_EPI_GATE ? __ldg(epi.rowmap + m) : 0);
+  epi_finish4(epi, m, n, o, 4, bias4, in);
+}
 
 // ------------------------------------------------------------------------------------------------
 // pre-pass: row-major X[R, C] (ld) -> planes.  TF32: fp32 [2][R][Cp] (hi, lo).  BF16: bf16 [1][R][Cp].
@@ -986,8 +1022,12 @@ static int run_tc(const nnr_gemm_args* a, cudaStream_t st) {
   if (pl.split_k) {
     size_t tot = (size_t)a->M * a->N;
     void* ph2 = nnr_prof_begin(2, 0.0, st);
-    tc_splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p.partial, a->K, a->k_dev, pl.kelem, pl.chain_kb, a->M,
-                                                                          a->N, a->m_dev, p.epi);
+    if (a->N % 4 == 0 && nnr_aligned16(p.partial))
+      tc_splitk_reduce4_kernel<<<(unsigned)((tot / 4 + 255) / 256), 256, 0, st>>>(p.partial, a->K, a->k_dev, pl.kelem, pl.chain_kb, a->M,
+                                                                                 a->N, a->m_dev, p.epi);
+    else
+      tc_splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p.partial, a->K, a->k_dev, pl.kelem, pl.chain_kb, a->M,
+                                                                            a->N, a->m_dev, p.epi);
     nnr_prof_end(ph2, st);
     NNR_LAUNCH_CHECK("tc_splitk_reduce_kernel");
   }
