@@ -181,9 +181,9 @@ __global__ void news_fuse_split_kernel(const float* __restrict__ dout, int D2, i
     else d_b[(size_t)r * D2 + d - D2] = v;
   }
 }
-// one block per table row, 32 warps.  Warp w walks news rows [w*span, (w+1)*span) four at a time: the four index loads
-// and then the (warp-uniformly predicated) row loads are issued together, so a category that matches a large share of
-// the rows (e.g. the padding category of the history) costs pipelined loads rather than one exposed latency per match.
+// one block per table row, 32 warps.  Warp w owns news rows [w*span, (w+1)*span): a category that matches a large share
+// of the rows (e.g. the padding category of the history) costs pipelined loads rather than one exposed latency per match,
+// and rows that do not match cost one vote per 32.
 // Lane = embedding column; rows are accumulated in order and the 32 per-warp partials are combined in warp order:
 // deterministic, no atomics.
 #define NF_MAXE 64
@@ -199,23 +199,35 @@ __global__ void __launch_bounds__(NF_WARPS * 32) news_fuse_table_bwd_kernel(cons
   const int r_begin = w * span, r_end = min(N, r_begin + span);
   const bool c0 = lane < Edim, c1 = lane + 32 < Edim;
   float acc0 = 0.f, acc1 = 0.f;                       // columns lane and lane + 32
-  for (int r0 = r_begin; r0 < r_end; r0 += 4) {
-    bool hit[4];
-    float v0[4], v1[4];
+  // the lanes fetch 32 indices at a time (coalesced) and vote; only the matching rows are visited, four at a time with
+  // their row loads issued together, in ascending row order
+  for (int rb = r_begin; rb < r_end; rb += 32) {
+    const int rl = rb + lane;
+    unsigned m = __ballot_sync(0xffffffffu, rl < r_end && __ldg(idx + rl) == row);
+    while (m) {
+      int rr[4];
+      float v0[4], v1[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) hit[j] = (r0 + j < r_end) && (idx[r0 + j] == row);
+      for (int j = 0; j < 4; ++j) {
+        rr[j] = -1;
+        if (m) { const int b = __ffs(m) - 1; m &= m - 1; rr[j] = rb + b; }
+      }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float* src = dout + (size_t)(r0 + j) * Dout + col0;
-      v0[j] = (hit[j] && c0) ? src[lane] : 0.f;
-      v1[j] = (hit[j] && c1) ? src[lane + 32] : 0.f;
-    }
+      for (int j = 0; j < 4; ++j) {
+        v0[j] = 0.f; v1[j] = 0.f;
+        if (rr[j] >= 0) {
+          const float* src = dout + (size_t)rr[j] * Dout + col0;
+          if (c0) v0[j] = src[lane];
+          if (c1) v1[j] = src[lane + 32];
+        }
+      }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (hit[j]) {
-        const uint64_t base = (uint64_t)(r0 + j) * Etot + eoff;
-        if (c0) acc0 += v0[j] * dropout_scale(seed, base + lane, p, inv_keep);
-        if (c1) acc1 += v1[j] * dropout_scale(seed, base + lane + 32, p, inv_keep);
+      for (int j = 0; j < 4; ++j) {
+        if (rr[j] >= 0) {
+          const uint64_t base = (uint64_t)rr[j] * Etot + eoff;
+          if (c0) acc0 += v0[j] * dropout_scale(seed, base + lane, p, inv_keep);
+          if (c1) acc1 += v1[j] * dropout_scale(seed, base + lane + 32, p, inv_keep);
+        }
       }
     }
   }
