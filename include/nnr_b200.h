@@ -144,7 +144,7 @@ int nnr_relu_bwd_split_colsum(const float* dy, const float* relu_out, int64_t ld
                               uint64_t seed, float* dy_dropped, int algo, void* planes, size_t planes_bytes,
                               float* colsum, int accumulate, void* workspace, size_t workspace_bytes,
                               void* stream);
-/* the algorithm NNR_GEMM_AUTO resolves to (env NNR_GEMM_ALGO = simt | tf32x3 | bf16; default tf32x3) */
+/* the algorithm NNR_GEMM_AUTO resolves to (env NNR_GEMM_ALGO = simt | tf32x3 | bf16 | bf16x3; default bf16x3) */
 int nnr_gemm_default_algo(void);
 
 /* column sums: out[n] (+)= sum_m X[m,n]   (bias gradients; deterministic two-stage)            */
