@@ -51,6 +51,19 @@ def _param_grads(P, names, G):
     return tuple(G[k] for k in names)
 
 
+_SHARE_SPLITS = os.environ.get('NNR_SHARE_SPLITS', '1') != '0'   # A/B switch: split small operands once per tensor
+
+
+def _shared_split(x, rows, cols, colsum_out=None):
+    """operand planes of a small activation that feeds two GEMMs (and, with ``colsum_out``, its column sums = a bias
+    gradient); NNR_SHARE_SPLITS=0 restores one split per GEMM call"""
+    if _SHARE_SPLITS:
+        return ops.tc_split(x, rows, cols, x.stride(0), colsum_out=colsum_out)
+    if colsum_out is not None:
+        ops.colsum(x, x.stride(0), rows, cols, colsum_out, False, None)
+    return None
+
+
 _FUSE_SUE_BWD = os.environ.get('NNR_FUSE_SUE_BWD', '1') != '0'     # A/B switch for the fused relu-backward split
 
 
@@ -367,12 +380,16 @@ class CNEFunction(torch.autograd.Function):
                                   scale=scale, alpha=m.alpha_cross, dpooled=d_out[x], lddp=D2, dX=m.dhg, lddx=D2,
                                   accumulate_dx=False, dqvec=dqk, lddq=D2)
                 dhg_written[x] = True
-                dq = linear(dqk, P[ca + 'K.weight'], N)                                      # [N,A] = dqk K^T
-                G[ca + 'K.weight'] = wgrad(m.q, dqk, N, A, D2)                                # q^T dqk
-                G[ca + 'Q.weight'] = wgrad(dq, m.other_self, N, A, D2)
-                G[ca + 'Q.bias'] = colsum(dq, N, A)
+                dqk_pl = _shared_split(dqk, N, D2)                                         # dqk and dq feed two GEMMs each:
+                dq = linear(dqk, P[ca + 'K.weight'], N, x_planes=dqk_pl)                      # [N,A] = dqk K^T
+                G[ca + 'K.weight'] = wgrad(m.q, dqk, N, A, D2, x_planes=dqk_pl)               # q^T dqk
+                dbq = _empty((A,), dev)
+                dq_pl = _shared_split(dq, N, A, colsum_out=dbq)                             # one split (+ the bias gradient)
+                G[ca + 'Q.weight'] = wgrad(dq, m.other_self, N, A, D2, dy_planes=dq_pl)
+                G[ca + 'Q.bias'] = dbq
                 # d(other self) = dq Q + its own output gradient
-                new_d_self[other[x]] = matmul_nn(dq, P[ca + 'Q.weight'], N, epilogue=EPI_ADD_AUX, aux=d_out[other[x]], ldaux=D2)
+                new_d_self[other[x]] = matmul_nn(dq, P[ca + 'Q.weight'], N, epilogue=EPI_ADD_AUX, aux=d_out[other[x]], ldaux=D2,
+                                                 x_planes=dq_pl)
             d_self = new_d_self
         # 3. self attention backward
         for x, m in mods.items():
@@ -413,9 +430,11 @@ class CNEFunction(torch.autograd.Function):
                              x_planes=dz_pl)
             G[x + '_H.weight'] = wgrad(dz, m.h, m.cap, D2, D2, k_dev=m.ntok, dy_planes=dz_pl, x_planes=m.h_pl)
             m.h_pl = None
-            G[x + '_M.weight'] = wgrad(dmproj, m.cm_sel, N, D2, D2)
-            G[x + '_M.bias'] = colsum(dmproj, N, D2)
-            d_cm_sel[x] = matmul_nn(dmproj, P[x + '_M.weight'], N)                            # grad of cn_other[partner]
+            dbm = _empty((D2,), dev)
+            dmproj_pl = _shared_split(dmproj, N, D2, colsum_out=dbm)                       # shared by both GEMMs, + bias gradient
+            G[x + '_M.weight'] = wgrad(dmproj, m.cm_sel, N, D2, D2, dy_planes=dmproj_pl)
+            G[x + '_M.bias'] = dbm
+            d_cm_sel[x] = matmul_nn(dmproj, P[x + '_M.weight'], N, x_planes=dmproj_pl)        # grad of cn_other[partner]
             del dz, dh0, dz_pl
         # partner_t and partner_c are inverse permutations of each other
         if gate:
@@ -635,11 +654,16 @@ class SUEFunction(torch.autograd.Function):
             ops.attn_pool_bwd(X=f, ldx=D, D=D, S=B * n, max_len=C1, mode=1, fixed_len=C1, qvec=qk2, ldq=D, scale=scale,
                               mask=cm, alpha=alpha2, dpooled=duser, lddp=D, dX=df, lddx=D, accumulate_dx=False,
                               dqvec=dqk2, lddq=D)
-            dq2 = linear(dqk2, P['interClusterAttention.K.weight'], B * n)                   # [B*n, Au]
-            G['interClusterAttention.K.weight'] = wgrad(q2, dqk2, B * n, Au, D)
-            G['interClusterAttention.Q.weight'] = wgrad(dq2, cand.view(B * n, D), B * n, Au, D)
-            G['interClusterAttention.Q.bias'] = colsum(dq2, B * n, Au)
-            dcand = matmul_nn(dq2, P['interClusterAttention.Q.weight'], B * n)               # [B*n, D]
+            cand2 = cand.view(B * n, D)
+            cand_pl = _shared_split(cand2, B * n, D)                                       # operands used by two GEMMs each are
+            dqk2_pl = _shared_split(dqk2, B * n, D)                                        # split once
+            dq2 = linear(dqk2, P['interClusterAttention.K.weight'], B * n, x_planes=dqk2_pl)  # [B*n, Au]
+            G['interClusterAttention.K.weight'] = wgrad(q2, dqk2, B * n, Au, D, x_planes=dqk2_pl)
+            dbq2 = _empty((Au,), dev)
+            dq2_pl = _shared_split(dq2, B * n, Au, colsum_out=dbq2)
+            G['interClusterAttention.Q.weight'] = wgrad(dq2, cand2, B * n, Au, D, dy_planes=dq2_pl, x_planes=cand_pl)
+            G['interClusterAttention.Q.bias'] = dbq2
+            dcand = matmul_nn(dq2, P['interClusterAttention.Q.weight'], B * n, x_planes=dq2_pl)   # [B*n, D]
             # cluster affine backward: f = (relu(W intra + b) + intra) * drop
             db_f = _empty((D,), dev)
             if _fused_relu_bwd(df, D):
@@ -662,11 +686,14 @@ class SUEFunction(torch.autograd.Function):
             dKp, dQp = _empty((B * H, Au), dev), _empty((B * n, Au), dev)
             dg = _empty((B * H, D), dev)
             ops.cluster_intra_bwd(dintra, Kp, Qp, gfeat, cidx, alpha, B, n, H, Au, D, C1, scale, da_ws, dKp, dQp, dg, False)
-            G['intraCluster_K.weight'] = wgrad(dKp, gfeat.view(B * H, D), B * H, Au, D)
-            matmul_nn(dKp, P['intraCluster_K.weight'], B * H, out=dg, accumulate=True)
-            G['intraCluster_Q.weight'] = wgrad(dQp, cand.view(B * n, D), B * n, Au, D)
-            G['intraCluster_Q.bias'] = colsum(dQp, B * n, Au)
-            matmul_nn(dQp, P['intraCluster_Q.weight'], B * n, out=dcand, accumulate=True)
+            dKp_pl = _shared_split(dKp, B * H, Au)
+            G['intraCluster_K.weight'] = wgrad(dKp, gfeat.view(B * H, D), B * H, Au, D, dy_planes=dKp_pl)
+            matmul_nn(dKp, P['intraCluster_K.weight'], B * H, out=dg, accumulate=True, x_planes=dKp_pl)
+            dbq = _empty((Au,), dev)
+            dQp_pl = _shared_split(dQp, B * n, Au, colsum_out=dbq)
+            G['intraCluster_Q.weight'] = wgrad(dQp, cand2, B * n, Au, D, dy_planes=dQp_pl, x_planes=cand_pl)
+            G['intraCluster_Q.bias'] = dbq
+            matmul_nn(dQp, P['intraCluster_Q.weight'], B * n, out=dcand, accumulate=True, x_planes=dQp_pl)
         if not meta.get('gcn', True):                  # SUE_wo_GCN: gfeat is the history embedding itself
             G['intraCluster_K.bias'] = torch.zeros_like(P['intraCluster_K.bias'])
             ctx.sv = None
