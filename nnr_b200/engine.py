@@ -258,7 +258,8 @@ def _cne_gate_self(P, x, m, m_other_cn, partner, N, Hd, A, gate=True):
     if gate:
         m.partner = partner
         m.cm_sel = m_other_cn.index_select(0, partner)                                            # [N, 2H]
-        m.mproj = linear(m.cm_sel, P[x + '_M.weight'], N, None, P[x + '_M.bias'])                 # [N, 2H]
+        m.cm_sel_pl = _shared_split(m.cm_sel, N, D2)
+        m.mproj = linear(m.cm_sel, P[x + '_M.weight'], N, None, P[x + '_M.bias'], x_planes=m.cm_sel_pl)   # [N, 2H]
         m.g = _empty((m.cap, D2), dev)
         m.h_pl = split_tokens(m.h, m.cap, D2, m.ntok)
         m.hg = linear(m.h, P[x + '_H.weight'], m.cap, m.ntok, None, EPI_GATE, rowbias=m.mproj, ldrowbias=D2,
@@ -280,8 +281,10 @@ def _cne_cross(P, x, m, other_self, N, Hd, A):
     D2 = 2 * Hd
     ca = x + '_cross_attention.'
     m.other_self = other_self
-    m.q = linear(other_self, P[ca + 'Q.weight'], N, None, P[ca + 'Q.bias'])                    # [N, A]
-    m.qk = matmul_nn(m.q, P[ca + 'K.weight'], N)                                               # [N, 2H] = q K
+    m.other_self_pl = _shared_split(other_self, N, D2)          # planes kept for the weight-gradient GEMMs of the backward
+    m.q = linear(other_self, P[ca + 'Q.weight'], N, None, P[ca + 'Q.bias'], x_planes=m.other_self_pl)   # [N, A]
+    m.q_pl = _shared_split(m.q, N, A)
+    m.qk = matmul_nn(m.q, P[ca + 'K.weight'], N, x_planes=m.q_pl)                              # [N, 2H] = q K
     m.cross_out = _empty((N, D2), dev)
     m.alpha_cross = _empty((m.cap,), dev)
     ops.attn_pool_fwd(X=m.hg, ldx=D2, D=D2, S=N, max_len=m.L, mode=1, seg_off=m.off, seg_order=m.order, qvec=m.qk, ldq=D2,
@@ -382,10 +385,10 @@ class CNEFunction(torch.autograd.Function):
                 dhg_written[x] = True
                 dqk_pl = _shared_split(dqk, N, D2)                                         # dqk and dq feed two GEMMs each:
                 dq = linear(dqk, P[ca + 'K.weight'], N, x_planes=dqk_pl)                      # [N,A] = dqk K^T
-                G[ca + 'K.weight'] = wgrad(m.q, dqk, N, A, D2, x_planes=dqk_pl)               # q^T dqk
+                G[ca + 'K.weight'] = wgrad(m.q, dqk, N, A, D2, dy_planes=m.q_pl, x_planes=dqk_pl)   # q^T dqk
                 dbq = _empty((A,), dev)
                 dq_pl = _shared_split(dq, N, A, colsum_out=dbq)                             # one split (+ the bias gradient)
-                G[ca + 'Q.weight'] = wgrad(dq, m.other_self, N, A, D2, dy_planes=dq_pl)
+                G[ca + 'Q.weight'] = wgrad(dq, m.other_self, N, A, D2, dy_planes=dq_pl, x_planes=m.other_self_pl)
                 G[ca + 'Q.bias'] = dbq
                 # d(other self) = dq Q + its own output gradient
                 new_d_self[other[x]] = matmul_nn(dq, P[ca + 'Q.weight'], N, epilogue=EPI_ADD_AUX, aux=d_out[other[x]], ldaux=D2,
@@ -432,7 +435,7 @@ class CNEFunction(torch.autograd.Function):
             m.h_pl = None
             dbm = _empty((D2,), dev)
             dmproj_pl = _shared_split(dmproj, N, D2, colsum_out=dbm)                       # shared by both GEMMs, + bias gradient
-            G[x + '_M.weight'] = wgrad(dmproj, m.cm_sel, N, D2, D2, dy_planes=dmproj_pl)
+            G[x + '_M.weight'] = wgrad(dmproj, m.cm_sel, N, D2, D2, dy_planes=dmproj_pl, x_planes=m.cm_sel_pl)
             G[x + '_M.bias'] = dbm
             d_cm_sel[x] = matmul_nn(dmproj, P[x + '_M.weight'], N, x_planes=dmproj_pl)        # grad of cn_other[partner]
             del dz, dh0, dz_pl
@@ -598,8 +601,10 @@ class SUEFunction(torch.autograd.Function):
         scale = 1.0 / math.sqrt(float(Au))
         # (an intraCluster_K.bias -- SUE_wo_GCN only -- shifts every score of a (user, candidate) pair equally and
         #  cancels in the per-cluster softmax: it is not applied, and its gradient is exactly zero)
-        Kp = linear(gfeat.view(B * H, D), P['intraCluster_K.weight'], B * H)
-        Qp = linear(cand.view(B * n, D), P['intraCluster_Q.weight'], B * n, None, P['intraCluster_Q.bias'])
+        gfeat_pl = _shared_split(gfeat.view(B * H, D), B * H, D)   # gfeat, cand, q2: split once for the forward GEMMs and the
+        cand_pl = _shared_split(cand.view(B * n, D), B * n, D)     # weight-gradient GEMMs of the backward
+        Kp = linear(gfeat.view(B * H, D), P['intraCluster_K.weight'], B * H, x_planes=gfeat_pl)
+        Qp = linear(cand.view(B * n, D), P['intraCluster_Q.weight'], B * n, None, P['intraCluster_Q.bias'], x_planes=cand_pl)
         alpha = _empty((B * n, H), dev)
         intra = _empty((B * n * C1, D), dev)
         cidx = cidx.contiguous()
@@ -609,14 +614,16 @@ class SUEFunction(torch.autograd.Function):
         f = linear(intra, P['clusterFeatureAffine.weight'], B * n * C1, None, P['clusterFeatureAffine.bias'],
                    EPI_BIAS_RELU_RES, aux=intra, ldaux=D, aux_out=r_f, ldaux_out=D, p_drop=pe, seed=seeds[L + 1],
                    x_planes=intra_pl)
-        q2 = linear(cand.view(B * n, D), P['interClusterAttention.Q.weight'], B * n, None, P['interClusterAttention.Q.bias'])
-        qk2 = matmul_nn(q2, P['interClusterAttention.K.weight'], B * n)
+        q2 = linear(cand.view(B * n, D), P['interClusterAttention.Q.weight'], B * n, None, P['interClusterAttention.Q.bias'],
+                    x_planes=cand_pl)
+        q2_pl = _shared_split(q2, B * n, Au)
+        qk2 = matmul_nn(q2, P['interClusterAttention.K.weight'], B * n, x_planes=q2_pl)
         cm = cmask.unsqueeze(1).expand(-1, n, -1).contiguous().view(torch.uint8)             # [B,n,C1]
         user = _empty((B * n, D), dev)
         alpha2 = _empty((B * n * C1,), dev)
         ops.attn_pool_fwd(X=f, ldx=D, D=D, S=B * n, max_len=C1, mode=1, fixed_len=C1, qvec=qk2, ldq=D, scale=scale,
                           mask=cm, pooled=user, ldp=D, alpha=alpha2)
-        ctx.sv = (Kp, Qp, alpha, intra, r_f, f, q2, qk2, cm, alpha2, cidx, Au, scale, intra_pl)
+        ctx.sv = (Kp, Qp, alpha, intra, r_f, f, q2, qk2, cm, alpha2, cidx, Au, scale, intra_pl, (gfeat_pl, cand_pl, q2_pl))
         return user.view(B, n, D)
 
 
@@ -646,7 +653,7 @@ class SUEFunction(torch.autograd.Function):
             G['attention.affine1.weight'] = wgrad(dU, gfeat.view(B * H, D), B * H, A, D)
             G['attention.affine1.bias'] = colsum(dU, B * H, A)
         else:
-            Kp, Qp, alpha, intra, r_f, f, q2, qk2, cm, alpha2, cidx, Au, scale, intra_pl = ctx.sv
+            Kp, Qp, alpha, intra, r_f, f, q2, qk2, cm, alpha2, cidx, Au, scale, intra_pl, (gfeat_pl, cand_pl, q2_pl) = ctx.sv
             duser = duser.contiguous().view(B * n, D)
             # inter-cluster attention backward
             df = _empty((B * n * C1, D), dev)
@@ -655,10 +662,9 @@ class SUEFunction(torch.autograd.Function):
                               mask=cm, alpha=alpha2, dpooled=duser, lddp=D, dX=df, lddx=D, accumulate_dx=False,
                               dqvec=dqk2, lddq=D)
             cand2 = cand.view(B * n, D)
-            cand_pl = _shared_split(cand2, B * n, D)                                       # operands used by two GEMMs each are
-            dqk2_pl = _shared_split(dqk2, B * n, D)                                        # split once
+            dqk2_pl = _shared_split(dqk2, B * n, D)                                        # operands used by two GEMMs: one split
             dq2 = linear(dqk2, P['interClusterAttention.K.weight'], B * n, x_planes=dqk2_pl)  # [B*n, Au]
-            G['interClusterAttention.K.weight'] = wgrad(q2, dqk2, B * n, Au, D, x_planes=dqk2_pl)
+            G['interClusterAttention.K.weight'] = wgrad(q2, dqk2, B * n, Au, D, dy_planes=q2_pl, x_planes=dqk2_pl)
             dbq2 = _empty((Au,), dev)
             dq2_pl = _shared_split(dq2, B * n, Au, colsum_out=dbq2)
             G['interClusterAttention.Q.weight'] = wgrad(dq2, cand2, B * n, Au, D, dy_planes=dq2_pl, x_planes=cand_pl)
@@ -687,7 +693,7 @@ class SUEFunction(torch.autograd.Function):
             dg = _empty((B * H, D), dev)
             ops.cluster_intra_bwd(dintra, Kp, Qp, gfeat, cidx, alpha, B, n, H, Au, D, C1, scale, da_ws, dKp, dQp, dg, False)
             dKp_pl = _shared_split(dKp, B * H, Au)
-            G['intraCluster_K.weight'] = wgrad(dKp, gfeat.view(B * H, D), B * H, Au, D, dy_planes=dKp_pl)
+            G['intraCluster_K.weight'] = wgrad(dKp, gfeat.view(B * H, D), B * H, Au, D, dy_planes=dKp_pl, x_planes=gfeat_pl)
             matmul_nn(dKp, P['intraCluster_K.weight'], B * H, out=dg, accumulate=True, x_planes=dKp_pl)
             dbq = _empty((Au,), dev)
             dQp_pl = _shared_split(dQp, B * n, Au, colsum_out=dbq)
