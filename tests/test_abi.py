@@ -45,6 +45,34 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert _lib.lib.nnr_gemm(ctypes.byref(a), None) < 0
 
 
+def test_plane_producing_entry_points_validate_arguments_without_a_gpu():
+    """the entry points that hand their result to nnr_gemm as operand planes (ABI 4): bad arguments are reported, the
+    capability query answers from the configuration alone"""
+    from nnr_b200 import _lib
+    L = _lib.lib
+    assert L.nnr_embed_gather_planes_fwd(None, None, None, None, 0, 0, 0, 0, 0, 0.0, 0, 4, None, 0, None) < 0
+    assert b'nnr_embed_gather_planes_fwd' in L.nnr_last_error()
+    assert L.nnr_lstm_shift_h_planes(None, None, None, None, 0, 0, 0, 0, 4, None, 0, None) < 0
+    assert L.nnr_gate_bwd_planes(None, None, None, None, 0, 0, 0, 4, None, 0, None, None, 0, None) < 0
+    assert L.nnr_relu_bwd_split_colsum(None, None, 0, 0, 0, 0.0, 0, None, 4, None, 0, None, 0, None, 0, None) < 0
+    assert L.nnr_gcn_aggregate_add(None, None, None, None, 0, 0, 0, None, None, None) < 0
+    assert L.nnr_lstm_bwd_planes(None, None, None, None, None, None, 0, 0, 200, None, None, None, 0, 4, None, 0, None, None, 0, None) < 0
+    assert L.nnr_lstm_bwd_planes_supported(200, 4) in (0, 1)          # 1 unless NNR_LSTM_ALGO=ffma
+    assert L.nnr_lstm_bwd_planes_supported(128, 4) == 0               # only hidden_dim 200 is instantiated
+    assert L.nnr_lstm_bwd_planes_supported(200, 1) == 0               # the exact-fp32 GEMM has no operand planes
+    assert L.nnr_lstm_bwd_planes_workspace_bytes(3520, 200) == 110 * 1600 * 4
+    # a GEMM whose operand exists only as planes cannot run on the exact-fp32 kernel
+    a = _lib.GemmArgs()
+    a.M, a.N, a.K = 64, 64, 64
+    a.lda = a.ldb = a.ldc = 64
+    a.algo = 1
+    a.A_planes = 16
+    a.B = 16
+    a.C = 16
+    assert L.nnr_gemm(ctypes.byref(a), None) < 0
+    assert b'planes' in L.nnr_last_error()
+
+
 def test_ops_reject_cpu_tensors():
     import pytest
     import torch
