@@ -337,3 +337,17 @@ def test_loss_log_reads_every_step_in_order(cuda):
     got += log.drain()
     assert got == want and log.count == 11
     assert abs(log.total - 3.0 * sum(want)) < 1e-4
+
+
+def test_exact_fp32_gemm_variant_subprocess(cuda):
+    """NNR_GEMM_ALGO=simt (exact-fp32 FFMA GEMMs, no operand planes: the unfused gather / BPTT / gate-prologue / relu-backward
+    paths of engine.py) is read once per process: replay two goldens and the clip+Adam step in a child."""
+    import os, subprocess, sys
+    env = dict(os.environ, NNR_GEMM_ALGO='simt')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import torch, tests.test_model_gpu as t; d = torch.device('cuda:0'); "
+            "t.test_train_loss_and_gradients_match_reference_golden(d, 'tiny'); "
+            "t.test_train_loss_and_gradients_match_reference_golden(d, 'ablation'); "
+            "t.test_train_step_matches_oracle_clip_adam(d); print('simt-ok')")
+    r = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'simt-ok' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
