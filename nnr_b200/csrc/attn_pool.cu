@@ -12,8 +12,10 @@
 #include "../../include/nnr_b200.h"
 
 #define POOL_THREADS 128       // backward kernels
+#ifndef POOL_FWD_THREADS
 #define POOL_FWD_THREADS 256   // forward kernel (sweep on B200, fwd / bwd ms per step: 64 threads 0.417 / 0.399, 128: 0.256 / 0.305,
-                               // 256: 0.207 / 0.344)
+                               // 256: 0.207 / 0.344, 512: 0.250 / -)
+#endif
 
 __global__ void __launch_bounds__(POOL_FWD_THREADS) attn_pool_fwd_kernel(nnr_pool_args a) {
   extern __shared__ float sc[];  // [max_len]
