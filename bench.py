@@ -26,6 +26,16 @@ METRIC = 'cne_sue_train_impressions_per_sec'
 UNIT = 'impressions/s'
 
 
+def load_synthetic():
+    """nnr_b200/synthetic.py (numpy / torch-CPU only) loaded by path: importing it as ``nnr_b200.synthetic`` would run
+    the package __init__ and dlopen libnnr_b200.so, which the CPU reference arm must not touch"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('_nnr_synthetic_standalone', os.path.join(ROOT, 'nnr_b200', 'synthetic.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -36,10 +46,12 @@ def parse():
     ap.add_argument('--vocab', type=int, default=40000)
     ap.add_argument('--lengths', default='mind', choices=['mind', 'full', 'uniform'])
     ap.add_argument('--dropout', type=float, default=0.2)
-    ap.add_argument('--cpu-sample', type=int, default=32, help='impressions per step of the bounded CPU-baseline sample')
+    ap.add_argument('--cpu-sample', type=int, default=16, help='impressions per step of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true', help='skip the per-op CUDA-event breakdown')
     ap.add_argument('--gemm-detail', action='store_true', help='print the per-shape GEMM table to stderr')
+    ap.add_argument('--no-extras', action='store_true', help='skip the extra measurements (scoring, full-length regime)')
+    ap.add_argument('--scoring-news', type=int, default=100000, help='news in the synthetic corpus of the scoring extra')
     return ap.parse_args()
 
 
@@ -108,14 +120,38 @@ class Clocks:
 # -------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port of the reference, bounded sample, all host threads
 # -------------------------------------------------------------------------------------------------
-def cpu_train_step_rate(a, sample, steps=1, warmup=0):
+def cpu_dropout_masks(cfg, batch, p, gen):
+    """keep-masks (0 or 1/(1-p)) for the seven dropout sites of the reference CNE+SUE (newsEncoders.py:53,117-118,
+    userEncoders.py:80,91, layers.py:320-322; GCN inter-layer rate = p/2), drawn on the CPU like nn.Dropout does"""
+    def keep(shape, rate):
+        return torch.bernoulli(torch.full(shape, 1.0 - rate), generator=gen) / (1.0 - rate)
+    B, n = batch['news_title_text'].shape[:2]
+    H = batch['user_title_text'].shape[1]
+    E, T, A = cfg.word_embedding_dim, cfg.max_title_length, cfg.max_abstract_length
+    D = 4 * cfg.hidden_dim + cfg.category_embedding_dim + cfg.subCategory_embedding_dim
+    C = cfg.category_num
+
+    def cne(N, Bn, nn_):
+        return {'title': keep((N, T, E), p), 'content': keep((N, A, E), p),
+                'category': keep((Bn, nn_, cfg.category_embedding_dim), p), 'subCategory': keep((Bn, nn_, cfg.subCategory_embedding_dim), p)}
+    sue = {'proxy': keep((B, C, D), p), 'cluster': keep((B, n, C + 1, D), p)}
+    for l in range(cfg.gcn_layer_num - 1):
+        sue['gcn%d' % l] = keep((B, H + C, D), p / 2.0)
+    return {'news': cne(B * n, B, n), 'history': cne(B * H, B, H), 'sue': sue}
+
+
+def cpu_train_step_rate(a, sample, steps, warmup):
+    """`warmup` untimed + EXACTLY `steps` timed training steps (forward, loss, backward, clip_grad_norm_(4), Adam) of the
+    oracle port on `sample` impressions per step, same shapes / vocabulary / length regime / dropout as the GPU arm,
+    all host threads.  Returns (impressions/s, cores, seconds per step)."""
     from oracle import nnr_oracle as O
-    from nnr_b200.synthetic import SyntheticMIND
+    syn_mod = load_synthetic()
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    cfg = O.make_config(vocabulary_size=a.vocab, dropout_rate=0.0)
-    syn = SyntheticMIND(news_num=20000, vocabulary_size=a.vocab, lengths=a.lengths, seed=0)
+    cfg = O.make_config(vocabulary_size=a.vocab, dropout_rate=a.dropout)
+    syn = syn_mod.SyntheticMIND(news_num=20000, vocabulary_size=a.vocab, lengths=a.lengths, seed=0)
     torch.manual_seed(0)
+    gen = torch.Generator().manual_seed(1)
     p = {k: (torch.randn(s) * 0.05) for k, s in O.param_shapes(cfg).items()}
     p['news_encoder.word_embedding.weight'] = syn.word_table()
     state = {}
@@ -123,7 +159,8 @@ def cpu_train_step_rate(a, sample, steps=1, warmup=0):
     for i in range(warmup + steps):
         batch = syn.batch(sample, seed=100 + i)
         t0 = time.perf_counter()
-        _, loss, grads = O.forward_backward(p, cfg, batch, lstm_impl='aten')     # ATen packed LSTM = reference path
+        masks = cpu_dropout_masks(cfg, batch, a.dropout, gen) if a.dropout > 0 else None
+        _, loss, grads = O.forward_backward(p, cfg, batch, lstm_impl='aten', dropout_masks=masks)   # ATen packed LSTM = reference path
         O.clip_and_adam(p, grads, state, i + 1)
         dt = time.perf_counter() - t0
         if i >= warmup:
@@ -132,21 +169,119 @@ def cpu_train_step_rate(a, sample, steps=1, warmup=0):
     return sample / t, cores, t
 
 
+def cpu_sample_note(a, sample, steps, warmup, t):
+    return ('%d impressions per step (a bounded sample of the %d-impression batch; same shapes, vocabulary, length regime and '
+            'dropout %.2f), %d warm-up + %d timed train steps (fwd+bwd+clip+Adam) of the oracle port with the packed ATen LSTM, '
+            '%.2f s per step' % (sample, a.batch, a.dropout, warmup, steps, t))
+
+
 def run_reference(a):
+    """--impl reference: the reference's CPU path (oracle port; the reference is Python and cannot travel to the GPU box),
+    EXACTLY --steps timed and --warmup untimed steps, each on --cpu-sample impressions.  Imports neither the nnr_b200
+    package nor its shared library."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     sample = a.cpu_sample
-    rate, cores, t = cpu_train_step_rate(a, sample, steps=max(1, min(a.steps, 3)), warmup=min(a.warmup, 1))
+    rate, cores, t = cpu_train_step_rate(a, sample, steps=a.steps, warmup=a.warmup)
     line = {'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic', 'impl': 'reference',
-            'config': {'workload': workload_name(a), 'note': 'CPU only: oracle port of the reference PyTorch path'},
+            'config': {'workload': workload_name(a), 'impressions_per_step': sample, 'dropout': a.dropout,
+                       'note': 'CPU only: oracle port of the reference PyTorch path; each step is a bounded %d-impression '
+                               'sample of the workload (value is impressions/s, i.e. batch-normalised)' % sample},
             'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                             'sample': '%d impressions per step (train step: fwd+bwd+clip+Adam), packed ATen LSTM' % sample},
+                             'sample': cpu_sample_note(a, sample, a.steps, a.warmup, t)},
             'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
+
+
+# -------------------------------------------------------------------------------------------------
+# extra measurements printed on the same JSON line (N = 1 only)
+# -------------------------------------------------------------------------------------------------
+CNE_FWD_FLOP_PER_TOKEN = 960000 + 640000 + 320000 + 160000 + 800      # SURVEY 8d: W_ih, recurrent, gate, self-attn affine, folded cross scores
+
+
+def extra_scoring(a, cfg, model, dev, peaks):
+    """BASELINE config 3 / metric "scoring news-enc/sec" (reference path util.py:10-68): encode a synthetic corpus once
+    with the CNE kernels (eval), then SUE + click scores of impressions against the cached corpus."""
+    from nnr_b200.scoring import CorpusScorer
+    from nnr_b200.synthetic import SyntheticMIND
+    news, impressions, cands, chunk, batch = a.scoring_news, 4096, 37, 4096, 256
+    syn = SyntheticMIND(news_num=news, vocabulary_size=a.vocab, lengths=a.lengths, seed=5)
+    was_training = model.training
+    sc = CorpusScorer(model, syn.news_title_text, syn.news_title_mask, syn.news_abstract_text, syn.news_abstract_mask,
+                      syn.news_category, syn.news_subCategory, chunk=chunk)
+    sc.encode_corpus()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        sc.encode_corpus()
+    e1.record()
+    torch.cuda.synchronize()
+    enc_ms = e0.elapsed_time(e1) / reps
+    hist, hl, cand = syn.sample_behaviors(impressions, news_num=cands, seed=1)
+    hist, hl, cand = torch.from_numpy(hist).to(dev), torch.from_numpy(hl).to(dev), torch.from_numpy(cand).to(dev)
+
+    def run():
+        out = None
+        for i in range(0, impressions, batch):
+            out = sc.score(hist[i:i + batch], hl[i:i + batch], cand[i:i + batch])
+        return out
+    run()
+    torch.cuda.synchronize()
+    e0.record()
+    out = run()
+    e1.record()
+    torch.cuda.synchronize()
+    sc_ms = e0.elapsed_time(e1)
+    tokens = int(syn.title_len.sum() + syn.abstract_len.sum())
+    tflops = tokens * CNE_FWD_FLOP_PER_TOKEN / (enc_ms * 1e-3) / 1e12
+    if was_training:
+        model.train()
+    return {'metric': 'cne_scoring_news_enc_per_sec', 'value': news / (enc_ms * 1e-3), 'unit': 'news/s', 'encode_ms': enc_ms,
+            'corpus_news': news, 'corpus_tokens': tokens, 'tokens_per_sec': tokens / (enc_ms * 1e-3), 'chunk': chunk,
+            'scored_impressions_per_sec': impressions / (sc_ms * 1e-3), 'candidates_per_impression': cands, 'history': 50,
+            'score_ms': sc_ms, 'finite': bool(torch.isfinite(out).all()),
+            'roofline': {'bound': 'tensor', 'achieved': tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': tflops / peaks['bf16_tflops'],
+                         'mma_per_algorithmic_flop': 3, 'frac_of_peak_in_issued_mma': 3 * tflops / peaks['bf16_tflops'], 'traffic': None,
+                         'note': 'whole CNE forward (all kernels of encode_corpus): %d algorithmic flop per valid token (SURVEY 8d) / wall time'
+                                 % CNE_FWD_FLOP_PER_TOKEN}}
+
+
+def extra_full_lengths(a, ts, dev, peaks):
+    """the roofline worst case of SURVEY 8d: every title has 32 and every abstract 128 valid tokens (563 200 tokens per step)"""
+    from nnr_b200 import profiler
+    from nnr_b200.synthetic import SyntheticMIND, batch_args
+    syn = SyntheticMIND(news_num=20000, vocabulary_size=a.vocab, lengths='full', seed=0)
+    devb = [batch_args(syn.batch(a.batch, seed=50 + i), dev) for i in range(2)]
+    for i in range(3):
+        ts.step(*devb[i % 2])
+    torch.cuda.synchronize()
+    steps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        ts.step(*devb[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    with profiler.capture() as prof:
+        ts.step(*devb[0])
+        torch.cuda.synchronize()
+    bd = prof.summary(steps=1)
+    out = {'workload': workload_name(a).replace('%s_lengths' % a.lengths, 'full_lengths'), 'value': a.batch / (ms * 1e-3), 'unit': UNIT,
+           'ms_per_step': ms, 'steps': steps, 'warmup': 3, 'tokens_per_step': a.batch * 55 * 160}
+    rows = {r['kernel']: r for r in profiler.roofline_table(bd, ROOT)}
+    for k in ('gemm_tc_kernel', 'lstm_fwd', 'lstm_bwd', 'embed_gather_fwd', 'embed_gather_bwd', 'attn_pool_fwd', 'attn_pool_bwd'):
+        if k in rows:
+            out[k] = {kk: rows[k][kk] for kk in ('ms', 'achieved', 'unit', 'frac') if kk in rows[k]}
+            if 'frac_of_peak_in_issued_mma' in rows[k]:
+                out[k]['frac_of_peak_in_issued_mma'] = rows[k]['frac_of_peak_in_issued_mma']
+    return out
 
 
 # -------------------------------------------------------------------------------------------------
@@ -305,9 +440,14 @@ def main():
 
     cpu = None
     if not a.no_cpu_baseline and world == 1:
-        rate, cores, tcpu = cpu_train_step_rate(a, a.cpu_sample, steps=2, warmup=1)
-        cpu = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-               'sample': '%d impressions per step, 1 warm-up + 2 timed train steps (fwd+bwd+clip+Adam) of the oracle port, %.1f s per step' % (a.cpu_sample, tcpu)}
+        rate, cores, tcpu = cpu_train_step_rate(a, a.cpu_sample, steps=3, warmup=1)
+        cpu = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': cpu_sample_note(a, a.cpu_sample, 3, 1, tcpu)}
+    extra = {}
+    if world == 1 and not a.no_extras:
+        from nnr_b200 import profiler as _prof
+        peaks = _prof.measured_peaks(ROOT)
+        extra['full_lengths'] = extra_full_lengths(a, ts, dev, peaks)
+        extra['scoring'] = extra_scoring(a, cfg, model, dev, peaks)
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
@@ -324,7 +464,8 @@ def main():
                                'corpus_bytes_resident': corpus.nbytes(),
                                'note': 'nnr_b200.corpus.DeviceCorpus + TrainStep.step_ids: ids in, batch gathered and graph built on the device'},
             'gpu_launches': int(launches),
-            'roofline': roofline, 'roofline_by_kernel': roofline_table, 'cpu_baseline': cpu, 'breakdown_ms_per_step': breakdown}
+            'roofline': roofline, 'roofline_by_kernel': roofline_table, 'cpu_baseline': cpu, 'extra': extra,
+            'breakdown_ms_per_step': breakdown}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -191,6 +191,15 @@ def _ncu_traffic(root, kernel):
     return entry['dram_bytes_per_launch'] if entry else None
 
 
+def _ncu_traffic_source(root, kernel):
+    path = os.path.join(root, 'profiles', 'traffic.json')
+    if not os.path.isfile(path):
+        return None
+    with open(path) as f:
+        entry = json.load(f).get(kernel)
+    return ('static: ' + entry['source']) if entry else None
+
+
 def roofline(breakdown, tokens_per_step, batch, root):
     """roofline entry for the dominant op of the step (largest share of device time)"""
     if not breakdown:
@@ -209,14 +218,16 @@ def roofline(breakdown, tokens_per_step, batch, root):
             peaks['source'], peaks['bf16_tflops'], ' x 0.5 (kind::tf32)' if tf32 else '')
         products = 3 if algo in (ops.ALGO_TF32X3, ops.ALGO_BF16X3) and name == 'gemm_tc_kernel' else 1
         return {'kernel': name, 'bound': 'tensor', 'achieved': top['tflops'], 'peak': peak, 'unit': 'TFLOP/s',
-                'frac': top['tflops'] / peak, 'traffic': traffic, 'share_of_step': top['ms'] / total,
+                'frac': top['tflops'] / peak, 'traffic': traffic, 'traffic_source': _ncu_traffic_source(root, name),
+                'share_of_step': top['ms'] / total,
                 'gemm_algo': {1: 'simt', 2: 'tf32x3', 3: 'bf16', 4: 'bf16x3'}.get(algo, str(algo)), 'peak_note': note,
                 # fp32-grade results on 16-bit tensor cores cost `products` MMAs per algorithmic flop: the fraction of
                 # the tensor pipe's measured peak that the kernel actually sustains is products x frac
                 'mma_per_algorithmic_flop': products, 'frac_of_peak_in_issued_mma': products * top['tflops'] / peak}
     if 'gbs' in top:
         return {'kernel': name, 'bound': 'hbm', 'achieved': top['gbs'], 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                'frac': top['gbs'] / peaks['hbm_gbs'], 'traffic': traffic, 'share_of_step': top['ms'] / total,
+                'frac': top['gbs'] / peaks['hbm_gbs'], 'traffic': traffic, 'traffic_source': _ncu_traffic_source(root, name),
+                'share_of_step': top['ms'] / total,
                 'peak_note': '%s HBM copy bandwidth' % peaks['source']}
     return {'kernel': name, 'bound': 'hbm', 'achieved': None, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': None,
             'traffic': traffic, 'share_of_step': top['ms'] / total}
