@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NNR_ABI_VERSION 4
+#define NNR_ABI_VERSION 5
 
 const char* nnr_last_error(void);
 int nnr_abi_version(void);
@@ -252,6 +252,29 @@ int nnr_news_fuse_bwd(const float* dout, const int32_t* cat, const int32_t* sub,
 int nnr_sue_graph_build(const int32_t* categories, const int32_t* history_len, int B, int H,
                         int C, float* graph, uint8_t* category_mask, int64_t* category_indices,
                         void* stream);
+/* the same with the reference's graph flags (config.py:56-58, MIND_corpus.py:179-182,203-213); a bit set = flag on.
+ * no_self_connection without no_adjacent_normalization is rejected like config.py:111 does.     */
+enum {
+  NNR_GRAPH_NO_SELF_CONNECTION = 1, /* adjacency starts from zeros instead of the identity       */
+  NNR_GRAPH_NO_NORMALIZATION = 2,   /* keep the 0/1 adjacency                                     */
+  NNR_GRAPH_ASYMMETRIC = 4          /* D^-1 A instead of D^-1/2 A D^-1/2                          */
+};
+int nnr_sue_graph_build_ex(const int32_t* categories, const int32_t* history_len, int B, int H,
+                           int C, int flags, float* graph, uint8_t* category_mask,
+                           int64_t* category_indices, void* stream);
+/* GCN layer with layer normalisation (flag gcn_layer_norm, layers.py:286-292).  y [R,D] is the output of
+ * nnr_gemm(EPI_BIAS) = W (A X) + b.  forward: n = LayerNorm(y) * gamma + beta (biased variance, eps), r = relu(n)
+ * -> relu_out, out = dropout(r + res) (res may be NULL; dropout counter = row * D + col), mean / rstd [R] are the
+ * backward stash.  backward: dout_dropped (optional) = dout * mask (the residual branch's gradient),
+ * dy = dL/dy, dgamma / dbeta [D] (deterministic).  D <= 1024.                                   */
+int nnr_ln_relu_res_fwd(const float* y, const float* gamma, const float* beta, const float* res,
+                        int R, int D, float eps, float p_drop, uint64_t seed, float* out,
+                        float* relu_out, float* mean, float* rstd, void* stream);
+size_t nnr_ln_relu_res_bwd_workspace_bytes(int R, int D);
+int nnr_ln_relu_res_bwd(const float* dout, const float* y, const float* gamma, const float* relu_out,
+                        const float* mean, const float* rstd, int R, int D, float p_drop,
+                        uint64_t seed, float* dout_dropped, float* dy, float* dgamma, float* dbeta,
+                        void* workspace, size_t workspace_bytes, void* stream);
 /* Dense (caller-supplied) graph -> per-row compressed neighbour lists (row-compressed with a fixed
  * row capacity of G entries).  transpose=1 emits the lists of A^T (for the backward pass).
  * nnz [B*G], col/val [B*G, G]; entries of a row are in ascending column order.                  */

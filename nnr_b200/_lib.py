@@ -98,6 +98,10 @@ SIGNATURES = {
     'nnr_news_fuse_fwd': (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, u64, vp, vp]),
     'nnr_news_fuse_bwd': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32, u64, vp, vp, vp, vp, C.c_int, vp]),
     'nnr_sue_graph_build': (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
+    'nnr_sue_graph_build_ex': (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
+    'nnr_ln_relu_res_fwd': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, f32, f32, u64, vp, vp, vp, vp, vp]),
+    'nnr_ln_relu_res_bwd_workspace_bytes': (sz, [C.c_int, C.c_int]),
+    'nnr_ln_relu_res_bwd': (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, f32, u64, vp, vp, vp, vp, vp, sz, vp]),
     'nnr_graph_to_csr': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
     'nnr_gcn_aggregate': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     'nnr_gcn_aggregate_add': (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),

@@ -12,8 +12,10 @@
 // ------------------------------------------------------------------------------------------------
 #define GB_MAXC 64
 #define GB_MAXH 256
+// flags (MIND_corpus.py:179-182,203-213): bit 0 = no_self_connection, bit 1 = no_adjacent_normalization,
+// bit 2 = gcn_normalization_type == 'asymmetric' (D^-1 A instead of D^-1/2 A D^-1/2)
 __global__ void sue_graph_build_kernel(const int32_t* __restrict__ categories, const int32_t* __restrict__ history_len,
-                                       int H, int C, float* __restrict__ graph, uint8_t* __restrict__ cmask,
+                                       int H, int C, int flags, float* __restrict__ graph, uint8_t* __restrict__ cmask,
                                        int64_t* __restrict__ cidx) {
   __shared__ int s_cat[GB_MAXH];     // category of slot, or C for padding
   __shared__ int s_cnt[GB_MAXC];
@@ -21,8 +23,12 @@ __global__ void sue_graph_build_kernel(const int32_t* __restrict__ categories, c
   __shared__ int s_P;
   const int b = blockIdx.x, tid = threadIdx.x;
   const int G = H + C;
+  const bool self_conn = !(flags & NNR_GRAPH_NO_SELF_CONNECTION);
+  const bool asym = (flags & NNR_GRAPH_ASYMMETRIC) != 0;
   int hl = history_len[b];
   hl = min(max(hl, 0), H);
+  // the reference normalises only inside `if len(history.strip()) > 0` (MIND_corpus.py:185,203)
+  const bool normalize = !(flags & NNR_GRAPH_NO_NORMALIZATION) && hl > 0;
   for (int i = tid; i < H; i += blockDim.x) {
     int c = (i < hl) ? categories[(size_t)b * H + i] : C;
     if (c < 0 || c > C) c = C;
@@ -43,12 +49,15 @@ __global__ void sue_graph_build_kernel(const int32_t* __restrict__ categories, c
   }
   __syncthreads();
   const int P = s_P;
-  // d = sqrt(1/deg) in fp32, correctly rounded like numpy (MIND_corpus.py:211-212)
+  // row sums are exact small integers; symmetric: d = sqrt(1/deg), asymmetric: d = 1/deg, both in fp32, correctly rounded
+  // like numpy (MIND_corpus.py:207,212)
+  const int sc = self_conn ? 1 : 0;
   for (int v = tid; v < G; v += blockDim.x) {
     int deg;
-    if (v < H) deg = (v < hl) ? (s_cnt[s_cat[v]] + 1) : 1;
-    else { int c = v - H; deg = (s_cnt[c] > 0) ? (1 + s_cnt[c] + (P - 1)) : 1; }
-    s_d[v] = __fsqrt_rn(__fdiv_rn(1.0f, (float)deg));
+    if (v < H) deg = (v < hl) ? (s_cnt[s_cat[v]] + sc) : sc;
+    else { int c = v - H; deg = (s_cnt[c] > 0) ? (sc + s_cnt[c] + (P - 1)) : sc; }
+    const float inv = __fdiv_rn(1.0f, (float)deg);          // deg == 0 only without self connections (rejected with normalisation)
+    s_d[v] = asym ? inv : __fsqrt_rn(inv);
   }
   __syncthreads();
   if (cidx) for (int i = tid; i < H; i += blockDim.x) cidx[(size_t)b * H + i] = (int64_t)s_cat[i];
@@ -58,25 +67,35 @@ __global__ void sue_graph_build_kernel(const int32_t* __restrict__ categories, c
     for (int e = tid; e < G * G; e += blockDim.x) {
       int i = e / G, j = e - i * G;
       bool edge;
-      if (i == j) edge = true;
+      if (i == j) edge = self_conn;
       else if (i < H && j < H) edge = (i < hl && j < hl && s_cat[i] == s_cat[j]);
       else if (i < H) edge = (i < hl && s_cat[i] == j - H);
       else if (j < H) edge = (j < hl && s_cat[j] == i - H);
       else edge = (s_cnt[i - H] > 0 && s_cnt[j - H] > 0);
-      // (D A) D with A in {0,1}: fl(fl(d_i * 1) * d_j)
-      g[e] = edge ? __fmul_rn(s_d[i], s_d[j]) : 0.0f;
+      // symmetric: (D A) D with A in {0,1} = fl(fl(d_i * 1) * d_j); asymmetric: D A = d_i; none: A
+      float v = 0.0f;
+      if (edge) v = !normalize ? 1.0f : (asym ? s_d[i] : __fmul_rn(s_d[i], s_d[j]));
+      g[e] = v;
     }
   }
 }
 
-extern "C" int nnr_sue_graph_build(const int32_t* categories, const int32_t* history_len, int B, int H, int C, float* graph,
-                                   uint8_t* category_mask, int64_t* category_indices, void* stream) {
+extern "C" int nnr_sue_graph_build_ex(const int32_t* categories, const int32_t* history_len, int B, int H, int C, int flags,
+                                      float* graph, uint8_t* category_mask, int64_t* category_indices, void* stream) {
   NNR_REQUIRE(categories && history_len && B > 0 && H > 0 && C > 0, NNR_ERR_ARG, "nnr_sue_graph_build: bad arguments");
   NNR_REQUIRE(H <= GB_MAXH && C <= GB_MAXC, NNR_ERR_UNSUPPORTED, "nnr_sue_graph_build: H<=%d, C<=%d", GB_MAXH, GB_MAXC);
-  sue_graph_build_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(categories, history_len, H, C, graph, category_mask,
+  NNR_REQUIRE((flags & ~7) == 0, NNR_ERR_ARG, "nnr_sue_graph_build: unknown flags 0x%x", flags);
+  // config.py:111: adjacent normalisation is only defined with self connections (rows without edges would divide by 0)
+  NNR_REQUIRE(!((flags & NNR_GRAPH_NO_SELF_CONNECTION) && !(flags & NNR_GRAPH_NO_NORMALIZATION)), NNR_ERR_ARG,
+              "nnr_sue_graph_build: no_self_connection requires no_adjacent_normalization (reference config.py:111)");
+  sue_graph_build_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(categories, history_len, H, C, flags, graph, category_mask,
                                                             category_indices);
   NNR_LAUNCH_CHECK("sue_graph_build_kernel");
   return 0;
+}
+extern "C" int nnr_sue_graph_build(const int32_t* categories, const int32_t* history_len, int B, int H, int C, float* graph,
+                                   uint8_t* category_mask, int64_t* category_indices, void* stream) {
+  return nnr_sue_graph_build_ex(categories, history_len, B, H, C, 0, graph, category_mask, category_indices, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -435,4 +454,158 @@ extern "C" int nnr_cluster_intra_bwd(const float* dintra, const float* Kp, const
   cluster_intra_bwd_b_kernel<<<B * H, 256, 0, st>>>(dintra, Qp, idx, alpha, da_ws, n, H, Au, D, C1, dKp, dg, accumulate_dg);
   NNR_LAUNCH_CHECK("cluster_intra_bwd_b_kernel");
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GCN layer with layer normalisation (flag gcn_layer_norm; layers.py:286-292):
+//   y = W (A X) + b  (nnr_gemm, EPI_BIAS);  n = LN(y) * gamma + beta;  r = relu(n);  out = dropout(r + res)
+// forward : a warp per row, the row lives in registers (D <= 1024), biased variance like nn.LayerNorm
+// backward: same mapping; a CTA's rows are accumulated per lane for dgamma / dbeta, warps combined in warp order, the
+//           per-CTA partials are summed by nnr_colsum (fixed order -> deterministic)
+// Dropout counter = r * D + c (regenerated in the backward), the convention of the EPI_BIAS_RELU_RES epilogue.
+// ------------------------------------------------------------------------------------------------
+#define LN_MAXPL 32          // columns per lane: D <= 1024
+#define LN_WARPS 8
+#define LN_ROWS_PER_CTA 32   // rows per CTA in the backward (4 per warp)
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_relu_res_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
+                                                                       const float* __restrict__ beta, const float* __restrict__ res,
+                                                                       int R, int D, float eps, float p, float inv_keep, uint64_t seed,
+                                                                       float* __restrict__ out, float* __restrict__ relu_out,
+                                                                       float* __restrict__ mean, float* __restrict__ rstd) {
+  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= R) return;
+  float v[LN_MAXPL];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAXPL; ++j) {
+    const int c = lane + 32 * j;
+    v[j] = c < D ? y[(size_t)row * D + c] : 0.f;
+    s += v[j];
+  }
+  const float mu = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAXPL; ++j) {
+    const int c = lane + 32 * j;
+    const float d = c < D ? v[j] - mu : 0.f;
+    q += d * d;
+  }
+  const float rs = rsqrtf(warp_sum(q) / (float)D + eps);
+  if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+#pragma unroll
+  for (int j = 0; j < LN_MAXPL; ++j) {
+    const int c = lane + 32 * j;
+    if (c < D) {
+      const float n = (v[j] - mu) * rs * gamma[c] + beta[c];
+      const float r = fmaxf(n, 0.f);
+      relu_out[(size_t)row * D + c] = r;
+      float o = res ? r + res[(size_t)row * D + c] : r;
+      if (p > 0.f) o *= dropout_scale(seed, (uint64_t)row * (uint64_t)D + c, p, inv_keep);
+      out[(size_t)row * D + c] = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_relu_res_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y,
+                                                                       const float* __restrict__ gamma, const float* __restrict__ relu_out,
+                                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                       int R, int D, float p, float inv_keep, uint64_t seed,
+                                                                       float* __restrict__ dout_dropped, float* __restrict__ dy,
+                                                                       float* __restrict__ part_g, float* __restrict__ part_b) {
+  __shared__ float s_g[LN_WARPS][32], s_b[LN_WARPS][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float ag[LN_MAXPL], ab[LN_MAXPL];
+#pragma unroll
+  for (int j = 0; j < LN_MAXPL; ++j) { ag[j] = 0.f; ab[j] = 0.f; }
+  for (int k = 0; k < LN_ROWS_PER_CTA / LN_WARPS; ++k) {
+    const int row = blockIdx.x * LN_ROWS_PER_CTA + k * LN_WARPS + warp;
+    if (row >= R) break;
+    const float mu = mean[row], rs = rstd[row];
+    float dxh[LN_MAXPL], xh[LN_MAXPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXPL; ++j) {
+      const int c = lane + 32 * j;
+      dxh[j] = 0.f; xh[j] = 0.f;
+      if (c < D) {
+        const size_t o = (size_t)row * D + c;
+        float g = dout[o];
+        if (p > 0.f) g *= dropout_scale(seed, (uint64_t)row * (uint64_t)D + c, p, inv_keep);
+        if (dout_dropped) dout_dropped[o] = g;
+        const float dn = relu_out[o] > 0.f ? g : 0.f;
+        xh[j] = (y[o] - mu) * rs;
+        dxh[j] = dn * gamma[c];
+        ag[j] += dn * xh[j];
+        ab[j] += dn;
+        s1 += dxh[j];
+        s2 += dxh[j] * xh[j];
+      }
+    }
+    const float m1 = warp_sum(s1) / (float)D, m2 = warp_sum(s2) / (float)D;
+#pragma unroll
+    for (int j = 0; j < LN_MAXPL; ++j) {
+      const int c = lane + 32 * j;
+      if (c < D) dy[(size_t)row * D + c] = rs * (dxh[j] - m1 - xh[j] * m2);
+    }
+  }
+  // per-CTA column partials: warps combined in warp order, 32 columns at a time
+  for (int j = 0; j < LN_MAXPL; ++j) {
+    if (32 * j >= D) break;
+    __syncthreads();
+    s_g[warp][lane] = ag[j]; s_b[warp][lane] = ab[j];
+    __syncthreads();
+    if (warp == 0) {
+      const int c = lane + 32 * j;
+      if (c < D) {
+        float tg = 0.f, tb = 0.f;
+#pragma unroll
+        for (int w = 0; w < LN_WARPS; ++w) { tg += s_g[w][lane]; tb += s_b[w][lane]; }
+        part_g[(size_t)blockIdx.x * D + c] = tg;
+        part_b[(size_t)blockIdx.x * D + c] = tb;
+      }
+    }
+  }
+}
+
+extern "C" int nnr_ln_relu_res_fwd(const float* y, const float* gamma, const float* beta, const float* res, int R, int D, float eps,
+                                   float p_drop, uint64_t seed, float* out, float* relu_out, float* mean, float* rstd, void* stream) {
+  NNR_REQUIRE(y && gamma && beta && out && relu_out && mean && rstd && R > 0 && D > 0, NNR_ERR_ARG, "nnr_ln_relu_res_fwd: bad arguments");
+  NNR_REQUIRE(D <= 32 * LN_MAXPL, NNR_ERR_UNSUPPORTED, "nnr_ln_relu_res_fwd: D <= %d", 32 * LN_MAXPL);
+  NNR_REQUIRE(p_drop >= 0.f && p_drop < 1.f, NNR_ERR_ARG, "nnr_ln_relu_res_fwd: p_drop=%f", p_drop);
+  ln_relu_res_fwd_kernel<<<(R + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      y, gamma, beta, res, R, D, eps, p_drop, 1.0f / (1.0f - p_drop), seed, out, relu_out, mean, rstd);
+  NNR_LAUNCH_CHECK("ln_relu_res_fwd_kernel");
+  return 0;
+}
+
+extern "C" size_t nnr_colsum_workspace_bytes(int M, int N);
+extern "C" int nnr_colsum(const float* X, int64_t ldx, int M, int N, const int32_t* m_dev, float* out, int accumulate, void* workspace,
+                          size_t workspace_bytes, void* stream);
+static size_t ln_up256(size_t x) { return (x + 255) / 256 * 256; }
+extern "C" size_t nnr_ln_relu_res_bwd_workspace_bytes(int R, int D) {
+  if (R <= 0 || D <= 0) return 0;
+  const int nb = (R + LN_ROWS_PER_CTA - 1) / LN_ROWS_PER_CTA;
+  return 2 * ln_up256((size_t)nb * D * sizeof(float)) + ln_up256(nnr_colsum_workspace_bytes(nb, D));
+}
+extern "C" int nnr_ln_relu_res_bwd(const float* dout, const float* y, const float* gamma, const float* relu_out, const float* mean,
+                                   const float* rstd, int R, int D, float p_drop, uint64_t seed, float* dout_dropped, float* dy,
+                                   float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, void* stream) {
+  NNR_REQUIRE(dout && y && gamma && relu_out && mean && rstd && dy && dgamma && dbeta && workspace && R > 0 && D > 0, NNR_ERR_ARG,
+              "nnr_ln_relu_res_bwd: bad arguments");
+  NNR_REQUIRE(D <= 32 * LN_MAXPL, NNR_ERR_UNSUPPORTED, "nnr_ln_relu_res_bwd: D <= %d", 32 * LN_MAXPL);
+  NNR_REQUIRE(p_drop >= 0.f && p_drop < 1.f, NNR_ERR_ARG, "nnr_ln_relu_res_bwd: p_drop=%f", p_drop);
+  NNR_REQUIRE(workspace_bytes >= nnr_ln_relu_res_bwd_workspace_bytes(R, D), NNR_ERR_WORKSPACE, "nnr_ln_relu_res_bwd: workspace too small");
+  NNR_REQUIRE(dout_dropped != dout, NNR_ERR_ARG, "nnr_ln_relu_res_bwd: dout_dropped must not alias dout");
+  const int nb = (R + LN_ROWS_PER_CTA - 1) / LN_ROWS_PER_CTA;
+  char* ws = (char*)workspace;
+  float* pg = (float*)ws;
+  float* pb = (float*)(ws + ln_up256((size_t)nb * D * sizeof(float)));
+  void* cws = ws + 2 * ln_up256((size_t)nb * D * sizeof(float));
+  const size_t cws_bytes = ln_up256(nnr_colsum_workspace_bytes(nb, D));
+  ln_relu_res_bwd_kernel<<<nb, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(dout, y, gamma, relu_out, mean, rstd, R, D, p_drop,
+                                                                        1.0f / (1.0f - p_drop), seed, dout_dropped, dy, pg, pb);
+  NNR_LAUNCH_CHECK("ln_relu_res_bwd_kernel");
+  int rc = nnr_colsum(pg, D, nb, D, nullptr, dgamma, 0, cws, cws_bytes, stream);
+  if (rc) return rc;
+  return nnr_colsum(pb, D, nb, D, nullptr, dbeta, 0, cws, cws_bytes, stream);
 }

@@ -496,8 +496,17 @@ class CNEFunction(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # SUE
 # ------------------------------------------------------------------------------------------------
-def sue_param_names(L):
-    return (['proxy_node_embedding'] + ['gcn.gcn_layers.%d.W.%s' % (l, w) for l in range(L) for w in ('weight', 'bias')]
+def _gcn_param_names(L, layer_norm=False):
+    names = []
+    for l in range(L):
+        names += ['gcn.gcn_layers.%d.W.weight' % l, 'gcn.gcn_layers.%d.W.bias' % l]
+        if layer_norm:                                    # layers.py:274-275
+            names += ['gcn.gcn_layers.%d.layer_normalization.weight' % l, 'gcn.gcn_layers.%d.layer_normalization.bias' % l]
+    return names
+
+
+def sue_param_names(L, layer_norm=False):
+    return (['proxy_node_embedding'] + _gcn_param_names(L, layer_norm)
             + ['intraCluster_K.weight', 'intraCluster_Q.weight', 'intraCluster_Q.bias', 'clusterFeatureAffine.weight',
                'clusterFeatureAffine.bias', 'interClusterAttention.K.weight', 'interClusterAttention.Q.weight',
                'interClusterAttention.Q.bias'])
@@ -510,8 +519,8 @@ def sue_wo_gcn_param_names():
             'interClusterAttention.Q.weight', 'interClusterAttention.Q.bias']
 
 
-def sue_wo_hca_param_names(L):
-    return (['proxy_node_embedding'] + ['gcn.gcn_layers.%d.W.%s' % (l, w) for l in range(L) for w in ('weight', 'bias')]
+def sue_wo_hca_param_names(L, layer_norm=False):
+    return (['proxy_node_embedding'] + _gcn_param_names(L, layer_norm)
             + ['attention.affine1.weight', 'attention.affine1.bias', 'attention.affine2.weight'])
 
 
@@ -523,7 +532,8 @@ class SUEFunction(torch.autograd.Function):
         hca = meta['hca']
         gcn = meta.get('gcn', True)
         L = meta['gcn_layers'] if gcn else 0
-        names = (sue_param_names(L) if hca else sue_wo_hca_param_names(L)) if gcn else sue_wo_gcn_param_names()
+        ln = meta.get('layer_norm', False)
+        names = (sue_param_names(L, ln) if hca else sue_wo_hca_param_names(L, ln)) if gcn else sue_wo_gcn_param_names()
         P = dict(zip(names, params))
         B, H, D = hist.shape
         n = cand.shape[1]
@@ -550,7 +560,7 @@ class SUEFunction(torch.autograd.Function):
         nnz, col, val = _empty((B * Gn,), dev, torch.int32), _empty((B * Gn, Gn), dev, torch.int32), _empty((B * Gn, Gn), dev)
         ops.graph_to_csr(graph, False, nnz, col, val)
         # GCN layers: X <- drop(relu(W (A X) + b) + X)   (layers.py:285-292,318-323)
-        xs, rs, aggs = [x0], [], []
+        xs, rs, aggs, lns = [x0], [], [], []
         x = x0
         for l in range(L):
             agg = _empty((B * Gn, D), dev)
@@ -559,9 +569,19 @@ class SUEFunction(torch.autograd.Function):
             xv = x.view(B * Gn, D)
             pl = (pe / 2.0) if l < L - 1 else 0.0
             agg_pl = ops.tc_split(agg, B * Gn, D, D)             # shared with the weight-gradient GEMM of the backward
-            xn = linear(agg, P['gcn.gcn_layers.%d.W.weight' % l], B * Gn, None, P['gcn.gcn_layers.%d.W.bias' % l],
-                        EPI_BIAS_RELU_RES, aux=xv if residual else None, ldaux=D, aux_out=r, ldaux_out=D, p_drop=pl,
-                        seed=seeds[l], x_planes=agg_pl)
+            if ln:                                                # layers.py:286-292 with layer_norm: relu(LN(W(AX)+b)) + X
+                lnp = 'gcn.gcn_layers.%d.layer_normalization.' % l
+                y = linear(agg, P['gcn.gcn_layers.%d.W.weight' % l], B * Gn, None, P['gcn.gcn_layers.%d.W.bias' % l], EPI_BIAS,
+                           x_planes=agg_pl)
+                xn = _empty((B * Gn, D), dev)
+                mu, rstd = _empty((B * Gn,), dev), _empty((B * Gn,), dev)
+                ops.ln_relu_res_fwd(y, P[lnp + 'weight'], P[lnp + 'bias'], xv if residual else None, B * Gn, D, 1e-5, pl, seeds[l],
+                                    xn, r, mu, rstd)
+                lns.append((y, mu, rstd))
+            else:
+                xn = linear(agg, P['gcn.gcn_layers.%d.W.weight' % l], B * Gn, None, P['gcn.gcn_layers.%d.W.bias' % l],
+                            EPI_BIAS_RELU_RES, aux=xv if residual else None, ldaux=D, aux_out=r, ldaux_out=D, p_drop=pl,
+                            seed=seeds[l], x_planes=agg_pl)
             aggs.append((agg, agg_pl))
             rs.append(r)
             x = xn.view(B, Gn, D)
@@ -570,7 +590,7 @@ class SUEFunction(torch.autograd.Function):
         ctx.meta, ctx.P, ctx.names = meta, P, names
         ctx.dims = (B, H, D, n, C, Gn, C1)
         ctx.seeds, ctx.graph = seeds, graph
-        ctx.xs, ctx.rs, ctx.aggs = xs, rs, aggs
+        ctx.xs, ctx.rs, ctx.aggs, ctx.lns = xs, rs, aggs, lns
         ctx.gfeat, ctx.cand = gfeat, cand
         if not hca:                                                                           # SUE_wo_HCA
             A = P['attention.affine1.weight'].shape[0]
@@ -715,7 +735,17 @@ class SUEFunction(torch.autograd.Function):
         for l in range(L - 1, -1, -1):
             pl = (pe / 2.0) if l < L - 1 else 0.0
             db_l = _empty((D,), dev)
-            if _fused_relu_bwd(dx, D):
+            if meta.get('layer_norm', False):
+                lnp = 'gcn.gcn_layers.%d.layer_normalization.' % l
+                y, mu, rstd = ctx.lns[l]
+                dx_d = _empty(dx.shape, dev) if pl > 0 else None
+                dpre = _empty((B * Gn, D), dev)                   # dL/dy (pre-normalisation)
+                G[lnp + 'weight'], G[lnp + 'bias'] = _empty((D,), dev), _empty((D,), dev)
+                ops.ln_relu_res_bwd(dx, y, P[lnp + 'weight'], ctx.rs[l], mu, rstd, B * Gn, D, pl, seeds[l], dx_d, dpre,
+                                    G[lnp + 'weight'], G[lnp + 'bias'])
+                dx = dx_d if pl > 0 else dx
+                dpre_pl = ops.tc_split(dpre, B * Gn, D, D, colsum_out=db_l)
+            elif _fused_relu_bwd(dx, D):
                 dx_d = _empty(dx.shape, dev) if pl > 0 else None
                 dpre = None
                 dpre_pl = ops.relu_bwd_split_colsum(dx, ctx.rs[l], B * Gn, D, pl, seeds[l], dx_d, db_l)
@@ -739,7 +769,7 @@ class SUEFunction(torch.autograd.Function):
         if pe > 0:
             ops.dropout(dproxy_b, pe, seeds[L], dproxy_b)
         G['proxy_node_embedding'] = dproxy_b.sum(dim=0)
-        ctx.xs = ctx.rs = ctx.aggs = ctx.sv = None
+        ctx.xs = ctx.rs = ctx.aggs = ctx.sv = ctx.lns = None
         return (None, dhist, dcand.view(B, n, D) if dcand is not None else None, None, None, None) + _param_grads(P, ctx.names, G)
 
 

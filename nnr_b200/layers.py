@@ -46,9 +46,9 @@ class GCNLayer(nn.Module):
         self.layer_norm = layer_norm
         if self.residual and in_dim != out_dim:
             raise Exception('To facilitate residual connection, in_dim must equal to out_dim')
-        if layer_norm:
-            raise NotImplementedError('nnr_b200: gcn_layer_norm is outside the CNE+SUE hot path (SURVEY 8f-4)')
         self.W = nn.Linear(in_dim, out_dim, bias=True)
+        if self.layer_norm:                                   # layers.py:274-275 (same construction order)
+            self.layer_normalization = nn.LayerNorm(normalized_shape=[out_dim])
 
     def initialize(self):
         nn.init.xavier_uniform_(self.W.weight, gain=nn.init.calculate_gain('relu'))

@@ -336,10 +336,33 @@ def news_fuse_bwd(dout, cat, sub, N, D2, p_drop, seed, d_a, d_b, dcat_table, dsu
           'nnr_news_fuse_bwd')
 
 
-def sue_graph_build(categories, history_len, C_num, graph=None, category_mask=None, category_indices=None):
+GRAPH_NO_SELF_CONNECTION, GRAPH_NO_NORMALIZATION, GRAPH_ASYMMETRIC = 1, 2, 4
+
+
+def graph_flags(no_self_connection=False, no_adjacent_normalization=False, gcn_normalization_type='symmetric'):
+    """the reference's graph options (config.py:56-58) as the flag word of nnr_sue_graph_build_ex"""
+    return ((GRAPH_NO_SELF_CONNECTION if no_self_connection else 0) | (GRAPH_NO_NORMALIZATION if no_adjacent_normalization else 0)
+            | (GRAPH_ASYMMETRIC if gcn_normalization_type == 'asymmetric' else 0))
+
+
+def sue_graph_build(categories, history_len, C_num, graph=None, category_mask=None, category_indices=None, flags=0):
     B, H = categories.shape
-    check(lib.nnr_sue_graph_build(_p(categories, _I32), _p(history_len, _I32), B, H, C_num, _p(graph, _F32),
-                                  _p(category_mask, _U8), _p(category_indices, _I64), _stream()), 'nnr_sue_graph_build')
+    check(lib.nnr_sue_graph_build_ex(_p(categories, _I32), _p(history_len, _I32), B, H, C_num, int(flags), _p(graph, _F32),
+                                     _p(category_mask, _U8), _p(category_indices, _I64), _stream()), 'nnr_sue_graph_build')
+
+
+def ln_relu_res_fwd(y, gamma, beta, res, R, D, eps, p_drop, seed, out, relu_out, mean, rstd):
+    check(lib.nnr_ln_relu_res_fwd(_p(y, _F32), _p(gamma, _F32), _p(beta, _F32), _p(res, _F32), R, D, float(eps), float(p_drop),
+                                  int(seed), _p(out, _F32), _p(relu_out, _F32), _p(mean, _F32), _p(rstd, _F32), _stream()),
+          'nnr_ln_relu_res_fwd')
+
+
+def ln_relu_res_bwd(dout, y, gamma, relu_out, mean, rstd, R, D, p_drop, seed, dout_dropped, dy, dgamma, dbeta):
+    nbytes = lib.nnr_ln_relu_res_bwd_workspace_bytes(R, D)
+    ws = workspace(nbytes, dout.device, 'ln')
+    check(lib.nnr_ln_relu_res_bwd(_p(dout, _F32), _p(y, _F32), _p(gamma, _F32), _p(relu_out, _F32), _p(mean, _F32), _p(rstd, _F32),
+                                  R, D, float(p_drop), int(seed), _p(dout_dropped, _F32), _p(dy, _F32), _p(dgamma, _F32),
+                                  _p(dbeta, _F32), ws.data_ptr(), ws.numel(), _stream()), 'nnr_ln_relu_res_bwd')
 
 
 def graph_to_csr(graph, transpose, nnz, col, val):

@@ -22,16 +22,20 @@ FIELDS = ['user_ID', 'user_category', 'user_subCategory', 'user_title_text', 'us
           'news_content_entity']
 
 
-def history_structure(categories, history_len, category_num, normalize=True):
+def history_structure(categories, history_len, category_num, normalize=True, no_self_connection=False,
+                      gcn_normalization_type='symmetric'):
     """categories [B,H] int (category of each history slot, valid slots first), history_len [B].
     Returns graph [B,H+C,H+C] float32, category_mask [B,C+1] bool, category_indices [B,H] int64.
-    Same values as MIND_corpus.py:178-213 with the default flags (self connections, symmetric
-    normalisation)."""
+    Same values as MIND_corpus.py:178-213; ``normalize=False`` = no_adjacent_normalization,
+    ``no_self_connection`` (:179-182) and ``gcn_normalization_type='asymmetric'`` (:204-208) are the reference's flags
+    (defaults: self connections, symmetric normalisation).  As in the reference an empty history is never normalised."""
     cats = torch.as_tensor(categories).long()
     hl = torch.as_tensor(history_len).long()
     B, H = cats.shape
     C = int(category_num)
     G = H + C
+    if no_self_connection and normalize:
+        raise ValueError('adjacent normalisation needs self connections (reference config.py:111)')
     valid = torch.arange(H).unsqueeze(0) < hl.unsqueeze(1)                    # [B,H]
     idx = torch.where(valid, cats, torch.full_like(cats, C))                  # pad slots -> cluster C
     onehot = torch.zeros(B, H, C + 1, dtype=torch.float32).scatter_(2, idx.unsqueeze(2), 1.0)[:, :, :C]
@@ -45,11 +49,19 @@ def history_structure(categories, history_len, category_num, normalize=True):
     pf = present.float()
     A[:, H:, H:] = pf.unsqueeze(2) * pf.unsqueeze(1)                          # clique over present proxies
     eye = torch.eye(G, dtype=torch.float32).unsqueeze(0)
-    A = torch.maximum(A, eye.expand(B, -1, -1))                               # self connections
+    if no_self_connection:
+        A = A * (1.0 - eye)                                                   # the pair products above set the diagonal
+    else:
+        A = torch.maximum(A, eye.expand(B, -1, -1))                           # self connections
     if normalize:
         deg = A.sum(dim=2)                                                    # exact small integers
-        d = torch.sqrt(1.0 / deg)                                             # fp32, correctly rounded
-        A = (d.unsqueeze(2) * A) * d.unsqueeze(1)
+        nonempty = (hl > 0).view(B, 1, 1)
+        if gcn_normalization_type == 'asymmetric':
+            An = (1.0 / deg).unsqueeze(2) * A                                 # D^-1 A
+        else:
+            d = torch.sqrt(1.0 / deg)                                         # fp32, correctly rounded
+            An = (d.unsqueeze(2) * A) * d.unsqueeze(1)
+        A = torch.where(nonempty, An, A)
     return A, mask, idx
 
 

@@ -43,6 +43,7 @@ class SUE(UserEncoder):
         self.max_history_num = config.max_history_num
         self.gcn_layer_num = config.gcn_layer_num
         self.gcn_residual = not config.no_gcn_residual
+        self.gcn_layer_norm = bool(config.gcn_layer_norm)
         self.attention_scalar = math.sqrt(float(self.attention_dim))
 
     def initialize(self):
@@ -58,7 +59,8 @@ class SUE(UserEncoder):
     def _params(self):
         cached = self.__dict__.get('_param_list')      # see newsEncoders.CNE._params
         if cached is None:
-            names = ((engine.sue_param_names(self.gcn_layer_num) if self.hca else engine.sue_wo_hca_param_names(self.gcn_layer_num))
+            ln = getattr(self, 'gcn_layer_norm', False)
+            names = ((engine.sue_param_names(self.gcn_layer_num, ln) if self.hca else engine.sue_wo_hca_param_names(self.gcn_layer_num, ln))
                      if self.use_gcn else engine.sue_wo_gcn_param_names())
             sd = {k: v for k, v in self.named_parameters() if not k.startswith('news_encoder.')}
             cached = [sd[k] for k in names]
@@ -80,6 +82,7 @@ class SUE(UserEncoder):
         with one CNE schedule, see CNE.encode_calls)."""
         user_history_category_mask[:, -1] = 1                                    # userEncoders.py:73 (in place, like the reference)
         meta = dict(hca=self.hca, gcn=self.use_gcn, gcn_layers=self.gcn_layer_num, residual=self.gcn_residual,
+                    layer_norm=getattr(self, 'gcn_layer_norm', False),
                     training=self.training, p_drop=float(self.dropout_rate), category_num=self.category_num - 1 if self.hca else 0)
         return engine.SUEFunction.apply(meta, history_embedding, candidate_news_representation, user_history_graph,
                                         user_history_category_mask, user_history_category_indices.long(), *self._params())

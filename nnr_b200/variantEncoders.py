@@ -87,6 +87,7 @@ class SUE_wo_HCA(UserEncoder):
         self.dropout_ = nn.Dropout(p=config.dropout_rate, inplace=False)
         self.gcn_layer_num = config.gcn_layer_num
         self.gcn_residual = not config.no_gcn_residual
+        self.gcn_layer_norm = bool(config.gcn_layer_norm)
 
     def initialize(self):
         nn.init.zeros_(self.proxy_node_embedding)

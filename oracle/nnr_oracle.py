@@ -77,6 +77,9 @@ def param_shapes(cfg):
         for l in range(cfg.gcn_layer_num):
             s[ue + f'gcn.gcn_layers.{l}.W.weight'] = (D, D)
             s[ue + f'gcn.gcn_layers.{l}.W.bias'] = (D,)
+            if getattr(cfg, 'gcn_layer_norm', False):   # layers.py:274-275
+                s[ue + f'gcn.gcn_layers.{l}.layer_normalization.weight'] = (D,)
+                s[ue + f'gcn.gcn_layers.{l}.layer_normalization.bias'] = (D,)
     if cfg.user_encoder in ('SUE', 'SUE_wo_GCN'):
         s[ue + 'intraCluster_K.weight'] = (Au, D)
         if cfg.user_encoder == 'SUE_wo_GCN':
@@ -116,6 +119,8 @@ def formula_params(cfg, dtype=torch.float32, salt=0):
                 scale = 0.1
         else:
             scale = 0.05
+        if name.endswith('layer_normalization.weight'):       # LayerNorm gain around 1
+            v, scale = 1.0 + 0.1 * v, 1.0
         out[name] = (v * scale).reshape(shape).to(dtype)
     out['news_encoder.word_embedding.weight'][0].zero_()        # <PAD> row (MIND_corpus.py:121-124)
     return out
@@ -322,11 +327,14 @@ def cne_forward(p, cfg, title_text, title_mask, content_text, content_mask, cate
 # SUE (userEncoders.py:42-98, layers.py:265-323)
 # ----------------------------------------------------------------------------------------------
 def gcn_forward(p, cfg, x, graph, pre, dropout_masks=None):
-    """layers.py:285-292 + :318-323 (layer norm flag not restated: off by default)."""
+    """layers.py:285-292 + :318-323 (optional nn.LayerNorm over the feature dim, :287-288)."""
     L = cfg.gcn_layer_num
     out = x
     for l in range(L):
         y = torch.bmm(graph, out) @ p[pre + f'gcn_layers.{l}.W.weight'].t() + p[pre + f'gcn_layers.{l}.W.bias']
+        if getattr(cfg, 'gcn_layer_norm', False):
+            y = F.layer_norm(y, (y.shape[-1],), p[pre + f'gcn_layers.{l}.layer_normalization.weight'],
+                             p[pre + f'gcn_layers.{l}.layer_normalization.bias'], 1e-5)
         y = F.relu(y)
         if not cfg.no_gcn_residual:
             y = y + out

@@ -19,6 +19,7 @@ sys.path.insert(0, ROOT)
 from oracle import nnr_oracle as O            # noqa: E402
 from oracle import reference_import as R      # noqa: E402
 from nnr_b200.synthetic import SyntheticMIND  # noqa: E402
+from tests import util as U                   # noqa: E402
 
 CASES = {
     # name: (config overrides, corpus kwargs, batch size, news_num, seeds)
@@ -46,6 +47,13 @@ CASES = {
                           subCategory_num=30, gcn_layer_num=2, news_encoder='CNE_Content'),
                      dict(news_num=200, lengths='mind', seed=17), 3, None, 8),
 }
+
+CASES.update({
+    'gcn5': (U.GOLDEN_CASES['gcn5'], dict(news_num=200, lengths='uniform', seed=31), 3, None, 9),
+    'gcn7': (U.GOLDEN_CASES['gcn7'], dict(news_num=200, lengths='uniform', seed=33), 3, None, 10),
+    'no_residual': (U.GOLDEN_CASES['no_residual'], dict(news_num=200, lengths='uniform', seed=35), 3, None, 11),
+    'layer_norm': (U.GOLDEN_CASES['layer_norm'], dict(news_num=200, lengths='uniform', seed=37), 3, None, 12),
+})
 
 SAMPLE = 8
 
@@ -97,7 +105,66 @@ def make_case(name):
     print(name, 'loss', float(loss), 'logits', out['logits_stable_sort'].reshape(-1)[:4])
 
 
+def make_big_case(name):
+    """BASELINE-shaped cases: inputs regenerated from seeds (only their SHA-256 is stored); eval logits, and at dropout 0 the
+    train-mode logits, loss and a digest (sum, abs-sum, max-abs, S sampled entries) of every parameter gradient of the
+    UNMODIFIED reference in fp32 AND with the reference module cast to fp64 (the tie-break judge of SURVEY 8c)"""
+    over, ckw, B, n, bseed, S = U.BIG_CASES[name]
+    cfg = O.make_config(**over)
+    batch = U.corpus_for(cfg, ckw).batch(B, news_num=n, seed=bseed)
+    p = O.formula_params(cfg)
+    out = {'in_sha256': np.array(U.batch_sha256(batch))}
+    torch.set_num_threads(os.cpu_count())
+    m = R.build_reference_model(cfg, p)
+    m.eval()
+    with torch.no_grad():
+        out['logits_stable_sort'] = R.run_reference(m, batch, sort_fn=O.stable_sort).numpy()
+    cfg.dropout_rate = 0.0
+    for tag, dtype in (('', torch.float32), ('64', torch.float64)):
+        m = R.build_reference_model(cfg, p)
+        m.to(dtype)
+        m.train()
+        b = {k: (v.to(dtype) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in batch.items()}
+        logits = R.run_reference(m, b, sort_fn=O.stable_sort)
+        loss = O.loss_fn(logits)
+        loss.backward()
+        out['train_logits' + tag] = logits.detach().numpy()
+        out['train_loss' + tag] = loss.detach().numpy()
+        named = dict(m.named_parameters())
+        for k in O.param_shapes(cfg):
+            g = named[k].grad
+            g = torch.zeros_like(named[k]) if g is None else g
+            out['grad%s_%s' % (tag, k)] = U.grad_digest(g, S)
+        print(name, 'fp' + (tag or '32'), 'loss', float(loss), flush=True)
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), name + '.npz'), **out)
+
+
+def make_pins():
+    """graph_flags.npz / metrics.npz: outputs of the reference's own source lines (MIND_corpus.py:179-213 executed under
+    stub variables, evaluate.py imported live, util.py:57-60 executed) on the seeded cases of tests/test_pins.py"""
+    from tests import test_pins as T
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = compile(T.reference_graph_source(), 'MIND_corpus.py:179-213', 'exec')
+    cases, H, C = T.graph_cases()
+    out = {}
+    for fi, flags in enumerate(T.FLAG_SETS):
+        g, m, i = zip(*[T.run_reference_graph(code, cats, H, C, flags) for cats in cases])
+        out['graph_%d' % fi], out['mask_%d' % fi], out['idx_%d' % fi] = np.stack(g), np.stack(m), np.stack(i)
+    np.savez_compressed(os.path.join(here, 'graph_flags.npz'), **out)
+    labels, scores = T.metric_cases()
+    ref, ranks = T.reference_metrics(labels, scores)
+    np.savez_compressed(os.path.join(here, 'metrics.npz'), metrics=np.array([float(x) for x in ref], dtype=np.float64),
+                        ranks=np.concatenate([np.array(r) for r in ranks]))
+    print('pins', [float(x) for x in ref])
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
-    for name in (sys.argv[1:] or CASES):
-        make_case(name)
+    names = sys.argv[1:] or (list(CASES) + ['pins'] + list(U.BIG_CASES))
+    for name in names:
+        if name == 'pins':
+            make_pins()
+        elif name in U.BIG_CASES:
+            make_big_case(name)
+        else:
+            make_case(name)

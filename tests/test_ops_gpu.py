@@ -260,7 +260,11 @@ def test_colsum_and_segment_colsum(cuda):
 
 # ---------------------------------------------------------------------------------------------
 def _lstm_setup(N, L, Hd, E, g, full=False):
-    lens = torch.full((N,), L) if full else torch.randint(1, L + 1, (N,), generator=g)
+    if full == 'mind':            # MIND-like abstract lengths (lognormal, mean ~ 24..40, clipped to [1, L]) with a block of maximal ones
+        lens = torch.exp(torch.randn(N, generator=g) * 0.8 + math.log(40.0) - 0.32).round().clamp_(1, L).long()
+        lens[: N // 50] = L
+    else:
+        lens = torch.full((N,), L) if full else torch.randint(1, L + 1, (N,), generator=g)
     x = torch.randn(N, L, E, generator=g) * 0.5
     w = {}
     for sfx in ('', '_reverse'):
@@ -271,16 +275,20 @@ def _lstm_setup(N, L, Hd, E, g, full=False):
     return lens, x, w
 
 
-@pytest.mark.parametrize('N,L,full', [(70, 12, False), (32, 9, True), (129, 33, False), (5, 128, False)])
+# (3520, 128, 'mind') is the history call of BASELINE config 2 (B*H + B*5 rows, abstracts): 110 row tiles x 2 directions on
+# 29 clusters, i.e. the multi-tile longest-first scheduler, tiles of very different lengths and > 100 k tokens
+@pytest.mark.parametrize('N,L,full', [(70, 12, False), (32, 9, True), (129, 33, False), (5, 128, False), (3520, 128, 'mind')])
 def test_lstm_forward_backward(cuda, N, L, full):
     ops = _ops()
     Hd, E = 200, 24
     g = torch.Generator().manual_seed(7 + N)
     lens, x, w = _lstm_setup(N, L, Hd, E, g, full)
-    # oracle (fp64 loop restatement) with autograd
+    # oracle with autograd: the fp64 loop restatement; at the BASELINE shape torch's own packed nn.LSTM in fp64 (what the
+    # reference executes; the loop would need minutes there -- tests/test_oracle.py checks loop == ATen)
     x64 = x.double().requires_grad_(True)
     w64 = {k: v.double().requires_grad_(True) for k, v in w.items()}
-    h_ref, m_ref = O.bilstm(w64, '', x64, lens)
+    torch.set_num_threads(max(1, __import__('os').cpu_count() or 1))
+    h_ref, m_ref = O.bilstm(w64, '', x64, lens, impl='aten' if N > 1000 else 'loop')
     dh = torch.randn(N, L, 2 * Hd, generator=g)
     dcn = torch.randn(N, 2 * Hd, generator=g)
     valid = (torch.arange(L)[None, :] < lens[:, None])
@@ -652,3 +660,91 @@ def test_relu_backward_split_colsum(cuda):
         assert torch.equal(cs, cs_ref)
         if p > 0:
             assert torch.equal(dd, ref_d)
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: graph flags (MIND_corpus.py:179-182,203-213) and the layer-normalised GCN layer (layers.py:286-292)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('no_self,no_norm,typ', [(False, False, 'asymmetric'), (False, True, 'symmetric'), (True, True, 'symmetric')])
+def test_graph_build_flags_bit_exact(cuda, no_self, no_norm, typ):
+    ops = _ops()
+    rng = np.random.default_rng(12)
+    B, H, C = 48, 50, 18
+    cats = rng.integers(0, C, size=(B, H)).astype(np.int32)
+    hl = rng.integers(0, H + 1, size=B).astype(np.int32)
+    hl[:3] = [0, 1, H]
+    G_ = H + C
+    graph = torch.empty(B, G_, G_, device=cuda)
+    cmask = torch.empty(B, C + 1, dtype=torch.bool, device=cuda)
+    cidx = torch.empty(B, H, dtype=torch.int64, device=cuda)
+    flags = ops.graph_flags(no_self, no_norm, typ)
+    ops.sue_graph_build(torch.from_numpy(cats).to(cuda), torch.from_numpy(hl).to(cuda), C, graph, cmask, cidx, flags=flags)
+    for b in range(B):
+        g, m, i = OG.build_history_graph(cats[b, :hl[b]], H, C, no_self_connection=no_self, no_adjacent_normalization=no_norm,
+                                         gcn_normalization_type=typ)
+        assert np.array_equal(g, graph[b].cpu().numpy()), b           # bit exact fp32 values
+        assert np.array_equal(m, cmask[b].cpu().numpy()) and np.array_equal(i, cidx[b].cpu().numpy()), b
+    # asymmetric graphs go through the same neighbour lists: A x and A^T x
+    x = torch.randn(B, G_, 900, device=cuda)
+    for transpose in (False, True):
+        nnz = torch.empty(B * G_, dtype=torch.int32, device=cuda)
+        col = torch.empty(B * G_, G_, dtype=torch.int32, device=cuda)
+        val = torch.empty(B * G_, G_, device=cuda)
+        ops.graph_to_csr(graph, transpose, nnz, col, val)
+        out = torch.empty(B * G_, 900, device=cuda)
+        ops.gcn_aggregate(nnz, col, val, x, B, G_, 900, out)
+        gm = graph.transpose(1, 2) if transpose else graph
+        assert (out.view(B, G_, 900).double() - torch.bmm(gm.double(), x.double())).abs().max() < 1e-4
+
+
+def test_graph_build_rejects_normalisation_without_self_connections(cuda):
+    ops = _ops()
+    cats = torch.zeros(2, 50, dtype=torch.int32, device=cuda)
+    hl = torch.ones(2, dtype=torch.int32, device=cuda)
+    graph = torch.empty(2, 68, 68, device=cuda)
+    with pytest.raises(RuntimeError, match='no_self_connection'):        # reference config.py:111
+        ops.sue_graph_build(cats, hl, 18, graph, None, None, flags=ops.graph_flags(True, False, 'symmetric'))
+
+
+@pytest.mark.parametrize('R,D,p,res', [(4352, 900, 0.0, True), (301, 900, 0.1, True), (77, 333, 0.0, False)])
+def test_ln_relu_res_forward_backward(cuda, R, D, p, res):
+    """relu(LayerNorm(y)) + x, dropout: against torch in fp64 with the kernel's own dropout mask"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(R)
+    y = (torch.randn(R, D, generator=g) * 1.5 + 0.3).to(cuda)
+    x = torch.randn(R, D, generator=g).to(cuda) if res else None
+    gamma = (1.0 + 0.1 * torch.randn(D, generator=g)).to(cuda)
+    beta = (0.1 * torch.randn(D, generator=g)).to(cuda)
+    out, r = torch.empty(R, D, device=cuda), torch.empty(R, D, device=cuda)
+    mu, rstd = torch.empty(R, device=cuda), torch.empty(R, device=cuda)
+    seed = 1234
+    ops.ln_relu_res_fwd(y, gamma, beta, x, R, D, 1e-5, p, seed, out, r, mu, rstd)
+    mask = torch.empty(R, D, device=cuda)
+    ops.dropout(torch.ones(R * D, device=cuda), p, seed, mask.view(-1))          # same counter convention (row * D + col)
+    y64 = y.double().requires_grad_(True)
+    g64, b64 = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    n = torch.nn.functional.layer_norm(y64, (D,), g64, b64, 1e-5)
+    r_ref = torch.relu(n)
+    o_ref = (r_ref + (x.double() if res else 0.0)) * mask.double()
+    assert (r.double() - r_ref).abs().max().item() < 2e-5
+    assert (out.double() - o_ref).abs().max().item() < 3e-5
+    if p > 0:
+        frac = (mask == 0).float().mean().item()
+        assert abs(frac - p) < 0.01
+    dout = torch.randn(R, D, generator=g).to(cuda)
+    o_ref.backward(dout.double())
+    dd = torch.empty(R, D, device=cuda) if p > 0 else None
+    dy, dgam, dbet = torch.empty(R, D, device=cuda), torch.empty(D, device=cuda), torch.empty(D, device=cuda)
+    ops.ln_relu_res_bwd(dout, y, gamma, r, mu, rstd, R, D, p, seed, dd, dy, dgam, dbet)
+    # elements whose pre-activation is within rounding of 0 can flip the relu mask: exclude rows containing such elements
+    safe = (n.detach().abs() > 1e-5).all(dim=1)
+    assert safe.float().mean().item() > 0.9
+    assert (dy.double() - y64.grad)[safe].abs().max().item() < 1e-4 * max(1.0, y64.grad.abs().max().item())
+    if safe.all():
+        assert (dgam.double() - g64.grad).abs().max().item() < 1e-4 * g64.grad.abs().max().item()
+        assert (dbet.double() - b64.grad).abs().max().item() < 1e-4 * b64.grad.abs().max().item()
+    if p > 0:
+        assert torch.equal(dd, dout * mask)
+    dgam2, dbet2, dy2 = torch.empty_like(dgam), torch.empty_like(dbet), torch.empty_like(dy)
+    ops.ln_relu_res_bwd(dout, y, gamma, r, mu, rstd, R, D, p, seed, dd, dy2, dgam2, dbet2)
+    assert torch.equal(dgam, dgam2) and torch.equal(dbet, dbet2) and torch.equal(dy, dy2)       # deterministic

@@ -6,7 +6,7 @@ import torch
 
 from oracle import nnr_oracle as O
 from oracle import reference_import as R
-from tests.util import GOLDEN_CASES, grad_digest, load_golden
+from tests.util import GOLDEN_CASES, grad_digest, load_big_golden, load_golden
 
 
 @pytest.mark.parametrize('name', list(GOLDEN_CASES))
@@ -20,7 +20,16 @@ def test_oracle_matches_golden_logits(name):
     np.testing.assert_allclose(out_stable.numpy(), z['logits_stable_sort'], rtol=0, atol=2e-5)
 
 
-@pytest.mark.parametrize('name', ['tiny', 'ablation'])
+def test_oracle_matches_full_length_golden_logits():
+    """full_b8 (8 impressions, every title 32 / abstract 128 tokens): inputs regenerated from the seeds and hash-checked"""
+    cfg, batch, z = load_big_golden('full_b8')
+    p = O.formula_params(cfg)
+    with torch.no_grad():
+        out = O.model_forward(p, cfg, batch, sort_fn=O.stable_sort, lstm_impl='aten')
+    np.testing.assert_allclose(out.numpy(), z['logits_stable_sort'], rtol=0, atol=2e-5 * float(np.abs(z['logits_stable_sort']).max()))
+
+
+@pytest.mark.parametrize('name', ['tiny', 'ablation', 'layer_norm', 'no_residual'])
 def test_oracle_matches_golden_gradients(name):
     cfg, batch, z = load_golden(name)
     cfg.dropout_rate = 0.0
