@@ -50,6 +50,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true', help='skip the per-op CUDA-event breakdown')
     ap.add_argument('--gemm-detail', action='store_true', help='print the per-shape GEMM table to stderr')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel of a step from the host instead of replaying a CUDA graph')
     ap.add_argument('--no-extras', action='store_true', help='skip the extra measurements (scoring, full-length regime)')
     ap.add_argument('--scoring-news', type=int, default=100000, help='news in the synthetic corpus of the scoring extra')
     return ap.parse_args()
@@ -270,7 +271,7 @@ def extra_full_lengths(a, ts, dev, peaks):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     with profiler.capture() as prof:
-        ts.step(*devb[0])
+        ts._eager_step(*devb[0])
         torch.cuda.synchronize()
     bd = prof.summary(steps=1)
     out = {'workload': workload_name(a).replace('%s_lengths' % a.lengths, 'full_lengths'), 'value': a.batch / (ms * 1e-3), 'unit': UNIT,
@@ -299,7 +300,7 @@ def main():
     import nnr_b200
     from nnr_b200 import ops
     from nnr_b200.synthetic import SyntheticMIND, batch_args, FIELDS
-    from nnr_b200.trainer import TrainStep
+    from nnr_b200.trainer import PackedBatch, TrainStep
 
     cfg = make_config(a)
     syn = SyntheticMIND(news_num=20000, vocabulary_size=a.vocab, lengths=a.lengths, seed=0)
@@ -308,7 +309,7 @@ def main():
     model = nnr_b200.Model(cfg)
     model.initialize()
     model.to(dev)
-    ts = TrainStep(model, lr=1e-4, gradient_clip_norm=4.0, world_size=world)
+    ts = TrainStep(model, lr=1e-4, gradient_clip_norm=4.0, world_size=world, cuda_graph=not a.no_graph)
     torch.manual_seed(1000 + rank)                            # dropout streams differ per rank
 
     nb = 4                                                    # distinct batches per rank, rotated
@@ -318,10 +319,14 @@ def main():
             if torch.is_tensor(b[k]):
                 b[k] = b[k].contiguous().pin_memory()
     devb = [batch_args(b, dev) for b in host]
+    # one contiguous buffer per batch: device-resident for `value`, pinned host memory for `e2e` (what a collate_fn +
+    # pin_memory worker hands over); a step is then ONE copy into the captured graph's input buffer + one graph launch
+    devp = [PackedBatch.pack(b, device=dev) for b in devb]
+    hostp = [PackedBatch.pack(batch_args(b), pin=True) for b in host]
     tok = sum(int(b['user_title_mask'].sum() + b['user_content_mask'].sum() + b['news_title_mask'].sum()
                   + b['news_content_mask'].sum()) for b in host) / nb
     slots = a.batch * 55 * 160
-    h2d = sum(v.numel() * v.element_size() for k, v in host[0].items() if k in FIELDS and torch.is_tensor(v))
+    h2d = hostp[0].flat.numel()
 
     def fresh(args):   # masks are mutated in place by the model (like the reference): idempotent, reuse is safe
         return args
@@ -333,18 +338,20 @@ def main():
 
     # ---- device-resident timing -------------------------------------------------------------
     for i in range(a.warmup):
-        ts.step(*fresh(devb[i % nb]))
+        ts.step(devp[i % nb])
     barrier()
     launches0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with Clocks(local_rank) as clk:
         e0.record()
         for i in range(a.steps):
-            loss = ts.step(*fresh(devb[i % nb]))
+            loss = ts.step(devp[i % nb])
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1)
     launches = ops.launch_count() - launches0
+    if ts.cuda_graph:            # kernels of this library inside one replayed graph (counted while it was captured) x replays
+        launches = a.steps * max(ts.launches_per_graph.values())
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -353,24 +360,27 @@ def main():
 
     # ---- end to end: pinned host batch -> device every step, loss read back every step ----------
     for i in range(2):                                        # untimed warm-up of this path (allocator, copy engine)
-        ts.step(*batch_args(host[i % nb], dev)).item()
+        ts.step(ts.prefetch(hostp[i % nb])).item()
     barrier()
     from nnr_b200.trainer import LossLog
 
     def run_e2e(blocking):
-        """K steps from pinned host batches; every step's loss is read back to the host inside the timed region:
-        blocking = float(loss) before the next step is enqueued (reference trainer.py:115); otherwise through
-        trainer.LossLog (pinned slot + event, consumed while the next step runs; all K values read before the end)"""
+        """K steps from pinned host batches; every step's inputs cross PCIe inside the timed region and every step's loss is
+        read back to the host: blocking = float(loss) before the next step is enqueued (reference trainer.py:115);
+        otherwise through trainer.LossLog (pinned slot + event, consumed while the next step runs; all K values read
+        before the end).  The next batch's host-to-device copy is enqueued on a copy stream before the host waits for
+        anything (what a pinned-memory DataLoader gives the reference)."""
         log = LossLog()
         vals = []
         e0.record()
-        args = batch_args(host[0], dev)                       # inside the timed region: every step's batch is copied H2D
+        nxt = ts.prefetch(hostp[0])                           # inside the timed region: every step's batch is copied H2D
         for i in range(a.steps):
-            loss = ts.step(*args)
+            cur = nxt
+            loss = ts.step(cur)
             if not blocking:
                 vals += log.push(loss, weight=a.batch)
-            if i + 1 < a.steps:                               # input prefetch, like a pinned-memory DataLoader: the next
-                args = batch_args(host[(i + 1) % nb], dev)    # batch's copies are enqueued before the host waits for a loss
+            if i + 1 < a.steps:
+                nxt = ts.prefetch(hostp[(i + 1) % nb])
             if blocking:
                 vals.append(loss.item())
         vals += log.drain()
@@ -417,9 +427,9 @@ def main():
         # every rank runs the two extra steps (they contain the gradient all-reduce); only rank 0 records events
         from nnr_b200 import profiler
         if rank == 0:
-            with profiler.capture() as prof:
+            with profiler.capture() as prof:              # per-op events need host launches: the same step, not replayed
                 for i in range(2):
-                    ts.step(*fresh(devb[i % nb]))
+                    ts._eager_step(*fresh(devb[i % nb]))
                 torch.cuda.synchronize()
             breakdown = prof.summary(steps=2)
             if a.gemm_detail:
@@ -429,7 +439,7 @@ def main():
             roofline_table = profiler.roofline_table(breakdown, ROOT)
         else:
             for i in range(2):
-                ts.step(*fresh(devb[i % nb]))
+                ts._eager_step(*fresh(devb[i % nb]))
             torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -454,6 +464,7 @@ def main():
             'config': {'workload': workload_name(a), 'global_batch': a.batch * world, 'parallelism': 'dp%d' % world,
                        'valid_token_fraction': tok / slots, 'tokens_per_step_per_gpu': tok,
                        'l2_policy': 'per-step working set (activations+stashes, GBs) >> 126 MB L2; %d rotating batches' % nb,
+                       'launch': 'cuda graph replay (one launch per step)' if ts.cuda_graph else 'host launches',
                        'loss': loss_host},
             'clocks': clk.summary(),
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,

@@ -13,6 +13,10 @@
  *     unless the argument is called `accumulate`.
  *   - launches go only to the passed stream; entry points are re-entrant.
  *   - fp32 everywhere unless the name says otherwise; token ids int32; masks uint8 (torch.bool).
+ *   - dropout `seed` arguments: a value below 2^62 is the seed itself.  With bit 62 set (NNR_SEED_INDIRECT) the seed is
+ *     indirect: bits 0..47 = device address of a uint64 base the caller advances on the device between steps, bits
+ *     48..61 = a site id; the kernels use hash(base + site).  This is what lets a whole training step be captured in a
+ *     CUDA graph and replayed with fresh masks (kernel arguments are frozen at capture).
  *
  * Token layout.  A CNE call sees N news rows with up to L tokens each.  `nnr_seq_prepare` turns
  * the [N,L] prefix mask into len[N], off[N+1] (exclusive prefix sum) and tok_row[N*L]; every
@@ -30,6 +34,7 @@ extern "C" {
 #endif
 
 #define NNR_ABI_VERSION 5
+#define NNR_SEED_INDIRECT (1ULL << 62)
 
 const char* nnr_last_error(void);
 int nnr_abi_version(void);
@@ -316,6 +321,12 @@ int nnr_flat_clip_adam(float* param, const float* grad, float* exp_avg, float* e
                        int64_t n, float lr, float beta1, float beta2, float eps, float max_norm,
                        float grad_scale, int32_t step, float* norm_out, void* workspace,
                        size_t workspace_bytes, void* stream);
+/* the same with Adam's step counter on the device: the call increments *step_dev (int32, starts at 0) and derives the
+ * bias corrections from it, so a CUDA graph that captured the call advances the step on every replay.               */
+int nnr_flat_clip_adam_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                           int64_t n, float lr, float beta1, float beta2, float eps, float max_norm,
+                           float grad_scale, int32_t* step_dev, float* norm_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -112,6 +112,7 @@ SIGNATURES = {
     'nnr_dropout': (C.c_int, [vp, i64, f32, u64, vp, vp]),
     'nnr_flat_clip_adam_workspace_bytes': (sz, [i64]),
     'nnr_flat_clip_adam': (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, i32, vp, vp, sz, vp]),
+    'nnr_flat_clip_adam_dev': (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp, vp, vp, sz, vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -65,6 +65,23 @@ __device__ __forceinline__ uint32_t mix32(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
   return (uint32_t)x;
 }
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return x;
+}
+// Dropout seeds cross the C ABI as uint64.  A value below 2^62 is used as is.  With bit 62 set (NNR_SEED_INDIRECT) the
+// seed is INDIRECT: bits 0..47 hold the device address of a uint64 base that the caller advances on the device once per
+// step, bits 48..61 a site id; the kernels then use hash(base + site).  A step captured in a CUDA graph replays with
+// fresh masks this way (kernel arguments are frozen at capture), and the backward of the same step resolves to the same
+// value as its forward because the base only moves between steps.
+#define NNR_SEED_INDIRECT (1ULL << 62)
+__device__ __forceinline__ uint64_t nnr_resolve_seed(uint64_t s) {
+  if (s & NNR_SEED_INDIRECT) {
+    const uint64_t base = *reinterpret_cast<const uint64_t*>(s & 0x0000FFFFFFFFFFFFULL);
+    return mix64(base + ((s >> 48) & 0x3FFFULL) * 0x9E3779B97F4A7C15ULL) >> 2;
+  }
+  return s;
+}
 // keep-scale: 0 if dropped, 1/(1-p) if kept.  p == 0 -> always 1.
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, float p, float inv_keep) {
   if (p <= 0.0f) return 1.0f;
@@ -75,10 +92,6 @@ __device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, floa
 // Four keep-scales from ONE 64-bit hash (16 uniform bits per element): used where the mask of a whole row of a
 // large tensor is regenerated (word-embedding gather / scatter: 300 elements per token), where the per-element
 // hash above is the bulk of the instruction count.  Element i of the tensor uses field (i & 3) of hash(i >> 2).
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
-  return x;
-}
 __device__ __forceinline__ void dropout_scale4(uint64_t seed, uint64_t idx4, float p, float inv_keep, float (&s)[4]) {
   const uint64_t r = mix64(seed * 0x9E3779B97F4A7C15ULL + idx4);
   const uint32_t thr = (uint32_t)(p * 65536.0f);

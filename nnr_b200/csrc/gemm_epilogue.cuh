@@ -21,7 +21,7 @@ __device__ __forceinline__ void epi_store(const EpiP& e, int m, int n, float acc
       float r = fmaxf(acc + (e.bias ? e.bias[n] : 0.f), 0.f);
       if (e.aux_out) e.aux_out[(size_t)m * e.ldaux_out + n] = r;
       v = r + (e.aux ? e.aux[(size_t)m * e.ldaux + n] : 0.f);
-      v *= dropout_scale(e.seed, (uint64_t)m * (uint64_t)e.N + n, e.p_drop, e.inv_keep);
+      v *= dropout_scale(nnr_resolve_seed(e.seed), (uint64_t)m * (uint64_t)e.N + n, e.p_drop, e.inv_keep);
       break;
     }
     case NNR_EPI_GATE: {

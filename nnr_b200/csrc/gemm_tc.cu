@@ -241,8 +241,9 @@ __device__ __forceinline__ void epi_finish4(const EpiP& e, int m, int n, float* 
       for (int i = 0; i < 4; ++i) v[i] += in.ax[i];
     }
     if (e.p_drop > 0.f) {
+      const uint64_t seed = nnr_resolve_seed(e.seed);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] *= dropout_scale(e.seed, (uint64_t)m * (uint64_t)e.N + n + i, e.p_drop, e.inv_keep);
+      for (int i = 0; i < 4; ++i) v[i] *= dropout_scale(seed, (uint64_t)m * (uint64_t)e.N + n + i, e.p_drop, e.inv_keep);
     }
   } else if (e.epilogue == NNR_EPI_GATE) {
 #pragma unroll
@@ -651,6 +652,7 @@ __global__ void __launch_bounds__(256) tc_split_colsum_kernel(const float* __res
                                                               const int32_t* __restrict__ r_dev, void* __restrict__ out,
                                                               size_t plane_stride, float* __restrict__ partial, SplitPre pre) {
   __shared__ float4 s_acc[256];
+  if (PRE && pre.p > 0.f) pre.seed = nnr_resolve_seed(pre.seed);
   int Rv = R;
   if (r_dev) Rv = min(R, *r_dev);
   const int Rw = r_dev ? min(R, (Rv + 63) / 64 * 64) : R;        // rows whose planes must be defined (zero tail)
@@ -1138,6 +1140,7 @@ __global__ void __launch_bounds__(256) embed_gather_planes_kernel(const float* _
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long slots = (long long)N * L;
+  if (p > 0.0f) seed = nnr_resolve_seed(seed);
   const int ncq = Cp >> 2, E4 = E >> 2;
   if (w >= slots) {                                                   // zero tail rows
     const int ntok = off[N];

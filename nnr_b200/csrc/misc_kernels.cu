@@ -143,6 +143,7 @@ __global__ void news_fuse_fwd_kernel(const float* __restrict__ ts, const float* 
                                      const int32_t* __restrict__ sub, int D2, int Ec, int Es, float p, float inv_keep,
                                      uint64_t seed, float* __restrict__ out) {
   int r = blockIdx.x;
+  if (p > 0.f) seed = nnr_resolve_seed(seed);
   const int DM = cs ? 2 * D2 : D2;                  // one or two modalities (CNE_Title / CNE_Content pass c_self = NULL)
   int Dout = DM + Ec + Es;
   float* o = out + (size_t)r * Dout;
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(NF_WARPS * 32) news_fuse_table_bwd_kernel(cons
                                                                           float p, float inv_keep, uint64_t seed,
                                                                           float* __restrict__ dtable, int accumulate) {
   __shared__ float s_part[NF_WARPS][NF_MAXE];
+  if (p > 0.f) seed = nnr_resolve_seed(seed);
   const int row = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int span = (N + NF_WARPS - 1) / NF_WARPS;
@@ -304,6 +306,7 @@ extern "C" int nnr_rowdot_bwd(const float* dout, const float* a, const float* b,
 // dropout
 // ------------------------------------------------------------------------------------------
 __global__ void dropout_kernel(const float* __restrict__ x, int64_t n, float p, float inv_keep, uint64_t seed, float* __restrict__ y) {
+  if (p > 0.f) seed = nnr_resolve_seed(seed);
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   y[i] = x[i] * dropout_scale(seed, (uint64_t)i, p, inv_keep);
@@ -319,8 +322,9 @@ extern "C" int nnr_dropout(const float* x, int64_t n, float p_drop, uint64_t see
 // clip_grad_norm_ + Adam over one flat buffer (trainer.py:118-120)
 // ------------------------------------------------------------------------------------------
 #define CA_BLOCKS 1184  // 148 SMs x 8
-__global__ void sumsq_stage1(const float* __restrict__ g, int64_t n, double* __restrict__ part) {
+__global__ void sumsq_stage1(const float* __restrict__ g, int64_t n, double* __restrict__ part, int32_t* __restrict__ step_dev) {
   __shared__ double sh[8];
+  if (step_dev && blockIdx.x == 0 && threadIdx.x == 0) *step_dev += 1;     // the update kernel (stream ordered after this one) reads it
   double acc = 0.0;
   int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
@@ -364,7 +368,13 @@ template <bool VEC>
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
                                                    float max_norm, float grad_scale, float bc1, float bc2_sqrt,
-                                                   const double* __restrict__ part, int nparts, float* __restrict__ norm_out) {
+                                                   const double* __restrict__ part, int nparts, float* __restrict__ norm_out,
+                                                   const int32_t* __restrict__ step_dev) {
+  if (step_dev) {       // device-side step counter (CUDA-graph replay): the bias corrections of step *step_dev, in double like the host path
+    const double st = (double)*step_dev;
+    bc1 = (float)(1.0 - pow((double)b1, st));
+    bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, st));
+  }
   const float total = grad_norm_from_partials(part, nparts, grad_scale);
   if (blockIdx.x == 0 && threadIdx.x == 0) norm_out[0] = total;
   float coef = 1.0f;
@@ -396,26 +406,42 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 extern "C" size_t nnr_flat_clip_adam_workspace_bytes(int64_t n) { (void)n; return CA_BLOCKS * sizeof(double); }
-extern "C" int nnr_flat_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                                  float beta1, float beta2, float eps, float max_norm, float grad_scale, int32_t step,
-                                  float* norm_out, void* workspace, size_t workspace_bytes, void* stream) {
-  NNR_REQUIRE(param && grad && exp_avg && exp_avg_sq && norm_out && workspace && n > 0 && step >= 1, NNR_ERR_ARG,
+static int flat_clip_adam_impl(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                               float beta1, float beta2, float eps, float max_norm, float grad_scale, int32_t step, int32_t* step_dev,
+                               float* norm_out, void* workspace, size_t workspace_bytes, void* stream) {
+  NNR_REQUIRE(param && grad && exp_avg && exp_avg_sq && norm_out && workspace && n > 0 && (step >= 1 || step_dev), NNR_ERR_ARG,
               "nnr_flat_clip_adam: bad arguments");
   NNR_REQUIRE(workspace_bytes >= CA_BLOCKS * sizeof(double), NNR_ERR_WORKSPACE, "nnr_flat_clip_adam: workspace too small");
   NNR_REQUIRE(nnr_aligned16(grad), NNR_ERR_ALIGN, "nnr_flat_clip_adam: grad must be 16B aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  sumsq_stage1<<<CA_BLOCKS, 256, 0, st>>>(grad, n, (double*)workspace);
+  sumsq_stage1<<<CA_BLOCKS, 256, 0, st>>>(grad, n, (double*)workspace, step_dev);
   NNR_LAUNCH_CHECK("sumsq_stage1");
-  double bc1d = 1.0 - pow((double)beta1, (double)step), bc2d = 1.0 - pow((double)beta2, (double)step);
+  double bc1d = 1.0, bc2d = 1.0;
+  if (!step_dev) { bc1d = 1.0 - pow((double)beta1, (double)step); bc2d = 1.0 - pow((double)beta2, (double)step); }
   const bool vec = (n % 4 == 0) && nnr_aligned16(param) && nnr_aligned16(exp_avg) && nnr_aligned16(exp_avg_sq);
   if (vec)
     adam_kernel<true><<<CA_BLOCKS, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, max_norm, grad_scale,
-                                                 (float)bc1d, (float)sqrt(bc2d), (const double*)workspace, CA_BLOCKS, norm_out);
+                                                 (float)bc1d, (float)sqrt(bc2d), (const double*)workspace, CA_BLOCKS, norm_out, step_dev);
   else
     adam_kernel<false><<<CA_BLOCKS, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, max_norm, grad_scale,
-                                                  (float)bc1d, (float)sqrt(bc2d), (const double*)workspace, CA_BLOCKS, norm_out);
+                                                  (float)bc1d, (float)sqrt(bc2d), (const double*)workspace, CA_BLOCKS, norm_out, step_dev);
   NNR_LAUNCH_CHECK("adam_kernel");
   return 0;
+}
+extern "C" int nnr_flat_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                  float beta1, float beta2, float eps, float max_norm, float grad_scale, int32_t step,
+                                  float* norm_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return flat_clip_adam_impl(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, max_norm, grad_scale, step, nullptr, norm_out,
+                             workspace, workspace_bytes, stream);
+}
+// the same with the step counter on the device: *step_dev is incremented by the call and the bias corrections are computed from
+// it, so a captured CUDA graph of the call advances Adam's step on every replay
+extern "C" int nnr_flat_clip_adam_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                      float beta1, float beta2, float eps, float max_norm, float grad_scale, int32_t* step_dev,
+                                      float* norm_out, void* workspace, size_t workspace_bytes, void* stream) {
+  NNR_REQUIRE(step_dev, NNR_ERR_ARG, "nnr_flat_clip_adam_dev: step_dev is NULL");
+  return flat_clip_adam_impl(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, max_norm, grad_scale, 0, step_dev, norm_out,
+                             workspace, workspace_bytes, stream);
 }
 
 // ------------------------------------------------------------------------------------------

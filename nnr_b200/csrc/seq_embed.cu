@@ -102,6 +102,7 @@ __global__ void embed_gather_kernel(const float* __restrict__ table, const int32
   if (slot >= N * L) return;
   int r = slot / L, t = slot - r * L;
   if (t >= len[r]) return;
+  if (p > 0.0f) seed = nnr_resolve_seed(seed);
   int id = ids[slot];
   id = min(max(id, 0), V - 1);
   const float* src = table + (size_t)id * E;
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(EB_CHUNK) eb_chunk_kernel(const float* __restr
   const int chunk = blockIdx.x;
   const int cs = chunk * EB_CHUNK;
   if (cs >= n_valid) return;
+  if (p > 0.0f) seed = nnr_resolve_seed(seed);
   const int ce = min(cs + EB_CHUNK, n_valid);
   const int cnt = ce - cs;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;

@@ -474,6 +474,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_relu_res_fwd_kernel(const fl
                                                                        float* __restrict__ mean, float* __restrict__ rstd) {
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= R) return;
+  if (p > 0.f) seed = nnr_resolve_seed(seed);
   float v[LN_MAXPL];
   float s = 0.f;
 #pragma unroll
@@ -514,6 +515,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_relu_res_bwd_kernel(const fl
                                                                        float* __restrict__ part_g, float* __restrict__ part_b) {
   __shared__ float s_g[LN_WARPS][32], s_b[LN_WARPS][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p > 0.f) seed = nnr_resolve_seed(seed);
   float ag[LN_MAXPL], ab[LN_MAXPL];
 #pragma unroll
   for (int j = 0; j < LN_MAXPL; ++j) { ag[j] = 0.f; ab[j] = 0.f; }

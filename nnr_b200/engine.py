@@ -20,8 +20,36 @@ from .ops import (EPI_ADD_AUX, EPI_BIAS, EPI_BIAS_RELU_RES, EPI_BIAS_TANH, EPI_G
 # torch.sort exactly as newsEncoders.py:112-115 calls it; tests swap in a stable sort on both sides
 sort_fn = torch.sort
 
+class SeedSource:
+    """Device-resident base of the dropout seeds (include/nnr_b200.h: NNR_SEED_INDIRECT).  Inside a step every dropout
+    site gets ``INDIRECT | site << 48 | address(base)``; ``advance()`` moves the base on the device (one tiny kernel on the
+    current stream), so a CUDA graph that captured the step draws fresh masks on every replay while the backward of a step
+    still sees the seeds of its forward."""
+    INDIRECT = 1 << 62
+    _GOLDEN = 0x9E3779B97F4A7C15 - (1 << 64)            # as a signed 64-bit increment
+
+    def __init__(self, device):
+        self.base = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).to(device)
+        self.site = 0
+
+    def advance(self):
+        self.base.add_(self._GOLDEN)
+        self.site = 0
+
+    def next(self):
+        self.site += 1
+        assert self.site < (1 << 14)
+        return self.INDIRECT | (self.site << 48) | self.base.data_ptr()
+
+
+seed_source = None        # trainer.TrainStep installs a SeedSource while it runs / captures a graph-mode step
+
+
 def fresh_seed():
-    """63-bit seed for the counter-based dropout RNG, drawn from torch's CPU RNG stream."""
+    """seed for the counter-based dropout RNG: drawn from torch's CPU RNG stream (a 62-bit value), or an indirect
+    device-side seed when a SeedSource is active"""
+    if seed_source is not None:
+        return seed_source.next()
     return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
 
 

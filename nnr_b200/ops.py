@@ -414,6 +414,16 @@ def flat_clip_adam(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, max_
                                  ws.data_ptr(), ws.numel(), _stream()), 'nnr_flat_clip_adam')
 
 
+def flat_clip_adam_dev(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, max_norm, grad_scale, step_dev, norm_out):
+    """nnr_flat_clip_adam with the step counter on the device (int32 tensor, incremented by the call): graph-capturable"""
+    n = param.numel()
+    nbytes = lib.nnr_flat_clip_adam_workspace_bytes(n)
+    ws = workspace(nbytes, param.device, 'adam')
+    check(lib.nnr_flat_clip_adam_dev(_p(param, _F32), _p(grad, _F32), _p(exp_avg, _F32), _p(exp_avg_sq, _F32), n, lr,
+                                     beta1, beta2, eps, max_norm, grad_scale, _p(step_dev, _I32), _p(norm_out, _F32),
+                                     ws.data_ptr(), ws.numel(), _stream()), 'nnr_flat_clip_adam_dev')
+
+
 # --------------------------------------------------------------------------------------------
 # registration as torch custom ops (torch.ops.nnr.*), CUDA dispatch key only
 # --------------------------------------------------------------------------------------------

@@ -20,10 +20,66 @@ def negative_log_softmax(logits):
     return (-torch.log_softmax(logits, dim=1).select(dim=1, index=0)).mean()
 
 
+class PackedBatch:
+    """The 21 model inputs of one batch in ONE contiguous byte buffer (device, or pinned host memory) plus the layout needed
+    to view it as tensors again: a step then needs a single copy into the static input buffer of the captured graph instead
+    of one copy per field (the reference issues 21 ``.cuda(non_blocking=True)`` calls per step, trainer.py:83-103)."""
+
+    def __init__(self, flat, layout):
+        self.flat, self.layout = flat, layout
+        self.staged = None                   # (device staging buffer, event) after TrainStep.prefetch
+
+    @staticmethod
+    def layout_of(batch):
+        layout, o = [], 0
+        for t in batch:
+            if torch.is_tensor(t):
+                nbytes = t.numel() * t.element_size()
+                layout.append((o, tuple(t.shape), t.dtype, nbytes))
+                o += (nbytes + 255) // 256 * 256
+            else:
+                layout.append(None)
+        return layout, max(o, 256)
+
+    @classmethod
+    def pack(cls, batch, device=None, pin=False):
+        layout, total = cls.layout_of(batch)
+        if pin:
+            flat = torch.empty(total, dtype=torch.uint8).pin_memory()
+        else:
+            flat = torch.empty(total, dtype=torch.uint8, device=device if device is not None else 'cpu')
+        pb = cls(flat, layout)
+        for v, t in zip(pb.views(), batch):
+            if v is not None:
+                v.copy_(t)
+        return pb
+
+    def views(self, flat=None):
+        flat = self.flat if flat is None else flat
+        out = []
+        for e in self.layout:
+            if e is None:
+                out.append(None)
+                continue
+            o, shape, dtype, nbytes = e
+            out.append(flat[o:o + nbytes].view(dtype).view(shape))
+        return out
+
+    def key(self):
+        return tuple(None if e is None else (e[1], e[2]) for e in self.layout)
+
+
 class TrainStep:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, gradient_clip_norm=4.0, process_group=None,
-                 world_size=None):
+                 world_size=None, cuda_graph=False):
+        """cuda_graph=True: every distinct batch layout is captured once (zero-grad, forward, loss, backward, gradient
+        all-reduce, clip+Adam, weight-plane refresh: a few hundred kernels) and replayed with one launch per step; dropout
+        seeds and Adam's step counter then live on the device (engine.SeedSource, nnr_flat_clip_adam_dev)."""
         self.model = model
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs = {}
+        self._copy_stream = None
+        self._stage = {}
         self.lr, self.betas, self.eps, self.max_norm = lr, betas, eps, gradient_clip_norm
         self.pg = process_group
         if world_size is None:
@@ -55,6 +111,9 @@ class TrainStep:
         self._refresh_weight_planes()
         self.step_count = 0
         self.grad_norm = torch.zeros(1, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev) if dev.type == 'cuda' else None   # graph mode
+        self.seeds = engine.SeedSource(dev) if (self.cuda_graph and dev.type == 'cuda') else None
+        self.launches_per_graph = {}
 
     def _refresh_weight_planes(self):
         engine.weights_changed()
@@ -71,15 +130,129 @@ class TrainStep:
                 raise RuntimeError('parameter .grad was rebound; use TrainStep.zero_grad() only')
 
     def step(self, *batch):
-        """one full training step; returns the (device) loss tensor without synchronising"""
+        """one full training step; returns the (device) loss tensor without synchronising.  ``batch`` is the 21 positional
+        tensors of Model.forward, or a single PackedBatch.  In graph mode the returned tensor is the graph's static loss
+        buffer: read (or copy) it before the next step."""
+        if len(batch) == 1 and isinstance(batch[0], PackedBatch):
+            if self.cuda_graph:
+                return self._graph_step(batch[0])
+            batch = batch[0].views(batch[0].flat.to(self.flat.device, non_blocking=True))
+        elif self.cuda_graph:
+            return self._graph_step(batch)
+        return self._eager_step(*batch)
+
+    def _eager_step(self, *batch):
         if not self.model.training:
             self.model.train()
+        self._check_grad_bindings()
         logits = self.model(*batch)
         loss = negative_log_softmax(logits)
         self.gflat.zero_()
         loss.backward()
         self.optimizer_step()
         return loss
+
+    def _check_grad_bindings(self):
+        """the engine adds gradients straight into the flat-buffer views; a ``model.zero_grad()`` / ``optimizer.zero_grad()``
+        with set_to_none=True unbinds them and the optimizer kernel would then see only zeros"""
+        lo, hi = self.gflat.data_ptr(), self.gflat.data_ptr() + self.gflat.numel() * 4
+        for p in self.params:
+            g = p.grad
+            if g is None or not (lo <= g.data_ptr() < hi):
+                raise RuntimeError('nnr_b200.TrainStep: a parameter .grad is no longer a view of the flat gradient buffer '
+                                   '(zero_grad(set_to_none=True)?); use TrainStep.zero_grad()')
+
+    # ---- graph mode -------------------------------------------------------------------------------------------------
+    def _graph_for(self, layout_key, example_views, layout):
+        g = self._graphs.get(layout_key)
+        if g is not None:
+            return g
+        dev = self.flat.device
+        total = PackedBatch.layout_of(example_views)[1]
+        static_flat = torch.empty(total, dtype=torch.uint8, device=dev)
+        spb = PackedBatch(static_flat, layout)
+        static = spb.views()
+        for s, t in zip(static, example_views):
+            if s is not None:
+                s.copy_(t)
+        # warm-up outside capture (lazy kernel attributes, workspaces, allocator), then restore the training state so that
+        # graph mode and eager mode walk the same trajectory
+        saved = [x.clone() for x in (self.flat, self.exp_avg, self.exp_avg_sq, self.step_dev, self.seeds.base)]
+        saved_count = self.step_count
+        engine.seed_source = self.seeds
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.seeds.advance()
+                    self._eager_step(*[s.clone() if torch.is_tensor(s) and s.dtype == torch.bool else s for s in static])
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            for dst, src in zip((self.flat, self.exp_avg, self.exp_avg_sq, self.step_dev, self.seeds.base), saved):
+                dst.copy_(src)
+            self.step_count = saved_count
+            self._refresh_weight_planes()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(graph):
+                self.seeds.advance()
+                loss = self._eager_step(*static)
+            self.launches_per_graph[layout_key] = ops.launch_count() - n0
+            self.step_count = saved_count
+        finally:
+            engine.seed_source = None
+        g = (static_flat, static, graph, loss)
+        self._graphs[layout_key] = g
+        return g
+
+    def _graph_step(self, batch):
+        if isinstance(batch, PackedBatch):
+            pb = batch
+            static_flat, static, graph, loss = self._graph_for(pb.key(), pb.views() if pb.flat.is_cuda else
+                                                               pb.views(pb.flat.to(self.flat.device)), pb.layout)
+            if pb.staged is not None:                        # prefetched on the copy stream: wait, then one D2D copy
+                buf, ev, ring, i = pb.staged
+                torch.cuda.current_stream().wait_event(ev)
+                static_flat.copy_(buf, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record()                                # the next prefetch into this staging buffer waits for this read
+                ring['events'][i] = done
+                pb.staged = None
+            else:
+                static_flat.copy_(pb.flat, non_blocking=True)
+        else:
+            layout, _ = PackedBatch.layout_of(batch)
+            key = tuple(None if e is None else (e[1], e[2]) for e in layout)
+            static_flat, static, graph, loss = self._graph_for(key, batch, layout)
+            for s, t in zip(static, batch):
+                if s is not None:
+                    s.copy_(t, non_blocking=True)
+        graph.replay()
+        self.step_count += 1
+        return loss
+
+    def prefetch(self, pb):
+        """enqueue the host-to-device copy of a pinned PackedBatch on a side stream (two rotating staging buffers), so that it
+        overlaps the step that is running; ``step(pb)`` then waits for it and moves it into the graph's input buffer"""
+        dev = self.flat.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        n = pb.flat.numel()
+        ring = self._stage.setdefault(n, {'bufs': [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(2)],
+                                          'events': [None, None], 'i': 0})
+        i = ring['i']
+        ring['i'] = 1 - i
+        buf = ring['bufs'][i]
+        if ring['events'][i] is not None:                    # the step that consumed this buffer last must have read it
+            self._copy_stream.wait_event(ring['events'][i])
+        with torch.cuda.stream(self._copy_stream):
+            buf.copy_(pb.flat, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        pb.staged = (buf, ev, ring, i)
+        return pb
 
     def step_ids(self, corpus, history_ids, history_len, candidate_ids):
         """index-only training step: the batch is gathered from a ``corpus.DeviceCorpus`` on the device"""
@@ -96,8 +269,12 @@ class TrainStep:
         if self.flat.device.type != 'cuda':
             raise RuntimeError('nnr_b200.TrainStep.optimizer_step needs CUDA (nnr_flat_clip_adam has no CPU path)')
         self.step_count += 1
-        ops.flat_clip_adam(self.flat, self.gflat, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
-                           self.eps, self.max_norm, 1.0 / self.world_size, self.step_count, self.grad_norm)
+        if self.cuda_graph:      # the step counter lives on the device so that a captured step advances it on every replay
+            ops.flat_clip_adam_dev(self.flat, self.gflat, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
+                                   self.eps, self.max_norm, 1.0 / self.world_size, self.step_dev, self.grad_norm)
+        else:
+            ops.flat_clip_adam(self.flat, self.gflat, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
+                               self.eps, self.max_norm, 1.0 / self.world_size, self.step_count, self.grad_norm)
         self._refresh_weight_planes()   # the kernel updates the parameters through raw pointers: re-split them (one launch)
 
 

@@ -434,3 +434,56 @@ def test_exact_fp32_gemm_variant_subprocess(cuda):
             "t.test_train_step_matches_oracle_clip_adam(d); print('simt-ok')")
     r = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and 'simt-ok' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def _graph_vs_eager_setup(cuda, dropout):
+    import nnr_b200
+    from nnr_b200.synthetic import SyntheticMIND, batch_args
+    from nnr_b200.trainer import TrainStep
+    cfg = O.make_config(vocabulary_size=800, max_history_num=10, max_title_length=16, max_abstract_length=40, subCategory_num=40,
+                        gcn_layer_num=2, dropout_rate=dropout)
+    syn = SyntheticMIND(news_num=300, vocabulary_size=800, subCategory_num=40, max_title_length=16, max_abstract_length=40,
+                        max_history_num=10, lengths='mind', seed=7)
+    batches = [batch_args(syn.batch(6, seed=s), cuda) for s in (1, 2, 3)]
+    p = O.formula_params(cfg)
+
+    def make(graph):
+        m = _build(cfg, p, cuda, train=True)
+        return m, TrainStep(m, lr=1e-3, gradient_clip_norm=4.0, world_size=1, cuda_graph=graph)
+    return batches, make
+
+
+def test_cuda_graph_step_equals_eager_step(cuda):
+    """TrainStep(cuda_graph=True): the captured step (zero-grad, forward, loss, backward, clip+Adam with the step counter on the
+    device, weight-plane refresh) replayed on three different batches walks the same trajectory as host-launched steps"""
+    from nnr_b200.trainer import PackedBatch
+    batches, make = _graph_vs_eager_setup(cuda, 0.0)
+    m_e, ts_e = make(False)
+    m_g, ts_g = make(True)
+    for i in range(5):
+        b = batches[i % 3]
+        le = ts_e.step(*[x.clone() if torch.is_tensor(x) else x for x in b]).item()
+        if i % 2 == 0:
+            lg = ts_g.step(*[x.clone() if torch.is_tensor(x) else x for x in b]).item()
+        else:                                                   # the packed path: one copy into the static input buffer
+            lg = ts_g.step(PackedBatch.pack([x.clone() if torch.is_tensor(x) else x for x in b], device=cuda)).item()
+        assert abs(le - lg) <= 1e-6 * max(1.0, abs(le)), (i, le, lg)
+    assert len(ts_g._graphs) == 1 and ts_g.step_count == 5 and int(ts_g.step_dev.item()) == 5
+    assert max(ts_g.launches_per_graph.values()) > 50
+    for (k, a), (_, b) in zip(m_e.named_parameters(), m_g.named_parameters()):
+        assert (a - b).abs().max().item() <= 1e-6 * max(1.0, a.abs().max().item()), k
+
+
+def test_cuda_graph_step_draws_fresh_dropout_masks(cuda):
+    """dropout seeds are indirect (a device-side base advanced inside the graph): replays of the SAME batch give different
+    losses, and a pinned host batch goes through prefetch (copy stream + staging ring) -> step"""
+    from nnr_b200.trainer import PackedBatch
+    batches, make = _graph_vs_eager_setup(cuda, 0.2)
+    m, ts = make(True)
+    ts.lr = 0.0                                                  # freeze the weights: only the masks differ between replays
+    host = PackedBatch.pack([x.cpu() if torch.is_tensor(x) else x for x in batches[0]], pin=True)
+    losses = []
+    for i in range(4):
+        losses.append(ts.step(ts.prefetch(host)).item())
+    assert all(np.isfinite(losses)) and len(set(losses)) == 4, losses
+    assert max(losses) - min(losses) < 0.5 * abs(np.mean(losses)) + 0.5
