@@ -270,6 +270,8 @@ def extra_full_lengths(a, ts, dev, peaks):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    ts._eager_step(*devb[1])
+    torch.cuda.synchronize()
     with profiler.capture() as prof:
         ts._eager_step(*devb[0])
         torch.cuda.synchronize()
@@ -419,6 +421,50 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ids = a.batch * world * a.steps / (t.item() / 1e3)
 
+    # ---- N > 1: what the scaling loss is made of: the collective alone, and the spread of the ranks' compute time ----------
+    scaling_detail = None
+    if world > 1:
+        barrier()
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            dist.all_reduce(ts.gflat, op=dist.ReduceOp.SUM)
+        e1.record()
+        barrier()
+        coll_all = e0.elapsed_time(e1) / reps
+        a_t, b_t = ts.stage_bounds['table']
+        e0.record()
+        for _ in range(reps):
+            dist.all_reduce(ts.gflat[a_t:b_t], op=dist.ReduceOp.SUM)
+        e1.record()
+        barrier()
+        coll_table = e0.elapsed_time(e1) / reps
+        ts.world_size = 1                                     # compute only: no collective, host-launched, per rank
+        for i in range(2):
+            ts._eager_step(*fresh(devb[i % nb]))
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(a.steps):
+            ts._eager_step(*fresh(devb[i % nb]))
+        e1.record()
+        torch.cuda.synchronize()
+        ts.world_size = world
+        mine = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev)
+        allms = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allms, mine)
+        allms = [float(x.item()) for x in allms]
+        # every rank changed its replica independently: restore identical parameters before anything else uses them
+        dist.broadcast(ts.flat, 0)
+        dist.broadcast(ts.exp_avg, 0)
+        dist.broadcast(ts.exp_avg_sq, 0)
+        ts._refresh_weight_planes()
+        scaling_detail = {'allreduce_whole_flat_buffer_ms': coll_all, 'allreduce_table_slice_ms': coll_table,
+                          'flat_buffer_bytes': ts.gflat.numel() * 4, 'table_slice_bytes': (b_t - a_t) * 4,
+                          'compute_only_ms_per_rank': allms, 'rank_skew_ms': max(allms) - sum(allms) / len(allms),
+                          'note': 'the collective alone (back to back after a barrier; the table slice is the part the step cannot '
+                                  'overlap), and each rank\'s host-launched step without any collective: a step of the job takes '
+                                  'max over ranks + the exposed part of the collective'}
+
     # ---- per-op breakdown with CUDA events (dominant kernel -> roofline) ---------------------------
     roofline = None
     roofline_table = None
@@ -426,6 +472,9 @@ def main():
     if not a.no_profile:
         # every rank runs the two extra steps (they contain the gradient all-reduce); only rank 0 records events
         from nnr_b200 import profiler
+        for i in range(2):                                    # host-launched warm-up (fills the eager allocator pool)
+            ts._eager_step(*fresh(devb[i % nb]))
+        torch.cuda.synchronize()
         if rank == 0:
             with profiler.capture() as prof:              # per-op events need host launches: the same step, not replayed
                 for i in range(2):
@@ -474,7 +523,7 @@ def main():
             'e2e_index_only': {'value': e2e_ids, 'unit': UNIT, 'h2d_bytes_per_step': ids_bytes, 'd2h_bytes_per_step': 4,
                                'corpus_bytes_resident': corpus.nbytes(),
                                'note': 'nnr_b200.corpus.DeviceCorpus + TrainStep.step_ids: ids in, batch gathered and graph built on the device'},
-            'gpu_launches': int(launches),
+            'gpu_launches': int(launches), 'scaling_detail': scaling_detail,
             'roofline': roofline, 'roofline_by_kernel': roofline_table, 'cpu_baseline': cpu, 'extra': extra,
             'breakdown_ms_per_step': breakdown}
     print(json.dumps(line))

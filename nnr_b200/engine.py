@@ -67,16 +67,29 @@ _weight_planes = {}
 _weight_epoch = 0
 
 
+# trainer.TrainStep registers a callback here: grads_ready(stage) is called from inside the backward pass as soon as a
+# group of parameter gradients is final in the flat gradient buffer ('sue': the user encoder's own parameters, 'cne': every
+# news-encoder parameter except the word table, 'table': the word-embedding gradient), so that the data-parallel reduction
+# of that group can start while the rest of the backward pass is still running (the reference's DDP does the same with
+# its gradient buckets, trainer.py:219,296-300).
+grads_ready = None
+
+
+def _notify(stage):
+    if grads_ready is not None:
+        grads_ready(stage)
+
+
 def _param_grads(P, names, G):
     """Gradients of the parameters for the tail of an autograd.Function.backward.  When every parameter's ``.grad`` is a
     preallocated buffer managed by trainer.TrainStep (flat gradient buffer, marked ``_nnr_flat_grad``), the gradients
     are added into those buffers with ONE multi-tensor add and ``None`` is returned to autograd, instead of ~70
     per-parameter AccumulateGrad add kernels per step."""
     if _flat_grads(P, names):
-        live = [k for k in names if G[k] is not None]        # None: already accumulated in place (embedding table)
+        live = [k for k in names if G.get(k) is not None]    # None: already accumulated in place (embedding table)
         torch._foreach_add_([P[k].grad for k in live], [G[k] for k in live])
         return (None,) * len(names)
-    return tuple(G[k] for k in names)
+    return tuple(G.get(k) for k in names)
 
 
 _SHARE_SPLITS = os.environ.get('NNR_SHARE_SPLITS', '1') != '0'   # A/B switch: split small operands once per tensor
@@ -480,6 +493,7 @@ class CNEFunction(torch.autograd.Function):
         in_place = _flat_grads(P, ctx.names) and wemb.grad.is_contiguous() and wemb.grad.data_ptr() % 16 == 0
         dtable = wemb.grad if in_place else _empty(wemb.shape, dev)
         first = not in_place
+        scatters = []
         for x, m in mods.items():
             pre = x + '_lstm.'
             db = _empty((8 * Hd,), dev)
@@ -512,10 +526,23 @@ class CNEFunction(torch.autograd.Function):
                 G[pre + 'bias_ih_l0' + sfx] = db[d * 4 * Hd:(d + 1) * 4 * Hd]
                 G[pre + 'bias_hh_l0' + sfx] = db[d * 4 * Hd:(d + 1) * 4 * Hd]
             demb = matmul_nn(dz, m.w_ih, m.cap, m.ntok, x_planes=dz_pl, w_planes=m.w_ih_pl)
-            del dz_pl
+            del dz_pl, hprev, hprev_pl
+            scatters.append((demb, m))
+        # every news-encoder gradient except the word table is final now: with a flat gradient buffer they are added in
+        # place and announced, so that their data-parallel reduction overlaps the two embedding scatters below
+        G['word_embedding.weight'] = None
+        pg = None
+        if in_place:
+            pg = _param_grads(P, ctx.names, G)
+            _notify('cne')
+        for demb, m in scatters:
             ops.embed_gather_bwd(demb, m.ids, m.len, m.off, dtable, m.p, m.seed, not first)
             first = False
-            del hprev, hprev_pl, demb
+        del scatters
+        ctx.t = ctx.c = None
+        if in_place:
+            _notify('table')
+            return (None,) * 7 + pg
         G['word_embedding.weight'] = None if in_place else dtable
         ctx.t = ctx.c = None
         return (None,) * 7 + _param_grads(P, ctx.names, G)
@@ -751,7 +778,9 @@ class SUEFunction(torch.autograd.Function):
         if not meta.get('gcn', True):                  # SUE_wo_GCN: gfeat is the history embedding itself
             G['intraCluster_K.bias'] = torch.zeros_like(P['intraCluster_K.bias'])
             ctx.sv = None
-            return (None, dg.view(B, H, D), dcand.view(B, n, D), None, None, None) + _param_grads(P, ctx.names, G)
+            pg = _param_grads(P, ctx.names, G)
+            _notify('sue')
+            return (None, dg.view(B, H, D), dcand.view(B, n, D), None, None, None) + pg
         # GCN backward.  gfeat = (x_L + x0)[:, :H]
         dxL = torch.zeros((B, Gn, D), device=dev)
         dxL[:, :H] = dg.view(B, H, D)
@@ -798,7 +827,9 @@ class SUEFunction(torch.autograd.Function):
             ops.dropout(dproxy_b, pe, seeds[L], dproxy_b)
         G['proxy_node_embedding'] = dproxy_b.sum(dim=0)
         ctx.xs = ctx.rs = ctx.aggs = ctx.sv = ctx.lns = None
-        return (None, dhist, dcand.view(B, n, D) if dcand is not None else None, None, None, None) + _param_grads(P, ctx.names, G)
+        pg = _param_grads(P, ctx.names, G)
+        _notify('sue')
+        return (None, dhist, dcand.view(B, n, D) if dcand is not None else None, None, None, None) + pg
 
 
 class RowDot(torch.autograd.Function):

@@ -85,7 +85,17 @@ class TrainStep:
         if world_size is None:
             world_size = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.world_size = world_size
-        params = [p for p in model.parameters() if p.requires_grad]
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]     # unique parameters, first name
+        # flat-buffer order = the order in which the backward pass finishes the gradients, so that each group is one
+        # contiguous slice that can be reduced as soon as it is final (engine.grads_ready): the user encoder's own
+        # parameters ('sue'), the news encoder without the word table ('cne'), the word-embedding table ('table', the last
+        # kernels of the backward pass and 60 % of the bytes)
+        def stage_of(name):
+            if name.endswith('word_embedding.weight'):
+                return 2
+            return 0 if (name.startswith('user_encoder.') and not name.startswith('user_encoder.news_encoder.')) else 1
+        named.sort(key=lambda np_: stage_of(np_[0]))                                 # stable: keeps the module order inside a group
+        params = [p for _, p in named]
         dev = params[0].device          # flat buffers / all-reduce are device agnostic; the optimizer kernel is CUDA only
         sizes = [(p.numel() + 3) // 4 * 4 for p in params]            # keep every slice 16-byte aligned
         total = sum(sizes)
@@ -94,13 +104,21 @@ class TrainStep:
         self.exp_avg = torch.zeros(total, device=dev)
         self.exp_avg_sq = torch.zeros(total, device=dev)
         o = 0
-        for p, s in zip(params, sizes):
+        bounds = [0, 0, 0, 0]
+        for (name, p), s in zip(named, sizes):
             n = p.numel()
             self.flat[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.flat[o:o + n].view(p.shape)
             p.grad = self.gflat[o:o + n].view(p.shape)
             p._nnr_flat_grad = True          # engine._param_grads adds straight into these views
             o += s
+            bounds[stage_of(name) + 1] = o
+        for i in range(1, 4):
+            bounds[i] = max(bounds[i], bounds[i - 1])
+        self.stage_bounds = {'sue': (bounds[0], bounds[1]), 'cne': (bounds[1], bounds[2]), 'table': (bounds[2], bounds[3])}
+        self.overlap = True               # reduce each group as soon as it is final, on a side stream (world_size > 1)
+        self._comm_stream = None
+        self._reduced = set()
         self.params = params
         # operand planes of every GEMM weight matrix, refreshed by one launch after each optimizer step (instead of one
         # small split launch per weight per step); embedding tables are gathered, not multiplied
@@ -148,7 +166,12 @@ class TrainStep:
         logits = self.model(*batch)
         loss = negative_log_softmax(logits)
         self.gflat.zero_()
-        loss.backward()
+        self._reduced = set()
+        engine.grads_ready = self._on_grads_ready
+        try:
+            loss.backward()
+        finally:
+            engine.grads_ready = None
         self.optimizer_step()
         return loss
 
@@ -259,10 +282,38 @@ class TrainStep:
         return self.step(*corpus.batch_from_ids(history_ids, history_len, candidate_ids))
 
     def reduce_gradients(self):
-        """the single collective of the step: SUM over ranks of the flat gradient buffer (the 1/world average
-        of DDP, trainer.py:219, is applied inside the fused clip+Adam kernel as grad_scale)"""
-        if self.world_size > 1:
+        """the collective of the step: SUM over ranks of the flat gradient buffer (the 1/world average of DDP, trainer.py:219,
+        is applied inside the fused clip+Adam kernel as grad_scale).  Groups that were already reduced during the backward
+        pass (``_on_grads_ready``) are skipped; what is left goes out as one all-reduce; the compute stream then waits for
+        the side stream."""
+        if self.world_size <= 1:
+            return
+        pending = [k for k in ('sue', 'cne', 'table') if k not in self._reduced]
+        if len(pending) == 3:
             dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
+        else:
+            for k in pending:
+                a, b = self.stage_bounds[k]
+                if b > a:
+                    dist.all_reduce(self.gflat[a:b], op=dist.ReduceOp.SUM, group=self.pg)
+            if self._comm_stream is not None:
+                torch.cuda.current_stream().wait_stream(self._comm_stream)
+        self._reduced = set()
+
+    def _on_grads_ready(self, stage):
+        """engine.grads_ready callback: the gradients of `stage` are final in the flat buffer -> start their all-reduce on the
+        communication stream while the compute stream goes on with the backward pass"""
+        if self.world_size <= 1 or not self.overlap or self.flat.device.type != 'cuda' or stage == 'table':
+            return                       # the table is the end of the backward pass: reduced on the compute stream
+        a, b = self.stage_bounds[stage]
+        if b <= a or stage in self._reduced:
+            return
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.flat.device)
+        self._comm_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._comm_stream):
+            dist.all_reduce(self.gflat[a:b], op=dist.ReduceOp.SUM, group=self.pg)
+        self._reduced.add(stage)
 
     def optimizer_step(self):
         self.reduce_gradients()
