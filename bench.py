@@ -493,9 +493,7 @@ def main():
     if world > 1:
         dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return finish(ts, world)
 
     cpu = None
     if not a.no_cpu_baseline and world == 1:
@@ -527,8 +525,22 @@ def main():
             'roofline': roofline, 'roofline_by_kernel': roofline_table, 'cpu_baseline': cpu, 'extra': extra,
             'breakdown_ms_per_step': breakdown}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish(ts, world)
+
+
+def finish(ts, world):
+    """N > 1: leave without tearing the NCCL communicator down -- destroying a process group whose collectives were captured
+    in CUDA graphs waits for minutes (measured: the first 2-GPU run of this round printed its line and then sat in
+    destroy_process_group until the driver's limit); the graphs are released first and every rank exits after a last barrier"""
+    if world <= 1:
+        return
+    ts._graphs.clear()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == '__main__':

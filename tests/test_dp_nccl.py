@@ -112,13 +112,20 @@ def _worker(rank, world, port, q):
             big = [k for k in ref if ref[k].numel() > 1000]
             close = sum(int((named[k].detach().cpu() - ref[k]).abs().median().item() < 2e-5) for k in big)
             assert close >= len(big) - 2, (graph, close, len(big))
+        del ts, m
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         q.put((rank, 'ok'))
     except Exception as ex:                                   # surface the failure in the parent
         import traceback
         q.put((rank, 'FAILED: %s\n%s' % (ex, traceback.format_exc())))
     finally:
-        if dist.is_initialized():
-            dist.destroy_process_group()
+        # no destroy_process_group(): tearing down a communicator whose collectives were captured in CUDA graphs takes minutes;
+        # the worker process ends here anyway
+        import sys
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def test_nccl_gradients_equal_mean_of_oracle_shard_gradients():
