@@ -125,6 +125,8 @@ def _worker(rank, world, port, q):
         # the worker process ends here anyway
         import sys
         sys.stdout.flush()
+        q.close()
+        q.join_thread()                                        # the result must reach the parent before the hard exit
         os._exit(0)
 
 
