@@ -50,6 +50,9 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true', help='skip the per-op CUDA-event breakdown')
     ap.add_argument('--gemm-detail', action='store_true', help='print the per-shape GEMM table to stderr')
+    ap.add_argument('--dtype', default='f32', choices=['f32', 'bf16'],
+                    help='f32: fp32-grade arithmetic (split-operand tensor-core products); bf16: the reduced-precision variant of '
+                         'BASELINE config 4 (one 16-bit product per GEMM and per recurrent step, fp32 accumulation)')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel of a step from the host instead of replaying a CUDA graph')
     ap.add_argument('--no-extras', action='store_true', help='skip the extra measurements (scoring, full-length regime)')
     ap.add_argument('--scoring-news', type=int, default=100000, help='news in the synthetic corpus of the scoring extra')
@@ -292,6 +295,8 @@ def main():
     a = parse()
     if a.impl == 'reference':
         return run_reference(a)
+    if a.dtype == 'bf16':
+        os.environ['NNR_GEMM_ALGO'] = 'bf16'                  # read once by libnnr_b200.so: GEMMs and the LSTM recurrence
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -507,11 +512,14 @@ def main():
         extra['scoring'] = extra_scoring(a, cfg, model, dev, peaks)
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic',
+            'dtype': a.dtype, 'data': 'synthetic',
             'config': {'workload': workload_name(a), 'global_batch': a.batch * world, 'parallelism': 'dp%d' % world,
                        'valid_token_fraction': tok / slots, 'tokens_per_step_per_gpu': tok,
                        'l2_policy': 'per-step working set (activations+stashes, GBs) >> 126 MB L2; %d rotating batches' % nb,
                        'launch': 'cuda graph replay (one launch per step)' if ts.cuda_graph else 'host launches',
+                       'arithmetic': ('bf16 variant: one 16-bit product per GEMM / recurrent step, fp32 accumulation, fp32 activations; '
+                                      'logits within 2e-2, gradients within 5e-2 of the fp64 reference per tensor (tests/test_model_gpu.py)')
+                       if a.dtype == 'bf16' else 'fp32-grade: split 16-bit operands, 3 tensor-core products per flop',
                        'loss': loss_host},
             'clocks': clk.summary(),
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,

@@ -987,18 +987,19 @@ static int run_tc(const nnr_gemm_args* a, cudaStream_t st) {
             ((uint32_t)(pl.block_n >> 3) << 17) | ((uint32_t)((pl.pair ? 2 * TC_BM : TC_BM) >> 4) << 24);
   p.partial = pl.split_k ? (float*)(ws + pl.partial_off) : nullptr;
   p.epi = make_epi(a);
-  static bool attr_set[2][2] = {{false, false}, {false, false}};
-  static int num_sms = 0;
-  if (!attr_set[BF16 ? 1 : 0][pl.pair]) {
+  // per-device caches: the dynamic shared-memory attribute is a property of (function, device), and so is the SM count
+  static bool attr_set[16][2][2] = {};
+  static int num_sms_tab[16] = {};
+  int dev = 0;
+  NNR_CUDA(cudaGetDevice(&dev));
+  dev &= 15;
+  if (!attr_set[dev][BF16 ? 1 : 0][pl.pair]) {
     if (pl.pair) NNR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     else NNR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set[BF16 ? 1 : 0][pl.pair] = true;
+    attr_set[dev][BF16 ? 1 : 0][pl.pair] = true;
   }
-  if (num_sms == 0) {
-    int dev = 0;
-    NNR_CUDA(cudaGetDevice(&dev));
-    NNR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  if (num_sms_tab[dev] == 0) NNR_CUDA(cudaDeviceGetAttribute(&num_sms_tab[dev], cudaDevAttrMultiProcessorCount, dev));
+  const int num_sms = num_sms_tab[dev];
   void* ph = nnr_prof_begin(0, -1.0, st);     // flops are filled in by the caller-side profiler (needs m_dev/k_dev)
   if (pl.pair) {
     long cap_tiles = (long)((a->M + 2 * TC_BM - 1) / (2 * TC_BM)) * ((a->N + pl.block_n - 1) / pl.block_n);

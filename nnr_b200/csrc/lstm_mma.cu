@@ -154,6 +154,7 @@ __device__ __forceinline__ int fwd_slot_unit(int kk) {
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+template <bool SINGLE>   // SINGLE: one 16-bit product (hi x hi) instead of the three split products -- the bf16 variant
 __global__ void __launch_bounds__(G::NT, 1)
 lstm_fwd_mma_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const int32_t* __restrict__ len,
                     const int32_t* __restrict__ off, const int32_t* __restrict__ order, int N, int ntiles,
@@ -338,24 +339,28 @@ lstm_fwd_mma_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, cons
             ad_l = a_hi ? zero_local : ad_h + G::F_HPLANE;
           }
           ldsm_x4(ad_h, f.ah[mt][0], f.ah[mt][1], f.ah[mt][2], f.ah[mt][3]);
-          ldsm_x4(ad_l, f.al[mt][0], f.al[mt][1], f.al[mt][2], f.al[mt][3]);
+          if (!SINGLE) ldsm_x4(ad_l, f.al[mt][0], f.al[mt][1], f.al[mt][2], f.al[mt][3]);
         }
         ldsm_x4(w_local + b_off + ks * 32, f.bh[0][0], f.bh[0][1], f.bh[1][0], f.bh[1][1]);
         ldsm_x4(w_local + b_off + 16 * PITCH + ks * 32, f.bh[2][0], f.bh[2][1], f.bh[3][0], f.bh[3][1]);
         ldsm_x2(w_local + b_off4 + ks * 32, f.bh[4][0], f.bh[4][1]);
-        ldsm_x4(w_local + G::F_W_PLANE + b_off + ks * 32, f.bl[0][0], f.bl[0][1], f.bl[1][0], f.bl[1][1]);
-        ldsm_x4(w_local + G::F_W_PLANE + b_off + 16 * PITCH + ks * 32, f.bl[2][0], f.bl[2][1], f.bl[3][0], f.bl[3][1]);
-        ldsm_x2(w_local + G::F_W_PLANE + b_off4 + ks * 32, f.bl[4][0], f.bl[4][1]);
+        if (!SINGLE) {
+          ldsm_x4(w_local + G::F_W_PLANE + b_off + ks * 32, f.bl[0][0], f.bl[0][1], f.bl[1][0], f.bl[1][1]);
+          ldsm_x4(w_local + G::F_W_PLANE + b_off + 16 * PITCH + ks * 32, f.bl[2][0], f.bl[2][1], f.bl[3][0], f.bl[3][1]);
+          ldsm_x2(w_local + G::F_W_PLANE + b_off4 + ks * 32, f.bl[4][0], f.bl[4][1]);
+        }
       };
       auto mma_all = [&](const Frag& f) {
+        if (!SINGLE) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int nt = 0; nt < NTW; ++nt) mma16816<true>(acc[mt][nt], f.al[mt], f.bh[nt][0], f.bh[nt][1]);
+            for (int nt = 0; nt < NTW; ++nt) mma16816<true>(acc[mt][nt], f.al[mt], f.bh[nt][0], f.bh[nt][1]);
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int nt = 0; nt < NTW; ++nt) mma16816<true>(acc[mt][nt], f.ah[mt], f.bl[nt][0], f.bl[nt][1]);
+            for (int nt = 0; nt < NTW; ++nt) mma16816<true>(acc[mt][nt], f.ah[mt], f.bl[nt][0], f.bl[nt][1]);
+        }
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -455,6 +460,7 @@ lstm_fwd_mma_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, cons
 // ------------------------------------------------------------------------------------------------
 // backward through time
 // ------------------------------------------------------------------------------------------------
+template <bool SINGLE>   // SINGLE: one 16-bit product (hi x hi) instead of the three split products -- the bf16 variant
 __global__ void __launch_bounds__(G::NT, 1)
 lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, const float* __restrict__ w_hh,
                     const int32_t* __restrict__ len, const int32_t* __restrict__ off, const int32_t* __restrict__ order,
@@ -786,25 +792,28 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
 #pragma unroll
         for (int pr = 0; pr < 3; ++pr) {
           ldsm_x4(w_local + b_row + pr * 16 * WP + bc, f.bh[2 * pr][0], f.bh[2 * pr][1], f.bh[2 * pr + 1][0], f.bh[2 * pr + 1][1]);
-          ldsm_x4(w_local + G::B_W_PLANE + b_row + pr * 16 * WP + bc, f.bl[2 * pr][0], f.bl[2 * pr][1], f.bl[2 * pr + 1][0],
-                  f.bl[2 * pr + 1][1]);
+          if (!SINGLE)
+            ldsm_x4(w_local + G::B_W_PLANE + b_row + pr * 16 * WP + bc, f.bl[2 * pr][0], f.bl[2 * pr][1], f.bl[2 * pr + 1][0],
+                    f.bl[2 * pr + 1][1]);
         }
         if (seven) {
           ldsm_x2(w_local + b_row6 + bc, f.bh[6][0], f.bh[6][1]);
-          ldsm_x2(w_local + G::B_W_PLANE + b_row6 + bc, f.bl[6][0], f.bl[6][1]);
+          if (!SINGLE) ldsm_x2(w_local + G::B_W_PLANE + b_row6 + bc, f.bl[6][0], f.bl[6][1]);
         }
       };
       auto mma_all = [&](const Frag& f) {
+        if (!SINGLE) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int nt = 0; nt < 7; ++nt)
-            if (nt < 6 || seven) mma16816<false>(acc[mt][nt], f.al[mt], f.bh[nt][0], f.bh[nt][1]);
+            for (int nt = 0; nt < 7; ++nt)
+              if (nt < 6 || seven) mma16816<false>(acc[mt][nt], f.al[mt], f.bh[nt][0], f.bh[nt][1]);
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int nt = 0; nt < 7; ++nt)
-            if (nt < 6 || seven) mma16816<false>(acc[mt][nt], f.ah[mt], f.bl[nt][0], f.bl[nt][1]);
+            for (int nt = 0; nt < 7; ++nt)
+              if (nt < 6 || seven) mma16816<false>(acc[mt][nt], f.ah[mt], f.bl[nt][0], f.bl[nt][1]);
+        }
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -861,7 +870,13 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
 }
 
 template <class K>
-int launch_cluster5(K kernel, size_t smem, int ntiles, cudaStream_t st, void** args, const char* name, int* cache, bool* attr_set) {
+int launch_cluster5(K kernel, size_t smem, int ntiles, cudaStream_t st, void** args, const char* name, int (*cache_tab)[16],
+                    bool (*attr_tab)[16], int variant) {
+  int dev = 0;
+  NNR_CUDA(cudaGetDevice(&dev));
+  dev &= 15;                                  // the attribute and the occupancy are per device (and per instantiation)
+  int* cache = &cache_tab[variant][dev];
+  bool* attr_set = &attr_tab[variant][dev];
   if (!*attr_set) {
     NNR_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     *attr_set = true;
@@ -898,16 +913,28 @@ extern "C" int nnr_debug_lstm_prof(unsigned long long* out16) {
 }
 #endif
 int nnr_lstm_mma_max_clusters = 0;   // reported by nnr_lstm_info
+extern "C" int nnr_gemm_default_algo(void);
+// the reduced-precision ("bf16") variant of BASELINE config 4: NNR_GEMM_ALGO=bf16 selects single-product tensor-core GEMMs and,
+// here, ONE 16-bit product per recurrent step instead of the three split products
+static int nnr_lstm_single_product() {
+  static int v = -1;
+  if (v < 0) v = (nnr_gemm_default_algo() == NNR_GEMM_TC_BF16) ? 1 : 0;
+  return v;
+}
 
 int nnr_lstm_fwd_mma(float* gx, const float* w_hh, const int32_t* len, const int32_t* off, const int32_t* order, int N,
                      float* h_out, float* c_stash, float* c_n, int32_t* tile_counters, cudaStream_t st) {
-  static int cache = 0;
-  static bool attr_set = false;
+  static int cache[2][16] = {};
+  static bool attr_set[2][16] = {};
   int ntiles = (N + G::MT - 1) / G::MT;
   NNR_CUDA(cudaMemsetAsync(tile_counters, 0, 2 * sizeof(int32_t), st));
   void* args[] = {&gx, &w_hh, &len, &off, &order, &N, &ntiles, &h_out, &c_stash, &c_n, &tile_counters};
-  int rc = launch_cluster5(lstm_fwd_mma_kernel, G::FWD_SMEM, ntiles, st, args, "lstm_fwd_mma_kernel", &cache, &attr_set);
-  nnr_lstm_mma_max_clusters = cache;
+  const int single = nnr_lstm_single_product();
+  int rc = single ? launch_cluster5(lstm_fwd_mma_kernel<true>, G::FWD_SMEM, ntiles, st, args, "lstm_fwd_mma_kernel<single>", cache, attr_set, 1)
+                  : launch_cluster5(lstm_fwd_mma_kernel<false>, G::FWD_SMEM, ntiles, st, args, "lstm_fwd_mma_kernel", cache, attr_set, 0);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  nnr_lstm_mma_max_clusters = cache[single][dev & 15];
   return rc;
 }
 
@@ -937,14 +964,16 @@ __global__ void lstm_dz_finish_kernel(const float* __restrict__ db_partial, int 
 int nnr_lstm_bwd_mma(float* gates, const float* c_stash, const float* w_hh, const int32_t* len, const int32_t* off,
                      const int32_t* order, int N, const float* dh, const float* dcn, int32_t* tile_counters, cudaStream_t st,
                      void* dz_planes, size_t plane_stride, int two_planes, float* db_partial, float* db, int cap) {
-  static int cache = 0;
-  static bool attr_set = false;
+  static int cache[2][16] = {};
+  static bool attr_set[2][16] = {};
   int ntiles = (N + G::MT - 1) / G::MT;
   NNR_CUDA(cudaMemsetAsync(tile_counters, 0, 2 * sizeof(int32_t), st));
   __nv_bfloat16* dzp = (__nv_bfloat16*)dz_planes;
   void* args[] = {&gates, &c_stash, &w_hh, &len, &off, &order, &N, &ntiles, &dh, &dcn, &tile_counters,
                   &dzp, &plane_stride, &two_planes, &db_partial};
-  int rc = launch_cluster5(lstm_bwd_mma_kernel, G::BWD_SMEM, ntiles, st, args, "lstm_bwd_mma_kernel", &cache, &attr_set);
+  int rc = nnr_lstm_single_product()
+               ? launch_cluster5(lstm_bwd_mma_kernel<true>, G::BWD_SMEM, ntiles, st, args, "lstm_bwd_mma_kernel<single>", cache, attr_set, 1)
+               : launch_cluster5(lstm_bwd_mma_kernel<false>, G::BWD_SMEM, ntiles, st, args, "lstm_bwd_mma_kernel", cache, attr_set, 0);
   if (rc || !dz_planes) return rc;
   const int cols = 8 * G::HID;
   lstm_dz_finish_kernel<<<(cols + 255) / 256 * 4, 256, 0, st>>>(db_partial, ntiles, cols, db, dzp, plane_stride, two_planes ? 2 : 1, cap, off + N);

@@ -246,8 +246,8 @@ def roofline_table(breakdown, root):
                 continue
             rows.append({'kernel': name, 'bound': 'tensor', 'ms': round(v['ms'], 3), 'achieved': round(v['tflops'], 1),
                          'unit': 'TFLOP/s (algorithmic)', 'peak': peaks['bf16_tflops'], 'frac': round(v['tflops'] / peaks['bf16_tflops'], 4),
-                         'mma_per_algorithmic_flop': 3 if name != 'gemm_tc_kernel' else products,
-                         'frac_of_peak_in_issued_mma': round((3 if name != 'gemm_tc_kernel' else products) * v['tflops'] / peaks['bf16_tflops'], 4)})
+                         'mma_per_algorithmic_flop': products,
+                         'frac_of_peak_in_issued_mma': round(products * v['tflops'] / peaks['bf16_tflops'], 4)})
         elif 'gbs' in v:
             rows.append({'kernel': name, 'bound': 'hbm', 'ms': round(v['ms'], 3), 'achieved': round(v['gbs'], 1), 'unit': 'GB/s (algorithmic)',
                          'peak': peaks['hbm_gbs'], 'frac': round(v['gbs'] / peaks['hbm_gbs'], 4)})

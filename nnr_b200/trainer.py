@@ -360,15 +360,15 @@ class LossLog:
     def push(self, loss, weight=1.0, lag=1):
         """enqueue the read of this step's (device) loss; returns the losses that are complete, waiting only if more than
         ``lag`` reads are outstanding"""
-        if len(self.pending) >= self.slots:
-            self._consume_one()
+        out = []
+        if len(self.pending) >= self.slots:                  # ring full (lag >= slots): that value is returned too
+            out += self._consume_one()
         slot = self.next
         self.next = (self.next + 1) % self.slots
         self.buf[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         self.pending.append((slot, ev, weight))
-        out = []
         while len(self.pending) > lag:
             out += self._consume_one()
         return out + self._consume(False)

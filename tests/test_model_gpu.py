@@ -487,3 +487,50 @@ def test_cuda_graph_step_draws_fresh_dropout_masks(cuda):
         losses.append(ts.step(ts.prefetch(host)).item())
     assert all(np.isfinite(losses)) and len(set(losses)) == 4, losses
     assert max(losses) - min(losses) < 0.5 * abs(np.mean(losses)) + 0.5
+
+
+def test_bf16_variant_model_level_tolerance_subprocess(cuda):
+    """BASELINE config 4 "bf16 variant": NNR_GEMM_ALGO=bf16 (read once per process -> child) = ONE 16-bit product per GEMM and
+    per LSTM step, fp32 accumulation.  Stated tolerance against the fp64 reference golden at the BASELINE shape
+    (full_b8: every abstract 128 steps long, the worst case for the recurrence):
+        logits   max|a-b| / max|b|  <= 2e-2        loss  |a-b| <= 1e-2
+        every gradient tensor:  max-abs + sampled entries within 5e-2 * max|g64| + 8x the fp32 reference's noise, and the
+        cosine of the sampled entries >= 0.999 for tensors with |g| well above that noise"""
+    import os, subprocess, sys
+    env = dict(os.environ, NNR_GEMM_ALGO='bf16')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = "import torch, tests.test_model_gpu as t; t._bf16_variant_check(torch.device('cuda:0')); print('bf16-ok')"
+    r = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'bf16-ok' in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def _bf16_variant_check(cuda):
+    from nnr_b200 import ops
+    from nnr_b200.trainer import negative_log_softmax
+    assert ops.default_algo() == ops.ALGO_BF16
+    for name in ('full_b8', 'config2'):
+        cfg, batch, z = load_big_golden(name)
+        S = BIG_CASES[name][5]
+        cfg.dropout_rate = 0.0
+        p = O.formula_params(cfg)
+        m = _build(cfg, p, cuda, train=True)
+        logits = m(*_args(batch, cuda))
+        loss = negative_log_softmax(logits)
+        loss.backward()
+        e_logits = rel_err(logits, torch.from_numpy(z['train_logits64']))
+        e_loss = abs(loss.item() - float(z['train_loss64']))
+        assert e_logits <= 2e-2 and e_loss <= 1e-2, (name, e_logits, e_loss)
+        named = dict(m.named_parameters())
+        worst = []
+        for k in [k for k in named if not k.startswith('user_encoder.news_encoder.')]:
+            mine, d32, d64 = grad_digest(named[k].grad, S), z['grad_' + k], z['grad64_' + k]
+            err = max(abs(mine[2] - d64[2]), np.abs(mine[3:] - d64[3:]).max())
+            noise = max(abs(d32[2] - d64[2]), np.abs(d32[3:] - d64[3:]).max())
+            worst.append((err / (5e-2 * d64[2] + 8 * noise + 1e-12), k, err, d64[2]))
+            a, b = mine[3:], d64[3:]
+            if np.abs(b).max() > 100 * noise and np.linalg.norm(b) > 0:
+                cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-300))
+                assert cos >= 0.999, (name, k, cos)
+        worst.sort(reverse=True)
+        print('bf16 variant, %s: logits rel err %.2e, |loss err| %.2e, worst gradient tensors %s' % (name, e_logits, e_loss, worst[:3]))
+        assert worst[0][0] < 1.0, (name, worst[:5])
