@@ -534,3 +534,58 @@ def _bf16_variant_check(cuda):
         worst.sort(reverse=True)
         print('bf16 variant, %s: logits rel err %.2e, |loss err| %.2e, worst gradient tensors %s' % (name, e_logits, e_loss, worst[:3]))
         assert worst[0][0] < 1.0, (name, worst[:5])
+
+
+def _reference_style_two_steps(cuda, wrap_ddp):
+    """the literal step of reference trainer.py:105-120 (and :285-300 under DDP) on the drop-in model: torch.optim.Adam,
+    optimizer.zero_grad(), loss.backward(), nn.utils.clip_grad_norm_(model.parameters(), 4), optimizer.step() -- no TrainStep"""
+    from nnr_b200.trainer import negative_log_softmax
+    cfg, batch, _ = load_golden('tiny')
+    cfg.dropout_rate = 0.0
+    p = O.formula_params(cfg)
+    model = _build(cfg, p, cuda, train=True)     # torch.optim updates in place -> ._version invalidates the cached weight planes
+    inner = model
+    if wrap_ddp:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[cuda.index or 0])
+    optimizer = torch.optim.Adam(filter(lambda q: q.requires_grad, inner.parameters()), lr=1e-3, weight_decay=0)
+    ref = {k: v.clone() for k, v in p.items()}
+    state = {}
+    for step in (1, 2):
+        logits = model(*_args(batch, cuda))
+        loss = negative_log_softmax(logits)
+        assert inner.news_encoder.auxiliary_loss is None and inner.user_encoder.auxiliary_loss is None      # trainer.py:109-114
+        epoch_loss = float(loss) * logits.size(0)
+        optimizer.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 4.0)
+        optimizer.step()
+        _, loss_ref, grads = O.forward_backward(ref, cfg, batch, sort_fn=O.stable_sort)
+        O.clip_and_adam(ref, grads, state, step, lr=1e-3, max_norm=4.0)
+        assert abs(epoch_loss / logits.size(0) - loss_ref.item()) < 1e-4
+    named = dict(inner.named_parameters())
+    close = 0
+    for k in ref:
+        d = (named[k].detach().cpu() - ref[k]).abs()
+        assert d.max().item() <= 2.5e-3, k
+        close += int(d.median().item() < 2e-5)
+    assert close >= len(ref) - 3, close
+
+
+def test_reference_trainer_step_sequence_on_the_drop_in_model(cuda):
+    _reference_style_two_steps(cuda, wrap_ddp=False)
+
+
+def test_reference_ddp_wrap_of_the_drop_in_model(cuda):
+    """trainer.py:212-219: DistributedDataParallel(model, device_ids=[rank]) around nnr_b200.Model (world size 1 here; the
+    2-rank gradient identity is tests/test_dp_nccl.py): DDP's reducer hooks fire on the gradients our autograd Functions return"""
+    import os
+    import torch.distributed as dist
+    if dist.is_initialized():
+        pytest.skip('a process group already exists in this process')
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    os.environ.setdefault('MASTER_PORT', '29533')
+    dist.init_process_group('nccl', rank=0, world_size=1, device_id=cuda)
+    try:
+        _reference_style_two_steps(cuda, wrap_ddp=True)
+    finally:
+        dist.destroy_process_group()
