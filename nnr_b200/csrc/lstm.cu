@@ -91,6 +91,8 @@ lstm_fwd_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const in
     lbar_init(&hfull[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  cluster_arrive();      // every CTA of the cluster runs before a peer writes into its shared memory
+  cluster_wait();
   uint32_t hph[2] = {0u, 0u};                       // phase parity per buffer (identical in every thread)
 
   const size_t GS = (size_t)2 * 4 * HID;  // gx row stride (both directions)
@@ -297,6 +299,8 @@ lstm_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, co
     lbar_init(rfree, CL);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  cluster_arrive();      // every CTA of the cluster runs before a peer writes into its shared memory
+  cluster_wait();
   uint32_t ph_full = 0u, ph_free = 0u;
 
   const size_t GS = (size_t)2 * 4 * HID;

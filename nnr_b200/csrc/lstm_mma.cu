@@ -202,6 +202,10 @@ lstm_fwd_mma_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, cons
     lbar_init(&hfull[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // every CTA of the cluster must have started before its shared memory is written from a peer (the tile index below, then
+  // the h exchange): compute-sanitizer racecheck flags the first remote store otherwise ("block that might not have entered yet")
+  cluster_arrive();
+  cluster_wait();
   uint32_t hph[2] = {0u, 0u};
   const size_t GS = (size_t)2 * 4 * HID;
   PROF_DECL
@@ -518,6 +522,8 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
     lbar_init(rfree, CL);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  cluster_arrive();      // all CTAs of the cluster are running before the first remote shared-memory store (see the forward kernel)
+  cluster_wait();
   uint32_t ph_full = 0u, ph_free = 0u;
   const size_t GS = (size_t)2 * 4 * HID;
   PROF_DECL
