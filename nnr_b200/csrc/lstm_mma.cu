@@ -118,6 +118,14 @@ __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.ar
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
+// L2 prefetch of a line a few recurrent steps ahead: the per-step gx / stash loads of all 29 clusters together see DRAM
+// latencies well above the ~2 us of MMA time they are supposed to hide behind (measured: 3.8 us per step for one tile alone,
+// 5.3 us with every cluster streaming), and there is no shared memory left for a deeper cp.async ring -- so the lines are
+// pulled into L2 early and the cp.async of the step before use finds them there.  NNR_LSTM_PFD = distance in steps, 0 = off.
+#ifndef NNR_LSTM_PFD
+#define NNR_LSTM_PFD 3
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -217,6 +225,7 @@ lstm_fwd_mma_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, cons
   const bool copy_role = w >= 4;                                 // warps 4-7 move the staging tile to / from global memory
   const int c_ch = tid & 15, c_rs = (tid - G::CT) >> 4;          // cooperative copy: chunk and row slot of a copy thread
   const uint32_t c_so = (uint32_t)(c_rs * G::SROW + c_ch * 16);  // its offset inside an array of the staging tile
+  const bool pf_lane = (c_ch == 0 || c_ch == 4 || c_ch == 8 || c_ch == 9);   // copy threads that issue the L2 prefetches
   const uint32_t b_off = (uint32_t)((w * 40 + (lane >> 4) * 8 + (lane & 7)) * PITCH + ((lane >> 3) & 1) * 16);
   const uint32_t b_off4 = (uint32_t)((w * 40 + 32 + (lane & 7)) * PITCH + ((lane >> 3) & 1) * 16);
   // where this lane's h values go inside this CTA's block of an h tile (plane 0; plane 1 is F_HPLANE further)
@@ -291,6 +300,11 @@ lstm_fwd_mma_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, cons
                 const float* g1 = dir ? g0 - GS : g0 + GS;
 #pragma unroll
                 for (int a = 0; a < 4; ++a) cp_async16(stg_local + c_so + rr * 8 * G::SROW + a * G::SARR, g1 + a * HID);
+              }
+              if (NNR_LSTM_PFD > 0 && pf_lane && s + NNR_LSTM_PFD < rl) {   // 160 B segment: chunks 0, 4, 8, 9 touch every line of it
+                const float* g3 = dir ? g0 - (size_t)NNR_LSTM_PFD * GS : g0 + (size_t)NNR_LSTM_PFD * GS;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) prefetch_l2(g3 + a * HID);
               }
             }
           }
@@ -539,6 +553,7 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
   const bool copy_role = w >= 4;                                 // warps 4-7 move the staging tile to / from global memory
   const int c_ch = tid & 15, c_rs = (tid - G::CT) >> 4;
   const uint32_t c_so = (uint32_t)(c_rs * G::SROW + c_ch * 16);
+  const bool pf_lane = (c_ch == 0 || c_ch == 4 || c_ch == 8 || c_ch == 9);   // copy threads that issue the L2 prefetches
   const bool leader = (tid == 96);                               // barrier / copy-engine duties (a warp with six n-tiles)
 
   for (;;) {
@@ -580,6 +595,15 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
 #pragma unroll
               for (int a = 0; a < 4; ++a) cp_async16(stg_local + c_so + rr * 8 * G::SROW + a * G::SARR, g1 + a * HID);
               cp_async16(stg_local + c_so + rr * 8 * G::SROW + 4 * G::SARR, dh + p * 2 * HID + (size_t)dir * HID + rank * UPC + c_ch * 4);
+            }
+            const int s3 = s1 - NNR_LSTM_PFD;                  // the iteration NNR_LSTM_PFD steps ahead: pull its lines into L2
+            if (NNR_LSTM_PFD > 0 && pf_lane && s3 >= 0 && s3 < c_len[rr]) {
+              const int t3 = dir ? (c_len[rr] - 1 - s3) : s3;
+              const size_t p3 = (size_t)c_off[rr] + t3;
+              const float* g3 = gates + p3 * GS + (size_t)dir * 4 * HID + rank * UPC + c_ch * 4;
+#pragma unroll
+              for (int a = 0; a < 4; ++a) prefetch_l2(g3 + a * HID);
+              prefetch_l2(dh + p3 * 2 * HID + (size_t)dir * HID + rank * UPC + c_ch * 4);
             }
           }
         }
