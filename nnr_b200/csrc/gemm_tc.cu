@@ -262,19 +262,6 @@ __device__ __forceinline__ void epi_finish4(const EpiP& e, int m, int n, float* 
   st4(e.C + (size_t)m * e.ldc + n, cnt, v);
 }
 
-// split-K schedule (see gemm_tc_kernel): CTA c owns items [W c / G, W (c + 1) / G); owner(i) = the CTA whose range holds item i
-__host__ __device__ __forceinline__ int tc_item_owner(long long i, int G, long long W) { return (int)(((i + 1) * G - 1) / W); }
-// plain (coherent) loads: the partial slice is rewritten by the same thread between chains, so no read-only path here
-__device__ __forceinline__ void ld4_cg(const float* p, int cnt, float* o) {
-  if (cnt == 4 && al16(p)) {
-    const float4 t = __ldcg(reinterpret_cast<const float4*>(p));
-    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] = (i < cnt) ? __ldcg(p + i) : 0.f;
-  }
-}
-
 template <bool BF16, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b, TcParams p) {
@@ -297,15 +284,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   const int kb_per = p.split_k ? p.chain_kb : max(nkb, 1);
   const int splits = p.split_k ? max(1, (nkb + kb_per - 1) / kb_per) : 1;
   const int total_tiles = m_tiles * n_tiles * splits;
-  // Work items.  Without split-K: item = output tile, static round-robin over the CTAs.  With split-K the items are ordered
-  // (output tile major, k chain minor) and CTA c owns the CONTIGUOUS range [W c / G, W (c + 1) / G): the chains of one
-  // output tile that fall into a CTA's range are accumulated by that CTA into ONE partial slice (slot = CTA index - index of
-  // the first CTA that touches the tile), so a tile leaves at most G / tiles + 2 partials instead of one per chain, and
-  // every CTA gets the same number of chains (+-1).  The schedule is a pure function of the sizes -> deterministic.
-  const long long W_items = total_tiles;
-  const long long it_begin = p.split_k ? (W_items * sched_id) / sched_n : sched_id;
-  const long long it_end = p.split_k ? (W_items * (sched_id + 1)) / sched_n : W_items;
-  const int it_step = p.split_k ? 1 : sched_n;
 
   // ---- smem carve-up ----
   const uint32_t a_tile = TC_BM * 128, b_tile = (uint32_t)b_rows * 128;
@@ -344,11 +322,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     // ===== TMA producer =====
     if (lane == 0) {
       int it = 0;
-      for (long long item = it_begin; item < it_end; item += it_step) {
-        const int tile = p.split_k ? (int)(item / splits) : (int)item;
-        const int z = p.split_k ? (int)(item - (long long)tile * splits) : 0;
+      for (int tile = sched_id; tile < total_tiles; tile += sched_n) {
         const int n_idx = tile % n_tiles, rest = tile / n_tiles;
-        const int m0 = (rest % m_tiles) * TILE_M + (int)rank * TC_BM, n0 = n_idx * p.block_n + (int)rank * b_rows;
+        const int m0 = (rest % m_tiles) * TILE_M + (int)rank * TC_BM, n0 = n_idx * p.block_n + (int)rank * b_rows, z = rest / m_tiles;
         const int kb0 = z * kb_per, kb1 = min(nkb, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % p.stages;
@@ -382,8 +358,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const uint32_t lbo = KELEM * 128;                               // bytes of one MN-group box
       const uint64_t a_step = p.a_mn ? (uint64_t)((BF16 ? 2048 : 1024) >> 4) : 2;   // descriptor advance per MMA
       const uint64_t b_step = p.b_mn ? (uint64_t)((BF16 ? 2048 : 1024) >> 4) : 2;
-      for (long long item = it_begin; item < it_end; item += it_step, ++tl) {
-        const int z = p.split_k ? (int)(item % splits) : 0;
+      for (int tile = sched_id; tile < total_tiles; tile += sched_n, ++tl) {
+        const int rest = tile / n_tiles;
+        const int z = rest / m_tiles;
         const int kb0 = z * kb_per, kb1 = min(nkb, kb0 + kb_per);
         const int buf = tl & 1;
         mbar_wait(&tmem_empty[buf], ((tl >> 1) & 1) ^ 1);              // epilogue has drained this accumulator
@@ -431,19 +408,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     const int c_begin = chalf ? ((nchunks + 1) >> 1) << 4 : 0;
     const int c_end = chalf ? p.block_n : ((nchunks + 1) >> 1) << 4;
     int tl = 0;
-    for (long long item = it_begin; item < it_end; item += it_step, ++tl) {
-      const int tile = p.split_k ? (int)(item / splits) : (int)item;
-      const int z = p.split_k ? (int)(item - (long long)tile * splits) : 0;
+    for (int tile = sched_id; tile < total_tiles; tile += sched_n, ++tl) {
       const int n_idx = tile % n_tiles, rest = tile / n_tiles;
-      const int m0 = (rest % m_tiles) * TILE_M + (int)rank * TC_BM, n0 = n_idx * p.block_n;
+      const int m0 = (rest % m_tiles) * TILE_M + (int)rank * TC_BM, n0 = n_idx * p.block_n, z = rest / m_tiles;
       const int kb0 = z * kb_per, kb1 = min(nkb, kb0 + kb_per);
-      // split-K: partial slice of this CTA for this output tile, and whether an earlier chain of the run already wrote it
-      int slot = 0;
-      bool run_cont = false;
-      if (p.split_k) {
-        slot = sched_id - tc_item_owner((long long)tile * splits, sched_n, W_items);
-        run_cont = (item > it_begin) && (z > 0);
-      }
       const int buf = tl & 1;
       const uint32_t lane_addr = tmem_base + buf * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
       // Each thread reads one accumulator row (tcgen05.ld 32x32b), the warp transposes 32 x 16 chunks through its
@@ -484,24 +452,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         }
         if (cnt > 0) {
           if (p.partial) {
-            float prev[4][4];
-            if (run_cont) {                      // written by this same thread one chain earlier: an L2 hit
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int mm = m0 + q * 32 + tr + 8 * i;
-                if (mm < M) ld4_cg(p.partial + ((size_t)slot * M + mm) * p.N + n, cnt, prev[i]);
-              }
-            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int mm = m0 + q * 32 + tr + 8 * i;
-              if (mm < M) {
-                if (run_cont) {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) o[i][e] += prev[i][e];
-                }
-                st4(p.partial + ((size_t)slot * M + mm) * p.N + n, cnt, o[i]);
-              }
+              if (mm < M) st4(p.partial + ((size_t)z * M + mm) * p.N + n, cnt, o[i]);
             }
           } else {
             Epi4In in[4];
@@ -539,52 +493,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   }
 }
 
-// deterministic combine of the split-K partials: an output tile owns the slices 0 .. (number of CTAs that touched it) - 1, which
-// is recomputed here from the same schedule (sizes from m_dev / k_dev) and added in slice order
-struct TcSched { int block_n, tile_m, chain_kb, kelem, grid; };
-__device__ __forceinline__ int tc_slots_of(int m, int n, int M, int N, int K, const TcSched sc) {
-  const int m_tiles = (M + sc.tile_m - 1) / sc.tile_m, n_tiles = (N + sc.block_n - 1) / sc.block_n;
-  const int nkb = (K + sc.kelem - 1) / sc.kelem;
-  const int splits = max(1, (nkb + sc.chain_kb - 1) / sc.chain_kb);
-  const long long W = (long long)m_tiles * n_tiles * splits;
-  const int tile = (m / sc.tile_m) * n_tiles + n / sc.block_n;
-  return tc_item_owner((long long)tile * splits + splits - 1, sc.grid, W) - tc_item_owner((long long)tile * splits, sc.grid, W) + 1;
-}
-__global__ void tc_splitk_reduce_kernel(const float* __restrict__ partial, int K, const int32_t* __restrict__ k_dev, TcSched sc, int M, int N,
-                                        const int32_t* __restrict__ m_dev, EpiP epi) {
+// deterministic combine of the split-K partials (number of active splits is recomputed from k_dev)
+__global__ void tc_splitk_reduce_kernel(const float* __restrict__ partial, int K, const int32_t* __restrict__ k_dev, int kelem,
+                                        int chain_kb, int M, int N, const int32_t* __restrict__ m_dev, EpiP epi) {
   if (m_dev) M = min(M, *m_dev);
   if (k_dev) K = min(K, *k_dev);
+  const int nkb = (K + kelem - 1) / kelem;
+  const int splits = max(1, (nkb + chain_kb - 1) / chain_kb);
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)M * N) return;
   int m = (int)(i / N), n = (int)(i - (size_t)m * N);
-  const int slots = tc_slots_of(m, n, M, N, K, sc);
   float acc = 0.f;
-  for (int s = 0; s < slots; ++s) acc += partial[((size_t)s * M + m) * N + n];
+  for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * M + m) * N + n];
   epi_store(epi, m, n, acc);
 }
-// N % 4 == 0 and block_n % 4 == 0: a thread combines four adjacent outputs (same tile) with 16-byte loads, four slices in flight;
-// the slices are added in the same ascending order as above (same bits), the epilogue is the 4-wide one of the main kernel
+// N % 4 == 0: a thread combines four adjacent outputs with 16-byte loads, four splits in flight; the splits are added in
+// the same ascending order as above (same bits), the epilogue is the 4-wide one of the main kernel
 __global__ void __launch_bounds__(256) tc_splitk_reduce4_kernel(const float* __restrict__ partial, int K, const int32_t* __restrict__ k_dev,
-                                                                TcSched sc, int M, int N, const int32_t* __restrict__ m_dev, EpiP epi) {
+                                                                int kelem, int chain_kb, int M, int N, const int32_t* __restrict__ m_dev,
+                                                                EpiP epi) {
   if (m_dev) M = min(M, *m_dev);
   if (k_dev) K = min(K, *k_dev);
+  const int nkb = (K + kelem - 1) / kelem;
+  const int splits = max(1, (nkb + chain_kb - 1) / chain_kb);
   const int N4 = N >> 2;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)M * N4) return;
   const int m = (int)(i / N4), n = (int)(i - (size_t)m * N4) * 4;
-  const int slots = tc_slots_of(m, n, M, N, K, sc);
   const size_t plane = (size_t)M * N;
   const float* src = partial + (size_t)m * N + n;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   int s = 0;
-  for (; s + 4 <= slots; s += 4) {
+  for (; s + 4 <= splits; s += 4) {
     float4 v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(s + u) * plane));
 #pragma unroll
     for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
   }
-  for (; s < slots; ++s) {
+  for (; s < splits; ++s) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)s * plane));
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
@@ -833,7 +780,7 @@ struct TcPlan {
   int a_mn, b_mn;               // MN-major flags
   int a_rows, a_cols, b_rows, b_cols;   // stored (row-major) shapes of the operands
   int a_cp, b_cp;               // plane pitches
-  int block_n, stages, split_k, chain_kb, max_splits, max_slots, grid, nplanes, kelem;
+  int block_n, stages, split_k, chain_kb, max_splits, nplanes, kelem;
   int pair;                     // 1: CTA-pair kernel (256-row tiles, B tile split across the pair)
   size_t a_plane, b_plane, a_off, b_off, partial_off, total, smem;
 };
@@ -915,30 +862,19 @@ static TcPlan make_plan(const nnr_gemm_args* a, int mode) {
     if (bnp) { pl.pair = 1; pl.block_n = bnp; }
   }
   long tiles = (long)((a->M + TC_BM - 1) / TC_BM) * ((a->N + pl.block_n - 1) / pl.block_n);
-  // split-K: (a) fill the machine when the output grid is small, (b) bound the TMEM accumulation chain.  The chains of an
-  // output tile are handed out as contiguous ranges (gemm_tc_kernel), so short chains cost no extra partial slices: aim at
-  // ~3 chains per CTA for balance, between 4 k-blocks and the accuracy limit of the accumulation chain
+  // split-K: (a) fill the machine when the output grid is small, (b) bound the TMEM accumulation chain
   int nkb_cap = (a->K + pl.kelem - 1) / pl.kelem;
   pl.split_k = 0;
   const int chain_k = chain_k_limit();
   pl.chain_kb = chain_k / pl.kelem;
   if (!pl.pair && tiles * 2 <= 148 && nkb_cap >= 8) {   // an output grid that already fills more than half the SMs is not split
-    long chain = ((long)nkb_cap * tiles) / (3 * 148);
+    int target = (int)((148 + tiles - 1) / tiles);
+    int chain = (nkb_cap + target - 1) / target;
     if (chain < 4) chain = 4;
     if (chain > chain_k / pl.kelem) chain = chain_k / pl.kelem;
-    if (chain < nkb_cap) { pl.split_k = 1; pl.chain_kb = (int)chain; }
+    if (chain < nkb_cap) { pl.split_k = 1; pl.chain_kb = chain; }
   }
   pl.max_splits = pl.split_k ? (nkb_cap + pl.chain_kb - 1) / pl.chain_kb : 1;
-  // partial slices per output tile: one per CTA that touches the tile (<= grid / tiles + 2, and never more than its chains);
-  // with a device-side row count the tile count is not known here, so the bound is the number of chains
-  pl.grid = 0;
-  pl.max_slots = 1;
-  if (pl.split_k) {
-    long cap_items = tiles * pl.max_splits;
-    pl.grid = (int)(cap_items < 148 ? cap_items : 148);
-    long slots = a->m_dev ? pl.max_splits : (pl.grid / tiles + 2);
-    pl.max_slots = (int)(slots < pl.max_splits ? slots : pl.max_splits);
-  }
   size_t stage = (size_t)pl.nplanes * ((size_t)TC_BM * 128 + (size_t)(pl.pair ? pl.block_n / 2 : pl.block_n) * 128);
   int stages = (int)(TC_SMEM_BUDGET / stage);
   if (stages < 2) stages = 2;
@@ -952,7 +888,7 @@ static TcPlan make_plan(const nnr_gemm_args* a, int mode) {
   pl.a_off = o; if (!a->A_planes) o = up(o + pl.a_plane * esz * pl.nplanes, 1024);
   pl.b_off = o; if (!a->B_planes) o = up(o + pl.b_plane * esz * pl.nplanes, 1024);
   pl.partial_off = o;
-  if (pl.split_k) o = up(o + (size_t)pl.max_slots * a->M * a->N * sizeof(float), 1024);
+  if (pl.split_k) o = up(o + (size_t)pl.max_splits * a->M * a->N * sizeof(float), 1024);
   pl.total = o;
   return pl;
 }
@@ -1082,23 +1018,19 @@ static int run_tc(const nnr_gemm_args* a, cudaStream_t st) {
   } else {
     long cap_tiles = (long)((a->M + TC_BM - 1) / TC_BM) * ((a->N + pl.block_n - 1) / pl.block_n) * pl.max_splits;
     int grid = (int)(cap_tiles < num_sms ? cap_tiles : num_sms);
-    if (pl.split_k) {
-      NNR_REQUIRE(num_sms >= pl.grid, NNR_ERR_UNSUPPORTED, "nnr_gemm(tc): split-K plan assumes >= %d SMs", pl.grid);
-      grid = pl.grid;                       // the partial-slice bound of make_plan and the reduce kernel use this grid
-    }
     gemm_tc_kernel<BF16, false><<<grid, TC_THREADS, pl.smem, st>>>(map_a, map_b, p);
     nnr_prof_end(ph, st);
     NNR_LAUNCH_CHECK("gemm_tc_kernel");
   }
   if (pl.split_k) {
     size_t tot = (size_t)a->M * a->N;
-    TcSched sc;
-    sc.block_n = pl.block_n; sc.tile_m = TC_BM; sc.chain_kb = pl.chain_kb; sc.kelem = pl.kelem; sc.grid = pl.grid;
     void* ph2 = nnr_prof_begin(2, 0.0, st);
     if (a->N % 4 == 0 && nnr_aligned16(p.partial))
-      tc_splitk_reduce4_kernel<<<(unsigned)((tot / 4 + 255) / 256), 256, 0, st>>>(p.partial, a->K, a->k_dev, sc, a->M, a->N, a->m_dev, p.epi);
+      tc_splitk_reduce4_kernel<<<(unsigned)((tot / 4 + 255) / 256), 256, 0, st>>>(p.partial, a->K, a->k_dev, pl.kelem, pl.chain_kb, a->M,
+                                                                                 a->N, a->m_dev, p.epi);
     else
-      tc_splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p.partial, a->K, a->k_dev, sc, a->M, a->N, a->m_dev, p.epi);
+      tc_splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p.partial, a->K, a->k_dev, pl.kelem, pl.chain_kb, a->M,
+                                                                            a->N, a->m_dev, p.epi);
     nnr_prof_end(ph2, st);
     NNR_LAUNCH_CHECK("tc_splitk_reduce_kernel");
   }

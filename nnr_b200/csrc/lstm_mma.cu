@@ -118,12 +118,11 @@ __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.ar
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
-// L2 prefetch of a line a few recurrent steps ahead: the per-step gx / stash loads of all 29 clusters together see DRAM
-// latencies well above the ~2 us of MMA time they are supposed to hide behind (measured: 3.8 us per step for one tile alone,
-// 5.3 us with every cluster streaming), and there is no shared memory left for a deeper cp.async ring -- so the lines are
-// pulled into L2 early and the cp.async of the step before use finds them there.  NNR_LSTM_PFD = distance in steps, 0 = off.
+// Optional L2 prefetch of the recurrent-step operands NNR_LSTM_PFD steps ahead (compile-time, 0 = off = default).  Measured in
+// round 2 with distance 3: no gain (4.71 -> 4.82 ms forward, 6.47 -> 6.51 ms BPTT at N = 3520, L = 128) -- a step is bound by
+// its own dependency chain (exchange wait -> ldmatrix/MMA -> cell -> exchange), not by the latency of the gx / stash loads.
 #ifndef NNR_LSTM_PFD
-#define NNR_LSTM_PFD 3
+#define NNR_LSTM_PFD 0
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
