@@ -58,6 +58,13 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// GEMM epilogues: the same functions from the hardware exp2 / reciprocal units (2 MUFU + 3 FP32 instructions instead of the
+// ~35 of expf + an IEEE division with its slow-path call).  ncu showed the sigmoid-gate epilogue issuing ~50 instructions per
+// output element and the K = 400 gate GEMM bound by exactly that (0.245 ms against 0.104 ms for the same product without an
+// epilogue).  Absolute error < 2e-7 (sigmoid), < 4e-7 (tanh) over the whole range; saturation and +-inf are handled by the
+// units (exp -> 0 / inf, 1 / inf -> 0).
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
 // Counter-based RNG for dropout masks: one 32-bit hash per element, reproducible from
 // (seed, element index) so the backward pass regenerates the forward mask instead of storing it.

@@ -16,7 +16,7 @@ __device__ __forceinline__ void epi_store(const EpiP& e, int m, int n, float acc
   float v;
   switch (e.epilogue) {
     case NNR_EPI_BIAS: v = acc + e.bias[n]; break;
-    case NNR_EPI_BIAS_TANH: v = tanhf(acc + e.bias[n]); break;
+    case NNR_EPI_BIAS_TANH: v = tanh_fast(acc + e.bias[n]); break;
     case NNR_EPI_BIAS_RELU_RES: {
       float r = fmaxf(acc + (e.bias ? e.bias[n] : 0.f), 0.f);
       if (e.aux_out) e.aux_out[(size_t)m * e.ldaux_out + n] = r;
@@ -25,7 +25,7 @@ __device__ __forceinline__ void epi_store(const EpiP& e, int m, int n, float acc
       break;
     }
     case NNR_EPI_GATE: {
-      float g = sigmoidf_(acc + e.rowbias[(size_t)e.rowmap[m] * e.ldrowbias + n]);
+      float g = sigmoid_fast(acc + e.rowbias[(size_t)e.rowmap[m] * e.ldrowbias + n]);
       if (e.aux_out) e.aux_out[(size_t)m * e.ldaux_out + n] = g;
       v = e.aux[(size_t)m * e.ldaux + n] * g;
       break;
