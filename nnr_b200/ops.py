@@ -440,16 +440,37 @@ _SCHEMAS = {
                  'int H, Tensor dh, Tensor dcn) -> ()', lstm_bwd),
     'lstm_shift_h': ('(Tensor h, Tensor len, Tensor off, Tensor tok_row, int N, int L, int H, Tensor(a!) hprev) -> ()',
                      lstm_shift_h),
-    'gcn_aggregate': ('(Tensor nnz, Tensor col, Tensor val, Tensor x, int B, int G, int D, Tensor(a!) out) -> ()',
+    'gcn_aggregate': ('(Tensor nnz, Tensor col, Tensor val, Tensor x, int B, int G, int D, Tensor(a!) out, Tensor? add=None) -> ()',
                       gcn_aggregate),
     'graph_to_csr': ('(Tensor graph, bool transpose, Tensor(a!) nnz, Tensor(b!) col, Tensor(c!) val) -> ()', graph_to_csr),
+    'sue_graph_build': ('(Tensor categories, Tensor history_len, int C_num, Tensor(a!)? graph=None, Tensor(b!)? category_mask=None, '
+                        'Tensor(c!)? category_indices=None, int flags=0) -> ()', sue_graph_build),
     'cluster_intra_fwd': ('(Tensor Kp, Tensor Qp, Tensor g, Tensor idx, int B, int n, int H, int Au, int D, int C1, '
                           'float scale, Tensor(a!) alpha, Tensor(b!) intra) -> ()', cluster_intra_fwd),
+    'cluster_intra_bwd': ('(Tensor dintra, Tensor Kp, Tensor Qp, Tensor g, Tensor idx, Tensor alpha, int B, int n, int H, int Au, int D, '
+                          'int C1, float scale, Tensor(a!) da_ws, Tensor(b!) dKp, Tensor(c!) dQp, Tensor(d!) dg, bool accumulate_dg) -> ()',
+                          cluster_intra_bwd),
     'rowdot_fwd': ('(Tensor a, Tensor b, int R, int D, Tensor(a!) out) -> ()', rowdot_fwd),
+    'rowdot_bwd': ('(Tensor dout, Tensor a, Tensor b, int R, int D, Tensor(a!) da, bool accumulate_a, Tensor(b!) db, bool accumulate_b) -> ()',
+                   rowdot_bwd),
+    'news_fuse_fwd': ('(Tensor ts, Tensor? tc, Tensor? cs, Tensor? cc, Tensor cat_table, Tensor sub_table, Tensor cat, Tensor sub, int N, '
+                      'int D2, float p_drop, int seed, Tensor(a!) out) -> ()', news_fuse_fwd),
+    'news_fuse_bwd': ('(Tensor dout, Tensor cat, Tensor sub, int N, int D2, float p_drop, int seed, Tensor(a!) d_a, Tensor(b!)? d_b, '
+                      'Tensor(c!) dcat_table, Tensor(d!) dsub_table, bool accumulate) -> ()', news_fuse_bwd),
+    'colsum': ('(Tensor X, int ldx, int M, int N, Tensor(a!) out, bool accumulate=False, Tensor? m_dev=None) -> ()', colsum),
+    'segment_colsum': ('(Tensor X, int ldx, Tensor off, int N, int D, Tensor(a!) out, int ldo) -> ()', segment_colsum),
+    'gate_bwd_pre': ('(Tensor dhg, Tensor h, Tensor g, int n_max, Tensor n_dev, int D, Tensor(a!) dz, Tensor(b!) dh0) -> ()', gate_bwd_pre),
+    'ln_relu_res_fwd': ('(Tensor y, Tensor gamma, Tensor beta, Tensor? res, int R, int D, float eps, float p_drop, int seed, Tensor(a!) out, '
+                        'Tensor(b!) relu_out, Tensor(c!) mean, Tensor(d!) rstd) -> ()', ln_relu_res_fwd),
+    'ln_relu_res_bwd': ('(Tensor dout, Tensor y, Tensor gamma, Tensor relu_out, Tensor mean, Tensor rstd, int R, int D, float p_drop, int seed, '
+                        'Tensor(a!)? dout_dropped, Tensor(b!) dy, Tensor(c!) dgamma, Tensor(d!) dbeta) -> ()', ln_relu_res_bwd),
     'dropout': ('(Tensor x, float p_drop, int seed, Tensor(a!) y) -> ()', dropout),
     'flat_clip_adam': ('(Tensor(a!) param, Tensor grad, Tensor(b!) exp_avg, Tensor(c!) exp_avg_sq, float lr, float beta1, '
                        'float beta2, float eps, float max_norm, float grad_scale, int step, Tensor(d!) norm_out) -> ()',
                        flat_clip_adam),
+    'flat_clip_adam_dev': ('(Tensor(a!) param, Tensor grad, Tensor(b!) exp_avg, Tensor(c!) exp_avg_sq, float lr, float beta1, '
+                           'float beta2, float eps, float max_norm, float grad_scale, Tensor(e!) step_dev, Tensor(d!) norm_out) -> ()',
+                           flat_clip_adam_dev),
 }
 
 
@@ -461,5 +482,25 @@ for _name, (_schema, _fn) in _SCHEMAS.items():
     _torch_lib.define(_name + _schema)
     _torch_lib.impl(_name, _fn, 'CUDA')
     _torch_lib.impl(_name, _noop, 'Meta')
+
+
+def _via_dispatcher(name):
+    op = getattr(torch.ops.nnr, name)
+
+    def call(*a, **k):
+        return op(*a, **k)
+    call.__name__ = name
+    call.__doc__ = 'torch.ops.nnr.%s (CUDA dispatch key) -> %s' % (name, _SCHEMAS[name][1].__doc__ or 'C-ABI nnr_' + name)
+    return call
+
+
+# The engine reaches these ops through PyTorch's dispatcher (torch.ops.nnr.*): module attributes are rebound to dispatcher
+# calls, the registered CUDA implementations are the ctypes wrappers above.  NNR_TORCH_OPS=0 calls the wrappers directly.
+# Ops whose arguments are argument STRUCTS of the C ABI (nnr_gemm, nnr_attn_pool_*) or that return operand-plane handles
+# (tc_split*, *_planes*) are plain functions: a dispatcher schema cannot carry them.
+import os as _os
+DISPATCHED = sorted(_SCHEMAS) if _os.environ.get('NNR_TORCH_OPS', '1') != '0' else []
+for _name in DISPATCHED:
+    globals()[_name] = _via_dispatcher(_name)
 
 launch_count = _lib.launch_count

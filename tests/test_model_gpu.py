@@ -589,3 +589,33 @@ def test_reference_ddp_wrap_of_the_drop_in_model(cuda):
         _reference_style_two_steps(cuda, wrap_ddp=True)
     finally:
         dist.destroy_process_group()
+
+
+def test_engine_reaches_the_kernels_through_torch_ops(cuda):
+    """north_star: "a thin C-ABI extension registered as torch custom ops".  Every op whose arguments fit a dispatcher schema is
+    called by the engine as torch.ops.nnr.<name>; a forward + backward of the model must therefore show up in a
+    TorchDispatchMode, and those ops must be real dispatcher entries (no CPU kernel: a CPU tensor is refused)."""
+    from torch.utils._python_dispatch import TorchDispatchMode
+    from nnr_b200 import ops
+    from nnr_b200.trainer import negative_log_softmax
+    assert len(ops.DISPATCHED) >= 20 and ops.lstm_fwd.__doc__.startswith('torch.ops.nnr.lstm_fwd')
+    seen = {}
+
+    class Spy(TorchDispatchMode):
+        def __torch_dispatch__(self, func, types, args=(), kwargs=None):
+            name = str(func)
+            if name.startswith('nnr.'):
+                seen[name.split('.')[1]] = seen.get(name.split('.')[1], 0) + 1
+            return func(*args, **(kwargs or {}))
+
+    cfg, batch, z = load_golden('tiny')
+    cfg.dropout_rate = 0.1
+    m = _build(cfg, O.formula_params(cfg), cuda, train=True)
+    with Spy():
+        loss = negative_log_softmax(m(*_args(batch, cuda)))
+        loss.backward()
+    for name in ('seq_prepare', 'lstm_fwd', 'gcn_aggregate', 'graph_to_csr', 'cluster_intra_fwd', 'cluster_intra_bwd', 'rowdot_fwd',
+                 'rowdot_bwd', 'news_fuse_fwd', 'news_fuse_bwd', 'embed_gather_bwd', 'dropout'):
+        assert seen.get(name, 0) >= 1, (name, seen)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        torch.ops.nnr.rowdot_fwd(torch.zeros(2, 4), torch.zeros(2, 4), 2, 4, torch.zeros(2))
