@@ -23,6 +23,7 @@
 #include "../../include/nnr_b200.h"
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 // optional in-kernel phase timing (clock64 of one lane of CTA 0), compiled in with -DNNR_LSTM_PROF
 #ifdef NNR_LSTM_PROF
@@ -59,6 +60,19 @@ struct G {
   static constexpr int B_NARR = 5;                       // i, f, g, o (stash in, dz out), dh
   static constexpr size_t BWD_SMEM = 2 * (size_t)B_W_PLANE + 2 * (size_t)B_Z_PLANE + 2 * (size_t)B_RECV + B_NARR * (size_t)SARR + 3 * MT * sizeof(int);
   static constexpr uint32_t B_TX = CL * B_RBLK;
+};
+
+
+// forward variant with the W slice in TENSOR MEMORY (lstm_fwd_tm_kernel): 4 compute + 2 copy warps, no W planes in shared memory
+struct G2 {
+  static constexpr int HID = G::HID, CL = G::CL, MT = G::MT, UPC = G::UPC, COLS = G::COLS, UPW = G::UPW, NTW = G::NTW;
+  static constexpr int CT = 128, NT = 192;
+  static constexpr int FK = G::FK, FKS = G::FKS;
+  static constexpr int F_HROW = G::F_HROW, F_HPLANE = G::F_HPLANE, F_HBLK = G::F_HBLK, F_HBUF = G::F_HBUF;
+  static constexpr int SROW = G::SROW, SARR = G::SARR, F_NARR = G::F_NARR;
+  static constexpr uint32_t F_TX = G::F_TX;
+  static constexpr int TM_COLS = 256;                      // 12 k-steps x 20 + 10 = 250 columns used
+  static constexpr size_t FWD_SMEM = 2 * (size_t)F_HBUF + 16 + F_NARR * (size_t)SARR + 3 * MT * sizeof(int);
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -473,6 +487,381 @@ lstm_fwd_mma_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, cons
   cluster_arrive();
   cluster_wait();
 }
+
+// ------------------------------------------------------------------------------------------------
+// forward, W slice in tensor memory, two CTAs per SM (see the comment at the W fill)
+// ------------------------------------------------------------------------------------------------
+template <bool SINGLE>   // SINGLE: one 16-bit product (hi x hi) instead of the three split products -- the bf16 variant
+__global__ void __launch_bounds__(G2::NT, 2)
+lstm_fwd_tm_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const int32_t* __restrict__ len,
+                    const int32_t* __restrict__ off, const int32_t* __restrict__ order, int N, int ntiles,
+                    float* __restrict__ h_out, float* __restrict__ c_stash, float* __restrict__ c_n, int* __restrict__ tile_counter) {
+  constexpr int HID = G2::HID, CL = G2::CL, MT = G2::MT, UPC = G2::UPC, COLS = G2::COLS, NTW = G2::NTW, UPW = G2::UPW;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* Hsm = smem_raw;                                   // [2 buffers][CL blocks][2 planes][MT][80 B]
+  unsigned char* Zero16 = Hsm + 2 * G2::F_HBUF;                     // the K pad chunk
+  unsigned char* Stg = Zero16 + 16;                                // [F_NARR][MT][SROW] staging tile
+  int* s_row = reinterpret_cast<int*>(Stg + G2::F_NARR * G2::SARR);
+  int* s_len = s_row + MT;
+  int* s_off = s_len + MT;
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cluster_id = blockIdx.x / CL;
+  const int dir = cluster_id & 1;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int q = lane & 3, r8 = lane >> 2;
+  const int R = r8 + 8 * q;                     // the tile row this lane owns in the point-wise phase
+  const int unit0 = rank * UPC + w * UPW;       // first of the lane's ten hidden units
+
+  // ---- W slice -> TENSOR MEMORY, already in mma.sync B-fragment form.  Lane l of compute warp w (TMEM lanes 32 w + l; a warp
+  // can only reach the lane quarter of its own index) keeps, for every k-step ks and n8 tile nt of the warp's 40 gate
+  // columns, the registers b0 = W[n][16 ks + 2 (l % 4) + {0, 1}], b1 = the same 8 further along k, n = 40 w + 8 nt + l / 4
+  // (rows in (warp, n-tile, gate, unit) order, k permuted by fwd_slot_unit like the h operand), as fp16 hi and lo:
+  // columns ks * 20 + {0..9: hi (nt, b0/b1), 10..19: lo}; the last k-step (k = 192..207, upper half = zero pad) only
+  // stores b0: columns 240 + {0..4: hi, 5..9: lo}.  250 of the 256 allocated columns.  This frees the 2 x 69 KB the W
+  // planes took in shared memory: two CTAs (of two different clusters) now share an SM, and the tensor pipe is busy with
+  // one CTA's products while the other CTA is in its exchange wait / cell / store phases.
+  __shared__ uint32_t tmem_slot;
+  if (w == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr_u32(&tmem_slot)), "n"(G2::TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm_w = tmem_slot + ((uint32_t)((w & 3) * 32) << 16);       // this warp's lane quarter
+  if (w < 4) {
+    const float* W = w_hh + (size_t)dir * 4 * HID * HID;
+    const int c = lane >> 2, g = c >> 1, u = c & 1;
+#pragma unroll 1
+    for (int ks = 0; ks < G2::FKS; ++ks) {
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt) {
+        const float* wrow = W + (size_t)(g * HID + rank * UPC + w * UPW + 2 * nt + u) * HID;
+        uint32_t hi[2], lo[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int kk = 16 * ks + 8 * j + 2 * (lane & 3);
+          const float v0 = (kk < HID) ? wrow[fwd_slot_unit(kk)] : 0.f;
+          const float v1 = (kk + 1 < HID) ? wrow[fwd_slot_unit(kk + 1)] : 0.f;
+          split2<true>(v0, v1, hi[j], lo[j]);
+        }
+        if (ks < G2::FKS - 1) {
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(tm_w + (uint32_t)(ks * 20 + nt * 2)), "r"(hi[0]), "r"(hi[1]) : "memory");
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(tm_w + (uint32_t)(ks * 20 + 10 + nt * 2)), "r"(lo[0]), "r"(lo[1]) : "memory");
+        } else {
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tm_w + (uint32_t)(ks * 20 + nt)), "r"(hi[0]) : "memory");
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tm_w + (uint32_t)(ks * 20 + 5 + nt)), "r"(lo[0]) : "memory");
+        }
+      }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  for (int idx = tid; idx < (2 * G2::F_HBUF + 16) / 16; idx += G2::NT) reinterpret_cast<uint4*>(Hsm)[idx] = make_uint4(0u, 0u, 0u, 0u);
+  __shared__ __align__(8) uint64_t hfull[2];        // "all of h for the next step has landed in buffer b"
+  __shared__ int s_tile;
+  const uint32_t h_local = smem_addr_u32(Hsm), bar_local = smem_addr_u32(&hfull[0]);
+  if (tid == 0) {
+    lbar_init(&hfull[0], 1);
+    lbar_init(&hfull[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // every CTA of the cluster must have started before its shared memory is written from a peer (the tile index below, then
+  // the h exchange): compute-sanitizer racecheck flags the first remote store otherwise ("block that might not have entered yet")
+  cluster_arrive();
+  cluster_wait();
+  uint32_t hph[2] = {0u, 0u};
+  const size_t GS = (size_t)2 * 4 * HID;
+  PROF_DECL
+
+  // per-lane fragment offsets (bytes)
+  const uint32_t a_row = (uint32_t)((lane & 15) * G2::F_HROW);   // A: lanes 0-15 address k chunk 2ks, lanes 16-31 chunk 2ks+1
+  const bool a_hi = (lane >> 4) != 0;
+  const uint32_t zero_local = smem_addr_u32(Zero16), stg_local = smem_addr_u32(Stg);
+  const bool copy_role = w >= 4;                                 // warps 4-7 move the staging tile to / from global memory
+  const int c_ch = tid & 15, c_rs = (tid - G2::CT) >> 4;          // cooperative copy: chunk and row slot of a copy thread
+  const uint32_t c_so = (uint32_t)(c_rs * G2::SROW + c_ch * 16);  // its offset inside an array of the staging tile
+  const bool pf_lane = (c_ch == 0 || c_ch == 4 || c_ch == 8 || c_ch == 9);   // copy threads that issue the L2 prefetches
+  // where this lane's h values go inside this CTA's block of an h tile (plane 0; plane 1 is F_HPLANE further)
+  const uint32_t stage_v4 = (uint32_t)(rank * G2::F_HBLK + R * G2::F_HROW + w * 16);
+  const uint32_t stage_b32 = (uint32_t)(rank * G2::F_HBLK + R * G2::F_HROW + 64 + w * 4);
+
+  for (;;) {
+    if (rank == 0 && tid == 0) {
+      int t = atomicAdd(&tile_counter[dir], 1);
+#pragma unroll
+      for (int d = 0; d < CL; ++d) *cluster.map_shared_rank(&s_tile, d) = t;
+    }
+    cluster_arrive();
+    cluster_wait();
+    const int tile = s_tile;
+    if (tile >= ntiles) break;
+    __syncthreads();
+    if (tid < MT) {
+      int i = tile * MT + tid;
+      int rr = (i < N) ? order[i] : -1;
+      s_row[tid] = rr;
+      s_len[tid] = (rr >= 0) ? len[rr] : 0;
+      s_off[tid] = (rr >= 0) ? off[rr] : 0;
+    }
+    for (int idx = tid; idx < G2::F_HBUF / 16; idx += G2::NT) reinterpret_cast<uint4*>(Hsm)[idx] = make_uint4(0u, 0u, 0u, 0u);  // h_0 = 0
+    __syncthreads();
+    int maxlen = 0;
+    for (int i = 0; i < MT; ++i) maxlen = max(maxlen, s_len[i]);
+    const int rlen = s_len[R], roff = s_off[R], rrow = s_row[R];
+
+    if (copy_role) {
+      // ---- copy warps: coalesced traffic between the staging tile and global memory, off the compute warps' critical
+      // path.  Thread t moves the 16 B chunk ch = t & 15 (10 of 16 lanes active) of the 160 B row segments of rows
+      // (t >> 4) + 4 rr, rr = 0..7, of every array (64 copy threads).
+      int c_len[8], c_off[8];
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) { c_len[rr] = s_len[c_rs + 4 * rr]; c_off[rr] = s_off[c_rs + 4 * rr]; }
+      if (c_ch < 10) {                    // gx of step 0
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          if (0 < c_len[rr]) {
+            const int t = dir ? (c_len[rr] - 1) : 0;
+            const float* g1 = gx + ((size_t)c_off[rr] + t) * GS + (size_t)dir * 4 * HID + rank * UPC + c_ch * 4;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) cp_async16(stg_local + c_so + rr * 4 * G2::SROW + a * G2::SARR, g1 + a * HID);
+          }
+        }
+      }
+      cp_async_commit();
+      cp_async_wait_all();
+      bar_arrive(3, G2::NT);
+      for (int s = 0; s < maxlen; ++s) {
+        bar_sync(2, G2::NT);              // the staging tile holds the stash of step s
+        if (c_ch < 10) {
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const int rl = c_len[rr];
+            if (s < rl) {
+              const int t = dir ? (rl - 1 - s) : s;
+              const size_t p = (size_t)c_off[rr] + t;
+              const unsigned char* sp = Stg + c_so + rr * 4 * G2::SROW;
+              float* g0 = gx + p * GS + (size_t)dir * 4 * HID + rank * UPC + c_ch * 4;
+#pragma unroll
+              for (int a = 0; a < 4; ++a) *reinterpret_cast<float4*>(g0 + a * HID) = *reinterpret_cast<const float4*>(sp + a * G2::SARR);
+              const float4 cv = *reinterpret_cast<const float4*>(sp + 4 * G2::SARR);
+              *reinterpret_cast<float4*>(c_stash + (p * 2 + dir) * HID + rank * UPC + c_ch * 4) = cv;
+              *reinterpret_cast<float4*>(h_out + p * 2 * HID + (size_t)dir * HID + rank * UPC + c_ch * 4) =
+                  *reinterpret_cast<const float4*>(sp + 5 * G2::SARR);
+              if (s == rl - 1)
+                *reinterpret_cast<float4*>(c_n + (size_t)s_row[c_rs + 4 * rr] * 2 * HID + (size_t)dir * HID + rank * UPC + c_ch * 4) = cv;
+              if (s + 1 < rl) {            // the row's next token is the adjacent one
+                const float* g1 = dir ? g0 - GS : g0 + GS;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) cp_async16(stg_local + c_so + rr * 4 * G2::SROW + a * G2::SARR, g1 + a * HID);
+              }
+              if (NNR_LSTM_PFD > 0 && pf_lane && s + NNR_LSTM_PFD < rl) {   // 160 B segment: chunks 0, 4, 8, 9 touch every line of it
+                const float* g3 = dir ? g0 - (size_t)NNR_LSTM_PFD * GS : g0 + (size_t)NNR_LSTM_PFD * GS;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) prefetch_l2(g3 + a * HID);
+              }
+            }
+          }
+        }
+        if (s + 1 < maxlen) {
+          cp_async_commit();
+          cp_async_wait_all();
+          bar_arrive(3, G2::NT);          // gx of step s+1 is in the staging tile
+        }
+      }
+      continue;
+    }
+
+    // ---- compute warps ---------------------------------------------------------------------------------------------
+    float cst[UPW], hst[UPW];
+#pragma unroll
+    for (int i = 0; i < UPW; ++i) cst[i] = hst[i] = 0.f;
+
+    for (int s = 0; s < maxlen; ++s) {
+      const int cur = s & 1, nxt = cur ^ 1;
+      PROF_MARK(5)
+      if (tid == 0 && s + 1 < maxlen) lbar_expect_tx(&hfull[nxt], G2::F_TX);
+      if (s > 0) { lbar_wait_cluster(&hfull[cur], hph[cur]); hph[cur] ^= 1u; }
+      PROF_MARK(0)
+
+      // ---- recurrent product on the tensor cores: acc[mt][nt] (16 x 8) += h_tile x W_slice^T --------------
+      float acc[2][NTW][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+      const uint32_t hA = h_local + (uint32_t)(cur * G2::F_HBUF) + a_row;
+      // fragments of k-step ks+1 are loaded before the MMAs of k-step ks are issued (register double buffer);
+      // consecutive MMAs on one accumulator are ten instructions apart
+      struct Frag { uint32_t ah[2][4], al[2][4], bh[NTW][2], bl[NTW][2]; };
+      auto load_frags = [&](Frag& f, int ks) {
+        // k chunks 2ks and 2ks+1 of the global slot order: chunk c lives in block c / 5 at 16 B offset c % 5
+        const int c0 = 2 * ks, c1 = 2 * ks + 1;
+        const uint32_t o0 = (uint32_t)((c0 / 5) * G2::F_HBLK + (c0 % 5) * 16), o1 = (uint32_t)((c1 / 5) * G2::F_HBLK + (c1 % 5) * 16);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          uint32_t ad_h, ad_l;
+          if (c1 < 25) {
+            ad_h = hA + mt * 16 * G2::F_HROW + (a_hi ? o1 : o0);
+            ad_l = ad_h + G2::F_HPLANE;
+          } else {                      // K pad: the upper chunk reads zeros
+            ad_h = a_hi ? zero_local : hA + mt * 16 * G2::F_HROW + o0;
+            ad_l = a_hi ? zero_local : ad_h + G2::F_HPLANE;
+          }
+          ldsm_x4(ad_h, f.ah[mt][0], f.ah[mt][1], f.ah[mt][2], f.ah[mt][3]);
+          if (!SINGLE) ldsm_x4(ad_l, f.al[mt][0], f.al[mt][1], f.al[mt][2], f.al[mt][3]);
+        }
+        // B fragments of this k-step from tensor memory (asynchronous: tm_wait() before their first use)
+        if (ks < G2::FKS - 1) {
+          uint32_t r[20];
+          if (!SINGLE) {
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                           "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                         : "r"(tm_w + (uint32_t)(ks * 20)));
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]) : "r"(tm_w + (uint32_t)(ks * 20 + 16)));
+          } else {
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                         : "r"(tm_w + (uint32_t)(ks * 20)));
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[8]), "=r"(r[9]) : "r"(tm_w + (uint32_t)(ks * 20 + 8)));
+          }
+#pragma unroll
+          for (int nt = 0; nt < NTW; ++nt) {
+            f.bh[nt][0] = r[2 * nt]; f.bh[nt][1] = r[2 * nt + 1];
+            if (!SINGLE) { f.bl[nt][0] = r[10 + 2 * nt]; f.bl[nt][1] = r[10 + 2 * nt + 1]; }
+          }
+        } else {                         // k = 192..207: the upper 8 are padding, b1 = 0
+          uint32_t r[10];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                       : "r"(tm_w + (uint32_t)(ks * 20)));
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[8]), "=r"(r[9]) : "r"(tm_w + (uint32_t)(ks * 20 + 8)));
+#pragma unroll
+          for (int nt = 0; nt < NTW; ++nt) {
+            f.bh[nt][0] = r[nt]; f.bh[nt][1] = 0u;
+            if (!SINGLE) { f.bl[nt][0] = r[5 + nt]; f.bl[nt][1] = 0u; }
+          }
+        }
+      };
+      auto tm_wait = [&]() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); };
+      auto mma_all = [&](const Frag& f) {
+        if (!SINGLE) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) mma16816<true>(acc[mt][nt], f.al[mt], f.bh[nt][0], f.bh[nt][1]);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) mma16816<true>(acc[mt][nt], f.ah[mt], f.bl[nt][0], f.bl[nt][1]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NTW; ++nt) mma16816<true>(acc[mt][nt], f.ah[mt], f.bh[nt][0], f.bh[nt][1]);
+      };
+      {
+        Frag f0, f1;
+        load_frags(f0, 0);
+        tm_wait();
+#pragma unroll
+        for (int ks = 0; ks < G2::FKS; ks += 2) {
+          if (ks + 1 < G2::FKS) load_frags(f1, ks + 1);       // in flight during the MMAs of k-step ks
+          mma_all(f0);
+          if (ks + 1 < G2::FKS) {
+            tm_wait();
+            if (ks + 2 < G2::FKS) load_frags(f0, ks + 2);
+            mma_all(f1);
+            if (ks + 2 < G2::FKS) tm_wait();
+          }
+        }
+      }
+
+      PROF_MARK(1)
+      // ---- quad transpose: lane (r8, q) ends with row R = r8 + 8q, gates x 10 units -------------------------
+      float2 pre[NTW][4];
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt) {
+        float2 X[4] = {make_float2(acc[0][nt][0], acc[0][nt][1]), make_float2(acc[0][nt][2], acc[0][nt][3]),
+                       make_float2(acc[1][nt][0], acc[1][nt][1]), make_float2(acc[1][nt][2], acc[1][nt][3])};
+        quad_transpose(X, q);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) pre[nt][g] = X[g];
+      }
+
+      // ---- LSTM cell on the lane's row: gx comes from the staging tile, the stash goes back into it --------------
+      bar_sync(3, G2::NT);            // the copy warps have stored step s-1 and fetched gx of step s
+      if (s < rlen) {
+        unsigned char* sp = Stg + R * G2::SROW + w * (UPW * 4);
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt) {
+          float2* gi = reinterpret_cast<float2*>(sp + 0 * G2::SARR + nt * 8);
+          float2* gf = reinterpret_cast<float2*>(sp + 1 * G2::SARR + nt * 8);
+          float2* gg_ = reinterpret_cast<float2*>(sp + 2 * G2::SARR + nt * 8);
+          float2* go = reinterpret_cast<float2*>(sp + 3 * G2::SARR + nt * 8);
+          const float2 xi = *gi, xf = *gf, xg = *gg_, xo = *go;
+          float ig[2], fg[2], gg[2], og[2];
+          const float zi[2] = {pre[nt][0].x + xi.x, pre[nt][0].y + xi.y};
+          const float zf[2] = {pre[nt][1].x + xf.x, pre[nt][1].y + xf.y};
+          const float zg[2] = {pre[nt][2].x + xg.x, pre[nt][2].y + xg.y};
+          const float zo[2] = {pre[nt][3].x + xo.x, pre[nt][3].y + xo.y};
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            ig[u] = fast_sigmoid(zi[u]);
+            fg[u] = fast_sigmoid(zf[u]);
+            gg[u] = fast_tanh(zg[u]);
+            og[u] = fast_sigmoid(zo[u]);
+            cst[2 * nt + u] = fg[u] * cst[2 * nt + u] + ig[u] * gg[u];
+            hst[2 * nt + u] = og[u] * fast_tanh(cst[2 * nt + u]);
+          }
+          *gi = make_float2(ig[0], ig[1]);
+          *gf = make_float2(fg[0], fg[1]);
+          *gg_ = make_float2(gg[0], gg[1]);
+          *go = make_float2(og[0], og[1]);
+          *reinterpret_cast<float2*>(sp + 4 * G2::SARR + nt * 8) = make_float2(cst[2 * nt], cst[2 * nt + 1]);
+          *reinterpret_cast<float2*>(sp + 5 * G2::SARR + nt * 8) = make_float2(hst[2 * nt], hst[2 * nt + 1]);
+        }
+      }
+      PROF_MARK(2)
+      // ---- the lane's ten h values (fp16 hi / lo) go into this CTA's block of the next tile; one bulk copy per peer
+      if (s + 1 < maxlen) {
+        uint32_t hi[NTW], lo[NTW];
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt) split2<true>(hst[2 * nt], hst[2 * nt + 1], hi[nt], lo[nt]);
+        unsigned char* blk = Hsm + (size_t)nxt * G2::F_HBUF;
+        *reinterpret_cast<uint4*>(blk + stage_v4) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint32_t*>(blk + stage_b32) = hi[4];
+        *reinterpret_cast<uint4*>(blk + G2::F_HPLANE + stage_v4) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint32_t*>(blk + G2::F_HPLANE + stage_b32) = lo[4];
+      }
+      bar_sync(1, G2::CT);              // the CTA's h block is complete
+      if (s + 1 < maxlen && tid == 0) {
+        fence_proxy_async_smem();
+        const uint32_t src = h_local + (uint32_t)(nxt * G2::F_HBUF + rank * G2::F_HBLK);
+        const uint32_t bar = bar_local + nxt * 8;
+#pragma unroll
+        for (int d = 1; d < CL; ++d) {
+          const int peer = (rank + d) % CL;
+          bulk_copy_to_peer(mapa_u32(src, peer), src, G2::F_HBLK, mapa_u32(bar, peer));
+        }
+      }
+      bar_arrive(2, G2::NT);            // hand the staging tile (stash of step s) to the copy warps
+      PROF_MARK(3)
+    }
+  }
+  PROF_FLUSH(0)
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "n"(G2::TM_COLS) : "memory");
+  cluster_arrive();
+  cluster_wait();
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // backward through time
@@ -900,7 +1289,7 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
 
 template <class K>
 int launch_cluster5(K kernel, size_t smem, int ntiles, cudaStream_t st, void** args, const char* name, int (*cache_tab)[16],
-                    bool (*attr_tab)[16], int variant) {
+                    bool (*attr_tab)[16], int variant, int nthreads = G::NT) {
   int dev = 0;
   NNR_CUDA(cudaGetDevice(&dev));
   dev &= 15;                                  // the attribute and the occupancy are per device (and per instantiation)
@@ -908,6 +1297,9 @@ int launch_cluster5(K kernel, size_t smem, int ntiles, cudaStream_t st, void** a
   bool* attr_set = &attr_tab[variant][dev];
   if (!*attr_set) {
     NNR_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // all of the L1 / shared-memory array as shared memory: without it the driver sizes the carve-out for ONE CTA of the
+    // tensor-memory variant (85 KB) and the second CTA per SM never becomes resident (measured: 26 clusters either way)
+    NNR_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     *attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -915,13 +1307,25 @@ int launch_cluster5(K kernel, size_t smem, int ntiles, cudaStream_t st, void** a
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = G::CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cfg.blockDim = dim3(G::NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.blockDim = dim3(nthreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   if (*cache == 0) {
     cfg.gridDim = dim3(G::CL * 2);
     int nc = 0;
     cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, (const void*)kernel, &cfg);
     if (e != cudaSuccess || nc < 2) { (void)cudaGetLastError(); nc = 24; }
     *cache = nc & ~1;
+    // Two CTAs per SM (tensor-memory variant, nthreads = G2::NT): the occupancy query does not see that the 85 KB CTAs fit
+    // twice (it answers 1 CTA / SM = 26 clusters on B200, with or without the shared-memory carve-out hint), the hardware
+    // does co-schedule them.  Measured on B200, N = 3520, L = 128 forward: 26 clusters 4.67 ms, 40: 4.09, 52: 3.50, 56: 3.43,
+    // 58: 3.32, 64: 3.45, 72: 3.40 -> 2 nc + 6.  Clusters beyond what fits start late, find the tile counter exhausted and exit.
+    if (nthreads == G2::NT) *cache = (2 * nc + 6) & ~1;
+    if (const char* ev = getenv("NNR_LSTM_FWD_CLUSTERS")) { int v = atoi(ev); if (v >= 2 && nthreads == G2::NT) *cache = v & ~1; }
+    if (getenv("NNR_LSTM_DEBUG")) {
+      int bps = -1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void*)kernel, nthreads, smem);
+      fprintf(stderr, "[nnr lstm] %s: threads %d smem %zu -> occupancy %d CTAs/SM, max active clusters %d (query rc %d), using %d\n", name,
+              nthreads, smem, bps, nc, (int)e, *cache);
+    }
   }
   int want = 2 * ntiles;                      // (tile, direction) pairs
   int nclusters = want < *cache ? want : *cache;
@@ -941,7 +1345,8 @@ extern "C" int nnr_debug_lstm_prof(unsigned long long* out16) {
   return (int)cudaMemcpyFromSymbol(out16, g_lstm_prof, 16 * sizeof(unsigned long long));
 }
 #endif
-int nnr_lstm_mma_max_clusters = 0;   // reported by nnr_lstm_info
+int nnr_lstm_mma_max_clusters = 0;   // co-resident clusters of the last forward launch (cudaOccupancyMaxActiveClusters)
+extern "C" int nnr_debug_lstm_clusters(void) { return nnr_lstm_mma_max_clusters; }
 extern "C" int nnr_gemm_default_algo(void);
 // the reduced-precision ("bf16") variant of BASELINE config 4: NNR_GEMM_ALGO=bf16 selects single-product tensor-core GEMMs and,
 // here, ONE 16-bit product per recurrent step instead of the three split products
@@ -953,12 +1358,22 @@ static int nnr_lstm_single_product() {
 
 int nnr_lstm_fwd_mma(float* gx, const float* w_hh, const int32_t* len, const int32_t* off, const int32_t* order, int N,
                      float* h_out, float* c_stash, float* c_n, int32_t* tile_counters, cudaStream_t st) {
-  static int cache[2][16] = {};
-  static bool attr_set[2][16] = {};
+  static int cache[4][16] = {};
+  static bool attr_set[4][16] = {};
   int ntiles = (N + G::MT - 1) / G::MT;
   NNR_CUDA(cudaMemsetAsync(tile_counters, 0, 2 * sizeof(int32_t), st));
   void* args[] = {&gx, &w_hh, &len, &off, &order, &N, &ntiles, &h_out, &c_stash, &c_n, &tile_counters};
   const int single = nnr_lstm_single_product();
+  static int use_tm = -1;          // W slice in tensor memory, two CTAs per SM (default); NNR_LSTM_FWD_TM=0: W planes in shared memory
+  if (use_tm < 0) { const char* e = getenv("NNR_LSTM_FWD_TM"); use_tm = e ? atoi(e) : 1; }
+  if (use_tm) {
+    int rc2 = single ? launch_cluster5(lstm_fwd_tm_kernel<true>, G2::FWD_SMEM, ntiles, st, args, "lstm_fwd_tm_kernel<single>", cache, attr_set, 3, G2::NT)
+                     : launch_cluster5(lstm_fwd_tm_kernel<false>, G2::FWD_SMEM, ntiles, st, args, "lstm_fwd_tm_kernel", cache, attr_set, 2, G2::NT);
+    int dev2 = 0;
+    cudaGetDevice(&dev2);
+    nnr_lstm_mma_max_clusters = cache[2 + single][dev2 & 15];
+    return rc2;
+  }
   int rc = single ? launch_cluster5(lstm_fwd_mma_kernel<true>, G::FWD_SMEM, ntiles, st, args, "lstm_fwd_mma_kernel<single>", cache, attr_set, 1)
                   : launch_cluster5(lstm_fwd_mma_kernel<false>, G::FWD_SMEM, ntiles, st, args, "lstm_fwd_mma_kernel", cache, attr_set, 0);
   int dev = 0;
