@@ -619,3 +619,24 @@ def test_engine_reaches_the_kernels_through_torch_ops(cuda):
         assert seen.get(name, 0) >= 1, (name, seen)
     with pytest.raises((RuntimeError, NotImplementedError)):
         torch.ops.nnr.rowdot_fwd(torch.zeros(2, 4), torch.zeros(2, 4), 2, 4, torch.zeros(2))
+
+
+def test_corpus_scorer_graph_replay_equals_host_launched(cuda):
+    """CorpusScorer replays one captured graph per full corpus chunk / per impression batch shape: bit-identical to the
+    host-launched path (eval mode, deterministic kernels)"""
+    from nnr_b200.scoring import CorpusScorer
+    from nnr_b200.synthetic import SyntheticMIND
+    cfg = O.make_config(vocabulary_size=600, max_history_num=8, max_title_length=10, max_abstract_length=20, subCategory_num=30, gcn_layer_num=2)
+    syn = SyntheticMIND(news_num=300, vocabulary_size=600, subCategory_num=30, max_title_length=10, max_abstract_length=20,
+                        max_history_num=8, lengths='mind', seed=23)
+    m = _build(cfg, O.formula_params(cfg), cuda)
+    sc = CorpusScorer(m, syn.news_title_text, syn.news_title_mask, syn.news_abstract_text, syn.news_abstract_mask,
+                      syn.news_category, syn.news_subCategory, chunk=64)
+    eager = sc.encode_corpus(cuda_graph=False).clone()
+    graphed = sc.encode_corpus(cuda_graph=True)
+    assert ('encode', 64) in sc._graphs and torch.equal(eager, graphed)
+    hist, hl, cand = syn.sample_behaviors(128, news_num=5, seed=4)
+    a = sc.score(hist, hl, cand, cuda_graph=False)
+    b = sc.score(hist, hl, cand, cuda_graph=True)
+    c = sc.score(hist, hl, cand, cuda_graph=True)             # second call = pure replay
+    assert torch.equal(a, b) and torch.equal(a, c)
