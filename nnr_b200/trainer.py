@@ -116,7 +116,8 @@ class TrainStep:
         for i in range(1, 4):
             bounds[i] = max(bounds[i], bounds[i - 1])
         self.stage_bounds = {'sue': (bounds[0], bounds[1]), 'cne': (bounds[1], bounds[2]), 'table': (bounds[2], bounds[3])}
-        self.overlap = True               # reduce each group as soon as it is final, on a side stream (world_size > 1)
+        import os
+        self.overlap = os.environ.get('NNR_DP_OVERLAP', '1') != '0'   # reduce each group as soon as it is final, on a side stream (world_size > 1)
         self._comm_stream = None
         self._reduced = set()
         self.params = params
