@@ -53,6 +53,8 @@ def parse():
     ap.add_argument('--dtype', default='f32', choices=['f32', 'bf16'],
                     help='f32: fp32-grade arithmetic (split-operand tensor-core products); bf16: the reduced-precision variant of '
                          'BASELINE config 4 (one 16-bit product per GEMM and per recurrent step, fp32 accumulation)')
+    ap.add_argument('--sharding', default='balanced', choices=['balanced', 'random'],
+                    help='N > 1: how the global batch is cut into per-rank shards (balanced = equal token counts per rank and step)')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel of a step from the host instead of replaying a CUDA graph')
     ap.add_argument('--no-extras', action='store_true', help='skip the extra measurements (scoring, full-length regime)')
     ap.add_argument('--scoring-news', type=int, default=100000, help='news in the synthetic corpus of the scoring extra')
@@ -320,7 +322,21 @@ def main():
     torch.manual_seed(1000 + rank)                            # dropout streams differ per rank
 
     nb = 4                                                    # distinct batches per rank, rotated
-    host = [syn.batch(a.batch, seed=7 * rank + i) for i in range(nb)]
+    if world == 1 or a.sharding == 'random':
+        host = [syn.batch(a.batch, seed=7 * rank + i) for i in range(nb)]
+    else:
+        # token-balanced sharding (trainer.balanced_shards): every rank draws the same global batch of world x batch
+        # impressions (like the reference, where every rank runs the same sampling with the same seed, trainer.py:255-258) and
+        # takes the shard a greedy longest-first assignment gives it, so that all ranks have the same number of tokens per step
+        from nnr_b200.trainer import balanced_shards
+        import numpy as np
+        host = []
+        for i in range(nb):
+            hist, hl, cand = syn.sample_behaviors(a.batch * world, seed=1000 + i)
+            per_news = (syn.title_len + syn.abstract_len)
+            cost = per_news[hist].sum(1) + per_news[cand].sum(1)
+            idx = np.asarray(balanced_shards(cost, world)[rank])
+            host.append(syn.materialize(hist[idx], hl[idx], cand[idx]))
     for b in host:
         for k in FIELDS:
             if torch.is_tensor(b[k]):
@@ -514,6 +530,10 @@ def main():
             'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': a.dtype, 'data': 'synthetic',
             'config': {'workload': workload_name(a), 'global_batch': a.batch * world, 'parallelism': 'dp%d' % world,
+                       'sharding': ('n/a (one rank)' if world == 1 else
+                                    'token-balanced: every rank draws the same global batch and takes the shard of a greedy longest-first '
+                                    'assignment over the impressions\' token counts (nnr_b200.trainer.balanced_shards)'
+                                    if a.sharding == 'balanced' else 'random shards (independent batches per rank)'),
                        'valid_token_fraction': tok / slots, 'tokens_per_step_per_gpu': tok,
                        'l2_policy': 'per-step working set (activations+stashes, GBs) >> 126 MB L2; %d rotating batches' % nb,
                        'launch': 'cuda graph replay (one launch per step)' if ts.cuda_graph else 'host launches',

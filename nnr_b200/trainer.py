@@ -386,6 +386,32 @@ class LossLog:
         return self._consume(True)
 
 
+def balanced_shards(cost, world_size):
+    """Token-balanced sharding of one global batch over the ranks of a synchronous data-parallel step.
+
+    ``cost[i]`` is the work of impression i (its number of valid tokens).  Every rank gets exactly ``len(cost) // world_size``
+    impressions; they are dealt longest first, each to the rank with the smallest total so far that still has room (greedy
+    LPT).  A synchronous step runs at the pace of its slowest rank, and with variable-length news the token count of a random
+    shard of 64 impressions varies by +-6 % (the slowest of 8 random shards is ~12 % above the mean), which is what limits the
+    weak scaling of the reference's DistributedSampler shards (trainer.py:256-258); the set of impressions in the global batch
+    -- hence the averaged gradient's meaning -- is unchanged.  Deterministic: every rank computes the same assignment.
+    Returns a list of ``world_size`` index lists (ascending inside a shard)."""
+    import numpy as np
+    cost = np.asarray(cost, dtype=np.int64)
+    n = len(cost)
+    if n % world_size:
+        raise ValueError('batch size %d not divisible by world size %d' % (n, world_size))
+    per = n // world_size
+    order = np.argsort(-cost, kind='stable')
+    totals = [0] * world_size
+    shards = [[] for _ in range(world_size)]
+    for i in order:
+        r = min((r for r in range(world_size) if len(shards[r]) < per), key=lambda r: (totals[r], r))
+        shards[r].append(int(i))
+        totals[r] += int(cost[i])
+    return [sorted(s) for s in shards]
+
+
 def shard_batch(batch, rank, world_size):
     """Reference DDP sharding (trainer.py:218,256-258): rank r takes impressions [r*B/W, (r+1)*B/W) of a global
     batch whose size is divisible by the world size (config.py:116).  Works on dicts or sequences of tensors;

@@ -78,3 +78,23 @@ def test_dp_gloo_world2():
         p.join(timeout=180)
         assert p.exitcode == 0
     assert sorted(q.get(timeout=5) for _ in range(2)) == [0, 1]
+
+
+def test_balanced_shards_equal_counts_and_tokens():
+    """trainer.balanced_shards: every rank gets B / world impressions, token totals within 1 % of each other, deterministic,
+    and a partition of the global batch (same set of impressions as any other sharding)"""
+    import numpy as np
+    from nnr_b200.trainer import balanced_shards
+    rng = np.random.default_rng(0)
+    cost = rng.integers(200, 9000, size=512)
+    shards = balanced_shards(cost, 8)
+    assert [len(s) for s in shards] == [64] * 8
+    assert sorted(i for s in shards for i in s) == list(range(512))
+    totals = np.array([cost[s].sum() for s in shards])
+    assert totals.max() / totals.mean() < 1.01
+    assert shards == balanced_shards(cost, 8)
+    random_totals = np.array([cost[r * 64:(r + 1) * 64].sum() for r in range(8)])
+    assert totals.max() < random_totals.max()
+    import pytest
+    with pytest.raises(ValueError):
+        balanced_shards(cost[:510], 8)
