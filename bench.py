@@ -332,7 +332,9 @@ def main():
         import numpy as np
         host = []
         for i in range(nb):
-            hist, hl, cand = syn.sample_behaviors(a.batch * world, seed=1000 + i)
+            # the global batch = exactly the impressions the ranks would draw on their own (--sharding random), re-dealt
+            parts = [syn.sample_behaviors(a.batch, seed=7 * r + i) for r in range(world)]
+            hist, hl, cand = (np.concatenate([p[j] for p in parts]) for j in range(3))
             per_news = (syn.title_len + syn.abstract_len)
             cost = per_news[hist].sum(1) + per_news[cand].sum(1)
             idx = np.asarray(balanced_shards(cost, world)[rank])
