@@ -58,6 +58,65 @@ def _empty(shape, dev, dtype=torch.float32):
 
 
 # ------------------------------------------------------------------------------------------------
+# Two-lane schedules
+# ------------------------------------------------------------------------------------------------
+# The title and the content branch of the news encoder are independent between their exchange points (the partner's final
+# cell state before the selective gate, the partner's self-attention vector before the cross attention, and the mirror
+# images of both in the backward pass), and so are the weight-gradient GEMMs of the user encoder and its candidate-side
+# projections.  Many kernels of the step cannot fill 148 SMs on their own: the LSTM recurrences end in a tail that is as
+# long as the longest sequence, the per-news and user-encoder GEMMs are one or two dozen CTAs.  `Lanes.run` therefore
+# issues one branch on a side stream and the other on the caller's stream and joins them before the next exchange point;
+# inside a captured step the two lanes become parallel branches of the CUDA graph.  NNR_LANES=0 (or
+# engine.concurrent = False, used by the per-op profiler) issues everything on the caller's stream in the same order.
+_LANES = os.environ.get('NNR_LANES', '1') != '0'
+concurrent = True
+_side_streams = {}
+
+
+class Lanes:
+    def __init__(self, dev):
+        self.on = _LANES and concurrent and dev.type == 'cuda'
+        self.keep = []                      # tensors of the caller's lane that the side lane reads: alive until the last join
+        if self.on:
+            idx = dev.index if dev.index is not None else torch.cuda.current_device()
+            self.main = torch.cuda.current_stream(idx)
+            self.side = _side_streams.get(idx)
+            if self.side is None:
+                self.side = _side_streams[idx] = torch.cuda.Stream(device=idx)
+            if self.side == self.main:      # nested use from the side lane itself: stay serial
+                self.on = False
+
+    def fork(self):
+        """the side lane may start after everything issued so far on the caller's stream"""
+        if self.on:
+            self.side.wait_stream(self.main)
+
+    def on_side(self, fn, *a, **k):
+        """issue fn on the side lane (no implicit fork / join)"""
+        if not self.on:
+            return fn(*a, **k)
+        prev, ops.lane = ops.lane, 1
+        try:
+            with torch.cuda.stream(self.side):
+                return fn(*a, **k)
+        finally:
+            ops.lane = prev
+
+    def join(self):
+        if self.on:
+            self.main.wait_stream(self.side)
+        self.keep.clear()
+
+    def run(self, fn_side, fn_main):
+        """fork; fn_side on the side lane, fn_main on the caller's stream; join.  Returns (side result, main result)."""
+        self.fork()
+        a = self.on_side(fn_side)
+        b = fn_main()
+        self.join()
+        return a, b
+
+
+# ------------------------------------------------------------------------------------------------
 # GEMM helpers (row-major; weights are nn.Linear layout [out, in])
 # ------------------------------------------------------------------------------------------------
 # Operand planes of WEIGHT matrices are split once per parameter version and shared by the forward and the dgrad
@@ -361,17 +420,21 @@ class CNEFunction(torch.autograd.Function):
             ctx.cat_i, ctx.sub_i, ctx.fuse_seed = cat_i, sub_i, seeds[2]
             ctx.names = names
             return rep
-        t = _cne_modality_forward(P, 'title', title_text.view(N, T), title_mask.reshape(N, T), N, T, E, Hd, training, p, seeds[0], domains)
-        c = _cne_modality_forward(P, 'content', content_text.view(N, Lc), content_mask.reshape(N, Lc), N, Lc, E, Hd, training, p, seeds[1], domains)
+        # title on the side lane, content on the caller's stream; joined at the three exchange points
+        lanes = Lanes(title_text.device)
+        t, c = lanes.run(
+            lambda: _cne_modality_forward(P, 'title', title_text.view(N, T), title_mask.reshape(N, T), N, T, E, Hd, training, p, seeds[0], domains),
+            lambda: _cne_modality_forward(P, 'content', content_text.view(N, Lc), content_mask.reshape(N, Lc), N, Lc, E, Hd, training, p, seeds[1], domains))
         # pairing by sort rank inside each domain (newsEncoders.py:124-129, SURVEY finding 2):
         # title row r of a call is gated with the content memory of the news at the same sorted rank
         partner_t = torch.cat([cs.index_select(0, td) for cs, td in zip(c.sorted_idx, t.desorted_idx)])
         partner_c = torch.cat([ts.index_select(0, cd) for ts, cd in zip(t.sorted_idx, c.desorted_idx)])
-        _cne_gate_self(P, 'title', t, c.c_n, partner_t, N, Hd, A, gate)
-        _cne_gate_self(P, 'content', c, t.c_n, partner_c, N, Hd, A, gate)
+        t.partner, c.partner = partner_t, partner_c
+        lanes.run(lambda: _cne_gate_self(P, 'title', t, c.c_n, partner_t, N, Hd, A, gate),
+                  lambda: _cne_gate_self(P, 'content', c, t.c_n, partner_c, N, Hd, A, gate))
         if meta['cross_attention']:
-            _cne_cross(P, 'title', t, c.self_out, N, Hd, A)
-            _cne_cross(P, 'content', c, t.self_out, N, Hd, A)
+            lanes.run(lambda: _cne_cross(P, 'title', t, c.self_out, N, Hd, A),
+                      lambda: _cne_cross(P, 'content', c, t.self_out, N, Hd, A))
         cat_t, sub_t = P['category_embedding.weight'], P['subCategory_embedding.weight']
         Dout = 4 * Hd + cat_t.shape[1] + sub_t.shape[1]
         rep = _empty((N, Dout), title_text.device)
@@ -414,34 +477,48 @@ class CNEFunction(torch.autograd.Function):
         for x, m in mods.items():
             m.dhg = _empty((m.cap, D2), dev)
         dhg_written = {'title': False, 'content': False}
+        gate = meta.get('gate', True) and not single
+        wemb = P['word_embedding.weight']
+        lanes = Lanes(dev)
+
+        def staged(fn, *per_mod):
+            """fn(x, m, ...) for every modality: title on the side lane and content on the caller's stream when both exist"""
+            if single:
+                x = modalities[0]
+                return {x: fn(x, mods[x], *[a[x] for a in per_mod])}
+            rt, rc = lanes.run(lambda: fn('title', t, *[a['title'] for a in per_mod]),
+                               lambda: fn('content', c, *[a['content'] for a in per_mod]))
+            return {'title': rt, 'content': rc}
+
         # 2. cross attention backward (produces the extra gradient of the other modality's self vector)
+        def cross_bwd(x, m):
+            ca = x + '_cross_attention.'
+            dqk = _empty((N, D2), dev)
+            ops.attn_pool_bwd(X=m.hg, ldx=D2, D=D2, S=N, max_len=m.L, mode=1, seg_off=m.off, seg_order=m.order, qvec=m.qk, ldq=D2,
+                              scale=scale, alpha=m.alpha_cross, dpooled=d_out[x], lddp=D2, dX=m.dhg, lddx=D2,
+                              accumulate_dx=False, dqvec=dqk, lddq=D2)
+            dhg_written[x] = True
+            dqk_pl = _shared_split(dqk, N, D2)                                         # dqk and dq feed two GEMMs each:
+            dq = linear(dqk, P[ca + 'K.weight'], N, x_planes=dqk_pl)                      # [N,A] = dqk K^T
+            G[ca + 'K.weight'] = wgrad(m.q, dqk, N, A, D2, dy_planes=m.q_pl, x_planes=dqk_pl)   # q^T dqk
+            dbq = _empty((A,), dev)
+            dq_pl = _shared_split(dq, N, A, colsum_out=dbq)                             # one split (+ the bias gradient)
+            G[ca + 'Q.weight'] = wgrad(dq, m.other_self, N, A, D2, dy_planes=dq_pl, x_planes=m.other_self_pl)
+            G[ca + 'Q.bias'] = dbq
+            # d(other self) = dq Q + its own output gradient
+            return matmul_nn(dq, P[ca + 'Q.weight'], N, epilogue=EPI_ADD_AUX, aux=d_out[other[x]], ldaux=D2, x_planes=dq_pl)
+
         if cross:
-            new_d_self = {}
-            for x, m in mods.items():
-                ca = x + '_cross_attention.'
-                dqk = _empty((N, D2), dev)
-                ops.attn_pool_bwd(X=m.hg, ldx=D2, D=D2, S=N, max_len=m.L, mode=1, seg_off=m.off, seg_order=m.order, qvec=m.qk, ldq=D2,
-                                  scale=scale, alpha=m.alpha_cross, dpooled=d_out[x], lddp=D2, dX=m.dhg, lddx=D2,
-                                  accumulate_dx=False, dqvec=dqk, lddq=D2)
-                dhg_written[x] = True
-                dqk_pl = _shared_split(dqk, N, D2)                                         # dqk and dq feed two GEMMs each:
-                dq = linear(dqk, P[ca + 'K.weight'], N, x_planes=dqk_pl)                      # [N,A] = dqk K^T
-                G[ca + 'K.weight'] = wgrad(m.q, dqk, N, A, D2, dy_planes=m.q_pl, x_planes=dqk_pl)   # q^T dqk
-                dbq = _empty((A,), dev)
-                dq_pl = _shared_split(dq, N, A, colsum_out=dbq)                             # one split (+ the bias gradient)
-                G[ca + 'Q.weight'] = wgrad(dq, m.other_self, N, A, D2, dy_planes=dq_pl, x_planes=m.other_self_pl)
-                G[ca + 'Q.bias'] = dbq
-                # d(other self) = dq Q + its own output gradient
-                new_d_self[other[x]] = matmul_nn(dq, P[ca + 'Q.weight'], N, epilogue=EPI_ADD_AUX, aux=d_out[other[x]], ldaux=D2,
-                                                 x_planes=dq_pl)
-            d_self = new_d_self
-        # 3. self attention backward
-        for x, m in mods.items():
+            r = staged(cross_bwd)
+            d_self = {'content': r['title'], 'title': r['content']}
+
+        # 3. self attention backward, 4. selective gate backward
+        def self_gate_bwd(x, m, d_self_x):
             sa = x + '_self_attention.'
             dU = _empty((m.cap, A), dev)
             dw2p = _empty((N, A), dev)
             ops.attn_pool_bwd(X=m.hg, ldx=D2, D=D2, S=N, max_len=m.L, mode=0, seg_off=m.off, seg_order=m.order, U=m.u, ldu=A, A=A,
-                              w2=P[sa + 'affine2.weight'], alpha=m.alpha_self, dpooled=d_self[x], lddp=D2, dX=m.dhg,
+                              w2=P[sa + 'affine2.weight'], alpha=m.alpha_self, dpooled=d_self_x, lddp=D2, dX=m.dhg,
                               lddx=D2, accumulate_dx=dhg_written[x], dU=dU, lddu=A, dw2_partial=dw2p)
             G[sa + 'affine2.weight'] = colsum(dw2p, N, A).view(1, A)
             db1 = _empty((A,), dev)
@@ -450,15 +527,11 @@ class CNEFunction(torch.autograd.Function):
             G[sa + 'affine1.weight'] = wgrad(dU, m.hg, m.cap, A, D2, k_dev=m.ntok, dy_planes=dU_pl, x_planes=m.hg_pl)
             G[sa + 'affine1.bias'] = db1
             del dU, dU_pl
+            lanes.keep.append(m.hg_pl)           # released at the join: a lane never hands memory back while the other may run
             m.hg_pl = None
-        # 4. selective gate backward
-        d_cm_sel = {}
-        gate = meta.get('gate', True) and not single
-        for x, m in mods.items():
             if not gate:                       # CNE_wo_CS / single modality: hg is h, nothing flows into another cell state
                 m.dh = m.dhg
-                d_cm_sel[x] = None
-                continue
+                return None
             dh0 = _empty((m.cap, D2), dev)
             dmproj = _empty((N, D2), dev)
             if ops.default_algo() != ops.ALGO_SIMT:
@@ -473,37 +546,33 @@ class CNEFunction(torch.autograd.Function):
             m.dh = matmul_nn(dz, P[x + '_H.weight'], m.cap, m.ntok, epilogue=EPI_ADD_AUX, aux=dh0, ldaux=D2, out=m.dhg,
                              x_planes=dz_pl)
             G[x + '_H.weight'] = wgrad(dz, m.h, m.cap, D2, D2, k_dev=m.ntok, dy_planes=dz_pl, x_planes=m.h_pl)
+            lanes.keep.append(m.h_pl)
             m.h_pl = None
             dbm = _empty((D2,), dev)
             dmproj_pl = _shared_split(dmproj, N, D2, colsum_out=dbm)                       # shared by both GEMMs, + bias gradient
             G[x + '_M.weight'] = wgrad(dmproj, m.cm_sel, N, D2, D2, dy_planes=dmproj_pl, x_planes=m.cm_sel_pl)
             G[x + '_M.bias'] = dbm
-            d_cm_sel[x] = matmul_nn(dmproj, P[x + '_M.weight'], N, x_planes=dmproj_pl)        # grad of cn_other[partner]
-            del dz, dh0, dz_pl
+            return matmul_nn(dmproj, P[x + '_M.weight'], N, x_planes=dmproj_pl)               # grad of cn_other[partner]
+
+        d_cm_sel = staged(self_gate_bwd, d_self)
         # partner_t and partner_c are inverse permutations of each other
         if gate:
             dcn = {'content': d_cm_sel['title'].index_select(0, c.partner),
                    'title': d_cm_sel['content'].index_select(0, t.partner)}
         else:
             dcn = {x: torch.zeros(N, D2, device=dev) for x in mods}
-        # 5. LSTM backward + input projection + embedding scatter
-        # with a flat gradient buffer (trainer.TrainStep) the scatter adds straight into the table's .grad view: no [V, E]
-        # temporary, no memset of it, no [V, E] add afterwards
-        wemb = P['word_embedding.weight']
-        in_place = _flat_grads(P, ctx.names) and wemb.grad.is_contiguous() and wemb.grad.data_ptr() % 16 == 0
-        dtable = wemb.grad if in_place else _empty(wemb.shape, dev)
-        first = not in_place
-        scatters = []
-        for x, m in mods.items():
+
+        # 5. LSTM backward + input projection (the embedding scatters follow on the caller's stream)
+        def lstm_stage_bwd(x, m, dcn_x):
             pre = x + '_lstm.'
             db = _empty((8 * Hd,), dev)
             if m.emb is None and ops.lstm_bwd_planes_supported(Hd):
                 # dL/dgx only feeds GEMMs and the bias gradient: the recurrence writes its operand planes and column sums
                 dz = None
                 dz_pl = ops.lstm_bwd_planes(m.gates, m.c_stash, m.w_hh, m.len, m.off, m.order, N, m.L, Hd, m.dh,
-                                            dcn[x].contiguous(), m.cap, db)
+                                            dcn_x.contiguous(), m.cap, db)
             else:
-                ops.lstm_bwd(m.gates, m.c_stash, m.w_hh, m.len, m.off, m.order, N, m.L, Hd, m.dh, dcn[x].contiguous())
+                ops.lstm_bwd(m.gates, m.c_stash, m.w_hh, m.len, m.off, m.order, N, m.L, Hd, m.dh, dcn_x.contiguous())
                 dz = m.gates                                                                  # [cap, 8H] = dL/dgx
                 dz_pl = split_tokens(dz, m.cap, 8 * Hd, m.ntok, colsum_out=db)
             if dz_pl is not None:                 # hprev is only a GEMM operand: straight to planes
@@ -520,14 +589,22 @@ class CNEFunction(torch.autograd.Function):
                                                      dy_planes=dz_pl.cols(d * 4 * Hd, (d + 1) * 4 * Hd) if dz_pl else None,
                                                      x_planes=hprev_pl.cols(d * Hd, (d + 1) * Hd) if hprev_pl else None)
             dwih = wgrad(dz, m.emb, m.cap, 8 * Hd, E, k_dev=m.ntok, dy_planes=dz_pl, x_planes=m.emb_pl)
+            lanes.keep.append(m.emb_pl)
             m.emb_pl = None
             for d, sfx in enumerate(('', '_reverse')):
                 G[pre + 'weight_ih_l0' + sfx] = dwih[d * 4 * Hd:(d + 1) * 4 * Hd]
                 G[pre + 'bias_ih_l0' + sfx] = db[d * 4 * Hd:(d + 1) * 4 * Hd]
                 G[pre + 'bias_hh_l0' + sfx] = db[d * 4 * Hd:(d + 1) * 4 * Hd]
-            demb = matmul_nn(dz, m.w_ih, m.cap, m.ntok, x_planes=dz_pl, w_planes=m.w_ih_pl)
-            del dz_pl, hprev, hprev_pl
-            scatters.append((demb, m))
+            return matmul_nn(dz, m.w_ih, m.cap, m.ntok, x_planes=dz_pl, w_planes=m.w_ih_pl)
+
+        demb = staged(lstm_stage_bwd, dcn)
+        # with a flat gradient buffer (trainer.TrainStep) the scatter adds straight into the table's .grad view: no [V, E]
+        # temporary, no memset of it, no [V, E] add afterwards
+        in_place = _flat_grads(P, ctx.names) and wemb.grad.is_contiguous() and wemb.grad.data_ptr() % 16 == 0
+        dtable = wemb.grad if in_place else _empty(wemb.shape, dev)
+        first = not in_place
+        scatters = [(demb[x], m) for x, m in mods.items()]
+        del demb
         # every news-encoder gradient except the word table is final now: with a flat gradient buffer they are added in
         # place and announced, so that their data-parallel reduction overlaps the two embedding scatters below
         G['word_embedding.weight'] = None
@@ -603,6 +680,13 @@ class SUEFunction(torch.autograd.Function):
         cand = cand.contiguous()
         if not gcn:                                                                           # SUE_wo_GCN: clusters over the raw history
             return SUEFunction._clusters_forward(ctx, meta, P, names, hist, cand, cmask, cidx, seeds, (B, H, D, n, C, Gn, C1), L, pe)
+        # the candidate-side projections of the cluster attentions do not depend on the GCN: side lane, joined before the
+        # intra-cluster attention needs them
+        lanes = Lanes(dev)
+        pre = None
+        if hca:
+            lanes.fork()
+            pre = lanes.on_side(SUEFunction._cand_side, P, cand, B, n, D)
         # X0 = [history | dropout_(proxy nodes)]   (userEncoders.py:80)
         x0 = _empty((B, Gn, D), dev)
         x0[:, :H] = hist
@@ -656,7 +740,21 @@ class SUEFunction(torch.autograd.Function):
                               w2=P['attention.affine2.weight'], pooled=pooled, ldp=D, alpha=alpha)
             ctx.u, ctx.alpha = u, alpha
             return pooled.unsqueeze(1).repeat(1, n, 1)
-        return SUEFunction._clusters_tail(ctx, P, gfeat, cand, cmask, cidx, seeds, (B, H, D, n, C, Gn, C1), L, pe)
+        lanes.join()
+        return SUEFunction._clusters_tail(ctx, P, gfeat, cand, cmask, cidx, seeds, (B, H, D, n, C, Gn, C1), L, pe, pre)
+
+    @staticmethod
+    def _cand_side(P, cand, B, n, D):
+        """what the cluster attentions need from the candidates alone (userEncoders.py:84,94: the two query projections;
+        the inter-cluster K is folded onto its query)"""
+        Au = P['intraCluster_K.weight'].shape[0]
+        cand_pl = _shared_split(cand.view(B * n, D), B * n, D)     # also the weight-gradient operand of the backward
+        Qp = linear(cand.view(B * n, D), P['intraCluster_Q.weight'], B * n, None, P['intraCluster_Q.bias'], x_planes=cand_pl)
+        q2 = linear(cand.view(B * n, D), P['interClusterAttention.Q.weight'], B * n, None, P['interClusterAttention.Q.bias'],
+                    x_planes=cand_pl)
+        q2_pl = _shared_split(q2, B * n, Au)
+        qk2 = matmul_nn(q2, P['interClusterAttention.K.weight'], B * n, x_planes=q2_pl)
+        return cand_pl, Qp, q2, q2_pl, qk2
 
     @staticmethod
     def _clusters_forward(ctx, meta, P, names, hist, cand, cmask, cidx, seeds, dims, L, pe):
@@ -668,7 +766,7 @@ class SUEFunction(torch.autograd.Function):
         return SUEFunction._clusters_tail(ctx, P, hist, cand, cmask, cidx, seeds, dims, L, pe)
 
     @staticmethod
-    def _clusters_tail(ctx, P, gfeat, cand, cmask, cidx, seeds, dims, L, pe):
+    def _clusters_tail(ctx, P, gfeat, cand, cmask, cidx, seeds, dims, L, pe, pre=None):
         """intra-cluster attention, cluster affine, inter-cluster attention (userEncoders.py:83-97)"""
         B, H, D, n, C, Gn, C1 = dims
         dev = gfeat.device
@@ -676,10 +774,9 @@ class SUEFunction(torch.autograd.Function):
         scale = 1.0 / math.sqrt(float(Au))
         # (an intraCluster_K.bias -- SUE_wo_GCN only -- shifts every score of a (user, candidate) pair equally and
         #  cancels in the per-cluster softmax: it is not applied, and its gradient is exactly zero)
+        cand_pl, Qp, q2, q2_pl, qk2 = pre if pre is not None else SUEFunction._cand_side(P, cand, B, n, D)
         gfeat_pl = _shared_split(gfeat.view(B * H, D), B * H, D)   # gfeat, cand, q2: split once for the forward GEMMs and the
-        cand_pl = _shared_split(cand.view(B * n, D), B * n, D)     # weight-gradient GEMMs of the backward
-        Kp = linear(gfeat.view(B * H, D), P['intraCluster_K.weight'], B * H, x_planes=gfeat_pl)
-        Qp = linear(cand.view(B * n, D), P['intraCluster_Q.weight'], B * n, None, P['intraCluster_Q.bias'], x_planes=cand_pl)
+        Kp = linear(gfeat.view(B * H, D), P['intraCluster_K.weight'], B * H, x_planes=gfeat_pl)   # weight-gradient GEMMs of the backward
         alpha = _empty((B * n, H), dev)
         intra = _empty((B * n * C1, D), dev)
         cidx = cidx.contiguous()
@@ -689,10 +786,6 @@ class SUEFunction(torch.autograd.Function):
         f = linear(intra, P['clusterFeatureAffine.weight'], B * n * C1, None, P['clusterFeatureAffine.bias'],
                    EPI_BIAS_RELU_RES, aux=intra, ldaux=D, aux_out=r_f, ldaux_out=D, p_drop=pe, seed=seeds[L + 1],
                    x_planes=intra_pl)
-        q2 = linear(cand.view(B * n, D), P['interClusterAttention.Q.weight'], B * n, None, P['interClusterAttention.Q.bias'],
-                    x_planes=cand_pl)
-        q2_pl = _shared_split(q2, B * n, Au)
-        qk2 = matmul_nn(q2, P['interClusterAttention.K.weight'], B * n, x_planes=q2_pl)
         cm = cmask.unsqueeze(1).expand(-1, n, -1).contiguous().view(torch.uint8)             # [B,n,C1]
         user = _empty((B * n, D), dev)
         alpha2 = _empty((B * n * C1,), dev)
@@ -714,6 +807,15 @@ class SUEFunction(torch.autograd.Function):
         seeds = ctx.seeds
         gfeat, cand = ctx.gfeat, ctx.cand
         dcand = None
+        lanes = Lanes(dev)
+
+        def side_wgrad(name, dy, x, M, N_, K_, dy_pl, x_pl):
+            """a weight-gradient GEMM is a leaf of the backward pass: side lane, while the caller's stream goes on with the
+            chain towards the inputs (its operands stay alive until the join)"""
+            lanes.keep.extend((dy, x, dy_pl, x_pl))
+            lanes.fork()
+            G[name] = lanes.on_side(wgrad, dy, x, M, N_, K_, dy_planes=dy_pl, x_planes=x_pl)
+
         if not meta['hca']:
             A = P['attention.affine1.weight'].shape[0]
             dpooled = duser.sum(dim=1).contiguous()                                          # repeat over candidates
@@ -737,14 +839,22 @@ class SUEFunction(torch.autograd.Function):
                               mask=cm, alpha=alpha2, dpooled=duser, lddp=D, dX=df, lddx=D, accumulate_dx=False,
                               dqvec=dqk2, lddq=D)
             cand2 = cand.view(B * n, D)
-            dqk2_pl = _shared_split(dqk2, B * n, D)                                        # operands used by two GEMMs: one split
-            dq2 = linear(dqk2, P['interClusterAttention.K.weight'], B * n, x_planes=dqk2_pl)  # [B*n, Au]
-            G['interClusterAttention.K.weight'] = wgrad(q2, dqk2, B * n, Au, D, dy_planes=q2_pl, x_planes=dqk2_pl)
-            dbq2 = _empty((Au,), dev)
-            dq2_pl = _shared_split(dq2, B * n, Au, colsum_out=dbq2)
-            G['interClusterAttention.Q.weight'] = wgrad(dq2, cand2, B * n, Au, D, dy_planes=dq2_pl, x_planes=cand_pl)
-            G['interClusterAttention.Q.bias'] = dbq2
-            dcand = matmul_nn(dq2, P['interClusterAttention.Q.weight'], B * n, x_planes=dq2_pl)   # [B*n, D]
+
+            # side lane: everything that only leads to weight gradients and to the candidates' gradient (the query chain of
+            # the inter-cluster attention, every weight-gradient GEMM); the caller's stream keeps the chain that leads to
+            # the history gradient.  Joined once, before the gradients are handed to autograd.
+            def query_chain():
+                dqk2_pl = _shared_split(dqk2, B * n, D)                                        # operands used by two GEMMs: one split
+                dq2 = linear(dqk2, P['interClusterAttention.K.weight'], B * n, x_planes=dqk2_pl)  # [B*n, Au]
+                G['interClusterAttention.K.weight'] = wgrad(q2, dqk2, B * n, Au, D, dy_planes=q2_pl, x_planes=dqk2_pl)
+                dbq2 = _empty((Au,), dev)
+                dq2_pl = _shared_split(dq2, B * n, Au, colsum_out=dbq2)
+                G['interClusterAttention.Q.weight'] = wgrad(dq2, cand2, B * n, Au, D, dy_planes=dq2_pl, x_planes=cand_pl)
+                G['interClusterAttention.Q.bias'] = dbq2
+                return matmul_nn(dq2, P['interClusterAttention.Q.weight'], B * n, x_planes=dq2_pl)   # [B*n, D]
+            lanes.keep.append(dqk2)
+            lanes.fork()
+            dcand = lanes.on_side(query_chain)
             # cluster affine backward: f = (relu(W intra + b) + intra) * drop
             db_f = _empty((D,), dev)
             if _fused_relu_bwd(df, D):
@@ -758,7 +868,7 @@ class SUEFunction(torch.autograd.Function):
                     ops.dropout(df, pe, seeds[L + 1], df)
                 dpre = df * (r_f > 0)                                                         # relu mask
                 dpre_pl = ops.tc_split(dpre, B * n * C1, D, D, colsum_out=db_f)  # planes + bias gradient in one pass
-            G['clusterFeatureAffine.weight'] = wgrad(dpre, intra, B * n * C1, D, D, dy_planes=dpre_pl, x_planes=intra_pl)
+            side_wgrad('clusterFeatureAffine.weight', dpre, intra, B * n * C1, D, D, dpre_pl, intra_pl)
             G['clusterFeatureAffine.bias'] = db_f
             dintra = matmul_nn(dpre, P['clusterFeatureAffine.weight'], B * n * C1, epilogue=EPI_ADD_AUX, aux=df, ldaux=D,
                                x_planes=dpre_pl)
@@ -768,15 +878,21 @@ class SUEFunction(torch.autograd.Function):
             dg = _empty((B * H, D), dev)
             ops.cluster_intra_bwd(dintra, Kp, Qp, gfeat, cidx, alpha, B, n, H, Au, D, C1, scale, da_ws, dKp, dQp, dg, False)
             dKp_pl = _shared_split(dKp, B * H, Au)
-            G['intraCluster_K.weight'] = wgrad(dKp, gfeat.view(B * H, D), B * H, Au, D, dy_planes=dKp_pl, x_planes=gfeat_pl)
+            side_wgrad('intraCluster_K.weight', dKp, gfeat.view(B * H, D), B * H, Au, D, dKp_pl, gfeat_pl)
             matmul_nn(dKp, P['intraCluster_K.weight'], B * H, out=dg, accumulate=True, x_planes=dKp_pl)
-            dbq = _empty((Au,), dev)
-            dQp_pl = _shared_split(dQp, B * n, Au, colsum_out=dbq)
-            G['intraCluster_Q.weight'] = wgrad(dQp, cand2, B * n, Au, D, dy_planes=dQp_pl, x_planes=cand_pl)
-            G['intraCluster_Q.bias'] = dbq
-            matmul_nn(dQp, P['intraCluster_Q.weight'], B * n, out=dcand, accumulate=True, x_planes=dQp_pl)
+
+            def cand_tail():
+                dbq = _empty((Au,), dev)
+                dQp_pl = _shared_split(dQp, B * n, Au, colsum_out=dbq)
+                G['intraCluster_Q.weight'] = wgrad(dQp, cand2, B * n, Au, D, dy_planes=dQp_pl, x_planes=cand_pl)
+                G['intraCluster_Q.bias'] = dbq
+                matmul_nn(dQp, P['intraCluster_Q.weight'], B * n, out=dcand, accumulate=True, x_planes=dQp_pl)
+            lanes.keep.append(dQp)
+            lanes.fork()
+            lanes.on_side(cand_tail)
         if not meta.get('gcn', True):                  # SUE_wo_GCN: gfeat is the history embedding itself
             G['intraCluster_K.bias'] = torch.zeros_like(P['intraCluster_K.bias'])
+            lanes.join()
             ctx.sv = None
             pg = _param_grads(P, ctx.names, G)
             _notify('sue')
@@ -813,7 +929,7 @@ class SUEFunction(torch.autograd.Function):
                     ops.dropout(dx, pl, seeds[l], dx)
                 dpre = dx * (ctx.rs[l] > 0)
                 dpre_pl = ops.tc_split(dpre, B * Gn, D, D, colsum_out=db_l)   # one split for the wgrad and the dgrad GEMM, + bias gradient
-            G['gcn.gcn_layers.%d.W.weight' % l] = wgrad(dpre, ctx.aggs[l][0], B * Gn, D, D, dy_planes=dpre_pl, x_planes=ctx.aggs[l][1])
+            side_wgrad('gcn.gcn_layers.%d.W.weight' % l, dpre, ctx.aggs[l][0], B * Gn, D, D, dpre_pl, ctx.aggs[l][1])
             G['gcn.gcn_layers.%d.W.bias' % l] = db_l
             dagg = matmul_nn(dpre, P['gcn.gcn_layers.%d.W.weight' % l], B * Gn, x_planes=dpre_pl)
             dprev = _empty((B * Gn, D), dev)
@@ -826,6 +942,7 @@ class SUEFunction(torch.autograd.Function):
         if pe > 0:
             ops.dropout(dproxy_b, pe, seeds[L], dproxy_b)
         G['proxy_node_embedding'] = dproxy_b.sum(dim=0)
+        lanes.join()
         ctx.xs = ctx.rs = ctx.aggs = ctx.sv = ctx.lns = None
         pg = _param_grads(P, ctx.names, G)
         _notify('sue')

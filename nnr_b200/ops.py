@@ -41,11 +41,13 @@ def _stream():
 
 
 _ws_cache = {}
+lane = 0      # engine.Lanes: index of the stream the caller is launching on (0 = the caller's own stream, 1 = the side lane)
 
 
 def workspace(nbytes, device, tag='default'):
-    """grow-only scratch buffer per (device, tag); safe because all launches are stream ordered"""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    """grow-only scratch buffer per (device, lane, tag); safe because all launches of one lane are stream ordered and
+    concurrent lanes (engine.Lanes) never share a scratch buffer"""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), lane, tag)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)

@@ -158,9 +158,12 @@ class Capture:
 
 @contextlib.contextmanager
 def capture():
+    from . import engine
     cap = Capture()
     _lib.lib.nnr_profile_enable(1)
     saved = {}
+    lanes_were = engine.concurrent
+    engine.concurrent = False          # per-op events time one op at a time: no second lane (engine.Lanes) underneath them
     for name in _TIMED:
         saved[name] = getattr(ops, name)
         setattr(ops, name, cap.wrap(name, saved[name]))
@@ -168,6 +171,7 @@ def capture():
         yield cap
     finally:
         _lib.lib.nnr_profile_enable(0)
+        engine.concurrent = lanes_were
         for name, fn in saved.items():
             setattr(ops, name, fn)
 

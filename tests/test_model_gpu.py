@@ -213,6 +213,32 @@ def test_backward_is_deterministic(cuda):
         assert torch.equal(grads[0][k], grads[1][k]), k
 
 
+@pytest.mark.parametrize('name', ['mind_shape', 'ablation', 'wo_gcn', 'title_only'])
+def test_two_lane_schedule_is_bit_identical_to_the_serial_schedule(cuda, name):
+    """engine.Lanes: the title / content branches (and the user encoder's weight-gradient leaves) issued on two streams give
+    bit-identical logits and gradients to the one-stream schedule -- same kernels, same accumulation order, fresh and
+    repeated (a race between the lanes would show as a difference between repeats)"""
+    from nnr_b200 import engine
+    from nnr_b200.trainer import negative_log_softmax
+    cfg, batch, _ = load_golden(name)
+    cfg.dropout_rate = 0.0
+    p = O.formula_params(cfg)
+    runs = []
+    try:
+        for lanes in (False, True, True, True):
+            engine.concurrent = lanes
+            m = _build(cfg, p, cuda, train=True)
+            logits = m(*_args(batch, cuda))
+            negative_log_softmax(logits).backward()
+            runs.append((logits.detach().clone(), {k: v.grad.clone() for k, v in m.named_parameters()}))
+    finally:
+        engine.concurrent = True
+    for logits, grads in runs[1:]:
+        assert torch.equal(runs[0][0], logits)
+        for k in grads:
+            assert torch.equal(runs[0][1][k], grads[k]), k
+
+
 def test_inputs_are_mutated_like_the_reference(cuda):
     cfg, batch, _ = load_golden('tiny')
     p = O.formula_params(cfg)
