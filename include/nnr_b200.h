@@ -245,11 +245,16 @@ int nnr_news_fuse_fwd(const float* t_self, const float* t_cross, const float* c_
                       const int32_t* cat, const int32_t* sub, int N, int D2, int Ec, int Es,
                       float p_drop, uint64_t seed, float* out, void* stream);
 /* backward: d_a[N,D2] = dout[:, :D2], d_b[N,D2] = dout[:, D2:2*D2]; dense table grads
- * (deterministic: one block per table row scanning the N rows in order).                        */
+ * (deterministic: one block per table row scanning the N rows in order).  dcat_table == dsub_table == NULL: only the
+ * activation split; the table gradients -- leaves of the backward pass -- can then be taken by
+ * nnr_news_fuse_tables_bwd on another stream (col0 = first category column of dout = 2*D2, or D2 for one modality). */
 int nnr_news_fuse_bwd(const float* dout, const int32_t* cat, const int32_t* sub, int N, int D2,
                       int Ec, int Es, int n_cat, int n_sub, float p_drop, uint64_t seed,
                       float* d_a, float* d_b, float* dcat_table, float* dsub_table,
                       int accumulate, void* stream);
+int nnr_news_fuse_tables_bwd(const float* dout, const int32_t* cat, const int32_t* sub, int N, int Dout, int col0,
+                             int Ec, int Es, int n_cat, int n_sub, float p_drop, uint64_t seed,
+                             float* dcat_table, float* dsub_table, int accumulate, void* stream);
 
 /* ---- SUE graph: MIND_corpus.py:162-216 (structure), layers.py:286 (aggregation) --------------
  * Build graph / mask / cluster indices on the device from per-slot categories (bit-exact with

@@ -244,25 +244,42 @@ __global__ void __launch_bounds__(NF_WARPS * 32) news_fuse_table_bwd_kernel(cons
     *d = accumulate ? (*d + v) : v;
   }
 }
+static int news_fuse_tables_launch(const float* dout, const int32_t* cat, const int32_t* sub, int N, int Dout, int col0, int Ec, int Es,
+                                   int n_cat, int n_sub, float p_drop, uint64_t seed, float* dcat_table, float* dsub_table,
+                                   int accumulate, cudaStream_t st) {
+  float inv_keep = 1.0f / (1.0f - p_drop);
+  news_fuse_table_bwd_kernel<<<n_cat, NF_WARPS * 32, 0, st>>>(dout, cat, N, Dout, col0, Ec, Ec + Es, 0, p_drop,
+                                                                     inv_keep, seed, dcat_table, accumulate);
+  NNR_LAUNCH_CHECK("news_fuse_table_bwd_kernel(cat)");
+  news_fuse_table_bwd_kernel<<<n_sub, NF_WARPS * 32, 0, st>>>(dout, sub, N, Dout, col0 + Ec, Es, Ec + Es, Ec,
+                                                                     p_drop, inv_keep, seed, dsub_table, accumulate);
+  NNR_LAUNCH_CHECK("news_fuse_table_bwd_kernel(sub)");
+  return 0;
+}
 extern "C" int nnr_news_fuse_bwd(const float* dout, const int32_t* cat, const int32_t* sub, int N, int D2, int Ec, int Es,
                                  int n_cat, int n_sub, float p_drop, uint64_t seed, float* d_a, float* d_b,
                                  float* dcat_table, float* dsub_table, int accumulate, void* stream) {
-  NNR_REQUIRE(dout && cat && sub && d_a && dcat_table && dsub_table && N > 0, NNR_ERR_ARG,
+  const bool tables = dcat_table || dsub_table;     // both NULL: only the activation split (the table gradients are then
+                                                    // taken by nnr_news_fuse_tables_bwd, possibly on another stream)
+  NNR_REQUIRE(dout && d_a && N > 0 && (!tables || (cat && sub && dcat_table && dsub_table)), NNR_ERR_ARG,
               "nnr_news_fuse_bwd: bad arguments");
   NNR_REQUIRE(Ec <= NF_MAXE && Es <= NF_MAXE, NNR_ERR_UNSUPPORTED, "nnr_news_fuse_bwd: embedding dim > %d", NF_MAXE);
   cudaStream_t st = (cudaStream_t)stream;
   const int DM = d_b ? 2 * D2 : D2;                 // d_b = NULL: single-modality encoders (CNE_Title / CNE_Content)
   int Dout = DM + Ec + Es;
-  float inv_keep = 1.0f / (1.0f - p_drop);
   news_fuse_split_kernel<<<N, 256, 0, st>>>(dout, D2, Dout, d_a, d_b);
   NNR_LAUNCH_CHECK("news_fuse_split_kernel");
-  news_fuse_table_bwd_kernel<<<n_cat, NF_WARPS * 32, 0, st>>>(dout, cat, N, Dout, DM, Ec, Ec + Es, 0, p_drop,
-                                                                     inv_keep, seed, dcat_table, accumulate);
-  NNR_LAUNCH_CHECK("news_fuse_table_bwd_kernel(cat)");
-  news_fuse_table_bwd_kernel<<<n_sub, NF_WARPS * 32, 0, st>>>(dout, sub, N, Dout, DM + Ec, Es, Ec + Es, Ec,
-                                                                     p_drop, inv_keep, seed, dsub_table, accumulate);
-  NNR_LAUNCH_CHECK("news_fuse_table_bwd_kernel(sub)");
-  return 0;
+  if (!tables) return 0;
+  return news_fuse_tables_launch(dout, cat, sub, N, Dout, DM, Ec, Es, n_cat, n_sub, p_drop, seed, dcat_table, dsub_table, accumulate, st);
+}
+extern "C" int nnr_news_fuse_tables_bwd(const float* dout, const int32_t* cat, const int32_t* sub, int N, int Dout, int col0, int Ec,
+                                        int Es, int n_cat, int n_sub, float p_drop, uint64_t seed, float* dcat_table,
+                                        float* dsub_table, int accumulate, void* stream) {
+  NNR_REQUIRE(dout && cat && sub && dcat_table && dsub_table && N > 0 && col0 >= 0 && col0 + Ec + Es <= Dout, NNR_ERR_ARG,
+              "nnr_news_fuse_tables_bwd: bad arguments");
+  NNR_REQUIRE(Ec <= NF_MAXE && Es <= NF_MAXE, NNR_ERR_UNSUPPORTED, "nnr_news_fuse_tables_bwd: embedding dim > %d", NF_MAXE);
+  return news_fuse_tables_launch(dout, cat, sub, N, Dout, col0, Ec, Es, n_cat, n_sub, p_drop, seed, dcat_table, dsub_table, accumulate,
+                                 (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -74,45 +74,56 @@ _side_streams = {}
 
 
 class Lanes:
+    """lane 0 = the caller's stream; lanes 1, 2 = side streams of the device (lane 2 takes leaves -- work nothing on the
+    critical path waits for -- so that they do not queue in front of the title branch on lane 1)"""
+    NSIDE = 2
+
     def __init__(self, dev):
         self.on = _LANES and concurrent and dev.type == 'cuda'
-        self.keep = []                      # tensors of the caller's lane that the side lane reads: alive until the last join
+        self.keep = []                      # tensors of one lane that another lane reads: alive until the next join
+        self.used = set()
         if self.on:
             idx = dev.index if dev.index is not None else torch.cuda.current_device()
             self.main = torch.cuda.current_stream(idx)
-            self.side = _side_streams.get(idx)
-            if self.side is None:
-                self.side = _side_streams[idx] = torch.cuda.Stream(device=idx)
-            if self.side == self.main:      # nested use from the side lane itself: stay serial
+            self.sides = _side_streams.get(idx)
+            if self.sides is None:
+                self.sides = _side_streams[idx] = [torch.cuda.Stream(device=idx) for _ in range(self.NSIDE)]
+            if any(s == self.main for s in self.sides):      # nested use from a side lane itself: stay serial
                 self.on = False
 
-    def fork(self):
-        """the side lane may start after everything issued so far on the caller's stream"""
+    def fork(self, lane=1, after=0):
+        """side lane `lane` may start after everything issued so far on lane `after` (0 = the caller's stream)"""
         if self.on:
-            self.side.wait_stream(self.main)
+            self.sides[lane - 1].wait_stream(self.main if after == 0 else self.sides[after - 1])
+            self.used.add(lane)
 
-    def on_side(self, fn, *a, **k):
-        """issue fn on the side lane (no implicit fork / join)"""
+    def on_side(self, fn, *a, lane=1, **k):
+        """issue fn on a side lane (no implicit fork / join)"""
         if not self.on:
             return fn(*a, **k)
-        prev, ops.lane = ops.lane, 1
+        prev, ops.lane = ops.lane, lane
         try:
-            with torch.cuda.stream(self.side):
+            with torch.cuda.stream(self.sides[lane - 1]):
                 return fn(*a, **k)
         finally:
             ops.lane = prev
 
-    def join(self):
+    def join(self, *which):
+        """the caller's stream waits for the given side lanes (default: every lane forked since its last join)"""
         if self.on:
-            self.main.wait_stream(self.side)
-        self.keep.clear()
+            for lane in sorted(which or self.used):
+                if lane in self.used:
+                    self.main.wait_stream(self.sides[lane - 1])
+                    self.used.discard(lane)
+        if not self.used:
+            self.keep.clear()
 
     def run(self, fn_side, fn_main):
-        """fork; fn_side on the side lane, fn_main on the caller's stream; join.  Returns (side result, main result)."""
+        """fork; fn_side on lane 1, fn_main on the caller's stream; join lane 1.  Returns (side result, main result)."""
         self.fork()
         a = self.on_side(fn_side)
         b = fn_main()
-        self.join()
+        self.join(1)
         return a, b
 
 
@@ -307,7 +318,9 @@ def _domain_sorts(len64, domains, max_key):
     return sorted_idx, desorted_idx
 
 
-def _cne_modality_forward(P, x, ids, mask_u8, N, L, E, Hd, training, p_drop, seed, domains):
+def _cne_prepare(ids, mask_u8, N, L, domains):
+    """sequence bookkeeping of one modality (newsEncoders.py:106-115): lengths, packed offsets, token -> row map, the
+    per-domain sort permutations and the longest-first tile order of the recurrence.  A few small kernels."""
     dev = ids.device
     cap = N * L
     m = _Mod()
@@ -324,6 +337,13 @@ def _cne_modality_forward(P, x, ids, mask_u8, N, L, E, Hd, training, p_drop, see
         m.order = m.sorted_idx[0].to(torch.int32)
     else:                                                     # LSTM tiling only needs "longest first"
         m.order = _sort_desc(len64, L).to(torch.int32)
+    return m
+
+
+def _cne_recurrent(P, x, m, N, E, Hd, training, p_drop, seed):
+    """embedding gather + dropout, input projection, bidirectional LSTM of one modality (newsEncoders.py:117-127)"""
+    dev = m.ids.device
+    ids, L, cap = m.ids, m.L, m.cap
     m.seed = seed
     m.p = p_drop if training else 0.0
     table = P['word_embedding.weight']
@@ -348,6 +368,10 @@ def _cne_modality_forward(P, x, ids, mask_u8, N, L, E, Hd, training, p_drop, see
     m.c_n = _empty((N, 2 * Hd), dev)
     ops.lstm_fwd(m.gates, m.w_hh, m.len, m.off, m.order, N, L, Hd, m.h, m.c_stash, m.c_n)
     return m
+
+
+def _cne_modality_forward(P, x, ids, mask_u8, N, L, E, Hd, training, p_drop, seed, domains):
+    return _cne_recurrent(P, x, _cne_prepare(ids, mask_u8, N, L, domains), N, E, Hd, training, p_drop, seed)
 
 
 def _cne_gate_self(P, x, m, m_other_cn, partner, N, Hd, A, gate=True):
@@ -420,16 +444,20 @@ class CNEFunction(torch.autograd.Function):
             ctx.cat_i, ctx.sub_i, ctx.fuse_seed = cat_i, sub_i, seeds[2]
             ctx.names = names
             return rep
-        # title on the side lane, content on the caller's stream; joined at the three exchange points
+        # title on the side lane, content on the caller's stream; joined at the exchange points
         lanes = Lanes(title_text.device)
-        t, c = lanes.run(
-            lambda: _cne_modality_forward(P, 'title', title_text.view(N, T), title_mask.reshape(N, T), N, T, E, Hd, training, p, seeds[0], domains),
-            lambda: _cne_modality_forward(P, 'content', content_text.view(N, Lc), content_mask.reshape(N, Lc), N, Lc, E, Hd, training, p, seeds[1], domains))
-        # pairing by sort rank inside each domain (newsEncoders.py:124-129, SURVEY finding 2):
-        # title row r of a call is gated with the content memory of the news at the same sorted rank
+        t, c = lanes.run(lambda: _cne_prepare(title_text.view(N, T), title_mask.reshape(N, T), N, T, domains),
+                         lambda: _cne_prepare(content_text.view(N, Lc), content_mask.reshape(N, Lc), N, Lc, domains))
+        lanes.fork()
+        lanes.on_side(_cne_recurrent, P, 'title', t, N, E, Hd, training, p, seeds[0])
+        # pairing by sort rank inside each domain (newsEncoders.py:124-129, SURVEY finding 2): title row r of a call is
+        # gated with the content memory of the news at the same sorted rank.  (A handful of [N]-sized kernels: issued here
+        # they run under the title branch's gather / GEMM instead of between the recurrences and the gates.)
         partner_t = torch.cat([cs.index_select(0, td) for cs, td in zip(c.sorted_idx, t.desorted_idx)])
         partner_c = torch.cat([ts.index_select(0, cd) for ts, cd in zip(t.sorted_idx, c.desorted_idx)])
         t.partner, c.partner = partner_t, partner_c
+        _cne_recurrent(P, 'content', c, N, E, Hd, training, p, seeds[1])
+        lanes.join()
         lanes.run(lambda: _cne_gate_self(P, 'title', t, c.c_n, partner_t, N, Hd, A, gate),
                   lambda: _cne_gate_self(P, 'content', c, t.c_n, partner_c, N, Hd, A, gate))
         if meta['cross_attention']:
@@ -459,12 +487,16 @@ class CNEFunction(torch.autograd.Function):
         single = len(modalities) == 1
         cross = meta['cross_attention'] and not single
         training, p = meta['training'], meta['p_drop']
-        # 1. split + category tables
+        # 1. split + category tables (the table gradients are leaves: lane 2)
+        lanes = Lanes(dev)
         d_a, d_b = _empty((N, D2), dev), (None if single else _empty((N, D2), dev))
         G['category_embedding.weight'] = _empty(P['category_embedding.weight'].shape, dev)
         G['subCategory_embedding.weight'] = _empty(P['subCategory_embedding.weight'].shape, dev)
-        ops.news_fuse_bwd(drep, ctx.cat_i, ctx.sub_i, N, D2, p if training else 0.0, ctx.fuse_seed, d_a, d_b,
-                          G['category_embedding.weight'], G['subCategory_embedding.weight'], False)
+        Ec, Es = P['category_embedding.weight'].shape[1], P['subCategory_embedding.weight'].shape[1]
+        ops.news_fuse_split_bwd(drep, N, D2, Ec, Es, d_a, d_b)
+        lanes.fork(2)
+        lanes.on_side(ops.news_fuse_tables_bwd, drep, ctx.cat_i, ctx.sub_i, N, D2 if single else 2 * D2, p if training else 0.0,
+                      ctx.fuse_seed, G['category_embedding.weight'], G['subCategory_embedding.weight'], False, lane=2)
         scale = 1.0 / math.sqrt(float(A))
         if single:
             d_self = d_out = {modalities[0]: d_a}
@@ -479,7 +511,6 @@ class CNEFunction(torch.autograd.Function):
         dhg_written = {'title': False, 'content': False}
         gate = meta.get('gate', True) and not single
         wemb = P['word_embedding.weight']
-        lanes = Lanes(dev)
 
         def staged(fn, *per_mod):
             """fn(x, m, ...) for every modality: title on the side lane and content on the caller's stream when both exist"""
@@ -562,9 +593,17 @@ class CNEFunction(torch.autograd.Function):
         else:
             dcn = {x: torch.zeros(N, D2, device=dev) for x in mods}
 
-        # 5. LSTM backward + input projection (the embedding scatters follow on the caller's stream)
-        def lstm_stage_bwd(x, m, dcn_x):
-            pre = x + '_lstm.'
+        # 5. LSTM backward, input projection, embedding scatter.  Per modality: the recurrence, then the data gradient of the
+        # input projection and its scatter into the word table, then the weight gradients (leaves).  The two scatters add
+        # into the same table in a fixed order (title, content), so both go to lane 1; the content branch's weight-gradient
+        # GEMMs -- the bulk of what is left -- run on the caller's stream meanwhile.
+        # With a flat gradient buffer (trainer.TrainStep) the scatter adds straight into the table's .grad view: no [V, E]
+        # temporary, no memset of it, no [V, E] add afterwards.
+        in_place = _flat_grads(P, ctx.names) and wemb.grad.is_contiguous() and wemb.grad.data_ptr() % 16 == 0
+        dtable = wemb.grad if in_place else _empty(wemb.shape, dev)
+        first = [not in_place]
+
+        def recurrence_bwd(x, m, dcn_x):
             db = _empty((8 * Hd,), dev)
             if m.emb is None and ops.lstm_bwd_planes_supported(Hd):
                 # dL/dgx only feeds GEMMs and the bias gradient: the recurrence writes its operand planes and column sums
@@ -575,6 +614,15 @@ class CNEFunction(torch.autograd.Function):
                 ops.lstm_bwd(m.gates, m.c_stash, m.w_hh, m.len, m.off, m.order, N, m.L, Hd, m.dh, dcn_x.contiguous())
                 dz = m.gates                                                                  # [cap, 8H] = dL/dgx
                 dz_pl = split_tokens(dz, m.cap, 8 * Hd, m.ntok, colsum_out=db)
+            demb = matmul_nn(dz, m.w_ih, m.cap, m.ntok, x_planes=dz_pl, w_planes=m.w_ih_pl)
+            return dz, dz_pl, db, demb
+
+        def scatter(x, m, demb):
+            ops.embed_gather_bwd(demb, m.ids, m.len, m.off, dtable, m.p, m.seed, not first[0])
+            first[0] = False
+
+        def weight_grads(x, m, dz, dz_pl, db):
+            pre = x + '_lstm.'
             if dz_pl is not None:                 # hprev is only a GEMM operand: straight to planes
                 hprev = None
                 hprev_pl = ops.lstm_shift_h_planes(m.h, m.len, m.off, m.tok_row, N, m.L, Hd, m.cap)
@@ -589,40 +637,42 @@ class CNEFunction(torch.autograd.Function):
                                                      dy_planes=dz_pl.cols(d * 4 * Hd, (d + 1) * 4 * Hd) if dz_pl else None,
                                                      x_planes=hprev_pl.cols(d * Hd, (d + 1) * Hd) if hprev_pl else None)
             dwih = wgrad(dz, m.emb, m.cap, 8 * Hd, E, k_dev=m.ntok, dy_planes=dz_pl, x_planes=m.emb_pl)
-            lanes.keep.append(m.emb_pl)
+            lanes.keep.extend((m.emb_pl, hprev, hprev_pl))
             m.emb_pl = None
             for d, sfx in enumerate(('', '_reverse')):
                 G[pre + 'weight_ih_l0' + sfx] = dwih[d * 4 * Hd:(d + 1) * 4 * Hd]
                 G[pre + 'bias_ih_l0' + sfx] = db[d * 4 * Hd:(d + 1) * 4 * Hd]
                 G[pre + 'bias_hh_l0' + sfx] = db[d * 4 * Hd:(d + 1) * 4 * Hd]
-            return matmul_nn(dz, m.w_ih, m.cap, m.ntok, x_planes=dz_pl, w_planes=m.w_ih_pl)
 
-        demb = staged(lstm_stage_bwd, dcn)
-        # with a flat gradient buffer (trainer.TrainStep) the scatter adds straight into the table's .grad view: no [V, E]
-        # temporary, no memset of it, no [V, E] add afterwards
-        in_place = _flat_grads(P, ctx.names) and wemb.grad.is_contiguous() and wemb.grad.data_ptr() % 16 == 0
-        dtable = wemb.grad if in_place else _empty(wemb.shape, dev)
-        first = not in_place
-        scatters = [(demb[x], m) for x, m in mods.items()]
-        del demb
-        # every news-encoder gradient except the word table is final now: with a flat gradient buffer they are added in
-        # place and announced, so that their data-parallel reduction overlaps the two embedding scatters below
-        G['word_embedding.weight'] = None
-        pg = None
-        if in_place:
-            pg = _param_grads(P, ctx.names, G)
-            _notify('cne')
-        for demb, m in scatters:
-            ops.embed_gather_bwd(demb, m.ids, m.len, m.off, dtable, m.p, m.seed, not first)
-            first = False
-        del scatters
-        ctx.t = ctx.c = None
-        if in_place:
-            _notify('table')
-            return (None,) * 7 + pg
+        if single:
+            x = modalities[0]
+            dz, dz_pl, db, demb = recurrence_bwd(x, mods[x], dcn[x])
+            scatter(x, mods[x], demb)
+            weight_grads(x, mods[x], dz, dz_pl, db)
+        else:
+            # lane 1: title recurrence, title scatter, content scatter (the chain the end of the backward pass waits for);
+            # lane 2: the title branch's weight gradients; caller's stream: content recurrence, content weight gradients
+            lanes.fork()
+            tz, tz_pl, tdb, tdemb = lanes.on_side(recurrence_bwd, 'title', t, dcn['title'])
+            lanes.on_side(scatter, 'title', t, tdemb)
+            lanes.fork(2, after=1)
+            lanes.on_side(weight_grads, 'title', t, tz, tz_pl, tdb, lane=2)
+            dz, dz_pl, db, demb = recurrence_bwd('content', c, dcn['content'])
+            lanes.keep.extend((tz, tz_pl, tdemb, dz, dz_pl, demb))
+            lanes.fork()                                       # lane 1, behind the title scatter
+            lanes.on_side(scatter, 'content', c, demb)
+            if in_place:
+                lanes.on_side(_notify, 'table')               # the table gradient is final once lane 1 gets here
+            weight_grads('content', c, dz, dz_pl, db)
+        lanes.join()
         G['word_embedding.weight'] = None if in_place else dtable
         ctx.t = ctx.c = None
-        return (None,) * 7 + _param_grads(P, ctx.names, G)
+        pg = _param_grads(P, ctx.names, G)
+        if in_place:
+            _notify('cne')
+            if single:
+                _notify('table')
+        return (None,) * 7 + pg
 
 
 # ------------------------------------------------------------------------------------------------

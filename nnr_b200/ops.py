@@ -338,6 +338,20 @@ def news_fuse_bwd(dout, cat, sub, N, D2, p_drop, seed, d_a, d_b, dcat_table, dsu
           'nnr_news_fuse_bwd')
 
 
+def news_fuse_split_bwd(dout, N, D2, Ec, Es, d_a, d_b):
+    """the activation half of news_fuse_bwd: d_a = dout[:, :D2], d_b = dout[:, D2:2*D2]"""
+    check(lib.nnr_news_fuse_bwd(_p(dout, _F32), None, None, N, D2, Ec, Es, 0, 0, 0.0, 0, _p(d_a, _F32), _p(d_b, _F32), None, None, 0,
+                                _stream()), 'nnr_news_fuse_bwd')
+
+
+def news_fuse_tables_bwd(dout, cat, sub, N, col0, p_drop, seed, dcat_table, dsub_table, accumulate):
+    """the table-gradient half of news_fuse_bwd (a leaf of the backward pass: the engine issues it on a side lane)"""
+    Ec, Es = dcat_table.shape[1], dsub_table.shape[1]
+    check(lib.nnr_news_fuse_tables_bwd(_p(dout, _F32), _p(cat, _I32), _p(sub, _I32), N, dout.shape[1], col0, Ec, Es,
+                                       dcat_table.shape[0], dsub_table.shape[0], float(p_drop), int(seed), _p(dcat_table, _F32),
+                                       _p(dsub_table, _F32), int(accumulate), _stream()), 'nnr_news_fuse_tables_bwd')
+
+
 GRAPH_NO_SELF_CONNECTION, GRAPH_NO_NORMALIZATION, GRAPH_ASYMMETRIC = 1, 2, 4
 
 
@@ -459,6 +473,9 @@ _SCHEMAS = {
                       'int D2, float p_drop, int seed, Tensor(a!) out) -> ()', news_fuse_fwd),
     'news_fuse_bwd': ('(Tensor dout, Tensor cat, Tensor sub, int N, int D2, float p_drop, int seed, Tensor(a!) d_a, Tensor(b!)? d_b, '
                       'Tensor(c!) dcat_table, Tensor(d!) dsub_table, bool accumulate) -> ()', news_fuse_bwd),
+    'news_fuse_split_bwd': ('(Tensor dout, int N, int D2, int Ec, int Es, Tensor(a!) d_a, Tensor(b!)? d_b) -> ()', news_fuse_split_bwd),
+    'news_fuse_tables_bwd': ('(Tensor dout, Tensor cat, Tensor sub, int N, int col0, float p_drop, int seed, Tensor(a!) dcat_table, '
+                             'Tensor(b!) dsub_table, bool accumulate) -> ()', news_fuse_tables_bwd),
     'colsum': ('(Tensor X, int ldx, int M, int N, Tensor(a!) out, bool accumulate=False, Tensor? m_dev=None) -> ()', colsum),
     'segment_colsum': ('(Tensor X, int ldx, Tensor off, int N, int D, Tensor(a!) out, int ldo) -> ()', segment_colsum),
     'gate_bwd_pre': ('(Tensor dhg, Tensor h, Tensor g, int n_max, Tensor n_dev, int D, Tensor(a!) dz, Tensor(b!) dh0) -> ()', gate_bwd_pre),

@@ -302,10 +302,12 @@ class TrainStep:
         self._reduced = set()
 
     def _on_grads_ready(self, stage):
-        """engine.grads_ready callback: the gradients of `stage` are final in the flat buffer -> start their all-reduce on the
-        communication stream while the compute stream goes on with the backward pass"""
-        if self.world_size <= 1 or not self.overlap or self.flat.device.type != 'cuda' or stage == 'table':
-            return                       # the table is the end of the backward pass: reduced on the compute stream
+        """engine.grads_ready callback: the gradients of `stage` are final in the flat buffer once the CURRENT stream gets here
+        (the engine announces the word table from the lane that runs the embedding scatters) -> start their all-reduce on
+        the communication stream while the backward pass goes on: the table's reduction runs under the weight-gradient GEMMs
+        of the content branch"""
+        if self.world_size <= 1 or not self.overlap or self.flat.device.type != 'cuda':
+            return
         a, b = self.stage_bounds[stage]
         if b <= a or stage in self._reduced:
             return

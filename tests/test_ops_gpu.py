@@ -562,6 +562,12 @@ def test_news_fuse_and_rowdot(cuda):
     ref_c = torch.zeros_like(ct).index_add_(0, cat.long(), dout[:, 2 * D2:2 * D2 + Ec])
     ref_s = torch.zeros_like(st).index_add_(0, sub.long(), dout[:, 2 * D2 + Ec:])
     assert torch.allclose(dct, ref_c, atol=1e-5) and torch.allclose(dst, ref_s, atol=1e-5)
+    # the two halves as separate calls (the engine issues the table gradients on a side lane): same bits
+    d_a2, d_b2 = torch.empty_like(d_a), torch.empty_like(d_b)
+    dct2, dst2 = torch.empty_like(ct), torch.empty_like(st)
+    ops.news_fuse_split_bwd(dout, N, D2, Ec, Es, d_a2, d_b2)
+    ops.news_fuse_tables_bwd(dout, cat, sub, N, 2 * D2, 0.0, 0, dct2, dst2, False)
+    assert torch.equal(d_a2, d_a) and torch.equal(d_b2, d_b) and torch.equal(dct2, dct) and torch.equal(dst2, dst)
     a, b = torch.randn(77, 900, generator=g).to(cuda), torch.randn(77, 900, generator=g).to(cuda)
     o = torch.empty(77, device=cuda)
     ops.rowdot_fwd(a, b, 77, 900, o)
