@@ -75,6 +75,15 @@ struct G2 {
   static constexpr size_t FWD_SMEM = 2 * (size_t)F_HBUF + 16 + F_NARR * (size_t)SARR + 3 * MT * sizeof(int);
 };
 
+// backward variant with the W slice in TENSOR MEMORY (lstm_bwd_mma_kernel<SINGLE, true>): 4 compute + 2 copy warps; six of a
+// warp's n8 tiles live in tensor memory as ready-made mma.sync B fragments, warp 0's seventh tile (8 units) stays in shared memory
+struct G3 {
+  static constexpr int NT = 192, TM_COLS = 256;            // 10 k-steps x 6 n-tiles x 4 registers = 240 columns used
+  static constexpr int W7_PLANE = 8 * G::BWPITCH;          // [8 units][160 k] bf16, same XOR swizzle as the full slice
+  static constexpr size_t BWD_SMEM = 2 * (size_t)W7_PLANE + 2 * (size_t)G::B_Z_PLANE + 2 * (size_t)G::B_RECV + G::B_NARR * (size_t)G::SARR +
+                                     3 * G::MT * sizeof(int);
+};
+
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
@@ -866,8 +875,12 @@ lstm_fwd_tm_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const
 // ------------------------------------------------------------------------------------------------
 // backward through time
 // ------------------------------------------------------------------------------------------------
-template <bool SINGLE>   // SINGLE: one 16-bit product (hi x hi) instead of the three split products -- the bf16 variant
-__global__ void __launch_bounds__(G::NT, 1)
+// TM: the W slice lives in tensor memory (see G3): the CTA needs 104 KB of shared memory instead of 224 KB and two CTAs (of
+// two different clusters) share an SM -- one CTA's products keep the tensor pipe busy while the other is in its exchange wait /
+// point-wise / store phases.  Same protocol, same arithmetic as the shared-memory variant (the per-tile bias-gradient partials group the
+// rows by 4 copy-thread slots instead of 8: deterministic, last-bit different).
+template <bool SINGLE, bool TM>   // SINGLE: one 16-bit product (hi x hi) instead of the three split products -- the bf16 variant
+__global__ void __launch_bounds__(TM ? G3::NT : G::NT, TM ? 2 : 1)
 lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash, const float* __restrict__ w_hh,
                     const int32_t* __restrict__ len, const int32_t* __restrict__ off, const int32_t* __restrict__ order,
                     int N, int ntiles, const float* __restrict__ dh, const float* __restrict__ dcn, int* __restrict__ tile_counter,
@@ -878,9 +891,13 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
   // ran the tile.
   constexpr int HID = G::HID, CL = G::CL, MT = G::MT, UPC = G::UPC, UPW = G::UPW, NTW = G::NTW;
   constexpr int PITCH = G::BPITCH, WP = G::BWPITCH, RP = G::RPITCH;
+  constexpr int NTH = TM ? G3::NT : G::NT;                         // threads of the CTA
+  constexpr int NCOPY = NTH - G::CT;                               // copy threads: 16 chunk lanes x RSLOT row slots
+  constexpr int RSLOT = NCOPY / 16, RPT = MT / RSLOT;              // row slots, rows per copy thread (8 x 4, or 4 x 8 with TM)
+  constexpr int W_PLANE = TM ? G3::W7_PLANE : G::B_W_PLANE;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned char* Wsm = smem_raw;                                   // [2 planes][HID units][WP] swizzled  (B operand)
-  unsigned char* Zsm = Wsm + 2 * G::B_W_PLANE;                     // [2 planes][MT][PITCH]          (A operand: dz)
+  unsigned char* Wsm = smem_raw;                                   // [2 planes][HID units][WP] swizzled  (B operand); TM: units 48..55 only
+  unsigned char* Zsm = Wsm + 2 * W_PLANE;                          // [2 planes][MT][PITCH]          (A operand: dz)
   unsigned char* Rsm = Zsm + 2 * G::B_Z_PLANE;                     // [CL sources][MT][40] fp32 partial dh from each CTA
   unsigned char* Ssm = Rsm + G::B_RECV;                            // [CL owners][MT][40]  fp32 partials staged for the bulk copies
   unsigned char* Stg = Ssm + G::B_RECV;                            // [B_NARR][MT][SROW] staging tile
@@ -897,11 +914,16 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
   const int R = r8 + 8 * q;
   const int unit0 = rank * UPC + w * UPW;
 
-  // W slice -> smem (bf16 hi / lo): row n = hidden unit k of the OUTPUT dh, column kk = own gate column in
+  // phase 2 tiling: 25 n8 tiles of output units over 4 warps: 7, 6, 6, 6
+  const int nt0 = w * 6 + (w > 0 ? 1 : 0);
+  const bool seven = (w == 0);
+  // W slice (bf16 hi / lo): row n = hidden unit k of the OUTPUT dh, column kk = own gate column in
   // (warp, gate, unit) order -- the order phase 1 writes dz in
-  {
+  __shared__ uint32_t tmem_slot;
+  uint32_t tm_w = 0;
+  if (!TM) {
     const float* W = w_hh + (size_t)dir * 4 * HID * HID;
-    for (int idx = tid; idx < G::BK * HID; idx += G::NT) {
+    for (int idx = tid; idx < G::BK * HID; idx += NTH) {
       const int kk = idx / HID, n = idx - kk * HID;
       const int ww = kk / 40, rem = kk - ww * 40, g = rem / UPW, i = rem - g * UPW;
       const float v = W[(size_t)(g * HID + rank * UPC + ww * UPW + i) * HID + n];
@@ -910,6 +932,49 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
       const size_t o = (size_t)n * WP + (((kk >> 3) ^ ((n >> 1) & 3)) << 4) + (kk & 7) * 2;
       *reinterpret_cast<uint16_t*>(Wsm + o) = hi;
       *reinterpret_cast<uint16_t*>(Wsm + G::B_W_PLANE + o) = lo;
+    }
+  } else {
+    // -> TENSOR MEMORY, already in mma.sync B-fragment form.  Lane l of compute warp w (TMEM lanes 32 w + l) keeps, for every
+    // k-step ks and each of the warp's first six n8 tiles nt, the registers b0 = W^T[16 ks + 2 (l % 4) + {0, 1}][n], b1 = the
+    // same 8 further along k, n = 8 (nt0 + nt) + l / 4, as bf16 hi and lo: columns (ks * 6 + nt) * 4 + {0: hi b0, 1: hi b1,
+    // 2: lo b0, 3: lo b1}.  Warp 0's seventh tile (units 48..55) stays in shared memory in the layout of the full slice.
+    if (w == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr_u32(&tmem_slot)), "n"(G3::TM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tm_w = tmem_slot + ((uint32_t)((w & 3) * 32) << 16);           // this warp's lane quarter
+    const float* W = w_hh + (size_t)dir * 4 * HID * HID;
+    auto wval = [&](int kk, int n) -> float {
+      const int ww = kk / 40, rem = kk - ww * 40, g = rem / UPW, i = rem - g * UPW;
+      return W[(size_t)(g * HID + rank * UPC + ww * UPW + i) * HID + n];
+    };
+    if (w < 4) {
+#pragma unroll 1
+      for (int ks = 0; ks < G::BKS; ++ks) {
+#pragma unroll 1
+        for (int nt = 0; nt < 6; ++nt) {
+          const int n = 8 * (nt0 + nt) + (lane >> 2);
+          const int k0 = 16 * ks + 2 * (lane & 3);
+          uint32_t h0, l0, h1, l1;
+          split2<false>(wval(k0, n), wval(k0 + 1, n), h0, l0);
+          split2<false>(wval(k0 + 8, n), wval(k0 + 9, n), h1, l1);
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tm_w + (uint32_t)((ks * 6 + nt) * 4)), "r"(h0),
+                       "r"(h1), "r"(l0), "r"(l1)
+                       : "memory");
+        }
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    for (int idx = tid; idx < G::BK * 8; idx += NTH) {             // units 48..55 (warp 0's seventh n-tile)
+      const int kk = idx >> 3, r = idx & 7;
+      uint16_t hi, lo;
+      split1<false>(wval(kk, 48 + r), hi, lo);
+      const size_t o = (size_t)r * WP + (((kk >> 3) ^ ((r >> 1) & 3)) << 4) + (kk & 7) * 2;
+      *reinterpret_cast<uint16_t*>(Wsm + o) = hi;
+      *reinterpret_cast<uint16_t*>(Wsm + G3::W7_PLANE + o) = lo;
     }
   }
   __shared__ __align__(8) uint64_t rbar[2];
@@ -930,13 +995,10 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
   const size_t GS = (size_t)2 * 4 * HID;
   PROF_DECL
 
-  // phase 2 tiling: 25 n8 tiles of output units over 4 warps: 7, 6, 6, 6
-  const int nt0 = w * 6 + (w > 0 ? 1 : 0);
-  const bool seven = (w == 0);
   const uint32_t a_off = (uint32_t)((lane & 15) * PITCH + (lane >> 4) * 16);
   // B: row = n-tile row (lane & 7), logical chunk 2ks + kh, physical chunk = logical ^ ((row >> 1) & 3)
   const uint32_t b_row = (uint32_t)(((nt0 + (lane >> 4)) * 8 + (lane & 7)) * WP);
-  const uint32_t b_row6 = (uint32_t)(((nt0 + 6) * 8 + (lane & 7)) * WP);
+  const uint32_t b_row6 = TM ? (uint32_t)((lane & 7) * WP) : (uint32_t)(((nt0 + 6) * 8 + (lane & 7)) * WP);
   const uint32_t b_kh = (uint32_t)((lane >> 3) & 1), b_x = (uint32_t)((lane & 7) >> 1);
   const bool copy_role = w >= 4;                                 // warps 4-7 move the staging tile to / from global memory
   const int c_ch = tid & 15, c_rs = (tid - G::CT) >> 4;
@@ -969,20 +1031,20 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
     if (copy_role) {
       // ---- copy warps: the activated gates and dh of iteration s-1 come into the staging tile, dL/dgx of iteration s
       // goes out, with the same chunk mapping as the forward kernel
-      int c_len[4], c_off[4];
+      int c_len[RPT], c_off[RPT];         // rows c_rs + RSLOT * rr of the tile
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr) { c_len[rr] = s_len[c_rs + 8 * rr]; c_off[rr] = s_off[c_rs + 8 * rr]; }
+      for (int rr = 0; rr < RPT; ++rr) { c_len[rr] = s_len[c_rs + RSLOT * rr]; c_off[rr] = s_off[c_rs + RSLOT * rr]; }
       auto prefetch_stash = [&](int s1) {
         if (c_ch < 10) {
 #pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
+          for (int rr = 0; rr < RPT; ++rr) {
             if (s1 < c_len[rr]) {
               const int t = dir ? (c_len[rr] - 1 - s1) : s1;
               const size_t p = (size_t)c_off[rr] + t;
               const float* g1 = gates + p * GS + (size_t)dir * 4 * HID + rank * UPC + c_ch * 4;
 #pragma unroll
-              for (int a = 0; a < 4; ++a) cp_async16(stg_local + c_so + rr * 8 * G::SROW + a * G::SARR, g1 + a * HID);
-              cp_async16(stg_local + c_so + rr * 8 * G::SROW + 4 * G::SARR, dh + p * 2 * HID + (size_t)dir * HID + rank * UPC + c_ch * 4);
+              for (int a = 0; a < 4; ++a) cp_async16(stg_local + c_so + rr * RSLOT * G::SROW + a * G::SARR, g1 + a * HID);
+              cp_async16(stg_local + c_so + rr * RSLOT * G::SROW + 4 * G::SARR, dh + p * 2 * HID + (size_t)dir * HID + rank * UPC + c_ch * 4);
             }
             const int s3 = s1 - NNR_LSTM_PFD;                  // the iteration NNR_LSTM_PFD steps ahead: pull its lines into L2
             if (NNR_LSTM_PFD > 0 && pf_lane && s3 >= 0 && s3 < c_len[rr]) {
@@ -997,7 +1059,7 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
         }
         cp_async_commit();
         cp_async_wait_all();
-        bar_arrive(3, G::NT);
+        bar_arrive(3, NTH);
       };
       prefetch_stash(maxlen - 1);
       float csum[4][4];                  // column sums of this thread's 4 gates x 4 units over its rows and all steps
@@ -1006,14 +1068,14 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
 #pragma unroll
         for (int j = 0; j < 4; ++j) csum[a][j] = 0.f;
       for (int s = maxlen - 1; s >= 0; --s) {
-        bar_sync(2, G::NT);              // the staging tile holds dL/dgx of iteration s
+        bar_sync(2, NTH);              // the staging tile holds dL/dgx of iteration s
         if (c_ch < 10) {
 #pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
+          for (int rr = 0; rr < RPT; ++rr) {
             if (s < c_len[rr]) {
               const int t = dir ? (c_len[rr] - 1 - s) : s;
               const size_t p = (size_t)c_off[rr] + t;
-              const unsigned char* spc = Stg + c_so + rr * 8 * G::SROW;
+              const unsigned char* spc = Stg + c_so + rr * RSLOT * G::SROW;
               const size_t go = p * GS + (size_t)dir * 4 * HID + rank * UPC + c_ch * 4;
               if (dzp) {
 #pragma unroll
@@ -1045,20 +1107,20 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
         if (s > 0) prefetch_stash(s - 1);
       }
       if (dzp) {
-        // per-tile column sums: the 8 row-slot threads of a column group are combined through the (now idle) staging
+        // per-tile column sums: the RSLOT row-slot threads of a column group are combined through the (now idle) staging
         // tile in slot order
         float* scr = reinterpret_cast<float*>(Stg);
-        bar_sync(4, G::NT - G::CT);      // every copy warp is done reading the staging tile
+        bar_sync(4, NCOPY);      // every copy warp is done reading the staging tile
         if (c_ch < 10) {
 #pragma unroll
           for (int a = 0; a < 4; ++a)
             *reinterpret_cast<float4*>(scr + c_rs * G::COLS + a * UPC + c_ch * 4) = make_float4(csum[a][0], csum[a][1], csum[a][2], csum[a][3]);
         }
-        bar_sync(4, G::NT - G::CT);
-        for (int col = tid - G::CT; col < G::COLS; col += G::NT - G::CT) {
+        bar_sync(4, NCOPY);
+        for (int col = tid - G::CT; col < G::COLS; col += NCOPY) {
           float sum = 0.f;
 #pragma unroll
-          for (int rs = 0; rs < 8; ++rs) sum += scr[rs * G::COLS + col];
+          for (int rs = 0; rs < RSLOT; ++rs) sum += scr[rs * G::COLS + col];
           const int a = col / UPC, u = col - a * UPC;
           db_partial[(size_t)tile * GS + (size_t)dir * 4 * HID + a * HID + rank * UPC + u] = sum;
         }
@@ -1096,7 +1158,7 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
       }
       PROF_MARK(0)
       if (s < maxlen - 1) { lbar_wait_cluster(rfull, ph_full); ph_full ^= 1u; }   // partials of iteration s+1 landed
-      bar_sync(3, G::NT);            // the copy warps have fetched the stash of iteration s
+      bar_sync(3, NTH);            // the copy warps have fetched the stash of iteration s
       PROF_MARK(1)
       // ---- phase 1: d(pre-activations) of this lane's row and ten units ---------------------------------------
       {
@@ -1188,7 +1250,7 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
 #pragma unroll
         for (int d = 0; d < CL; ++d) rbar_arrive_relaxed(mapa_u32(rfree_local, d));  // "my recv may be overwritten"
       }
-      bar_arrive(2, G::NT);  // hand the staging tile (dL/dgx of iteration s) to the copy warps
+      bar_arrive(2, NTH);  // hand the staging tile (dL/dgx of iteration s) to the copy warps
       if (s == 0) break;
       PROF_MARK(3)
       // ---- phase 2: partial dh_{t-1}[32 x units of this warp's n-tiles] = dz[32 x 160] x W_slice --------------
@@ -1238,7 +1300,7 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
           for (int nt = 0; nt < 7; ++nt)
             if (nt < 6 || seven) mma16816<false>(acc[mt][nt], f.ah[mt], f.bh[nt][0], f.bh[nt][1]);
       };
-      {
+      if (!TM) {
         Frag f0, f1;
         load_frags(f0, 0);
 #pragma unroll
@@ -1247,6 +1309,63 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
           mma_all(f0);
           if (ks + 2 < G::BKS) load_frags(f0, ks + 2);
           mma_all(f1);
+        }
+      } else {
+        // A fragments (dz, shared memory) double-buffered in registers; B fragments of one k-step from tensor memory
+        // (24 registers: six tiles x {hi b0, hi b1, lo b0, lo b1}), the seventh tile of warp 0 from shared memory
+        struct FragA { uint32_t ah[2][4], al[2][4]; };
+        auto load_a = [&](FragA& f, int ks) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            ldsm_x4(z_local + a_off + mt * 16 * PITCH + ks * 32, f.ah[mt][0], f.ah[mt][1], f.ah[mt][2], f.ah[mt][3]);
+            if (!SINGLE)
+              ldsm_x4(z_local + G::B_Z_PLANE + a_off + mt * 16 * PITCH + ks * 32, f.al[mt][0], f.al[mt][1], f.al[mt][2], f.al[mt][3]);
+          }
+        };
+        auto step = [&](const FragA& fa, int ks) {
+          uint32_t r[24], b6h[2] = {0u, 0u}, b6l[2] = {0u, 0u};
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                       : "r"(tm_w + (uint32_t)(ks * 24)));
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
+                       : "r"(tm_w + (uint32_t)(ks * 24 + 16)));
+          if (seven) {
+            const uint32_t bc = (((uint32_t)(2 * ks) + b_kh) ^ b_x) << 4;
+            ldsm_x2(w_local + b_row6 + bc, b6h[0], b6h[1]);
+            if (!SINGLE) ldsm_x2(w_local + G3::W7_PLANE + b_row6 + bc, b6l[0], b6l[1]);
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (!SINGLE) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+              for (int nt = 0; nt < 6; ++nt) mma16816<false>(acc[mt][nt], fa.al[mt], r[4 * nt], r[4 * nt + 1]);
+              if (seven) mma16816<false>(acc[mt][6], fa.al[mt], b6h[0], b6h[1]);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+              for (int nt = 0; nt < 6; ++nt) mma16816<false>(acc[mt][nt], fa.ah[mt], r[4 * nt + 2], r[4 * nt + 3]);
+              if (seven) mma16816<false>(acc[mt][6], fa.ah[mt], b6l[0], b6l[1]);
+            }
+          }
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+            for (int nt = 0; nt < 6; ++nt) mma16816<false>(acc[mt][nt], fa.ah[mt], r[4 * nt], r[4 * nt + 1]);
+            if (seven) mma16816<false>(acc[mt][6], fa.ah[mt], b6h[0], b6h[1]);
+          }
+        };
+        FragA a0, a1;
+        load_a(a0, 0);
+#pragma unroll
+        for (int ks = 0; ks < G::BKS; ks += 2) {
+          load_a(a1, ks + 1);
+          step(a0, ks);
+          if (ks + 2 < G::BKS) load_a(a0, ks + 2);
+          step(a1, ks + 1);
         }
       }
       PROF_MARK(4)
@@ -1283,13 +1402,18 @@ lstm_bwd_mma_kernel(float* __restrict__ gates, const float* __restrict__ c_stash
     }
   }
   PROF_FLUSH(8)
+  if (TM) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "n"(G3::TM_COLS) : "memory");
+  }
   cluster_arrive();
   cluster_wait();
 }
 
 template <class K>
 int launch_cluster5(K kernel, size_t smem, int ntiles, cudaStream_t st, void** args, const char* name, int (*cache_tab)[16],
-                    bool (*attr_tab)[16], int variant, int nthreads = G::NT) {
+                    bool (*attr_tab)[16], int variant, int nthreads = G::NT, bool bwd = false) {
   int dev = 0;
   NNR_CUDA(cudaGetDevice(&dev));
   dev &= 15;                                  // the attribute and the occupancy are per device (and per instantiation)
@@ -1319,7 +1443,7 @@ int launch_cluster5(K kernel, size_t smem, int ntiles, cudaStream_t st, void** a
     // does co-schedule them.  Measured on B200, N = 3520, L = 128 forward: 26 clusters 4.67 ms, 40: 4.09, 52: 3.50, 56: 3.43,
     // 58: 3.32, 64: 3.45, 72: 3.40 -> 2 nc + 6.  Clusters beyond what fits start late, find the tile counter exhausted and exit.
     if (nthreads == G2::NT) *cache = (2 * nc + 6) & ~1;
-    if (const char* ev = getenv("NNR_LSTM_FWD_CLUSTERS")) { int v = atoi(ev); if (v >= 2 && nthreads == G2::NT) *cache = v & ~1; }
+    if (const char* ev = getenv(bwd ? "NNR_LSTM_BWD_CLUSTERS" : "NNR_LSTM_FWD_CLUSTERS")) { int v = atoi(ev); if (v >= 2 && nthreads == G2::NT) *cache = v & ~1; }
     if (getenv("NNR_LSTM_DEBUG")) {
       int bps = -1;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void*)kernel, nthreads, smem);
@@ -1408,16 +1532,24 @@ __global__ void lstm_dz_finish_kernel(const float* __restrict__ db_partial, int 
 int nnr_lstm_bwd_mma(float* gates, const float* c_stash, const float* w_hh, const int32_t* len, const int32_t* off,
                      const int32_t* order, int N, const float* dh, const float* dcn, int32_t* tile_counters, cudaStream_t st,
                      void* dz_planes, size_t plane_stride, int two_planes, float* db_partial, float* db, int cap) {
-  static int cache[2][16] = {};
-  static bool attr_set[2][16] = {};
+  static int cache[4][16] = {};
+  static bool attr_set[4][16] = {};
   int ntiles = (N + G::MT - 1) / G::MT;
   NNR_CUDA(cudaMemsetAsync(tile_counters, 0, 2 * sizeof(int32_t), st));
   __nv_bfloat16* dzp = (__nv_bfloat16*)dz_planes;
   void* args[] = {&gates, &c_stash, &w_hh, &len, &off, &order, &N, &ntiles, &dh, &dcn, &tile_counters,
                   &dzp, &plane_stride, &two_planes, &db_partial};
-  int rc = nnr_lstm_single_product()
-               ? launch_cluster5(lstm_bwd_mma_kernel<true>, G::BWD_SMEM, ntiles, st, args, "lstm_bwd_mma_kernel<single>", cache, attr_set, 1)
-               : launch_cluster5(lstm_bwd_mma_kernel<false>, G::BWD_SMEM, ntiles, st, args, "lstm_bwd_mma_kernel", cache, attr_set, 0);
+  static int use_tm = -1;          // W slice in tensor memory, two CTAs per SM (default); NNR_LSTM_BWD_TM=0: W planes in shared memory
+  if (use_tm < 0) { const char* e = getenv("NNR_LSTM_BWD_TM"); use_tm = e ? atoi(e) : 1; }
+  int rc;
+  if (use_tm)
+    rc = nnr_lstm_single_product()
+             ? launch_cluster5(lstm_bwd_mma_kernel<true, true>, G3::BWD_SMEM, ntiles, st, args, "lstm_bwd_tm_kernel<single>", cache, attr_set, 3, G3::NT, true)
+             : launch_cluster5(lstm_bwd_mma_kernel<false, true>, G3::BWD_SMEM, ntiles, st, args, "lstm_bwd_tm_kernel", cache, attr_set, 2, G3::NT, true);
+  else
+    rc = nnr_lstm_single_product()
+             ? launch_cluster5(lstm_bwd_mma_kernel<true, false>, G::BWD_SMEM, ntiles, st, args, "lstm_bwd_mma_kernel<single>", cache, attr_set, 1)
+             : launch_cluster5(lstm_bwd_mma_kernel<false, false>, G::BWD_SMEM, ntiles, st, args, "lstm_bwd_mma_kernel", cache, attr_set, 0);
   if (rc || !dz_planes) return rc;
   const int cols = 8 * G::HID;
   lstm_dz_finish_kernel<<<(cols + 255) / 256 * 4, 256, 0, st>>>(db_partial, ntiles, cols, db, dzp, plane_stride, two_planes ? 2 : 1, cap, off + N);
