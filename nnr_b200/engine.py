@@ -69,6 +69,7 @@ def _empty(shape, dev, dtype=torch.float32):
 # inside a captured step the two lanes become parallel branches of the CUDA graph.  NNR_LANES=0 (or
 # engine.concurrent = False, used by the per-op profiler) issues everything on the caller's stream in the same order.
 _LANES = os.environ.get('NNR_LANES', '1') != '0'
+_CONTENT_FIRST = os.environ.get('NNR_CONTENT_FIRST', '1') != '0'     # A/B switch: issue order of the two BPTT recurrences
 concurrent = True
 _side_streams = {}
 
@@ -621,15 +622,17 @@ class CNEFunction(torch.autograd.Function):
             ops.embed_gather_bwd(demb, m.ids, m.len, m.off, dtable, m.p, m.seed, not first[0])
             first[0] = False
 
-        def weight_grads(x, m, dz, dz_pl, db):
+        def shifted_h(m, planes):
+            """h_{t-1} of every token = the second operand of the recurrent weight gradient; a GEMM operand only: straight to planes"""
+            if planes:
+                return None, ops.lstm_shift_h_planes(m.h, m.len, m.off, m.tok_row, N, m.L, Hd, m.cap)
+            hprev = _empty((m.cap, D2), dev)
+            ops.lstm_shift_h(m.h, m.len, m.off, m.tok_row, N, m.L, Hd, hprev)
+            return hprev, None
+
+        def weight_grads(x, m, dz, dz_pl, db, hp=None):
             pre = x + '_lstm.'
-            if dz_pl is not None:                 # hprev is only a GEMM operand: straight to planes
-                hprev = None
-                hprev_pl = ops.lstm_shift_h_planes(m.h, m.len, m.off, m.tok_row, N, m.L, Hd, m.cap)
-            else:
-                hprev_pl = None
-                hprev = _empty((m.cap, D2), dev)
-                ops.lstm_shift_h(m.h, m.len, m.off, m.tok_row, N, m.L, Hd, hprev)
+            hprev, hprev_pl = hp if hp is not None else shifted_h(m, dz_pl is not None)
             for d, sfx in enumerate(('', '_reverse')):
                 G[pre + 'weight_hh_l0' + sfx] = wgrad(dz[:, d * 4 * Hd:(d + 1) * 4 * Hd] if dz is not None else None,
                                                      hprev[:, d * Hd:(d + 1) * Hd] if hprev is not None else None,
@@ -652,13 +655,24 @@ class CNEFunction(torch.autograd.Function):
         else:
             # lane 1: title recurrence, title scatter, content scatter (the chain the end of the backward pass waits for);
             # lane 2: the title branch's weight gradients; caller's stream: content recurrence, content weight gradients
+            # (the content recurrence is issued first: its longest sequences are the critical path of this stage, the title
+            # recurrence fills the SMs its short tiles leave idle)
             lanes.fork()
+            thp = None
+            if _CONTENT_FIRST:
+                # the content recurrence must get the SMs first -- its longest sequences are the critical path of this stage
+                # and the title recurrence fits into the SMs its short tiles leave idle: the title lane starts with a kernel
+                # it needs anyway (h_{t-1} planes), so its recurrence is launched a few microseconds after the content one
+                planes = t.emb is None and ops.lstm_bwd_planes_supported(Hd)
+                thp = lanes.on_side(shifted_h, t, planes)
+                dz, dz_pl, db, demb = recurrence_bwd('content', c, dcn['content'])
             tz, tz_pl, tdb, tdemb = lanes.on_side(recurrence_bwd, 'title', t, dcn['title'])
             lanes.on_side(scatter, 'title', t, tdemb)
             lanes.fork(2, after=1)
-            lanes.on_side(weight_grads, 'title', t, tz, tz_pl, tdb, lane=2)
-            dz, dz_pl, db, demb = recurrence_bwd('content', c, dcn['content'])
-            lanes.keep.extend((tz, tz_pl, tdemb, dz, dz_pl, demb))
+            lanes.on_side(weight_grads, 'title', t, tz, tz_pl, tdb, thp, lane=2)
+            if not _CONTENT_FIRST:
+                dz, dz_pl, db, demb = recurrence_bwd('content', c, dcn['content'])
+            lanes.keep.extend((tz, tz_pl, tdemb, dz, dz_pl, demb, thp))
             lanes.fork()                                       # lane 1, behind the title scatter
             lanes.on_side(scatter, 'content', c, demb)
             if in_place:
