@@ -109,6 +109,17 @@ class Lanes:
         finally:
             ops.lane = prev
 
+    def leaf(self, fn, *a, **k):
+        """issue fn on lane 2, ordered after everything issued so far on the CURRENT lane: for work nothing on the critical
+        path waits for (weight gradients); its results are valid after the next full join()"""
+        if not self.on:
+            return fn(*a, **k)
+        cur = ops.lane
+        if cur == 2:
+            return fn(*a, **k)
+        self.fork(2, after=cur)
+        return self.on_side(fn, *a, lane=2, **k)
+
     def join(self, *which):
         """the caller's stream waits for the given side lanes (default: every lane forked since its last join)"""
         if self.on:
@@ -556,10 +567,10 @@ class CNEFunction(torch.autograd.Function):
             db1 = _empty((A,), dev)
             dU_pl = split_tokens(dU, m.cap, A, m.ntok, colsum_out=db1)
             matmul_nn(dU, P[sa + 'affine1.weight'], m.cap, m.ntok, out=m.dhg, accumulate=True, x_planes=dU_pl)
-            G[sa + 'affine1.weight'] = wgrad(dU, m.hg, m.cap, A, D2, k_dev=m.ntok, dy_planes=dU_pl, x_planes=m.hg_pl)
+            # (weight gradients are leaves: lane 2, under the memory-bound gate backward and the next data-gradient GEMM)
+            G[sa + 'affine1.weight'] = lanes.leaf(wgrad, dU, m.hg, m.cap, A, D2, k_dev=m.ntok, dy_planes=dU_pl, x_planes=m.hg_pl)
             G[sa + 'affine1.bias'] = db1
-            del dU, dU_pl
-            lanes.keep.append(m.hg_pl)           # released at the join: a lane never hands memory back while the other may run
+            lanes.keep.extend((dU, dU_pl, m.hg_pl))   # released at the join: a lane never hands memory back while another may read it
             m.hg_pl = None
             if not gate:                       # CNE_wo_CS / single modality: hg is h, nothing flows into another cell state
                 m.dh = m.dhg
@@ -577,8 +588,8 @@ class CNEFunction(torch.autograd.Function):
                 ops.segment_colsum(dz, D2, m.off, N, D2, dmproj, D2)
             m.dh = matmul_nn(dz, P[x + '_H.weight'], m.cap, m.ntok, epilogue=EPI_ADD_AUX, aux=dh0, ldaux=D2, out=m.dhg,
                              x_planes=dz_pl)
-            G[x + '_H.weight'] = wgrad(dz, m.h, m.cap, D2, D2, k_dev=m.ntok, dy_planes=dz_pl, x_planes=m.h_pl)
-            lanes.keep.append(m.h_pl)
+            G[x + '_H.weight'] = lanes.leaf(wgrad, dz, m.h, m.cap, D2, D2, k_dev=m.ntok, dy_planes=dz_pl, x_planes=m.h_pl)
+            lanes.keep.extend((m.h_pl, dz, dz_pl))
             m.h_pl = None
             dbm = _empty((D2,), dev)
             dmproj_pl = _shared_split(dmproj, N, D2, colsum_out=dbm)                       # shared by both GEMMs, + bias gradient
