@@ -110,6 +110,11 @@ typedef struct {
    * plane_rows = rows of the full planes (plane stride = plane_rows * pitch). */
   const void* A_planes; int64_t a_planes_pitch; int64_t a_planes_rows;
   const void* B_planes; int64_t b_planes_pitch; int64_t b_planes_rows;
+  /* optional (bf16 tensor-core algos, N % 8 == 0, epilogue operands 16-byte aligned, no split-K): the result is ALSO written
+   * as the operand planes nnr_tc_split(C, ..., m_dev) would produce -- [hi|lo][c_planes_rows][pitch] bf16, rows
+   * [M_eff, round_up(M_eff, 64)) zero-filled -- so that a GEMM whose output feeds further GEMMs needs no split pass
+   * (newsEncoders.py:128-131: the gated states feed the attention projections).  NNR_ERR_UNSUPPORTED otherwise. */
+  void* C_planes; int64_t c_planes_pitch; int64_t c_planes_rows;
 } nnr_gemm_args;
 size_t nnr_gemm_workspace_bytes(const nnr_gemm_args* args);
 int nnr_gemm(const nnr_gemm_args* args, void* stream);
@@ -178,6 +183,13 @@ int nnr_lstm_fwd(float* gx, const float* w_hh, const int32_t* len, const int32_t
 int nnr_lstm_bwd(float* gates, const float* c_stash, const float* w_hh, const int32_t* len,
                  const int32_t* off, const int32_t* order, int N, int L, int H, const float* dh,
                  const float* dcn, int32_t* tile_counters, void* stream);
+/* nnr_lstm_fwd whose h ALSO leaves as the operand planes nnr_tc_split(h, cap, 2H, ntok) would produce ([hi|lo][cap][2H] bf16,
+ * rows [tokens, round_up(tokens, 64)) zeroed): h feeds the selective-gate GEMM and two weight-gradient GEMMs
+ * (newsEncoders.py:128-131), the split pass over it is skipped.  bf16 tensor-core algos, H = 200. */
+int nnr_lstm_fwd_planes_supported(int H, int algo);
+int nnr_lstm_fwd_planes(float* gx, const float* w_hh, const int32_t* len, const int32_t* off, const int32_t* order,
+                        int N, int L, int H, float* h_out, float* c_stash, float* c_n, int32_t* tile_counters, int cap,
+                        int algo, void* planes, size_t planes_bytes, void* stream);
 /* The same BPTT with dL/d(gx) written as the operand planes of the tensor-core GEMM (layout of nnr_tc_split for a
  * [cap, 8H] matrix, rows [tokens, round_up(tokens, 64)) zeroed) and db[8H] = its column sums over the tokens (the bias
  * gradient; per-tile partials added in tile order, run-to-run identical).  dL/d(gx) feeds only GEMMs and that column

@@ -33,7 +33,8 @@ class GemmArgs(C.Structure):
                 ('algo', i32),
                 ('workspace', vp), ('workspace_bytes', sz),
                 ('A_planes', vp), ('a_planes_pitch', i64), ('a_planes_rows', i64),
-                ('B_planes', vp), ('b_planes_pitch', i64), ('b_planes_rows', i64)]
+                ('B_planes', vp), ('b_planes_pitch', i64), ('b_planes_rows', i64),
+                ('C_planes', vp), ('c_planes_pitch', i64), ('c_planes_rows', i64)]
 
 
 class PoolArgs(C.Structure):
@@ -86,6 +87,8 @@ SIGNATURES = {
     'nnr_lstm_fwd': (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]),
     'nnr_lstm_bwd': (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
     'nnr_lstm_bwd_planes_supported': (C.c_int, [C.c_int, C.c_int]),
+    'nnr_lstm_fwd_planes_supported': (C.c_int, [C.c_int, C.c_int]),
+    'nnr_lstm_fwd_planes': (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp, sz, vp]),
     'nnr_lstm_bwd_planes_workspace_bytes': (sz, [C.c_int, C.c_int]),
     'nnr_lstm_bwd_planes': (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, sz, vp,
                                       vp, sz, vp]),

@@ -68,6 +68,7 @@ extern "C" int nnr_gemm(const nnr_gemm_args* a, void* stream) {
   int algo = pick_algo(a);
   if (algo == NNR_GEMM_SIMT_FP32) {
     NNR_REQUIRE(a->A && a->B, NNR_ERR_UNSUPPORTED, "nnr_gemm: an operand given only as planes needs the tensor-core path");
+    NNR_REQUIRE(!a->C_planes, NNR_ERR_UNSUPPORTED, "nnr_gemm: C_planes needs the tensor-core path");
     return nnr_gemm_simt(a, stream);
   }
   NNR_REQUIRE(nnr_gemm_tc_supported(a), NNR_ERR_UNSUPPORTED, "nnr_gemm: tensor-core path does not support this shape/layout");

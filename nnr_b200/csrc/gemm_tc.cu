@@ -189,6 +189,9 @@ struct TcParams {
   uint32_t idesc;
   float* partial;
   int epi_fast;                // N % 4 == 0 and every epilogue pointer / leading dimension 16-byte aligned: straight-line float4 path
+  __nv_bfloat16* c_planes;     // optional: the result also as bf16 operand planes [hi|lo][c_prows][c_pitch] (fast epilogue only)
+  long long c_pitch, c_pstride;   // row pitch and plane stride in elements
+  int c_lo, c_rows;            // write the lo plane (split algos); rows of the planes
   EpiP epi;
 };
 
@@ -521,6 +524,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                 v.x += cc.x; v.y += cc.y; v.z += cc.z; v.w += cc.w;
               }
               *reinterpret_cast<float4*>(p.epi.C + o_c[i] + n) = v;
+              if (p.c_planes) {           // same rounding as tc_split_store4: hi = rn(x), lo = rn(x - hi)
+                const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+                __nv_bfloat16* o = p.c_planes + (long long)(m0 + q * 32 + tr + 8 * i) * p.c_pitch + n;
+                uint2 hv;
+                hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                *reinterpret_cast<uint2*>(o) = hv;
+                if (p.c_lo) {
+                  const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __low2float(h01), v.y - __high2float(h01));
+                  const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __low2float(h23), v.w - __high2float(h23));
+                  uint2 lv;
+                  lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                  *reinterpret_cast<uint2*>(o + p.c_pstride) = lv;
+                }
+              }
+            }
+            if (p.c_planes) {             // rows [M, round_up(M, 64)) of the planes are the zero tail an MN-major consumer reads
+              const int mz = min(p.c_rows, (M + 63) & ~63);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int mm = m0 + q * 32 + tr + 8 * i;
+                if (mm >= M && mm < mz) {
+                  __nv_bfloat16* o = p.c_planes + (long long)mm * p.c_pitch + n;
+                  *reinterpret_cast<uint2*>(o) = make_uint2(0u, 0u);
+                  if (p.c_lo) *reinterpret_cast<uint2*>(o + p.c_pstride) = make_uint2(0u, 0u);
+                }
+              }
             }
           }
         } else if (cnt > 0) {
@@ -1075,6 +1104,17 @@ static int run_tc(const nnr_gemm_args* a, cudaStream_t st) {
     if ((double)a->M * (double)a->ldc >= lim || (double)a->M * (double)a->ldaux >= lim || (double)a->M * (double)a->ldaux_out >= lim ||
         (double)a->M * (double)a->ldrowbias >= lim)
       p.epi_fast = 0;
+  }
+  p.c_planes = nullptr; p.c_pitch = 0; p.c_pstride = 0; p.c_lo = 0; p.c_rows = 0;
+  if (a->C_planes) {
+    NNR_REQUIRE(BF16 && p.epi_fast && !pl.split_k && a->N % 8 == 0 && a->c_planes_pitch >= a->N && a->c_planes_pitch % 8 == 0 &&
+                    a->c_planes_rows >= a->M && nnr_aligned16(a->C_planes),
+                NNR_ERR_UNSUPPORTED, "nnr_gemm: C_planes needs a bf16 tensor-core algo, N %% 8 == 0, aligned epilogue operands, no split-K");
+    p.c_planes = (__nv_bfloat16*)a->C_planes;
+    p.c_pitch = a->c_planes_pitch;
+    p.c_pstride = a->c_planes_rows * a->c_planes_pitch;
+    p.c_lo = pl.nplanes == 2;
+    p.c_rows = (int)a->c_planes_rows;
   }
   // per-device caches: the dynamic shared-memory attribute is a property of (function, device), and so is the SM count
   static bool attr_set[16][2][2] = {};

@@ -506,7 +506,9 @@ static int launch_cluster(K kernel, size_t smem, int ntiles, cudaStream_t st, vo
 
 // tensor-core variant (lstm_mma.cu); NNR_LSTM_ALGO=ffma selects the exact-fp32 FFMA kernels of this file
 int nnr_lstm_fwd_mma(float* gx, const float* w_hh, const int32_t* len, const int32_t* off, const int32_t* order, int N,
-                     float* h_out, float* c_stash, float* c_n, int32_t* tile_counters, cudaStream_t st);
+                     float* h_out, float* c_stash, float* c_n, int32_t* tile_counters, cudaStream_t st, void* h_planes,
+                     size_t plane_stride, int two_planes, int cap);
+int nnr_lstm_fwd_planes_ok(void);
 int nnr_lstm_bwd_mma(float* gates, const float* c_stash, const float* w_hh, const int32_t* len, const int32_t* off,
                      const int32_t* order, int N, const float* dh, const float* dcn, int32_t* tile_counters, cudaStream_t st,
                      void* dz_planes, size_t plane_stride, int two_planes, float* db_partial, float* db, int cap);
@@ -527,7 +529,7 @@ extern "C" int nnr_lstm_fwd(float* gx, const float* w_hh, const int32_t* len, co
   NNR_REQUIRE(H == 200, NNR_ERR_UNSUPPORTED, "nnr_lstm_fwd: hidden_dim %d not instantiated (200 only)", H);
   NNR_REQUIRE(nnr_aligned16(gx) && nnr_aligned16(h_out) && nnr_aligned16(c_stash) && nnr_aligned16(c_n), NNR_ERR_ALIGN,
               "nnr_lstm_fwd: buffers must be 16B aligned");
-  if (lstm_use_mma()) return nnr_lstm_fwd_mma(gx, w_hh, len, off, order, N, h_out, c_stash, c_n, tile_counters, (cudaStream_t)stream);
+  if (lstm_use_mma()) return nnr_lstm_fwd_mma(gx, w_hh, len, off, order, N, h_out, c_stash, c_n, tile_counters, (cudaStream_t)stream, NULL, 0, 0, 0);
   typedef FwdCfg200 C;
   int ntiles = (N + C::MT - 1) / C::MT;
   NNR_CUDA(cudaMemsetAsync(tile_counters, 0, 2 * sizeof(int32_t), (cudaStream_t)stream));
@@ -550,6 +552,29 @@ extern "C" int nnr_lstm_bwd(float* gates, const float* c_stash, const float* w_h
   NNR_CUDA(cudaMemsetAsync(tile_counters, 0, 2 * sizeof(int32_t), (cudaStream_t)stream));
   void* args[] = {&gates, &c_stash, &w_hh, &len, &off, &order, &N, &ntiles, &dh, &dcn, &tile_counters};
   return launch_cluster<C>(lstm_bwd_kernel<C>, C::BWD_SMEM, ntiles, (cudaStream_t)stream, args, "lstm_bwd_kernel");
+}
+
+// forward recurrence whose h ALSO leaves as GEMM operand planes (h feeds the selective-gate GEMM and, in the backward pass, two
+// weight-gradient GEMMs: newsEncoders.py:128-131): the split pass over h is skipped.  planes = [hi|lo][cap][2H] bf16 as
+// nnr_tc_split(h, cap, 2H, ntok) would write them, rows [ntok, round_up(ntok, 64)) zeroed.
+extern "C" int nnr_lstm_fwd_planes_supported(int H, int algo) {
+  if (algo == NNR_GEMM_AUTO) algo = nnr_gemm_default_algo();
+  return H == 200 && lstm_use_mma() && nnr_lstm_fwd_planes_ok() && (algo == NNR_GEMM_TC_BF16 || algo == NNR_GEMM_TC_BF16X3);
+}
+extern "C" int nnr_lstm_fwd_planes(float* gx, const float* w_hh, const int32_t* len, const int32_t* off, const int32_t* order,
+                                   int N, int L, int H, float* h_out, float* c_stash, float* c_n, int32_t* tile_counters, int cap,
+                                   int algo, void* planes, size_t planes_bytes, void* stream) {
+  NNR_REQUIRE(gx && w_hh && len && off && order && h_out && c_stash && c_n && tile_counters && planes && N > 0 && L > 0 && cap > 0,
+              NNR_ERR_ARG, "nnr_lstm_fwd_planes: bad arguments");
+  if (algo == NNR_GEMM_AUTO) algo = nnr_gemm_default_algo();
+  NNR_REQUIRE(nnr_lstm_fwd_planes_supported(H, algo), NNR_ERR_UNSUPPORTED,
+              "nnr_lstm_fwd_planes: needs H = 200, the tensor-memory forward kernel and a bf16 GEMM algorithm");
+  NNR_REQUIRE(nnr_aligned16(gx) && nnr_aligned16(h_out) && nnr_aligned16(c_stash) && nnr_aligned16(c_n) && nnr_aligned16(planes),
+              NNR_ERR_ALIGN, "nnr_lstm_fwd_planes: buffers must be 16B aligned");
+  const int two = algo == NNR_GEMM_TC_BF16X3;
+  const size_t plane = (size_t)cap * 2 * H;
+  NNR_REQUIRE(planes_bytes >= plane * 2 * (two ? 2 : 1), NNR_ERR_WORKSPACE, "nnr_lstm_fwd_planes: planes buffer too small");
+  return nnr_lstm_fwd_mma(gx, w_hh, len, off, order, N, h_out, c_stash, c_n, tile_counters, (cudaStream_t)stream, planes, plane, two, cap);
 }
 
 // BPTT with dL/dgx emitted as GEMM operand planes + its column sums (the bias gradient): dL/dgx is only ever read by the

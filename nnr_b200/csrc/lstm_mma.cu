@@ -504,7 +504,10 @@ template <bool SINGLE>   // SINGLE: one 16-bit product (hi x hi) instead of the 
 __global__ void __launch_bounds__(G2::NT, 2)
 lstm_fwd_tm_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const int32_t* __restrict__ len,
                     const int32_t* __restrict__ off, const int32_t* __restrict__ order, int N, int ntiles,
-                    float* __restrict__ h_out, float* __restrict__ c_stash, float* __restrict__ c_n, int* __restrict__ tile_counter) {
+                    float* __restrict__ h_out, float* __restrict__ c_stash, float* __restrict__ c_n, int* __restrict__ tile_counter,
+                    __nv_bfloat16* __restrict__ hp, size_t hp_stride, int hp_lo) {
+  // hp != NULL: h also leaves as the bf16 operand planes of the tensor-core GEMMs that consume it ([hi|lo][cap][2H], plane
+  // stride hp_stride elements, lo plane only if hp_lo) -- the split pass over h is skipped (same rounding as tc_split_store4)
   constexpr int HID = G2::HID, CL = G2::CL, MT = G2::MT, UPC = G2::UPC, COLS = G2::COLS, NTW = G2::NTW, UPW = G2::UPW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char* Hsm = smem_raw;                                   // [2 buffers][CL blocks][2 planes][MT][80 B]
@@ -656,8 +659,22 @@ lstm_fwd_tm_kernel(float* __restrict__ gx, const float* __restrict__ w_hh, const
               for (int a = 0; a < 4; ++a) *reinterpret_cast<float4*>(g0 + a * HID) = *reinterpret_cast<const float4*>(sp + a * G2::SARR);
               const float4 cv = *reinterpret_cast<const float4*>(sp + 4 * G2::SARR);
               *reinterpret_cast<float4*>(c_stash + (p * 2 + dir) * HID + rank * UPC + c_ch * 4) = cv;
-              *reinterpret_cast<float4*>(h_out + p * 2 * HID + (size_t)dir * HID + rank * UPC + c_ch * 4) =
-                  *reinterpret_cast<const float4*>(sp + 5 * G2::SARR);
+              const float4 hv = *reinterpret_cast<const float4*>(sp + 5 * G2::SARR);
+              const size_t ho = p * 2 * HID + (size_t)dir * HID + rank * UPC + c_ch * 4;
+              *reinterpret_cast<float4*>(h_out + ho) = hv;
+              if (hp) {
+                const __nv_bfloat162 h01 = __floats2bfloat162_rn(hv.x, hv.y), h23 = __floats2bfloat162_rn(hv.z, hv.w);
+                uint2 hw;
+                hw.x = *reinterpret_cast<const uint32_t*>(&h01); hw.y = *reinterpret_cast<const uint32_t*>(&h23);
+                *reinterpret_cast<uint2*>(hp + ho) = hw;
+                if (hp_lo) {
+                  const __nv_bfloat162 l01 = __floats2bfloat162_rn(hv.x - __low2float(h01), hv.y - __high2float(h01));
+                  const __nv_bfloat162 l23 = __floats2bfloat162_rn(hv.z - __low2float(h23), hv.w - __high2float(h23));
+                  uint2 lw;
+                  lw.x = *reinterpret_cast<const uint32_t*>(&l01); lw.y = *reinterpret_cast<const uint32_t*>(&l23);
+                  *reinterpret_cast<uint2*>(hp + hp_stride + ho) = lw;
+                }
+              }
               if (s == rl - 1)
                 *reinterpret_cast<float4*>(c_n + (size_t)s_row[c_rs + 4 * rr] * 2 * HID + (size_t)dir * HID + rank * UPC + c_ch * 4) = cv;
               if (s + 1 < rl) {            // the row's next token is the adjacent one
@@ -1480,24 +1497,55 @@ static int nnr_lstm_single_product() {
   return v;
 }
 
+// zero rows [ntok, round_up(ntok, 64)) of operand planes written by a producer kernel: the k tail MN-major GEMM tiles read
+__global__ void planes_zero_tail_kernel(__nv_bfloat16* __restrict__ pl, size_t stride, int nplanes, int cols, int cap,
+                                        const int32_t* __restrict__ ntok_dev) {
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const int ntok = min(*ntok_dev, cap);
+  const int r1 = min(cap, (ntok + 63) / 64 * 64);
+  const int c8 = cols / 8;                                     // 16-byte groups per row
+  const long long total = (long long)(r1 - ntok) * c8 * nplanes;
+  for (long long i = gt; i < total; i += nthreads) {
+    const int p = (int)(i / ((long long)(r1 - ntok) * c8));
+    const long long rem = i - (long long)p * (r1 - ntok) * c8;
+    const int r = ntok + (int)(rem / c8), c = (int)(rem % c8) * 8;
+    *reinterpret_cast<uint4*>(pl + (size_t)p * stride + (size_t)r * cols + c) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+static int lstm_fwd_use_tm() {
+  static int use_tm = -1;          // W slice in tensor memory, two CTAs per SM (default); NNR_LSTM_FWD_TM=0: W planes in shared memory
+  if (use_tm < 0) { const char* e = getenv("NNR_LSTM_FWD_TM"); use_tm = e ? atoi(e) : 1; }
+  return use_tm;
+}
+int nnr_lstm_fwd_planes_ok(void) { return lstm_fwd_use_tm(); }
+
 int nnr_lstm_fwd_mma(float* gx, const float* w_hh, const int32_t* len, const int32_t* off, const int32_t* order, int N,
-                     float* h_out, float* c_stash, float* c_n, int32_t* tile_counters, cudaStream_t st) {
+                     float* h_out, float* c_stash, float* c_n, int32_t* tile_counters, cudaStream_t st, void* h_planes,
+                     size_t plane_stride, int two_planes, int cap) {
   static int cache[4][16] = {};
   static bool attr_set[4][16] = {};
   int ntiles = (N + G::MT - 1) / G::MT;
   NNR_CUDA(cudaMemsetAsync(tile_counters, 0, 2 * sizeof(int32_t), st));
-  void* args[] = {&gx, &w_hh, &len, &off, &order, &N, &ntiles, &h_out, &c_stash, &c_n, &tile_counters};
   const int single = nnr_lstm_single_product();
-  static int use_tm = -1;          // W slice in tensor memory, two CTAs per SM (default); NNR_LSTM_FWD_TM=0: W planes in shared memory
-  if (use_tm < 0) { const char* e = getenv("NNR_LSTM_FWD_TM"); use_tm = e ? atoi(e) : 1; }
+  const int use_tm = lstm_fwd_use_tm();
   if (use_tm) {
+    __nv_bfloat16* hp = (__nv_bfloat16*)h_planes;
+    void* args[] = {&gx, &w_hh, &len, &off, &order, &N, &ntiles, &h_out, &c_stash, &c_n, &tile_counters, &hp, &plane_stride, &two_planes};
     int rc2 = single ? launch_cluster5(lstm_fwd_tm_kernel<true>, G2::FWD_SMEM, ntiles, st, args, "lstm_fwd_tm_kernel<single>", cache, attr_set, 3, G2::NT)
                      : launch_cluster5(lstm_fwd_tm_kernel<false>, G2::FWD_SMEM, ntiles, st, args, "lstm_fwd_tm_kernel", cache, attr_set, 2, G2::NT);
     int dev2 = 0;
     cudaGetDevice(&dev2);
     nnr_lstm_mma_max_clusters = cache[2 + single][dev2 & 15];
-    return rc2;
+    if (rc2 || !hp) return rc2;
+    planes_zero_tail_kernel<<<32, 256, 0, st>>>(hp, plane_stride, two_planes ? 2 : 1, 2 * G::HID, cap, off + N);
+    nnr_count_launch(1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { nnr_set_error("planes_zero_tail_kernel: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
   }
+  if (h_planes) { nnr_set_error("nnr_lstm_fwd_planes: needs the tensor-memory forward kernel (NNR_LSTM_FWD_TM=1)"); return NNR_ERR_UNSUPPORTED; }
+  void* args[] = {&gx, &w_hh, &len, &off, &order, &N, &ntiles, &h_out, &c_stash, &c_n, &tile_counters};
   int rc = single ? launch_cluster5(lstm_fwd_mma_kernel<true>, G::FWD_SMEM, ntiles, st, args, "lstm_fwd_mma_kernel<single>", cache, attr_set, 1)
                   : launch_cluster5(lstm_fwd_mma_kernel<false>, G::FWD_SMEM, ntiles, st, args, "lstm_fwd_mma_kernel", cache, attr_set, 0);
   int dev = 0;

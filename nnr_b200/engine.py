@@ -69,6 +69,7 @@ def _empty(shape, dev, dtype=torch.float32):
 # inside a captured step the two lanes become parallel branches of the CUDA graph.  NNR_LANES=0 (or
 # engine.concurrent = False, used by the per-op profiler) issues everything on the caller's stream in the same order.
 _LANES = os.environ.get('NNR_LANES', '1') != '0'
+_PRODUCER_PLANES = os.environ.get('NNR_PRODUCER_PLANES', '1') != '0'   # A/B switch: h / gated-state planes written by their producers
 _CONTENT_FIRST = os.environ.get('NNR_CONTENT_FIRST', '1') != '0'     # A/B switch: issue order of the two BPTT recurrences
 concurrent = True
 _side_streams = {}
@@ -352,7 +353,7 @@ def _cne_prepare(ids, mask_u8, N, L, domains):
     return m
 
 
-def _cne_recurrent(P, x, m, N, E, Hd, training, p_drop, seed):
+def _cne_recurrent(P, x, m, N, E, Hd, training, p_drop, seed, want_h_planes=False):
     """embedding gather + dropout, input projection, bidirectional LSTM of one modality (newsEncoders.py:117-127)"""
     dev = m.ids.device
     ids, L, cap = m.ids, m.L, m.cap
@@ -378,12 +379,17 @@ def _cne_recurrent(P, x, m, N, E, Hd, training, p_drop, seed):
     m.h = _empty((cap, 2 * Hd), dev)
     m.c_stash = _empty((cap, 2 * Hd), dev)
     m.c_n = _empty((N, 2 * Hd), dev)
-    ops.lstm_fwd(m.gates, m.w_hh, m.len, m.off, m.order, N, L, Hd, m.h, m.c_stash, m.c_n)
+    m.h_pl = None
+    if want_h_planes and _PRODUCER_PLANES and ops.lstm_fwd_planes_supported(Hd):
+        # h feeds GEMMs (selective gate, two weight gradients): the recurrence writes its operand planes next to the fp32 states
+        m.h_pl = ops.lstm_fwd_planes(m.gates, m.w_hh, m.len, m.off, m.order, N, L, Hd, m.h, m.c_stash, m.c_n, cap)
+    else:
+        ops.lstm_fwd(m.gates, m.w_hh, m.len, m.off, m.order, N, L, Hd, m.h, m.c_stash, m.c_n)
     return m
 
 
 def _cne_modality_forward(P, x, ids, mask_u8, N, L, E, Hd, training, p_drop, seed, domains):
-    return _cne_recurrent(P, x, _cne_prepare(ids, mask_u8, N, L, domains), N, E, Hd, training, p_drop, seed)
+    return _cne_recurrent(P, x, _cne_prepare(ids, mask_u8, N, L, domains), N, E, Hd, training, p_drop, seed, True)
 
 
 def _cne_gate_self(P, x, m, m_other_cn, partner, N, Hd, A, gate=True):
@@ -397,13 +403,18 @@ def _cne_gate_self(P, x, m, m_other_cn, partner, N, Hd, A, gate=True):
         m.cm_sel_pl = _shared_split(m.cm_sel, N, D2)
         m.mproj = linear(m.cm_sel, P[x + '_M.weight'], N, None, P[x + '_M.bias'], x_planes=m.cm_sel_pl)   # [N, 2H]
         m.g = _empty((m.cap, D2), dev)
-        m.h_pl = split_tokens(m.h, m.cap, D2, m.ntok)
+        if m.h_pl is None:
+            m.h_pl = split_tokens(m.h, m.cap, D2, m.ntok)
+        # the gated states feed the attention projection and its weight gradient: the epilogue also writes their planes
+        m.hg_pl = ops.planes_empty(m.cap, D2, dev) if (_PRODUCER_PLANES and D2 % 8 == 0) else None
         m.hg = linear(m.h, P[x + '_H.weight'], m.cap, m.ntok, None, EPI_GATE, rowbias=m.mproj, ldrowbias=D2,
-                      rowmap=m.tok_row, aux=m.h, ldaux=D2, aux_out=m.g, ldaux_out=D2, x_planes=m.h_pl)
+                      rowmap=m.tok_row, aux=m.h, ldaux=D2, aux_out=m.g, ldaux_out=D2, x_planes=m.h_pl, c_planes=m.hg_pl)
     else:
         m.hg = m.h
+        m.hg_pl = m.h_pl
     sa = x + '_self_attention.'
-    m.hg_pl = split_tokens(m.hg, m.cap, D2, m.ntok)
+    if m.hg_pl is None:
+        m.hg_pl = split_tokens(m.hg, m.cap, D2, m.ntok)
     m.u = linear(m.hg, P[sa + 'affine1.weight'], m.cap, m.ntok, P[sa + 'affine1.bias'], EPI_BIAS_TANH, x_planes=m.hg_pl)
     m.self_out = _empty((N, D2), dev)
     m.alpha_self = _empty((m.cap,), dev)
@@ -461,14 +472,14 @@ class CNEFunction(torch.autograd.Function):
         t, c = lanes.run(lambda: _cne_prepare(title_text.view(N, T), title_mask.reshape(N, T), N, T, domains),
                          lambda: _cne_prepare(content_text.view(N, Lc), content_mask.reshape(N, Lc), N, Lc, domains))
         lanes.fork()
-        lanes.on_side(_cne_recurrent, P, 'title', t, N, E, Hd, training, p, seeds[0])
+        lanes.on_side(_cne_recurrent, P, 'title', t, N, E, Hd, training, p, seeds[0], True)
         # pairing by sort rank inside each domain (newsEncoders.py:124-129, SURVEY finding 2): title row r of a call is
         # gated with the content memory of the news at the same sorted rank.  (A handful of [N]-sized kernels: issued here
         # they run under the title branch's gather / GEMM instead of between the recurrences and the gates.)
         partner_t = torch.cat([cs.index_select(0, td) for cs, td in zip(c.sorted_idx, t.desorted_idx)])
         partner_c = torch.cat([ts.index_select(0, cd) for ts, cd in zip(t.sorted_idx, c.desorted_idx)])
         t.partner, c.partner = partner_t, partner_c
-        _cne_recurrent(P, 'content', c, N, E, Hd, training, p, seeds[1])
+        _cne_recurrent(P, 'content', c, N, E, Hd, training, p, seeds[1], True)
         lanes.join()
         lanes.run(lambda: _cne_gate_self(P, 'title', t, c.c_n, partner_t, N, Hd, A, gate),
                   lambda: _cne_gate_self(P, 'content', c, t.c_n, partner_c, N, Hd, A, gate))

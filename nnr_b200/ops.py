@@ -113,6 +113,15 @@ def default_algo():
     return int(lib.nnr_gemm_default_algo())
 
 
+def planes_empty(rows, cols, device):
+    """uninitialised operand planes for a producer kernel to fill (bf16 tensor-core algos), or None"""
+    algo = default_algo()
+    if algo not in (ALGO_BF16, ALGO_BF16X3):
+        return None
+    buf = torch.empty(int(lib.nnr_tc_split_bytes(rows, cols, algo)), dtype=torch.uint8, device=device)
+    return Planes(buf, rows, cols, int(lib.nnr_tc_split_pitch(cols, algo)), 2)
+
+
 def tc_split(x, rows, cols, ld, r_dev=None, colsum_out=None, accumulate=False):
     """pre-split a row-major [rows, cols] fp32 matrix once so several GEMMs can share the planes; returns None
     when the exact-fp32 backend is selected (NNR_GEMM_ALGO=simt).  With ``colsum_out`` the column sums of the valid
@@ -184,7 +193,7 @@ class SplitMany:
 
 def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, transA, transB, epilogue=EPI_NONE, accumulate=False, bias=None,
          aux=None, ldaux=0, aux_out=None, ldaux_out=0, rowbias=None, ldrowbias=0, rowmap=None, m_dev=None,
-         k_dev=None, p_drop=0.0, seed=0, algo=ALGO_AUTO, a_planes=None, b_planes=None):
+         k_dev=None, p_drop=0.0, seed=0, algo=ALGO_AUTO, a_planes=None, b_planes=None, c_planes=None):
     a = GemmArgs()
     a.A, a.lda, a.transA = _p(A, _F32), lda, int(transA)
     a.B, a.ldb, a.transB = _p(B, _F32), ldb, int(transB)
@@ -201,6 +210,8 @@ def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, transA, transB, epilogue=EPI_NONE, 
         a.A_planes, a.a_planes_pitch, a.a_planes_rows = a_planes.ptr(), a_planes.pitch, a_planes.rows
     if b_planes is not None and algo == ALGO_AUTO:
         a.B_planes, a.b_planes_pitch, a.b_planes_rows = b_planes.ptr(), b_planes.pitch, b_planes.rows
+    if c_planes is not None:
+        a.C_planes, a.c_planes_pitch, a.c_planes_rows = c_planes.ptr(), c_planes.pitch, c_planes.rows
     nbytes = lib.nnr_gemm_workspace_bytes(C.byref(a))
     if nbytes:
         ws = workspace(nbytes, Cout.device, 'gemm')
@@ -236,6 +247,21 @@ def lstm_fwd(gx, w_hh, len_, off, order, N, L, H, h_out, c_stash, c_n):
     check(lib.nnr_lstm_fwd(_p(gx, _F32), _p(w_hh, _F32), _p(len_, _I32), _p(off, _I32), _p(order, _I32), N, L, H,
                            _p(h_out, _F32), _p(c_stash, _F32), _p(c_n, _F32), _tile_counters(gx.device).data_ptr(),
                            _stream()), 'nnr_lstm_fwd')
+
+
+def lstm_fwd_planes_supported(H):
+    return bool(lib.nnr_lstm_fwd_planes_supported(H, default_algo()))
+
+
+def lstm_fwd_planes(gx, w_hh, len_, off, order, N, L, H, h_out, c_stash, c_n, cap):
+    """lstm_fwd whose h also leaves as GEMM operand planes (returned): no split pass over h"""
+    algo = default_algo()
+    nbytes = int(lib.nnr_tc_split_bytes(cap, 2 * H, algo))
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=gx.device)
+    check(lib.nnr_lstm_fwd_planes(_p(gx, _F32), _p(w_hh, _F32), _p(len_, _I32), _p(off, _I32), _p(order, _I32), N, L, H,
+                                  _p(h_out, _F32), _p(c_stash, _F32), _p(c_n, _F32), _tile_counters(gx.device).data_ptr(), cap, algo,
+                                  buf.data_ptr(), nbytes, _stream()), 'nnr_lstm_fwd_planes')
+    return Planes(buf, cap, 2 * H, int(lib.nnr_tc_split_pitch(2 * H, algo)), 2)
 
 
 def lstm_bwd(gates, c_stash, w_hh, len_, off, order, N, L, H, dh, dcn):

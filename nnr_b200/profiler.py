@@ -33,8 +33,8 @@ def _tc_class(M, N, K, transA, transB, m_dev, k_dev):
         return False
     return True
 
-_TIMED = ['seq_prepare', 'embed_gather_fwd', 'embed_gather_planes_fwd', 'embed_gather_bwd', 'gemm', 'colsum', 'segment_colsum', 'lstm_fwd',
-          'lstm_bwd', 'lstm_bwd_planes', 'lstm_shift_h', 'lstm_shift_h_planes', 'gate_bwd_pre', 'gate_bwd_planes', 'attn_pool_fwd', 'attn_pool_bwd', 'news_fuse_fwd', 'news_fuse_bwd',
+_TIMED = ['seq_prepare', 'embed_gather_fwd', 'embed_gather_planes_fwd', 'embed_gather_bwd', 'gemm', 'colsum', 'segment_colsum', 'lstm_fwd', 'lstm_fwd_planes',
+          'lstm_bwd', 'lstm_bwd_planes', 'lstm_shift_h', 'lstm_shift_h_planes', 'gate_bwd_pre', 'gate_bwd_planes', 'attn_pool_fwd', 'attn_pool_bwd', 'news_fuse_fwd', 'news_fuse_bwd', 'news_fuse_split_bwd', 'news_fuse_tables_bwd',
           'graph_to_csr', 'gcn_aggregate', 'cluster_intra_fwd', 'cluster_intra_bwd', 'rowdot_fwd', 'rowdot_bwd',
           'dropout', 'flat_clip_adam', 'sue_graph_build', 'relu_bwd_split_colsum']
 
@@ -56,8 +56,8 @@ class Capture:
             tc = _tc_class(M, N, K, args[9], args[10], m_dev, k_dev)
             return lambda: (2.0 * (min(M, _dev_int(m_dev)) if m_dev is not None else M) * N *
                             (min(K, _dev_int(k_dev)) if k_dev is not None else K), None, tc)
-        if name in ('lstm_fwd', 'lstm_bwd', 'lstm_bwd_planes'):
-            if name == 'lstm_fwd':
+        if name in ('lstm_fwd', 'lstm_fwd_planes', 'lstm_bwd', 'lstm_bwd_planes'):
+            if name in ('lstm_fwd', 'lstm_fwd_planes'):
                 off, N, H = args[3], args[5], args[7]
             else:
                 off, N, H = args[4], args[6], args[8]
@@ -107,7 +107,7 @@ class Capture:
             if name == 'gemm':
                 label = 'gemm[%dx%dx%d %s%s e%d]' % (args[3], args[4], args[5], 'T' if args[9] else 'N', 'T' if args[10] else 'N',
                                                    kw.get('epilogue', args[11] if len(args) > 11 else 0))
-            alias = {'embed_gather_planes_fwd': 'embed_gather_fwd', 'lstm_bwd_planes': 'lstm_bwd', 'lstm_shift_h_planes': 'lstm_shift_h',
+            alias = {'embed_gather_planes_fwd': 'embed_gather_fwd', 'lstm_bwd_planes': 'lstm_bwd', 'lstm_fwd_planes': 'lstm_fwd', 'lstm_shift_h_planes': 'lstm_shift_h',
                      'gate_bwd_planes': 'gate_bwd_pre'}   # same op, planes output
             self.records.append((alias.get(name, name), e0, e1, work, label))
             return r

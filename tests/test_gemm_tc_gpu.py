@@ -202,3 +202,34 @@ def test_split_with_column_sums(cuda, cols):
     out3 = torch.empty_like(out)
     ops.tc_split(x, cap, cols, cols, r_dev, colsum_out=out3)
     assert torch.equal(out3, out)                                  # deterministic
+
+
+@pytest.mark.parametrize('M,m_valid', [(1000, 1000), (1000, 333), (40000, 38017)])     # the last one runs on CTA pairs
+def test_result_also_written_as_operand_planes(cuda, M, m_valid):
+    """nnr_gemm_args.C_planes: the epilogue writes the result a second time as bf16 hi / lo operand planes -- bit for bit what
+    nnr_tc_split of the fp32 result produces, rows [m, round_up(m, 64)) zeroed -- for the gate epilogue and the plain one"""
+    from nnr_b200 import ops
+    if ops.default_algo() not in (ops.ALGO_BF16, ops.ALGO_BF16X3):
+        pytest.skip('operand planes of the bf16 tensor-core algorithms')
+    g = torch.Generator().manual_seed(M + m_valid)
+    N, K, R = 400, 400, 57
+    A = torch.randn(M, K, generator=g).to(cuda)
+    W = (torch.randn(N, K, generator=g) / 20).to(cuda)
+    m_dev = torch.tensor([m_valid], dtype=torch.int32, device=cuda)
+    rowbias = torch.randn(R, N, generator=g).to(cuda)
+    rowmap = torch.randint(0, R, (M,), generator=g, dtype=torch.int32).to(cuda)
+    aux = torch.randn(M, N, generator=g).to(cuda)
+    for epi, kw in ((ops.EPI_NONE, {}),
+                    (ops.EPI_GATE, dict(rowbias=rowbias, ldrowbias=N, rowmap=rowmap, aux=aux, ldaux=N,
+                                        aux_out=torch.empty(M, N, device=cuda), ldaux_out=N))):
+        C0 = torch.zeros(M, N, device=cuda)
+        ops.gemm(A, W, C0, M, N, K, K, K, N, False, True, epi, m_dev=m_dev, **kw)
+        C1 = torch.zeros(M, N, device=cuda)
+        pl = ops.planes_empty(M, N, cuda)
+        pl.buf.fill_(0x7f)
+        ops.gemm(A, W, C1, M, N, K, K, K, N, False, True, epi, m_dev=m_dev, c_planes=pl, **kw)
+        assert torch.equal(C0, C1)
+        ref = ops.tc_split(C1, M, N, N, m_dev)
+        rows = min(M, (m_valid + 63) // 64 * 64)
+        npl = ref.buf.numel() // (M * ref.pitch * ref.esz)
+        assert torch.equal(ref.buf.view(npl, M, -1)[:, :rows], pl.buf.view(npl, M, -1)[:, :rows]), (M, m_valid, epi)

@@ -640,7 +640,7 @@ def test_engine_reaches_the_kernels_through_torch_ops(cuda):
     with Spy():
         loss = negative_log_softmax(m(*_args(batch, cuda)))
         loss.backward()
-    for name in ('seq_prepare', 'lstm_fwd', 'gcn_aggregate', 'graph_to_csr', 'cluster_intra_fwd', 'cluster_intra_bwd', 'rowdot_fwd',
+    for name in ('seq_prepare', 'gcn_aggregate', 'graph_to_csr', 'cluster_intra_fwd', 'cluster_intra_bwd', 'rowdot_fwd',
                  'rowdot_bwd', 'news_fuse_fwd', 'news_fuse_split_bwd', 'news_fuse_tables_bwd', 'embed_gather_bwd', 'dropout'):
         assert seen.get(name, 0) >= 1, (name, seen)
     with pytest.raises((RuntimeError, NotImplementedError)):

@@ -309,8 +309,20 @@ def test_lstm_forward_backward(cuda, N, L, full):
     h = torch.zeros(N * L, 2 * Hd, device=cuda)
     cst = torch.zeros(N * L, 2 * Hd, device=cuda)
     cn = torch.zeros(N, 2 * Hd, device=cuda)
+    gx_copy = gx_full.clone()
     ops.lstm_fwd(gx_full, w_hh, len_, off, order, N, L, Hd, h, cst, cn)
     torch.cuda.synchronize()
+    if ops.lstm_fwd_planes_supported(Hd):
+        # the variant whose h also leaves as GEMM operand planes: same states bit for bit, planes == nnr_tc_split(h) incl. the
+        # zeroed row tail
+        h2, cst2, cn2 = torch.zeros_like(h), torch.zeros_like(cst), torch.zeros_like(cn)
+        hpl = ops.lstm_fwd_planes(gx_copy, w_hh, len_, off, order, N, L, Hd, h2, cst2, cn2, N * L)
+        assert torch.equal(h2[:ntok], h[:ntok]) and torch.equal(cst2[:ntok], cst[:ntok]) and torch.equal(cn2, cn)
+        assert torch.equal(gx_copy[:ntok], gx_full[:ntok])
+        ref_pl = ops.tc_split(h, N * L, 2 * Hd, 2 * Hd, off[N:])
+        rows = min(N * L, (ntok + 63) // 64 * 64)
+        npl = ref_pl.buf.numel() // (N * L * ref_pl.pitch * ref_pl.esz)
+        assert torch.equal(ref_pl.buf.view(npl, N * L, -1)[:, :rows], hpl.buf.view(npl, N * L, -1)[:, :rows])
     h_ref_p = _packed(h_ref.detach(), lens)
     e_h = (h[:ntok].cpu().double() - h_ref_p).abs().max().item()
     e_c = (cn.cpu().double() - m_ref.detach()).abs().max().item()
