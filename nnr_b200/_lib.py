@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_lib', 'libnnr_b200.so')
+# NNR_B200_LIB: another build of the same library (the -DNNR_TC_PROF / -DNNR_LSTM_PROF instrumented ones of scripts/*_prof.py)
+LIB_PATH = os.environ.get('NNR_B200_LIB') or os.path.join(_HERE, '_lib', 'libnnr_b200.so')
 
 if not os.path.isfile(LIB_PATH):
     raise ImportError('nnr_b200: CUDA library not built (%s missing). Run nnr_b200/csrc/build.sh or '

@@ -178,6 +178,14 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t
   return d;
 }
 
+// optional in-kernel phase stamps (clock64 of CTA 0), compiled in with -DNNR_TC_PROF; read back with nnr_debug_tc_prof
+#ifdef NNR_TC_PROF
+__device__ unsigned long long g_tc_prof[16];
+#define TC_STAMP(i) { if (blockIdx.x == 0) g_tc_prof[i] = clock64(); }
+#else
+#define TC_STAMP(i) {}
+#endif
+
 struct TcParams {
   int M, N, K;                 // capacities
   const int32_t* m_dev;
@@ -266,7 +274,172 @@ __device__ __forceinline__ void epi_finish4(const EpiP& e, int m, int n, float* 
   st4(e.C + (size_t)m * e.ldc + n, cnt, v);
 }
 
-template <bool BF16, bool PAIR>
+// ---- fast epilogue of one output tile (one warp: 32 rows x its half of the tile's columns) -----------------------------
+// The epilogue kind is a template parameter and every per-tile quantity is hoisted, so a 16-column chunk is a short
+// straight-line sequence: the in-kernel stamps (scripts/gemm_phase_prof.py) of the run-time-switched version showed 1.1-1.4 us
+// per chunk (5.5 us per 128 x 128 tile, 13 us with the relu/residual/dropout epilogue) -- more than the main loop of every
+// K <= 400 token-level GEMM.  Three more things hide latency: the tcgen05.ld of chunk c+1 is issued as soon as chunk c has
+// left the registers, the streamed operands (aux / C / row bias) of chunk c+1 are loaded before chunk c is finished, and the
+// transpose tile is addressed in the shared state space (the generic form compiled to LD.E / ST.E).
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// the registers pass through the wait so that no use of them is scheduled above it
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
+struct EpiTile {                 // per-lane constants of one tile: the lane finishes rows row0 + 8 i, i = 0..3, in every chunk
+  uint32_t o_c[4], o_aux[4], o_ao[4], o_rb[4];   // element offsets of those rows (32-bit: host-checked)
+  uint32_t rvalid;               // bit i: row row0 + 8 i < M
+  int row0;
+};
+// the streamed operands of one chunk: aux (or the old C when accumulating without aux), the gate's row bias, the bias
+template <int EP>
+__device__ __forceinline__ void epi_load_in(const TcParams& p, const EpiTile& t, int n, bool has_bias, bool need_ax, bool acc_early,
+                                            float4 (&ax)[4], float4 (&rb)[4], float4& bb) {
+  bb = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { ax[i] = make_float4(0.f, 0.f, 0.f, 0.f); rb[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  if (n < p.N) {
+    if (has_bias) bb = __ldg(reinterpret_cast<const float4*>(p.epi.bias + n));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (t.rvalid & (1u << i)) {
+        if (need_ax) ax[i] = __ldg(reinterpret_cast<const float4*>(p.epi.aux + t.o_aux[i] + n));
+        else if (acc_early) ax[i] = *reinterpret_cast<const float4*>(p.epi.C + t.o_c[i] + n);
+        if (EP == NNR_EPI_GATE) rb[i] = __ldg(reinterpret_cast<const float4*>(p.epi.rowbias + t.o_rb[i] + n));
+      }
+    }
+  }
+}
+
+template <int EP>
+__device__ __forceinline__ void epi_tile_fast(const TcParams& p, const EpiTile& t, uint32_t lane_addr, bool has_k, int c_begin, int c_end,
+                                              int n0, uint32_t tile_s, int lane, int M, uint64_t drop_seed) {
+  const int tr = lane >> 2, tc4 = (lane & 3) * 4;
+  constexpr bool BIASED = EP == NNR_EPI_BIAS || EP == NNR_EPI_BIAS_TANH || EP == NNR_EPI_BIAS_RELU_RES;
+  const bool has_bias = BIASED && p.epi.bias != nullptr;
+  const bool need_ax = EP == NNR_EPI_GATE || EP == NNR_EPI_ADD_AUX || (EP == NNR_EPI_BIAS_RELU_RES && p.epi.aux != nullptr);
+  const bool accumulate = p.epi.accumulate != 0;
+  const bool acc_early = accumulate && !need_ax;      // one streamed operand per row lives in registers: aux, else the old C
+  const bool drop = EP == NNR_EPI_BIAS_RELU_RES && p.epi.p_drop > 0.f;
+  const uint32_t my_row = tile_s + (uint32_t)lane * TC_EPI_PITCH;
+  const uint32_t rd_row = tile_s + (uint32_t)tr * TC_EPI_PITCH + (uint32_t)tc4 * 4;
+
+  // the gate epilogue streams two operands per row (aux and the row bias: 32 registers per chunk): its inputs are loaded at
+  // the top of their own chunk (under the tcgen05.ld wait and the transpose) instead of one chunk ahead -- the second set
+  // would not fit the 168 registers a 320-thread CTA leaves per thread
+  constexpr bool AHEAD = EP != NNR_EPI_GATE;
+  uint32_t r[16];
+  float4 ax[4], rb[4], bb, axn[4], rbn[4], bbn;
+  if (has_k) tmem_ld16_issue(lane_addr + (uint32_t)c_begin, r);
+  if (AHEAD) epi_load_in<EP>(p, t, n0 + c_begin + tc4, has_bias, need_ax, acc_early, ax, rb, bb);
+  for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+    const bool more = c0 + 16 < c_end;
+    if (AHEAD) { if (more) epi_load_in<EP>(p, t, n0 + c0 + 16 + tc4, has_bias, need_ax, acc_early, axn, rbn, bbn); }
+    else epi_load_in<EP>(p, t, n0 + c0 + tc4, has_bias, need_ax, acc_early, ax, rb, bb);
+    if (has_k) tmem_ld16_wait(r);
+    else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = 0u;
+    }
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) sts128(my_row + qd * 16, r[4 * qd], r[4 * qd + 1], r[4 * qd + 2], r[4 * qd + 3]);
+    if (has_k && more) tmem_ld16_issue(lane_addr + (uint32_t)(c0 + 16), r);
+    __syncwarp();
+    float4 o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = lds128(rd_row + (uint32_t)(8 * i) * TC_EPI_PITCH);
+    const int n = n0 + c0 + tc4;
+    if (n < p.N) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (!(t.rvalid & (1u << i))) continue;
+        float4 v = make_float4(o[i].x + bb.x, o[i].y + bb.y, o[i].z + bb.z, o[i].w + bb.w);
+        if (EP == NNR_EPI_BIAS_TANH) {
+          v.x = tanh_fast(v.x); v.y = tanh_fast(v.y); v.z = tanh_fast(v.z); v.w = tanh_fast(v.w);
+        } else if (EP == NNR_EPI_BIAS_RELU_RES) {
+          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+          if (p.epi.aux_out) *reinterpret_cast<float4*>(p.epi.aux_out + t.o_ao[i] + n) = v;
+          if (need_ax) { v.x += ax[i].x; v.y += ax[i].y; v.z += ax[i].z; v.w += ax[i].w; }
+          if (drop) {
+            const uint64_t e0 = (uint64_t)(t.row0 + 8 * i) * (uint64_t)p.epi.N + n;
+            v.x *= dropout_scale(drop_seed, e0, p.epi.p_drop, p.epi.inv_keep);
+            v.y *= dropout_scale(drop_seed, e0 + 1, p.epi.p_drop, p.epi.inv_keep);
+            v.z *= dropout_scale(drop_seed, e0 + 2, p.epi.p_drop, p.epi.inv_keep);
+            v.w *= dropout_scale(drop_seed, e0 + 3, p.epi.p_drop, p.epi.inv_keep);
+          }
+        } else if (EP == NNR_EPI_GATE) {
+          v.x = sigmoid_fast(v.x + rb[i].x); v.y = sigmoid_fast(v.y + rb[i].y);
+          v.z = sigmoid_fast(v.z + rb[i].z); v.w = sigmoid_fast(v.w + rb[i].w);
+          if (p.epi.aux_out) *reinterpret_cast<float4*>(p.epi.aux_out + t.o_ao[i] + n) = v;
+          v.x *= ax[i].x; v.y *= ax[i].y; v.z *= ax[i].z; v.w *= ax[i].w;
+        } else if (EP == NNR_EPI_ADD_AUX) {
+          v.x += ax[i].x; v.y += ax[i].y; v.z += ax[i].z; v.w += ax[i].w;
+        }
+        if (acc_early) { v.x += ax[i].x; v.y += ax[i].y; v.z += ax[i].z; v.w += ax[i].w; }
+        else if (accumulate) {
+          const float4 cc = *reinterpret_cast<const float4*>(p.epi.C + t.o_c[i] + n);
+          v.x += cc.x; v.y += cc.y; v.z += cc.z; v.w += cc.w;
+        }
+        *reinterpret_cast<float4*>(p.epi.C + t.o_c[i] + n) = v;
+        if (p.c_planes) {           // same rounding as tc_split_store4: hi = rn(x), lo = rn(x - hi)
+          const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+          __nv_bfloat16* op = p.c_planes + (long long)(t.row0 + 8 * i) * p.c_pitch + n;
+          uint2 hv;
+          hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+          *reinterpret_cast<uint2*>(op) = hv;
+          if (p.c_lo) {
+            const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __low2float(h01), v.y - __high2float(h01));
+            const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __low2float(h23), v.w - __high2float(h23));
+            uint2 lv;
+            lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+            *reinterpret_cast<uint2*>(op + p.c_pstride) = lv;
+          }
+        }
+      }
+      if (p.c_planes) {             // rows [M, round_up(M, 64)) of the planes are the zero tail an MN-major consumer reads
+        const int mz = min(p.c_rows, (M + 63) & ~63);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int mm = t.row0 + 8 * i;
+          if (mm >= M && mm < mz) {
+            __nv_bfloat16* op = p.c_planes + (long long)mm * p.c_pitch + n;
+            *reinterpret_cast<uint2*>(op) = make_uint2(0u, 0u);
+            if (p.c_lo) *reinterpret_cast<uint2*>(op + p.c_pstride) = make_uint2(0u, 0u);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (AHEAD && more) {
+      bb = bbn;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { ax[i] = axn[i]; rb[i] = rbn[i]; }
+    }
+  }
+}
+
+// EPK >= 0: the epilogue kind, fixed at compile time (fast path: the host guarantees p.epi_fast, no split-K partials);
+// EPK = -1: the run-time-switched epilogue that takes any alignment, N tail and the split-K partials
+template <bool BF16, bool PAIR, int EPK>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b, TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -276,6 +449,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   if (p.m_dev) M = min(M, *p.m_dev);
   if (p.k_dev) K = min(K, *p.k_dev);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TC_STAMP(0)
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs of the pair)
   const int sched_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int sched_n = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -321,6 +495,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TC_STAMP(1)
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -375,6 +550,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           const int s = it % p.stages;
           mbar_wait(&full_bar[s], (it / p.stages) & 1);
           tc_fence_after();
+          if (it == 0) TC_STAMP(2)
           const uint32_t base = smem_u32(tiles + (size_t)s * stage_bytes);
           // MN-major fp32 operands use the BASE32B layout (type 1, 4-row atoms); everything else plain SW128
           const uint32_t a_lt = (p.a_mn && !BF16) ? 1u : 2u, a_sbo = (p.a_mn && !BF16) ? 512u : 1024u;
@@ -401,6 +577,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           }
           if (PAIR) tc_commit_pair(&empty_bar[s]); else tc_commit(&empty_bar[s]);     // frees the stage in both CTAs
         }
+        if (tl < 2) TC_STAMP(3 + tl)
         if (PAIR) tc_commit_pair(&tmem_full[buf]); else tc_commit(&tmem_full[buf]);
       }
     }
@@ -427,7 +604,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       // a lane finishes the same four rows in every chunk of the tile: their row-map entries (gate epilogue) are fetched
       // once, before the accumulator is waited for, so the row-bias loads of the chunks are not behind a dependent load
       int rmap[4] = {0, 0, 0, 0};
-      if (p.epi.epilogue == NNR_EPI_GATE && !p.partial) {
+      if ((EPK < 0 || EPK == NNR_EPI_GATE) && p.epi.epilogue == NNR_EPI_GATE && !p.partial) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int mm = m0 + q * 32 + tr + 8 * i;
@@ -436,7 +613,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
       // fast path: the four rows a lane finishes are the same in every chunk of the tile -> their element offsets once per
       // tile (32-bit: the host enables the path only when every operand has fewer than 2^32 elements)
-      const bool fast = p.epi_fast && !p.partial;
+      const bool fast = EPK >= 0;
       uint32_t o_c[4], o_aux[4], o_ao[4], o_rb[4];
       uint32_t rvalid = 0;
       if (fast) {
@@ -453,6 +630,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
       mbar_wait(&tmem_full[buf], (tl >> 1) & 1);
       tc_fence_after();
+      if (warp == 2 && lane == 0 && tl < 2) TC_STAMP(5 + 2 * tl)
+      if (EPK >= 0) {
+        EpiTile et;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { et.o_c[i] = o_c[i]; et.o_aux[i] = o_aux[i]; et.o_ao[i] = o_ao[i]; et.o_rb[i] = o_rb[i]; }
+        et.rvalid = rvalid; et.row0 = m0 + q * 32 + tr;
+        epi_tile_fast<(EPK >= 0 ? EPK : 0)>(p, et, lane_addr, kb1 > kb0, c_begin, c_end, n0, smem_u32(my_tile), lane, M, drop_seed);
+      } else
       for (int c0 = c_begin; c0 < c_end; c0 += 16) {
         float v[16];
         if (kb1 > kb0) tmem_ld16(lane_addr + (uint32_t)c0, v);
@@ -472,87 +657,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           const float4 x = *reinterpret_cast<const float4*>(my_tile + (tr + 8 * i) * TC_EPI_PITCH + tc4 * 4);
           o[i][0] = x.x; o[i][1] = x.y; o[i][2] = x.z; o[i][3] = x.w;
         }
-        if (fast) {
-          // straight-line path: 16-byte accesses at row offsets hoisted out of the chunk loop; every load of the lane's four
-          // rows is issued before the first use (measured: two rows at a time is 30 % slower on the add-aux epilogue).  One
-          // streamed operand per row lives in registers (aux, or C when accumulating without aux) plus the row bias of the
-          // gate; the rare aux + accumulate combination reads C late
-          if (n < p.N) {
-            const int ep = p.epi.epilogue;
-            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.epi.bias && (ep == NNR_EPI_BIAS || ep == NNR_EPI_BIAS_TANH || ep == NNR_EPI_BIAS_RELU_RES))
-              bb = __ldg(reinterpret_cast<const float4*>(p.epi.bias + n));
-            const bool need_ax = (ep == NNR_EPI_GATE) || (ep == NNR_EPI_ADD_AUX) || (ep == NNR_EPI_BIAS_RELU_RES && p.epi.aux);
-            const bool acc_early = p.epi.accumulate && !need_ax;
-            float4 ax[4], rb[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (rvalid & (1u << i)) {
-                if (need_ax) ax[i] = __ldg(reinterpret_cast<const float4*>(p.epi.aux + o_aux[i] + n));
-                else if (acc_early) ax[i] = *reinterpret_cast<const float4*>(p.epi.C + o_c[i] + n);
-                if (ep == NNR_EPI_GATE) rb[i] = __ldg(reinterpret_cast<const float4*>(p.epi.rowbias + o_rb[i] + n));
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (!(rvalid & (1u << i))) continue;
-              float4 v = make_float4(o[i][0] + bb.x, o[i][1] + bb.y, o[i][2] + bb.z, o[i][3] + bb.w);
-              if (ep == NNR_EPI_BIAS_TANH) {
-                v.x = tanh_fast(v.x); v.y = tanh_fast(v.y); v.z = tanh_fast(v.z); v.w = tanh_fast(v.w);
-              } else if (ep == NNR_EPI_BIAS_RELU_RES) {
-                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                if (p.epi.aux_out) *reinterpret_cast<float4*>(p.epi.aux_out + o_ao[i] + n) = v;
-                if (p.epi.aux) { v.x += ax[i].x; v.y += ax[i].y; v.z += ax[i].z; v.w += ax[i].w; }
-                if (p.epi.p_drop > 0.f) {
-                  const uint64_t e0 = (uint64_t)(m0 + q * 32 + tr + 8 * i) * (uint64_t)p.epi.N + n;
-                  v.x *= dropout_scale(drop_seed, e0, p.epi.p_drop, p.epi.inv_keep);
-                  v.y *= dropout_scale(drop_seed, e0 + 1, p.epi.p_drop, p.epi.inv_keep);
-                  v.z *= dropout_scale(drop_seed, e0 + 2, p.epi.p_drop, p.epi.inv_keep);
-                  v.w *= dropout_scale(drop_seed, e0 + 3, p.epi.p_drop, p.epi.inv_keep);
-                }
-              } else if (ep == NNR_EPI_GATE) {
-                v.x = sigmoid_fast(v.x + rb[i].x); v.y = sigmoid_fast(v.y + rb[i].y);
-                v.z = sigmoid_fast(v.z + rb[i].z); v.w = sigmoid_fast(v.w + rb[i].w);
-                if (p.epi.aux_out) *reinterpret_cast<float4*>(p.epi.aux_out + o_ao[i] + n) = v;
-                v.x *= ax[i].x; v.y *= ax[i].y; v.z *= ax[i].z; v.w *= ax[i].w;
-              } else if (ep == NNR_EPI_ADD_AUX) {
-                v.x += ax[i].x; v.y += ax[i].y; v.z += ax[i].z; v.w += ax[i].w;
-              }
-              if (acc_early) { v.x += ax[i].x; v.y += ax[i].y; v.z += ax[i].z; v.w += ax[i].w; }
-              else if (p.epi.accumulate) {
-                const float4 cc = *reinterpret_cast<const float4*>(p.epi.C + o_c[i] + n);
-                v.x += cc.x; v.y += cc.y; v.z += cc.z; v.w += cc.w;
-              }
-              *reinterpret_cast<float4*>(p.epi.C + o_c[i] + n) = v;
-              if (p.c_planes) {           // same rounding as tc_split_store4: hi = rn(x), lo = rn(x - hi)
-                const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
-                __nv_bfloat16* o = p.c_planes + (long long)(m0 + q * 32 + tr + 8 * i) * p.c_pitch + n;
-                uint2 hv;
-                hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-                *reinterpret_cast<uint2*>(o) = hv;
-                if (p.c_lo) {
-                  const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __low2float(h01), v.y - __high2float(h01));
-                  const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __low2float(h23), v.w - __high2float(h23));
-                  uint2 lv;
-                  lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-                  *reinterpret_cast<uint2*>(o + p.c_pstride) = lv;
-                }
-              }
-            }
-            if (p.c_planes) {             // rows [M, round_up(M, 64)) of the planes are the zero tail an MN-major consumer reads
-              const int mz = min(p.c_rows, (M + 63) & ~63);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int mm = m0 + q * 32 + tr + 8 * i;
-                if (mm >= M && mm < mz) {
-                  __nv_bfloat16* o = p.c_planes + (long long)mm * p.c_pitch + n;
-                  *reinterpret_cast<uint2*>(o) = make_uint2(0u, 0u);
-                  if (p.c_lo) *reinterpret_cast<uint2*>(o + p.c_pstride) = make_uint2(0u, 0u);
-                }
-              }
-            }
-          }
-        } else if (cnt > 0) {
+        if (cnt > 0) {
           if (p.partial) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -580,6 +685,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
       tc_fence_before();
       __syncwarp();
+      if (warp == 2 && lane == 0 && tl < 2) TC_STAMP(6 + 2 * tl)
       if (lane == 0) {
         if (PAIR && rank != 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[buf]), 0));   // the leader's MMA warp waits for both CTAs
         else mbar_arrive(&tmem_empty[buf]);
@@ -588,6 +694,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TC_STAMP(9)
   if (PAIR) cluster_sync_all();         // no CTA leaves while its peer may still read its operands / signal its barriers
   if (warp == 1) {
     if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
@@ -929,6 +1036,18 @@ static int pair_mode() {
   if (v < 0) { const char* e = getenv("NNR_TC_PAIR"); v = e ? atoi(e) : 1; }
   return v;
 }
+// Row count from which 256-row pair tiles are considered, and the least number of pair tiles a mid-size problem must have
+// (below it the 128-row grid fills more SMs).  Token-level GEMMs (M >= 2*128*148) always qualify.
+static int pair_min_m() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NNR_TC_PAIR_MIN_M"); v = e ? atoi(e) : 2 * TC_BM * 148; }
+  return v;
+}
+static int pair_min_tiles() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NNR_TC_PAIR_MIN_TILES"); v = e ? atoi(e) : 48; }
+  return v;
+}
 static int pick_block_n_pair(int N, int step, int nplanes) {
   int best = 0;
   double best_cost = 1e30;
@@ -964,8 +1083,12 @@ static TcPlan make_plan(const nnr_gemm_args* a, int mode) {
   pl.block_n = pick_block_n(a->N, pl.b_mn ? pl.kelem : 16, pl.nplanes);
   // large row counts (token-level GEMMs) are bound by L2->SM operand delivery: use 256-row tiles on CTA pairs
   pl.pair = 0;
-  if (pair_mode() && a->M >= 2 * TC_BM * 148 && !(a->transA) && a->k_dev == nullptr) {
+  if (pair_mode() && a->M >= pair_min_m() && !(a->transA) && a->k_dev == nullptr) {
     int bnp = pick_block_n_pair(a->N, pl.b_mn ? 2 * pl.kelem : 16, pl.nplanes);
+    if (bnp && a->M < 2 * TC_BM * 148) {   // mid-size problem: only when the pair grid still fills the machine
+      long ptiles = (long)((a->M + 2 * TC_BM - 1) / (2 * TC_BM)) * ((a->N + bnp - 1) / bnp);
+      if (ptiles < pair_min_tiles()) bnp = 0;
+    }
     if (bnp) { pl.pair = 1; pl.block_n = bnp; }
   }
   long tiles = (long)((a->M + TC_BM - 1) / TC_BM) * ((a->N + pl.block_n - 1) / pl.block_n);
@@ -1047,6 +1170,24 @@ static int split_operand(const float* X, int64_t ld, int R, int C, int Cp, const
   return 0;
 }
 
+template <bool BF16, bool PAIR>
+static const void* tc_kernel_ptr2(int epk) {
+  if (!BF16) return (const void*)gemm_tc_kernel<BF16, PAIR, -1>;
+  switch (epk) {
+    case NNR_EPI_NONE: return (const void*)gemm_tc_kernel<BF16, PAIR, BF16 ? NNR_EPI_NONE : -1>;
+    case NNR_EPI_BIAS: return (const void*)gemm_tc_kernel<BF16, PAIR, BF16 ? NNR_EPI_BIAS : -1>;
+    case NNR_EPI_BIAS_TANH: return (const void*)gemm_tc_kernel<BF16, PAIR, BF16 ? NNR_EPI_BIAS_TANH : -1>;
+    case NNR_EPI_BIAS_RELU_RES: return (const void*)gemm_tc_kernel<BF16, PAIR, BF16 ? NNR_EPI_BIAS_RELU_RES : -1>;
+    case NNR_EPI_GATE: return (const void*)gemm_tc_kernel<BF16, PAIR, BF16 ? NNR_EPI_GATE : -1>;
+    case NNR_EPI_ADD_AUX: return (const void*)gemm_tc_kernel<BF16, PAIR, BF16 ? NNR_EPI_ADD_AUX : -1>;
+    default: return (const void*)gemm_tc_kernel<BF16, PAIR, -1>;
+  }
+}
+template <bool BF16>
+static const void* tc_kernel_ptr(bool pair, int epk) {
+  return pair ? tc_kernel_ptr2<BF16, true>(epk) : tc_kernel_ptr2<BF16, false>(epk);
+}
+
 template <int MODE>
 static int run_tc(const nnr_gemm_args* a, cudaStream_t st) {
   constexpr bool BF16 = MODE != 0;
@@ -1117,39 +1258,42 @@ static int run_tc(const nnr_gemm_args* a, cudaStream_t st) {
     p.c_rows = (int)a->c_planes_rows;
   }
   // per-device caches: the dynamic shared-memory attribute is a property of (function, device), and so is the SM count
-  static bool attr_set[16][2][2] = {};
+  static bool attr_set[16][2][2][8] = {};
   static int num_sms_tab[16] = {};
   int dev = 0;
   NNR_CUDA(cudaGetDevice(&dev));
   dev &= 15;
-  if (!attr_set[dev][BF16 ? 1 : 0][pl.pair]) {
-    if (pl.pair) NNR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    else NNR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set[dev][BF16 ? 1 : 0][pl.pair] = true;
+  // the epilogue kind is a template parameter of the kernel on the fast path (bf16 operand planes only; the fp32-plane
+  // kernels keep the run-time-switched epilogue)
+  const int epk = (BF16 && p.epi_fast && !pl.split_k) ? a->epilogue : -1;
+  const void* kernel = tc_kernel_ptr<BF16>(pl.pair != 0, epk);
+  if (!attr_set[dev][BF16 ? 1 : 0][pl.pair][epk + 1]) {
+    NNR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[dev][BF16 ? 1 : 0][pl.pair][epk + 1] = true;
   }
   if (num_sms_tab[dev] == 0) NNR_CUDA(cudaDeviceGetAttribute(&num_sms_tab[dev], cudaDevAttrMultiProcessorCount, dev));
   const int num_sms = num_sms_tab[dev];
   void* ph = nnr_prof_begin(0, -1.0, st);     // flops are filled in by the caller-side profiler (needs m_dev/k_dev)
-  if (pl.pair) {
-    long cap_tiles = (long)((a->M + 2 * TC_BM - 1) / (2 * TC_BM)) * ((a->N + pl.block_n - 1) / pl.block_n);
-    long pairs = cap_tiles < num_sms / 2 ? cap_tiles : num_sms / 2;
+  {
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cfg.gridDim = dim3((unsigned)(2 * pairs)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+    if (pl.pair) {
+      long cap_tiles = (long)((a->M + 2 * TC_BM - 1) / (2 * TC_BM)) * ((a->N + pl.block_n - 1) / pl.block_n);
+      long pairs = cap_tiles < num_sms / 2 ? cap_tiles : num_sms / 2;
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      cfg.gridDim = dim3((unsigned)(2 * pairs));
+    } else {
+      long cap_tiles = (long)((a->M + TC_BM - 1) / TC_BM) * ((a->N + pl.block_n - 1) / pl.block_n) * pl.max_splits;
+      cfg.gridDim = dim3((unsigned)(cap_tiles < num_sms ? cap_tiles : num_sms));
+    }
+    cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
     void* kargs[] = {(void*)&map_a, (void*)&map_b, (void*)&p};
-    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)gemm_tc_kernel<BF16, true>, kargs);
+    cudaError_t e = cudaLaunchKernelExC(&cfg, kernel, kargs);
     nnr_count_launch(1);
-    if (e != cudaSuccess) { nnr_set_error("gemm_tc_kernel(pair): launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+    if (e != cudaSuccess) { nnr_set_error("gemm_tc_kernel(%s): launch failed: %s", pl.pair ? "pair" : "single", cudaGetErrorString(e)); return (int)e; }
     nnr_prof_end(ph, st);
-  } else {
-    long cap_tiles = (long)((a->M + TC_BM - 1) / TC_BM) * ((a->N + pl.block_n - 1) / pl.block_n) * pl.max_splits;
-    int grid = (int)(cap_tiles < num_sms ? cap_tiles : num_sms);
-    gemm_tc_kernel<BF16, false><<<grid, TC_THREADS, pl.smem, st>>>(map_a, map_b, p);
-    nnr_prof_end(ph, st);
-    NNR_LAUNCH_CHECK("gemm_tc_kernel");
   }
   if (pl.split_k) {
     size_t tot = (size_t)a->M * a->N;
@@ -1489,4 +1633,16 @@ extern "C" int nnr_tc_split_many(const nnr_split_desc* descs, int n, int algo, v
   nnr_prof_end(ph, st);
   NNR_LAUNCH_CHECK("tc_split_many_kernel");
   return 0;
+}
+
+// phase stamps of the last gemm_tc_kernel launch (CTA 0; library built with -DNNR_TC_PROF), 16 clock64 values; returns 0 when
+// the library was built without them
+extern "C" int nnr_debug_tc_prof(unsigned long long* out) {
+#ifdef NNR_TC_PROF
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, g_tc_prof, sizeof(unsigned long long) * 16) == cudaSuccess ? 1 : 0;
+#else
+  (void)out;
+  return 0;
+#endif
 }

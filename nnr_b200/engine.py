@@ -71,6 +71,7 @@ def _empty(shape, dev, dtype=torch.float32):
 _LANES = os.environ.get('NNR_LANES', '1') != '0'
 _PRODUCER_PLANES = os.environ.get('NNR_PRODUCER_PLANES', '1') != '0'   # A/B switch: h / gated-state planes written by their producers
 _CONTENT_FIRST = os.environ.get('NNR_CONTENT_FIRST', '1') != '0'     # A/B switch: issue order of the two BPTT recurrences
+_FWD_CONTENT_FIRST = os.environ.get('NNR_FWD_CONTENT_FIRST', '1') != '0'   # A/B switch: issue order of the two forward recurrences
 concurrent = True
 _side_streams = {}
 
@@ -89,7 +90,9 @@ class Lanes:
             self.main = torch.cuda.current_stream(idx)
             self.sides = _side_streams.get(idx)
             if self.sides is None:
-                self.sides = _side_streams[idx] = [torch.cuda.Stream(device=idx) for _ in range(self.NSIDE)]
+                # NNR_SIDE_PRIORITIES (A/B switch): stream priorities of lanes 1, 2 (0 = lowest ... -5); a captured step keeps them
+                prios = [int(v) for v in os.environ.get('NNR_SIDE_PRIORITIES', '0,0').split(',')]
+                self.sides = _side_streams[idx] = [torch.cuda.Stream(device=idx, priority=prios[i]) for i in range(self.NSIDE)]
             if any(s == self.main for s in self.sides):      # nested use from a side lane itself: stay serial
                 self.on = False
 
@@ -472,6 +475,9 @@ class CNEFunction(torch.autograd.Function):
         t, c = lanes.run(lambda: _cne_prepare(title_text.view(N, T), title_mask.reshape(N, T), N, T, domains),
                          lambda: _cne_prepare(content_text.view(N, Lc), content_mask.reshape(N, Lc), N, Lc, domains))
         lanes.fork()
+        if _FWD_CONTENT_FIRST:
+            # the content branch (gather, input projection, 128-step recurrence) is the critical path of the forward stage
+            _cne_recurrent(P, 'content', c, N, E, Hd, training, p, seeds[1], True)
         lanes.on_side(_cne_recurrent, P, 'title', t, N, E, Hd, training, p, seeds[0], True)
         # pairing by sort rank inside each domain (newsEncoders.py:124-129, SURVEY finding 2): title row r of a call is
         # gated with the content memory of the news at the same sorted rank.  (A handful of [N]-sized kernels: issued here
@@ -479,7 +485,8 @@ class CNEFunction(torch.autograd.Function):
         partner_t = torch.cat([cs.index_select(0, td) for cs, td in zip(c.sorted_idx, t.desorted_idx)])
         partner_c = torch.cat([ts.index_select(0, cd) for ts, cd in zip(t.sorted_idx, c.desorted_idx)])
         t.partner, c.partner = partner_t, partner_c
-        _cne_recurrent(P, 'content', c, N, E, Hd, training, p, seeds[1], True)
+        if not _FWD_CONTENT_FIRST:
+            _cne_recurrent(P, 'content', c, N, E, Hd, training, p, seeds[1], True)
         lanes.join()
         lanes.run(lambda: _cne_gate_self(P, 'title', t, c.c_n, partner_t, N, Hd, A, gate),
                   lambda: _cne_gate_self(P, 'content', c, t.c_n, partner_c, N, Hd, A, gate))
