@@ -8,7 +8,7 @@
 //   NNR_GEMM_TC_TF32X3            tf32 hi / lo planes, tcgen05.mma kind::tf32 -- 4e-6 (K=400) ... 1.1e-5 (K=1600)
 //   NNR_GEMM_TC_BF16              one bf16 plane (the reduced-precision variant)
 // What remains of the error comes from the tensor core truncating when it adds into the TMEM accumulator, so long
-// contractions (wgrad: K = tokens) are cut into chains of <= 1024 k whose partial sums are combined in a fixed order
+// contractions (wgrad: K = tokens) are cut into chains of <= 2048 k whose partial sums are combined in a fixed order
 // in exact fp32.
 //
 // Structure
@@ -45,7 +45,7 @@ extern "C" int nnr_gemm_default_algo(void);
 #define TC_EPI_PITCH 80       // bytes per row of an epilogue warp's 32 x 16 fp32 transpose tile (conflict-free 16 B accesses)
 #define TC_EPI_SCRATCH (8 * 32 * TC_EPI_PITCH)
 #define TC_SMEM_BUDGET (205 * 1024)   // pipeline stages; + TC_EPI_SCRATCH + alignment slack + barriers <= 227 KB
-#define TC_CHAIN_K 1024      // max contraction length accumulated in TMEM before an fp32 combine (split-K GEMMs)
+#define TC_CHAIN_K 2048      // max contraction length accumulated in TMEM before an fp32 combine (split-K GEMMs); 1024 and 2048 give the same gradient error tables (profiles/r2_parity_config2.md), 2048 halves the partial traffic
 
 // ------------------------------------------------------------------------------------------------
 // device helpers (raw PTX)
@@ -330,15 +330,18 @@ __device__ __forceinline__ void epi_load_in(const TcParams& p, const EpiTile& t,
   }
 }
 
+#define TC_EPK_PARTIAL 6      // kernel-template value: the tile is one split-K partial (plain store into the partial slices)
 template <int EP>
 __device__ __forceinline__ void epi_tile_fast(const TcParams& p, const EpiTile& t, uint32_t lane_addr, bool has_k, int c_begin, int c_end,
-                                              int n0, uint32_t tile_s, int lane, int M, uint64_t drop_seed) {
+                                              int n0, uint32_t tile_s, int lane, int M, uint64_t drop_seed, float* __restrict__ Cout) {
   const int tr = lane >> 2, tc4 = (lane & 3) * 4;
+  constexpr bool PARTIAL = EP == TC_EPK_PARTIAL;
   constexpr bool BIASED = EP == NNR_EPI_BIAS || EP == NNR_EPI_BIAS_TANH || EP == NNR_EPI_BIAS_RELU_RES;
   const bool has_bias = BIASED && p.epi.bias != nullptr;
   const bool need_ax = EP == NNR_EPI_GATE || EP == NNR_EPI_ADD_AUX || (EP == NNR_EPI_BIAS_RELU_RES && p.epi.aux != nullptr);
-  const bool accumulate = p.epi.accumulate != 0;
+  const bool accumulate = !PARTIAL && p.epi.accumulate != 0;
   const bool acc_early = accumulate && !need_ax;      // one streamed operand per row lives in registers: aux, else the old C
+  const bool planes = !PARTIAL && p.c_planes != nullptr;
   const bool drop = EP == NNR_EPI_BIAS_RELU_RES && p.epi.p_drop > 0.f;
   const uint32_t my_row = tile_s + (uint32_t)lane * TC_EPI_PITCH;
   const uint32_t rd_row = tile_s + (uint32_t)tr * TC_EPI_PITCH + (uint32_t)tc4 * 4;
@@ -396,11 +399,11 @@ __device__ __forceinline__ void epi_tile_fast(const TcParams& p, const EpiTile& 
         }
         if (acc_early) { v.x += ax[i].x; v.y += ax[i].y; v.z += ax[i].z; v.w += ax[i].w; }
         else if (accumulate) {
-          const float4 cc = *reinterpret_cast<const float4*>(p.epi.C + t.o_c[i] + n);
+          const float4 cc = *reinterpret_cast<const float4*>(Cout + t.o_c[i] + n);
           v.x += cc.x; v.y += cc.y; v.z += cc.z; v.w += cc.w;
         }
-        *reinterpret_cast<float4*>(p.epi.C + t.o_c[i] + n) = v;
-        if (p.c_planes) {           // same rounding as tc_split_store4: hi = rn(x), lo = rn(x - hi)
+        *reinterpret_cast<float4*>(Cout + t.o_c[i] + n) = v;
+        if (planes) {               // same rounding as tc_split_store4: hi = rn(x), lo = rn(x - hi)
           const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
           __nv_bfloat16* op = p.c_planes + (long long)(t.row0 + 8 * i) * p.c_pitch + n;
           uint2 hv;
@@ -415,7 +418,7 @@ __device__ __forceinline__ void epi_tile_fast(const TcParams& p, const EpiTile& 
           }
         }
       }
-      if (p.c_planes) {             // rows [M, round_up(M, 64)) of the planes are the zero tail an MN-major consumer reads
+      if (planes) {                 // rows [M, round_up(M, 64)) of the planes are the zero tail an MN-major consumer reads
         const int mz = min(p.c_rows, (M + 63) & ~63);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -622,7 +625,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           const int mm = m0 + q * 32 + tr + 8 * i;
           if (mm < M) rvalid |= 1u << i;
           const uint32_t mr = (mm < M) ? (uint32_t)mm : 0u;
-          o_c[i] = mr * (uint32_t)p.epi.ldc;
+          o_c[i] = (EPK == TC_EPK_PARTIAL) ? ((uint32_t)z * (uint32_t)M + mr) * (uint32_t)p.N : mr * (uint32_t)p.epi.ldc;
           o_aux[i] = mr * (uint32_t)p.epi.ldaux;
           o_ao[i] = mr * (uint32_t)p.epi.ldaux_out;
           o_rb[i] = (uint32_t)rmap[i] * (uint32_t)p.epi.ldrowbias;
@@ -636,7 +639,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
         for (int i = 0; i < 4; ++i) { et.o_c[i] = o_c[i]; et.o_aux[i] = o_aux[i]; et.o_ao[i] = o_ao[i]; et.o_rb[i] = o_rb[i]; }
         et.rvalid = rvalid; et.row0 = m0 + q * 32 + tr;
-        epi_tile_fast<(EPK >= 0 ? EPK : 0)>(p, et, lane_addr, kb1 > kb0, c_begin, c_end, n0, smem_u32(my_tile), lane, M, drop_seed);
+        epi_tile_fast<(EPK >= 0 ? EPK : 0)>(p, et, lane_addr, kb1 > kb0, c_begin, c_end, n0, smem_u32(my_tile), lane, M, drop_seed,
+                                            EPK == TC_EPK_PARTIAL ? p.partial : p.epi.C);
       } else
       for (int c0 = c_begin; c0 < c_end; c0 += 16) {
         float v[16];
@@ -1180,6 +1184,7 @@ static const void* tc_kernel_ptr2(int epk) {
     case NNR_EPI_BIAS_RELU_RES: return (const void*)gemm_tc_kernel<BF16, PAIR, BF16 ? NNR_EPI_BIAS_RELU_RES : -1>;
     case NNR_EPI_GATE: return (const void*)gemm_tc_kernel<BF16, PAIR, BF16 ? NNR_EPI_GATE : -1>;
     case NNR_EPI_ADD_AUX: return (const void*)gemm_tc_kernel<BF16, PAIR, BF16 ? NNR_EPI_ADD_AUX : -1>;
+    case TC_EPK_PARTIAL: return (const void*)gemm_tc_kernel<BF16, PAIR, BF16 ? TC_EPK_PARTIAL : -1>;
     default: return (const void*)gemm_tc_kernel<BF16, PAIR, -1>;
   }
 }
@@ -1265,7 +1270,11 @@ static int run_tc(const nnr_gemm_args* a, cudaStream_t st) {
   dev &= 15;
   // the epilogue kind is a template parameter of the kernel on the fast path (bf16 operand planes only; the fp32-plane
   // kernels keep the run-time-switched epilogue)
-  const int epk = (BF16 && p.epi_fast && !pl.split_k) ? a->epilogue : -1;
+  int epk = (BF16 && p.epi_fast && !pl.split_k) ? a->epilogue : -1;
+  // split-K partials: plain 16-byte stores into the [split][M][N] slices (offsets in 32 bits)
+  if (BF16 && pl.split_k && fast_epilogue_enabled() && a->N % 4 == 0 && nnr_aligned16(p.partial) &&
+      (double)pl.max_splits * (double)a->M * (double)a->N < 4294967296.0)
+    epk = TC_EPK_PARTIAL;
   const void* kernel = tc_kernel_ptr<BF16>(pl.pair != 0, epk);
   if (!attr_set[dev][BF16 ? 1 : 0][pl.pair][epk + 1]) {
     NNR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
