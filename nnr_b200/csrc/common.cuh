@@ -90,24 +90,23 @@ __device__ __forceinline__ uint64_t nnr_resolve_seed(uint64_t s) {
   return s;
 }
 // keep-scale: 0 if dropped, 1/(1-p) if kept.  p == 0 -> always 1.
-__device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, float p, float inv_keep) {
-  if (p <= 0.0f) return 1.0f;
-  uint32_t r = mix32(seed * 0x9E3779B97F4A7C15ULL + idx);
-  float u = (float)(r >> 8) * (1.0f / 16777216.0f);
-  return u < p ? 0.0f : inv_keep;
-}
-// Four keep-scales from ONE 64-bit hash (16 uniform bits per element): used where the mask of a whole row of a
-// large tensor is regenerated (word-embedding gather / scatter: 300 elements per token), where the per-element
-// hash above is the bulk of the instruction count.  Element i of the tensor uses field (i & 3) of hash(i >> 2).
+// ONE 64-bit hash serves four consecutive elements (16 uniform bits each): element i of a tensor uses field (i & 3) of
+// hash(i >> 2).  Every mask in the library follows this rule, so a kernel that walks aligned quads (the embedding gather /
+// scatter, the GEMM's relu-residual epilogue and its backward pre-pass: there the per-element hash was the bulk of the
+// instruction count) computes one hash per float4 with dropout_scale4 and still agrees element for element with a kernel
+// that asks for single elements (dropout_scale).
 __device__ __forceinline__ void dropout_scale4(uint64_t seed, uint64_t idx4, float p, float inv_keep, float (&s)[4]) {
   const uint64_t r = mix64(seed * 0x9E3779B97F4A7C15ULL + idx4);
   const uint32_t thr = (uint32_t)(p * 65536.0f);
 #pragma unroll
   for (int i = 0; i < 4; ++i) s[i] = ((uint32_t)(r >> (16 * i)) & 0xffffu) < thr ? 0.0f : inv_keep;
 }
-__device__ __forceinline__ float dropout_scale_e4(uint64_t seed, uint64_t idx, float p, float inv_keep) {
+__device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, float p, float inv_keep) {
   if (p <= 0.0f) return 1.0f;
   const uint64_t r = mix64(seed * 0x9E3779B97F4A7C15ULL + (idx >> 2));
   return ((uint32_t)(r >> (16 * (idx & 3))) & 0xffffu) < (uint32_t)(p * 65536.0f) ? 0.0f : inv_keep;
+}
+__device__ __forceinline__ float dropout_scale_e4(uint64_t seed, uint64_t idx, float p, float inv_keep) {
+  return dropout_scale(seed, idx, p, inv_keep);
 }
 #endif

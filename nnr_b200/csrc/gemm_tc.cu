@@ -383,11 +383,11 @@ __device__ __forceinline__ void epi_tile_fast(const TcParams& p, const EpiTile& 
           if (p.epi.aux_out) *reinterpret_cast<float4*>(p.epi.aux_out + t.o_ao[i] + n) = v;
           if (need_ax) { v.x += ax[i].x; v.y += ax[i].y; v.z += ax[i].z; v.w += ax[i].w; }
           if (drop) {
+            // N % 4 == 0 and n % 4 == 0 on this path: the four elements are one quad of the mask, one hash
             const uint64_t e0 = (uint64_t)(t.row0 + 8 * i) * (uint64_t)p.epi.N + n;
-            v.x *= dropout_scale(drop_seed, e0, p.epi.p_drop, p.epi.inv_keep);
-            v.y *= dropout_scale(drop_seed, e0 + 1, p.epi.p_drop, p.epi.inv_keep);
-            v.z *= dropout_scale(drop_seed, e0 + 2, p.epi.p_drop, p.epi.inv_keep);
-            v.w *= dropout_scale(drop_seed, e0 + 3, p.epi.p_drop, p.epi.inv_keep);
+            float ks[4];
+            dropout_scale4(drop_seed, e0 >> 2, p.epi.p_drop, p.epi.inv_keep, ks);
+            v.x *= ks[0]; v.y *= ks[1]; v.z *= ks[2]; v.w *= ks[3];
           }
         } else if (EP == NNR_EPI_GATE) {
           v.x = sigmoid_fast(v.x + rb[i].x); v.y = sigmoid_fast(v.y + rb[i].y);
@@ -901,10 +901,19 @@ __global__ void __launch_bounds__(256) tc_split_colsum_kernel(const float* __res
             if (PRE) {
               float* xv = reinterpret_cast<float*>(&x[u][j]);
               const size_t o = (size_t)r * ld + cq;
+              float ks[4] = {1.f, 1.f, 1.f, 1.f};
+              if (pre.p > 0.f) {
+                const uint64_t e0 = (uint64_t)r * (uint64_t)C + cq;
+                if ((e0 & 3) == 0) dropout_scale4(pre.seed, e0 >> 2, pre.p, pre.inv_keep, ks);      // one hash for the quad
+                else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) ks[e] = dropout_scale(pre.seed, e0 + e, pre.p, pre.inv_keep);
+                }
+              }
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 if (cq + e < C) {
-                  if (pre.p > 0.f) xv[e] *= dropout_scale(pre.seed, (uint64_t)r * (uint64_t)C + cq + e, pre.p, pre.inv_keep);
+                  if (pre.p > 0.f) xv[e] *= ks[e];
                   if (pre.dropped) pre.dropped[o + e] = xv[e];
                   xv[e] *= (__ldg(pre.relu_out + o + e) > 0.f) ? 1.f : 0.f;
                 }

@@ -1,8 +1,8 @@
 cd /root/repo; mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_ops_gpu.py -x -q -m gpu -k "embed" 2>&1 | tail -3
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
 b() { env "$@" timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras --no-profile 2>gpurun_out/_err.txt | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$*', d['value'], d['ms_per_step'], d['e2e']['value'])" || tail -5 gpurun_out/_err.txt; }
 b NNR_X=1
-python scripts/step_timeline.py gpurun_out/step_timeline_new3.csv 2>&1 | tail -1
-grep -n "eb_chunk\|eb_fix" gpurun_out/step_timeline_new3.csv | cut -c1-50
+b NNR_TC_STAGE_PENALTY=1.15
+b NNR_TC_STAGE_PENALTY=1.0
