@@ -81,7 +81,9 @@ def _worker(rank, world, port, q):
             loss.backward()
             engine.grads_ready = None
             if overlap:
-                assert ts._reduced == {'sue', 'cne'}, ts._reduced
+                # the three stages of the flat buffer, each announced when its gradients are final: the user encoder, the news
+                # encoder's weights, and the word table (announced from the lane that runs the embedding scatters)
+                assert ts._reduced == {'sue', 'cne', 'table'}, ts._reduced
             ts.reduce_gradients()
             torch.cuda.synchronize()
             assert abs(loss.item() - shard_losses[rank]) < 1e-5
