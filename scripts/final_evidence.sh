@@ -1,7 +1,8 @@
 #!/bin/bash
 # Round-end evidence of the final build on one B200: the default bench line, the bf16 line, the ncu launch list of host-launched
 # steps, per-launch counters of every gemm_tc_kernel launch, one `--set full` capture of the selective-gate GEMM.
-# Outputs under gpurun_out/final/ (summarised into profiles/ by hand).
+# Outputs under gpurun_out/final/ (summarised into profiles/ by hand).  The multi-metric pass over every gemm_tc_kernel launch of the
+# run (659 launches x 5 metrics) takes ~10 minutes of box time; `-c 134` after the warm-up launches is enough for one step.
 cd "$(dirname "$0")/.."
 O=gpurun_out/final; mkdir -p $O
 timeout 900 python bench.py --gemm-detail > $O/bench_default.json 2> $O/bench_default_detail.txt; tail -c 600 $O/bench_default.json
